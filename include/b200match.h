@@ -1,0 +1,230 @@
+/* b200match.h -- C ABI of libb200match.so (B200 / sm_100a exhaustive matcher + two-view verifier).
+ *
+ * This is the drop-in boundary for the hot path of pycolmap.match_exhaustive /
+ * match_sequential / verify_matches / estimate_two_view_geometry.  Every entry point
+ * cites the reference interface it replaces.  Citation tags:
+ *   R:<path>:<lines>  file under /root/reference (colmap/pycolmap @ b6627db)
+ *   U:<path>          upstream COLMAP 3.9.1 (the un-vendored dependency the reference
+ *                     forwards into, R:CMakeLists.txt:17, R:pyproject.toml:36)
+ *
+ * Rules of the ABI: plain C structs, `struct_size` first (forward compatibility), plain
+ * pointers + sizes, no exceptions, no STL, no torch / Python types.  All functions return
+ * 0 on success or a negative B2M_E* code; the message is in b2m_last_error().  The caller
+ * owns every input buffer (the library copies what it keeps); the library owns a
+ * b2m_results until b2m_results_free().  One in-flight call per context.
+ *
+ * There is NO CPU fallback: b2m_create() fails with B2M_ENODEV when no sm_100 device is
+ * visible.
+ */
+#ifndef B200MATCH_H_
+#define B200MATCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2M_ABI_VERSION 1
+
+/* error codes */
+#define B2M_OK 0
+#define B2M_EINVAL (-1)   /* bad argument (reference: THROW_CHECK -> ValueError, R:log_exceptions.h:114-147) */
+#define B2M_ENODEV (-2)   /* no CUDA device / not sm_100 (reference: VerifyGPUParams, R:utils.h:22-31) */
+#define B2M_ECUDA (-3)    /* CUDA runtime / driver error */
+#define B2M_ENOMEM (-4)
+#define B2M_ESTOPPED (-5) /* b2m_request_stop() honoured (reference: PyInterrupt, R:helpers.h:306-347) */
+#define B2M_ESTATE (-6)   /* call order violated (e.g. match before set_images) */
+
+typedef struct b2m_ctx b2m_ctx;
+typedef struct b2m_results b2m_results;
+
+/* ---- context ----------------------------------------------------------------------- */
+
+typedef struct b2m_device_cfg {
+  uint32_t struct_size;
+  int32_t device;        /* CUDA ordinal; replaces SiftMatchingOptions.gpu_index (R:pipeline/match_features.h:76-81) */
+  uint64_t seed;         /* RANSAC seed; replaces SetPRNGSeed(0) (R:estimators/essential_matrix.h:25) */
+  int32_t pair_batch;    /* image pairs per kernel batch, 0 = default */
+  int32_t reserved;
+} b2m_device_cfg;
+
+int b2m_abi_version(void);
+int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out);
+void b2m_destroy(b2m_ctx* ctx);
+/* Message of the last failing call on this context (ctx may be NULL for create failures). */
+const char* b2m_last_error(const b2m_ctx* ctx);
+/* Async-signal-safe stop flag, checked between batches (R:helpers.h:335-347 PyWait / Thread::Stop). */
+int b2m_request_stop(b2m_ctx* ctx);
+
+/* ---- options ------------------------------------------------------------------------ */
+
+/* SiftMatchingOptions (R:pipeline/match_features.h:71-100; defaults U:feature/sift.h). */
+typedef struct b2m_sift_opts {
+  uint32_t struct_size;
+  float max_ratio;        /* 0.8 */
+  float max_distance;     /* 0.7 */
+  int32_t cross_check;    /* 1 */
+  int32_t max_num_matches;/* 32768: upper bound on descriptors per image taken into account */
+  int32_t guided_matching;/* 0 */
+} b2m_sift_opts;
+
+/* RANSACOptions (R:optim/bindings.h:7-27; U:optim/ransac.h). */
+typedef struct b2m_ransac_opts {
+  uint32_t struct_size;
+  int32_t min_num_trials;           /* 100  */
+  int32_t max_num_trials;           /* 10000 */
+  int32_t reserved;
+  double max_error;                 /* 4.0  */
+  double min_inlier_ratio;          /* 0.25 */
+  double confidence;                /* 0.999 */
+  double dyn_num_trials_multiplier; /* 3.0  */
+} b2m_ransac_opts;
+
+/* TwoViewGeometryOptions (R:estimators/two_view_geometry.h:41-65; U:estimators/two_view_geometry.h). */
+typedef struct b2m_tvg_opts {
+  uint32_t struct_size;
+  int32_t min_num_inliers;            /* 15 */
+  double min_E_F_inlier_ratio;        /* 0.95 */
+  double max_H_inlier_ratio;          /* 0.8 */
+  double watermark_min_inlier_ratio;  /* 0.7 */
+  double watermark_border_size;       /* 0.1 */
+  int32_t detect_watermark;           /* 1 */
+  int32_t multiple_ignore_watermark;  /* 1 */
+  int32_t force_H_use;                /* 0 */
+  int32_t compute_relative_pose;      /* 0 */
+  int32_t multiple_models;            /* 0 */
+  int32_t reserved;
+  b2m_ransac_opts ransac;
+} b2m_tvg_opts;
+
+void b2m_sift_opts_default(b2m_sift_opts* o);
+void b2m_ransac_opts_default(b2m_ransac_opts* o);
+void b2m_tvg_opts_default(b2m_tvg_opts* o);
+
+/* TwoViewGeometryConfiguration (R:estimators/two_view_geometry.h:67-80). */
+enum b2m_tvg_config {
+  B2M_UNDEFINED = 0,
+  B2M_DEGENERATE = 1,
+  B2M_CALIBRATED = 2,
+  B2M_UNCALIBRATED = 3,
+  B2M_PLANAR = 4,
+  B2M_PANORAMIC = 5,
+  B2M_PLANAR_OR_PANORAMIC = 6,
+  B2M_WATERMARK = 7,
+  B2M_MULTIPLE = 8
+};
+
+/* Camera (subset of R:scene/camera.h:20-213 the verifier touches: SIMPLE_PINHOLE / PINHOLE,
+ * CamFromImg, CamFromImgThreshold, has_prior_focal_length). */
+typedef struct b2m_camera {
+  uint32_t struct_size;
+  int32_t model;                  /* 0 = SIMPLE_PINHOLE (f,cx,cy), 1 = PINHOLE (fx,fy,cx,cy) */
+  int32_t width, height;
+  int32_t has_prior_focal_length;
+  int32_t reserved;
+  double params[4];
+} b2m_camera;
+
+/* ---- single-pair entry points (the unit the reference's workers call) -------------- */
+
+/* Replaces FeatureMatcher::Match(descriptors1, descriptors2, &matches)
+ * (U:feature/sift.cc MatchSiftFeaturesCPUBruteForce semantics; called from
+ * U:controllers/feature_matching_utils.cc FeatureMatcherWorker::Run; reached from
+ * R:pipeline/match_features.h:45-48).
+ * desc1/desc2: HOST pointers, [n x 128] uint8 row-major.  out_matches: HOST buffer of
+ * capacity `cap` (idx1, idx2) uint32 pairs (PyFeatureMatches layout, R:estimators/two_view_geometry.h:19-38);
+ * *out_n receives the number of matches (sorted by idx1 ascending). */
+int b2m_match_pair(b2m_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2,
+                   const b2m_sift_opts* opts, uint32_t* out_matches, int64_t cap, int64_t* out_n);
+
+/* ---- image-set path (exhaustive / sequential / pair-list pipelines) ---------------- */
+
+/* Upload the descriptor set once; it stays resident in HBM (replaces FeatureMatcherCache,
+ * U:controllers/feature_matching_utils.cc).  desc[i]: HOST [n_feat[i] x 128] uint8.
+ * kpts[i]: HOST [n_feat[i] x 2] float32 (x, y) or kpts == NULL for match-only.
+ * cams: one per image, or NULL for match-only. */
+int b2m_set_images(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const uint8_t* const* desc,
+                   const float* const* kpts, const b2m_camera* cams);
+
+/* Same, but the descriptors already live in device memory as one packed array
+ * [sum(n_feat) x 128] (row-major, image after image).  Used by the multi-GPU path after the
+ * NCCL all-gather and by benchmarks that keep inputs resident in HBM. */
+int b2m_set_images_device(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const void* dev_desc_packed,
+                          const void* dev_kpts_packed /* float2 per feature or NULL */, const b2m_camera* cams);
+
+/* Match (and verify when tvg != NULL) a list of image pairs given as indices into the image
+ * set.  Replaces FeatureMatcherController::Match (U:controllers/feature_matching_utils.cc)
+ * as driven by Exhaustive/Sequential/ImagePairs FeatureMatcher::Run
+ * (U:controllers/feature_matching.cc; R:pipeline/match_features.h:22-68).  Blocking. */
+int b2m_match_pairs(b2m_ctx* ctx, const int32_t* pairs /* [n_pairs x 2] */, int64_t n_pairs,
+                    const b2m_sift_opts* sift, const b2m_tvg_opts* tvg /* NULL = match only */,
+                    b2m_results** out);
+
+typedef struct b2m_pair_view {
+  uint32_t struct_size;
+  int32_t image1, image2;
+  int32_t config;                /* enum b2m_tvg_config; B2M_UNDEFINED when not verified */
+  int64_t n_matches;
+  const uint32_t* matches;       /* [n_matches x 2] raw matches (idx1, idx2), idx1 ascending */
+  int64_t n_inliers;
+  const uint32_t* inlier_matches;/* [n_inliers x 2] */
+  double E[9], F[9], H[9];       /* row-major, zero when not estimated */
+} b2m_pair_view;
+
+int64_t b2m_results_num_pairs(const b2m_results* r);
+int64_t b2m_results_total_matches(const b2m_results* r);
+int b2m_results_get(const b2m_results* r, int64_t pair, b2m_pair_view* out);
+void b2m_results_free(b2m_results* r);
+
+/* ---- estimators (callable without an image set) ------------------------------------ */
+
+/* Replaces EstimateTwoViewGeometry / EstimateCalibratedTwoViewGeometry
+ * (U:estimators/two_view_geometry.cc; R:estimators/two_view_geometry.h:95-151).
+ * points: HOST [n x 2] float64; matches: [m x 2] uint32 or NULL (identity, R:two_view_geometry.h:136-142).
+ * inlier_matches: HOST buffer capacity m x 2. */
+typedef struct b2m_tvg_result {
+  uint32_t struct_size;
+  int32_t config;
+  int64_t n_inliers;
+  double E[9], F[9], H[9];
+  int32_t nE, nF, nH;            /* inlier counts of the three LO-RANSAC runs (diagnostic) */
+  int32_t reserved;
+} b2m_tvg_result;
+
+int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const double* points1, int64_t n1,
+                                   const b2m_camera* cam2, const double* points2, int64_t n2,
+                                   const uint32_t* matches, int64_t m, const b2m_tvg_opts* opts,
+                                   b2m_tvg_result* out, uint32_t* inlier_matches);
+
+/* Single-model LO-RANSAC.  Replaces essential/fundamental/homography_matrix_estimation
+ * (R:estimators/essential_matrix.h:19-103, fundamental_matrix.h:17-50, homography_matrix.h:17-48).
+ * kind: 0 = E (points already normalised by the caller), 1 = F, 2 = H.
+ * out_model: 9 doubles row-major; inlier_mask: m bytes.  *success = 0 mirrors the `None` return. */
+int b2m_ransac_model(b2m_ctx* ctx, int32_t kind, const double* points1, const double* points2, int64_t m,
+                     const b2m_ransac_opts* opts, double* out_model, uint8_t* inlier_mask,
+                     int64_t* num_inliers, int32_t* success);
+
+/* Replaces ComputeSquaredSampsonError (U:estimators/utils.cc; R:estimators/two_view_geometry.h:161-175). */
+int b2m_squared_sampson_error(b2m_ctx* ctx, const double* points1, const double* points2, int64_t m,
+                              const double* E, double* out_residuals);
+
+/* ---- instrumentation ---------------------------------------------------------------- */
+
+typedef struct b2m_stats {
+  uint32_t struct_size;
+  uint32_t reserved;
+  uint64_t kernel_launches;   /* kernels of this library launched since create / last reset */
+  uint64_t match_tiles;       /* 128x256 MMA tiles issued */
+  double last_match_ms;       /* device time of the matching stage of the last b2m_match_pairs */
+  double last_verify_ms;      /* device time of the verification stage */
+  double last_total_ms;       /* device time of the whole call (events on the library stream) */
+} b2m_stats;
+int b2m_get_stats(b2m_ctx* ctx, b2m_stats* out);
+int b2m_reset_stats(b2m_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MATCH_H_ */

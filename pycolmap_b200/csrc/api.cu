@@ -1,0 +1,595 @@
+// api.cu -- C ABI of libb200match.so: context, resident image set, batched pair scheduler.
+// Host side of the hot path: replaces FeatureMatcherController / FeatureMatcherWorker /
+// FeatureMatcherCache (U:controllers/feature_matching_utils.cc) for the pipelines bound at
+// R:pipeline/match_features.h:22-68.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+#include "match_kernel.cuh"
+#include "verify.cuh"
+
+using namespace b2m;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(b2m_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_create_err = msg;
+  return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      char _b[512];                                                                             \
+      snprintf(_b, sizeof(_b), "[%s:%d] CUDA error: %s (%s)", __FILE__, __LINE__,              \
+               cudaGetErrorString(_e), #expr);                                                  \
+      return fail(ctx, _e == cudaErrorMemoryAllocation ? B2M_ENOMEM : B2M_ECUDA, _b);            \
+    }                                                                                           \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Lay out the image table and allocate the padded descriptor array (zero-filled).
+int layout_images(b2m_ctx* ctx, ImageSet& S, int n_images, const int32_t* n_feat, bool want_kpts) {
+  S.release();
+  S.n_images = n_images;
+  S.nfeat.assign(n_feat, n_feat + n_images);
+  S.row0.resize(n_images);
+  int64_t rows = 0;
+  S.max_feat = 0;
+  for (int i = 0; i < n_images; ++i) {
+    if (n_feat[i] < 0) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: n_feat[i] >= 0");
+    S.row0[i] = static_cast<int32_t>(rows);
+    rows += round_up(n_feat[i], kRowPad);
+    S.max_feat = std::max(S.max_feat, n_feat[i]);
+    if (rows > (int64_t(1) << 31) - kRowPad)
+      return fail(ctx, B2M_EINVAL, "[api.cu] image set exceeds 2^31 descriptor rows");
+  }
+  rows = std::max<int64_t>(rows, kRowPad);
+  S.max_feat_pad = std::max(round_up(S.max_feat, kRowPad), kRowPad);
+  S.total_rows = rows;
+  CU_TRY(ctx, cudaMalloc(&S.d_desc, static_cast<size_t>(rows) * 128));
+  CU_TRY(ctx, cudaMemsetAsync(S.d_desc, 0, static_cast<size_t>(rows) * 128, ctx->stream));
+  if (want_kpts) {
+    CU_TRY(ctx, cudaMalloc(&S.d_kpts, static_cast<size_t>(rows) * sizeof(float2)));
+    CU_TRY(ctx, cudaMemsetAsync(S.d_kpts, 0, static_cast<size_t>(rows) * sizeof(float2), ctx->stream));
+  }
+  CU_TRY(ctx, cudaMalloc(&S.d_row0, sizeof(int32_t) * std::max(1, n_images)));
+  CU_TRY(ctx, cudaMalloc(&S.d_nfeat, sizeof(int32_t) * std::max(1, n_images)));
+  if (n_images > 0) {
+    CU_TRY(ctx, cudaMemcpyAsync(S.d_row0, S.row0.data(), sizeof(int32_t) * n_images, cudaMemcpyHostToDevice,
+                                ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(S.d_nfeat, S.nfeat.data(), sizeof(int32_t) * n_images, cudaMemcpyHostToDevice,
+                                ctx->stream));
+  }
+  // One TMA tensor map over the whole set: dim0 = 128 descriptor bytes, dim1 = rows; box 128 x 128,
+  // SWIZZLE_128B so that the tile lands in the canonical K-major UMMA layout.
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(ctx, B2M_ECUDA, "[api.cu] cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {128, static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {128};
+  cuuint32_t box[2] = {128, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&S.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, S.d_desc, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[128];
+    snprintf(b, sizeof(b), "[api.cu] cuTensorMapEncodeTiled failed: CUresult %d", static_cast<int>(r));
+    return fail(ctx, B2M_ECUDA, b);
+  }
+  return B2M_OK;
+}
+
+int ensure_workspace(b2m_ctx* ctx, int batch, int32_t mstride) {
+  Workspace& W = ctx->ws;
+  if (W.batch >= batch && W.mstride >= mstride) return B2M_OK;
+  W.release();
+  batch = std::max(batch, W.batch);
+  mstride = std::max(mstride, W.mstride);
+  const size_t arena_matches = static_cast<size_t>(batch) * mstride;
+  CU_TRY(ctx, cudaMalloc(&W.d_mbuf, sizeof(int32_t) * 2 * arena_matches));
+  for (int s = 0; s < 2; ++s) {
+    CU_TRY(ctx, cudaMalloc(&W.d_arena[s], sizeof(uint2) * arena_matches));
+    CU_TRY(ctx, cudaMalloc(&W.d_cursor[s], sizeof(unsigned long long)));
+    CU_TRY(ctx, cudaMalloc(&W.d_pair_off[s], sizeof(int64_t) * batch));
+    CU_TRY(ctx, cudaMalloc(&W.d_pair_cnt[s], sizeof(int32_t) * batch));
+    CU_TRY(ctx, cudaMallocHost(&W.h_arena[s], sizeof(uint2) * arena_matches));
+    CU_TRY(ctx, cudaMallocHost(&W.h_cursor[s], sizeof(unsigned long long)));
+    CU_TRY(ctx, cudaMallocHost(&W.h_pair_off[s], sizeof(int64_t) * batch));
+    CU_TRY(ctx, cudaMallocHost(&W.h_pair_cnt[s], sizeof(int32_t) * batch));
+  }
+  W.batch = batch;
+  W.mstride = mstride;
+  return B2M_OK;
+}
+
+int check_sift(b2m_ctx* ctx, const b2m_sift_opts* o) {
+  if (!o) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: sift options != NULL");
+  if (!(o->max_ratio > 0.f)) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: max_ratio > 0");
+  if (!(o->max_distance > 0.f)) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: max_distance > 0");
+  return B2M_OK;
+}
+
+// Core scheduler: match (and optionally verify) `n_pairs` pairs of image set S in batches.
+int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_pairs, const b2m_sift_opts* sift,
+                     const b2m_tvg_opts* tvg, b2m_results** out) {
+  if (!out) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: out != NULL");
+  *out = nullptr;
+  if (int rc = check_sift(ctx, sift)) return rc;
+  if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: pairs");
+  if (!S.d_desc) return fail(ctx, B2M_ESTATE, "[api.cu] b2m_set_images must be called before matching");
+  for (int64_t k = 0; k < 2 * n_pairs; ++k)
+    if (pairs[k] < 0 || pairs[k] >= S.n_images)
+      return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: pair image index out of range");
+  if (tvg && (!S.d_kpts || S.cams.empty()))
+    return fail(ctx, B2M_ESTATE, "[api.cu] verification requested but the image set has no keypoints/cameras");
+  if (S.max_feat > sift->max_num_matches)
+    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: num descriptors <= SiftMatchingOptions.max_num_matches");
+
+  b2m_results* res = new (std::nothrow) b2m_results();
+  if (!res) return fail(ctx, B2M_ENOMEM, "[api.cu] out of host memory");
+  res->pairs.assign(pairs, pairs + 2 * n_pairs);
+  res->off.assign(n_pairs, 0);
+  res->cnt.assign(n_pairs, 0);
+  if (tvg) verify_results_init(res, n_pairs);
+  auto bail = [&](int rc) {
+    delete res;
+    return rc;
+  };
+
+  const int B = ctx->pair_batch;
+  if (int rc = ensure_workspace(ctx, B, S.max_feat_pad)) return bail(rc);
+  if (ctx->d_pairs_cap < n_pairs) {
+    if (ctx->d_pairs) cudaFree(ctx->d_pairs);
+    ctx->d_pairs = nullptr;
+    ctx->d_pairs_cap = 0;
+    cudaError_t e = cudaMalloc(&ctx->d_pairs, sizeof(int32_t) * 2 * std::max<int64_t>(n_pairs, 1));
+    if (e != cudaSuccess) return bail(fail(ctx, B2M_ENOMEM, "[api.cu] cudaMalloc(pairs) failed"));
+    ctx->d_pairs_cap = n_pairs;
+  }
+  Workspace& W = ctx->ws;
+  cudaStream_t st = ctx->stream;
+#define CU_TRY_R(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      char _b[512];                                                                         \
+      snprintf(_b, sizeof(_b), "[%s:%d] CUDA error: %s (%s)", __FILE__, __LINE__,          \
+               cudaGetErrorString(_e), #expr);                                              \
+      return bail(fail(ctx, B2M_ECUDA, _b));                                                \
+    }                                                                                       \
+  } while (0)
+
+  if (n_pairs > 0)
+    CU_TRY_R(cudaMemcpyAsync(ctx->d_pairs, pairs, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyHostToDevice, st));
+  CU_TRY_R(cudaEventRecord(ctx->ev_t0, st));
+
+  const int max_strips = S.max_feat_pad / 128;
+  const int n_dirs = sift->cross_check ? 2 : 1;
+  const int64_t n_batches = (n_pairs + B - 1) / B;
+  double verify_ms = 0.0;
+
+  // Drain one finished batch: counts -> host, then offsets + matches on the copy stream.
+  auto finish = [&](int64_t b) -> int {
+    const int s = static_cast<int>(b & 1);
+    const int64_t p0 = b * B;
+    const int nb = static_cast<int>(std::min<int64_t>(B, n_pairs - p0));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->ev_k[s]));
+    const unsigned long long total = *W.h_cursor[s];
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[s], 0));
+    CU_TRY(ctx, cudaMemcpyAsync(W.h_pair_off[s], W.d_pair_off[s], sizeof(int64_t) * nb, cudaMemcpyDeviceToHost,
+                                ctx->copy_stream));
+    CU_TRY(ctx, cudaMemcpyAsync(W.h_pair_cnt[s], W.d_pair_cnt[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost,
+                                ctx->copy_stream));
+    if (total > 0)
+      CU_TRY(ctx, cudaMemcpyAsync(W.h_arena[s], W.d_arena[s], sizeof(uint2) * total, cudaMemcpyDeviceToHost,
+                                  ctx->copy_stream));
+    if (tvg)
+      if (int rc = verify_batch_download(ctx, res, s, p0, nb)) return rc;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_data[s], ctx->copy_stream));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->ev_data[s]));
+    const int64_t base = static_cast<int64_t>(res->matches.size() / 2);
+    res->matches.resize(res->matches.size() + 2 * total);
+    if (total > 0) memcpy(res->matches.data() + 2 * base, W.h_arena[s], sizeof(uint2) * total);
+    for (int k = 0; k < nb; ++k) {
+      res->off[p0 + k] = base + W.h_pair_off[s][k];
+      res->cnt[p0 + k] = W.h_pair_cnt[s][k];
+    }
+    if (tvg)
+      if (int rc = verify_batch_collect(ctx, res, s, p0, nb)) return rc;
+    return B2M_OK;
+  };
+
+  for (int64_t b = 0; b < n_batches; ++b) {
+    if (ctx->stop) {
+      cudaStreamSynchronize(st);
+      cudaStreamSynchronize(ctx->copy_stream);
+      ctx->stop = 0;
+      return bail(fail(ctx, B2M_ESTOPPED, "[api.cu] stopped by b2m_request_stop"));
+    }
+    const int s = static_cast<int>(b & 1);
+    const int64_t p0 = b * B;
+    const int nb = static_cast<int>(std::min<int64_t>(B, n_pairs - p0));
+    if (b >= 2) CU_TRY_R(cudaStreamWaitEvent(st, ctx->ev_data[s], 0));
+    CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
+    MatchParams mp;
+    mp.pairs = ctx->d_pairs + 2 * p0;
+    mp.img_row0 = S.d_row0;
+    mp.img_nfeat = S.d_nfeat;
+    mp.mbuf = W.d_mbuf;
+    mp.mstride = W.mstride;
+    mp.acos_lut = ctx->d_lut;
+    mp.max_ratio = sift->max_ratio;
+    mp.max_distance = sift->max_distance;
+    CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.match_tiles += 0;
+    CompactParams cp;
+    cp.pairs = mp.pairs;
+    cp.img_nfeat = S.d_nfeat;
+    cp.mbuf = W.d_mbuf;
+    cp.mstride = W.mstride;
+    cp.cross_check = sift->cross_check ? 1 : 0;
+    cp.arena = W.d_arena[s];
+    cp.cursor = W.d_cursor[s];
+    cp.pair_off = W.d_pair_off[s];
+    cp.pair_cnt = W.d_pair_cnt[s];
+    CU_TRY_R(launch_crosscheck_compact(cp, nb, st));
+    ctx->stats.kernel_launches += 1;
+    if (tvg)
+      if (int rc = verify_batch_launch(ctx, S, tvg, sift, s, p0, nb)) return bail(rc);
+    CU_TRY_R(cudaMemcpyAsync(W.h_cursor[s], W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY_R(cudaEventRecord(ctx->ev_k[s], st));
+    if (b > 0)
+      if (int rc = finish(b - 1)) return bail(rc);
+  }
+  if (n_batches > 0)
+    if (int rc = finish(n_batches - 1)) return bail(rc);
+  CU_TRY_R(cudaEventRecord(ctx->ev_t1, st));
+  CU_TRY_R(cudaEventSynchronize(ctx->ev_t1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1);
+  ctx->stats.last_total_ms = ms;
+  ctx->stats.last_verify_ms = verify_ms;
+  ctx->stats.last_match_ms = ms - verify_ms;
+#undef CU_TRY_R
+  *out = res;
+  return B2M_OK;
+}
+
+}  // namespace
+
+namespace b2m {
+void ImageSet::release() {
+  if (d_desc) cudaFree(d_desc);
+  if (d_kpts) cudaFree(d_kpts);
+  if (d_row0) cudaFree(d_row0);
+  if (d_nfeat) cudaFree(d_nfeat);
+  d_desc = nullptr;
+  d_kpts = nullptr;
+  d_row0 = nullptr;
+  d_nfeat = nullptr;
+  n_images = 0;
+  nfeat.clear();
+  row0.clear();
+  cams.clear();
+  max_feat = max_feat_pad = 0;
+  total_rows = 0;
+}
+void Workspace::release() {
+  if (d_mbuf) cudaFree(d_mbuf);
+  d_mbuf = nullptr;
+  for (int s = 0; s < 2; ++s) {
+    if (d_arena[s]) cudaFree(d_arena[s]);
+    if (d_cursor[s]) cudaFree(d_cursor[s]);
+    if (d_pair_off[s]) cudaFree(d_pair_off[s]);
+    if (d_pair_cnt[s]) cudaFree(d_pair_cnt[s]);
+    if (h_arena[s]) cudaFreeHost(h_arena[s]);
+    if (h_cursor[s]) cudaFreeHost(h_cursor[s]);
+    if (h_pair_off[s]) cudaFreeHost(h_pair_off[s]);
+    if (h_pair_cnt[s]) cudaFreeHost(h_pair_cnt[s]);
+    d_arena[s] = nullptr;
+    d_cursor[s] = nullptr;
+    d_pair_off[s] = nullptr;
+    d_pair_cnt[s] = nullptr;
+    h_arena[s] = nullptr;
+    h_cursor[s] = nullptr;
+    h_pair_off[s] = nullptr;
+    h_pair_cnt[s] = nullptr;
+  }
+  batch = 0;
+  mstride = 0;
+}
+}  // namespace b2m
+
+extern "C" {
+
+int b2m_abi_version(void) { return B2M_ABI_VERSION; }
+
+void b2m_sift_opts_default(b2m_sift_opts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->struct_size = sizeof(*o);
+  o->max_ratio = 0.8f;
+  o->max_distance = 0.7f;
+  o->cross_check = 1;
+  o->max_num_matches = 32768;
+  o->guided_matching = 0;
+}
+void b2m_ransac_opts_default(b2m_ransac_opts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->struct_size = sizeof(*o);
+  o->min_num_trials = 100;
+  o->max_num_trials = 10000;
+  o->max_error = 4.0;
+  o->min_inlier_ratio = 0.25;
+  o->confidence = 0.999;
+  o->dyn_num_trials_multiplier = 3.0;
+}
+void b2m_tvg_opts_default(b2m_tvg_opts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->struct_size = sizeof(*o);
+  o->min_num_inliers = 15;
+  o->min_E_F_inlier_ratio = 0.95;
+  o->max_H_inlier_ratio = 0.8;
+  o->watermark_min_inlier_ratio = 0.7;
+  o->watermark_border_size = 0.1;
+  o->detect_watermark = 1;
+  o->multiple_ignore_watermark = 1;
+  o->force_H_use = 0;
+  o->compute_relative_pose = 0;
+  o->multiple_models = 0;
+  b2m_ransac_opts_default(&o->ransac);
+}
+
+int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
+  if (!out) return fail(nullptr, B2M_EINVAL, "[api.cu] Check Failed: out != NULL");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, B2M_ENODEV,
+                "[api.cu] no CUDA device visible: libb200match has no CPU fallback (B200 / sm_100 required)");
+  }
+  const int dev = cfg ? cfg->device : 0;
+  if (dev < 0 || dev >= ndev) return fail(nullptr, B2M_EINVAL, "[api.cu] Check Failed: device ordinal in range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(nullptr, B2M_ECUDA, "cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    char b[256];
+    snprintf(b, sizeof(b), "[api.cu] device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major,
+             prop.minor);
+    return fail(nullptr, B2M_ENODEV, b);
+  }
+  b2m_ctx* ctx = new (std::nothrow) b2m_ctx();
+  if (!ctx) return fail(nullptr, B2M_ENOMEM, "out of host memory");
+  ctx->device = dev;
+  ctx->seed = cfg ? cfg->seed : 0;
+  if (cfg && cfg->pair_batch > 0) ctx->pair_batch = std::min(cfg->pair_batch, 65535);
+  ctx->stats.struct_size = sizeof(b2m_stats);
+#define CU_TRY_C(expr)                                                            \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      std::string m = std::string("[api.cu] CUDA error in b2m_create: ") + cudaGetErrorString(_e); \
+      delete ctx;                                                                 \
+      return fail(nullptr, B2M_ECUDA, m);                                         \
+    }                                                                             \
+  } while (0)
+  CU_TRY_C(cudaSetDevice(dev));
+  CU_TRY_C(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU_TRY_C(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; ++s) {
+    CU_TRY_C(cudaEventCreateWithFlags(&ctx->ev_k[s], cudaEventDisableTiming));
+    CU_TRY_C(cudaEventCreateWithFlags(&ctx->ev_data[s], cudaEventDisableTiming));
+  }
+  CU_TRY_C(cudaEventCreate(&ctx->ev_t0));
+  CU_TRY_C(cudaEventCreate(&ctx->ev_t1));
+  // acos LUT: the float32 accept test of FindBestMatchesOneWayBruteForce depends only on the
+  // integer dot product d in [0, 2^18] (clamped); tabulating it with the HOST libm makes the
+  // device decisions identical to a CPU run on the same machine.
+  {
+    std::vector<float> lut(262145);
+    const float kDistNorm = 1.0f / (512.0f * 512.0f);
+    for (int d = 0; d <= 262144; ++d) lut[d] = acosf(std::min(kDistNorm * static_cast<float>(d), 1.0f));
+    CU_TRY_C(cudaMalloc(&ctx->d_lut, sizeof(float) * lut.size()));
+    CU_TRY_C(cudaMemcpy(ctx->d_lut, lut.data(), sizeof(float) * lut.size(), cudaMemcpyHostToDevice));
+  }
+#undef CU_TRY_C
+  *out = ctx;
+  return B2M_OK;
+}
+
+void b2m_destroy(b2m_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->images.release();
+  ctx->ws.release();
+  verify_release(ctx);
+  if (ctx->d_pairs) cudaFree(ctx->d_pairs);
+  if (ctx->d_lut) cudaFree(ctx->d_lut);
+  for (int s = 0; s < 2; ++s) {
+    if (ctx->ev_k[s]) cudaEventDestroy(ctx->ev_k[s]);
+    if (ctx->ev_data[s]) cudaEventDestroy(ctx->ev_data[s]);
+  }
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+const char* b2m_last_error(const b2m_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int b2m_request_stop(b2m_ctx* ctx) {
+  if (!ctx) return B2M_EINVAL;
+  ctx->stop = 1;
+  return B2M_OK;
+}
+
+int b2m_set_images(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const uint8_t* const* desc,
+                   const float* const* kpts, const b2m_camera* cams) {
+  if (!ctx) return B2M_EINVAL;
+  if (n_images < 0 || (n_images > 0 && (!n_feat || !desc)))
+    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: n_images >= 0 && n_feat && desc");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ImageSet& S = ctx->images;
+  if (int rc = layout_images(ctx, S, n_images, n_feat, kpts != nullptr)) return rc;
+  for (int i = 0; i < n_images; ++i) {
+    if (n_feat[i] == 0) continue;
+    if (!desc[i]) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: desc[i] != NULL");
+    CU_TRY(ctx, cudaMemcpyAsync(S.d_desc + static_cast<size_t>(S.row0[i]) * 128, desc[i],
+                                static_cast<size_t>(n_feat[i]) * 128, cudaMemcpyHostToDevice, ctx->stream));
+    if (kpts) {
+      if (!kpts[i]) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: kpts[i] != NULL");
+      CU_TRY(ctx, cudaMemcpyAsync(S.d_kpts + S.row0[i], kpts[i], static_cast<size_t>(n_feat[i]) * sizeof(float2),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  if (cams) S.cams.assign(cams, cams + n_images);
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+
+int b2m_set_images_device(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const void* dev_desc_packed,
+                          const void* dev_kpts_packed, const b2m_camera* cams) {
+  if (!ctx) return B2M_EINVAL;
+  if (n_images < 0 || (n_images > 0 && (!n_feat || !dev_desc_packed)))
+    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: n_images >= 0 && n_feat && dev_desc_packed");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ImageSet& S = ctx->images;
+  if (int rc = layout_images(ctx, S, n_images, n_feat, dev_kpts_packed != nullptr)) return rc;
+  int64_t src_row = 0;
+  const uint8_t* src = static_cast<const uint8_t*>(dev_desc_packed);
+  const float2* ksrc = static_cast<const float2*>(dev_kpts_packed);
+  // contiguous runs of images whose counts are multiples of kRowPad are copied in one go
+  int i = 0;
+  while (i < n_images) {
+    int j = i;
+    int64_t run = 0;
+    while (j < n_images && n_feat[j] % kRowPad == 0) run += n_feat[j++];
+    if (j == i) {  // ragged image
+      run = n_feat[i];
+      j = i + 1;
+    }
+    if (run > 0) {
+      CU_TRY(ctx, cudaMemcpyAsync(S.d_desc + static_cast<size_t>(S.row0[i]) * 128, src + src_row * 128,
+                                  static_cast<size_t>(run) * 128, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (ksrc)
+        CU_TRY(ctx, cudaMemcpyAsync(S.d_kpts + S.row0[i], ksrc + src_row, static_cast<size_t>(run) * sizeof(float2),
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    src_row += run;
+    i = j;
+  }
+  if (cams) S.cams.assign(cams, cams + n_images);
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+
+int b2m_match_pairs(b2m_ctx* ctx, const int32_t* pairs, int64_t n_pairs, const b2m_sift_opts* sift,
+                    const b2m_tvg_opts* tvg, b2m_results** out) {
+  if (!ctx) return B2M_EINVAL;
+  cudaSetDevice(ctx->device);
+  return match_pairs_impl(ctx, ctx->images, pairs, n_pairs, sift, tvg, out);
+}
+
+int b2m_match_pair(b2m_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2,
+                   const b2m_sift_opts* opts, uint32_t* out_matches, int64_t cap, int64_t* out_n) {
+  if (!ctx) return B2M_EINVAL;
+  if (!out_n) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: out_n != NULL");
+  *out_n = 0;
+  if (n1 < 0 || n2 < 0) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: n1 >= 0 && n2 >= 0");
+  if (int rc = check_sift(ctx, opts)) return rc;
+  if (n1 == 0 || n2 == 0) return B2M_OK;
+  if (!desc1 || !desc2) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: descriptors != NULL");
+  cudaSetDevice(ctx->device);
+  // a private two-image set; the resident set of the context is left untouched
+  ImageSet tmp;
+  const int32_t nf[2] = {n1, n2};
+  std::swap(tmp, ctx->images);
+  const uint8_t* d[2] = {desc1, desc2};
+  int rc = b2m_set_images(ctx, 2, nf, d, nullptr, nullptr);
+  b2m_results* res = nullptr;
+  const int32_t pr[2] = {0, 1};
+  if (rc == B2M_OK) rc = match_pairs_impl(ctx, ctx->images, pr, 1, opts, nullptr, &res);
+  ctx->images.release();
+  std::swap(tmp, ctx->images);
+  if (rc != B2M_OK) return rc;
+  const int64_t n = res->cnt[0];
+  if (n > cap || (n > 0 && !out_matches)) {
+    delete res;
+    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: out_matches capacity");
+  }
+  if (n > 0) memcpy(out_matches, res->matches.data() + 2 * res->off[0], sizeof(uint32_t) * 2 * n);
+  *out_n = n;
+  delete res;
+  return B2M_OK;
+}
+
+int64_t b2m_results_num_pairs(const b2m_results* r) { return r ? static_cast<int64_t>(r->cnt.size()) : 0; }
+int64_t b2m_results_total_matches(const b2m_results* r) { return r ? static_cast<int64_t>(r->matches.size() / 2) : 0; }
+
+int b2m_results_get(const b2m_results* r, int64_t pair, b2m_pair_view* out) {
+  if (!r || !out || pair < 0 || pair >= static_cast<int64_t>(r->cnt.size())) return B2M_EINVAL;
+  memset(out, 0, sizeof(*out));
+  out->struct_size = sizeof(*out);
+  out->image1 = r->pairs[2 * pair];
+  out->image2 = r->pairs[2 * pair + 1];
+  out->n_matches = r->cnt[pair];
+  out->matches = r->cnt[pair] ? r->matches.data() + 2 * r->off[pair] : nullptr;
+  out->config = B2M_UNDEFINED;
+  if (r->verified) {
+    out->config = r->config[pair];
+    out->n_inliers = r->in_cnt[pair];
+    out->inlier_matches = r->in_cnt[pair] ? r->inliers.data() + 2 * r->in_off[pair] : nullptr;
+    memcpy(out->E, r->models.data() + 27 * pair, sizeof(double) * 9);
+    memcpy(out->F, r->models.data() + 27 * pair + 9, sizeof(double) * 9);
+    memcpy(out->H, r->models.data() + 27 * pair + 18, sizeof(double) * 9);
+  }
+  return B2M_OK;
+}
+
+void b2m_results_free(b2m_results* r) { delete r; }
+
+int b2m_get_stats(b2m_ctx* ctx, b2m_stats* out) {
+  if (!ctx || !out) return B2M_EINVAL;
+  *out = ctx->stats;
+  out->struct_size = sizeof(b2m_stats);
+  return B2M_OK;
+}
+int b2m_reset_stats(b2m_ctx* ctx) {
+  if (!ctx) return B2M_EINVAL;
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.struct_size = sizeof(b2m_stats);
+  return B2M_OK;
+}
+
+}  // extern "C"

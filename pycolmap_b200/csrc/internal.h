@@ -1,0 +1,80 @@
+// internal.h -- context / image-set / results objects behind the C ABI (include/b200match.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/b200match.h"
+
+namespace b2m {
+
+// The descriptor set resident in HBM (replaces upstream's host-side FeatureMatcherCache,
+// U:controllers/feature_matching_utils.cc).  Layout: one [total_rows x 128] uint8 array, image i
+// occupying rows [row0[i], row0[i] + nfeat[i]) followed by zero rows up to a multiple of kRowPad.
+struct ImageSet {
+  int n_images = 0;
+  std::vector<int32_t> nfeat, row0;
+  int32_t max_feat = 0;      // max valid rows
+  int32_t max_feat_pad = 0;  // max padded rows
+  int64_t total_rows = 0;    // padded rows over all images
+  uint8_t* d_desc = nullptr;
+  float2* d_kpts = nullptr;  // indexed by padded row, or nullptr
+  int32_t* d_row0 = nullptr;
+  int32_t* d_nfeat = nullptr;
+  std::vector<b2m_camera> cams;
+  CUtensorMap tmap;
+  void release();
+};
+
+struct Workspace {
+  int batch = 0;
+  int32_t mstride = 0;
+  int32_t* d_mbuf = nullptr;
+  uint2* d_arena[2] = {nullptr, nullptr};
+  unsigned long long* d_cursor[2] = {nullptr, nullptr};
+  int64_t* d_pair_off[2] = {nullptr, nullptr};
+  int32_t* d_pair_cnt[2] = {nullptr, nullptr};
+  uint2* h_arena[2] = {nullptr, nullptr};
+  unsigned long long* h_cursor[2] = {nullptr, nullptr};
+  int64_t* h_pair_off[2] = {nullptr, nullptr};
+  int32_t* h_pair_cnt[2] = {nullptr, nullptr};
+  void release();
+};
+
+}  // namespace b2m
+
+struct b2m_ctx {
+  int device = 0;
+  uint64_t seed = 0;
+  int pair_batch = 1024;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_k[2] = {nullptr, nullptr};
+  cudaEvent_t ev_data[2] = {nullptr, nullptr};
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  float* d_lut = nullptr;
+  b2m::ImageSet images;
+  b2m::Workspace ws;
+  int32_t* d_pairs = nullptr;
+  int64_t d_pairs_cap = 0;
+  std::string err;
+  volatile int stop = 0;
+  b2m_stats stats{};
+};
+
+struct b2m_results {
+  std::vector<int32_t> pairs;    // [n x 2]
+  std::vector<int64_t> off;      // per pair offset (in matches) into `matches`
+  std::vector<int32_t> cnt;      // per pair match count
+  std::vector<uint32_t> matches; // [total x 2]
+  // verification outputs (filled when tvg options were given)
+  bool verified = false;
+  std::vector<int32_t> config;
+  std::vector<int64_t> in_off;
+  std::vector<int32_t> in_cnt;
+  std::vector<uint32_t> inliers;
+  std::vector<double> models;    // per pair 27 doubles: E, F, H
+};

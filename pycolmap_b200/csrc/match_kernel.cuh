@@ -1,0 +1,40 @@
+// match_kernel.cuh -- launch interface of the K1 matching kernels (internal to libb200match.so).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace b2m {
+
+struct MatchParams {
+  const int32_t* pairs;      // device [n_pairs x 2] image indices of this batch
+  const int32_t* img_row0;   // device [n_images] first (padded) row of each image in the descriptor array
+  const int32_t* img_nfeat;  // device [n_images] valid rows of each image
+  int32_t* mbuf;             // device [n_pairs][2][mstride]: m12 / m21 (column index or -1)
+  int32_t mstride;           // >= max padded feature count
+  const float* acos_lut;     // device [262145] acosf(min(d * 2^-18, 1)) built with the host libm
+  float max_ratio;
+  float max_distance;
+};
+
+struct CompactParams {
+  const int32_t* pairs;
+  const int32_t* img_nfeat;
+  const int32_t* mbuf;
+  int32_t mstride;
+  int32_t cross_check;
+  uint2* arena;                 // device match arena of this batch
+  unsigned long long* cursor;   // device arena cursor (matches)
+  int64_t* pair_off;            // device [n_pairs] offset (in matches) of each pair inside the arena
+  int32_t* pair_cnt;            // device [n_pairs]
+};
+
+// Rows per A strip / columns per B tile: images are padded (with zero descriptors, which can
+// never win a strict `>` comparison against the initial best = 0) to a multiple of this.
+constexpr int kRowPad = 256;
+
+cudaError_t launch_k1_match(const CUtensorMap& tmap, const MatchParams& p, int n_pairs, int max_strips, int n_dirs,
+                            cudaStream_t stream);
+cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream);
+
+}  // namespace b2m

@@ -1,0 +1,15 @@
+// verify.cuh -- two-view geometric verification stage (K2/K3) hooks used by the pair scheduler.
+#pragma once
+#include "internal.h"
+
+namespace b2m {
+void verify_results_init(b2m_results* res, int64_t n_pairs);
+// Enqueue verification of batch slot `s` (pairs [p0, p0+nb)) on ctx->stream, after compaction.
+int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, const b2m_sift_opts* sift, int s,
+                        int64_t p0, int nb);
+// Enqueue the D2H copies of the verification outputs of slot `s` on ctx->copy_stream.
+int verify_batch_download(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int nb);
+// After the copies completed: move staging -> results.
+int verify_batch_collect(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int nb);
+void verify_release(b2m_ctx* ctx);
+}  // namespace b2m

@@ -220,6 +220,8 @@ typedef struct b2m_stats {
   double last_match_ms;       /* device time of the matching stage of the last b2m_match_pairs */
   double last_verify_ms;      /* device time of the verification stage */
   double last_total_ms;       /* device time of the whole call (events on the library stream) */
+  double last_k1_ms;          /* sum of K1 (GEMM + fused top-2) kernel durations of the last call */
+  uint64_t last_k1_launches;  /* K1 launches of the last call */
 } b2m_stats;
 int b2m_get_stats(b2m_ctx* ctx, b2m_stats* out);
 int b2m_reset_stats(b2m_ctx* ctx);

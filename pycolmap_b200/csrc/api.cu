@@ -187,6 +187,8 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
   if (n_pairs > 0)
     CU_TRY_R(cudaMemcpyAsync(ctx->d_pairs, pairs, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyHostToDevice, st));
   CU_TRY_R(cudaEventRecord(ctx->ev_t0, st));
+  ctx->stats.last_k1_ms = 0.0;
+  ctx->stats.last_k1_launches = 0;
 
   const int max_strips = S.max_feat_pad / 128;
   const int n_dirs = sift->cross_check ? 2 : 1;
@@ -200,6 +202,10 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     const int nb = static_cast<int>(std::min<int64_t>(B, n_pairs - p0));
     CU_TRY(ctx, cudaEventSynchronize(ctx->ev_k[s]));
     const unsigned long long total = *W.h_cursor[s];
+    {
+      float k1ms = 0.f;
+      if (cudaEventElapsedTime(&k1ms, ctx->ev_k1a[s], ctx->ev_k1b[s]) == cudaSuccess) ctx->stats.last_k1_ms += k1ms;
+    }
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[s], 0));
     CU_TRY(ctx, cudaMemcpyAsync(W.h_pair_off[s], W.d_pair_off[s], sizeof(int64_t) * nb, cudaMemcpyDeviceToHost,
                                 ctx->copy_stream));
@@ -245,8 +251,11 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     mp.acos_lut = ctx->d_lut;
     mp.max_ratio = sift->max_ratio;
     mp.max_distance = sift->max_distance;
+    CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
     CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
+    CU_TRY_R(cudaEventRecord(ctx->ev_k1b[s], st));
     ctx->stats.kernel_launches += 1;
+    ctx->stats.last_k1_launches += 1;
     ctx->stats.match_tiles += 0;
     CompactParams cp;
     cp.pairs = mp.pairs;
@@ -409,6 +418,10 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
     CU_TRY_C(cudaEventCreateWithFlags(&ctx->ev_k[s], cudaEventDisableTiming));
     CU_TRY_C(cudaEventCreateWithFlags(&ctx->ev_data[s], cudaEventDisableTiming));
   }
+  for (int s = 0; s < 2; ++s) {
+    CU_TRY_C(cudaEventCreate(&ctx->ev_k1a[s]));
+    CU_TRY_C(cudaEventCreate(&ctx->ev_k1b[s]));
+  }
   CU_TRY_C(cudaEventCreate(&ctx->ev_t0));
   CU_TRY_C(cudaEventCreate(&ctx->ev_t1));
   // acos LUT: the float32 accept test of FindBestMatchesOneWayBruteForce depends only on the
@@ -438,6 +451,8 @@ void b2m_destroy(b2m_ctx* ctx) {
   for (int s = 0; s < 2; ++s) {
     if (ctx->ev_k[s]) cudaEventDestroy(ctx->ev_k[s]);
     if (ctx->ev_data[s]) cudaEventDestroy(ctx->ev_data[s]);
+    if (ctx->ev_k1a[s]) cudaEventDestroy(ctx->ev_k1a[s]);
+    if (ctx->ev_k1b[s]) cudaEventDestroy(ctx->ev_k1b[s]);
   }
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);

@@ -55,6 +55,7 @@ struct b2m_ctx {
   cudaEvent_t ev_k[2] = {nullptr, nullptr};
   cudaEvent_t ev_data[2] = {nullptr, nullptr};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_k1a[2] = {nullptr, nullptr}, ev_k1b[2] = {nullptr, nullptr};
   float* d_lut = nullptr;
   b2m::ImageSet images;
   b2m::Workspace ws;

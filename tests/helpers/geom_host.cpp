@@ -1,0 +1,27 @@
+// Host build of pycolmap_b200/csrc/geom.h for CPU unit tests (test infrastructure: lets pytest
+// check the solver math against numpy without a GPU).  Not part of the product library.
+#include "../../pycolmap_b200/csrc/geom.h"
+using namespace b2m::geom;
+extern "C" {
+int gh_poly_roots(const double* c, int deg, double* roots) { return poly_real_roots(c, deg, roots); }
+void gh_jacobi9(const double* A_in, double* V, double* w) {
+  double A[81];
+  for (int i = 0; i < 81; ++i) A[i] = A_in[i];
+  jacobi_eig_sym<9>(A, V, w);
+}
+int gh_estimate_E(const double* x1, const double* y1, const double* x2, const double* y2, int n, double* models) {
+  return estimate_E(x1, y1, x2, y2, n, models);
+}
+int gh_estimate_F7(const double* x1, const double* y1, const double* x2, const double* y2, double* models) {
+  return estimate_F7(x1, y1, x2, y2, models);
+}
+int gh_estimate_F8(const double* x1, const double* y1, const double* x2, const double* y2, int n, double* model) {
+  return estimate_F8(x1, y1, x2, y2, n, model);
+}
+int gh_estimate_H(const double* x1, const double* y1, const double* x2, const double* y2, int n, double* model) {
+  return estimate_H(x1, y1, x2, y2, n, model);
+}
+double gh_sampson(const double* E, double x1, double y1, double x2, double y2) { return sampson_sq(E, x1, y1, x2, y2); }
+double gh_homography(const double* H, double x1, double y1, double x2, double y2) { return homography_sq(H, x1, y1, x2, y2); }
+double gh_num_trials(double ni, double ns, double conf, double mult, int k) { return compute_num_trials(ni, ns, conf, mult, k); }
+}

@@ -1,0 +1,549 @@
+"""CPU restatement (numpy, fp64) of the reference's two-view geometric verifier.
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED: the reference
+(/root/reference) forwards into COLMAP 3.9.1 which is not vendored and holds no golden vectors
+for this path; this file restates the published algorithms, anchored on the reference call sites:
+
+  estimate_two_view_geometry        <- R:estimators/two_view_geometry.h:95-151 -> U:estimators/two_view_geometry.cc
+                                       EstimateTwoViewGeometry / EstimateCalibrated... / EstimateUncalibrated...  (V1, V2)
+  loransac                          <- R:estimators/essential_matrix.h:48-52, fundamental_matrix.h:26-29,
+                                       homography_matrix.h:25-27 -> U:optim/loransac.h LORANSAC::Estimate      (V3)
+  EssentialFivePoint                <- U:estimators/essential_matrix.cc EssentialMatrixFivePointEstimator       (V4)
+  FundamentalSevenPoint/EightPoint  <- U:estimators/fundamental_matrix.cc                                      (V5)
+  Homography                        <- U:estimators/homography_matrix.cc                                       (V6)
+  squared_sampson_error             <- R:estimators/two_view_geometry.h:161-175 -> U:estimators/utils.cc        (V7)
+  detect_watermark                  <- U:estimators/two_view_geometry.cc DetectWatermark                       (V8)
+  cam_from_img / cam_from_img_threshold <- R:scene/camera.h cam_from_img, cam_from_img_threshold               (V9)
+  exhaustive_pairs / sequential_pairs   <- U:controllers/feature_matching.cc                                   (P1, P2)
+
+The control flow is the sequential upstream one (one trial at a time, LO on every new best);
+numpy's PCG64 stands in for upstream's thread-local mt19937, so results are statistically --
+not bitwise -- comparable, exactly like two upstream runs with different thread counts.
+The 5-point solver uses the action-matrix (Stewenius) formulation on purpose: it is a different
+algorithm from the hidden-variable elimination the CUDA path uses, so the two check each other.
+"""
+import math
+
+import numpy as np
+
+UNDEFINED, DEGENERATE, CALIBRATED, UNCALIBRATED, PLANAR, PANORAMIC, PLANAR_OR_PANORAMIC, WATERMARK, MULTIPLE = range(9)
+
+# cost constants published for the roofline arithmetic
+FLOPS_SAMPSON = 33
+FLOPS_HOMOGRAPHY = 19
+
+
+# ---------------------------------------------------------------------------------------------
+# residuals
+# ---------------------------------------------------------------------------------------------
+def squared_sampson_error(points1, points2, E):
+    x1, y1 = points1[:, 0], points1[:, 1]
+    x2, y2 = points2[:, 0], points2[:, 1]
+    Ex1_0 = E[0, 0] * x1 + E[0, 1] * y1 + E[0, 2]
+    Ex1_1 = E[1, 0] * x1 + E[1, 1] * y1 + E[1, 2]
+    Ex1_2 = E[2, 0] * x1 + E[2, 1] * y1 + E[2, 2]
+    Etx2_0 = E[0, 0] * x2 + E[1, 0] * y2 + E[2, 0]
+    Etx2_1 = E[0, 1] * x2 + E[1, 1] * y2 + E[2, 1]
+    x2tEx1 = x2 * Ex1_0 + y2 * Ex1_1 + Ex1_2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return x2tEx1 * x2tEx1 / (Ex1_0 * Ex1_0 + Ex1_1 * Ex1_1 + Etx2_0 * Etx2_0 + Etx2_1 * Etx2_1)
+
+
+def homography_residuals(points1, points2, H):
+    s0, s1 = points1[:, 0], points1[:, 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pd2 = H[2, 0] * s0 + H[2, 1] * s1 + H[2, 2]
+        inv = 1.0 / pd2
+        dd0 = points2[:, 0] - (H[0, 0] * s0 + H[0, 1] * s1 + H[0, 2]) * inv
+        dd1 = points2[:, 1] - (H[1, 0] * s0 + H[1, 1] * s1 + H[1, 2]) * inv
+        return dd0 * dd0 + dd1 * dd1
+
+
+def center_and_normalize(points):
+    c = points.mean(0)
+    rms = math.sqrt(((points - c) ** 2).sum(1).mean())
+    s = math.sqrt(2.0) / rms if rms > 0 else float("inf")
+    T = np.array([[s, 0, -s * c[0]], [0, s, -s * c[1]], [0, 0, 1.0]])
+    return (points - c) * s, T
+
+
+def _epipolar_rows(p1, p2):
+    x1, y1, x2, y2 = p1[:, 0], p1[:, 1], p2[:, 0], p2[:, 1]
+    o = np.ones_like(x1)
+    return np.stack([x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, o], 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# 5-point essential (action matrix)
+# ---------------------------------------------------------------------------------------------
+def _pmul(a, b):
+    """Product of dense trivariate polynomials (coefficient tensors indexed by exponents)."""
+    out = np.zeros(tuple(np.array(a.shape) + np.array(b.shape) - 1))
+    for idx in np.ndindex(*a.shape):
+        if a[idx] != 0.0:
+            out[idx[0]:idx[0] + b.shape[0], idx[1]:idx[1] + b.shape[1], idx[2]:idx[2] + b.shape[2]] += a[idx] * b
+    return out
+
+
+_CUBICS = [(3, 0, 0), (2, 1, 0), (2, 0, 1), (1, 2, 0), (1, 1, 1), (1, 0, 2), (0, 3, 0), (0, 2, 1), (0, 1, 2), (0, 0, 3)]
+_BASIS = [(2, 0, 0), (1, 1, 0), (1, 0, 1), (0, 2, 0), (0, 1, 1), (0, 0, 2), (1, 0, 0), (0, 1, 0), (0, 0, 1), (0, 0, 0)]
+
+
+def _pad3(p):
+    out = np.zeros((4, 4, 4))
+    out[:p.shape[0], :p.shape[1], :p.shape[2]] = p
+    return out
+
+
+def five_point_from_nullspace(N):
+    """N: [4, 9] rows X, Y, Z, W; E = x X + y Y + z Z + W.  Returns list of 3x3 E."""
+    Ep = np.empty((3, 3), object)
+    for i in range(3):
+        for j in range(3):
+            p = np.zeros((2, 2, 2))
+            p[1, 0, 0], p[0, 1, 0], p[0, 0, 1], p[0, 0, 0] = N[0, 3 * i + j], N[1, 3 * i + j], N[2, 3 * i + j], N[3, 3 * i + j]
+            Ep[i, j] = p
+    eqs = []
+    det = (_pmul(Ep[0, 0], _pmul(Ep[1, 1], Ep[2, 2]) - _pmul(Ep[1, 2], Ep[2, 1]))
+           - _pmul(Ep[0, 1], _pmul(Ep[1, 0], Ep[2, 2]) - _pmul(Ep[1, 2], Ep[2, 0]))
+           + _pmul(Ep[0, 2], _pmul(Ep[1, 0], Ep[2, 1]) - _pmul(Ep[1, 1], Ep[2, 0])))
+    eqs.append(_pad3(det))
+    EEt = np.empty((3, 3), object)
+    for i in range(3):
+        for j in range(3):
+            EEt[i, j] = sum(_pmul(Ep[i, k], Ep[j, k]) for k in range(3))
+    tr = EEt[0, 0] + EEt[1, 1] + EEt[2, 2]
+    for i in range(3):
+        for j in range(3):
+            acc = np.zeros((4, 4, 4))
+            for k in range(3):
+                lam = EEt[i, k] - (0.5 * tr if i == k else 0.0)
+                acc += _pad3(_pmul(lam, Ep[k, j]))
+            eqs.append(acc)
+    M = np.array([[e[m] for m in _CUBICS + _BASIS] for e in eqs])
+    try:
+        R = np.linalg.solve(M[:, :10], M[:, 10:])     # cubic_i = -R[i] . basis
+    except np.linalg.LinAlgError:
+        return []
+    A = np.zeros((10, 10))
+    # x * basis_i expressed in the basis
+    for i, (a, b, c) in enumerate(_BASIS):
+        m = (a + 1, b, c)
+        if m in _BASIS:
+            A[i, _BASIS.index(m)] = 1.0
+        else:
+            A[i, :] = -R[_CUBICS.index(m)]
+    w, V = np.linalg.eig(A)
+    out = []
+    for k in range(10):
+        if abs(w[k].imag) > 1e-9 * max(1.0, abs(w[k].real)):
+            continue
+        v = V[:, k].real
+        if abs(v[9]) < 1e-14 * np.abs(v).max():
+            continue
+        x, y, z = v[6] / v[9], v[7] / v[9], v[8] / v[9]
+        out.append((x * N[0] + y * N[1] + z * N[2] + N[3]).reshape(3, 3))
+    return out
+
+
+class EssentialFivePoint:
+    kMinNumSamples = 5
+
+    @staticmethod
+    def estimate(p1, p2):
+        Q = _epipolar_rows(p1, p2)
+        _, _, Vt = np.linalg.svd(Q, full_matrices=True)
+        return five_point_from_nullspace(Vt[5:9])
+
+    residuals = staticmethod(squared_sampson_error)
+
+
+class FundamentalSevenPoint:
+    kMinNumSamples = 7
+
+    @staticmethod
+    def estimate(p1, p2):
+        A = _epipolar_rows(p1, p2)
+        _, _, Vt = np.linalg.svd(A, full_matrices=True)
+        f1, f2 = Vt[7].reshape(3, 3), Vt[8].reshape(3, 3)
+        # det(l f1 + (1-l) f2) sampled at 4 points -> cubic coefficients
+        ls = np.array([-1.0, 0.0, 1.0, 2.0])
+        d = [np.linalg.det(l * f1 + (1 - l) * f2) for l in ls]
+        c = np.linalg.solve(np.vander(ls, 4), d)
+        out = []
+        for r in np.roots(c):
+            if abs(r.imag) < 1e-10:
+                out.append(r.real * f1 + (1 - r.real) * f2)
+        return out
+
+    residuals = staticmethod(squared_sampson_error)
+
+
+class FundamentalEightPoint:
+    kMinNumSamples = 8
+
+    @staticmethod
+    def estimate(p1, p2):
+        n1, T1 = center_and_normalize(p1)
+        n2, T2 = center_and_normalize(p2)
+        A = _epipolar_rows(n1, n2)
+        _, _, Vt = np.linalg.svd(A, full_matrices=True)
+        F = Vt[8].reshape(3, 3)
+        U, S, Vt2 = np.linalg.svd(F)
+        S[2] = 0.0
+        return [T2.T @ (U @ np.diag(S) @ Vt2) @ T1]
+
+    residuals = staticmethod(squared_sampson_error)
+
+
+class Homography:
+    kMinNumSamples = 4
+
+    @staticmethod
+    def estimate(p1, p2):
+        n1, T1 = center_and_normalize(p1)
+        n2, T2 = center_and_normalize(p2)
+        N = len(p1)
+        A = np.zeros((2 * N, 9))
+        s0, s1, d0, d1 = n1[:, 0], n1[:, 1], n2[:, 0], n2[:, 1]
+        A[0::2, 0], A[0::2, 1], A[0::2, 2] = -s0, -s1, -1
+        A[0::2, 6], A[0::2, 7], A[0::2, 8] = s0 * d0, s1 * d0, d0
+        A[1::2, 3], A[1::2, 4], A[1::2, 5] = -s0, -s1, -1
+        A[1::2, 6], A[1::2, 7], A[1::2, 8] = s0 * d1, s1 * d1, d1
+        if not np.isfinite(A).all():
+            return []
+        _, _, Vt = np.linalg.svd(A, full_matrices=True)
+        H = Vt[8].reshape(3, 3)
+        return [np.linalg.inv(T2) @ H @ T1]
+
+    residuals = staticmethod(homography_residuals)
+
+
+class Translation2D:
+    """U:estimators/translation_transform.h (used by DetectWatermark)."""
+    kMinNumSamples = 1
+
+    @staticmethod
+    def estimate(p1, p2):
+        return [(p2 - p1).mean(0)]
+
+    @staticmethod
+    def residuals(p1, p2, t):
+        d = p2 - (p1 + t)
+        return (d * d).sum(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# LO-RANSAC
+# ---------------------------------------------------------------------------------------------
+class RansacOptions:
+    def __init__(self, max_error=4.0, min_inlier_ratio=0.25, confidence=0.999, dyn_num_trials_multiplier=3.0,
+                 min_num_trials=100, max_num_trials=10000):
+        self.max_error, self.min_inlier_ratio, self.confidence = max_error, min_inlier_ratio, confidence
+        self.dyn_num_trials_multiplier, self.min_num_trials, self.max_num_trials = (
+            dyn_num_trials_multiplier, min_num_trials, max_num_trials)
+
+    def copy(self, **kw):
+        o = RansacOptions(**self.__dict__)
+        o.__dict__.update(kw)
+        return o
+
+
+def compute_num_trials(num_inliers, num_samples, confidence, multiplier, k_min):
+    ratio = num_inliers / float(num_samples)
+    nom = 1.0 - confidence
+    if nom <= 0:
+        return float("inf")
+    denom = 1.0 - ratio ** k_min
+    if denom <= 0:
+        return 1
+    if denom == 1.0:
+        return float("inf")
+    return math.ceil(math.log(nom) / math.log(denom) * multiplier)
+
+
+class Report:
+    def __init__(self):
+        self.success, self.num_trials, self.num_inliers, self.residual_sum = False, 0, 0, float("inf")
+        self.model, self.inlier_mask = None, None
+        self.num_models_scored = 0
+
+
+def _support(res, max_residual):
+    with np.errstate(invalid="ignore"):
+        m = res <= max_residual
+    return int(m.sum()), float(res[m].sum())
+
+
+def _better(a, b):
+    return a[0] > b[0] or (a[0] == b[0] and a[1] < b[1])
+
+
+def loransac(est, local_est, X, Y, opt, rng):
+    """LORANSAC<est, local_est>::Estimate (U:optim/loransac.h), sequential restatement."""
+    rep = Report()
+    n = len(X)
+    rep.inlier_mask = np.zeros(n, bool)
+    if n < est.kMinNumSamples:
+        return rep
+    # RANSAC ctor: clip max_num_trials by the trials needed at min_inlier_ratio
+    max_trials = min(opt.max_num_trials,
+                     compute_num_trials(int(opt.min_inlier_ratio * 100000), 100000, opt.confidence,
+                                        opt.dyn_num_trials_multiplier, est.kMinNumSamples))
+    dyn_max = max_trials
+    max_residual = opt.max_error * opt.max_error
+    best = (0, float("inf"))
+    best_model, best_local = None, False
+    idx = np.arange(n)
+    abort = False
+    trial = 0
+    while trial < max_trials:
+        if abort:
+            trial += 1
+            break
+        # RandomSampler: partial Fisher-Yates on a persistent index vector
+        k = est.kMinNumSamples
+        for i in range(k):
+            j = int(rng.integers(i, n))
+            idx[i], idx[j] = idx[j], idx[i]
+        s = idx[:k]
+        for model in est.estimate(X[s], Y[s]):
+            res = est.residuals(X, Y, model)
+            rep.num_models_scored += 1
+            sup = _support(res, max_residual)
+            if _better(sup, best):
+                best, best_model, best_local = sup, model, False
+                if sup[0] > est.kMinNumSamples and sup[0] >= local_est.kMinNumSamples:
+                    for _ in range(10):
+                        with np.errstate(invalid="ignore"):
+                            inl = res <= max_residual
+                        prev = best[0]
+                        best_local_res = None
+                        for lm in local_est.estimate(X[inl], Y[inl]):
+                            lres = local_est.residuals(X, Y, lm)
+                            rep.num_models_scored += 1
+                            lsup = _support(lres, max_residual)
+                            if _better(lsup, best):
+                                best, best_model, best_local, best_local_res = lsup, lm, True, lres
+                        if best[0] <= prev:
+                            break
+                        res = best_local_res
+                dyn_max = compute_num_trials(best[0], n, opt.confidence, opt.dyn_num_trials_multiplier,
+                                             est.kMinNumSamples)
+            if trial >= dyn_max and trial >= opt.min_num_trials:
+                abort = True
+                break
+        trial += 1
+    rep.num_trials = trial
+    rep.num_inliers, rep.residual_sum, rep.model = best[0], best[1], best_model
+    if best[0] < est.kMinNumSamples or best_model is None:
+        return rep
+    rep.success = True
+    res = (local_est if best_local else est).residuals(X, Y, best_model)
+    with np.errstate(invalid="ignore"):
+        rep.inlier_mask = res <= max_residual
+    return rep
+
+
+# ---------------------------------------------------------------------------------------------
+# cameras (SIMPLE_PINHOLE = 0: f, cx, cy; PINHOLE = 1: fx, fy, cx, cy)
+# ---------------------------------------------------------------------------------------------
+def cam_from_img(cam, pts):
+    p = cam["params"]
+    if cam.get("model", 0) == 0:
+        return (pts - [p[1], p[2]]) / p[0]
+    return (pts - [p[2], p[3]]) / [p[0], p[1]]
+
+
+def mean_focal_length(cam):
+    p = cam["params"]
+    return p[0] if cam.get("model", 0) == 0 else 0.5 * (p[0] + p[1])
+
+
+def cam_from_img_threshold(cam, thr):
+    return thr / mean_focal_length(cam)
+
+
+# ---------------------------------------------------------------------------------------------
+# two-view geometry
+# ---------------------------------------------------------------------------------------------
+class TwoViewGeometryOptions:
+    def __init__(self, **kw):
+        self.min_num_inliers = 15
+        self.min_E_F_inlier_ratio = 0.95
+        self.max_H_inlier_ratio = 0.8
+        self.watermark_min_inlier_ratio = 0.7
+        self.watermark_border_size = 0.1
+        self.detect_watermark = True
+        self.multiple_ignore_watermark = True
+        self.force_H_use = False
+        self.compute_relative_pose = False
+        self.multiple_models = False
+        self.ransac = RansacOptions()
+        for k, v in kw.items():
+            assert hasattr(self, k), k
+            setattr(self, k, v)
+
+
+class TwoViewGeometry:
+    def __init__(self):
+        self.config = UNDEFINED
+        self.E, self.F, self.H = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 3))
+        self.inlier_matches = np.zeros((0, 2), np.uint32)
+        self.nE = self.nF = self.nH = 0
+        self.reports = {}
+
+
+def detect_watermark(cam1, pts1, cam2, pts2, num_inliers, mask, opt, rng):
+    """DetectWatermark (U:estimators/two_view_geometry.cc)."""
+    if num_inliers == 0:
+        return False
+    d1 = opt.watermark_border_size * math.hypot(cam1["width"], cam1["height"])
+    d2 = opt.watermark_border_size * math.hypot(cam2["width"], cam2["height"])
+    a, b = pts1[mask], pts2[mask]
+
+    def border(p, cam, d):
+        return (p[:, 0] < d) | (p[:, 0] > cam["width"] - d) | (p[:, 1] < d) | (p[:, 1] > cam["height"] - d)
+    sel = border(a, cam1, d1) & border(b, cam2, d2)
+    if sel.sum() / float(num_inliers) < opt.watermark_min_inlier_ratio:
+        return False
+    ro = opt.ransac.copy(min_inlier_ratio=opt.watermark_min_inlier_ratio)
+    rep = loransac(Translation2D, Translation2D, a[sel], b[sel], ro, rng)
+    inl_ratio = rep.num_inliers / float(num_inliers)
+    return rep.success and inl_ratio >= opt.watermark_min_inlier_ratio
+
+
+def _decide(g, opt, repE, repF, repH, calibrated):
+    nE = repE.num_inliers if calibrated else 0
+    nF, nH = repF.num_inliers, repH.num_inliers
+    mn = opt.min_num_inliers
+    okE = calibrated and repE.success
+    if (not okE and not repF.success and not repH.success) or (nE < mn and nF < mn and nH < mn):
+        g.config = DEGENERATE
+        return None, 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        E_F = np.float64(nE) / np.float64(nF)
+        H_F = np.float64(nH) / np.float64(nF)
+        H_E = np.float64(nH) / np.float64(nE)
+    if okE and E_F > opt.min_E_F_inlier_ratio and nE >= mn:
+        if nE >= nF:
+            num, mask = nE, repE.inlier_mask
+        else:
+            num, mask = nF, repF.inlier_mask
+        if H_E > opt.max_H_inlier_ratio:
+            g.config = PLANAR_OR_PANORAMIC
+            if nH > num:
+                num, mask = nH, repH.inlier_mask
+        else:
+            g.config = CALIBRATED
+    elif repF.success and nF >= mn:
+        num, mask = nF, repF.inlier_mask
+        if H_F > opt.max_H_inlier_ratio:
+            g.config = PLANAR_OR_PANORAMIC
+            if nH > num:
+                num, mask = nH, repH.inlier_mask
+        else:
+            g.config = UNCALIBRATED
+    elif repH.success and nH >= mn:
+        num, mask = nH, repH.inlier_mask
+        g.config = PLANAR_OR_PANORAMIC
+    else:
+        g.config = DEGENERATE
+        return None, 0
+    return mask, num
+
+
+def estimate_two_view_geometry(cam1, points1, cam2, points2, matches=None, options=None, seed=0):
+    """EstimateTwoViewGeometry.  points: [n, 2] float64; matches: [m, 2] or None (identity)."""
+    opt = options or TwoViewGeometryOptions()
+    rng = np.random.default_rng(seed)
+    points1, points2 = np.asarray(points1, np.float64), np.asarray(points2, np.float64)
+    if matches is None:
+        assert len(points1) == len(points2)
+        matches = np.stack([np.arange(len(points1))] * 2, 1)
+    matches = np.asarray(matches, np.int64).reshape(-1, 2)
+    g = TwoViewGeometry()
+    if opt.multiple_models:
+        raise NotImplementedError("multiple_models (SURVEY.md section 8(f) item 4)")
+    if len(matches) < opt.min_num_inliers:
+        g.config = DEGENERATE
+        return g
+    p1, p2 = points1[matches[:, 0]], points2[matches[:, 1]]
+    calibrated = bool(cam1.get("has_prior_focal_length")) and bool(cam2.get("has_prior_focal_length"))
+    if opt.force_H_use:
+        calibrated = False
+    repE = Report()
+    if calibrated:
+        n1, n2 = cam_from_img(cam1, p1), cam_from_img(cam2, p2)
+        e_opt = opt.ransac.copy(max_error=0.5 * (cam_from_img_threshold(cam1, opt.ransac.max_error)
+                                                 + cam_from_img_threshold(cam2, opt.ransac.max_error)))
+        repE = loransac(EssentialFivePoint, EssentialFivePoint, n1, n2, e_opt, rng)
+        if repE.model is not None:
+            g.E = repE.model
+    repF = loransac(FundamentalSevenPoint, FundamentalEightPoint, p1, p2, opt.ransac, rng)
+    if repF.model is not None:
+        g.F = repF.model
+    repH = loransac(Homography, Homography, p1, p2, opt.ransac, rng)
+    if repH.model is not None:
+        g.H = repH.model
+    g.nE, g.nF, g.nH = repE.num_inliers, repF.num_inliers, repH.num_inliers
+    g.reports = {"E": repE, "F": repF, "H": repH}
+    if opt.force_H_use:
+        # EstimateCalibratedHomography: H only
+        if not repH.success or repH.num_inliers < opt.min_num_inliers:
+            g.config = DEGENERATE
+            return g
+        g.config = PLANAR_OR_PANORAMIC
+        mask, num = repH.inlier_mask, repH.num_inliers
+    else:
+        mask, num = _decide(g, opt, repE, repF, repH, calibrated)
+    if mask is None:
+        return g
+    g.inlier_matches = matches[mask].astype(np.uint32)
+    if opt.detect_watermark and detect_watermark(cam1, p1, cam2, p2, num, mask, opt, rng):
+        g.config = WATERMARK
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+# pair generators (U:controllers/feature_matching.cc)
+# ---------------------------------------------------------------------------------------------
+def exhaustive_pairs(image_ids, block_size=50):
+    """ExhaustiveFeatureMatcher::Run visiting order (row P1)."""
+    ids = list(image_ids)
+    n = len(ids)
+    out = []
+    nb = int(math.ceil(n / block_size))
+    for b1 in range(nb):
+        s1, e1 = b1 * block_size, min(n, (b1 + 1) * block_size) - 1
+        for b2 in range(nb):
+            s2, e2 = b2 * block_size, min(n, (b2 + 1) * block_size) - 1
+            for i1 in range(s1, e1 + 1):
+                for i2 in range(s2, e2 + 1):
+                    b_i1, b_i2 = i1 % block_size, i2 % block_size
+                    if (i1 > i2 and b_i1 <= b_i2) or (i1 < i2 and b_i1 < b_i2):
+                        out.append((ids[i1], ids[i2]))
+    return out
+
+
+def sequential_pairs(image_ids, overlap=10, quadratic_overlap=True):
+    """SequentialFeatureMatcher::RunSequentialMatching (row P2); images ordered by name upstream."""
+    ids = list(image_ids)
+    n = len(ids)
+    out = []
+    for i1 in range(n):
+        for k in range(overlap):
+            i2 = i1 + k + 1
+            if i2 < n:
+                out.append((ids[i1], ids[i2]))
+            if quadratic_overlap:
+                i2q = i1 + (1 << k)
+                if i2q < n:
+                    out.append((ids[i1], ids[i2q]))
+    seen, uniq = set(), []
+    for a, b in out:            # the controller drops duplicates
+        key = (min(a, b), max(a, b))
+        if key not in seen:
+            seen.add(key)
+            uniq.append((a, b))
+    return uniq

@@ -248,6 +248,47 @@ class Context:
                                             ctypes.byref(tvg) if tvg is not None else None, ctypes.byref(res)))
         return Results(self.lib, res)
 
+    # -- estimators ----------------------------------------------------------------------
+    def estimate_two_view_geometry(self, cam1, points1, cam2, points2, matches=None, opts=None):
+        """Returns (TvgResult, inlier_matches [k x 2] uint32)."""
+        p1 = np.ascontiguousarray(points1, np.float64).reshape(-1, 2)
+        p2 = np.ascontiguousarray(points2, np.float64).reshape(-1, 2)
+        opts = opts or self.tvg_opts()
+        cams = self.make_cameras([cam1, cam2])
+        if matches is not None:
+            matches = np.ascontiguousarray(matches, np.uint32).reshape(-1, 2)
+            m = len(matches)
+        else:
+            m = len(p1)
+        out = TvgResult()
+        inl = np.zeros((max(1, m), 2), np.uint32)
+        self.check(self.lib.b2m_estimate_two_view_geometry(
+            self.h, ctypes.byref(cams[0]), ptr(p1), len(p1), ctypes.byref(cams[1]), ptr(p2), len(p2),
+            ptr(matches) if matches is not None else None, m, ctypes.byref(opts), ctypes.byref(out), ptr(inl)))
+        return out, inl[:out.n_inliers].copy()
+
+    def ransac_model(self, kind, points1, points2, opts=None):
+        """kind 0 = E (normalised points), 1 = F, 2 = H.  Returns dict or None (reference: None on failure)."""
+        p1 = np.ascontiguousarray(points1, np.float64).reshape(-1, 2)
+        p2 = np.ascontiguousarray(points2, np.float64).reshape(-1, 2)
+        opts = opts or self.ransac_opts()
+        model = np.zeros(9, np.float64)
+        mask = np.zeros(max(1, len(p1)), np.uint8)
+        n, ok = c_i64(0), c_i32(0)
+        self.check(self.lib.b2m_ransac_model(self.h, int(kind), ptr(p1), ptr(p2), len(p1), ctypes.byref(opts),
+                                             ptr(model), ptr(mask), ctypes.byref(n), ctypes.byref(ok)))
+        if not ok.value:
+            return None
+        return {"model": model.reshape(3, 3), "num_inliers": int(n.value), "inliers": mask[:len(p1)].astype(bool)}
+
+    def squared_sampson_error(self, points1, points2, E):
+        p1 = np.ascontiguousarray(points1, np.float64).reshape(-1, 2)
+        p2 = np.ascontiguousarray(points2, np.float64).reshape(-1, 2)
+        E = np.ascontiguousarray(E, np.float64).reshape(9)
+        out = np.zeros(len(p1), np.float64)
+        self.check(self.lib.b2m_squared_sampson_error(self.h, ptr(p1), ptr(p2), len(p1), ptr(E), ptr(out)))
+        return out
+
     def stats(self):
         s = Stats()
         self.check(self.lib.b2m_get_stats(self.h, ctypes.byref(s)))

@@ -163,6 +163,9 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
 
   const int B = ctx->pair_batch;
   if (int rc = ensure_workspace(ctx, B, S.max_feat_pad)) return bail(rc);
+  if (tvg)
+    if (int rc = verify_prepare(ctx, S, ctx->ws.batch, static_cast<int64_t>(ctx->ws.batch) * ctx->ws.mstride))
+      return bail(rc);
   if (ctx->d_pairs_cap < n_pairs) {
     if (ctx->d_pairs) cudaFree(ctx->d_pairs);
     ctx->d_pairs = nullptr;
@@ -226,7 +229,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       res->cnt[p0 + k] = W.h_pair_cnt[s][k];
     }
     if (tvg)
-      if (int rc = verify_batch_collect(ctx, res, s, p0, nb)) return rc;
+      if (int rc = verify_batch_collect(ctx, res, s, p0, nb, tvg->min_num_inliers)) return rc;
     return B2M_OK;
   };
 
@@ -267,6 +270,9 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     cp.cursor = W.d_cursor[s];
     cp.pair_off = W.d_pair_off[s];
     cp.pair_cnt = W.d_pair_cnt[s];
+    cp.img_row0 = S.d_row0;
+    cp.kpts = tvg ? S.d_kpts : nullptr;
+    cp.pts = tvg ? static_cast<double4*>(verify_points_arena(ctx, s)) : nullptr;
     CU_TRY_R(launch_crosscheck_compact(cp, nb, st));
     ctx->stats.kernel_launches += 1;
     if (tvg)

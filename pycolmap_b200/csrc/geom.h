@@ -618,6 +618,94 @@ B2M_HD inline int estimate_F8(const double* x1, const double* y1, const double* 
   return finish_F8(S, s1, cx1, cy1, s2, cx2, cy2, model);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Null space of an R x 9 matrix (R < 9, full row rank) by Gauss-Jordan elimination with complete
+// pivoting.  A is destroyed.  basis: [(9-R)][9], not orthonormal (none of the solvers needs that).
+// Much cheaper than an eigen-decomposition for the minimal samples (5x9, 7x9, 8x9).
+// ---------------------------------------------------------------------------------------------
+template <int R>
+B2M_HD inline bool nullspace_gauss(double* A /* [R][9] */, double* basis) {
+  int perm[9];
+  for (int j = 0; j < 9; ++j) perm[j] = j;
+  for (int r = 0; r < R; ++r) {
+    int pi = r, pj = r;
+    double best = 0.0;
+    for (int i = r; i < R; ++i)
+      for (int j = r; j < 9; ++j) {
+        const double v = fabs(A[i * 9 + j]);
+        if (v > best) {
+          best = v;
+          pi = i;
+          pj = j;
+        }
+      }
+    if (!(best > 0.0) || !(best < 1e300)) return false;
+    if (pi != r)
+      for (int j = 0; j < 9; ++j) {
+        const double t = A[r * 9 + j];
+        A[r * 9 + j] = A[pi * 9 + j];
+        A[pi * 9 + j] = t;
+      }
+    if (pj != r) {
+      for (int i = 0; i < R; ++i) {
+        const double t = A[i * 9 + r];
+        A[i * 9 + r] = A[i * 9 + pj];
+        A[i * 9 + pj] = t;
+      }
+      const int t = perm[r];
+      perm[r] = perm[pj];
+      perm[pj] = t;
+    }
+    const double inv = 1.0 / A[r * 9 + r];
+    for (int j = r; j < 9; ++j) A[r * 9 + j] *= inv;
+    for (int i = 0; i < R; ++i) {
+      if (i == r) continue;
+      const double f = A[i * 9 + r];
+      if (f == 0.0) continue;
+      for (int j = r; j < 9; ++j) A[i * 9 + j] -= f * A[r * 9 + j];
+    }
+  }
+  for (int k = 0; k < 9 - R; ++k) {
+    double* v = basis + k * 9;
+    for (int j = 0; j < 9; ++j) v[j] = 0.0;
+    v[perm[R + k]] = 1.0;
+    for (int i = 0; i < R; ++i) v[perm[i]] = -A[i * 9 + R + k];
+  }
+  return true;
+}
+
+// Minimal solvers (exactly 5 / 7 / 4 correspondences), elimination-based null spaces.
+B2M_HD inline int minimal_E5(const double* x1, const double* y1, const double* x2, const double* y2, double* models) {
+  double A[45], N[36];
+  for (int i = 0; i < 5; ++i) epipolar_row(x1[i], y1[i], x2[i], y2[i], A + 9 * i);
+  if (!nullspace_gauss<5>(A, N)) return 0;
+  return five_point_from_nullspace(N, models);
+}
+B2M_HD inline int minimal_F7(const double* x1, const double* y1, const double* x2, const double* y2, double* models) {
+  double s1, cx1, cy1, s2, cx2, cy2;
+  moments(x1, y1, 7, &s1, &cx1, &cy1);
+  moments(x2, y2, 7, &s2, &cx2, &cy2);
+  double A[63], N[18];
+  for (int i = 0; i < 7; ++i)
+    epipolar_row(s1 * (x1[i] - cx1), s1 * (y1[i] - cy1), s2 * (x2[i] - cx2), s2 * (y2[i] - cy2), A + 9 * i);
+  if (!nullspace_gauss<7>(A, N)) return 0;
+  double Fn[27];
+  const int n = seven_point_from_nullspace(N, N + 9, Fn);
+  for (int k = 0; k < n; ++k) denormalize_F(Fn + 9 * k, s1, cx1, cy1, s2, cx2, cy2, models + 9 * k);
+  return n;
+}
+B2M_HD inline int minimal_H4(const double* x1, const double* y1, const double* x2, const double* y2, double* model) {
+  double s1, cx1, cy1, s2, cx2, cy2;
+  moments(x1, y1, 4, &s1, &cx1, &cy1);
+  moments(x2, y2, 4, &s2, &cx2, &cy2);
+  double A[72], Hn[9];
+  for (int i = 0; i < 4; ++i)
+    dlt_rows(s1 * (x1[i] - cx1), s1 * (y1[i] - cy1), s2 * (x2[i] - cx2), s2 * (y2[i] - cy2), A + 18 * i, A + 18 * i + 9);
+  if (!nullspace_gauss<8>(A, Hn)) return 0;
+  denormalize_H(Hn, s1, cx1, cy1, s2, cx2, cy2, model);
+  return 1;
+}
+
 // ComputeNumTrials (U:optim/ransac.h)
 B2M_HD inline double compute_num_trials(double num_inliers, double num_samples, double confidence,
                                         double multiplier, int k_min) {

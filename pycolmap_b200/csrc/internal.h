@@ -64,6 +64,7 @@ struct b2m_ctx {
   std::string err;
   volatile int stop = 0;
   b2m_stats stats{};
+  void* verify_state = nullptr;  // b2m::VerifyState (verify.cu)
 };
 
 struct b2m_results {

@@ -46,7 +46,7 @@ __device__ __forceinline__ void merge_top2(uint32_t& a1, uint32_t& a2, uint32_t 
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1)
-k1_match_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p) {
+b2m_k1_match_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p) {
   const int pair = blockIdx.z;
   const int dir = blockIdx.y;
   const int strip = blockIdx.x;
@@ -207,7 +207,7 @@ k1_match_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p) {
 // Cross-check + ordered compaction.  One CTA per pair.  FindBestMatchesBruteForce tail
 // (U:feature/sift.cc): keep (i1, m12[i1]) iff m12[i1] != -1 and (no cross-check or
 // m21[m12[i1]] == i1); output sorted by i1.
-__global__ void __launch_bounds__(256) k_crosscheck_compact(const CompactParams p) {
+__global__ void __launch_bounds__(256) b2m_crosscheck_compact_kernel(const CompactParams p) {
   const int pair = blockIdx.x;
   const int i1 = p.pairs[2 * pair];
   const int n1 = p.img_nfeat[i1];
@@ -253,7 +253,14 @@ __global__ void __launch_bounds__(256) k_crosscheck_compact(const CompactParams 
     __syncthreads();
     int base = s_base;
     for (int w = 0; w < warp; ++w) base += s_warp[w];
-    if (keep) out[base + wpre] = make_uint2(static_cast<unsigned>(i), static_cast<unsigned>(j));
+    if (keep) {
+      out[base + wpre] = make_uint2(static_cast<unsigned>(i), static_cast<unsigned>(j));
+      if (p.pts) {  // matched pixel coordinates for the verifier (keypoints are float32, exact in double)
+        const float2 a = p.kpts[p.img_row0[i1] + i];
+        const float2 b = p.kpts[p.img_row0[p.pairs[2 * pair + 1]] + j];
+        p.pts[s_off + base + wpre] = make_double4(a.x, a.y, b.x, b.y);
+      }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       int total = 0;
@@ -268,18 +275,18 @@ cudaError_t launch_k1_match(const CUtensorMap& tmap, const MatchParams& p, int n
                             cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k1_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(b2m_k1_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(kSmemBytes));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid(max_strips, n_dirs, n_pairs);
-  k1_match_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, p);
+  b2m_k1_match_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream) {
-  k_crosscheck_compact<<<n_pairs, 256, 0, stream>>>(p);
+  b2m_crosscheck_compact_kernel<<<n_pairs, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

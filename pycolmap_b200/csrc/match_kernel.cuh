@@ -27,6 +27,10 @@ struct CompactParams {
   unsigned long long* cursor;   // device arena cursor (matches)
   int64_t* pair_off;            // device [n_pairs] offset (in matches) of each pair inside the arena
   int32_t* pair_cnt;            // device [n_pairs]
+  // verification input (optional): pixel coordinates of every raw match, same arena offsets
+  const int32_t* img_row0;      // device [n_images]
+  const float2* kpts;           // device keypoints indexed by padded row, or nullptr
+  double4* pts;                 // device arena (x1, y1, x2, y2), or nullptr
 };
 
 // Rows per A strip / columns per B tile: images are padded (with zero descriptors, which can

@@ -1,7 +1,735 @@
-// verify.cu -- placeholder until the K2/K3 LO-RANSAC kernels land (next milestone).
+// verify.cu -- K2/K3: batched LO-RANSAC two-view geometric verification (E 5-pt, F 7-pt + 8-pt LO,
+// H 4-pt DLT), decision tree, inlier extraction and watermark detection, plus the stand-alone
+// estimator entry points of the C ABI.
+//
+// One CTA per (image pair, model kind).  Inside a CTA a round evaluates up to 128 minimal-sample
+// hypotheses at once (thread = hypothesis for the solver, warp = model for the residual scoring
+// with coalesced double4 loads and shuffle reductions), the best of the round goes through the
+// recursive local optimisation (N-point refits from parallel normal-equation reductions), and the
+// dynamic trial bound of U:optim/ransac.h terminates the loop.  Sampling is counter-based
+// (seed, image ids, kind, trial) so results do not depend on batching or sharding.
+//
+// Semantics: U:estimators/two_view_geometry.cc (EstimateTwoViewGeometry, EstimateCalibrated...,
+// EstimateUncalibrated..., DetectWatermark, ExtractInlierMatches), U:optim/loransac.h, reached from
+// R:pipeline/match_features.h:45-48 (VerifierWorker) and R:estimators/two_view_geometry.h:95-151.
+// SURVEY.md section 8 rows V1-V9.  RANSAC parity vs the sequential reference is statistical
+// (+-1% inliers), as it is between two runs of the reference itself.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "geom.h"
 #include "verify.cuh"
 
 namespace b2m {
+
+namespace {
+
+using namespace geom;
+
+constexpr int kRansacThreads = 128;
+constexpr int kMaxLocalTrials = 10;
+
+struct DevCamera {
+  double fx, fy, cx, cy;
+  double mean_f;
+  int32_t width, height;
+  int32_t has_prior;
+  int32_t pad;
+};
+
+struct VerifyParams {
+  const int32_t* pairs;       // [nb x 2] image indices
+  const int64_t* pair_off;    // [nb] offset into the arenas
+  const int32_t* pair_cnt;    // [nb] matches of the pair
+  const double4* pts;         // arena: (x1, y1, x2, y2) pixel coordinates of each raw match
+  const uint2* matches;       // arena: raw matches
+  const DevCamera* cams;      // per image
+  uint8_t* mask;              // [3][arena_cap] inlier masks per kind
+  int64_t arena_cap;
+  double* models;             // [nb][3][9]
+  int32_t* sup_cnt;           // [nb][3]
+  int32_t* success;           // [nb][3]
+  // outputs of the decision kernel
+  int32_t* config;            // [nb]
+  int32_t* inl_cnt;           // [nb]
+  uint2* inliers;             // arena (same offsets as matches)
+  // options
+  b2m_tvg_opts opt;
+  uint64_t seed;
+  int32_t single_kind;        // >= 0: only this kind runs (stand-alone estimator API), no camera model
+  int32_t force_calibrated;   // stand-alone: -1 use camera flags
+};
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double warp_sum_d(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// residual of point i under `model` for problem kind (0 = E on normalised coordinates)
+struct PointXform {
+  double ax1, bx1, ay1, by1, ax2, bx2, ay2, by2;  // n = a * p + b  (identity for F / H)
+};
+__device__ __forceinline__ void load_pt(const double4* pts, int64_t i, const PointXform& X, double& x1, double& y1,
+                                        double& x2, double& y2) {
+  const double4 p = pts[i];
+  x1 = X.ax1 * p.x + X.bx1;
+  y1 = X.ay1 * p.y + X.by1;
+  x2 = X.ax2 * p.z + X.bx2;
+  y2 = X.ay2 * p.w + X.by2;
+}
+template <int KIND>
+__device__ __forceinline__ double residual(const double* M, double x1, double y1, double x2, double y2) {
+  if (KIND == 2) return homography_sq(M, x1, y1, x2, y2);
+  return sampson_sq(M, x1, y1, x2, y2);
+}
+
+template <int KIND>
+struct Traits;
+template <>
+struct Traits<0> {  // E: 5-point for minimal and local
+  static constexpr int kMin = 5, kLocalMin = 5, kMaxModels = 10, kMaxLocalModels = 10;
+};
+template <>
+struct Traits<1> {  // F: 7-point minimal, 8-point local
+  static constexpr int kMin = 7, kLocalMin = 8, kMaxModels = 3, kMaxLocalModels = 1;
+};
+template <>
+struct Traits<2> {  // H: 4-point DLT for both
+  static constexpr int kMin = 4, kLocalMin = 4, kMaxModels = 1, kMaxLocalModels = 1;
+};
+
+struct Shared {
+  double best_model[9];
+  double cand_models[10 * 9];
+  double red[4][64];     // per-warp partial sums (45 normal-equation entries + 8 moments)
+  double sum_arr[kRansacThreads];
+  int cnt_arr[kRansacThreads];
+  int cand_cnt[10];
+  double cand_sum[10];
+  int n_cand;
+  int best_cnt;
+  double best_sum;
+  int winner;
+  int improved;
+  double norm[6];        // s1, cx1, cy1, s2, cx2, cy2
+};
+
+// Score `model` (registers of every lane hold the same 9 values) over all points; warp-cooperative.
+template <int KIND>
+__device__ __forceinline__ void warp_score(const double* M, const double4* pts, int64_t off, int n,
+                                           const PointXform& X, double thr, int lane, int& cnt, double& sum) {
+  int c = 0;
+  double s = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    double x1, y1, x2, y2;
+    load_pt(pts, off + i, X, x1, y1, x2, y2);
+    const double r = residual<KIND>(M, x1, y1, x2, y2);
+    if (r <= thr) {
+      ++c;
+      s += r;
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, c);
+  sum = warp_sum_d(s);
+}
+
+template <int KIND>
+__device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int64_t off, int n,
+                               const PointXform& X, double thr, uint64_t key, const b2m_ransac_opts& ro) {
+  using T = Traits<KIND>;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double4* pts = P.pts;
+  uint8_t* mask = P.mask + static_cast<int64_t>(KIND) * P.arena_cap + off;
+  const int out_idx = pair * 3 + KIND;
+
+  if (n < T::kMin) {  // report.success = false, no inliers (U:optim/loransac.h)
+    for (int i = tid; i < n; i += kRansacThreads) mask[i] = 0;
+    if (tid == 0) {
+      P.sup_cnt[out_idx] = 0;
+      P.success[out_idx] = 0;
+      for (int k = 0; k < 9; ++k) P.models[out_idx * 9 + k] = 0.0;
+    }
+    return;
+  }
+  // RANSAC ctor: clip max_num_trials by the bound at min_inlier_ratio
+  double max_trials_d = compute_num_trials(floor(ro.min_inlier_ratio * 100000.0), 100000.0, ro.confidence,
+                                           ro.dyn_num_trials_multiplier, T::kMin);
+  const int max_trials = static_cast<int>(fmin(static_cast<double>(ro.max_num_trials), max_trials_d));
+  double dyn_max = max_trials;
+  if (tid == 0) {
+    sh.best_cnt = 0;
+    sh.best_sum = 1e300;
+    for (int k = 0; k < 9; ++k) sh.best_model[k] = 0.0;
+  }
+  __syncthreads();
+
+  int trials = 0;
+  double mdl[T::kMaxModels * 9];
+  while (trials < max_trials) {
+    int nb = min(kRansacThreads, max_trials - trials);
+    if (trials < ro.min_num_trials) nb = min(nb, ro.min_num_trials - trials);
+    // ---- phase 1: one minimal-sample hypothesis per thread
+    int nm = 0;
+    if (tid < nb) {
+      const uint64_t tkey = splitmix64(key + static_cast<uint64_t>(trials + tid) * 0x100000001B3ull);
+      int idx[T::kMin];
+      for (int j = 0; j < T::kMin; ++j) {
+        int cand = 0;
+        for (int attempt = 0; attempt < 64; ++attempt) {
+          const uint64_t r = splitmix64(tkey + static_cast<uint64_t>(j * 64 + attempt));
+          cand = static_cast<int>(__umul64hi(r, static_cast<uint64_t>(n)));
+          bool dup = false;
+          for (int q = 0; q < j; ++q) dup |= (idx[q] == cand);
+          if (!dup) break;
+        }
+        idx[j] = cand;
+      }
+      double x1[T::kMin], y1[T::kMin], x2[T::kMin], y2[T::kMin];
+      for (int j = 0; j < T::kMin; ++j) load_pt(pts, off + idx[j], X, x1[j], y1[j], x2[j], y2[j]);
+      if (KIND == 0) nm = minimal_E5(x1, y1, x2, y2, mdl);
+      if (KIND == 1) nm = minimal_F7(x1, y1, x2, y2, mdl);
+      if (KIND == 2) nm = minimal_H4(x1, y1, x2, y2, mdl);
+    }
+    // ---- phase 2: score every model of every hypothesis of this warp (warp = one model at a time)
+    int my_cnt = -1, my_m = 0;
+    double my_sum = 1e300;
+    for (int h = 0; h < 32; ++h) {
+      const int nm_h = __shfl_sync(0xffffffffu, nm, h);
+      for (int m = 0; m < nm_h; ++m) {
+        double M[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) M[k] = shfl_d(mdl[(lane == h ? m : 0) * 9 + k], h);
+        int c;
+        double s;
+        warp_score<KIND>(M, pts, off, n, X, thr, lane, c, s);
+        if (lane == h && (c > my_cnt || (c == my_cnt && s < my_sum))) {
+          my_cnt = c;
+          my_sum = s;
+          my_m = m;
+        }
+      }
+    }
+    sh.cnt_arr[tid] = my_cnt;
+    sh.sum_arr[tid] = my_sum;
+    __syncthreads();
+    if (tid == 0) {
+      int w = -1, bc = sh.best_cnt;
+      double bs = sh.best_sum;
+      for (int t = 0; t < nb; ++t) {
+        const int c = sh.cnt_arr[t];
+        const double s = sh.sum_arr[t];
+        if (c > bc || (c == bc && s < bs)) {
+          bc = c;
+          bs = s;
+          w = t;
+        }
+      }
+      sh.winner = w;
+      sh.improved = (w >= 0);
+      if (w >= 0) {
+        sh.best_cnt = bc;
+        sh.best_sum = bs;
+      }
+    }
+    __syncthreads();
+    if (sh.improved) {
+      if (tid == sh.winner)
+        for (int k = 0; k < 9; ++k) sh.best_model[k] = mdl[my_m * 9 + k];
+      __syncthreads();
+      // ---- phase 3: recursive local optimisation on the inliers of the current best
+      if (sh.best_cnt > T::kMin && sh.best_cnt >= T::kLocalMin) {
+        for (int lt = 0; lt < kMaxLocalTrials; ++lt) {
+          const int prev_best = sh.best_cnt;
+          double M[9];
+          for (int k = 0; k < 9; ++k) M[k] = sh.best_model[k];
+          double s1 = 1, cx1 = 0, cy1 = 0, s2 = 1, cx2 = 0, cy2 = 0;
+          if (KIND != 0) {  // Hartley normalisation of the inlier set: moments first
+            double mo[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (int i = tid; i < n; i += kRansacThreads) {
+              double x1, y1, x2, y2;
+              load_pt(pts, off + i, X, x1, y1, x2, y2);
+              if (residual<KIND>(M, x1, y1, x2, y2) <= thr) {
+                mo[0] += 1.0;
+                mo[1] += x1; mo[2] += y1; mo[3] += x1 * x1 + y1 * y1;
+                mo[4] += x2; mo[5] += y2; mo[6] += x2 * x2 + y2 * y2;
+              }
+            }
+            for (int k = 0; k < 7; ++k) {
+              const double v = warp_sum_d(mo[k]);
+              if (lane == 0) sh.red[warp][k] = v;
+            }
+            __syncthreads();
+            if (tid == 0) {
+              double t[7];
+              for (int k = 0; k < 7; ++k) t[k] = sh.red[0][k] + sh.red[1][k] + sh.red[2][k] + sh.red[3][k];
+              norm_from_moments(t[0], t[1], t[2], t[3], &sh.norm[0], &sh.norm[1], &sh.norm[2]);
+              norm_from_moments(t[0], t[4], t[5], t[6], &sh.norm[3], &sh.norm[4], &sh.norm[5]);
+            }
+            __syncthreads();
+            s1 = sh.norm[0]; cx1 = sh.norm[1]; cy1 = sh.norm[2];
+            s2 = sh.norm[3]; cx2 = sh.norm[4]; cy2 = sh.norm[5];
+          }
+          double S[45];
+#pragma unroll
+          for (int k = 0; k < 45; ++k) S[k] = 0.0;
+          for (int i = tid; i < n; i += kRansacThreads) {
+            double x1, y1, x2, y2;
+            load_pt(pts, off + i, X, x1, y1, x2, y2);
+            if (residual<KIND>(M, x1, y1, x2, y2) <= thr) {
+              double r1[9], r2[9];
+              if (KIND == 2) {
+                dlt_rows(s1 * (x1 - cx1), s1 * (y1 - cy1), s2 * (x2 - cx2), s2 * (y2 - cy2), r1, r2);
+                sym9_add_row(S, r1);
+                sym9_add_row(S, r2);
+              } else {
+                epipolar_row(s1 * (x1 - cx1), s1 * (y1 - cy1), s2 * (x2 - cx2), s2 * (y2 - cy2), r1);
+                sym9_add_row(S, r1);
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 45; ++k) {
+            const double v = warp_sum_d(S[k]);
+            if (lane == 0) sh.red[warp][k] = v;
+          }
+          __syncthreads();
+          if (tid == 0) {
+            double St[45];
+            for (int k = 0; k < 45; ++k) St[k] = sh.red[0][k] + sh.red[1][k] + sh.red[2][k] + sh.red[3][k];
+            int nc = 0;
+            if (KIND == 0) {
+              double A[81], V[81], w[9], N[36];
+              sym9_expand(St, A);
+              jacobi_eig_sym<9>(A, V, w);
+              int idx[4];
+              smallest_k<9>(w, 4, idx);
+              for (int k = 0; k < 4; ++k)
+                for (int e = 0; e < 9; ++e) N[k * 9 + e] = V[e * 9 + idx[3 - k]];
+              nc = five_point_from_nullspace(N, sh.cand_models);
+            } else if (KIND == 1) {
+              nc = finish_F8(St, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
+            } else {
+              nc = finish_H(St, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
+            }
+            sh.n_cand = nc;
+          }
+          __syncthreads();
+          const int nc = sh.n_cand;
+          for (int m = warp; m < nc; m += kRansacThreads / 32) {
+            double C[9];
+            for (int k = 0; k < 9; ++k) C[k] = sh.cand_models[m * 9 + k];
+            int c;
+            double s;
+            warp_score<KIND>(C, pts, off, n, X, thr, lane, c, s);
+            if (lane == 0) {
+              sh.cand_cnt[m] = c;
+              sh.cand_sum[m] = s;
+            }
+          }
+          __syncthreads();
+          if (tid == 0) {
+            int w = -1;
+            for (int m = 0; m < nc; ++m)
+              if (sh.cand_cnt[m] > sh.best_cnt || (sh.cand_cnt[m] == sh.best_cnt && sh.cand_sum[m] < sh.best_sum)) {
+                sh.best_cnt = sh.cand_cnt[m];
+                sh.best_sum = sh.cand_sum[m];
+                w = m;
+              }
+            if (w >= 0)
+              for (int k = 0; k < 9; ++k) sh.best_model[k] = sh.cand_models[w * 9 + k];
+          }
+          __syncthreads();
+          if (sh.best_cnt <= prev_best) break;
+        }
+      }
+      dyn_max = compute_num_trials(sh.best_cnt, n, ro.confidence, ro.dyn_num_trials_multiplier, T::kMin);
+    }
+    trials += nb;
+    __syncthreads();
+    if (trials >= dyn_max && trials >= ro.min_num_trials) break;
+  }
+
+  // ---- final inlier mask from the best model
+  double M[9];
+  for (int k = 0; k < 9; ++k) M[k] = sh.best_model[k];
+  const bool ok = sh.best_cnt >= T::kMin;
+  for (int i = tid; i < n; i += kRansacThreads) {
+    double x1, y1, x2, y2;
+    load_pt(pts, off + i, X, x1, y1, x2, y2);
+    mask[i] = (ok && residual<KIND>(M, x1, y1, x2, y2) <= thr) ? 1 : 0;
+  }
+  if (tid == 0) {
+    P.sup_cnt[out_idx] = sh.best_cnt;
+    P.success[out_idx] = ok ? 1 : 0;
+    for (int k = 0; k < 9; ++k) P.models[out_idx * 9 + k] = M[k];
+  }
+}
+
+__global__ void __launch_bounds__(kRansacThreads) b2m_ransac_kernel(const VerifyParams P) {
+  __shared__ Shared sh;
+  const int pair = blockIdx.x;
+  const int kind = P.single_kind >= 0 ? P.single_kind : static_cast<int>(blockIdx.y);
+  const int n = P.pair_cnt[pair];
+  const int64_t off = P.pair_off[pair];
+  const int i1 = P.pairs[2 * pair], i2 = P.pairs[2 * pair + 1];
+  const int out_idx = pair * 3 + kind;
+  const DevCamera c1 = P.cams[i1], c2 = P.cams[i2];
+  bool run = true;
+  if (P.single_kind < 0) {
+    const bool calibrated = c1.has_prior && c2.has_prior;
+    if (n < P.opt.min_num_inliers) run = false;             // EstimateTwoViewGeometry: DEGENERATE up front
+    if (P.opt.force_H_use && kind != 2) run = false;
+    if (kind == 0 && !calibrated) run = false;              // uncalibrated: F and H only
+  }
+  if (!run) {
+    if (threadIdx.x == 0) {
+      P.sup_cnt[out_idx] = 0;
+      P.success[out_idx] = 0;
+      for (int k = 0; k < 9; ++k) P.models[out_idx * 9 + k] = 0.0;
+    }
+    uint8_t* mask = P.mask + static_cast<int64_t>(kind) * P.arena_cap + off;
+    for (int i = threadIdx.x; i < n; i += kRansacThreads) mask[i] = 0;
+    return;
+  }
+  PointXform X = {1, 0, 1, 0, 1, 0, 1, 0};
+  double thr = P.opt.ransac.max_error * P.opt.ransac.max_error;
+  if (kind == 0 && P.single_kind < 0) {
+    // CamFromImg for (SIMPLE_)PINHOLE and the CamFromImgThreshold-averaged error (row V9)
+    X.ax1 = 1.0 / c1.fx; X.bx1 = -c1.cx / c1.fx; X.ay1 = 1.0 / c1.fy; X.by1 = -c1.cy / c1.fy;
+    X.ax2 = 1.0 / c2.fx; X.bx2 = -c2.cx / c2.fx; X.ay2 = 1.0 / c2.fy; X.by2 = -c2.cy / c2.fy;
+    const double e = 0.5 * (P.opt.ransac.max_error / c1.mean_f + P.opt.ransac.max_error / c2.mean_f);
+    thr = e * e;
+  }
+  const uint64_t key = splitmix64(P.seed ^ splitmix64((static_cast<uint64_t>(static_cast<uint32_t>(i1)) << 34) ^
+                                                        (static_cast<uint64_t>(static_cast<uint32_t>(i2)) << 2) ^
+                                                        static_cast<uint64_t>(kind)));
+  if (kind == 0) ransac_problem<0>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
+  else if (kind == 1) ransac_problem<1>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
+  else ransac_problem<2>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
+}
+
+// Decision tree of EstimateCalibrated/UncalibratedTwoViewGeometry, ExtractInlierMatches (ordered
+// compaction) and DetectWatermark.  One CTA per pair.
+__global__ void __launch_bounds__(256) b2m_decide_kernel(const VerifyParams P) {
+  const int pair = blockIdx.x;
+  const int n = P.pair_cnt[pair];
+  const int64_t off = P.pair_off[pair];
+  const int i1 = P.pairs[2 * pair], i2 = P.pairs[2 * pair + 1];
+  const DevCamera c1 = P.cams[i1], c2 = P.cams[i2];
+  const b2m_tvg_opts& o = P.opt;
+  __shared__ int s_cfg, s_kind, s_num, s_base, s_warp[8], s_border;
+  __shared__ double s_tsum[2];
+  __shared__ int s_tcnt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    int cfg = B2M_DEGENERATE, kind = -1, num = 0;
+    if (n >= o.min_num_inliers) {
+      const bool calibrated = c1.has_prior && c2.has_prior && !o.force_H_use;
+      const int nE = P.sup_cnt[pair * 3 + 0], nF = P.sup_cnt[pair * 3 + 1], nH = P.sup_cnt[pair * 3 + 2];
+      const bool okE = calibrated && P.success[pair * 3 + 0], okF = P.success[pair * 3 + 1] != 0,
+                 okH = P.success[pair * 3 + 2] != 0;
+      const int mn = o.min_num_inliers;
+      if (o.force_H_use) {
+        if (okH && nH >= mn) {
+          cfg = B2M_PLANAR_OR_PANORAMIC; kind = 2; num = nH;
+        }
+      } else if ((!okE && !okF && !okH) || (nE < mn && nF < mn && nH < mn)) {
+        cfg = B2M_DEGENERATE;
+      } else {
+        const double E_F = static_cast<double>(nE) / nF, H_F = static_cast<double>(nH) / nF,
+                     H_E = static_cast<double>(nH) / nE;
+        if (okE && E_F > o.min_E_F_inlier_ratio && nE >= mn) {
+          if (nE >= nF) { kind = 0; num = nE; } else { kind = 1; num = nF; }
+          if (H_E > o.max_H_inlier_ratio) {
+            cfg = B2M_PLANAR_OR_PANORAMIC;
+            if (nH > num) { kind = 2; num = nH; }
+          } else {
+            cfg = B2M_CALIBRATED;
+          }
+        } else if (okF && nF >= mn) {
+          kind = 1; num = nF;
+          if (H_F > o.max_H_inlier_ratio) {
+            cfg = B2M_PLANAR_OR_PANORAMIC;
+            if (nH > num) { kind = 2; num = nH; }
+          } else {
+            cfg = B2M_UNCALIBRATED;
+          }
+        } else if (okH && nH >= mn) {
+          kind = 2; num = nH; cfg = B2M_PLANAR_OR_PANORAMIC;
+        } else {
+          cfg = B2M_DEGENERATE;
+        }
+      }
+    }
+    s_cfg = cfg; s_kind = kind; s_num = num; s_base = 0; s_border = 0;
+    s_tsum[0] = s_tsum[1] = 0.0; s_tcnt = 0;
+  }
+  __syncthreads();
+  const int kind = s_kind;
+  if (kind < 0) {
+    if (tid == 0) {
+      P.config[pair] = s_cfg;
+      P.inl_cnt[pair] = 0;
+    }
+    return;
+  }
+  const uint8_t* mask = P.mask + static_cast<int64_t>(kind) * P.arena_cap + off;
+  // ordered compaction of the inlier matches + border statistics for the watermark test
+  const double d1 = o.watermark_border_size * sqrt(static_cast<double>(c1.width) * c1.width + static_cast<double>(c1.height) * c1.height);
+  const double d2 = o.watermark_border_size * sqrt(static_cast<double>(c2.width) * c2.width + static_cast<double>(c2.height) * c2.height);
+  int border_local = 0;
+  for (int i0 = 0; i0 < n; i0 += 256) {
+    const int i = i0 + tid;
+    const bool keep = i < n && mask[i] != 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int base = s_base;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    if (keep) {
+      P.inliers[off + base + __popc(ballot & ((1u << lane) - 1u))] = P.matches[off + i];
+      const double4 p = P.pts[off + i];
+      const bool b1 = p.x < d1 || p.x > c1.width - d1 || p.y < d1 || p.y > c1.height - d1;
+      const bool b2 = p.z < d2 || p.z > c2.width - d2 || p.w < d2 || p.w > c2.height - d2;
+      border_local += (b1 && b2) ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += s_warp[w];
+      s_base += t;
+    }
+    __syncthreads();
+  }
+  border_local = __reduce_add_sync(0xffffffffu, border_local);
+  if (lane == 0) atomicAdd(&s_border, border_local);
+  __syncthreads();
+  int cfg = s_cfg;
+  const int num = s_base;
+  // DetectWatermark: enough inliers in the border region of BOTH images, then a pure 2-D
+  // translation must explain >= watermark_min_inlier_ratio of all inliers.
+  if (o.detect_watermark && num > 0 &&
+      static_cast<double>(s_border) / num >= o.watermark_min_inlier_ratio) {
+    // LO-RANSAC<Translation, Translation> on the border inliers; with kMinNumSamples = 1 every
+    // border inlier is a hypothesis: evaluate them all (exhaustive instead of sampled), then refit
+    // on the inliers of the best (local optimisation), keeping the better of the two.
+    const double thr = o.ransac.max_error * o.ransac.max_error;
+    __shared__ int s_best_cnt;
+    __shared__ double s_best_t[2];
+    __shared__ unsigned long long s_best_key;
+    if (tid == 0) {
+      s_best_cnt = 0;
+      s_best_key = 0ull;
+    }
+    __syncthreads();
+    const int nbp = s_border;
+    // hypotheses: border inlier h -> t = p2 - p1; support counted over border inliers
+    for (int h0 = 0; h0 < n; h0 += 256) {
+      const int h = h0 + tid;
+      bool is_b = false;
+      double tx = 0, ty = 0;
+      if (h < n && mask[h]) {
+        const double4 p = P.pts[off + h];
+        const bool b1 = p.x < d1 || p.x > c1.width - d1 || p.y < d1 || p.y > c1.height - d1;
+        const bool b2 = p.z < d2 || p.z > c2.width - d2 || p.w < d2 || p.w > c2.height - d2;
+        is_b = b1 && b2;
+        tx = p.z - p.x;
+        ty = p.w - p.y;
+      }
+      if (is_b) {
+        int c = 0;
+        for (int i = 0; i < n; ++i) {
+          if (!mask[i]) continue;
+          const double4 q = P.pts[off + i];
+          const bool qb1 = q.x < d1 || q.x > c1.width - d1 || q.y < d1 || q.y > c1.height - d1;
+          const bool qb2 = q.z < d2 || q.z > c2.width - d2 || q.w < d2 || q.w > c2.height - d2;
+          if (!(qb1 && qb2)) continue;
+          const double ex = q.z - (q.x + tx), ey = q.w - (q.y + ty);
+          c += (ex * ex + ey * ey <= thr) ? 1 : 0;
+        }
+        const unsigned long long key = (static_cast<unsigned long long>(c) << 32) | static_cast<unsigned>(n - h);
+        atomicMax(&s_best_key, key);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && s_best_key != 0ull) {
+      const int h = n - static_cast<int>(s_best_key & 0xffffffffull);
+      const double4 p = P.pts[off + h];
+      double tx = p.z - p.x, ty = p.w - p.y;
+      int bc = static_cast<int>(s_best_key >> 32);
+      for (int it = 0; it < kMaxLocalTrials; ++it) {
+        double sx = 0, sy = 0;
+        int c = 0;
+        for (int i = 0; i < n; ++i) {
+          if (!mask[i]) continue;
+          const double4 q = P.pts[off + i];
+          const bool qb1 = q.x < d1 || q.x > c1.width - d1 || q.y < d1 || q.y > c1.height - d1;
+          const bool qb2 = q.z < d2 || q.z > c2.width - d2 || q.w < d2 || q.w > c2.height - d2;
+          if (!(qb1 && qb2)) continue;
+          const double ex = q.z - (q.x + tx), ey = q.w - (q.y + ty);
+          if (ex * ex + ey * ey <= thr) {
+            sx += q.z - q.x;
+            sy += q.w - q.y;
+            ++c;
+          }
+        }
+        if (c == 0) break;
+        const double ntx = sx / c, nty = sy / c;
+        int c2n = 0;
+        for (int i = 0; i < n; ++i) {
+          if (!mask[i]) continue;
+          const double4 q = P.pts[off + i];
+          const bool qb1 = q.x < d1 || q.x > c1.width - d1 || q.y < d1 || q.y > c1.height - d1;
+          const bool qb2 = q.z < d2 || q.z > c2.width - d2 || q.w < d2 || q.w > c2.height - d2;
+          if (!(qb1 && qb2)) continue;
+          const double ex = q.z - (q.x + ntx), ey = q.w - (q.y + nty);
+          c2n += (ex * ex + ey * ey <= thr) ? 1 : 0;
+        }
+        if (c2n > bc) {
+          bc = c2n;
+          tx = ntx;
+          ty = nty;
+        } else {
+          break;
+        }
+      }
+      s_best_cnt = bc;
+      (void)nbp;
+    }
+    __syncthreads();
+    if (s_best_cnt >= 1 && static_cast<double>(s_best_cnt) / num >= o.watermark_min_inlier_ratio) cfg = B2M_WATERMARK;
+  }
+  if (tid == 0) {
+    P.config[pair] = cfg;
+    P.inl_cnt[pair] = num;
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+
+struct VerifyState {
+  int batch = 0;
+  int64_t arena_cap = 0;
+  double4* d_pts[2] = {nullptr, nullptr};
+  uint8_t* d_mask = nullptr;      // [3][arena_cap], shared by both slots (stream-ordered)
+  double* d_models[2] = {nullptr, nullptr};
+  int32_t* d_sup = nullptr;
+  int32_t* d_success = nullptr;
+  int32_t* d_config[2] = {nullptr, nullptr};
+  int32_t* d_inl_cnt[2] = {nullptr, nullptr};
+  uint2* d_inliers[2] = {nullptr, nullptr};
+  double* h_models[2] = {nullptr, nullptr};
+  int32_t* h_config[2] = {nullptr, nullptr};
+  int32_t* h_inl_cnt[2] = {nullptr, nullptr};
+  uint2* h_inliers[2] = {nullptr, nullptr};
+  DevCamera* d_cams = nullptr;
+  int n_cams = 0;
+  const void* cams_of = nullptr;  // ImageSet the cameras were uploaded for
+  void release() {
+    for (int s = 0; s < 2; ++s) {
+      cudaFree(d_pts[s]); cudaFree(d_models[s]); cudaFree(d_config[s]); cudaFree(d_inl_cnt[s]); cudaFree(d_inliers[s]);
+      cudaFreeHost(h_models[s]); cudaFreeHost(h_config[s]); cudaFreeHost(h_inl_cnt[s]); cudaFreeHost(h_inliers[s]);
+      d_pts[s] = nullptr; d_models[s] = nullptr; d_config[s] = nullptr; d_inl_cnt[s] = nullptr; d_inliers[s] = nullptr;
+      h_models[s] = nullptr; h_config[s] = nullptr; h_inl_cnt[s] = nullptr; h_inliers[s] = nullptr;
+    }
+    cudaFree(d_mask); cudaFree(d_sup); cudaFree(d_success); cudaFree(d_cams);
+    d_mask = nullptr; d_sup = nullptr; d_success = nullptr; d_cams = nullptr;
+    batch = 0; arena_cap = 0; n_cams = 0; cams_of = nullptr;
+  }
+};
+
+VerifyState* vstate(b2m_ctx* ctx) {
+  if (!ctx->verify_state) ctx->verify_state = new VerifyState();
+  return static_cast<VerifyState*>(ctx->verify_state);
+}
+
+#define V_TRY(ctx, expr)                                                                    \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      char _b[512];                                                                         \
+      snprintf(_b, sizeof(_b), "[%s:%d] CUDA error: %s (%s)", __FILE__, __LINE__,          \
+               cudaGetErrorString(_e), #expr);                                              \
+      (ctx)->err = _b;                                                                      \
+      return _e == cudaErrorMemoryAllocation ? B2M_ENOMEM : B2M_ECUDA;                      \
+    }                                                                                       \
+  } while (0)
+
+DevCamera to_dev(const b2m_camera& c) {
+  DevCamera d{};
+  if (c.model == 0) {
+    d.fx = d.fy = c.params[0]; d.cx = c.params[1]; d.cy = c.params[2]; d.mean_f = c.params[0];
+  } else {
+    d.fx = c.params[0]; d.fy = c.params[1]; d.cx = c.params[2]; d.cy = c.params[3];
+    d.mean_f = 0.5 * (c.params[0] + c.params[1]);
+  }
+  d.width = c.width; d.height = c.height; d.has_prior = c.has_prior_focal_length;
+  return d;
+}
+
+int ensure_verify_ws(b2m_ctx* ctx, int batch, int64_t arena_cap) {
+  VerifyState* V = vstate(ctx);
+  if (V->batch >= batch && V->arena_cap >= arena_cap) return B2M_OK;
+  DevCamera* keep_cams = V->d_cams;
+  const int keep_n = V->n_cams;
+  const void* keep_of = V->cams_of;
+  V->d_cams = nullptr;
+  V->release();
+  V->d_cams = keep_cams; V->n_cams = keep_n; V->cams_of = keep_of;
+  for (int s = 0; s < 2; ++s) {
+    V_TRY(ctx, cudaMalloc(&V->d_pts[s], sizeof(double4) * arena_cap));
+    V_TRY(ctx, cudaMalloc(&V->d_models[s], sizeof(double) * 27 * batch));
+    V_TRY(ctx, cudaMalloc(&V->d_config[s], sizeof(int32_t) * batch));
+    V_TRY(ctx, cudaMalloc(&V->d_inl_cnt[s], sizeof(int32_t) * batch));
+    V_TRY(ctx, cudaMalloc(&V->d_inliers[s], sizeof(uint2) * arena_cap));
+    V_TRY(ctx, cudaMallocHost(&V->h_models[s], sizeof(double) * 27 * batch));
+    V_TRY(ctx, cudaMallocHost(&V->h_config[s], sizeof(int32_t) * batch));
+    V_TRY(ctx, cudaMallocHost(&V->h_inl_cnt[s], sizeof(int32_t) * batch));
+    V_TRY(ctx, cudaMallocHost(&V->h_inliers[s], sizeof(uint2) * arena_cap));
+  }
+  V_TRY(ctx, cudaMalloc(&V->d_mask, 3 * arena_cap));
+  V_TRY(ctx, cudaMalloc(&V->d_sup, sizeof(int32_t) * 3 * batch));
+  V_TRY(ctx, cudaMalloc(&V->d_success, sizeof(int32_t) * 3 * batch));
+  V->batch = batch;
+  V->arena_cap = arena_cap;
+  return B2M_OK;
+}
+
+}  // namespace
+
+void* verify_points_arena(b2m_ctx* ctx, int s) {
+  VerifyState* V = vstate(ctx);
+  return V->d_pts[s];
+}
+
+int verify_prepare(b2m_ctx* ctx, ImageSet& S, int batch, int64_t arena_cap) {
+  if (int rc = ensure_verify_ws(ctx, batch, arena_cap)) return rc;
+  VerifyState* V = vstate(ctx);
+  if (V->cams_of != S.d_desc || V->n_cams != S.n_images) {
+    cudaFree(V->d_cams);
+    V->d_cams = nullptr;
+    std::vector<DevCamera> dc(S.n_images);
+    for (int i = 0; i < S.n_images; ++i) dc[i] = to_dev(S.cams[i]);
+    V_TRY(ctx, cudaMalloc(&V->d_cams, sizeof(DevCamera) * std::max(1, S.n_images)));
+    V_TRY(ctx, cudaMemcpyAsync(V->d_cams, dc.data(), sizeof(DevCamera) * S.n_images, cudaMemcpyHostToDevice,
+                               ctx->stream));
+    V_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    V->n_cams = S.n_images;
+    V->cams_of = S.d_desc;
+  }
+  return B2M_OK;
+}
+
 void verify_results_init(b2m_results* res, int64_t n_pairs) {
   res->verified = true;
   res->config.assign(n_pairs, B2M_UNDEFINED);
@@ -9,29 +737,309 @@ void verify_results_init(b2m_results* res, int64_t n_pairs) {
   res->in_cnt.assign(n_pairs, 0);
   res->models.assign(27 * n_pairs, 0.0);
 }
-int verify_batch_launch(b2m_ctx* ctx, ImageSet&, const b2m_tvg_opts*, const b2m_sift_opts*, int, int64_t, int) {
-  ctx->err = "[verify.cu] two-view verification kernels not built yet";
-  return B2M_ESTATE;
+
+int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, const b2m_sift_opts*, int s, int64_t p0,
+                        int nb) {
+  VerifyState* V = vstate(ctx);
+  Workspace& W = ctx->ws;
+  VerifyParams P{};
+  P.pairs = ctx->d_pairs + 2 * p0;
+  P.pair_off = W.d_pair_off[s];
+  P.pair_cnt = W.d_pair_cnt[s];
+  P.pts = V->d_pts[s];
+  P.matches = W.d_arena[s];
+  P.cams = V->d_cams;
+  P.mask = V->d_mask;
+  P.arena_cap = V->arena_cap;
+  P.models = V->d_models[s];
+  P.sup_cnt = V->d_sup;
+  P.success = V->d_success;
+  P.config = V->d_config[s];
+  P.inl_cnt = V->d_inl_cnt[s];
+  P.inliers = V->d_inliers[s];
+  P.opt = *tvg;
+  P.seed = ctx->seed;
+  P.single_kind = -1;
+  P.force_calibrated = -1;
+  (void)S;
+  b2m_ransac_kernel<<<dim3(nb, 3), kRansacThreads, 0, ctx->stream>>>(P);
+  V_TRY(ctx, cudaGetLastError());
+  b2m_decide_kernel<<<nb, 256, 0, ctx->stream>>>(P);
+  V_TRY(ctx, cudaGetLastError());
+  ctx->stats.kernel_launches += 2;
+  return B2M_OK;
 }
-int verify_batch_download(b2m_ctx*, b2m_results*, int, int64_t, int) { return B2M_OK; }
-int verify_batch_collect(b2m_ctx*, b2m_results*, int, int64_t, int) { return B2M_OK; }
-void verify_release(b2m_ctx*) {}
+
+int verify_batch_download(b2m_ctx* ctx, b2m_results*, int s, int64_t, int nb) {
+  VerifyState* V = vstate(ctx);
+  Workspace& W = ctx->ws;
+  const unsigned long long total = *W.h_cursor[s];
+  V_TRY(ctx, cudaMemcpyAsync(V->h_models[s], V->d_models[s], sizeof(double) * 27 * nb, cudaMemcpyDeviceToHost,
+                             ctx->copy_stream));
+  V_TRY(ctx, cudaMemcpyAsync(V->h_config[s], V->d_config[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost,
+                             ctx->copy_stream));
+  V_TRY(ctx, cudaMemcpyAsync(V->h_inl_cnt[s], V->d_inl_cnt[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost,
+                             ctx->copy_stream));
+  if (total > 0)
+    V_TRY(ctx, cudaMemcpyAsync(V->h_inliers[s], V->d_inliers[s], sizeof(uint2) * total, cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+  return B2M_OK;
+}
+
+int verify_batch_collect(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int nb, int min_num_inliers) {
+  VerifyState* V = vstate(ctx);
+  Workspace& W = ctx->ws;
+  for (int k = 0; k < nb; ++k) {
+    const int64_t p = p0 + k;
+    int cfg = V->h_config[s][k];
+    int ni = V->h_inl_cnt[s][k];
+    // FeatureMatcherController::Match write rule (row P3): raw matches below min_num_inliers are
+    // stored empty (the verifier never ran: default TwoViewGeometry); geometries with fewer than
+    // min_num_inliers inliers are stored as the default TwoViewGeometry (config UNDEFINED).
+    if (res->cnt[p] < min_num_inliers) {
+      res->cnt[p] = 0;
+      cfg = B2M_UNDEFINED;
+      ni = 0;
+    }
+    if (ni < min_num_inliers) {
+      cfg = B2M_UNDEFINED;
+      ni = 0;
+    }
+    res->config[p] = cfg;
+    res->in_cnt[p] = ni;
+    res->in_off[p] = static_cast<int64_t>(res->inliers.size() / 2);
+    if (ni > 0) {
+      const uint2* src = V->h_inliers[s] + W.h_pair_off[s][k];
+      const size_t at = res->inliers.size();
+      res->inliers.resize(at + 2 * static_cast<size_t>(ni));
+      memcpy(res->inliers.data() + at, src, sizeof(uint2) * ni);
+      memcpy(res->models.data() + 27 * p, V->h_models[s] + 27 * k, sizeof(double) * 27);
+    }
+  }
+  return B2M_OK;
+}
+
+void verify_release(b2m_ctx* ctx) {
+  if (ctx->verify_state) {
+    VerifyState* V = static_cast<VerifyState*>(ctx->verify_state);
+    V->release();
+    delete V;
+    ctx->verify_state = nullptr;
+  }
+}
+
+// ---- stand-alone estimators ------------------------------------------------------------------
+
+namespace {
+
+struct Single {
+  double4* d_pts = nullptr;
+  uint2* d_matches = nullptr;
+  uint2* d_inliers = nullptr;
+  uint8_t* d_mask = nullptr;
+  DevCamera* d_cams = nullptr;
+  int32_t* d_i32 = nullptr;   // pairs[2], cnt[1], sup[3], success[3], config[1], inl_cnt[1]
+  int64_t* d_off = nullptr;
+  double* d_models = nullptr;
+  ~Single() {
+    cudaFree(d_pts); cudaFree(d_matches); cudaFree(d_inliers); cudaFree(d_mask); cudaFree(d_cams);
+    cudaFree(d_i32); cudaFree(d_off); cudaFree(d_models);
+  }
+};
+
+int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<uint2>& matches, const DevCamera cams[2],
+               const b2m_tvg_opts& opt, int single_kind, Single& G, VerifyParams& P) {
+  const int64_t m = static_cast<int64_t>(pts.size());
+  const int64_t cap = std::max<int64_t>(m, 1);
+  V_TRY(ctx, cudaMalloc(&G.d_pts, sizeof(double4) * cap));
+  V_TRY(ctx, cudaMalloc(&G.d_matches, sizeof(uint2) * cap));
+  V_TRY(ctx, cudaMalloc(&G.d_inliers, sizeof(uint2) * cap));
+  V_TRY(ctx, cudaMalloc(&G.d_mask, 3 * cap));
+  V_TRY(ctx, cudaMalloc(&G.d_cams, sizeof(DevCamera) * 2));
+  V_TRY(ctx, cudaMalloc(&G.d_i32, sizeof(int32_t) * 16));
+  V_TRY(ctx, cudaMalloc(&G.d_off, sizeof(int64_t)));
+  V_TRY(ctx, cudaMalloc(&G.d_models, sizeof(double) * 27));
+  const int32_t i32[16] = {0, 1, static_cast<int32_t>(m), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const int64_t off0 = 0;
+  cudaStream_t st = ctx->stream;
+  if (m > 0) {
+    V_TRY(ctx, cudaMemcpyAsync(G.d_pts, pts.data(), sizeof(double4) * m, cudaMemcpyHostToDevice, st));
+    V_TRY(ctx, cudaMemcpyAsync(G.d_matches, matches.data(), sizeof(uint2) * m, cudaMemcpyHostToDevice, st));
+  }
+  V_TRY(ctx, cudaMemcpyAsync(G.d_cams, cams, sizeof(DevCamera) * 2, cudaMemcpyHostToDevice, st));
+  V_TRY(ctx, cudaMemcpyAsync(G.d_i32, i32, sizeof(i32), cudaMemcpyHostToDevice, st));
+  V_TRY(ctx, cudaMemcpyAsync(G.d_off, &off0, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  V_TRY(ctx, cudaMemsetAsync(G.d_models, 0, sizeof(double) * 27, st));
+  P = VerifyParams{};
+  P.pairs = G.d_i32;
+  P.pair_cnt = G.d_i32 + 2;
+  P.sup_cnt = G.d_i32 + 3;
+  P.success = G.d_i32 + 6;
+  P.config = G.d_i32 + 9;
+  P.inl_cnt = G.d_i32 + 10;
+  P.pair_off = G.d_off;
+  P.pts = G.d_pts;
+  P.matches = G.d_matches;
+  P.cams = G.d_cams;
+  P.mask = G.d_mask;
+  P.arena_cap = cap;
+  P.models = G.d_models;
+  P.inliers = G.d_inliers;
+  P.opt = opt;
+  P.seed = ctx->seed;
+  P.single_kind = single_kind;
+  if (single_kind >= 0) {
+    b2m_ransac_kernel<<<dim3(1, 1), kRansacThreads, 0, st>>>(P);
+  } else {
+    b2m_ransac_kernel<<<dim3(1, 3), kRansacThreads, 0, st>>>(P);
+    V_TRY(ctx, cudaGetLastError());
+    b2m_decide_kernel<<<1, 256, 0, st>>>(P);
+    ctx->stats.kernel_launches += 1;
+  }
+  V_TRY(ctx, cudaGetLastError());
+  ctx->stats.kernel_launches += 1;
+  return B2M_OK;
+}
+
+__global__ void b2m_sampson_kernel(const double* p1, const double* p2, int64_t m, const double* E, double* out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= m) return;
+  double M[9];
+  for (int k = 0; k < 9; ++k) M[k] = E[k];
+  out[i] = sampson_sq(M, p1[2 * i], p1[2 * i + 1], p2[2 * i], p2[2 * i + 1]);
+}
+
+}  // namespace
 }  // namespace b2m
 
+using namespace b2m;
+
 extern "C" {
-int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera*, const double*, int64_t, const b2m_camera*,
-                                   const double*, int64_t, const uint32_t*, int64_t, const b2m_tvg_opts*,
-                                   b2m_tvg_result*, uint32_t*) {
-  if (ctx) ctx->err = "[verify.cu] not built yet";
-  return B2M_ESTATE;
+
+int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const double* points1, int64_t n1,
+                                   const b2m_camera* cam2, const double* points2, int64_t n2,
+                                   const uint32_t* matches, int64_t m, const b2m_tvg_opts* opts,
+                                   b2m_tvg_result* out, uint32_t* inlier_matches) {
+  if (!ctx) return B2M_EINVAL;
+  auto bad = [&](const char* msg) {
+    ctx->err = msg;
+    return B2M_EINVAL;
+  };
+  if (!cam1 || !cam2 || !opts || !out) return bad("[verify.cu] Check Failed: cameras, options and out != NULL");
+  if (n1 < 0 || n2 < 0 || (n1 > 0 && !points1) || (n2 > 0 && !points2)) return bad("[verify.cu] Check Failed: points");
+  if (opts->multiple_models) return bad("[verify.cu] multiple_models is not supported (SURVEY.md section 8(f) item 4)");
+  if (!matches) {  // identity matching (R:estimators/two_view_geometry.h:136-142)
+    if (n1 != n2) return bad("[verify.cu] Check Failed: points1.size() == points2.size()");
+    m = n1;
+  }
+  if (m < 0) return bad("[verify.cu] Check Failed: m >= 0");
+  cudaSetDevice(ctx->device);
+  std::vector<double4> pts(m);
+  std::vector<uint2> mm(m);
+  for (int64_t i = 0; i < m; ++i) {
+    const uint32_t a = matches ? matches[2 * i] : static_cast<uint32_t>(i);
+    const uint32_t b = matches ? matches[2 * i + 1] : static_cast<uint32_t>(i);
+    if (a >= n1 || b >= n2) return bad("[verify.cu] Check Failed: match index < number of points");
+    pts[i] = make_double4(points1[2 * a], points1[2 * a + 1], points2[2 * b], points2[2 * b + 1]);
+    mm[i] = make_uint2(a, b);
+  }
+  const DevCamera cams[2] = {to_dev(*cam1), to_dev(*cam2)};
+  Single G;
+  VerifyParams P;
+  if (int rc = run_single(ctx, pts, mm, cams, *opts, -1, G, P)) return rc;
+  int32_t i32[16];
+  double models[27];
+  V_TRY(ctx, cudaMemcpyAsync(i32, G.d_i32, sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
+  V_TRY(ctx, cudaMemcpyAsync(models, G.d_models, sizeof(models), cudaMemcpyDeviceToHost, ctx->stream));
+  V_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  memset(out, 0, sizeof(*out));
+  out->struct_size = sizeof(*out);
+  out->config = i32[9];
+  out->n_inliers = i32[10];
+  out->nE = i32[3]; out->nF = i32[4]; out->nH = i32[5];
+  memcpy(out->E, models, sizeof(double) * 9);
+  memcpy(out->F, models + 9, sizeof(double) * 9);
+  memcpy(out->H, models + 18, sizeof(double) * 9);
+  if (out->n_inliers > 0 && inlier_matches) {
+    V_TRY(ctx, cudaMemcpy(inlier_matches, G.d_inliers, sizeof(uint2) * out->n_inliers, cudaMemcpyDeviceToHost));
+  }
+  return B2M_OK;
 }
-int b2m_ransac_model(b2m_ctx* ctx, int32_t, const double*, const double*, int64_t, const b2m_ransac_opts*, double*,
-                     uint8_t*, int64_t*, int32_t*) {
-  if (ctx) ctx->err = "[verify.cu] not built yet";
-  return B2M_ESTATE;
+
+int b2m_ransac_model(b2m_ctx* ctx, int32_t kind, const double* points1, const double* points2, int64_t m,
+                     const b2m_ransac_opts* opts, double* out_model, uint8_t* inlier_mask, int64_t* num_inliers,
+                     int32_t* success) {
+  if (!ctx) return B2M_EINVAL;
+  auto bad = [&](const char* msg) {
+    ctx->err = msg;
+    return B2M_EINVAL;
+  };
+  if (kind < 0 || kind > 2) return bad("[verify.cu] Check Failed: kind in {0 (E), 1 (F), 2 (H)}");
+  if (!opts || !out_model || !num_inliers || !success) return bad("[verify.cu] Check Failed: outputs != NULL");
+  if (m < 0 || (m > 0 && (!points1 || !points2))) return bad("[verify.cu] Check Failed: points");
+  cudaSetDevice(ctx->device);
+  std::vector<double4> pts(m);
+  std::vector<uint2> mm(m);
+  for (int64_t i = 0; i < m; ++i) {
+    pts[i] = make_double4(points1[2 * i], points1[2 * i + 1], points2[2 * i], points2[2 * i + 1]);
+    mm[i] = make_uint2(static_cast<uint32_t>(i), static_cast<uint32_t>(i));
+  }
+  b2m_tvg_opts t;
+  b2m_tvg_opts_default(&t);
+  t.ransac = *opts;
+  DevCamera cams[2];
+  memset(cams, 0, sizeof(cams));
+  cams[0].fx = cams[0].fy = cams[0].mean_f = 1.0;
+  cams[1] = cams[0];
+  Single G;
+  VerifyParams P;
+  if (int rc = run_single(ctx, pts, mm, cams, t, kind, G, P)) return rc;
+  int32_t i32[16];
+  double models[27];
+  V_TRY(ctx, cudaMemcpyAsync(i32, G.d_i32, sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
+  V_TRY(ctx, cudaMemcpyAsync(models, G.d_models, sizeof(models), cudaMemcpyDeviceToHost, ctx->stream));
+  if (m > 0 && inlier_mask)
+    V_TRY(ctx, cudaMemcpyAsync(inlier_mask, G.d_mask + static_cast<int64_t>(kind) * P.arena_cap, m,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  V_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *num_inliers = i32[3 + kind];
+  *success = i32[6 + kind];
+  memcpy(out_model, models + 9 * kind, sizeof(double) * 9);
+  return B2M_OK;
 }
-int b2m_squared_sampson_error(b2m_ctx* ctx, const double*, const double*, int64_t, const double*, double*) {
-  if (ctx) ctx->err = "[verify.cu] not built yet";
-  return B2M_ESTATE;
+
+int b2m_squared_sampson_error(b2m_ctx* ctx, const double* points1, const double* points2, int64_t m, const double* E,
+                              double* out_residuals) {
+  if (!ctx) return B2M_EINVAL;
+  if (m < 0 || (m > 0 && (!points1 || !points2 || !out_residuals)) || !E) {
+    ctx->err = "[verify.cu] Check Failed: points, E, out != NULL";
+    return B2M_EINVAL;
+  }
+  if (m == 0) return B2M_OK;
+  cudaSetDevice(ctx->device);
+  double *d1 = nullptr, *d2 = nullptr, *dE = nullptr, *dout = nullptr;
+  int rc = B2M_OK;
+  auto cleanup = [&]() {
+    cudaFree(d1); cudaFree(d2); cudaFree(dE); cudaFree(dout);
+  };
+  if (cudaMalloc(&d1, sizeof(double) * 2 * m) != cudaSuccess || cudaMalloc(&d2, sizeof(double) * 2 * m) != cudaSuccess ||
+      cudaMalloc(&dE, sizeof(double) * 9) != cudaSuccess || cudaMalloc(&dout, sizeof(double) * m) != cudaSuccess) {
+    cleanup();
+    ctx->err = "[verify.cu] cudaMalloc failed";
+    return B2M_ENOMEM;
+  }
+  cudaMemcpyAsync(d1, points1, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d2, points2, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dE, E, sizeof(double) * 9, cudaMemcpyHostToDevice, ctx->stream);
+  b2m_sampson_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, ctx->stream>>>(d1, d2, m, dE, dout);
+  ctx->stats.kernel_launches += 1;
+  cudaMemcpyAsync(out_residuals, dout, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = std::string("[verify.cu] CUDA error: ") + cudaGetErrorString(cudaGetLastError());
+    rc = B2M_ECUDA;
+  }
+  cleanup();
+  return rc;
 }
-}
+
+}  // extern "C"

@@ -21,6 +21,9 @@ int gh_estimate_F8(const double* x1, const double* y1, const double* x2, const d
 int gh_estimate_H(const double* x1, const double* y1, const double* x2, const double* y2, int n, double* model) {
   return estimate_H(x1, y1, x2, y2, n, model);
 }
+int gh_minimal_E5(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_E5(x1, y1, x2, y2, m); }
+int gh_minimal_F7(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_F7(x1, y1, x2, y2, m); }
+int gh_minimal_H4(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_H4(x1, y1, x2, y2, m); }
 double gh_sampson(const double* E, double x1, double y1, double x2, double y2) { return sampson_sq(E, x1, y1, x2, y2); }
 double gh_homography(const double* H, double x1, double y1, double x2, double y2) { return homography_sq(H, x1, y1, x2, y2); }
 double gh_num_trials(double ni, double ns, double conf, double mult, int k) { return compute_num_trials(ni, ns, conf, mult, k); }

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -112,6 +113,9 @@ int ensure_workspace(b2m_ctx* ctx, int batch, int32_t mstride) {
   mstride = std::max(mstride, W.mstride);
   const size_t arena_matches = static_cast<size_t>(batch) * mstride;
   CU_TRY(ctx, cudaMalloc(&W.d_mbuf, sizeof(int32_t) * 2 * arena_matches));
+  CU_TRY(ctx, cudaMalloc(&W.d_aux, sizeof(uint2) * 2 * arena_matches));
+  CU_TRY(ctx, cudaMalloc(&W.d_cand_rows, sizeof(int32_t) * 2 * arena_matches));
+  CU_TRY(ctx, cudaMalloc(&W.d_cand_cnt, sizeof(int32_t) * 2 * batch));
   for (int s = 0; s < 2; ++s) {
     CU_TRY(ctx, cudaMalloc(&W.d_arena[s], sizeof(uint2) * arena_matches));
     CU_TRY(ctx, cudaMalloc(&W.d_cursor[s], sizeof(unsigned long long)));
@@ -208,6 +212,8 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     {
       float k1ms = 0.f;
       if (cudaEventElapsedTime(&k1ms, ctx->ev_k1a[s], ctx->ev_k1b[s]) == cudaSuccess) ctx->stats.last_k1_ms += k1ms;
+      float vms = 0.f;  // compaction + verification kernels of this batch
+      if (cudaEventElapsedTime(&vms, ctx->ev_k1b[s], ctx->ev_k[s]) == cudaSuccess) verify_ms += vms;
     }
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[s], 0));
     CU_TRY(ctx, cudaMemcpyAsync(W.h_pair_off[s], W.d_pair_off[s], sizeof(int64_t) * nb, cudaMemcpyDeviceToHost,
@@ -254,8 +260,16 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     mp.acos_lut = ctx->d_lut;
     mp.max_ratio = sift->max_ratio;
     mp.max_distance = sift->max_distance;
+    mp.aux = W.d_aux;
+    mp.cand_cnt = W.d_cand_cnt;
+    mp.cand_rows = W.d_cand_rows;
     CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
-    CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
+    if (ctx->exact_k1) {
+      CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
+    } else {
+      CU_TRY_R(launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, st));
+      ctx->stats.kernel_launches += 1;
+    }
     CU_TRY_R(cudaEventRecord(ctx->ev_k1b[s], st));
     ctx->stats.kernel_launches += 1;
     ctx->stats.last_k1_launches += 1;
@@ -317,7 +331,13 @@ void ImageSet::release() {
 }
 void Workspace::release() {
   if (d_mbuf) cudaFree(d_mbuf);
+  if (d_aux) cudaFree(d_aux);
+  if (d_cand_cnt) cudaFree(d_cand_cnt);
+  if (d_cand_rows) cudaFree(d_cand_rows);
   d_mbuf = nullptr;
+  d_aux = nullptr;
+  d_cand_cnt = nullptr;
+  d_cand_rows = nullptr;
   for (int s = 0; s < 2; ++s) {
     if (d_arena[s]) cudaFree(d_arena[s]);
     if (d_cursor[s]) cudaFree(d_cursor[s]);
@@ -421,7 +441,7 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
   CU_TRY_C(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU_TRY_C(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (int s = 0; s < 2; ++s) {
-    CU_TRY_C(cudaEventCreateWithFlags(&ctx->ev_k[s], cudaEventDisableTiming));
+    CU_TRY_C(cudaEventCreate(&ctx->ev_k[s]));
     CU_TRY_C(cudaEventCreateWithFlags(&ctx->ev_data[s], cudaEventDisableTiming));
   }
   for (int s = 0; s < 2; ++s) {
@@ -437,6 +457,12 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
     std::vector<float> lut(262145);
     const float kDistNorm = 1.0f / (512.0f * 512.0f);
     for (int d = 0; d <= 262144; ++d) lut[d] = acosf(std::min(kDistNorm * static_cast<float>(d), 1.0f));
+    // K1 v2 rejects rows against a lower bound of the second-best dot product, which is exact only
+    // if the tabulated acos is non-increasing; otherwise (or on request) use the exact epilogue.
+    bool monotone = true;
+    for (int d = 1; d <= 262144; ++d) monotone &= (lut[d] <= lut[d - 1]);
+    const char* env = getenv("B2M_EXACT_K1");
+    ctx->exact_k1 = !monotone || (env && env[0] == '1');
     CU_TRY_C(cudaMalloc(&ctx->d_lut, sizeof(float) * lut.size()));
     CU_TRY_C(cudaMemcpy(ctx->d_lut, lut.data(), sizeof(float) * lut.size(), cudaMemcpyHostToDevice));
   }

@@ -33,6 +33,9 @@ struct Workspace {
   int batch = 0;
   int32_t mstride = 0;
   int32_t* d_mbuf = nullptr;
+  uint2* d_aux = nullptr;          // K1 v2: (best, S1) per candidate row
+  int32_t* d_cand_cnt = nullptr;   // K1 v2: [batch][2]
+  int32_t* d_cand_rows = nullptr;  // K1 v2: [batch][2][mstride]
   uint2* d_arena[2] = {nullptr, nullptr};
   unsigned long long* d_cursor[2] = {nullptr, nullptr};
   int64_t* d_pair_off[2] = {nullptr, nullptr};
@@ -63,6 +66,7 @@ struct b2m_ctx {
   int64_t d_pairs_cap = 0;
   std::string err;
   volatile int stop = 0;
+  bool exact_k1 = false;  // use the exact top-2 epilogue (K1 v1) instead of filter + resolve (K1 v2)
   b2m_stats stats{};
   void* verify_state = nullptr;  // b2m::VerifyState (verify.cu)
 };

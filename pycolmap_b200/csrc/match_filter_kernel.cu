@@ -1,0 +1,321 @@
+// match_filter_kernel.cu -- K1 v2: the same tcgen05 int8 GEMM pipeline as match_kernel.cu, but the
+// fused epilogue is a *filter*: 0.5 ALU op per accumulator instead of 4.
+//
+// Per row (TMEM lane) the epilogue keeps 32 "slot maxima"  B[r] = max over columns j == r (mod 32)
+// of dot(i, j), updated with one 3-input max (VIMNMX3) per two accumulators.  At the end of the row
+//     best  = max_r B[r]                    (exact)
+//     S1    = second largest slot maximum   (a LOWER bound of the true second-best: the true second
+//                                            is max(S1, second-largest element inside the winning slot))
+// Since acos is monotone, a row that fails `acos(best) <= max_distance` or already fails the ratio
+// test against S1 is rejected exactly.  The few survivors ("candidates": essentially the true
+// matches) are resolved exactly by k1_resolve: it recomputes the <= n2/32 dot products of the winning
+// slot with dp4a, finds the lowest-index arg-max and the hidden second-best, and applies the exact
+// float32 test of FindBestMatchesOneWayBruteForce.  Results are bit-identical to the exact kernel.
+//
+// Semantics: U:feature/sift.cc (COLMAP 3.9.1), SURVEY.md section 8 rows M1-M3.
+#include "match_kernel.cuh"
+#include "ptx.cuh"
+
+namespace b2m {
+
+namespace {
+
+constexpr int kDim = 128;
+constexpr int kTileM = 128;
+constexpr int kTileN = 256;
+constexpr int kUmmaK = 32;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kBytesA = kTileM * kDim;
+constexpr int kBytesB = kTileN * kDim;
+constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quarter: each takes 128 of the 256 columns
+constexpr int kThreads = (kEpiWarps + 2) * 32;     // + TMA warp + MMA warp
+constexpr uint32_t kIdesc = make_idesc_u8u8_s32(kTileM, kTileN);
+
+struct __align__(8) Barriers {
+  uint64_t full_a;
+  uint64_t full_b[kStages];
+  uint64_t empty_b[kStages];
+  uint64_t tmem_full[kAccStages];
+  uint64_t tmem_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+constexpr int kMergeBytes = kTileM * 32 * 4;  // slot maxima of the upper column half, [128 rows][32]
+constexpr size_t kSmemBytes = 1024 + kBytesA + kStages * kBytesB + kMergeBytes + sizeof(Barriers);
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p) {
+  const int pair = blockIdx.z;
+  const int dir = blockIdx.y;
+  const int strip = blockIdx.x;
+  const int ia = p.pairs[2 * pair + dir];
+  const int ib = p.pairs[2 * pair + (dir ^ 1)];
+  const int nA = p.img_nfeat[ia];
+  const int nB = p.img_nfeat[ib];
+  if (strip * kTileM >= nA) return;
+  const int rowA = p.img_row0[ia] + strip * kTileM;
+  const int rowB = p.img_row0[ib];
+  const int n_tiles = (nB + kTileN - 1) / kTileN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + kBytesA;
+  uint32_t* merge = reinterpret_cast<uint32_t*>(smem + kBytesA + kStages * kBytesB);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + kBytesA + kStages * kBytesB + kMergeBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == kEpiWarps && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(&bars->full_a, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars->full_b[s], 1);
+      mbar_init(&bars->empty_b[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&bars->tmem_full[s], 1);
+      mbar_init(&bars->tmem_empty[s], kEpiWarps * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kEpiWarps + 1) {
+    tmem_alloc(&bars->tmem_base, kAccStages * kTileN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == kEpiWarps) {
+    // ===== TMA producer =====
+    if (lane == 0 && n_tiles > 0) {
+      mbar_arrive_expect_tx(&bars->full_a, kBytesA);
+      tma_load_2d(smA, &tmap, &bars->full_a, 0, rowA);
+      uint32_t stage = 0, phase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&bars->empty_b[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bars->full_b[stage], kBytesB);
+        uint8_t* dst = smB + stage * kBytesB;
+        tma_load_2d(dst, &tmap, &bars->full_b[stage], 0, rowB + t * kTileN);
+        tma_load_2d(dst + kBytesA, &tmap, &bars->full_b[stage], 0, rowB + t * kTileN + 128);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ===== MMA issuer =====
+    if (lane == 0 && n_tiles > 0) {
+      mbar_wait(&bars->full_a, 0);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smA));
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        mbar_wait(&bars->full_b[stage], phase);
+        tc_fence_after();
+        const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smB + stage * kBytesB));
+        const uint32_t tmem_d = tmem_base + as * kTileN;
+#pragma unroll
+        for (int k = 0; k < kDim / kUmmaK; ++k)
+          mma_i8_ss(tmem_d, adesc0 + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
+        mma_commit(&bars->empty_b[stage]);
+        mma_commit(&bars->tmem_full[as]);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++as == kAccStages) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== filter epilogue: warp w -> TMEM lanes 32*(w%4).., columns 128*(w/4).. of every tile =====
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    const int row_in_strip = quarter * 32 + lane;
+    uint32_t B[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) B[r] = 0u;
+    uint32_t as = 0, aphase = 0;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_base + as * kTileN + half * 128;
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr, va);
+      tmem_ld_32x32(taddr + 32, vb);
+      tmem_wait_ld();
+#pragma unroll
+      for (int r = 0; r < 32; ++r) B[r] = max(B[r], max(va[r], vb[r]));
+      tmem_ld_32x32(taddr + 64, va);
+      tmem_ld_32x32(taddr + 96, vb);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&bars->tmem_empty[as]);  // registers hold the last two chunks: TMEM stage is free
+#pragma unroll
+      for (int r = 0; r < 32; ++r) B[r] = max(B[r], max(va[r], vb[r]));
+      if (++as == kAccStages) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    // merge the two column halves of each row through shared memory
+    if (half == 1) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) merge[r * kTileM + row_in_strip] = B[r];  // [slot][row]: conflict-free
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+    if (half == 0) {
+      uint32_t best = 0, s1 = 0;
+      int rstar = 0;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const uint32_t v = max(B[r], merge[r * kTileM + row_in_strip]);
+        // running (largest, second largest) over the slot maxima, multiset semantics
+        if (v > best) {
+          s1 = best;
+          best = v;
+          rstar = r;
+        } else {
+          s1 = max(s1, v);
+        }
+      }
+      int32_t out = -1;
+      if (best > 0u) {
+        const float a = __ldg(p.acos_lut + min(best, 262144u));
+        if (!(a > p.max_distance)) {
+          const float b = __ldg(p.acos_lut + min(s1, 262144u));
+          if (!(a >= __fmul_rn(p.max_ratio, b))) out = -2 - rstar;  // candidate: resolve exactly
+        }
+      }
+      const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
+      const int row = strip * kTileM + row_in_strip;
+      p.mbuf[base + row] = out;
+      if (out != -1) {
+        p.aux[base + row] = make_uint2(best, s1);
+        const int k = atomicAdd(p.cand_cnt + pair * 2 + dir, 1);
+        p.cand_rows[base + k] = row;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kAccStages * kTileN);
+  }
+}
+
+// Exact resolution of the candidate rows of one (pair, direction).  One warp per candidate:
+// recompute dot(i, j) for the columns j of the winning slot (all columns if the maximum is shared
+// by several slots), oracle scan order per lane, multiset-aware merge across lanes.
+__global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p, const uint8_t* __restrict__ desc) {
+  const int pair = blockIdx.x >> 1;
+  const int dir = blockIdx.x & 1;
+  const int n_cand = p.cand_cnt[pair * 2 + dir];
+  if (n_cand == 0) return;
+  const int ia = p.pairs[2 * pair + dir];
+  const int ib = p.pairs[2 * pair + (dir ^ 1)];
+  const int nB = p.img_nfeat[ib];
+  const int nB_pad = (nB + kRowPad - 1) / kRowPad * kRowPad;
+  const uint8_t* A = desc + static_cast<int64_t>(p.img_row0[ia]) * kDim;
+  const uint8_t* Bm = desc + static_cast<int64_t>(p.img_row0[ib]) * kDim;
+  const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < n_cand; c += 8) {
+    const int row = p.cand_rows[base + c];
+    const int code = p.mbuf[base + row];  // -2 - slot
+    const uint2 ax = p.aux[base + row];
+    const uint32_t best_f = ax.x, s1 = ax.y;
+    const int slot = -2 - code;
+    const bool multi = (s1 == best_f);
+    // descriptor of the row, kept in registers
+    uint32_t a[32];
+    const uint4* ap = reinterpret_cast<const uint4*>(A + static_cast<int64_t>(row) * kDim);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 v = __ldg(ap + q);
+      a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+    }
+    uint32_t bd = 0, sd = 0;
+    int bj = -1;
+    const int step = multi ? 32 : 1024;           // column stride between consecutive items of a lane
+    const int first = multi ? lane : slot + 32 * lane;
+    for (int j = first; j < nB_pad; j += step) {
+      const uint4* bp = reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim);
+      uint32_t d = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 v = __ldg(bp + q);
+        d = __dp4a(a[4 * q], v.x, d);
+        d = __dp4a(a[4 * q + 1], v.y, d);
+        d = __dp4a(a[4 * q + 2], v.z, d);
+        d = __dp4a(a[4 * q + 3], v.w, d);
+      }
+      if (d > bd) {
+        sd = bd;
+        bd = d;
+        bj = j;
+      } else if (d > sd) {
+        sd = d;
+      }
+    }
+    // merge lanes: larger best wins, ties -> lower column; second = max(min(b1, b2), s1, s2)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t obd = __shfl_xor_sync(0xffffffffu, bd, o);
+      const uint32_t osd = __shfl_xor_sync(0xffffffffu, sd, o);
+      const int obj = __shfl_xor_sync(0xffffffffu, bj, o);
+      const uint32_t nsd = max(max(sd, osd), min(bd, obd));
+      if (obd > bd || (obd == bd && obj >= 0 && (bj < 0 || obj < bj))) {
+        bd = obd;
+        bj = obj;
+      }
+      sd = nsd;
+    }
+    if (lane == 0) {
+      const uint32_t second = multi ? sd : max(sd, s1);
+      int32_t out = -1;
+      if (bd > 0u && bd == best_f) {
+        const float fa = __ldg(p.acos_lut + min(bd, 262144u));
+        if (!(fa > p.max_distance)) {
+          const float fb = __ldg(p.acos_lut + min(second, 262144u));
+          if (!(fa >= __fmul_rn(p.max_ratio, fb))) out = bj;
+        }
+      }
+      p.mbuf[base + row] = out;
+    }
+  }
+}
+
+cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p, const uint8_t* desc, int n_pairs,
+                             int max_strips, int n_dirs, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(b2m_k1_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSmemBytes));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaError_t e = cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * 2 * n_pairs, stream);
+  if (e != cudaSuccess) return e;
+  dim3 grid(max_strips, n_dirs, n_pairs);
+  b2m_k1_filter_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  b2m_k1_resolve_kernel<<<2 * n_pairs, 256, 0, stream>>>(p, desc);
+  return cudaGetLastError();
+}
+
+}  // namespace b2m

@@ -15,6 +15,10 @@ struct MatchParams {
   const float* acos_lut;     // device [262145] acosf(min(d * 2^-18, 1)) built with the host libm
   float max_ratio;
   float max_distance;
+  // K1 v2 (filter + resolve) only:
+  uint2* aux;                // device [n_pairs][2][mstride]: (best, S1) of candidate rows
+  int32_t* cand_cnt;         // device [n_pairs][2] number of candidate rows
+  int32_t* cand_rows;        // device [n_pairs][2][mstride] candidate row list
 };
 
 struct CompactParams {
@@ -39,6 +43,10 @@ constexpr int kRowPad = 256;
 
 cudaError_t launch_k1_match(const CUtensorMap& tmap, const MatchParams& p, int n_pairs, int max_strips, int n_dirs,
                             cudaStream_t stream);
+// K1 v2: filter epilogue (slot maxima) + exact dp4a resolution of the candidate rows.  Bit-identical
+// results to launch_k1_match; requires a monotone (non-increasing) acos LUT.
+cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p, const uint8_t* desc, int n_pairs,
+                             int max_strips, int n_dirs, cudaStream_t stream);
 cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream);
 
 }  // namespace b2m

@@ -1,16 +1,25 @@
-// match_filter_kernel.cu -- K1 v2: the same tcgen05 int8 GEMM pipeline as match_kernel.cu, but the
-// fused epilogue is a *filter*: 0.5 ALU op per accumulator instead of 4.
+// match_filter_kernel.cu -- K1 v3: tcgen05 int8 GEMM with a *filter* epilogue and 256-row CTAs.
 //
-// Per row (TMEM lane) the epilogue keeps 32 "slot maxima"  B[r] = max over columns j == r (mod 32)
-// of dot(i, j), updated with one 3-input max (VIMNMX3) per two accumulators.  At the end of the row
-//     best  = max_r B[r]                    (exact)
-//     S1    = second largest slot maximum   (a LOWER bound of the true second-best: the true second
-//                                            is max(S1, second-largest element inside the winning slot))
-// Since acos is monotone, a row that fails `acos(best) <= max_distance` or already fails the ratio
-// test against S1 is rejected exactly.  The few survivors ("candidates": essentially the true
-// matches) are resolved exactly by k1_resolve: it recomputes the <= n2/32 dot products of the winning
-// slot with dp4a, finds the lowest-index arg-max and the hidden second-best, and applies the exact
-// float32 test of FindBestMatchesOneWayBruteForce.  Results are bit-identical to the exact kernel.
+// Work unit (CTA) = (image pair, direction, 256-row block of the "row" image A).  The CTA keeps its
+// two 128-row A strips resident in shared memory and streams 128-column tiles of image B through an
+// 8-stage TMA ring; every B tile feeds two 128x128x128 MMAs (one per strip), which halves the
+// L2 -> SM operand traffic per MAC compared with one strip per CTA (the v2 profile showed the
+// pipeline bound by L2 feed latency/bandwidth, profiles/r01_k1_v2_*.txt).  Accumulators live in
+// TMEM: 2 stages x 2 strips x 128 columns = 512 columns.
+//
+// Epilogue (8 warps: warp w -> TMEM lane quarter w%4 of strip w/4; thread <-> row): instead of an
+// exact running top-2 (4 ALU ops per accumulator) each thread keeps 64 "slot maxima"
+//     B[cp][r] = max over columns j with ((j mod 128) div 64, j mod 32) == (cp, r)   of dot(i, j)
+// updated with one 3-input max (VIMNMX3) per two accumulators = 0.5 ALU op per accumulator.  At the
+// end of the row
+//     best = max over slots (exact);   S1 = second largest slot maximum (multiset), which is a LOWER
+//     bound of the true second-best (= max(S1, second largest element inside the winning slot)).
+// acos is monotone, so a row failing `acos(best) <= max_distance`, or failing the ratio test already
+// against S1, is rejected exactly.  The survivors ("candidates": essentially the true matches) are
+// resolved exactly by b2m_k1_resolve_kernel: it recomputes the n2/64 dot products of the winning slot
+// with dp4a (all columns if several slots share the maximum), finds the lowest-index arg-max and the
+// hidden second-best, and applies the float32 test of FindBestMatchesOneWayBruteForce.  The match
+// indices are bit-identical to the exact kernel (match_kernel.cu) and to the CPU oracle.
 //
 // Semantics: U:feature/sift.cc (COLMAP 3.9.1), SURVEY.md section 8 rows M1-M3.
 #include "match_kernel.cuh"
@@ -21,16 +30,20 @@ namespace b2m {
 namespace {
 
 constexpr int kDim = 128;
-constexpr int kTileM = 128;
-constexpr int kTileN = 256;
+constexpr int kTileM = 128;                        // rows per MMA (TMEM lanes)
+constexpr int kStrips = 2;                         // A strips per CTA
+constexpr int kRowsPerCta = kTileM * kStrips;      // 256 == kRowPad
+constexpr int kTileN = 128;                        // columns per B tile
 constexpr int kUmmaK = 32;
-constexpr int kStages = 4;
+constexpr int kStages = 8;                         // B-tile ring depth (8 x 16 KiB)
 constexpr int kAccStages = 2;
-constexpr int kBytesA = kTileM * kDim;
-constexpr int kBytesB = kTileN * kDim;
-constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quarter: each takes 128 of the 256 columns
+constexpr int kBytesA = kTileM * kDim;             // 16 KiB per strip
+constexpr int kBytesB = kTileN * kDim;             // 16 KiB
+constexpr int kEpiWarps = 4 * kStrips;             // one warp per (strip, TMEM lane quarter)
 constexpr int kThreads = (kEpiWarps + 2) * 32;     // + TMA warp + MMA warp
+constexpr int kAccCols = kStrips * kTileN;         // TMEM columns per accumulator stage
 constexpr uint32_t kIdesc = make_idesc_u8u8_s32(kTileM, kTileN);
+static_assert(kRowsPerCta == kRowPad, "images are padded to whole CTA row blocks");
 
 struct __align__(8) Barriers {
   uint64_t full_a;
@@ -41,8 +54,7 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
-constexpr int kMergeBytes = kTileM * 32 * 4;  // slot maxima of the upper column half, [128 rows][32]
-constexpr size_t kSmemBytes = 1024 + kBytesA + kStages * kBytesB + kMergeBytes + sizeof(Barriers);
+constexpr size_t kSmemBytes = 1024 + kStrips * kBytesA + kStages * kBytesB + sizeof(Barriers);
 
 }  // namespace
 
@@ -50,22 +62,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p) {
   const int pair = blockIdx.z;
   const int dir = blockIdx.y;
-  const int strip = blockIdx.x;
+  const int blk = blockIdx.x;
   const int ia = p.pairs[2 * pair + dir];
   const int ib = p.pairs[2 * pair + (dir ^ 1)];
   const int nA = p.img_nfeat[ia];
   const int nB = p.img_nfeat[ib];
-  if (strip * kTileM >= nA) return;
-  const int rowA = p.img_row0[ia] + strip * kTileM;
+  if (blk * kRowsPerCta >= nA) return;  // uniform exit before any barrier / TMEM allocation
+  const int rowA = p.img_row0[ia] + blk * kRowsPerCta;
   const int rowB = p.img_row0[ib];
   const int n_tiles = (nB + kTileN - 1) / kTileN;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
-  uint8_t* smB = smem + kBytesA;
-  uint32_t* merge = reinterpret_cast<uint32_t*>(smem + kBytesA + kStages * kBytesB);
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + kBytesA + kStages * kBytesB + kMergeBytes);
+  uint8_t* smB = smem + kStrips * kBytesA;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + kStrips * kBytesA + kStages * kBytesB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -84,7 +95,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
     fence_mbar_init();
   }
   if (warp == kEpiWarps + 1) {
-    tmem_alloc(&bars->tmem_base, kAccStages * kTileN);
+    tmem_alloc(&bars->tmem_base, kAccStages * kAccCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -95,15 +106,14 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
   if (warp == kEpiWarps) {
     // ===== TMA producer =====
     if (lane == 0 && n_tiles > 0) {
-      mbar_arrive_expect_tx(&bars->full_a, kBytesA);
-      tma_load_2d(smA, &tmap, &bars->full_a, 0, rowA);
+      mbar_arrive_expect_tx(&bars->full_a, kStrips * kBytesA);
+#pragma unroll
+      for (int s = 0; s < kStrips; ++s) tma_load_2d(smA + s * kBytesA, &tmap, &bars->full_a, 0, rowA + s * kTileM);
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&bars->empty_b[stage], phase ^ 1);
         mbar_arrive_expect_tx(&bars->full_b[stage], kBytesB);
-        uint8_t* dst = smB + stage * kBytesB;
-        tma_load_2d(dst, &tmap, &bars->full_b[stage], 0, rowB + t * kTileN);
-        tma_load_2d(dst + kBytesA, &tmap, &bars->full_b[stage], 0, rowB + t * kTileN + 128);
+        tma_load_2d(smB + stage * kBytesB, &tmap, &bars->full_b[stage], 0, rowB + t * kTileN);
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -111,20 +121,25 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer (one thread): two 128x128x128 MMAs per B tile =====
     if (lane == 0 && n_tiles > 0) {
       mbar_wait(&bars->full_a, 0);
-      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smA));
+      uint64_t adesc[kStrips];
+#pragma unroll
+      for (int s = 0; s < kStrips; ++s) adesc[s] = make_smem_desc_sw128(smem_u32(smA + s * kBytesA));
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
         mbar_wait(&bars->full_b[stage], phase);
         tc_fence_after();
         const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smB + stage * kBytesB));
-        const uint32_t tmem_d = tmem_base + as * kTileN;
 #pragma unroll
-        for (int k = 0; k < kDim / kUmmaK; ++k)
-          mma_i8_ss(tmem_d, adesc0 + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
+        for (int s = 0; s < kStrips; ++s) {
+          const uint32_t tmem_d = tmem_base + as * kAccCols + s * kTileN;
+#pragma unroll
+          for (int k = 0; k < kDim / kUmmaK; ++k)
+            mma_i8_ss(tmem_d, adesc[s] + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
+        }
         mma_commit(&bars->empty_b[stage]);
         mma_commit(&bars->tmem_full[as]);
         if (++stage == kStages) {
@@ -138,74 +153,69 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
       }
     }
   } else {
-    // ===== filter epilogue: warp w -> TMEM lanes 32*(w%4).., columns 128*(w/4).. of every tile =====
+    // ===== filter epilogue =====
     const int quarter = warp & 3;
-    const int half = warp >> 2;
-    const int row_in_strip = quarter * 32 + lane;
-    uint32_t B[32];
+    const int strip = warp >> 2;
+    const int row_in_blk = strip * kTileM + quarter * 32 + lane;
+    uint32_t B0[32], B1[32];
 #pragma unroll
-    for (int r = 0; r < 32; ++r) B[r] = 0u;
+    for (int r = 0; r < 32; ++r) {
+      B0[r] = 0u;
+      B1[r] = 0u;
+    }
     uint32_t as = 0, aphase = 0;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     for (int t = 0; t < n_tiles; ++t) {
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + lane_base + as * kTileN + half * 128;
+      const uint32_t taddr = tmem_base + lane_base + as * kAccCols + strip * kTileN;
       uint32_t va[32], vb[32];
       tmem_ld_32x32(taddr, va);
       tmem_ld_32x32(taddr + 32, vb);
       tmem_wait_ld();
 #pragma unroll
-      for (int r = 0; r < 32; ++r) B[r] = max(B[r], max(va[r], vb[r]));
+      for (int r = 0; r < 32; ++r) B0[r] = max(B0[r], max(va[r], vb[r]));
       tmem_ld_32x32(taddr + 64, va);
       tmem_ld_32x32(taddr + 96, vb);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&bars->tmem_empty[as]);  // registers hold the last two chunks: TMEM stage is free
+      mbar_arrive(&bars->tmem_empty[as]);  // the last two chunks are in registers: TMEM stage is free
 #pragma unroll
-      for (int r = 0; r < 32; ++r) B[r] = max(B[r], max(va[r], vb[r]));
+      for (int r = 0; r < 32; ++r) B1[r] = max(B1[r], max(va[r], vb[r]));
       if (++as == kAccStages) {
         as = 0;
         aphase ^= 1;
       }
     }
-    // merge the two column halves of each row through shared memory
-    if (half == 1) {
+    // (largest, second largest) over the 64 slot maxima, multiset semantics; lowest slot id on ties
+    uint32_t best = 0, s1 = 0;
+    int sstar = 0;
 #pragma unroll
-      for (int r = 0; r < 32; ++r) merge[r * kTileM + row_in_strip] = B[r];  // [slot][row]: conflict-free
+    for (int r = 0; r < 64; ++r) {
+      const uint32_t v = r < 32 ? B0[r & 31] : B1[r & 31];
+      if (v > best) {
+        s1 = best;
+        best = v;
+        sstar = r;
+      } else {
+        s1 = max(s1, v);
+      }
     }
-    asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
-    if (half == 0) {
-      uint32_t best = 0, s1 = 0;
-      int rstar = 0;
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const uint32_t v = max(B[r], merge[r * kTileM + row_in_strip]);
-        // running (largest, second largest) over the slot maxima, multiset semantics
-        if (v > best) {
-          s1 = best;
-          best = v;
-          rstar = r;
-        } else {
-          s1 = max(s1, v);
-        }
+    int32_t out = -1;
+    if (best > 0u) {
+      const float a = __ldg(p.acos_lut + min(best, 262144u));
+      if (!(a > p.max_distance)) {
+        const float b = __ldg(p.acos_lut + min(s1, 262144u));
+        if (!(a >= __fmul_rn(p.max_ratio, b))) out = -2 - sstar;  // candidate: resolve exactly
       }
-      int32_t out = -1;
-      if (best > 0u) {
-        const float a = __ldg(p.acos_lut + min(best, 262144u));
-        if (!(a > p.max_distance)) {
-          const float b = __ldg(p.acos_lut + min(s1, 262144u));
-          if (!(a >= __fmul_rn(p.max_ratio, b))) out = -2 - rstar;  // candidate: resolve exactly
-        }
-      }
-      const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
-      const int row = strip * kTileM + row_in_strip;
-      p.mbuf[base + row] = out;
-      if (out != -1) {
-        p.aux[base + row] = make_uint2(best, s1);
-        const int k = atomicAdd(p.cand_cnt + pair * 2 + dir, 1);
-        p.cand_rows[base + k] = row;
-      }
+    }
+    const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
+    const int row = blk * kRowsPerCta + row_in_blk;
+    p.mbuf[base + row] = out;
+    if (out != -1) {
+      p.aux[base + row] = make_uint2(best, s1);
+      const int k = atomicAdd(p.cand_cnt + pair * 2 + dir, 1);
+      p.cand_rows[base + k] = row;
     }
   }
 
@@ -213,13 +223,14 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
   __syncthreads();
   if (warp == kEpiWarps + 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kAccStages * kTileN);
+    tmem_dealloc(tmem_base, kAccStages * kAccCols);
   }
 }
 
 // Exact resolution of the candidate rows of one (pair, direction).  One warp per candidate:
 // recompute dot(i, j) for the columns j of the winning slot (all columns if the maximum is shared
 // by several slots), oracle scan order per lane, multiset-aware merge across lanes.
+// Slot s = cp * 32 + r holds the columns j = 128 t + 64 cp + 32 c + r, c in {0, 1}, t = 0, 1, ...
 __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p, const uint8_t* __restrict__ desc) {
   const int pair = blockIdx.x >> 1;
   const int dir = blockIdx.x & 1;
@@ -239,8 +250,8 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
     const uint2 ax = p.aux[base + row];
     const uint32_t best_f = ax.x, s1 = ax.y;
     const int slot = -2 - code;
+    const int cp = slot >> 5, r = slot & 31;
     const bool multi = (s1 == best_f);
-    // descriptor of the row, kept in registers
     uint32_t a[32];
     const uint4* ap = reinterpret_cast<const uint4*>(A + static_cast<int64_t>(row) * kDim);
 #pragma unroll
@@ -250,9 +261,9 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
     }
     uint32_t bd = 0, sd = 0;
     int bj = -1;
-    const int step = multi ? 32 : 1024;           // column stride between consecutive items of a lane
-    const int first = multi ? lane : slot + 32 * lane;
-    for (int j = first; j < nB_pad; j += step) {
+    const int n_items = multi ? nB_pad : nB_pad / 64;
+    for (int it = lane; it < n_items; it += 32) {
+      const int j = multi ? it : (128 * (it >> 1) + 64 * cp + 32 * (it & 1) + r);
       const uint4* bp = reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim);
       uint32_t d = 0;
 #pragma unroll
@@ -310,7 +321,7 @@ cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p, cons
   }
   cudaError_t e = cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * 2 * n_pairs, stream);
   if (e != cudaSuccess) return e;
-  dim3 grid(max_strips, n_dirs, n_pairs);
+  dim3 grid((max_strips + kStrips - 1) / kStrips, n_dirs, n_pairs);
   b2m_k1_filter_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200match.so")
+LIB_PATH = os.environ.get("B2M_LIB") or os.path.join(_HERE, "libb200match.so")  # B2M_LIB: experiment builds only
 
 c_i32, c_i64, c_u32, c_u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64
 c_f32, c_f64 = ctypes.c_float, ctypes.c_double

@@ -97,6 +97,11 @@ int layout_images(b2m_ctx* ctx, ImageSet& S, int n_images, const int32_t* n_feat
   CUresult r = enc(&S.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, S.d_desc, gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint32_t box_half[2] = {128, 64};
+  if (r == CUDA_SUCCESS)
+    r = enc(&S.tmap_half, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, S.d_desc, gdim, gstride, box_half, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char b[128];
     snprintf(b, sizeof(b), "[api.cu] cuTensorMapEncodeTiled failed: CUresult %d", static_cast<int>(r));
@@ -115,6 +120,7 @@ int ensure_workspace(b2m_ctx* ctx, int batch, int32_t mstride) {
   CU_TRY(ctx, cudaMalloc(&W.d_mbuf, sizeof(int32_t) * 2 * arena_matches));
   CU_TRY(ctx, cudaMalloc(&W.d_aux, sizeof(uint2) * 2 * arena_matches));
   CU_TRY(ctx, cudaMalloc(&W.d_cand_rows, sizeof(int32_t) * 2 * arena_matches));
+  CU_TRY(ctx, cudaMalloc(&W.d_cand_sorted, sizeof(int32_t) * 2 * arena_matches));
   CU_TRY(ctx, cudaMalloc(&W.d_cand_cnt, sizeof(int32_t) * 2 * batch));
   for (int s = 0; s < 2; ++s) {
     CU_TRY(ctx, cudaMalloc(&W.d_arena[s], sizeof(uint2) * arena_matches));
@@ -166,7 +172,8 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
   };
 
   const int B = ctx->pair_batch;
-  if (int rc = ensure_workspace(ctx, B, S.max_feat_pad)) return bail(rc);
+  // rows are handed out in 512-row cluster blocks: keep the per-pair stride a multiple of that
+  if (int rc = ensure_workspace(ctx, B, round_up(S.max_feat_pad, 512))) return bail(rc);
   if (tvg)
     if (int rc = verify_prepare(ctx, S, ctx->ws.batch, static_cast<int64_t>(ctx->ws.batch) * ctx->ws.mstride))
       return bail(rc);
@@ -263,11 +270,12 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     mp.aux = W.d_aux;
     mp.cand_cnt = W.d_cand_cnt;
     mp.cand_rows = W.d_cand_rows;
+    mp.cand_sorted = W.d_cand_sorted;
     CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
     if (ctx->exact_k1) {
       CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
     } else {
-      CU_TRY_R(launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, st));
+      CU_TRY_R(launch_k1_filter(S.tmap, S.tmap_half, mp, S.d_desc, nb, max_strips, n_dirs, st));
       ctx->stats.kernel_launches += 1;
     }
     CU_TRY_R(cudaEventRecord(ctx->ev_k1b[s], st));
@@ -334,6 +342,8 @@ void Workspace::release() {
   if (d_aux) cudaFree(d_aux);
   if (d_cand_cnt) cudaFree(d_cand_cnt);
   if (d_cand_rows) cudaFree(d_cand_rows);
+  if (d_cand_sorted) cudaFree(d_cand_sorted);
+  d_cand_sorted = nullptr;
   d_mbuf = nullptr;
   d_aux = nullptr;
   d_cand_cnt = nullptr;

@@ -281,13 +281,79 @@ B2M_HD inline void enforce_rank2(double* F) {
 }
 
 // Smallest-eigenvalue eigenvector of the accumulated 9x9 normal matrix -> 3x3 (row-major).
-B2M_HD inline void smallest_eigvec9(const double* S45, double* out9) {
+B2M_HD inline void smallest_eigvec9_jacobi(const double* S45, double* out9) {
   double A[81], V[81], w[9];
   sym9_expand(S45, A);
   jacobi_eig_sym<9>(A, V, w);
   int idx[1];
   smallest_k<9>(w, 1, idx);
   for (int i = 0; i < 9; ++i) out9[i] = V[i * 9 + idx[0]];
+}
+template <int K>
+B2M_HD inline void smallest_eigvecs_invit(const double* S45, double* out);
+B2M_HD inline void smallest_eigvec9(const double* S45, double* out9) { smallest_eigvecs_invit<1>(S45, out9); }
+
+// K smallest eigenvectors (an orthonormal basis of that invariant subspace) of a symmetric
+// positive semi-definite 9x9 matrix by Cholesky-based inverse subspace iteration.  ~50x cheaper than
+// the Jacobi sweep and good to full precision whenever the K-th and (K+1)-th eigenvalues are
+// separated, which is exactly when the least-squares null space of the LO refits is well defined.
+// out: [K][9]; out[0] belongs to the smallest eigenvalue (Rayleigh-ordered).
+template <int K>
+B2M_HD inline void smallest_eigvecs_invit(const double* S45, double* out) {
+  double L[81];
+  sym9_expand(S45, L);
+  double tr = 0.0;
+  for (int i = 0; i < 9; ++i) tr += L[i * 9 + i];
+  const double mu = tr * 1e-14 + 1e-300;
+  for (int i = 0; i < 9; ++i) L[i * 9 + i] += mu;
+  // in-place Cholesky, lower triangle
+  for (int j = 0; j < 9; ++j) {
+    double d = L[j * 9 + j];
+    for (int k = 0; k < j; ++k) d -= L[j * 9 + k] * L[j * 9 + k];
+    if (!(d > mu * 1e-3)) d = mu * 1e-3;
+    const double ljj = sqrt(d);
+    L[j * 9 + j] = ljj;
+    const double inv = 1.0 / ljj;
+    for (int i = j + 1; i < 9; ++i) {
+      double s = L[i * 9 + j];
+      for (int k = 0; k < j; ++k) s -= L[i * 9 + k] * L[j * 9 + k];
+      L[i * 9 + j] = s * inv;
+    }
+  }
+  // deterministic, generic start vectors
+  for (int k = 0; k < K; ++k)
+    for (int i = 0; i < 9; ++i) {
+      const int h = (i * 37 + k * 101 + 11) % 17;
+      out[k * 9 + i] = (static_cast<double>(h) - 8.0) * 0.1 + (i == 8 - k ? 1.0 : 0.0);
+    }
+  for (int it = 0; it < 6; ++it) {
+    for (int k = 0; k < K; ++k) {
+      double* v = out + k * 9;
+      for (int i = 0; i < 9; ++i) {  // L y = v
+        double s = v[i];
+        for (int j = 0; j < i; ++j) s -= L[i * 9 + j] * v[j];
+        v[i] = s / L[i * 9 + i];
+      }
+      for (int i = 8; i >= 0; --i) {  // L^T x = y
+        double s = v[i];
+        for (int j = i + 1; j < 9; ++j) s -= L[j * 9 + i] * v[j];
+        v[i] = s / L[i * 9 + i];
+      }
+    }
+    for (int k = 0; k < K; ++k) {  // modified Gram-Schmidt
+      double* v = out + k * 9;
+      for (int q = 0; q < k; ++q) {
+        const double* u = out + q * 9;
+        double dot = 0.0;
+        for (int i = 0; i < 9; ++i) dot += u[i] * v[i];
+        for (int i = 0; i < 9; ++i) v[i] -= dot * u[i];
+      }
+      double nn = 0.0;
+      for (int i = 0; i < 9; ++i) nn += v[i] * v[i];
+      const double inv = 1.0 / sqrt(nn > 0.0 ? nn : 1.0);
+      for (int i = 0; i < 9; ++i) v[i] *= inv;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -694,6 +760,59 @@ B2M_HD inline int minimal_F7(const double* x1, const double* y1, const double* x
   for (int k = 0; k < n; ++k) denormalize_F(Fn + 9 * k, s1, cx1, cy1, s2, cx2, cy2, models + 9 * k);
   return n;
 }
+// Closed-form 4-point homography, registers only (no arrays -> no local memory on the GPU):
+// for each image find the projective map taking the canonical frame (e1, e2, e3, e1+e2+e3) to the
+// four points, A = [l p0 | m p1 | n p2] with l p0 + m p1 + n p2 = p3 (Cramer), then H = B adj(A).
+// Four correspondences in general position determine H uniquely up to scale, so this equals the
+// DLT null vector of HomographyMatrixEstimator::Estimate for minimal samples.
+B2M_HD inline bool frame_from_4pts(const double* x, const double* y, double* A) {
+  // columns p0, p1, p2 (homogeneous, w = 1); solve [p0 p1 p2] (l, m, n)^T = p3
+  const double x0 = x[0], y0 = y[0], x1 = x[1], y1 = y[1], x2 = x[2], y2 = y[2], x3 = x[3], y3 = y[3];
+  const double det = x0 * (y1 - y2) - x1 * (y0 - y2) + x2 * (y0 - y1);
+  const double l = x3 * (y1 - y2) - x1 * (y3 - y2) + x2 * (y3 - y1);
+  const double m = x0 * (y3 - y2) - x3 * (y0 - y2) + x2 * (y0 - y3);
+  const double n = x0 * (y1 - y3) - x1 * (y0 - y3) + x3 * (y0 - y1);
+  if (!(fabs(det) > 0.0)) return false;
+  // scale by 1/det is irrelevant (homogeneous); keep l, m, n un-normalised
+  A[0] = l * x0; A[1] = m * x1; A[2] = n * x2;
+  A[3] = l * y0; A[4] = m * y1; A[5] = n * y2;
+  A[6] = l;      A[7] = m;      A[8] = n;
+  return true;
+}
+B2M_HD inline int minimal_H4_closed(const double* x1, const double* y1, const double* x2, const double* y2,
+                                    double* H) {
+  // translate both point sets to their centroids first (conditioning), undo at the end
+  const double c1x = 0.25 * (x1[0] + x1[1] + x1[2] + x1[3]), c1y = 0.25 * (y1[0] + y1[1] + y1[2] + y1[3]);
+  const double c2x = 0.25 * (x2[0] + x2[1] + x2[2] + x2[3]), c2y = 0.25 * (y2[0] + y2[1] + y2[2] + y2[3]);
+  const double ax[4] = {x1[0] - c1x, x1[1] - c1x, x1[2] - c1x, x1[3] - c1x};
+  const double ay[4] = {y1[0] - c1y, y1[1] - c1y, y1[2] - c1y, y1[3] - c1y};
+  const double bx[4] = {x2[0] - c2x, x2[1] - c2x, x2[2] - c2x, x2[3] - c2x};
+  const double by[4] = {y2[0] - c2y, y2[1] - c2y, y2[2] - c2y, y2[3] - c2y};
+  double A[9], B[9];
+  if (!frame_from_4pts(ax, ay, A) || !frame_from_4pts(bx, by, B)) return 0;
+  // adj(A) (transpose of the cofactor matrix)
+  const double J[9] = {A[4] * A[8] - A[5] * A[7], A[2] * A[7] - A[1] * A[8], A[1] * A[5] - A[2] * A[4],
+                       A[5] * A[6] - A[3] * A[8], A[0] * A[8] - A[2] * A[6], A[2] * A[3] - A[0] * A[5],
+                       A[3] * A[7] - A[4] * A[6], A[1] * A[6] - A[0] * A[7], A[0] * A[4] - A[1] * A[3]};
+  double Hc[9];
+  mat3_mul(B, J, Hc);
+  // H = T2^-1 Hc T1 with T1 = translate(-c1), T2^-1 = translate(+c2)
+  double nrm = 0.0;
+  for (int i = 0; i < 9; ++i) nrm += Hc[i] * Hc[i];
+  if (!(nrm > 0.0) || !(nrm < 1e300)) return 0;
+  const double s = 1.0 / sqrt(nrm);
+  for (int i = 0; i < 9; ++i) Hc[i] *= s;
+  // right-multiply by T1: third column += -(c1x * col0 + c1y * col1)
+  for (int r = 0; r < 3; ++r) Hc[r * 3 + 2] -= Hc[r * 3] * c1x + Hc[r * 3 + 1] * c1y;
+  // left-multiply by T2^-1: row0 += c2x * row2, row1 += c2y * row2
+  for (int c = 0; c < 3; ++c) {
+    H[c] = Hc[c] + c2x * Hc[6 + c];
+    H[3 + c] = Hc[3 + c] + c2y * Hc[6 + c];
+    H[6 + c] = Hc[6 + c];
+  }
+  return 1;
+}
+
 B2M_HD inline int minimal_H4(const double* x1, const double* y1, const double* x2, const double* y2, double* model) {
   double s1, cx1, cy1, s2, cx2, cy2;
   moments(x1, y1, 4, &s1, &cx1, &cy1);

@@ -25,7 +25,8 @@ struct ImageSet {
   int32_t* d_row0 = nullptr;
   int32_t* d_nfeat = nullptr;
   std::vector<b2m_camera> cams;
-  CUtensorMap tmap;
+  CUtensorMap tmap;       // box 128 bytes x 128 rows
+  CUtensorMap tmap_half;  // box 128 bytes x 64 rows (cluster-multicast halves of a B tile)
   void release();
 };
 
@@ -36,6 +37,7 @@ struct Workspace {
   uint2* d_aux = nullptr;          // K1 v2: (best, S1) per candidate row
   int32_t* d_cand_cnt = nullptr;   // K1 v2: [batch][2]
   int32_t* d_cand_rows = nullptr;  // K1 v2: [batch][2][mstride]
+  int32_t* d_cand_sorted = nullptr;
   uint2* d_arena[2] = {nullptr, nullptr};
   unsigned long long* d_cursor[2] = {nullptr, nullptr};
   int64_t* d_pair_off[2] = {nullptr, nullptr};

@@ -37,6 +37,7 @@ constexpr int kTileN = 128;                        // columns per B tile
 constexpr int kUmmaK = 32;
 constexpr int kStages = 8;                         // B-tile ring depth (8 x 16 KiB)
 constexpr int kAccStages = 2;
+constexpr int kCluster = 2;                        // CTAs per cluster sharing every B tile by TMA multicast
 constexpr int kBytesA = kTileM * kDim;             // 16 KiB per strip
 constexpr int kBytesB = kTileN * kDim;             // 16 KiB
 constexpr int kEpiWarps = 4 * kStrips;             // one warp per (strip, TMEM lane quarter)
@@ -58,8 +59,9 @@ constexpr size_t kSmemBytes = 1024 + kStrips * kBytesA + kStages * kBytesB + siz
 
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 1)
-b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p) {
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
+b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
+                     const MatchParams p) {
   const int pair = blockIdx.z;
   const int dir = blockIdx.y;
   const int blk = blockIdx.x;
@@ -67,7 +69,10 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
   const int ib = p.pairs[2 * pair + (dir ^ 1)];
   const int nA = p.img_nfeat[ia];
   const int nB = p.img_nfeat[ib];
-  if (blk * kRowsPerCta >= nA) return;  // uniform exit before any barrier / TMEM allocation
+  // uniform exit of the whole CLUSTER (both CTAs or none) before any barrier / TMEM allocation; a CTA
+  // whose own rows are out of range still relays its half of every B tile to its peer
+  if ((blk / kCluster) * kCluster * kRowsPerCta >= nA) return;
+  const uint32_t cta_rank = cluster_ctarank();
   const int rowA = p.img_row0[ia] + blk * kRowsPerCta;
   const int rowB = p.img_row0[ib];
   const int n_tiles = (nB + kTileN - 1) / kTileN;
@@ -86,7 +91,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
     mbar_init(&bars->full_a, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars->full_b[s], 1);
-      mbar_init(&bars->empty_b[s], 1);
+      mbar_init(&bars->empty_b[s], kCluster);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
@@ -100,6 +105,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised before any multicast can signal them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -113,7 +119,11 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&bars->empty_b[stage], phase ^ 1);
         mbar_arrive_expect_tx(&bars->full_b[stage], kBytesB);
-        tma_load_2d(smB + stage * kBytesB, &tmap, &bars->full_b[stage], 0, rowB + t * kTileN);
+        // this CTA fetches its 64-row half of the tile and multicasts it to the whole cluster, so every
+        // B byte crosses L2 -> SM once per cluster instead of once per CTA
+        tma_load_2d_multicast(smB + stage * kBytesB + cta_rank * (kBytesB / kCluster), &tmap_half,
+                              &bars->full_b[stage], 0, rowB + t * kTileN + cta_rank * (kTileN / kCluster),
+                              static_cast<uint16_t>((1u << kCluster) - 1u));
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -140,7 +150,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
           for (int k = 0; k < kDim / kUmmaK; ++k)
             mma_i8_ss(tmem_d, adesc[s] + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
         }
-        mma_commit(&bars->empty_b[stage]);
+        mma_commit_multicast(&bars->empty_b[stage], static_cast<uint16_t>((1u << kCluster) - 1u));
         mma_commit(&bars->tmem_full[as]);
         if (++stage == kStages) {
           stage = 0;
@@ -212,7 +222,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
     const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
     const int row = blk * kRowsPerCta + row_in_blk;
     p.mbuf[base + row] = out;
-    if (out != -1) {
+    if (out != -1 && row < nA) {
       p.aux[base + row] = make_uint2(best, s1);
       const int k = atomicAdd(p.cand_cnt + pair * 2 + dir, 1);
       p.cand_rows[base + k] = row;
@@ -225,12 +235,75 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
     tc_fence_after();
     tmem_dealloc(tmem_base, kAccStages * kAccCols);
   }
+  cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
 }
 
-// Exact resolution of the candidate rows of one (pair, direction).  One warp per candidate:
-// recompute dot(i, j) for the columns j of the winning slot (all columns if the maximum is shared
-// by several slots), oracle scan order per lane, multiset-aware merge across lanes.
+// Exact resolution of the candidate rows of one (pair, direction).
 // Slot s = cp * 32 + r holds the columns j = 128 t + 64 cp + 32 c + r, c in {0, 1}, t = 0, 1, ...
+// Candidates are bucketed by winning slot (counting sort in shared memory) so that the n2/64 columns
+// of a slot are staged in shared memory ONCE and reused by every candidate of the bucket (a warp per
+// candidate, dp4a, oracle scan order per lane, multiset-aware merge across lanes).  Rows whose
+// maximum is shared by several slots, and images with more than 8192 features, take the generic
+// path that scans global memory.
+namespace {
+
+constexpr int kSlotColsMax = 128;      // columns of one slot staged in shared memory (n2 <= 8192)
+constexpr int kSlotRowStride = 144;    // bytes; 128-byte descriptors padded so that LDS.128 is conflict-free
+
+__device__ __forceinline__ uint32_t dot128(const uint32_t (&a)[32], const uint4* bp) {
+  uint32_t d = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint4 v = bp[q];
+    d = __dp4a(a[4 * q], v.x, d);
+    d = __dp4a(a[4 * q + 1], v.y, d);
+    d = __dp4a(a[4 * q + 2], v.z, d);
+    d = __dp4a(a[4 * q + 3], v.w, d);
+  }
+  return d;
+}
+
+__device__ __forceinline__ void scan_update(uint32_t d, int j, uint32_t& bd, uint32_t& sd, int& bj) {
+  if (d > bd) {
+    sd = bd;
+    bd = d;
+    bj = j;
+  } else if (d > sd) {
+    sd = d;
+  }
+}
+
+// merge the per-lane scans and take the exact accept decision (lane 0 writes)
+__device__ __forceinline__ void finish_candidate(const MatchParams& p, int64_t out_index, uint32_t bd, uint32_t sd,
+                                                 int bj, uint32_t best_f, uint32_t s1, bool multi, int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t obd = __shfl_xor_sync(0xffffffffu, bd, o);
+    const uint32_t osd = __shfl_xor_sync(0xffffffffu, sd, o);
+    const int obj = __shfl_xor_sync(0xffffffffu, bj, o);
+    const uint32_t nsd = max(max(sd, osd), min(bd, obd));
+    if (obd > bd || (obd == bd && obj >= 0 && (bj < 0 || obj < bj))) {
+      bd = obd;
+      bj = obj;
+    }
+    sd = nsd;
+  }
+  if (lane == 0) {
+    const uint32_t second = multi ? sd : max(sd, s1);
+    int32_t out = -1;
+    if (bd > 0u && bd == best_f) {
+      const float fa = __ldg(p.acos_lut + min(bd, 262144u));
+      if (!(fa > p.max_distance)) {
+        const float fb = __ldg(p.acos_lut + min(second, 262144u));
+        if (!(fa >= __fmul_rn(p.max_ratio, fb))) out = bj;
+      }
+    }
+    p.mbuf[out_index] = out;
+  }
+}
+
+}  // namespace
+
 __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p, const uint8_t* __restrict__ desc) {
   const int pair = blockIdx.x >> 1;
   const int dir = blockIdx.x & 1;
@@ -244,14 +317,82 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
   const uint8_t* Bm = desc + static_cast<int64_t>(p.img_row0[ib]) * kDim;
   const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = warp; c < n_cand; c += 8) {
+  const int n_items = nB_pad / 64;
+  const bool staged = n_items <= kSlotColsMax;
+
+  __shared__ int s_start[66];
+  __shared__ int s_fill[65];
+  __shared__ __align__(16) uint8_t s_cols[kSlotColsMax * kSlotRowStride];
+
+  // ---- counting sort of the candidates by bucket (slot 0..63, 64 = generic path)
+  for (int b = threadIdx.x; b < 65; b += 256) s_fill[b] = 0;
+  __syncthreads();
+  for (int c = threadIdx.x; c < n_cand; c += 256) {
     const int row = p.cand_rows[base + c];
-    const int code = p.mbuf[base + row];  // -2 - slot
     const uint2 ax = p.aux[base + row];
-    const uint32_t best_f = ax.x, s1 = ax.y;
-    const int slot = -2 - code;
-    const int cp = slot >> 5, r = slot & 31;
-    const bool multi = (s1 == best_f);
+    const int bucket = (ax.x == ax.y || !staged) ? 64 : (-2 - p.mbuf[base + row]);
+    atomicAdd(&s_fill[bucket], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < 65; ++b) {
+      s_start[b] = acc;
+      acc += s_fill[b];
+      s_fill[b] = 0;
+    }
+    s_start[65] = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n_cand; c += 256) {
+    const int row = p.cand_rows[base + c];
+    const uint2 ax = p.aux[base + row];
+    const int bucket = (ax.x == ax.y || !staged) ? 64 : (-2 - p.mbuf[base + row]);
+    p.cand_sorted[base + s_start[bucket] + atomicAdd(&s_fill[bucket], 1)] = row;
+  }
+  __syncthreads();
+
+  // ---- staged buckets
+  for (int b = 0; b < 64; ++b) {
+    const int c0 = s_start[b], c1 = s_start[b + 1];
+    if (c0 == c1) continue;  // uniform
+    const int g = b >> 5, r = b & 31;
+    __syncthreads();  // previous bucket's readers are done with s_cols
+    for (int q = threadIdx.x; q < n_items * 8; q += 256) {
+      const int it = q >> 3, part = q & 7;
+      const int j = 128 * (it >> 1) + 64 * g + 32 * (it & 1) + r;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim) + part);
+      *reinterpret_cast<uint4*>(s_cols + it * kSlotRowStride + part * 16) = v;
+    }
+    __syncthreads();
+    for (int c = c0 + warp; c < c1; c += 8) {
+      const int row = p.cand_sorted[base + c];
+      const uint2 ax = p.aux[base + row];
+      uint32_t a[32];
+      const uint4* ap = reinterpret_cast<const uint4*>(A + static_cast<int64_t>(row) * kDim);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 v = __ldg(ap + q);
+        a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+      }
+      uint32_t bd = 0, sd = 0;
+      int bj = -1;
+      for (int it = lane; it < n_items; it += 32) {
+        const int j = 128 * (it >> 1) + 64 * g + 32 * (it & 1) + r;
+        const uint32_t d = dot128(a, reinterpret_cast<const uint4*>(s_cols + it * kSlotRowStride));
+        scan_update(d, j, bd, sd, bj);
+      }
+      finish_candidate(p, base + row, bd, sd, bj, ax.x, ax.y, false, lane);
+    }
+  }
+
+  // ---- generic bucket: scan global memory (whole row if the maximum is shared by several slots)
+  for (int c = s_start[64] + warp; c < s_start[65]; c += 8) {
+    const int row = p.cand_sorted[base + c];
+    const uint2 ax = p.aux[base + row];
+    const bool multi = (ax.x == ax.y);
+    const int slot = -2 - p.mbuf[base + row];
+    const int g = slot >> 5, r = slot & 31;
     uint32_t a[32];
     const uint4* ap = reinterpret_cast<const uint4*>(A + static_cast<int64_t>(row) * kDim);
 #pragma unroll
@@ -261,56 +402,17 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
     }
     uint32_t bd = 0, sd = 0;
     int bj = -1;
-    const int n_items = multi ? nB_pad : nB_pad / 64;
-    for (int it = lane; it < n_items; it += 32) {
-      const int j = multi ? it : (128 * (it >> 1) + 64 * cp + 32 * (it & 1) + r);
-      const uint4* bp = reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim);
-      uint32_t d = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint4 v = __ldg(bp + q);
-        d = __dp4a(a[4 * q], v.x, d);
-        d = __dp4a(a[4 * q + 1], v.y, d);
-        d = __dp4a(a[4 * q + 2], v.z, d);
-        d = __dp4a(a[4 * q + 3], v.w, d);
-      }
-      if (d > bd) {
-        sd = bd;
-        bd = d;
-        bj = j;
-      } else if (d > sd) {
-        sd = d;
-      }
+    const int n_scan = multi ? nB_pad : n_items;
+    for (int it = lane; it < n_scan; it += 32) {
+      const int j = multi ? it : (128 * (it >> 1) + 64 * g + 32 * (it & 1) + r);
+      const uint32_t d = dot128(a, reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim));
+      scan_update(d, j, bd, sd, bj);
     }
-    // merge lanes: larger best wins, ties -> lower column; second = max(min(b1, b2), s1, s2)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const uint32_t obd = __shfl_xor_sync(0xffffffffu, bd, o);
-      const uint32_t osd = __shfl_xor_sync(0xffffffffu, sd, o);
-      const int obj = __shfl_xor_sync(0xffffffffu, bj, o);
-      const uint32_t nsd = max(max(sd, osd), min(bd, obd));
-      if (obd > bd || (obd == bd && obj >= 0 && (bj < 0 || obj < bj))) {
-        bd = obd;
-        bj = obj;
-      }
-      sd = nsd;
-    }
-    if (lane == 0) {
-      const uint32_t second = multi ? sd : max(sd, s1);
-      int32_t out = -1;
-      if (bd > 0u && bd == best_f) {
-        const float fa = __ldg(p.acos_lut + min(bd, 262144u));
-        if (!(fa > p.max_distance)) {
-          const float fb = __ldg(p.acos_lut + min(second, 262144u));
-          if (!(fa >= __fmul_rn(p.max_ratio, fb))) out = bj;
-        }
-      }
-      p.mbuf[base + row] = out;
-    }
+    finish_candidate(p, base + row, bd, sd, bj, ax.x, ax.y, multi, lane);
   }
 }
 
-cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p, const uint8_t* desc, int n_pairs,
+cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const MatchParams& p, const uint8_t* desc, int n_pairs,
                              int max_strips, int n_dirs, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -321,8 +423,9 @@ cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p, cons
   }
   cudaError_t e = cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * 2 * n_pairs, stream);
   if (e != cudaSuccess) return e;
-  dim3 grid((max_strips + kStrips - 1) / kStrips, n_dirs, n_pairs);
-  b2m_k1_filter_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, p);
+  const int blocks = (max_strips + kStrips - 1) / kStrips;
+  dim3 grid((blocks + kCluster - 1) / kCluster * kCluster, n_dirs, n_pairs);
+  b2m_k1_filter_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, tmap_half, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   b2m_k1_resolve_kernel<<<2 * n_pairs, 256, 0, stream>>>(p, desc);

@@ -19,6 +19,7 @@ struct MatchParams {
   uint2* aux;                // device [n_pairs][2][mstride]: (best, S1) of candidate rows
   int32_t* cand_cnt;         // device [n_pairs][2] number of candidate rows
   int32_t* cand_rows;        // device [n_pairs][2][mstride] candidate row list
+  int32_t* cand_sorted;      // device [n_pairs][2][mstride] candidate rows bucketed by winning slot
 };
 
 struct CompactParams {
@@ -45,7 +46,7 @@ cudaError_t launch_k1_match(const CUtensorMap& tmap, const MatchParams& p, int n
                             cudaStream_t stream);
 // K1 v2: filter epilogue (slot maxima) + exact dp4a resolution of the candidate rows.  Bit-identical
 // results to launch_k1_match; requires a monotone (non-increasing) acos LUT.
-cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p, const uint8_t* desc, int n_pairs,
+cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const MatchParams& p, const uint8_t* desc, int n_pairs,
                              int max_strips, int n_dirs, cudaStream_t stream);
 cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream);
 

@@ -16,6 +16,7 @@
 // (+-1% inliers), as it is between two runs of the reference itself.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -60,6 +61,7 @@ struct VerifyParams {
   uint64_t seed;
   int32_t single_kind;        // >= 0: only this kind runs (stand-alone estimator API), no camera model
   int32_t force_calibrated;   // stand-alone: -1 use camera flags
+  unsigned long long* prof;   // optional [3][8] cycle counters (B2M_PROF=1), else nullptr
 };
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -93,6 +95,34 @@ __device__ __forceinline__ double residual(const double* M, double x1, double y1
   return sampson_sq(M, x1, y1, x2, y2);
 }
 
+// Division-free fp32 inlier test used by the hypothesis-scoring loop: r <= thr  <=>  lhs <= thr * rhs
+// with r = lhs / rhs.  Returns +1 inlier, 0 outlier, -1 borderline (within 1 % of the threshold, or
+// not finite): the caller re-evaluates those in fp64, so decisions equal the fp64 evaluation.
+template <int KIND>
+__device__ __forceinline__ int inlier_f32(const float* M, float x1, float y1, float x2, float y2, float thr) {
+  float lhs, rhs;
+  if (KIND == 2) {
+    const float u = fmaf(M[0], x1, fmaf(M[1], y1, M[2]));
+    const float v = fmaf(M[3], x1, fmaf(M[4], y1, M[5]));
+    const float w = fmaf(M[6], x1, fmaf(M[7], y1, M[8]));
+    const float ex = fmaf(x2, w, -u), ey = fmaf(y2, w, -v);
+    lhs = fmaf(ex, ex, ey * ey);
+    rhs = thr * w * w;
+  } else {
+    const float a0 = fmaf(M[0], x1, fmaf(M[1], y1, M[2]));
+    const float a1 = fmaf(M[3], x1, fmaf(M[4], y1, M[5]));
+    const float a2 = fmaf(M[6], x1, fmaf(M[7], y1, M[8]));
+    const float b0 = fmaf(M[0], x2, fmaf(M[3], y2, M[6]));
+    const float b1 = fmaf(M[1], x2, fmaf(M[4], y2, M[7]));
+    const float num = fmaf(x2, a0, fmaf(y2, a1, a2));
+    lhs = num * num;
+    rhs = thr * fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, b1 * b1)));
+  }
+  const int in = lhs <= 0.99f * rhs ? 1 : 0;
+  const int out = lhs >= 1.01f * rhs ? 1 : 0;
+  return in | ((in | out) ^ 1) << 1;  // bit 0: inlier, bit 1: borderline (neither clearly in nor out)
+}
+
 template <int KIND>
 struct Traits;
 template <>
@@ -108,7 +138,14 @@ struct Traits<2> {  // H: 4-point DLT for both
   static constexpr int kMin = 4, kLocalMin = 4, kMaxModels = 1, kMaxLocalModels = 1;
 };
 
+constexpr int kChunkModels = 256;  // models scored per pass of the fp32 scoring loop
+constexpr int kPtsPerThread = 8;    // points held in registers per thread and pass
+
 struct Shared {
+  double chunk_d[kChunkModels][9];  // models of the current chunk (fp64, for borderline rechecks)
+  float chunk_f[kChunkModels][12];  // same, fp32, padded to three 16-byte loads
+  int chunk_cnt[kChunkModels];      // inlier counts of the chunk's models
+  int scan[kRansacThreads];
   double best_model[9];
   double cand_models[10 * 9];
   double red[4][64];     // per-warp partial sums (45 normal-equation entries + 8 moments)
@@ -143,6 +180,15 @@ __device__ __forceinline__ void warp_score(const double* M, const double4* pts, 
   sum = warp_sum_d(s);
 }
 
+#define B2M_TICK(slot)                                   \
+  do {                                                   \
+    if (P.prof && tid == 0) {                            \
+      const long long _n = clock64();                    \
+      prof_acc[slot] += _n - prof_t;                     \
+      prof_t = _n;                                       \
+    }                                                    \
+  } while (0)
+
 template <int KIND>
 __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int64_t off, int n,
                                const PointXform& X, double thr, uint64_t key, const b2m_ransac_opts& ro) {
@@ -175,6 +221,8 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
 
   int trials = 0;
   double mdl[T::kMaxModels * 9];
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_t = clock64();
   while (trials < max_trials) {
     int nb = min(kRansacThreads, max_trials - trials);
     if (trials < ro.min_num_trials) nb = min(nb, ro.min_num_trials - trials);
@@ -198,30 +246,95 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       for (int j = 0; j < T::kMin; ++j) load_pt(pts, off + idx[j], X, x1[j], y1[j], x2[j], y2[j]);
       if (KIND == 0) nm = minimal_E5(x1, y1, x2, y2, mdl);
       if (KIND == 1) nm = minimal_F7(x1, y1, x2, y2, mdl);
-      if (KIND == 2) nm = minimal_H4(x1, y1, x2, y2, mdl);
+      if (KIND == 2) nm = minimal_H4_closed(x1, y1, x2, y2, mdl);
     }
     // ---- phase 2: score every model of every hypothesis of this warp (warp = one model at a time)
+    B2M_TICK(0);
+    //      Models go to shared memory in chunks; every thread keeps kPtsPerThread points in registers
+    //      (fp32) and sweeps the chunk's models: division-free fp32 test, fp64 only for borderline
+    //      points.  Only inlier COUNTS are formed here; among equal counts the earlier trial wins
+    //      (the residual-sum tie-break of U:optim/support_measurement.h applies from the LO stage on).
     int my_cnt = -1, my_m = 0;
     double my_sum = 1e300;
-    for (int h = 0; h < 32; ++h) {
-      const int nm_h = __shfl_sync(0xffffffffu, nm, h);
-      for (int m = 0; m < nm_h; ++m) {
-        double M[9];
+    sh.scan[tid] = nm;
+    __syncthreads();
+    int my_base = 0, total_models = 0;
+    for (int t = 0; t < kRansacThreads; ++t) {
+      const int v = sh.scan[t];
+      if (t < tid) my_base += v;
+      total_models += v;
+    }
+    const float thr_f = static_cast<float>(thr);
+    for (int chunk0 = 0; chunk0 < total_models; chunk0 += kChunkModels) {
+      const int n_chunk = min(kChunkModels, total_models - chunk0);
+      for (int m = 0; m < nm; ++m) {
+        const int g = my_base + m - chunk0;
+        if (g >= 0 && g < kChunkModels) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) M[k] = shfl_d(mdl[(lane == h ? m : 0) * 9 + k], h);
-        int c;
-        double s;
-        warp_score<KIND>(M, pts, off, n, X, thr, lane, c, s);
-        if (lane == h && (c > my_cnt || (c == my_cnt && s < my_sum))) {
-          my_cnt = c;
-          my_sum = s;
-          my_m = m;
+          for (int k = 0; k < 9; ++k) {
+            sh.chunk_d[g][k] = mdl[m * 9 + k];
+            sh.chunk_f[g][k] = static_cast<float>(mdl[m * 9 + k]);
+          }
         }
       }
+      for (int m = tid; m < kChunkModels; m += kRansacThreads) sh.chunk_cnt[m] = 0;
+      __syncthreads();
+      for (int pb = 0; pb < n; pb += kRansacThreads * kPtsPerThread) {
+        float px1[kPtsPerThread], py1[kPtsPerThread], px2[kPtsPerThread], py2[kPtsPerThread];
+#pragma unroll
+        for (int q = 0; q < kPtsPerThread; ++q) {
+          const int i = pb + q * kRansacThreads + tid;
+          // slots past the end get a far-away point: a clear outlier for every finite model
+          double x1 = 0, y1 = 0, x2 = 1e15, y2 = 1e15;
+          if (i < n) load_pt(pts, off + i, X, x1, y1, x2, y2);
+          px1[q] = static_cast<float>(x1); py1[q] = static_cast<float>(y1);
+          px2[q] = static_cast<float>(x2); py2[q] = static_cast<float>(y2);
+        }
+        for (int m = 0; m < n_chunk; ++m) {
+          float Mf[12];
+          const float4* mp = reinterpret_cast<const float4*>(sh.chunk_f[m]);
+          const float4 m0 = mp[0], m1 = mp[1], m2 = mp[2];
+          Mf[0] = m0.x; Mf[1] = m0.y; Mf[2] = m0.z; Mf[3] = m0.w;
+          Mf[4] = m1.x; Mf[5] = m1.y; Mf[6] = m1.z; Mf[7] = m1.w; Mf[8] = m2.x;
+          int c = 0, flags = 0;
+#pragma unroll
+          for (int q = 0; q < kPtsPerThread; ++q) {
+            const int f = inlier_f32<KIND>(Mf, px1[q], py1[q], px2[q], py2[q], thr_f);
+            c += f & 1;
+            flags |= f;
+          }
+          if (flags & 2) {  // rare: a borderline point -> redo this thread's points of this model in fp64
+            c = 0;
+            for (int q = 0; q < kPtsPerThread; ++q) {
+              const int i = pb + q * kRansacThreads + tid;
+              if (i < n) {
+                double x1, y1, x2, y2;
+                load_pt(pts, off + i, X, x1, y1, x2, y2);
+                c += (residual<KIND>(sh.chunk_d[m], x1, y1, x2, y2) <= thr) ? 1 : 0;
+              }
+            }
+          }
+          c = __reduce_add_sync(0xffffffffu, c);
+          if (lane == 0 && c) atomicAdd(&sh.chunk_cnt[m], c);
+        }
+      }
+      __syncthreads();
+      for (int m = 0; m < nm; ++m) {
+        const int g = my_base + m - chunk0;
+        if (g >= 0 && g < kChunkModels) {
+          const int c = sh.chunk_cnt[g];
+          if (c > my_cnt) {
+            my_cnt = c;
+            my_m = m;
+          }
+        }
+      }
+      __syncthreads();
     }
     sh.cnt_arr[tid] = my_cnt;
     sh.sum_arr[tid] = my_sum;
     __syncthreads();
+    B2M_TICK(1);
     if (tid == 0) {
       int w = -1, bc = sh.best_cnt;
       double bs = sh.best_sum;
@@ -246,6 +359,36 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       if (tid == sh.winner)
         for (int k = 0; k < 9; ++k) sh.best_model[k] = mdl[my_m * 9 + k];
       __syncthreads();
+      {  // exact fp64 support (count, residual sum) of the new best model
+        double M[9];
+        for (int k = 0; k < 9; ++k) M[k] = sh.best_model[k];
+        int c;
+        double s;
+        int cl = 0;
+        double sl = 0.0;
+        for (int i = tid; i < n; i += kRansacThreads) {
+          double x1, y1, x2, y2;
+          load_pt(pts, off + i, X, x1, y1, x2, y2);
+          const double r = residual<KIND>(M, x1, y1, x2, y2);
+          if (r <= thr) {
+            ++cl;
+            sl += r;
+          }
+        }
+        c = __reduce_add_sync(0xffffffffu, cl);
+        s = warp_sum_d(sl);
+        if (lane == 0) {
+          sh.cand_cnt[warp] = c;
+          sh.cand_sum[warp] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          sh.best_cnt = sh.cand_cnt[0] + sh.cand_cnt[1] + sh.cand_cnt[2] + sh.cand_cnt[3];
+          sh.best_sum = sh.cand_sum[0] + sh.cand_sum[1] + sh.cand_sum[2] + sh.cand_sum[3];
+        }
+        __syncthreads();
+      }
+      B2M_TICK(2);
       // ---- phase 3: recursive local optimisation on the inliers of the current best
       if (sh.best_cnt > T::kMin && sh.best_cnt >= T::kLocalMin) {
         for (int lt = 0; lt < kMaxLocalTrials; ++lt) {
@@ -303,18 +446,19 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
             if (lane == 0) sh.red[warp][k] = v;
           }
           __syncthreads();
+          B2M_TICK(3);
           if (tid == 0) {
             double St[45];
             for (int k = 0; k < 45; ++k) St[k] = sh.red[0][k] + sh.red[1][k] + sh.red[2][k] + sh.red[3][k];
             int nc = 0;
             if (KIND == 0) {
-              double A[81], V[81], w[9], N[36];
-              sym9_expand(St, A);
-              jacobi_eig_sym<9>(A, V, w);
-              int idx[4];
-              smallest_k<9>(w, 4, idx);
+              // least-squares 4-D null space of the N x 9 system.  five_point_from_nullspace fixes the
+              // coefficient of its LAST basis vector to 1, so that one must be the smallest singular
+              // vector (for noise-free inliers it IS the essential matrix).
+              double Nr[36], N[36];
+              smallest_eigvecs_invit<4>(St, Nr);
               for (int k = 0; k < 4; ++k)
-                for (int e = 0; e < 9; ++e) N[k * 9 + e] = V[e * 9 + idx[3 - k]];
+                for (int e = 0; e < 9; ++e) N[k * 9 + e] = Nr[(3 - k) * 9 + e];
               nc = five_point_from_nullspace(N, sh.cand_models);
             } else if (KIND == 1) {
               nc = finish_F8(St, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
@@ -324,6 +468,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
             sh.n_cand = nc;
           }
           __syncthreads();
+          B2M_TICK(4);
           const int nc = sh.n_cand;
           for (int m = warp; m < nc; m += kRansacThreads / 32) {
             double C[9];
@@ -349,6 +494,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
               for (int k = 0; k < 9; ++k) sh.best_model[k] = sh.cand_models[w * 9 + k];
           }
           __syncthreads();
+          B2M_TICK(5);
           if (sh.best_cnt <= prev_best) break;
         }
       }
@@ -368,6 +514,9 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
     load_pt(pts, off + i, X, x1, y1, x2, y2);
     mask[i] = (ok && residual<KIND>(M, x1, y1, x2, y2) <= thr) ? 1 : 0;
   }
+  B2M_TICK(6);
+  if (P.prof && tid == 0)
+    for (int k = 0; k < 8; ++k) atomicAdd(P.prof + KIND * 8 + k, static_cast<unsigned long long>(prof_acc[k]));
   if (tid == 0) {
     P.sup_cnt[out_idx] = sh.best_cnt;
     P.success[out_idx] = ok ? 1 : 0;
@@ -375,7 +524,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
   }
 }
 
-__global__ void __launch_bounds__(kRansacThreads) b2m_ransac_kernel(const VerifyParams P) {
+__global__ void __launch_bounds__(kRansacThreads, 3) b2m_ransac_kernel(const VerifyParams P) {
   __shared__ Shared sh;
   const int pair = blockIdx.x;
   const int kind = P.single_kind >= 0 ? P.single_kind : static_cast<int>(blockIdx.y);
@@ -633,6 +782,7 @@ struct VerifyState {
   int32_t* h_inl_cnt[2] = {nullptr, nullptr};
   uint2* h_inliers[2] = {nullptr, nullptr};
   DevCamera* d_cams = nullptr;
+  unsigned long long* d_prof = nullptr;
   int n_cams = 0;
   const void* cams_of = nullptr;  // ImageSet the cameras were uploaded for
   void release() {
@@ -761,6 +911,11 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
   P.seed = ctx->seed;
   P.single_kind = -1;
   P.force_calibrated = -1;
+  if (!V->d_prof && getenv("B2M_PROF")) {
+    cudaMalloc(&V->d_prof, sizeof(unsigned long long) * 24);
+    cudaMemset(V->d_prof, 0, sizeof(unsigned long long) * 24);
+  }
+  P.prof = V->d_prof;
   (void)S;
   b2m_ransac_kernel<<<dim3(nb, 3), kRansacThreads, 0, ctx->stream>>>(P);
   V_TRY(ctx, cudaGetLastError());
@@ -822,6 +977,16 @@ int verify_batch_collect(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int 
 void verify_release(b2m_ctx* ctx) {
   if (ctx->verify_state) {
     VerifyState* V = static_cast<VerifyState*>(ctx->verify_state);
+    if (V->d_prof) {
+      unsigned long long h[24];
+      cudaMemcpy(h, V->d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+      const char* names[8] = {"solve", "score", "exact_support", "lo_accumulate", "lo_solve", "lo_score", "final", "-"};
+      for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 7; ++j)
+          fprintf(stderr, "[b2m prof] kind %d %-14s %10.3f Mcycles\n", k, names[j], h[k * 8 + j] / 1e6);
+      cudaFree(V->d_prof);
+      V->d_prof = nullptr;
+    }
     V->release();
     delete V;
     ctx->verify_state = nullptr;

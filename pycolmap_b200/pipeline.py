@@ -1,0 +1,410 @@
+"""Host-side mirror of the reference's matching / verification entry points.
+
+Same names, keyword arguments, defaults, dict-merge behaviour and error types as
+  match_exhaustive / match_sequential   R:pipeline/match_features.h:22-49, 219-235
+  verify_matches                        R:pipeline/match_features.h:51-68, 255-260
+  estimate_two_view_geometry, estimate_calibrated_two_view_geometry, squared_sampson_error
+                                        R:estimators/two_view_geometry.h:95-175
+  essential / fundamental / homography_matrix_estimation
+                                        R:estimators/essential_matrix.h:19-103, fundamental_matrix.h:17-50,
+                                        homography_matrix.h:17-48
+The compute path is libb200match.so (C ABI, include/b200match.h); this module only does what the
+reference's controllers do on the host: database I/O, pair generation, the write rules.
+"""
+import os
+import threading
+import time
+
+import numpy as np
+
+from . import _lib
+from .database import Database
+from .options import (Device, ExhaustiveMatchingOptions, RANSACOptions, SequentialMatchingOptions,
+                      SiftMatchingOptions, TwoViewGeometryConfiguration, TwoViewGeometryOptions, _enum_from)
+
+_contexts = {}
+_ctx_lock = threading.Lock()
+
+
+def get_context(device_index=0):
+    """One b2m context per process and GPU (created lazily)."""
+    with _ctx_lock:
+        c = _contexts.get(device_index)
+        if c is None or c.h is None:
+            c = _lib.Context(device=device_index, seed=0)
+            _contexts[device_index] = c
+        return c
+
+
+def _check_file_exists(path, where):
+    # THROW_CHECK_FILE_EXISTS (R:log_exceptions.h:137-141) -> ValueError with the [file:line] prefix
+    if not os.path.isfile(os.fspath(path)):
+        raise ValueError(f"[{where}] Check Failed: File {os.fspath(path)} does not exist.")
+
+
+def _resolve_device(device, sift_options):
+    """IsGPU / VerifyGPUParams (R:utils.h:11-31).  `auto` means the GPU; there is no CPU path."""
+    device = _enum_from(Device, device)
+    if device == Device.cpu:
+        raise ValueError("[pipeline.py] pycolmap_b200 has no CPU path: use Device.auto or Device.cuda")
+    gi = str(sift_options.gpu_index).split(",")[0].strip()
+    return max(0, int(gi)) if gi not in ("", "-1") else 0
+
+
+def _sift_struct(ctx, o):
+    return ctx.sift_opts(max_ratio=float(o.max_ratio), max_distance=float(o.max_distance),
+                         cross_check=int(bool(o.cross_check)), max_num_matches=int(o.max_num_matches),
+                         guided_matching=int(bool(o.guided_matching)))
+
+
+def _ransac_kwargs(r):
+    return dict(max_error=float(r.max_error), min_inlier_ratio=float(r.min_inlier_ratio),
+                confidence=float(r.confidence), dyn_num_trials_multiplier=float(r.dyn_num_trials_multiplier),
+                min_num_trials=int(r.min_num_trials), max_num_trials=int(r.max_num_trials))
+
+
+def _tvg_struct(ctx, o):
+    return ctx.tvg_opts(ransac=_ransac_kwargs(o.ransac), min_num_inliers=int(o.min_num_inliers),
+                        min_E_F_inlier_ratio=float(o.min_E_F_inlier_ratio),
+                        max_H_inlier_ratio=float(o.max_H_inlier_ratio),
+                        watermark_min_inlier_ratio=float(o.watermark_min_inlier_ratio),
+                        watermark_border_size=float(o.watermark_border_size),
+                        detect_watermark=int(bool(o.detect_watermark)),
+                        multiple_ignore_watermark=int(bool(o.multiple_ignore_watermark)),
+                        force_H_use=int(bool(o.force_H_use)), compute_relative_pose=int(bool(o.compute_relative_pose)),
+                        multiple_models=int(bool(o.multiple_models)))
+
+
+def _run_interruptible(ctx, fn):
+    """PyWait (R:helpers.h:335-347): the C call runs in a worker thread, the caller polls so that
+    Ctrl-C is honoured: KeyboardInterrupt -> b2m_request_stop -> join -> re-raise."""
+    box = {}
+
+    def work():
+        try:
+            box["r"] = fn()
+        except BaseException as e:  # noqa: BLE001
+            box["e"] = e
+    t = threading.Thread(target=work, daemon=True)
+    t.start()
+    try:
+        while t.is_alive():
+            t.join(0.2)
+    except KeyboardInterrupt:
+        ctx.lib.b2m_request_stop(ctx.h)
+        t.join()
+        raise
+    if "e" in box:
+        raise box["e"]
+    return box["r"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# pair generators (U:controllers/feature_matching.cc)
+# ---------------------------------------------------------------------------------------------------
+def exhaustive_pair_blocks(n, block_size):
+    """Yields index-pair arrays block by block in ExhaustiveFeatureMatcher::Run order."""
+    nb = (n + block_size - 1) // block_size
+    for b1 in range(nb):
+        i1 = np.arange(b1 * block_size, min(n, (b1 + 1) * block_size))
+        for b2 in range(nb):
+            i2 = np.arange(b2 * block_size, min(n, (b2 + 1) * block_size))
+            a, b = np.meshgrid(i1, i2, indexing="ij")
+            ma, mb = a % block_size, b % block_size
+            keep = ((a > b) & (ma <= mb)) | ((a < b) & (ma < mb))
+            if keep.any():
+                yield np.stack([a[keep], b[keep]], 1).astype(np.int32)
+
+
+def sequential_pairs(n, overlap, quadratic_overlap):
+    out, seen = [], set()
+    for i1 in range(n):
+        for k in range(overlap):
+            for i2 in ((i1 + k + 1,) + ((i1 + (1 << k),) if quadratic_overlap else ())):
+                if i2 < n and (i1, i2) not in seen:
+                    seen.add((i1, i2))
+                    out.append((i1, i2))
+    return np.array(out, np.int32).reshape(-1, 2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# database-driven pipelines
+# ---------------------------------------------------------------------------------------------------
+class _Loaded:
+    pass
+
+
+def _load_image_set(db, ctx, need_geometry, order_by_name=False):
+    images = db.read_all_images()
+    if order_by_name:
+        images = sorted(images, key=lambda r: r[1])
+    L = _Loaded()
+    L.ids = [r[0] for r in images]
+    L.names = [r[1] for r in images]
+    descs = [db.read_descriptors(i) for i in L.ids]
+    kpts = cams = None
+    if need_geometry:
+        kpts = [np.ascontiguousarray(db.read_keypoints(i)[:, :2]) for i in L.ids]
+        cam_cache = {}
+        cams = []
+        for (_, _, cid) in images:
+            if cid not in cam_cache:
+                cam_cache[cid] = db.read_camera(cid)
+            cams.append(cam_cache[cid])
+        for d, k in zip(descs, kpts):
+            if len(d) != len(k):
+                raise ValueError("[pipeline.py] Check Failed: keypoints.rows == descriptors.rows")
+    ctx.set_images(descs, kpts, cams)
+    return L
+
+
+def _write_results(db, L, pairs, res, verified):
+    """FeatureMatcherController::Match tail (row P3): one transaction per chunk."""
+    with db.transaction():
+        for k in range(len(pairs)):
+            id1, id2 = L.ids[pairs[k, 0]], L.ids[pairs[k, 1]]
+            v = res.view(k)
+            db.write_matches(id1, id2, res.matches(k))
+            if verified:
+                E = np.array(v.E).reshape(3, 3)
+                F = np.array(v.F).reshape(3, 3)
+                H = np.array(v.H).reshape(3, 3)
+                db.write_two_view_geometry(id1, id2, v.config, res.inlier_matches(k), F, E, H)
+
+
+def _match_pairs_into_db(db, ctx, L, pair_chunks, sift, tvg, skip_existing=True):
+    have_m = db.existing_pair_ids("matches") if skip_existing else set()
+    have_g = db.existing_pair_ids("two_view_geometries") if skip_existing else set()
+    from .database import image_pair_to_pair_id
+    for pairs in pair_chunks:
+        if len(pairs) == 0:
+            continue
+        keep = np.ones(len(pairs), bool)
+        for k, (a, b) in enumerate(pairs):
+            if a == b:
+                keep[k] = False
+                continue
+            pid = image_pair_to_pair_id(L.ids[a], L.ids[b])
+            if pid in have_m and pid in have_g:
+                keep[k] = False  # both results stored: skip (resume semantics)
+            have_m.add(pid)
+            have_g.add(pid)
+        pairs = np.ascontiguousarray(pairs[keep])
+        if len(pairs) == 0:
+            continue
+        res = _run_interruptible(ctx, lambda p=pairs: ctx.match_pairs(p, sift, tvg))
+        _write_results(db, L, pairs, res, tvg is not None)
+        res.free()
+
+
+def _chunked(gen, target=65536):
+    buf, n = [], 0
+    for p in gen:
+        buf.append(p)
+        n += len(p)
+        if n >= target:
+            yield np.concatenate(buf)
+            buf, n = [], 0
+    if buf:
+        yield np.concatenate(buf)
+
+
+def match_exhaustive(database_path, sift_options=None, matching_options=None, verification_options=None,
+                     device=Device.auto):
+    """Exhaustive feature matching + geometric verification of every image pair of the database."""
+    _check_file_exists(database_path, "match_features.h:32")
+    sift_options = SiftMatchingOptions.coerce(sift_options)
+    matching_options = ExhaustiveMatchingOptions.coerce(matching_options)
+    verification_options = TwoViewGeometryOptions.coerce(verification_options)
+    if matching_options.block_size <= 1:
+        raise ValueError("[pipeline.py] Check Failed: block_size > 1")
+    ctx = get_context(_resolve_device(device, sift_options))
+    with Database(database_path) as db:
+        L = _load_image_set(db, ctx, need_geometry=True)
+        _match_pairs_into_db(db, ctx, L, _chunked(exhaustive_pair_blocks(len(L.ids), matching_options.block_size)),
+                             _sift_struct(ctx, sift_options), _tvg_struct(ctx, verification_options))
+
+
+def match_sequential(database_path, sift_options=None, matching_options=None, verification_options=None,
+                     device=Device.auto):
+    """Sequential feature matching (images ordered by name; overlap / quadratic overlap)."""
+    _check_file_exists(database_path, "match_features.h:32")
+    sift_options = SiftMatchingOptions.coerce(sift_options)
+    matching_options = SequentialMatchingOptions.coerce(matching_options)
+    verification_options = TwoViewGeometryOptions.coerce(verification_options)
+    if matching_options.loop_detection:
+        raise ValueError("[pipeline.py] loop_detection needs a vocabulary tree: out of scope (SURVEY.md row B6)")
+    ctx = get_context(_resolve_device(device, sift_options))
+    with Database(database_path) as db:
+        L = _load_image_set(db, ctx, need_geometry=True, order_by_name=True)
+        pairs = sequential_pairs(len(L.ids), matching_options.overlap, matching_options.quadratic_overlap)
+        _match_pairs_into_db(db, ctx, L, [pairs], _sift_struct(ctx, sift_options),
+                             _tvg_struct(ctx, verification_options))
+
+
+def verify_matches(database_path, pairs_path, options=None):
+    """Run geometric verification of the matches of the listed pairs (`name1 name2` per line).
+    Pairs without stored raw matches are matched first, like the reference's ImagePairsFeatureMatcher."""
+    _check_file_exists(database_path, "match_features.h:54")
+    _check_file_exists(pairs_path, "match_features.h:55")
+    options = TwoViewGeometryOptions.coerce(options)
+    sift_options = SiftMatchingOptions()
+    ctx = get_context(0)
+    with Database(database_path) as db:
+        L = _load_image_set(db, ctx, need_geometry=True)
+        name_to_idx = {n: i for i, n in enumerate(L.names)}
+        todo_verify, todo_match, seen = [], [], set()
+        with open(pairs_path) as f:
+            for line in f:
+                line = line.strip()
+                if not line or line.startswith("#"):
+                    continue
+                parts = line.split()
+                if len(parts) < 2 or parts[0] not in name_to_idx or parts[1] not in name_to_idx:
+                    continue  # upstream logs and skips unknown images
+                a, b = name_to_idx[parts[0]], name_to_idx[parts[1]]
+                if a == b or (min(a, b), max(a, b)) in seen:
+                    continue
+                seen.add((min(a, b), max(a, b)))
+                has_m = db.exists_matches(L.ids[a], L.ids[b])
+                has_g = db.exists_inlier_matches(L.ids[a], L.ids[b])
+                if has_m and has_g:
+                    continue
+                (todo_verify if has_m else todo_match).append((a, b))
+        tvg = _tvg_struct(ctx, options)
+        if todo_match:
+            _match_pairs_into_db(db, ctx, L, [np.array(todo_match, np.int32)], _sift_struct(ctx, sift_options), tvg,
+                                 skip_existing=False)
+        with db.transaction():
+            for a, b in todo_verify:
+                id1, id2 = L.ids[a], L.ids[b]
+                m = db.read_matches(id1, id2)
+                kp1 = db.read_keypoints(id1)[:, :2].astype(np.float64)
+                kp2 = db.read_keypoints(id2)[:, :2].astype(np.float64)
+                cam1 = db.read_camera(db.con.execute("SELECT camera_id FROM images WHERE image_id=?", (id1,)).fetchone()[0])
+                cam2 = db.read_camera(db.con.execute("SELECT camera_id FROM images WHERE image_id=?", (id2,)).fetchone()[0])
+                cfg, inl, E, F, H = TwoViewGeometryConfiguration.UNDEFINED, np.zeros((0, 2), np.uint32), None, None, None
+                if len(m) >= options.min_num_inliers:
+                    r, inl = ctx.estimate_two_view_geometry(cam1, kp1, cam2, kp2, m, tvg)
+                    cfg = r.config
+                    E, F, H = (np.array(x).reshape(3, 3) for x in (r.E, r.F, r.H))
+                if len(inl) < options.min_num_inliers:  # controller write rule (row P3)
+                    cfg, inl, E, F, H = TwoViewGeometryConfiguration.UNDEFINED, np.zeros((0, 2), np.uint32), None, None, None
+                db.write_two_view_geometry(id1, id2, int(cfg), inl, F, E, H)
+
+
+# ---------------------------------------------------------------------------------------------------
+# estimators
+# ---------------------------------------------------------------------------------------------------
+class TwoViewGeometry:
+    """R:estimators/two_view_geometry.h:82-93 (read-only members)."""
+
+    def __init__(self, config=TwoViewGeometryConfiguration.UNDEFINED, E=None, F=None, H=None, inlier_matches=None,
+                 tri_angle=0.0):
+        self.config = TwoViewGeometryConfiguration(int(config))
+        self.E = np.zeros((3, 3)) if E is None else np.array(E, np.float64).reshape(3, 3)
+        self.F = np.zeros((3, 3)) if F is None else np.array(F, np.float64).reshape(3, 3)
+        self.H = np.zeros((3, 3)) if H is None else np.array(H, np.float64).reshape(3, 3)
+        self.cam2_from_cam1 = None
+        self.inlier_matches = (np.zeros((0, 2), np.uint32) if inlier_matches is None
+                               else np.array(inlier_matches, np.uint32).reshape(-1, 2))
+        self.tri_angle = float(tri_angle)
+
+    def invert(self):
+        self.F = self.F.T.copy()
+        self.E = self.E.T.copy()
+        if np.abs(self.H).sum() > 0:
+            self.H = np.linalg.inv(self.H)
+        self.inlier_matches = self.inlier_matches[:, ::-1].copy()
+
+    def __repr__(self):
+        return f"TwoViewGeometry(config={self.config.name}, num_inliers={len(self.inlier_matches)})"
+
+
+def _camera_dict(camera):
+    if isinstance(camera, dict):
+        return camera
+    # duck-typed pycolmap.Camera: model (name or id), width, height, params, has_prior_focal_length
+    model = getattr(camera, "model", getattr(camera, "model_id", 0))
+    name = getattr(model, "name", model)
+    model_id = {"SIMPLE_PINHOLE": 0, "PINHOLE": 1, 0: 0, 1: 1}.get(name)
+    if model_id is None:
+        raise ValueError(f"[pipeline.py] camera model {name} is not supported (SIMPLE_PINHOLE / PINHOLE)")
+    return dict(model=model_id, width=int(camera.width), height=int(camera.height), params=list(camera.params),
+                has_prior_focal_length=int(getattr(camera, "has_prior_focal_length", False)))
+
+
+def _points(p, name):
+    p = np.asarray(p, np.float64)
+    if p.ndim != 2 or p.shape[1] != 2:
+        raise ValueError(f"[pipeline.py] Check Failed: {name} is an N x 2 array")
+    return np.ascontiguousarray(p)
+
+
+def estimate_two_view_geometry(camera1, points1, camera2, points2, matches=None, options=None):
+    options = TwoViewGeometryOptions.coerce(options)
+    p1, p2 = _points(points1, "points1"), _points(points2, "points2")
+    if matches is None and len(p1) != len(p2):
+        raise ValueError("[two_view_geometry.h:137] Check Failed: points1.size() == points2.size()")
+    ctx = get_context(0)
+    r, inl = ctx.estimate_two_view_geometry(_camera_dict(camera1), p1, _camera_dict(camera2), p2, matches,
+                                            _tvg_struct(ctx, options))
+    return TwoViewGeometry(r.config, r.E, r.F, r.H, inl)
+
+
+def estimate_calibrated_two_view_geometry(camera1, points1, camera2, points2, matches=None, options=None):
+    c1, c2 = dict(_camera_dict(camera1)), dict(_camera_dict(camera2))
+    c1["has_prior_focal_length"] = c2["has_prior_focal_length"] = 1
+    return estimate_two_view_geometry(c1, points1, c2, points2, matches, options)
+
+
+def _ransac(kind, p1, p2, opts):
+    ctx = get_context(0)
+    opts = RANSACOptions.coerce(opts)
+    return ctx.ransac_model(kind, p1, p2, ctx.ransac_opts(**_ransac_kwargs(opts)))
+
+
+def fundamental_matrix_estimation(points1, points2, estimation_options=None):
+    p1, p2 = _points(points1, "points1"), _points(points2, "points2")
+    if len(p1) != len(p2):
+        raise ValueError("[fundamental_matrix.h:22] Check Failed: points1.size() == points2.size()")
+    r = _ransac(1, p1, p2, estimation_options)
+    return None if r is None else {"F": r["model"], "num_inliers": r["num_inliers"], "inliers": r["inliers"]}
+
+
+def homography_matrix_estimation(points1, points2, estimation_options=None):
+    p1, p2 = _points(points1, "points1"), _points(points2, "points2")
+    if len(p1) != len(p2):
+        raise ValueError("[homography_matrix.h:21] Check Failed: points1.size() == points2.size()")
+    r = _ransac(2, p1, p2, estimation_options)
+    return None if r is None else {"H": r["model"], "num_inliers": r["num_inliers"], "inliers": r["inliers"]}
+
+
+def essential_matrix_estimation(points1, points2, camera1, camera2, estimation_options=None):
+    p1, p2 = _points(points1, "points1"), _points(points2, "points2")
+    if len(p1) != len(p2):
+        raise ValueError("[essential_matrix.h:26] Check Failed: points1.size() == points2.size()")
+    c1, c2 = _camera_dict(camera1), _camera_dict(camera2)
+
+    def norm(c, p):
+        pr = c["params"]
+        return (p - [pr[1], pr[2]]) / pr[0] if c["model"] == 0 else (p - [pr[2], pr[3]]) / [pr[0], pr[1]]
+
+    def mean_f(c):
+        return c["params"][0] if c["model"] == 0 else 0.5 * (c["params"][0] + c["params"][1])
+    o = RANSACOptions.coerce(estimation_options)
+    o = RANSACOptions(o.todict())
+    # R:estimators/essential_matrix.h:42-46: threshold averaged over both cameras
+    o.max_error = 0.5 * (o.max_error / mean_f(c1) + o.max_error / mean_f(c2))
+    r = _ransac(0, norm(c1, p1), norm(c2, p2), o)
+    return None if r is None else {"E": r["model"], "num_inliers": r["num_inliers"], "inliers": r["inliers"]}
+
+
+def squared_sampson_error(points1, points2, E):
+    ctx = get_context(0)
+    return ctx.squared_sampson_error(_points(points1, "points1"), _points(points2, "points2"), E)
+
+
+def wait_idle():
+    """Test helper: nothing is asynchronous at this level."""
+    time.sleep(0)

@@ -24,6 +24,16 @@ int gh_estimate_H(const double* x1, const double* y1, const double* x2, const do
 int gh_minimal_E5(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_E5(x1, y1, x2, y2, m); }
 int gh_minimal_F7(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_F7(x1, y1, x2, y2, m); }
 int gh_minimal_H4(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_H4(x1, y1, x2, y2, m); }
+int gh_minimal_H4_closed(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_H4_closed(x1, y1, x2, y2, m); }
+// S: symmetric 9x9 (row-major) -> K smallest eigenvectors by inverse subspace iteration
+void gh_invit(const double* S, int K, double* out) {
+  double S45[45];
+  int k = 0;
+  for (int i = 0; i < 9; ++i)
+    for (int j = i; j < 9; ++j) S45[k++] = S[i * 9 + j];
+  if (K == 1) smallest_eigvecs_invit<1>(S45, out);
+  if (K == 4) smallest_eigvecs_invit<4>(S45, out);
+}
 double gh_sampson(const double* E, double x1, double y1, double x2, double y2) { return sampson_sq(E, x1, y1, x2, y2); }
 double gh_homography(const double* H, double x1, double y1, double x2, double y2) { return homography_sq(H, x1, y1, x2, y2); }
 double gh_num_trials(double ni, double ns, double conf, double mult, int k) { return compute_num_trials(ni, ns, conf, mult, k); }

@@ -121,6 +121,28 @@ def test_seven_eight_dlt_recover_model(geom):
         m = np.zeros(9)
         geom.gh_minimal_H4(P(q1[:4, 0]), P(q1[:4, 1]), P(q2[:4, 0]), P(q2[:4, 1]), P(m))
         assert np.allclose(_canon(m), _canon(H), atol=1e-6)
+        m = np.zeros(9)
+        assert geom.gh_minimal_H4_closed(P(q1[4:8, 0]), P(q1[4:8, 1]), P(q2[4:8, 0]), P(q2[4:8, 1]), P(m)) == 1
+        assert np.allclose(_canon(m), _canon(H), atol=1e-6)          # closed form == DLT on minimal samples
+
+
+def test_inverse_iteration_null_space(geom):
+    """LO refits: K smallest eigenvectors by inverse subspace iteration span numpy's eigh subspace."""
+    rng = np.random.default_rng(9)
+    for K, rows, noise in [(1, 40, 1e-3), (4, 60, 1e-4), (1, 8, 0.0), (4, 5, 0.0), (4, 200, 1e-2)]:
+        for _ in range(10):
+            basis = np.linalg.qr(rng.normal(size=(9, 9)))[0]
+            null, rest = basis[:, :K], basis[:, K:]
+            A = rng.normal(size=(rows, 9 - K)) @ rest.T + noise * rng.normal(size=(rows, 9))
+            S = A.T @ A
+            out = np.zeros((K, 9))
+            geom.gh_invit(P(S), K, P(out))
+            w, V = np.linalg.eigh(S)
+            ref = V[:, :K]
+            # principal angles between the two K-dim subspaces
+            sv = np.linalg.svd(ref.T @ out.T, compute_uv=False)
+            assert sv.min() > 1 - 1e-9, (K, rows, noise, sv)
+            assert np.allclose(out @ out.T, np.eye(K), atol=1e-12)
 
 
 def test_num_trials(geom):

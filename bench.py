@@ -290,12 +290,20 @@ def main():
     if not bf16:
         bf16, peak_src = 1400.0, "2 x fallback sustained bf16 1.4 PFLOP/s (B200_PROFILING.md), derived int8 peak"
     peak = 2.0 * bf16
+    try:
+        # measured on this pool's B200 by tools/microbench.cu (tcgen05.mma.kind::i8 issue loop, all SMs)
+        mb = json.load(open(os.path.join(ROOT, "profiles", "r01_microbench_tmem_i8mma.json")))
+        peak = float(mb["i8_mma_n256_chip_TOPS"])
+        peak_src = ("measured int8 tcgen05 peak, tools/microbench.cu on this pool's B200 "
+                    "(profiles/r01_microbench_tmem_i8mma.json, burst, 1965 MHz)")
+    except Exception:
+        pass
     ops_per_pair = 2.0 * K * K * 128
     k1_avg_ms = k1_ms / max(k1_n, 1)
     pairs_per_launch = len(my_pairs) * args.steps / max(k1_n, 1)
     achieved = ops_per_pair * pairs_per_launch / (k1_avg_ms / 1e3) / 1e12
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "k1_match_kernel", "avg_launch_ms": k1_avg_ms,
+            "traffic": None, "kernel": "b2m_k1_filter_kernel", "avg_launch_ms": k1_avg_ms,
             "pairs_per_launch": pairs_per_launch, "peak_source": peak_src,
             "algorithmic": "2*K1*K2*128 int8 ops per pair (one GEMM; the transposed GEMM of the cross-check "
                            "direction is not counted)"}

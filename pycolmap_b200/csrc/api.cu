@@ -275,10 +275,11 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     if (ctx->exact_k1) {
       CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
     } else {
-      CU_TRY_R(launch_k1_filter(S.tmap, S.tmap_half, mp, S.d_desc, nb, max_strips, n_dirs, st));
+      CU_TRY_R(launch_k1_filter(S.tmap, S.tmap_half, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st,
+                                ctx->ev_k1b[s]));
       ctx->stats.kernel_launches += 1;
     }
-    CU_TRY_R(cudaEventRecord(ctx->ev_k1b[s], st));
+    if (ctx->exact_k1) CU_TRY_R(cudaEventRecord(ctx->ev_k1b[s], st));
     ctx->stats.kernel_launches += 1;
     ctx->stats.last_k1_launches += 1;
     ctx->stats.match_tiles += 0;
@@ -435,6 +436,7 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
   b2m_ctx* ctx = new (std::nothrow) b2m_ctx();
   if (!ctx) return fail(nullptr, B2M_ENOMEM, "out of host memory");
   ctx->device = dev;
+  ctx->num_sms = prop.multiProcessorCount;
   ctx->seed = cfg ? cfg->seed : 0;
   if (cfg && cfg->pair_batch > 0) ctx->pair_batch = std::min(cfg->pair_batch, 65535);
   ctx->stats.struct_size = sizeof(b2m_stats);

@@ -53,6 +53,7 @@ struct Workspace {
 
 struct b2m_ctx {
   int device = 0;
+  int num_sms = 148;
   uint64_t seed = 0;
   int pair_batch = 1024;
   cudaStream_t stream = nullptr;

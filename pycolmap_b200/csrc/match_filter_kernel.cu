@@ -1,11 +1,16 @@
-// match_filter_kernel.cu -- K1 v3: tcgen05 int8 GEMM with a *filter* epilogue and 256-row CTAs.
+// match_filter_kernel.cu -- K1 (current): persistent, clustered tcgen05 int8 GEMM with a *filter*
+// epilogue.
 //
-// Work unit (CTA) = (image pair, direction, 256-row block of the "row" image A).  The CTA keeps its
-// two 128-row A strips resident in shared memory and streams 128-column tiles of image B through an
-// 8-stage TMA ring; every B tile feeds two 128x128x128 MMAs (one per strip), which halves the
-// L2 -> SM operand traffic per MAC compared with one strip per CTA (the v2 profile showed the
-// pipeline bound by L2 feed latency/bandwidth, profiles/r01_k1_v2_*.txt).  Accumulators live in
-// TMEM: 2 stages x 2 strips x 128 columns = 512 columns.
+// Grid = one 2-CTA cluster per SM pair, persistent: every cluster walks a static list of work items
+// (image pair, direction, 512-row block of the "row" image A); inside an item each CTA owns two
+// 128-row A strips (256 rows) and the B image streams through an 8-stage ring of 128-column tiles.
+//   * every B tile is fetched ONCE per cluster: each CTA loads its 64-row half with TMA and multicasts
+//     it to both CTAs; a tile feeds 2 strips x 2 CTAs = four 128x128x128 MMAs;
+//   * the pipelines (TMA ring, TMEM accumulator stages, mbarrier phases) run straight across item
+//     boundaries: the A strips are double-buffered, so the prologue of item i+1 overlaps the tail of
+//     item i and TMEM / barriers are set up once per launch (profiles/r01_*: with one CTA per item
+//     ~45 % of the time went to CTA launch + pipeline fill/drain);
+//   * accumulators: TMEM, 2 stages x 2 strips x 128 columns = 512 columns.
 //
 // Epilogue (8 warps: warp w -> TMEM lane quarter w%4 of strip w/4; thread <-> row): instead of an
 // exact running top-2 (4 ALU ops per accumulator) each thread keeps 64 "slot maxima"
@@ -33,21 +38,25 @@ constexpr int kDim = 128;
 constexpr int kTileM = 128;                        // rows per MMA (TMEM lanes)
 constexpr int kStrips = 2;                         // A strips per CTA
 constexpr int kRowsPerCta = kTileM * kStrips;      // 256 == kRowPad
+constexpr int kCluster = 2;                        // CTAs per cluster sharing every B tile by TMA multicast
+constexpr int kRowsPerItem = kRowsPerCta * kCluster;  // 512 rows of A per work item
 constexpr int kTileN = 128;                        // columns per B tile
 constexpr int kUmmaK = 32;
 constexpr int kStages = 8;                         // B-tile ring depth (8 x 16 KiB)
 constexpr int kAccStages = 2;
-constexpr int kCluster = 2;                        // CTAs per cluster sharing every B tile by TMA multicast
+constexpr int kABufs = 2;                          // A strips double-buffered across work items
 constexpr int kBytesA = kTileM * kDim;             // 16 KiB per strip
 constexpr int kBytesB = kTileN * kDim;             // 16 KiB
 constexpr int kEpiWarps = 4 * kStrips;             // one warp per (strip, TMEM lane quarter)
 constexpr int kThreads = (kEpiWarps + 2) * 32;     // + TMA warp + MMA warp
 constexpr int kAccCols = kStrips * kTileN;         // TMEM columns per accumulator stage
 constexpr uint32_t kIdesc = make_idesc_u8u8_s32(kTileM, kTileN);
+constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << kCluster) - 1u);
 static_assert(kRowsPerCta == kRowPad, "images are padded to whole CTA row blocks");
 
 struct __align__(8) Barriers {
-  uint64_t full_a;
+  uint64_t full_a[kABufs];
+  uint64_t empty_a[kABufs];
   uint64_t full_b[kStages];
   uint64_t empty_b[kStages];
   uint64_t tmem_full[kAccStages];
@@ -55,40 +64,57 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
-constexpr size_t kSmemBytes = 1024 + kStrips * kBytesA + kStages * kBytesB + sizeof(Barriers);
+constexpr size_t kSmemBytes = 1024 + kABufs * kStrips * kBytesA + kStages * kBytesB + sizeof(Barriers);
+
+// A work item and the data every warp role derives from its index (pure function of `w`).
+struct Item {
+  int pair, dir, nA, nB, rowA, rowB, n_tiles, row0;  // row0: first row (inside image A) of this CTA
+  bool valid;
+};
+__device__ __forceinline__ Item decode_item(const MatchParams& p, int w, uint32_t cta_rank) {
+  Item it;
+  const int cb = w % p.blocks_per_image;
+  const int pd = w / p.blocks_per_image;
+  it.dir = pd % p.n_dirs;
+  it.pair = pd / p.n_dirs;
+  const int ia = p.pairs[2 * it.pair + it.dir];
+  const int ib = p.pairs[2 * it.pair + (it.dir ^ 1)];
+  it.nA = p.img_nfeat[ia];
+  it.nB = p.img_nfeat[ib];
+  // same answer in both CTAs of the cluster; an empty image B still yields an item (n_tiles == 0)
+  // so that its rows are written as "no match"
+  it.valid = cb * kRowsPerItem < it.nA;
+  it.row0 = cb * kRowsPerItem + static_cast<int>(cta_rank) * kRowsPerCta;
+  it.rowA = p.img_row0[ia] + it.row0;
+  it.rowB = p.img_row0[ib];
+  it.n_tiles = (it.nB + kTileN - 1) / kTileN;
+  return it;
+}
 
 }  // namespace
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
                      const MatchParams p) {
-  const int pair = blockIdx.z;
-  const int dir = blockIdx.y;
-  const int blk = blockIdx.x;
-  const int ia = p.pairs[2 * pair + dir];
-  const int ib = p.pairs[2 * pair + (dir ^ 1)];
-  const int nA = p.img_nfeat[ia];
-  const int nB = p.img_nfeat[ib];
-  // uniform exit of the whole CLUSTER (both CTAs or none) before any barrier / TMEM allocation; a CTA
-  // whose own rows are out of range still relays its half of every B tile to its peer
-  if ((blk / kCluster) * kCluster * kRowsPerCta >= nA) return;
-  const uint32_t cta_rank = cluster_ctarank();
-  const int rowA = p.img_row0[ia] + blk * kRowsPerCta;
-  const int rowB = p.img_row0[ib];
-  const int n_tiles = (nB + kTileN - 1) / kTileN;
-
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smA = smem;
-  uint8_t* smB = smem + kStrips * kBytesA;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + kStrips * kBytesA + kStages * kBytesB);
+  uint8_t* smA = smem;                                     // [kABufs][kStrips][16 KiB]
+  uint8_t* smB = smem + kABufs * kStrips * kBytesA;        // [kStages][16 KiB]
+  Barriers* bars = reinterpret_cast<Barriers*>(smB + kStages * kBytesB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x / kCluster;
+  const int n_clusters = gridDim.x / kCluster;
 
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tmap);
-    mbar_init(&bars->full_a, 1);
+    tma_prefetch_desc(&tmap_half);
+    for (int s = 0; s < kABufs; ++s) {
+      mbar_init(&bars->full_a[s], 1);
+      mbar_init(&bars->empty_a[s], 1);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars->full_b[s], 1);
       mbar_init(&bars->empty_b[s], kCluster);  // one tcgen05.commit arrival from every CTA of the cluster
@@ -111,54 +137,70 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 
   if (warp == kEpiWarps) {
     // ===== TMA producer =====
-    if (lane == 0 && n_tiles > 0) {
-      mbar_arrive_expect_tx(&bars->full_a, kStrips * kBytesA);
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, n_done = 0;
+      for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+        const Item it = decode_item(p, w, cta_rank);
+        if (!it.valid) continue;
+        const uint32_t ab = n_done & 1, aph = (n_done >> 1) & 1;
+        ++n_done;
+        mbar_wait(&bars->empty_a[ab], aph ^ 1);  // the MMAs of the item that used this A buffer retired
+        mbar_arrive_expect_tx(&bars->full_a[ab], kStrips * kBytesA);
 #pragma unroll
-      for (int s = 0; s < kStrips; ++s) tma_load_2d(smA + s * kBytesA, &tmap, &bars->full_a, 0, rowA + s * kTileM);
-      uint32_t stage = 0, phase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(&bars->empty_b[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&bars->full_b[stage], kBytesB);
-        // this CTA fetches its 64-row half of the tile and multicasts it to the whole cluster, so every
-        // B byte crosses L2 -> SM once per cluster instead of once per CTA
-        tma_load_2d_multicast(smB + stage * kBytesB + cta_rank * (kBytesB / kCluster), &tmap_half,
-                              &bars->full_b[stage], 0, rowB + t * kTileN + cta_rank * (kTileN / kCluster),
-                              static_cast<uint16_t>((1u << kCluster) - 1u));
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
+        for (int s = 0; s < kStrips; ++s)
+          tma_load_2d(smA + (ab * kStrips + s) * kBytesA, &tmap, &bars->full_a[ab], 0, it.rowA + s * kTileM);
+        for (int t = 0; t < it.n_tiles; ++t) {
+          mbar_wait(&bars->empty_b[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bars->full_b[stage], kBytesB);
+          // this CTA fetches its 64-row half of the tile and multicasts it to the whole cluster, so every
+          // B byte crosses L2 -> SM once per cluster instead of once per CTA
+          tma_load_2d_multicast(smB + stage * kBytesB + cta_rank * (kBytesB / kCluster), &tmap_half,
+                                &bars->full_b[stage], 0, it.rowB + t * kTileN + cta_rank * (kTileN / kCluster),
+                                kClusterMask);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
   } else if (warp == kEpiWarps + 1) {
     // ===== MMA issuer (one thread): two 128x128x128 MMAs per B tile =====
-    if (lane == 0 && n_tiles > 0) {
-      mbar_wait(&bars->full_a, 0);
-      uint64_t adesc[kStrips];
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0, n_done = 0;
+      for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+        const Item it = decode_item(p, w, cta_rank);
+        if (!it.valid) continue;
+        const uint32_t ab = n_done & 1, aph = (n_done >> 1) & 1;
+        ++n_done;
+        mbar_wait(&bars->full_a[ab], aph);
+        uint64_t adesc[kStrips];
 #pragma unroll
-      for (int s = 0; s < kStrips; ++s) adesc[s] = make_smem_desc_sw128(smem_u32(smA + s * kBytesA));
-      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
-        mbar_wait(&bars->full_b[stage], phase);
-        tc_fence_after();
-        const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smB + stage * kBytesB));
+        for (int s = 0; s < kStrips; ++s) adesc[s] = make_smem_desc_sw128(smem_u32(smA + (ab * kStrips + s) * kBytesA));
+        if (it.n_tiles == 0) mbar_arrive(&bars->empty_a[ab]);  // nothing will read this A buffer
+        for (int t = 0; t < it.n_tiles; ++t) {
+          mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+          mbar_wait(&bars->full_b[stage], phase);
+          tc_fence_after();
+          const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smB + stage * kBytesB));
 #pragma unroll
-        for (int s = 0; s < kStrips; ++s) {
-          const uint32_t tmem_d = tmem_base + as * kAccCols + s * kTileN;
+          for (int s = 0; s < kStrips; ++s) {
+            const uint32_t tmem_d = tmem_base + as * kAccCols + s * kTileN;
 #pragma unroll
-          for (int k = 0; k < kDim / kUmmaK; ++k)
-            mma_i8_ss(tmem_d, adesc[s] + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
-        }
-        mma_commit_multicast(&bars->empty_b[stage], static_cast<uint16_t>((1u << kCluster) - 1u));
-        mma_commit(&bars->tmem_full[as]);
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-        if (++as == kAccStages) {
-          as = 0;
-          aphase ^= 1;
+            for (int k = 0; k < kDim / kUmmaK; ++k)
+              mma_i8_ss(tmem_d, adesc[s] + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
+          }
+          mma_commit_multicast(&bars->empty_b[stage], kClusterMask);  // both CTAs' producers may refill
+          mma_commit(&bars->tmem_full[as]);
+          if (t == it.n_tiles - 1) mma_commit(&bars->empty_a[ab]);   // A buffer reusable after the last MMA
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++as == kAccStages) {
+            as = 0;
+            aphase ^= 1;
+          }
         }
       }
     }
@@ -166,66 +208,70 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     // ===== filter epilogue =====
     const int quarter = warp & 3;
     const int strip = warp >> 2;
-    const int row_in_blk = strip * kTileM + quarter * 32 + lane;
-    uint32_t B0[32], B1[32];
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      B0[r] = 0u;
-      B1[r] = 0u;
-    }
-    uint32_t as = 0, aphase = 0;
+    const int row_in_cta = strip * kTileM + quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    for (int t = 0; t < n_tiles; ++t) {
-      mbar_wait(&bars->tmem_full[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + lane_base + as * kAccCols + strip * kTileN;
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32(taddr, va);
-      tmem_ld_32x32(taddr + 32, vb);
-      tmem_wait_ld();
+    uint32_t as = 0, aphase = 0;
+    for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+      const Item it = decode_item(p, w, cta_rank);
+      if (!it.valid) continue;
+      uint32_t B0[32], B1[32];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) B0[r] = max(B0[r], max(va[r], vb[r]));
-      tmem_ld_32x32(taddr + 64, va);
-      tmem_ld_32x32(taddr + 96, vb);
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(&bars->tmem_empty[as]);  // the last two chunks are in registers: TMEM stage is free
+      for (int r = 0; r < 32; ++r) {
+        B0[r] = 0u;
+        B1[r] = 0u;
+      }
+      for (int t = 0; t < it.n_tiles; ++t) {
+        mbar_wait(&bars->tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_base + as * kAccCols + strip * kTileN;
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(taddr, va);
+        tmem_ld_32x32(taddr + 32, vb);
+        tmem_wait_ld();
 #pragma unroll
-      for (int r = 0; r < 32; ++r) B1[r] = max(B1[r], max(va[r], vb[r]));
-      if (++as == kAccStages) {
-        as = 0;
-        aphase ^= 1;
-      }
-    }
-    // (largest, second largest) over the 64 slot maxima, multiset semantics; lowest slot id on ties
-    uint32_t best = 0, s1 = 0;
-    int sstar = 0;
+        for (int r = 0; r < 32; ++r) B0[r] = max(B0[r], max(va[r], vb[r]));
+        tmem_ld_32x32(taddr + 64, va);
+        tmem_ld_32x32(taddr + 96, vb);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&bars->tmem_empty[as]);  // the last two chunks are in registers: TMEM stage is free
 #pragma unroll
-    for (int r = 0; r < 64; ++r) {
-      const uint32_t v = r < 32 ? B0[r & 31] : B1[r & 31];
-      if (v > best) {
-        s1 = best;
-        best = v;
-        sstar = r;
-      } else {
-        s1 = max(s1, v);
+        for (int r = 0; r < 32; ++r) B1[r] = max(B1[r], max(va[r], vb[r]));
+        if (++as == kAccStages) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
-    }
-    int32_t out = -1;
-    if (best > 0u) {
-      const float a = __ldg(p.acos_lut + min(best, 262144u));
-      if (!(a > p.max_distance)) {
-        const float b = __ldg(p.acos_lut + min(s1, 262144u));
-        if (!(a >= __fmul_rn(p.max_ratio, b))) out = -2 - sstar;  // candidate: resolve exactly
+      // (largest, second largest) over the 64 slot maxima, multiset semantics; lowest slot id on ties
+      uint32_t best = 0, s1 = 0;
+      int sstar = 0;
+#pragma unroll
+      for (int r = 0; r < 64; ++r) {
+        const uint32_t v = r < 32 ? B0[r & 31] : B1[r & 31];
+        if (v > best) {
+          s1 = best;
+          best = v;
+          sstar = r;
+        } else {
+          s1 = max(s1, v);
+        }
       }
-    }
-    const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
-    const int row = blk * kRowsPerCta + row_in_blk;
-    p.mbuf[base + row] = out;
-    if (out != -1 && row < nA) {
-      p.aux[base + row] = make_uint2(best, s1);
-      const int k = atomicAdd(p.cand_cnt + pair * 2 + dir, 1);
-      p.cand_rows[base + k] = row;
+      int32_t out = -1;
+      if (best > 0u) {
+        const float a = __ldg(p.acos_lut + min(best, 262144u));
+        if (!(a > p.max_distance)) {
+          const float b = __ldg(p.acos_lut + min(s1, 262144u));
+          if (!(a >= __fmul_rn(p.max_ratio, b))) out = -2 - sstar;  // candidate: resolve exactly
+        }
+      }
+      const int64_t base = (static_cast<int64_t>(it.pair) * 2 + it.dir) * p.mstride;
+      const int row = it.row0 + row_in_cta;
+      p.mbuf[base + row] = out;
+      if (out != -1 && row < it.nA) {
+        p.aux[base + row] = make_uint2(best, s1);
+        const int k = atomicAdd(p.cand_cnt + it.pair * 2 + it.dir, 1);
+        p.cand_rows[base + k] = row;
+      }
     }
   }
 
@@ -412,8 +458,9 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
   }
 }
 
-cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const MatchParams& p, const uint8_t* desc, int n_pairs,
-                             int max_strips, int n_dirs, cudaStream_t stream) {
+cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const MatchParams& p_in,
+                             const uint8_t* desc, int n_pairs, int max_strips, int n_dirs, int num_sms,
+                             cudaStream_t stream, cudaEvent_t after_filter) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(b2m_k1_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -421,13 +468,23 @@ cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_ha
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  MatchParams p = p_in;
   cudaError_t e = cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * 2 * n_pairs, stream);
   if (e != cudaSuccess) return e;
-  const int blocks = (max_strips + kStrips - 1) / kStrips;
-  dim3 grid((blocks + kCluster - 1) / kCluster * kCluster, n_dirs, n_pairs);
-  b2m_k1_filter_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, tmap_half, p);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  // rows never visited by a work item (dir 1 without cross-check is simply not produced)
+  p.n_dirs = n_dirs;
+  p.blocks_per_image = (max_strips * kTileM + kRowsPerItem - 1) / kRowsPerItem;
+  p.n_items = n_pairs * n_dirs * p.blocks_per_image;
+  const int clusters = p.n_items < num_sms / kCluster ? p.n_items : num_sms / kCluster;
+  if (clusters > 0) {
+    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap_half, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  if (after_filter) {
+    e = cudaEventRecord(after_filter, stream);  // the roofline times the GEMM kernel alone
+    if (e != cudaSuccess) return e;
+  }
   b2m_k1_resolve_kernel<<<2 * n_pairs, 256, 0, stream>>>(p, desc);
   return cudaGetLastError();
 }

@@ -20,6 +20,8 @@ struct MatchParams {
   int32_t* cand_cnt;         // device [n_pairs][2] number of candidate rows
   int32_t* cand_rows;        // device [n_pairs][2][mstride] candidate row list
   int32_t* cand_sorted;      // device [n_pairs][2][mstride] candidate rows bucketed by winning slot
+  // persistent K1: filled in by launch_k1_filter
+  int32_t n_items, blocks_per_image, n_dirs;
 };
 
 struct CompactParams {
@@ -46,8 +48,9 @@ cudaError_t launch_k1_match(const CUtensorMap& tmap, const MatchParams& p, int n
                             cudaStream_t stream);
 // K1 v2: filter epilogue (slot maxima) + exact dp4a resolution of the candidate rows.  Bit-identical
 // results to launch_k1_match; requires a monotone (non-increasing) acos LUT.
-cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const MatchParams& p, const uint8_t* desc, int n_pairs,
-                             int max_strips, int n_dirs, cudaStream_t stream);
+cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const MatchParams& p,
+                             const uint8_t* desc, int n_pairs, int max_strips, int n_dirs, int num_sms,
+                             cudaStream_t stream, cudaEvent_t after_filter);
 cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream);
 
 }  // namespace b2m

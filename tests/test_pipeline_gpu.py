@@ -49,7 +49,8 @@ def test_match_exhaustive_database(tmp_path):
                     # ExhaustiveFeatureMatcher visits some pairs as (b, a): same match set, rows ordered
                     # by the other image's index (mutual nearest neighbours are symmetric under cross-check)
                     assert np.array_equal(got[np.argsort(got[:, 0], kind="stable")], want)
-                    assert g["config"] in (2, 6) and len(g["inlier_matches"]) >= 15
+                    # CALIBRATED normally; UNCALIBRATED when E keeps < 95 % of F's inliers on a noisy pair
+                    assert g["config"] in (2, 3, 6) and len(g["inlier_matches"]) >= 15
                     verified += 1
         assert verified >= 10 and db.num_verified_image_pairs == verified
     # resume semantics: a second run finds everything stored and changes nothing

@@ -160,30 +160,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- data: every rank synthesises its own shard of images, ONE all-gather makes the set resident
-    per = (n_img + world - 1) // world
-    lo, hi = min(rank * per, n_img), min((rank + 1) * per, n_img)
+    from pycolmap_b200 import sharding
+    lo, hi, _per = sharding.image_shard(n_img, rank, world)
     scene = syn.make_scene(n_img, K, seed=0, device=dev, image_range=(lo, hi))
-    desc_shard = scene["desc"].reshape(-1, 128)
-    kpts_shard = scene["kpts"].reshape(-1, 2)
-    if world > 1:
-        pad = per - (hi - lo)
-        if pad:
-            desc_shard = torch.cat([desc_shard, torch.zeros(pad * K, 128, dtype=torch.uint8, device=dev)])
-            kpts_shard = torch.cat([kpts_shard, torch.zeros(pad * K, 2, dtype=torch.float32, device=dev)])
-        desc_full = torch.empty(world * per * K, 128, dtype=torch.uint8, device=dev)
-        kpts_full = torch.empty(world * per * K, 2, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(desc_full, desc_shard)
-        dist.all_gather_into_tensor(kpts_full, kpts_shard)
-        desc_full, kpts_full = desc_full[: n_img * K], kpts_full[: n_img * K]
-    else:
-        desc_full, kpts_full = desc_shard, kpts_shard
+    desc_full = sharding.all_gather_rows(scene["desc"].reshape(-1, 128), n_img, K, rank, world, dist)
+    kpts_full = sharding.all_gather_rows(scene["kpts"].reshape(-1, 2), n_img, K, rank, world, dist)
+    desc_full, kpts_full = desc_full.contiguous(), kpts_full.contiguous()
     torch.cuda.synchronize()
     cams = [dict(model=0, width=1600, height=1200, params=[1200.0, 800.0, 600.0], has_prior_focal_length=1)
             for _ in range(n_img)]
     nfeat = np.full(n_img, K, np.int32)
 
     all_pairs = syn.exhaustive_pairs(n_img)
-    my_pairs = np.ascontiguousarray(all_pairs[rank::world])      # independent units, no data-path collective
+    my_pairs = sharding.pair_shard(all_pairs, rank, world)       # independent units, no data-path collective
 
     ctx = pb.Context(device=local_rank, pair_batch=args.pair_batch)
     ctx.set_images_device(nfeat, desc_full.data_ptr(), kpts_full.data_ptr() if verify else None,

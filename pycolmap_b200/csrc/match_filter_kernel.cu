@@ -36,23 +36,24 @@ namespace {
 
 constexpr int kDim = 128;
 constexpr int kTileM = 128;                        // rows per MMA (TMEM lanes)
-constexpr int kStrips = 2;                         // A strips per CTA
-constexpr int kRowsPerCta = kTileM * kStrips;      // 256 == kRowPad
+constexpr int kStrips = 1;                         // A strips per CTA
+constexpr int kRowsPerCta = kTileM * kStrips;      // 128
 constexpr int kCluster = 2;                        // CTAs per cluster sharing every B tile by TMA multicast
-constexpr int kRowsPerItem = kRowsPerCta * kCluster;  // 512 rows of A per work item
-constexpr int kTileN = 128;                        // columns per B tile
+constexpr int kRowsPerItem = kRowsPerCta * kCluster;  // 256 rows of A per work item == kRowPad
+constexpr int kTileN = 256;                        // columns per B tile: a 128x256x32 MMA hides the smem A read
+                                                   // (N <= 128 costs ~92 cycles per MMA regardless of N, profiles/r01_microbench2)
 constexpr int kUmmaK = 32;
-constexpr int kStages = 8;                         // B-tile ring depth (8 x 16 KiB)
+constexpr int kStages = 5;                         // B-tile ring depth (5 x 32 KiB)
 constexpr int kAccStages = 2;
 constexpr int kABufs = 2;                          // A strips double-buffered across work items
 constexpr int kBytesA = kTileM * kDim;             // 16 KiB per strip
-constexpr int kBytesB = kTileN * kDim;             // 16 KiB
-constexpr int kEpiWarps = 4 * kStrips;             // one warp per (strip, TMEM lane quarter)
+constexpr int kBytesB = kTileN * kDim;             // 32 KiB
+constexpr int kEpiWarps = 8;                       // warp w: TMEM lane quarter w%4, column half w/4 of every tile
 constexpr int kThreads = (kEpiWarps + 2) * 32;     // + TMA warp + MMA warp
 constexpr int kAccCols = kStrips * kTileN;         // TMEM columns per accumulator stage
 constexpr uint32_t kIdesc = make_idesc_u8u8_s32(kTileM, kTileN);
 constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << kCluster) - 1u);
-static_assert(kRowsPerCta == kRowPad, "images are padded to whole CTA row blocks");
+static_assert(kRowsPerItem == kRowPad && kTileN == kRowPad, "images are padded to whole items / column tiles");
 
 struct __align__(8) Barriers {
   uint64_t full_a[kABufs];
@@ -64,7 +65,8 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
-constexpr size_t kSmemBytes = 1024 + kABufs * kStrips * kBytesA + kStages * kBytesB + sizeof(Barriers);
+constexpr int kMergeBytes = kTileM * 64 * 4;       // slot maxima of the upper column half, [64 slots][128 rows]
+constexpr size_t kSmemBytes = 1024 + kABufs * kStrips * kBytesA + kStages * kBytesB + kMergeBytes + sizeof(Barriers);
 
 // A work item and the data every warp role derives from its index (pure function of `w`).
 struct Item {
@@ -100,7 +102,8 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;                                     // [kABufs][kStrips][16 KiB]
   uint8_t* smB = smem + kABufs * kStrips * kBytesA;        // [kStages][16 KiB]
-  Barriers* bars = reinterpret_cast<Barriers*>(smB + kStages * kBytesB);
+  uint32_t* merge = reinterpret_cast<uint32_t*>(smB + kStages * kBytesB);
+  Barriers* bars = reinterpret_cast<Barriers*>(smB + kStages * kBytesB + kMergeBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -139,6 +142,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, n_done = 0;
+      long long pw = 0, pt0 = clock64();
       for (int w = cluster_id; w < p.n_items; w += n_clusters) {
         const Item it = decode_item(p, w, cta_rank);
         if (!it.valid) continue;
@@ -150,11 +154,13 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         for (int s = 0; s < kStrips; ++s)
           tma_load_2d(smA + (ab * kStrips + s) * kBytesA, &tmap, &bars->full_a[ab], 0, it.rowA + s * kTileM);
         for (int t = 0; t < it.n_tiles; ++t) {
+          const long long c0 = clock64();
           mbar_wait(&bars->empty_b[stage], phase ^ 1);
+          pw += clock64() - c0;
           mbar_arrive_expect_tx(&bars->full_b[stage], kBytesB);
-          // this CTA fetches its 64-row half of the tile and multicasts it to the whole cluster, so every
+          // this CTA fetches its 128-row half of the tile and multicasts it to the whole cluster, so every
           // B byte crosses L2 -> SM once per cluster instead of once per CTA
-          tma_load_2d_multicast(smB + stage * kBytesB + cta_rank * (kBytesB / kCluster), &tmap_half,
+          tma_load_2d_multicast(smB + stage * kBytesB + cta_rank * (kBytesB / kCluster), &tmap,
                                 &bars->full_b[stage], 0, it.rowB + t * kTileN + cta_rank * (kTileN / kCluster),
                                 kClusterMask);
           if (++stage == kStages) {
@@ -163,11 +169,16 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           }
         }
       }
+      if (p.prof) {
+        atomicAdd(p.prof + 0, static_cast<unsigned long long>(pw));
+        atomicAdd(p.prof + 1, static_cast<unsigned long long>(clock64() - pt0));
+      }
     }
   } else if (warp == kEpiWarps + 1) {
     // ===== MMA issuer (one thread): two 128x128x128 MMAs per B tile =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, n_done = 0;
+      long long mw_e = 0, mw_f = 0, mt0 = clock64();
       for (int w = cluster_id; w < p.n_items; w += n_clusters) {
         const Item it = decode_item(p, w, cta_rank);
         if (!it.valid) continue;
@@ -179,8 +190,12 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         for (int s = 0; s < kStrips; ++s) adesc[s] = make_smem_desc_sw128(smem_u32(smA + (ab * kStrips + s) * kBytesA));
         if (it.n_tiles == 0) mbar_arrive(&bars->empty_a[ab]);  // nothing will read this A buffer
         for (int t = 0; t < it.n_tiles; ++t) {
+          const long long c0 = clock64();
           mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+          const long long c1 = clock64();
           mbar_wait(&bars->full_b[stage], phase);
+          mw_e += c1 - c0;
+          mw_f += clock64() - c1;
           tc_fence_after();
           const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smB + stage * kBytesB));
 #pragma unroll
@@ -203,14 +218,20 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           }
         }
       }
+      if (p.prof) {
+        atomicAdd(p.prof + 2, static_cast<unsigned long long>(mw_e));
+        atomicAdd(p.prof + 3, static_cast<unsigned long long>(mw_f));
+        atomicAdd(p.prof + 5, static_cast<unsigned long long>(clock64() - mt0));
+      }
     }
   } else {
     // ===== filter epilogue =====
     const int quarter = warp & 3;
-    const int strip = warp >> 2;
-    const int row_in_cta = strip * kTileM + quarter * 32 + lane;
+    const int half = warp >> 2;
+    const int row_in_cta = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t as = 0, aphase = 0;
+    long long ew = 0, et0 = clock64();
     for (int w = cluster_id; w < p.n_items; w += n_clusters) {
       const Item it = decode_item(p, w, cta_rank);
       if (!it.valid) continue;
@@ -221,9 +242,11 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         B1[r] = 0u;
       }
       for (int t = 0; t < it.n_tiles; ++t) {
+        const long long c0 = clock64();
         mbar_wait(&bars->tmem_full[as], aphase);
+        ew += clock64() - c0;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_base + as * kAccCols + strip * kTileN;
+        const uint32_t taddr = tmem_base + lane_base + as * kAccCols + half * 128;
         uint32_t va[32], vb[32];
         tmem_ld_32x32(taddr, va);
         tmem_ld_32x32(taddr + 32, vb);
@@ -242,36 +265,53 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           aphase ^= 1;
         }
       }
-      // (largest, second largest) over the 64 slot maxima, multiset semantics; lowest slot id on ties
-      uint32_t best = 0, s1 = 0;
-      int sstar = 0;
+      // 128 slots per row: slot = half * 64 + cp * 32 + r.  The upper column half hands its 64 maxima
+      // to the lower-half thread of the same row through shared memory.
+      if (half == 1) {
 #pragma unroll
-      for (int r = 0; r < 64; ++r) {
-        const uint32_t v = r < 32 ? B0[r & 31] : B1[r & 31];
-        if (v > best) {
-          s1 = best;
-          best = v;
-          sstar = r;
-        } else {
-          s1 = max(s1, v);
+        for (int r = 0; r < 32; ++r) {
+          merge[r * kTileM + row_in_cta] = B0[r];
+          merge[(32 + r) * kTileM + row_in_cta] = B1[r];
         }
       }
-      int32_t out = -1;
-      if (best > 0u) {
-        const float a = __ldg(p.acos_lut + min(best, 262144u));
-        if (!(a > p.max_distance)) {
-          const float b = __ldg(p.acos_lut + min(s1, 262144u));
-          if (!(a >= __fmul_rn(p.max_ratio, b))) out = -2 - sstar;  // candidate: resolve exactly
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+      if (half == 0) {
+        // (largest, second largest) over the slot maxima, multiset semantics; lowest slot id on ties
+        uint32_t best = 0, s1 = 0;
+        int sstar = 0;
+#pragma unroll
+        for (int r = 0; r < 128; ++r) {
+          const uint32_t v = r < 32 ? B0[r & 31] : (r < 64 ? B1[r & 31] : merge[(r - 64) * kTileM + row_in_cta]);
+          if (v > best) {
+            s1 = best;
+            best = v;
+            sstar = r;
+          } else {
+            s1 = max(s1, v);
+          }
+        }
+        int32_t out = -1;
+        if (best > 0u) {
+          const float a = __ldg(p.acos_lut + min(best, 262144u));
+          if (!(a > p.max_distance)) {
+            const float b = __ldg(p.acos_lut + min(s1, 262144u));
+            if (!(a >= __fmul_rn(p.max_ratio, b))) out = -2 - sstar;  // candidate: resolve exactly
+          }
+        }
+        const int64_t base = (static_cast<int64_t>(it.pair) * 2 + it.dir) * p.mstride;
+        const int row = it.row0 + row_in_cta;
+        p.mbuf[base + row] = out;
+        if (out != -1 && row < it.nA) {
+          p.aux[base + row] = make_uint2(best, s1);
+          const int k = atomicAdd(p.cand_cnt + it.pair * 2 + it.dir, 1);
+          p.cand_rows[base + k] = row;
         }
       }
-      const int64_t base = (static_cast<int64_t>(it.pair) * 2 + it.dir) * p.mstride;
-      const int row = it.row0 + row_in_cta;
-      p.mbuf[base + row] = out;
-      if (out != -1 && row < it.nA) {
-        p.aux[base + row] = make_uint2(best, s1);
-        const int k = atomicAdd(p.cand_cnt + it.pair * 2 + it.dir, 1);
-        p.cand_rows[base + k] = row;
-      }
+      asm volatile("bar.sync 2, %0;" ::"r"(kEpiWarps * 32) : "memory");  // merge buffer free for the next item
+    }
+    if (p.prof && threadIdx.x == 0) {
+      atomicAdd(p.prof + 6, static_cast<unsigned long long>(ew));
+      atomicAdd(p.prof + 8, static_cast<unsigned long long>(clock64() - et0));
     }
   }
 
@@ -285,7 +325,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 }
 
 // Exact resolution of the candidate rows of one (pair, direction).
-// Slot s = cp * 32 + r holds the columns j = 128 t + 64 cp + 32 c + r, c in {0, 1}, t = 0, 1, ...
+// Slot s = h * 64 + cp * 32 + r holds the columns j = 256 t + 128 h + 64 cp + 32 c + r, c in {0, 1}, t = 0, 1, ...
 // Candidates are bucketed by winning slot (counting sort in shared memory) so that the n2/64 columns
 // of a slot are staged in shared memory ONCE and reused by every candidate of the bucket (a warp per
 // candidate, dp4a, oracle scan order per lane, multiset-aware merge across lanes).  Rows whose
@@ -363,50 +403,50 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
   const uint8_t* Bm = desc + static_cast<int64_t>(p.img_row0[ib]) * kDim;
   const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = nB_pad / 64;
+  const int n_items = nB_pad / 128;
   const bool staged = n_items <= kSlotColsMax;
 
-  __shared__ int s_start[66];
-  __shared__ int s_fill[65];
+  __shared__ int s_start[130];
+  __shared__ int s_fill[129];
   __shared__ __align__(16) uint8_t s_cols[kSlotColsMax * kSlotRowStride];
 
-  // ---- counting sort of the candidates by bucket (slot 0..63, 64 = generic path)
-  for (int b = threadIdx.x; b < 65; b += 256) s_fill[b] = 0;
+  // ---- counting sort of the candidates by bucket (slot 0..127, 128 = generic path)
+  for (int b = threadIdx.x; b < 129; b += 256) s_fill[b] = 0;
   __syncthreads();
   for (int c = threadIdx.x; c < n_cand; c += 256) {
     const int row = p.cand_rows[base + c];
     const uint2 ax = p.aux[base + row];
-    const int bucket = (ax.x == ax.y || !staged) ? 64 : (-2 - p.mbuf[base + row]);
+    const int bucket = (ax.x == ax.y || !staged) ? 128 : (-2 - p.mbuf[base + row]);
     atomicAdd(&s_fill[bucket], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int b = 0; b < 65; ++b) {
+    for (int b = 0; b < 129; ++b) {
       s_start[b] = acc;
       acc += s_fill[b];
       s_fill[b] = 0;
     }
-    s_start[65] = acc;
+    s_start[129] = acc;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < n_cand; c += 256) {
     const int row = p.cand_rows[base + c];
     const uint2 ax = p.aux[base + row];
-    const int bucket = (ax.x == ax.y || !staged) ? 64 : (-2 - p.mbuf[base + row]);
+    const int bucket = (ax.x == ax.y || !staged) ? 128 : (-2 - p.mbuf[base + row]);
     p.cand_sorted[base + s_start[bucket] + atomicAdd(&s_fill[bucket], 1)] = row;
   }
   __syncthreads();
 
   // ---- staged buckets
-  for (int b = 0; b < 64; ++b) {
+  for (int b = 0; b < 128; ++b) {
     const int c0 = s_start[b], c1 = s_start[b + 1];
     if (c0 == c1) continue;  // uniform
-    const int g = b >> 5, r = b & 31;
+    const int g = b >> 5, r = b & 31;  // g = 2 * h + cp: column offset 64 * g inside a 256-column tile
     __syncthreads();  // previous bucket's readers are done with s_cols
     for (int q = threadIdx.x; q < n_items * 8; q += 256) {
       const int it = q >> 3, part = q & 7;
-      const int j = 128 * (it >> 1) + 64 * g + 32 * (it & 1) + r;
+      const int j = 256 * (it >> 1) + 64 * g + 32 * (it & 1) + r;
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim) + part);
       *reinterpret_cast<uint4*>(s_cols + it * kSlotRowStride + part * 16) = v;
     }
@@ -424,7 +464,7 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
       uint32_t bd = 0, sd = 0;
       int bj = -1;
       for (int it = lane; it < n_items; it += 32) {
-        const int j = 128 * (it >> 1) + 64 * g + 32 * (it & 1) + r;
+        const int j = 256 * (it >> 1) + 64 * g + 32 * (it & 1) + r;
         const uint32_t d = dot128(a, reinterpret_cast<const uint4*>(s_cols + it * kSlotRowStride));
         scan_update(d, j, bd, sd, bj);
       }
@@ -433,7 +473,7 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
   }
 
   // ---- generic bucket: scan global memory (whole row if the maximum is shared by several slots)
-  for (int c = s_start[64] + warp; c < s_start[65]; c += 8) {
+  for (int c = s_start[128] + warp; c < s_start[129]; c += 8) {
     const int row = p.cand_sorted[base + c];
     const uint2 ax = p.aux[base + row];
     const bool multi = (ax.x == ax.y);
@@ -450,7 +490,7 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
     int bj = -1;
     const int n_scan = multi ? nB_pad : n_items;
     for (int it = lane; it < n_scan; it += 32) {
-      const int j = multi ? it : (128 * (it >> 1) + 64 * g + 32 * (it & 1) + r);
+      const int j = multi ? it : (256 * (it >> 1) + 64 * g + 32 * (it & 1) + r);
       const uint32_t d = dot128(a, reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim));
       scan_update(d, j, bd, sd, bj);
     }

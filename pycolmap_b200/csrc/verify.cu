@@ -314,8 +314,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
               }
             }
           }
-          c = __reduce_add_sync(0xffffffffu, c);
-          if (lane == 0 && c) atomicAdd(&sh.chunk_cnt[m], c);
+          if (c) atomicAdd(&sh.chunk_cnt[m], c);  // most hypotheses have (almost) no inliers: cheaper than a warp reduce
         }
       }
       __syncthreads();
@@ -524,10 +523,22 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
   }
 }
 
-__global__ void __launch_bounds__(kRansacThreads, 3) b2m_ransac_kernel(const VerifyParams P) {
+// One instantiation per model kind, so that each gets its own register allocation and occupancy
+// (the closed-form H path needs a fraction of the registers / local memory of the 5-point E path).
+template <int KIND>
+struct KindBlocks;
+template <>
+struct KindBlocks<0> { static constexpr int v = 3; };
+template <>
+struct KindBlocks<1> { static constexpr int v = 4; };
+template <>
+struct KindBlocks<2> { static constexpr int v = 5; };
+
+template <int KIND>
+__global__ void __launch_bounds__(kRansacThreads, KindBlocks<KIND>::v) b2m_ransac_kernel(const VerifyParams P) {
   __shared__ Shared sh;
   const int pair = blockIdx.x;
-  const int kind = P.single_kind >= 0 ? P.single_kind : static_cast<int>(blockIdx.y);
+  constexpr int kind = KIND;
   const int n = P.pair_cnt[pair];
   const int64_t off = P.pair_off[pair];
   const int i1 = P.pairs[2 * pair], i2 = P.pairs[2 * pair + 1];
@@ -562,9 +573,14 @@ __global__ void __launch_bounds__(kRansacThreads, 3) b2m_ransac_kernel(const Ver
   const uint64_t key = splitmix64(P.seed ^ splitmix64((static_cast<uint64_t>(static_cast<uint32_t>(i1)) << 34) ^
                                                         (static_cast<uint64_t>(static_cast<uint32_t>(i2)) << 2) ^
                                                         static_cast<uint64_t>(kind)));
-  if (kind == 0) ransac_problem<0>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
-  else if (kind == 1) ransac_problem<1>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
-  else ransac_problem<2>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
+  ransac_problem<KIND>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
+}
+
+cudaError_t launch_ransac(const VerifyParams& P, int nb, cudaStream_t st) {
+  if (P.single_kind < 0 || P.single_kind == 0) b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, st>>>(P);
+  if (P.single_kind < 0 || P.single_kind == 1) b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, st>>>(P);
+  if (P.single_kind < 0 || P.single_kind == 2) b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
+  return cudaGetLastError();
 }
 
 // Decision tree of EstimateCalibrated/UncalibratedTwoViewGeometry, ExtractInlierMatches (ordered
@@ -917,8 +933,8 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
   }
   P.prof = V->d_prof;
   (void)S;
-  b2m_ransac_kernel<<<dim3(nb, 3), kRansacThreads, 0, ctx->stream>>>(P);
-  V_TRY(ctx, cudaGetLastError());
+  V_TRY(ctx, launch_ransac(P, nb, ctx->stream));
+  ctx->stats.kernel_launches += 2;
   b2m_decide_kernel<<<nb, 256, 0, ctx->stream>>>(P);
   V_TRY(ctx, cudaGetLastError());
   ctx->stats.kernel_launches += 2;
@@ -1054,10 +1070,10 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   P.seed = ctx->seed;
   P.single_kind = single_kind;
   if (single_kind >= 0) {
-    b2m_ransac_kernel<<<dim3(1, 1), kRansacThreads, 0, st>>>(P);
+    V_TRY(ctx, launch_ransac(P, 1, st));
   } else {
-    b2m_ransac_kernel<<<dim3(1, 3), kRansacThreads, 0, st>>>(P);
-    V_TRY(ctx, cudaGetLastError());
+    V_TRY(ctx, launch_ransac(P, 1, st));
+    ctx->stats.kernel_launches += 2;
     b2m_decide_kernel<<<1, 256, 0, st>>>(P);
     ctx->stats.kernel_launches += 1;
   }

@@ -175,6 +175,9 @@ typedef struct b2m_pair_view {
 
 int64_t b2m_results_num_pairs(const b2m_results* r);
 int64_t b2m_results_total_matches(const b2m_results* r);
+/* Number of pairs whose stored geometry is not the default one (config != UNDEFINED), i.e. pairs the
+ * controller would write a verified TwoViewGeometry for (U:controllers/feature_matching_utils.cc). */
+int64_t b2m_results_num_verified(const b2m_results* r);
 int b2m_results_get(const b2m_results* r, int64_t pair, b2m_pair_view* out);
 void b2m_results_free(b2m_results* r);
 

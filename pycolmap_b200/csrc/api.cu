@@ -630,6 +630,13 @@ int b2m_match_pair(b2m_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t
 int64_t b2m_results_num_pairs(const b2m_results* r) { return r ? static_cast<int64_t>(r->cnt.size()) : 0; }
 int64_t b2m_results_total_matches(const b2m_results* r) { return r ? static_cast<int64_t>(r->matches.size() / 2) : 0; }
 
+int64_t b2m_results_num_verified(const b2m_results* r) {
+  if (!r || !r->verified) return 0;
+  int64_t n = 0;
+  for (int32_t c : r->config) n += (c != B2M_UNDEFINED);
+  return n;
+}
+
 int b2m_results_get(const b2m_results* r, int64_t pair, b2m_pair_view* out) {
   if (!r || !out || pair < 0 || pair >= static_cast<int64_t>(r->cnt.size())) return B2M_EINVAL;
   memset(out, 0, sizeof(*out));

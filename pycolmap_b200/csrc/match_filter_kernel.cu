@@ -43,15 +43,15 @@ constexpr int kRowsPerItem = kRowsPerCta * kCluster;  // 256 rows of A per work 
 constexpr int kTileN = 256;                        // columns per B tile: a 128x256x32 MMA hides the smem A read
                                                    // (N <= 128 costs ~92 cycles per MMA regardless of N, profiles/r01_microbench2)
 constexpr int kUmmaK = 32;
-constexpr int kStages = 5;                         // B-tile ring depth (5 x 32 KiB)
+constexpr int kStages = 8;                         // B-tile ring depth (8 x 16 KiB: each CTA stages only ITS half)
 constexpr int kAccStages = 2;
 constexpr int kABufs = 2;                          // A strips double-buffered across work items
 constexpr int kBytesA = kTileM * kDim;             // 16 KiB per strip
-constexpr int kBytesB = kTileN * kDim;             // 32 KiB
+constexpr int kBytesB = (kTileN / kCluster) * kDim;  // 16 KiB: this CTA's half (128 columns) of a B tile
 constexpr int kEpiWarps = 8;                       // warp w: TMEM lane quarter w%4, column half w/4 of every tile
 constexpr int kThreads = (kEpiWarps + 2) * 32;     // + TMA warp + MMA warp
 constexpr int kAccCols = kStrips * kTileN;         // TMEM columns per accumulator stage
-constexpr uint32_t kIdesc = make_idesc_u8u8_s32(kTileM, kTileN);
+constexpr uint32_t kIdesc = make_idesc_u8u8_s32(kTileM * kCluster, kTileN);  // one 256 x 256 x 32 MMA per CTA pair
 constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << kCluster) - 1u);
 static_assert(kRowsPerItem == kRowPad && kTileN == kRowPad, "images are padded to whole items / column tiles");
 
@@ -120,17 +120,17 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars->full_b[s], 1);
-      mbar_init(&bars->empty_b[s], kCluster);  // one tcgen05.commit arrival from every CTA of the cluster
+      mbar_init(&bars->empty_b[s], 1);  // the leader's pair-commit arrives here in both CTAs
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
-      mbar_init(&bars->tmem_empty[s], kEpiWarps * 32);
+      mbar_init(&bars->tmem_empty[s], kCluster * kEpiWarps);  // leader only: one arrival per epilogue warp of the pair
     }
     fence_mbar_init();
   }
   if (warp == kEpiWarps + 1) {
-    tmem_alloc(&bars->tmem_base, kAccStages * kAccCols);
-    tmem_relinquish();
+    tmem_alloc_pair(&bars->tmem_base, kAccStages * kAccCols);  // executed by the same warp of both CTAs
+    tmem_relinquish_pair();
   }
   tc_fence_before();
   __syncthreads();
@@ -149,20 +149,18 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         const uint32_t ab = n_done & 1, aph = (n_done >> 1) & 1;
         ++n_done;
         mbar_wait(&bars->empty_a[ab], aph ^ 1);  // the MMAs of the item that used this A buffer retired
-        mbar_arrive_expect_tx(&bars->full_a[ab], kStrips * kBytesA);
-#pragma unroll
-        for (int s = 0; s < kStrips; ++s)
-          tma_load_2d(smA + (ab * kStrips + s) * kBytesA, &tmap, &bars->full_a[ab], 0, it.rowA + s * kTileM);
+        // both CTAs' bytes are accounted on the LEADER's barriers (the leader issues the pair MMA)
+        if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full_a[ab], kCluster * kBytesA);
+        tma_load_2d_pair(smA + ab * kBytesA, &tmap, &bars->full_a[ab], 0, it.rowA);
         for (int t = 0; t < it.n_tiles; ++t) {
           const long long c0 = clock64();
           mbar_wait(&bars->empty_b[stage], phase ^ 1);
           pw += clock64() - c0;
-          mbar_arrive_expect_tx(&bars->full_b[stage], kBytesB);
-          // this CTA fetches its 128-row half of the tile and multicasts it to the whole cluster, so every
-          // B byte crosses L2 -> SM once per cluster instead of once per CTA
-          tma_load_2d_multicast(smB + stage * kBytesB + cta_rank * (kBytesB / kCluster), &tmap,
-                                &bars->full_b[stage], 0, it.rowB + t * kTileN + cta_rank * (kTileN / kCluster),
-                                kClusterMask);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full_b[stage], kCluster * kBytesB);
+          // this CTA stages only ITS 128-column half of the tile; the pair MMA reads the other half from
+          // the peer's shared memory, so each B byte is written to and read from shared memory once per pair
+          tma_load_2d_pair(smB + stage * kBytesB, &tmap, &bars->full_b[stage], 0,
+                           it.rowB + t * kTileN + cta_rank * (kTileN / kCluster));
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -175,8 +173,8 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    // ===== MMA issuer (one thread): two 128x128x128 MMAs per B tile =====
-    if (lane == 0) {
+    // ===== MMA issuer: ONE thread of the leader CTA drives the 256-row MMAs of the pair =====
+    if (lane == 0 && cta_rank == 0) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, n_done = 0;
       long long mw_e = 0, mw_f = 0, mt0 = clock64();
       for (int w = cluster_id; w < p.n_items; w += n_clusters) {
@@ -188,7 +186,10 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         uint64_t adesc[kStrips];
 #pragma unroll
         for (int s = 0; s < kStrips; ++s) adesc[s] = make_smem_desc_sw128(smem_u32(smA + (ab * kStrips + s) * kBytesA));
-        if (it.n_tiles == 0) mbar_arrive(&bars->empty_a[ab]);  // nothing will read this A buffer
+        if (it.n_tiles == 0) {  // nothing will read this A buffer: release it in both CTAs
+          mbar_arrive_cluster(&bars->empty_a[ab], 0);
+          mbar_arrive_cluster(&bars->empty_a[ab], 1);
+        }
         for (int t = 0; t < it.n_tiles; ++t) {
           const long long c0 = clock64();
           mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
@@ -203,11 +204,11 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
             const uint32_t tmem_d = tmem_base + as * kAccCols + s * kTileN;
 #pragma unroll
             for (int k = 0; k < kDim / kUmmaK; ++k)
-              mma_i8_ss(tmem_d, adesc[s] + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
+              mma_i8_ss_pair(tmem_d, adesc[s] + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
           }
-          mma_commit_multicast(&bars->empty_b[stage], kClusterMask);  // both CTAs' producers may refill
-          mma_commit(&bars->tmem_full[as]);
-          if (t == it.n_tiles - 1) mma_commit(&bars->empty_a[ab]);   // A buffer reusable after the last MMA
+          mma_commit_pair(&bars->empty_b[stage], kClusterMask);  // both CTAs' producers may refill
+          mma_commit_pair(&bars->tmem_full[as], kClusterMask);   // both CTAs' epilogues may drain
+          if (t == it.n_tiles - 1) mma_commit_pair(&bars->empty_a[ab], kClusterMask);  // A buffers reusable
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -257,7 +258,8 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         tmem_ld_32x32(taddr + 96, vb);
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(&bars->tmem_empty[as]);  // the last two chunks are in registers: TMEM stage is free
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[as], 0);  // registers hold the tile: stage is free
 #pragma unroll
         for (int r = 0; r < 32; ++r) B1[r] = max(B1[r], max(va[r], vb[r]));
         if (++as == kAccStages) {
@@ -319,9 +321,9 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   __syncthreads();
   if (warp == kEpiWarps + 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kAccStages * kAccCols);
   }
-  cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
+  cluster_sync_all();  // both CTAs are done with the pair's TMEM / barriers
+  if (warp == kEpiWarps + 1) tmem_dealloc_pair(tmem_base, kAccStages * kAccCols);
 }
 
 // Exact resolution of the candidate rows of one (pair, direction).

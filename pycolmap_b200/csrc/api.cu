@@ -495,9 +495,10 @@ void b2m_destroy(b2m_ctx* ctx) {
   if (ctx->d_k1_prof) {
     unsigned long long h[16];
     cudaMemcpy(h, ctx->d_k1_prof, sizeof(h), cudaMemcpyDeviceToHost);
-    const char* names[9] = {"producer wait empty_b", "producer total", "mma wait tmem_empty", "mma wait full_b", "-",
-                            "mma total", "epi(warp0) wait tmem_full", "-", "epi(warp0) total"};
-    for (int k = 0; k < 9; ++k)
+    const char* names[13] = {"producer wait empty_b", "producer total", "mma wait tmem_empty", "mma wait full_b", "-",
+                             "mma total", "epi(warp0) wait tmem_full", "-", "epi(warp0) total", "epi ld pair 1",
+                             "epi max3 #1", "epi ld pair 2", "epi fence+arrive"};
+    for (int k = 0; k < 13; ++k)
       if (names[k][0] != '-') fprintf(stderr, "[b2m prof] K1 %-28s %12.3f Mcycles\n", names[k], h[k] / 1e6);
     cudaFree(ctx->d_k1_prof);
   }

@@ -232,7 +232,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     const int row_in_cta = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t as = 0, aphase = 0;
-    long long ew = 0, et0 = clock64();
+    long long ew = 0, e_ld1 = 0, e_c1 = 0, e_ld2 = 0, e_arr = 0, et0 = clock64();
     for (int w = cluster_id; w < p.n_items; w += n_clusters) {
       const Item it = decode_item(p, w, cta_rank);
       if (!it.valid) continue;
@@ -249,17 +249,23 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + as * kAccCols + half * 128;
         uint32_t va[32], vb[32];
+        const long long q0 = clock64();
         tmem_ld_32x32(taddr, va);
         tmem_ld_32x32(taddr + 32, vb);
         tmem_wait_ld();
+        const long long q1 = clock64();
 #pragma unroll
         for (int r = 0; r < 32; ++r) B0[r] = max(B0[r], max(va[r], vb[r]));
+        const long long q2 = clock64();
         tmem_ld_32x32(taddr + 64, va);
         tmem_ld_32x32(taddr + 96, vb);
         tmem_wait_ld();
+        const long long q3 = clock64();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[as], 0);  // registers hold the tile: stage is free
+        const long long q4 = clock64();
+        e_ld1 += q1 - q0; e_c1 += q2 - q1; e_ld2 += q3 - q2; e_arr += q4 - q3;
 #pragma unroll
         for (int r = 0; r < 32; ++r) B1[r] = max(B1[r], max(va[r], vb[r]));
         if (++as == kAccStages) {
@@ -313,6 +319,10 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     }
     if (p.prof && threadIdx.x == 0) {
       atomicAdd(p.prof + 6, static_cast<unsigned long long>(ew));
+      atomicAdd(p.prof + 9, static_cast<unsigned long long>(e_ld1));
+      atomicAdd(p.prof + 10, static_cast<unsigned long long>(e_c1));
+      atomicAdd(p.prof + 11, static_cast<unsigned long long>(e_ld2));
+      atomicAdd(p.prof + 12, static_cast<unsigned long long>(e_arr));
       atomicAdd(p.prof + 8, static_cast<unsigned long long>(clock64() - et0));
     }
   }

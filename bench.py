@@ -214,7 +214,11 @@ def main():
             for _ in range(n_img)]
     nfeat = np.full(n_img, K, np.int32)
 
-    all_pairs = syn.exhaustive_pairs(n_img)
+    # every unordered pair once, visited block by block like ExhaustiveFeatureMatcher::Run with the
+    # default block_size = 50 (U:controllers/feature_matching.cc): a 50 x 50 block re-uses 100 images
+    # (105 MB of descriptors), which stay L2-resident
+    from pycolmap_b200.pipeline import exhaustive_pair_blocks
+    all_pairs = np.concatenate(list(exhaustive_pair_blocks(n_img, 50)))
     my_pairs = sharding.pair_shard(all_pairs, rank, world)       # independent units, no data-path collective
 
     ctx = pb.Context(device=local_rank, pair_batch=args.pair_batch)

@@ -95,12 +95,25 @@ __device__ __forceinline__ Item decode_item(const MatchParams& p, int w, uint32_
 
 }  // namespace
 
+// elect.sync: true in exactly one (converged) lane.  The MMA / TMA roles keep their whole warp converged
+// and predicate only the tcgen05 / TMA instructions, so descriptors and addresses stay warp-uniform
+// (uniform registers) instead of being rebuilt in vector registers and moved over for every instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
                      const MatchParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smA = smem;                                     // [kABufs][kStrips][16 KiB]
+  uint8_t* smA = smem;                                     // [kABufs][16 KiB]
   uint8_t* smB = smem + kABufs * kStrips * kBytesA;        // [kStages][16 KiB]
   uint32_t* merge = reinterpret_cast<uint32_t*>(smB + kStages * kBytesB);
   Barriers* bars = reinterpret_cast<Barriers*>(smB + kStages * kBytesB + kMergeBytes);
@@ -113,7 +126,6 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tmap);
-    tma_prefetch_desc(&tmap_half);
     for (int s = 0; s < kABufs; ++s) {
       mbar_init(&bars->full_a[s], 1);
       mbar_init(&bars->empty_a[s], 1);
@@ -134,81 +146,75 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // peer barriers are initialised before any multicast can signal them
+  cluster_sync_all();  // peer barriers are initialised before any remote arrival / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == kEpiWarps) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, n_done = 0;
-      long long pw = 0, pt0 = clock64();
-      for (int w = cluster_id; w < p.n_items; w += n_clusters) {
-        const Item it = decode_item(p, w, cta_rank);
-        if (!it.valid) continue;
-        const uint32_t ab = n_done & 1, aph = (n_done >> 1) & 1;
-        ++n_done;
-        mbar_wait(&bars->empty_a[ab], aph ^ 1);  // the MMAs of the item that used this A buffer retired
+    // ===== TMA producer (whole warp converged, one elected lane issues) =====
+    uint32_t stage = 0, phase = 0, n_done = 0;
+    for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+      const Item it = decode_item(p, w, cta_rank);
+      if (!it.valid) continue;
+      const uint32_t ab = n_done & 1, aph = (n_done >> 1) & 1;
+      ++n_done;
+      mbar_wait(&bars->empty_a[ab], aph ^ 1);  // the MMAs of the item that used this A buffer retired
+      if (elect_one()) {
         // both CTAs' bytes are accounted on the LEADER's barriers (the leader issues the pair MMA)
         if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full_a[ab], kCluster * kBytesA);
         tma_load_2d_pair(smA + ab * kBytesA, &tmap, &bars->full_a[ab], 0, it.rowA);
-        for (int t = 0; t < it.n_tiles; ++t) {
-          const long long c0 = clock64();
-          mbar_wait(&bars->empty_b[stage], phase ^ 1);
-          pw += clock64() - c0;
+      }
+      __syncwarp();
+      for (int t = 0; t < it.n_tiles; ++t) {
+        mbar_wait(&bars->empty_b[stage], phase ^ 1);
+        if (elect_one()) {
           if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full_b[stage], kCluster * kBytesB);
           // this CTA stages only ITS 128-column half of the tile; the pair MMA reads the other half from
           // the peer's shared memory, so each B byte is written to and read from shared memory once per pair
           tma_load_2d_pair(smB + stage * kBytesB, &tmap, &bars->full_b[stage], 0,
-                           it.rowB + t * kTileN + cta_rank * (kTileN / kCluster));
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+                           it.rowB + t * kTileN + static_cast<int>(cta_rank) * (kTileN / kCluster));
         }
-      }
-      if (p.prof) {
-        atomicAdd(p.prof + 0, static_cast<unsigned long long>(pw));
-        atomicAdd(p.prof + 1, static_cast<unsigned long long>(clock64() - pt0));
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    // ===== MMA issuer: ONE thread of the leader CTA drives the 256-row MMAs of the pair =====
-    if (lane == 0 && cta_rank == 0) {
+    // ===== MMA issuer: the leader CTA's warp drives the 256-row MMAs of the pair (one elected lane issues) =====
+    if (cta_rank == 0) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, n_done = 0;
-      long long mw_e = 0, mw_f = 0, mt0 = clock64();
+      const uint32_t smA_u32 = smem_u32(smA), smB_u32 = smem_u32(smB);
       for (int w = cluster_id; w < p.n_items; w += n_clusters) {
         const Item it = decode_item(p, w, cta_rank);
         if (!it.valid) continue;
         const uint32_t ab = n_done & 1, aph = (n_done >> 1) & 1;
         ++n_done;
         mbar_wait(&bars->full_a[ab], aph);
-        uint64_t adesc[kStrips];
-#pragma unroll
-        for (int s = 0; s < kStrips; ++s) adesc[s] = make_smem_desc_sw128(smem_u32(smA + (ab * kStrips + s) * kBytesA));
+        const uint64_t adesc = make_smem_desc_sw128(smA_u32 + ab * kBytesA);
         if (it.n_tiles == 0) {  // nothing will read this A buffer: release it in both CTAs
-          mbar_arrive_cluster(&bars->empty_a[ab], 0);
-          mbar_arrive_cluster(&bars->empty_a[ab], 1);
+          if (elect_one()) {
+            mbar_arrive_cluster(&bars->empty_a[ab], 0);
+            mbar_arrive_cluster(&bars->empty_a[ab], 1);
+          }
+          __syncwarp();
         }
         for (int t = 0; t < it.n_tiles; ++t) {
-          const long long c0 = clock64();
           mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
-          const long long c1 = clock64();
           mbar_wait(&bars->full_b[stage], phase);
-          mw_e += c1 - c0;
-          mw_f += clock64() - c1;
           tc_fence_after();
-          const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smB + stage * kBytesB));
-#pragma unroll
-          for (int s = 0; s < kStrips; ++s) {
-            const uint32_t tmem_d = tmem_base + as * kAccCols + s * kTileN;
+          const uint64_t bdesc = make_smem_desc_sw128(smB_u32 + stage * kBytesB);
+          const uint32_t tmem_d = tmem_base + as * kAccCols;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kDim / kUmmaK; ++k)
-              mma_i8_ss_pair(tmem_d, adesc[s] + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
+              mma_i8_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0 ? 1u : 0u);
+            mma_commit_pair(&bars->empty_b[stage], kClusterMask);  // both CTAs' producers may refill
+            mma_commit_pair(&bars->tmem_full[as], kClusterMask);   // both CTAs' epilogues may drain
+            if (t == it.n_tiles - 1) mma_commit_pair(&bars->empty_a[ab], kClusterMask);  // A buffers reusable
           }
-          mma_commit_pair(&bars->empty_b[stage], kClusterMask);  // both CTAs' producers may refill
-          mma_commit_pair(&bars->tmem_full[as], kClusterMask);   // both CTAs' epilogues may drain
-          if (t == it.n_tiles - 1) mma_commit_pair(&bars->empty_a[ab], kClusterMask);  // A buffers reusable
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -219,11 +225,6 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           }
         }
       }
-      if (p.prof) {
-        atomicAdd(p.prof + 2, static_cast<unsigned long long>(mw_e));
-        atomicAdd(p.prof + 3, static_cast<unsigned long long>(mw_f));
-        atomicAdd(p.prof + 5, static_cast<unsigned long long>(clock64() - mt0));
-      }
     }
   } else {
     // ===== filter epilogue =====
@@ -232,7 +233,6 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     const int row_in_cta = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t as = 0, aphase = 0;
-    long long ew = 0, e_ld1 = 0, e_c1 = 0, e_ld2 = 0, e_arr = 0, et0 = clock64();
     for (int w = cluster_id; w < p.n_items; w += n_clusters) {
       const Item it = decode_item(p, w, cta_rank);
       if (!it.valid) continue;
@@ -243,29 +243,21 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         B1[r] = 0u;
       }
       for (int t = 0; t < it.n_tiles; ++t) {
-        const long long c0 = clock64();
         mbar_wait(&bars->tmem_full[as], aphase);
-        ew += clock64() - c0;
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + as * kAccCols + half * 128;
         uint32_t va[32], vb[32];
-        const long long q0 = clock64();
         tmem_ld_32x32(taddr, va);
         tmem_ld_32x32(taddr + 32, vb);
         tmem_wait_ld();
-        const long long q1 = clock64();
 #pragma unroll
         for (int r = 0; r < 32; ++r) B0[r] = max(B0[r], max(va[r], vb[r]));
-        const long long q2 = clock64();
         tmem_ld_32x32(taddr + 64, va);
         tmem_ld_32x32(taddr + 96, vb);
         tmem_wait_ld();
-        const long long q3 = clock64();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[as], 0);  // registers hold the tile: stage is free
-        const long long q4 = clock64();
-        e_ld1 += q1 - q0; e_c1 += q2 - q1; e_ld2 += q3 - q2; e_arr += q4 - q3;
 #pragma unroll
         for (int r = 0; r < 32; ++r) B1[r] = max(B1[r], max(va[r], vb[r]));
         if (++as == kAccStages) {
@@ -317,23 +309,15 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       }
       asm volatile("bar.sync 2, %0;" ::"r"(kEpiWarps * 32) : "memory");  // merge buffer free for the next item
     }
-    if (p.prof && threadIdx.x == 0) {
-      atomicAdd(p.prof + 6, static_cast<unsigned long long>(ew));
-      atomicAdd(p.prof + 9, static_cast<unsigned long long>(e_ld1));
-      atomicAdd(p.prof + 10, static_cast<unsigned long long>(e_c1));
-      atomicAdd(p.prof + 11, static_cast<unsigned long long>(e_ld2));
-      atomicAdd(p.prof + 12, static_cast<unsigned long long>(e_arr));
-      atomicAdd(p.prof + 8, static_cast<unsigned long long>(clock64() - et0));
-    }
   }
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // both CTAs are done with the pair's TMEM / barriers
   if (warp == kEpiWarps + 1) {
     tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kAccStages * kAccCols);
   }
-  cluster_sync_all();  // both CTAs are done with the pair's TMEM / barriers
-  if (warp == kEpiWarps + 1) tmem_dealloc_pair(tmem_base, kAccStages * kAccCols);
 }
 
 // Exact resolution of the candidate rows of one (pair, direction).

@@ -576,10 +576,31 @@ __global__ void __launch_bounds__(kRansacThreads, KindBlocks<KIND>::v) b2m_ransa
   ransac_problem<KIND>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
 }
 
-cudaError_t launch_ransac(const VerifyParams& P, int nb, cudaStream_t st) {
-  if (P.single_kind < 0 || P.single_kind == 0) b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, st>>>(P);
-  if (P.single_kind < 0 || P.single_kind == 1) b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, st>>>(P);
-  if (P.single_kind < 0 || P.single_kind == 2) b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
+// The three model kinds are independent problems: E and F go to two side streams so that their
+// (few, long) CTAs fill the tail of the H kernel instead of serialising behind it.
+struct RansacStreams {
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+};
+
+cudaError_t launch_ransac(const VerifyParams& P, int nb, cudaStream_t st, RansacStreams* rs = nullptr) {
+  if (P.single_kind >= 0 || !rs || !rs->side[0]) {
+    if (P.single_kind < 0 || P.single_kind == 0) b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, st>>>(P);
+    if (P.single_kind < 0 || P.single_kind == 1) b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, st>>>(P);
+    if (P.single_kind < 0 || P.single_kind == 2) b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaEventRecord(rs->fork, st);
+  if (e != cudaSuccess) return e;
+  cudaStreamWaitEvent(rs->side[0], rs->fork, 0);
+  cudaStreamWaitEvent(rs->side[1], rs->fork, 0);
+  b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, rs->side[0]>>>(P);
+  b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, rs->side[1]>>>(P);
+  b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
+  cudaEventRecord(rs->join[0], rs->side[0]);
+  cudaEventRecord(rs->join[1], rs->side[1]);
+  cudaStreamWaitEvent(st, rs->join[0], 0);
+  cudaStreamWaitEvent(st, rs->join[1], 0);
   return cudaGetLastError();
 }
 
@@ -799,6 +820,7 @@ struct VerifyState {
   uint2* h_inliers[2] = {nullptr, nullptr};
   DevCamera* d_cams = nullptr;
   unsigned long long* d_prof = nullptr;
+  RansacStreams rs;
   int n_cams = 0;
   const void* cams_of = nullptr;  // ImageSet the cameras were uploaded for
   void release() {
@@ -933,7 +955,14 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
   }
   P.prof = V->d_prof;
   (void)S;
-  V_TRY(ctx, launch_ransac(P, nb, ctx->stream));
+  if (!V->rs.side[0]) {
+    V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[0], cudaStreamNonBlocking));
+    V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[1], cudaStreamNonBlocking));
+    V_TRY(ctx, cudaEventCreateWithFlags(&V->rs.fork, cudaEventDisableTiming));
+    V_TRY(ctx, cudaEventCreateWithFlags(&V->rs.join[0], cudaEventDisableTiming));
+    V_TRY(ctx, cudaEventCreateWithFlags(&V->rs.join[1], cudaEventDisableTiming));
+  }
+  V_TRY(ctx, launch_ransac(P, nb, ctx->stream, &V->rs));
   ctx->stats.kernel_launches += 2;
   b2m_decide_kernel<<<nb, 256, 0, ctx->stream>>>(P);
   V_TRY(ctx, cudaGetLastError());

@@ -25,6 +25,11 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 
+def log(msg):
+    """Progress on stderr (stdout carries exactly one JSON line)."""
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -130,8 +135,15 @@ def cpu_baseline(desc_np, n_feat, pairs, budget_s, verify, kpts_np=None, cam=Non
                      kpts_np[sample[k, 1] * K:(sample[k, 1] + 1) * K].astype(np.float64), res[k], k) for k in cand]
             procs = min(cores, len(jobs))
             t0 = time.perf_counter()
-            with mp.get_context("fork").Pool(procs) as pool:
-                times = pool.map(_verify_worker, jobs)
+            # "spawn": the parent may hold a CUDA context and helper threads -- fork() is not safe there
+            try:
+                with mp.get_context("spawn").Pool(procs) as pool:
+                    pool.map(_verify_worker, jobs[:procs])          # warm-up: interpreter + numpy import
+                    t0 = time.perf_counter()
+                    pool.map_async(_verify_worker, jobs).get(timeout=180)
+            except Exception as e:  # noqa: BLE001  (never let the baseline leg hang the bench)
+                out["verify_error"] = repr(e)
+                return out, sample, res
             wall = time.perf_counter() - t0
             core_s_verify = wall * procs / len(jobs)
             core_s_match = cores * dt / n
@@ -210,6 +222,8 @@ def main():
     kpts_full = sharding.all_gather_rows(scene["kpts"].reshape(-1, 2), n_img, K, rank, world, dist)
     desc_full, kpts_full = desc_full.contiguous(), kpts_full.contiguous()
     torch.cuda.synchronize()
+    if rank == 0:
+        log(f"scene ready: {n_img} images x {K} features on {world} rank(s)")
     cams = [dict(model=0, width=1600, height=1200, params=[1200.0, 800.0, 600.0], has_prior_focal_length=1)
             for _ in range(n_img)]
     nfeat = np.full(n_img, K, np.int32)
@@ -244,6 +258,8 @@ def main():
     for _ in range(args.warmup):
         one_step()
     barrier()
+    if rank == 0:
+        log("warm-up done")
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -259,6 +275,8 @@ def main():
         total_matches = d
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    if rank == 0:
+        log(f"timed region done: {wall_ms / max(args.steps, 1):.0f} ms/step")
     clk = clocks.stop() if rank == 0 else None
     launches = ctx.stats().kernel_launches - launches0
 
@@ -346,6 +364,8 @@ def main():
             "algorithmic": "2*K1*K2*128 int8 ops per pair (one GEMM; the transposed GEMM of the cross-check "
                            "direction is not counted)"}
 
+    if rank == 0:
+        log("e2e leg done; cpu baseline ...")
     cb = None
     if not args.no_cpu:
         n_small = min(n_img, 48)

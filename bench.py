@@ -133,17 +133,28 @@ def cpu_baseline(desc_np, n_feat, pairs, budget_s, verify, kpts_np=None, cam=Non
         if cand:
             jobs = [(cam, kpts_np[sample[k, 0] * K:(sample[k, 0] + 1) * K].astype(np.float64),
                      kpts_np[sample[k, 1] * K:(sample[k, 1] + 1) * K].astype(np.float64), res[k], k) for k in cand]
-            procs = min(cores, len(jobs))
+            procs = min(cores, len(jobs), 64)
+            jobs = jobs[: 2 * procs]
             t0 = time.perf_counter()
-            # "spawn": the parent may hold a CUDA context and helper threads -- fork() is not safe there
+            # "spawn": the parent may hold a CUDA context and helper threads -- fork() is not safe there.
+            # One BLAS thread per worker: the children must see these BEFORE they import numpy (128
+            # processes x 128 OpenBLAS threads on 9x9 matrices made this leg crawl for minutes).
+            saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+            os.environ.update({k: "1" for k in saved})
             try:
                 with mp.get_context("spawn").Pool(procs) as pool:
-                    pool.map(_verify_worker, jobs[:procs])          # warm-up: interpreter + numpy import
+                    pool.map_async(_verify_worker, jobs[:procs]).get(timeout=120)   # warm-up: interpreter + imports
                     t0 = time.perf_counter()
                     pool.map_async(_verify_worker, jobs).get(timeout=180)
             except Exception as e:  # noqa: BLE001  (never let the baseline leg hang the bench)
                 out["verify_error"] = repr(e)
                 return out, sample, res
+            finally:
+                for k, v in saved.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
             wall = time.perf_counter() - t0
             core_s_verify = wall * procs / len(jobs)
             core_s_match = cores * dt / n

@@ -297,10 +297,35 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     cp.img_row0 = S.d_row0;
     cp.kpts = tvg ? S.d_kpts : nullptr;
     cp.pts = tvg ? static_cast<double4*>(verify_points_arena(ctx, s)) : nullptr;
+    cp.enable = nullptr;
     CU_TRY_R(launch_crosscheck_compact(cp, nb, st));
     ctx->stats.kernel_launches += 1;
     if (tvg)
       if (int rc = verify_batch_launch(ctx, S, tvg, sift, s, p0, nb)) return bail(rc);
+    if (tvg && sift->guided_matching) {
+      // K1g: re-match the verified pairs under their geometry; the result replaces the inlier matches
+      GuidedSlot gs;
+      if (int rc = verify_guided_slot(ctx, s, &gs)) return bail(rc);
+      GuidedParams gp;
+      gp.kind = gs.kind;
+      gp.model = gs.model;
+      gp.kpts = S.d_kpts;
+      const float me = static_cast<float>(tvg->ransac.max_error);
+      gp.max_residual = me * me;
+      CU_TRY_R(launch_k1_guided(S.tmap, mp, gp, nb, max_strips, n_dirs, st));
+      CU_TRY_R(cudaMemsetAsync(gs.cursor, 0, sizeof(unsigned long long), st));
+      CompactParams gc = cp;
+      gc.arena = gs.arena;
+      gc.cursor = gs.cursor;
+      gc.pair_off = gs.off;
+      gc.pair_cnt = gs.cnt;
+      gc.kpts = nullptr;
+      gc.pts = nullptr;
+      gc.enable = gs.kind;
+      CU_TRY_R(launch_crosscheck_compact(gc, nb, st));
+      CU_TRY_R(cudaMemcpyAsync(gs.h_cursor, gs.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      ctx->stats.kernel_launches += 2;
+    }
     CU_TRY_R(cudaMemcpyAsync(W.h_cursor[s], W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU_TRY_R(cudaEventRecord(ctx->ev_k[s], st));
     if (b > 0)

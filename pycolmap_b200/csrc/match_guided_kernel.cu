@@ -1,0 +1,265 @@
+// match_guided_kernel.cu -- K1g: guided matching.  The tcgen05 int8 GEMM of K1 with an epilogue that
+// first zeroes every dot product whose keypoint pair violates the two-view geometry of the image pair
+// (float32, as upstream) and then runs the exact running top-2 / ratio / distance logic.
+//
+// Semantics: U:feature/sift.cc MatchGuidedSiftFeaturesCPU (COLMAP 3.9.1), SURVEY.md section 8 row G1,
+// reached from R:pipeline/match_features.h:97-100 (SiftMatchingOptions.guided_matching):
+//   CALIBRATED / UNCALIBRATED geometry -> squared Sampson error of F,  PLANAR / PANORAMIC /
+//   PLANAR_OR_PANORAMIC -> squared forward transfer error of H; entries with error > max_error^2 get
+//   dist = 0; then FindBestMatchesBruteForce; the result replaces TwoViewGeometry::inlier_matches.
+// The float32 filter is written with non-fused single operations in the same order as the oracle
+// (oracle/oracle_match.c orc_match_guided, compiled with -ffp-contract=off) so that the match indices
+// are bit-identical.  Work unit = (pair, direction, 128-row strip); only pairs flagged by the decision
+// kernel do any work, so the simple non-persistent pipeline of match_kernel.cu is reused.
+#include "match_kernel.cuh"
+#include "ptx.cuh"
+
+namespace b2m {
+
+namespace {
+
+constexpr int kDim = 128;
+constexpr int kTileM = 128;
+constexpr int kTileN = 256;
+constexpr int kUmmaK = 32;
+constexpr int kStages = 3;
+constexpr int kAccStages = 2;
+constexpr int kBytesA = kTileM * kDim;
+constexpr int kBytesB = kTileN * kDim;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr uint32_t kIdesc = make_idesc_u8u8_s32(kTileM, kTileN);
+
+struct __align__(8) Barriers {
+  uint64_t full_a;
+  uint64_t full_b[kStages];
+  uint64_t empty_b[kStages];
+  uint64_t tmem_full[kAccStages];
+  uint64_t tmem_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+constexpr int kKpBytes = 2 * kTileN * 8;  // two buffers of 256 column keypoints (float2)
+constexpr size_t kSmemBytes = 1024 + kBytesA + kStages * kBytesB + kKpBytes + sizeof(Barriers);
+
+__device__ __forceinline__ void merge_top2(uint32_t& a1, uint32_t& a2, uint32_t b1, uint32_t b2) {
+  const uint32_t lo = min(a1, b1);
+  a1 = max(a1, b1);
+  a2 = max(max(a2, b2), lo);
+}
+
+// 1 when the correspondence (x1, y1) in image 1 <-> (x2, y2) in image 2 is consistent with the model.
+// kind 0: F (squared Sampson error), kind 1: H (squared forward transfer error).  Same operation order
+// as orc_match_guided, every operation rounded separately.
+__device__ __forceinline__ bool consistent(int kind, const float* M, float x1, float y1, float x2, float y2,
+                                           float thr) {
+  float r;
+  if (kind == 0) {
+    const float Fx0 = __fadd_rn(__fadd_rn(__fmul_rn(M[0], x1), __fmul_rn(M[1], y1)), M[2]);
+    const float Fx1 = __fadd_rn(__fadd_rn(__fmul_rn(M[3], x1), __fmul_rn(M[4], y1)), M[5]);
+    const float Fx2 = __fadd_rn(__fadd_rn(__fmul_rn(M[6], x1), __fmul_rn(M[7], y1)), M[8]);
+    const float Ft0 = __fadd_rn(__fadd_rn(__fmul_rn(M[0], x2), __fmul_rn(M[3], y2)), M[6]);
+    const float Ft1 = __fadd_rn(__fadd_rn(__fmul_rn(M[1], x2), __fmul_rn(M[4], y2)), M[7]);
+    const float num = __fadd_rn(__fadd_rn(__fmul_rn(x2, Fx0), __fmul_rn(y2, Fx1)), Fx2);
+    const float den = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Fx0, Fx0), __fmul_rn(Fx1, Fx1)), __fmul_rn(Ft0, Ft0)),
+                                __fmul_rn(Ft1, Ft1));
+    r = __fdiv_rn(__fmul_rn(num, num), den);
+  } else {
+    const float w = __fadd_rn(__fadd_rn(__fmul_rn(M[6], x1), __fmul_rn(M[7], y1)), M[8]);
+    const float u = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x1), __fmul_rn(M[1], y1)), M[2]), w);
+    const float v = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[3], x1), __fmul_rn(M[4], y1)), M[5]), w);
+    const float du = __fsub_rn(u, x2), dv = __fsub_rn(v, y2);
+    r = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
+  }
+  return r <= thr;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p, const GuidedParams g) {
+  const int pair = blockIdx.z;
+  const int gkind = g.kind[pair];
+  if (gkind < 0) return;  // pair not eligible for guided matching (uniform exit)
+  const int dir = blockIdx.y;
+  const int strip = blockIdx.x;
+  const int ia = p.pairs[2 * pair + dir];
+  const int ib = p.pairs[2 * pair + (dir ^ 1)];
+  const int nA = p.img_nfeat[ia];
+  const int nB = p.img_nfeat[ib];
+  if (strip * kTileM >= nA) return;
+  const int rowA = p.img_row0[ia] + strip * kTileM;
+  const int rowB = p.img_row0[ib];
+  const int n_tiles = (nB + kTileN - 1) / kTileN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + kBytesA;
+  float2* kp_s = reinterpret_cast<float2*>(smem + kBytesA + kStages * kBytesB);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + kBytesA + kStages * kBytesB + kKpBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == kEpiWarps && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(&bars->full_a, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars->full_b[s], 1);
+      mbar_init(&bars->empty_b[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&bars->tmem_full[s], 1);
+      mbar_init(&bars->tmem_empty[s], kEpiWarps * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kEpiWarps + 1) {
+    tmem_alloc(&bars->tmem_base, kAccStages * kTileN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == kEpiWarps) {
+    if (lane == 0 && n_tiles > 0) {
+      mbar_arrive_expect_tx(&bars->full_a, kBytesA);
+      tma_load_2d(smA, &tmap, &bars->full_a, 0, rowA);
+      uint32_t stage = 0, phase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&bars->empty_b[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bars->full_b[stage], kBytesB);
+        uint8_t* dst = smB + stage * kBytesB;
+        tma_load_2d(dst, &tmap, &bars->full_b[stage], 0, rowB + t * kTileN);
+        tma_load_2d(dst + kBytesA, &tmap, &bars->full_b[stage], 0, rowB + t * kTileN + 128);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    if (lane == 0 && n_tiles > 0) {
+      mbar_wait(&bars->full_a, 0);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smA));
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        mbar_wait(&bars->full_b[stage], phase);
+        tc_fence_after();
+        const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smB + stage * kBytesB));
+        const uint32_t tmem_d = tmem_base + as * kTileN;
+#pragma unroll
+        for (int k = 0; k < kDim / kUmmaK; ++k)
+          mma_i8_ss(tmem_d, adesc0 + 2 * k, bdesc0 + 2 * k, kIdesc, k > 0 ? 1u : 0u);
+        mma_commit(&bars->empty_b[stage]);
+        mma_commit(&bars->tmem_full[as]);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++as == kAccStages) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: geometric mask, then exact running top-2 (thread <-> row) =====
+    const int row_in_strip = warp * 32 + lane;
+    const int row = strip * kTileM + row_in_strip;
+    float M[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) M[k] = g.model[pair * 9 + k];
+    const float thr = g.max_residual;
+    const float2 kr = (row < nA) ? g.kpts[p.img_row0[ia] + row] : make_float2(0.f, 0.f);
+    const float2* kcol = g.kpts + p.img_row0[ib];
+    int32_t best_d = 0, best_c = -1, second_d = 0;
+    uint32_t as = 0, aphase = 0;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    for (int t = 0; t < n_tiles; ++t) {
+      // stage the 256 column keypoints of this tile (two per thread), double-buffered by tile parity
+      float2* kb = kp_s + (t & 1) * kTileN;
+      for (int c = threadIdx.x; c < kTileN; c += kEpiWarps * 32) {
+        const int j = t * kTileN + c;
+        kb[c] = (j < nB) ? kcol[j] : make_float2(0.f, 0.f);
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_base + as * kTileN;
+      uint32_t k1[4] = {0, 0, 0, 0}, k2[4] = {0, 0, 0, 0};
+#pragma unroll 1
+      for (int c = 0; c < kTileN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 kc = kb[c * 32 + j];
+          // image 1 is pairs[2*pair], image 2 is pairs[2*pair+1]: in direction 1 rows are image 2
+          const bool ok = (dir == 0) ? consistent(gkind, M, kr.x, kr.y, kc.x, kc.y, thr)
+                                     : consistent(gkind, M, kc.x, kc.y, kr.x, kr.y, thr);
+          const uint32_t d = ok ? v[j] : 0u;
+          const uint32_t key = (d << 8) | static_cast<uint32_t>(255 - (c * 32 + j));
+          const uint32_t lo = min(k1[j & 3], key);
+          k1[j & 3] = max(k1[j & 3], key);
+          k2[j & 3] = max(k2[j & 3], lo);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->tmem_empty[as]);
+      merge_top2(k1[0], k2[0], k1[1], k2[1]);
+      merge_top2(k1[2], k2[2], k1[3], k2[3]);
+      merge_top2(k1[0], k2[0], k1[2], k2[2]);
+      const int32_t d1 = static_cast<int32_t>(k1[0] >> 8);
+      const int32_t d2 = static_cast<int32_t>(k2[0] >> 8);
+      if (d1 > best_d) {
+        second_d = max(best_d, d2);
+        best_d = d1;
+        best_c = t * kTileN + (255 - static_cast<int32_t>(k1[0] & 255u));
+      } else {
+        second_d = max(second_d, d1);
+      }
+      if (++as == kAccStages) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    int32_t out = -1;
+    if (best_d > 0) {
+      const float a = __ldg(p.acos_lut + min(best_d, 262144));
+      if (!(a > p.max_distance)) {
+        const float b = __ldg(p.acos_lut + min(second_d, 262144));
+        if (!(a >= __fmul_rn(p.max_ratio, b))) out = best_c;
+      }
+    }
+    p.mbuf[(static_cast<int64_t>(pair) * 2 + dir) * p.mstride + row] = out;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kAccStages * kTileN);
+  }
+}
+
+cudaError_t launch_k1_guided(const CUtensorMap& tmap, const MatchParams& p, const GuidedParams& g, int n_pairs,
+                             int max_strips, int n_dirs, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(b2m_k1_guided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSmemBytes));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(max_strips, n_dirs, n_pairs);
+  b2m_k1_guided_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, p, g);
+  return cudaGetLastError();
+}
+
+}  // namespace b2m

@@ -217,6 +217,13 @@ __global__ void __launch_bounds__(256) b2m_crosscheck_compact_kernel(const Compa
   __shared__ int s_base;
   __shared__ unsigned long long s_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.enable && p.enable[pair] < 0) {  // guided pass: this pair keeps its verified inliers
+    if (threadIdx.x == 0) {
+      p.pair_off[pair] = 0;
+      p.pair_cnt[pair] = -1;
+    }
+    return;
+  }
 
   // pass 1: count
   int cnt = 0;

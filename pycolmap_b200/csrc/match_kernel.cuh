@@ -39,6 +39,15 @@ struct CompactParams {
   const int32_t* img_row0;      // device [n_images]
   const float2* kpts;           // device keypoints indexed by padded row, or nullptr
   double4* pts;                 // device arena (x1, y1, x2, y2), or nullptr
+  const int32_t* enable;        // optional [n_pairs]: pairs with enable[pair] < 0 produce no output (guided pass)
+};
+
+// Guided matching (K1g): per pair of the batch the geometry chosen by the verifier.
+struct GuidedParams {
+  const int32_t* kind;          // device [n_pairs]: -1 = not eligible, 0 = F (Sampson), 1 = H (forward transfer)
+  const float* model;           // device [n_pairs][9] float32 row-major (as upstream: Eigen::Matrix3f)
+  const float2* kpts;           // device keypoints indexed by padded row
+  float max_residual;           // max_error^2 in float32
 };
 
 // Rows per A strip / columns per B tile: images are padded (with zero descriptors, which can
@@ -52,6 +61,8 @@ cudaError_t launch_k1_match(const CUtensorMap& tmap, const MatchParams& p, int n
 cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const MatchParams& p,
                              const uint8_t* desc, int n_pairs, int max_strips, int n_dirs, int num_sms,
                              cudaStream_t stream, cudaEvent_t after_filter);
+cudaError_t launch_k1_guided(const CUtensorMap& tmap, const MatchParams& p, const GuidedParams& g, int n_pairs,
+                             int max_strips, int n_dirs, cudaStream_t stream);
 cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream);
 
 }  // namespace b2m

@@ -62,6 +62,10 @@ struct VerifyParams {
   int32_t single_kind;        // >= 0: only this kind runs (stand-alone estimator API), no camera model
   int32_t force_calibrated;   // stand-alone: -1 use camera flags
   unsigned long long* prof;   // optional [3][8] cycle counters (B2M_PROF=1), else nullptr
+  // guided matching hand-over (written by the decision kernel when guided_min_inliers >= 0)
+  int32_t* guided_kind;       // [nb] -1 / 0 (F) / 1 (H)
+  float* guided_model;        // [nb][9]
+  int32_t guided_min_inliers; // < 0: guided matching off
 };
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -666,6 +670,7 @@ __global__ void __launch_bounds__(256) b2m_decide_kernel(const VerifyParams P) {
     if (tid == 0) {
       P.config[pair] = s_cfg;
       P.inl_cnt[pair] = 0;
+      if (P.guided_kind) P.guided_kind[pair] = -1;
     }
     return;
   }
@@ -798,6 +803,20 @@ __global__ void __launch_bounds__(256) b2m_decide_kernel(const VerifyParams P) {
   if (tid == 0) {
     P.config[pair] = cfg;
     P.inl_cnt[pair] = num;
+    if (P.guided_kind) {
+      // MatchGuidedSiftFeatures is run when the verified geometry has >= min_num_inliers inliers
+      // (U:controllers/feature_matching_utils.cc); F for CALIBRATED / UNCALIBRATED, H for the planar /
+      // panoramic configurations (U:feature/sift.cc MatchGuidedSiftFeaturesCPU)
+      int gk = -1;
+      if (P.guided_min_inliers >= 0 && num >= P.guided_min_inliers) {
+        if (cfg == B2M_CALIBRATED || cfg == B2M_UNCALIBRATED) gk = 0;
+        else if (cfg == B2M_PLANAR || cfg == B2M_PANORAMIC || cfg == B2M_PLANAR_OR_PANORAMIC) gk = 1;
+      }
+      P.guided_kind[pair] = gk;
+      if (gk >= 0)
+        for (int k = 0; k < 9; ++k)
+          P.guided_model[pair * 9 + k] = static_cast<float>(P.models[(pair * 3 + (gk == 0 ? 1 : 2)) * 9 + k]);
+    }
   }
 }
 
@@ -814,6 +833,18 @@ struct VerifyState {
   int32_t* d_config[2] = {nullptr, nullptr};
   int32_t* d_inl_cnt[2] = {nullptr, nullptr};
   uint2* d_inliers[2] = {nullptr, nullptr};
+  // guided matching (lazily allocated): hand-over arrays + a second match arena per slot
+  int32_t* d_guided_kind = nullptr;
+  float* d_guided_model = nullptr;
+  uint2* d_garena[2] = {nullptr, nullptr};
+  unsigned long long* d_gcursor[2] = {nullptr, nullptr};
+  int64_t* d_goff[2] = {nullptr, nullptr};
+  int32_t* d_gcnt[2] = {nullptr, nullptr};
+  uint2* h_garena[2] = {nullptr, nullptr};
+  unsigned long long* h_gcursor[2] = {nullptr, nullptr};
+  int64_t* h_goff[2] = {nullptr, nullptr};
+  int32_t* h_gcnt[2] = {nullptr, nullptr};
+  bool guided_on[2] = {false, false};
   double* h_models[2] = {nullptr, nullptr};
   int32_t* h_config[2] = {nullptr, nullptr};
   int32_t* h_inl_cnt[2] = {nullptr, nullptr};
@@ -831,6 +862,15 @@ struct VerifyState {
       h_models[s] = nullptr; h_config[s] = nullptr; h_inl_cnt[s] = nullptr; h_inliers[s] = nullptr;
     }
     cudaFree(d_mask); cudaFree(d_sup); cudaFree(d_success); cudaFree(d_cams);
+    cudaFree(d_guided_kind); cudaFree(d_guided_model);
+    d_guided_kind = nullptr; d_guided_model = nullptr;
+    for (int s = 0; s < 2; ++s) {
+      cudaFree(d_garena[s]); cudaFree(d_gcursor[s]); cudaFree(d_goff[s]); cudaFree(d_gcnt[s]);
+      cudaFreeHost(h_garena[s]); cudaFreeHost(h_gcursor[s]); cudaFreeHost(h_goff[s]); cudaFreeHost(h_gcnt[s]);
+      d_garena[s] = nullptr; d_gcursor[s] = nullptr; d_goff[s] = nullptr; d_gcnt[s] = nullptr;
+      h_garena[s] = nullptr; h_gcursor[s] = nullptr; h_goff[s] = nullptr; h_gcnt[s] = nullptr;
+      guided_on[s] = false;
+    }
     d_mask = nullptr; d_sup = nullptr; d_success = nullptr; d_cams = nullptr;
     batch = 0; arena_cap = 0; n_cams = 0; cams_of = nullptr;
   }
@@ -918,6 +958,33 @@ int verify_prepare(b2m_ctx* ctx, ImageSet& S, int batch, int64_t arena_cap) {
   return B2M_OK;
 }
 
+int verify_guided_slot(b2m_ctx* ctx, int s, GuidedSlot* out) {
+  VerifyState* V = vstate(ctx);
+  if (!V->d_guided_kind) {
+    V_TRY(ctx, cudaMalloc(&V->d_guided_kind, sizeof(int32_t) * V->batch));
+    V_TRY(ctx, cudaMalloc(&V->d_guided_model, sizeof(float) * 9 * V->batch));
+    for (int k = 0; k < 2; ++k) {
+      V_TRY(ctx, cudaMalloc(&V->d_garena[k], sizeof(uint2) * V->arena_cap));
+      V_TRY(ctx, cudaMalloc(&V->d_gcursor[k], sizeof(unsigned long long)));
+      V_TRY(ctx, cudaMalloc(&V->d_goff[k], sizeof(int64_t) * V->batch));
+      V_TRY(ctx, cudaMalloc(&V->d_gcnt[k], sizeof(int32_t) * V->batch));
+      V_TRY(ctx, cudaMallocHost(&V->h_garena[k], sizeof(uint2) * V->arena_cap));
+      V_TRY(ctx, cudaMallocHost(&V->h_gcursor[k], sizeof(unsigned long long)));
+      V_TRY(ctx, cudaMallocHost(&V->h_goff[k], sizeof(int64_t) * V->batch));
+      V_TRY(ctx, cudaMallocHost(&V->h_gcnt[k], sizeof(int32_t) * V->batch));
+    }
+  }
+  out->kind = V->d_guided_kind;
+  out->model = V->d_guided_model;
+  out->arena = V->d_garena[s];
+  out->cursor = V->d_gcursor[s];
+  out->off = V->d_goff[s];
+  out->cnt = V->d_gcnt[s];
+  out->h_cursor = V->h_gcursor[s];
+  V->guided_on[s] = true;
+  return B2M_OK;
+}
+
 void verify_results_init(b2m_results* res, int64_t n_pairs) {
   res->verified = true;
   res->config.assign(n_pairs, B2M_UNDEFINED);
@@ -926,8 +993,8 @@ void verify_results_init(b2m_results* res, int64_t n_pairs) {
   res->models.assign(27 * n_pairs, 0.0);
 }
 
-int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, const b2m_sift_opts*, int s, int64_t p0,
-                        int nb) {
+int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, const b2m_sift_opts* sift, int s,
+                        int64_t p0, int nb) {
   VerifyState* V = vstate(ctx);
   Workspace& W = ctx->ws;
   VerifyParams P{};
@@ -949,6 +1016,15 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
   P.seed = ctx->seed;
   P.single_kind = -1;
   P.force_calibrated = -1;
+  V->guided_on[s] = false;
+  P.guided_min_inliers = -1;
+  if (sift && sift->guided_matching) {
+    GuidedSlot gs;
+    if (int rc = verify_guided_slot(ctx, s, &gs)) return rc;
+    P.guided_kind = gs.kind;
+    P.guided_model = gs.model;
+    P.guided_min_inliers = tvg->min_num_inliers;
+  }
   if (!V->d_prof && getenv("B2M_PROF")) {
     cudaMalloc(&V->d_prof, sizeof(unsigned long long) * 24);
     cudaMemset(V->d_prof, 0, sizeof(unsigned long long) * 24);
@@ -983,6 +1059,16 @@ int verify_batch_download(b2m_ctx* ctx, b2m_results*, int s, int64_t, int nb) {
   if (total > 0)
     V_TRY(ctx, cudaMemcpyAsync(V->h_inliers[s], V->d_inliers[s], sizeof(uint2) * total, cudaMemcpyDeviceToHost,
                                ctx->copy_stream));
+  if (V->guided_on[s]) {
+    const unsigned long long gtotal = *V->h_gcursor[s];
+    V_TRY(ctx, cudaMemcpyAsync(V->h_goff[s], V->d_goff[s], sizeof(int64_t) * nb, cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+    V_TRY(ctx, cudaMemcpyAsync(V->h_gcnt[s], V->d_gcnt[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+    if (gtotal > 0)
+      V_TRY(ctx, cudaMemcpyAsync(V->h_garena[s], V->d_garena[s], sizeof(uint2) * gtotal, cudaMemcpyDeviceToHost,
+                                 ctx->copy_stream));
+  }
   return B2M_OK;
 }
 
@@ -993,6 +1079,12 @@ int verify_batch_collect(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int 
     const int64_t p = p0 + k;
     int cfg = V->h_config[s][k];
     int ni = V->h_inl_cnt[s][k];
+    const uint2* inl_src = V->h_inliers[s] + W.h_pair_off[s][k];
+    if (V->guided_on[s] && V->h_gcnt[s][k] >= 0) {
+      // guided matching replaced TwoViewGeometry::inlier_matches (U:feature/sift.cc MatchGuidedSiftFeaturesCPU)
+      ni = V->h_gcnt[s][k];
+      inl_src = V->h_garena[s] + V->h_goff[s][k];
+    }
     // FeatureMatcherController::Match write rule (row P3): raw matches below min_num_inliers are
     // stored empty (the verifier never ran: default TwoViewGeometry); geometries with fewer than
     // min_num_inliers inliers are stored as the default TwoViewGeometry (config UNDEFINED).
@@ -1009,7 +1101,7 @@ int verify_batch_collect(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int 
     res->in_cnt[p] = ni;
     res->in_off[p] = static_cast<int64_t>(res->inliers.size() / 2);
     if (ni > 0) {
-      const uint2* src = V->h_inliers[s] + W.h_pair_off[s][k];
+      const uint2* src = inl_src;
       const size_t at = res->inliers.size();
       res->inliers.resize(at + 2 * static_cast<size_t>(ni));
       memcpy(res->inliers.data() + at, src, sizeof(uint2) * ni);

@@ -15,5 +15,16 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
 int verify_batch_download(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int nb);
 // After the copies completed: move staging -> results (applies the controller's write rule, row P3).
 int verify_batch_collect(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int nb, int min_num_inliers);
+// Guided matching buffers of slot `s` (lazily allocated); marks the slot as guided for download / collect.
+struct GuidedSlot {
+  int32_t* kind;
+  float* model;
+  uint2* arena;
+  unsigned long long* cursor;
+  int64_t* off;
+  int32_t* cnt;
+  unsigned long long* h_cursor;
+};
+int verify_guided_slot(b2m_ctx* ctx, int s, GuidedSlot* out);
 void verify_release(b2m_ctx* ctx);
 }  // namespace b2m

@@ -232,7 +232,7 @@ def match_sequential(database_path, sift_options=None, matching_options=None, ve
     sift_options = SiftMatchingOptions.coerce(sift_options)
     matching_options = SequentialMatchingOptions.coerce(matching_options)
     verification_options = TwoViewGeometryOptions.coerce(verification_options)
-    if matching_options.loop_detection:
+    if matching_options.loop_detection:  # guided matching IS supported (K1g)
         raise ValueError("[pipeline.py] loop_detection needs a vocabulary tree: out of scope (SURVEY.md row B6)")
     ctx = get_context(_resolve_device(device, sift_options))
     with Database(database_path) as db:

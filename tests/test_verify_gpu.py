@@ -135,3 +135,34 @@ def test_pipeline_match_and_verify(ctx):
             rawset = {tuple(x) for x in raw.tolist()}
             assert all(tuple(x) in rawset for x in inl.tolist())
     assert n_verified >= 10
+
+
+def test_guided_matching_replaces_inliers(ctx):
+    """K1g (row G1): with SiftMatchingOptions.guided_matching the inlier matches of a verified pair are
+    the brute-force matches under the geometric filter of its F / H -- bit-exact vs the oracle given the
+    same model (the model itself comes from the GPU verifier)."""
+    scene = syn.make_scene(10, 1024, seed=4, window_images=2.5)
+    descs = [d.numpy() for d in scene["desc"]]
+    kpts = [k.numpy() for k in scene["kpts"]]
+    ctx.set_images(descs, kpts, scene["cameras"])
+    pairs = syn.exhaustive_pairs(10)
+    plain = ctx.match_pairs(pairs, tvg=ctx.tvg_opts())
+    guided = ctx.match_pairs(pairs, sift=ctx.sift_opts(guided_matching=1), tvg=ctx.tvg_opts())
+    n_guided = 0
+    for k, (i, j) in enumerate(pairs):
+        vp, vg = plain.view(k), guided.view(k)
+        assert np.array_equal(plain.matches(k), guided.matches(k))          # raw matches are untouched
+        if vp.config in (R.CALIBRATED, R.UNCALIBRATED, R.PLANAR_OR_PANORAMIC) and vp.n_inliers >= 15:
+            assert vg.config == vp.config
+            kind = 1 if vp.config == R.PLANAR_OR_PANORAMIC else 0
+            model = np.array(vg.H if kind else vg.F).reshape(3, 3)
+            want = oracle.match_guided(descs[i], kpts[i], descs[j], kpts[j], kind, model, 4.0)
+            got = guided.inlier_matches(k)
+            if len(want) >= 15:
+                assert np.array_equal(got, want), (k, len(got), len(want))
+                n_guided += 1
+                # the geometric filter removes ambiguous second-best candidates: never fewer than ~the inliers
+                assert len(got) >= 0.9 * vp.n_inliers
+        else:
+            assert vg.n_inliers == vp.n_inliers
+    assert n_guided >= 5

@@ -1,27 +1,31 @@
-// match_filter_kernel.cu -- K1 (current): persistent, clustered tcgen05 int8 GEMM with a *filter*
-// epilogue.
+// match_filter_kernel.cu -- K1 (v9): persistent, clustered, pair-MMA tcgen05 int8 GEMM with a *filter*
+// epilogue, plus the exact resolve kernel.
 //
-// Grid = one 2-CTA cluster per SM pair, persistent: every cluster walks a static list of work items
-// (image pair, direction, 512-row block of the "row" image A); inside an item each CTA owns two
-// 128-row A strips (256 rows) and the B image streams through an 8-stage ring of 128-column tiles.
-//   * every B tile is fetched ONCE per cluster: each CTA loads its 64-row half with TMA and multicasts
-//     it to both CTAs; a tile feeds 2 strips x 2 CTAs = four 128x128x128 MMAs;
-//   * the pipelines (TMA ring, TMEM accumulator stages, mbarrier phases) run straight across item
-//     boundaries: the A strips are double-buffered, so the prologue of item i+1 overlaps the tail of
-//     item i and TMEM / barriers are set up once per launch (profiles/r01_*: with one CTA per item
-//     ~45 % of the time went to CTA launch + pipeline fill/drain);
-//   * accumulators: TMEM, 2 stages x 2 strips x 128 columns = 512 columns.
+// Grid = one 2-CTA cluster per SM pair (74 clusters), persistent: every cluster walks a static list of
+// work items (image pair, direction, 256-row block of the "row" image A).
+//   * The two CTAs form a cta_group::2 pair: ONE elected thread of the leader CTA issues
+//     tcgen05.mma.cta_group::2.kind::i8 256x256x32 (four k-steps per 256-column tile of image B).  Each SM
+//     contributes its own 128-row A strip and stages only ITS 128-column half of every B tile, so each
+//     operand byte is written to and read from shared memory once per pair of SMs.
+//   * B streams through an 8-stage ring of 16 KiB half tiles (TMA, SWIZZLE_128B, both halves accounted on
+//     the leader's mbarrier); the A strips are double-buffered across work items, so the pipelines
+//     (TMA ring, TMEM accumulator stages, mbarrier phases) run straight across item boundaries and
+//     TMEM / barriers are set up once per launch.
+//   * Accumulators: TMEM, 2 stages x 256 columns = all 512 columns of each SM; every SM drains its own
+//     128 lanes.  Stage hand-back to the leader = cluster-scope mbarrier arrivals (one per epilogue warp).
+//   * The TMA and MMA warps stay warp-converged and predicate only the tcgen05 / TMA instructions with
+//     elect.sync, so descriptors and addresses live in uniform registers.
 //
-// Epilogue (8 warps: warp w -> TMEM lane quarter w%4 of strip w/4; thread <-> row): instead of an
-// exact running top-2 (4 ALU ops per accumulator) each thread keeps 64 "slot maxima"
-//     B[cp][r] = max over columns j with ((j mod 128) div 64, j mod 32) == (cp, r)   of dot(i, j)
-// updated with one 3-input max (VIMNMX3) per two accumulators = 0.5 ALU op per accumulator.  At the
-// end of the row
+// Epilogue (8 warps: warp w -> TMEM lane quarter w%4, column half w/4 of every tile; thread <-> row):
+// instead of an exact running top-2 (4 ALU ops per accumulator) each row keeps 128 "slot maxima"
+//     slot(h, cp, r) = max over columns j = 256 t + 128 h + 64 cp + 32 c + r  (c in {0,1}, all tiles t)
+// updated with one 3-input max (VIMNMX3) per two accumulators = 0.5 ALU op per accumulator.  At the end
+// of the row
 //     best = max over slots (exact);   S1 = second largest slot maximum (multiset), which is a LOWER
 //     bound of the true second-best (= max(S1, second largest element inside the winning slot)).
 // acos is monotone, so a row failing `acos(best) <= max_distance`, or failing the ratio test already
 // against S1, is rejected exactly.  The survivors ("candidates": essentially the true matches) are
-// resolved exactly by b2m_k1_resolve_kernel: it recomputes the n2/64 dot products of the winning slot
+// resolved exactly by b2m_k1_resolve_kernel: it recomputes the n2/128 dot products of the winning slot
 // with dp4a (all columns if several slots share the maximum), finds the lowest-index arg-max and the
 // hidden second-best, and applies the float32 test of FindBestMatchesOneWayBruteForce.  The match
 // indices are bit-identical to the exact kernel (match_kernel.cu) and to the CPU oracle.

@@ -305,13 +305,16 @@ def main():
     # ---- e2e: same call with HOST buffers; H2D of the descriptor set and D2H of the results inside
     e2e = None
     if not args.no_e2e:
-        h_desc = torch.empty(desc_full.shape, dtype=torch.uint8, pin_memory=True)
+        # pinned staging (as the contract asks) unless the set is so large that pinning it on every rank
+        # of the box would lock > 64 GB of host memory (8 ranks x 23 GB at N = 8): then pageable
+        pin = desc_full.numel() <= 8 * 2**30
+        h_desc = torch.empty(desc_full.shape, dtype=torch.uint8, pin_memory=pin)
         h_desc.copy_(desc_full)
         h_np = h_desc.numpy().reshape(n_img, K, 128)
         descs = [h_np[i] for i in range(n_img)]
         kp = None
         if verify:
-            h_k = torch.empty(kpts_full.shape, dtype=torch.float32, pin_memory=True)
+            h_k = torch.empty(kpts_full.shape, dtype=torch.float32, pin_memory=pin)
             h_k.copy_(kpts_full)
             kp = [h_k.numpy().reshape(n_img, K, 2)[i] for i in range(n_img)]
 

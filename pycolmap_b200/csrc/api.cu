@@ -271,7 +271,6 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     mp.cand_cnt = W.d_cand_cnt;
     mp.cand_rows = W.d_cand_rows;
     mp.cand_sorted = W.d_cand_sorted;
-    mp.prof = ctx->d_k1_prof;
     CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
     if (ctx->exact_k1) {
       CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
@@ -463,10 +462,6 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
   if (!ctx) return fail(nullptr, B2M_ENOMEM, "out of host memory");
   ctx->device = dev;
   ctx->num_sms = prop.multiProcessorCount;
-  if (getenv("B2M_PROF")) {
-    cudaMalloc(&ctx->d_k1_prof, sizeof(unsigned long long) * 16);
-    cudaMemset(ctx->d_k1_prof, 0, sizeof(unsigned long long) * 16);
-  }
   ctx->seed = cfg ? cfg->seed : 0;
   if (cfg && cfg->pair_batch > 0) ctx->pair_batch = std::min(cfg->pair_batch, 65535);
   ctx->stats.struct_size = sizeof(b2m_stats);
@@ -517,16 +512,6 @@ void b2m_destroy(b2m_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  if (ctx->d_k1_prof) {
-    unsigned long long h[16];
-    cudaMemcpy(h, ctx->d_k1_prof, sizeof(h), cudaMemcpyDeviceToHost);
-    const char* names[13] = {"producer wait empty_b", "producer total", "mma wait tmem_empty", "mma wait full_b", "-",
-                             "mma total", "epi(warp0) wait tmem_full", "-", "epi(warp0) total", "epi ld pair 1",
-                             "epi max3 #1", "epi ld pair 2", "epi fence+arrive"};
-    for (int k = 0; k < 13; ++k)
-      if (names[k][0] != '-') fprintf(stderr, "[b2m prof] K1 %-28s %12.3f Mcycles\n", names[k], h[k] / 1e6);
-    cudaFree(ctx->d_k1_prof);
-  }
   ctx->images.release();
   ctx->ws.release();
   verify_release(ctx);

@@ -54,7 +54,6 @@ struct Workspace {
 struct b2m_ctx {
   int device = 0;
   int num_sms = 148;
-  unsigned long long* d_k1_prof = nullptr;  // B2M_PROF=1 cycle counters of the K1 pipeline roles
   uint64_t seed = 0;
   int pair_batch = 1024;
   cudaStream_t stream = nullptr;

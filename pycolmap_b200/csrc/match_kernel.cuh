@@ -22,7 +22,6 @@ struct MatchParams {
   int32_t* cand_sorted;      // device [n_pairs][2][mstride] candidate rows bucketed by winning slot
   // persistent K1: filled in by launch_k1_filter
   int32_t n_items, blocks_per_image, n_dirs;
-  unsigned long long* prof;  // optional cycle counters (B2M_PROF=1), else nullptr
 };
 
 struct CompactParams {

@@ -97,11 +97,6 @@ int layout_images(b2m_ctx* ctx, ImageSet& S, int n_images, const int32_t* n_feat
   CUresult r = enc(&S.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, S.d_desc, gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  cuuint32_t box_half[2] = {128, 64};
-  if (r == CUDA_SUCCESS)
-    r = enc(&S.tmap_half, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, S.d_desc, gdim, gstride, box_half, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char b[128];
     snprintf(b, sizeof(b), "[api.cu] cuTensorMapEncodeTiled failed: CUresult %d", static_cast<int>(r));
@@ -275,7 +270,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     if (ctx->exact_k1) {
       CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
     } else {
-      CU_TRY_R(launch_k1_filter(S.tmap, S.tmap_half, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st,
+      CU_TRY_R(launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st,
                                 ctx->ev_k1b[s]));
       ctx->stats.kernel_launches += 1;
     }

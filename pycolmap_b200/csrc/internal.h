@@ -25,8 +25,7 @@ struct ImageSet {
   int32_t* d_row0 = nullptr;
   int32_t* d_nfeat = nullptr;
   std::vector<b2m_camera> cams;
-  CUtensorMap tmap;       // box 128 bytes x 128 rows
-  CUtensorMap tmap_half;  // box 128 bytes x 64 rows (cluster-multicast halves of a B tile)
+  CUtensorMap tmap{};       // box 128 bytes x 128 rows
   void release();
 };
 

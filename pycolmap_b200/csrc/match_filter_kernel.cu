@@ -1,4 +1,4 @@
-// match_filter_kernel.cu -- K1 (v9): persistent, clustered, pair-MMA tcgen05 int8 GEMM with a *filter*
+// match_filter_kernel.cu -- K1 (v14): persistent, clustered, pair-MMA tcgen05 int8 GEMM with a *filter*
 // epilogue, plus the exact resolve kernel.
 //
 // Grid = one 2-CTA cluster per SM pair (74 clusters), persistent: every cluster walks a static list of
@@ -12,25 +12,39 @@
 //     (TMA ring, TMEM accumulator stages, mbarrier phases) run straight across item boundaries and
 //     TMEM / barriers are set up once per launch.
 //   * Accumulators: TMEM, 2 stages x 256 columns = all 512 columns of each SM; every SM drains its own
-//     128 lanes.  Stage hand-back to the leader = cluster-scope mbarrier arrivals (one per epilogue warp).
+//     128 lanes.  Stage hand-back to the leader = one cluster-scope mbarrier arrival per epilogue warp
+//     (aggregating them on a shared-memory counter first was measured slower).
 //   * The TMA and MMA warps stay warp-converged and predicate only the tcgen05 / TMA instructions with
 //     elect.sync, so descriptors and addresses live in uniform registers.
 //
-// Epilogue (8 warps: warp w -> TMEM lane quarter w%4, column half w/4 of every tile; thread <-> row):
-// instead of an exact running top-2 (4 ALU ops per accumulator) each row keeps 128 "slot maxima"
-//     slot(h, cp, r) = max over columns j = 256 t + 128 h + 64 cp + 32 c + r  (c in {0,1}, all tiles t)
-// updated with one 3-input max (VIMNMX3) per two accumulators = 0.5 ALU op per accumulator.  At the end
+// Warp roles (19 warps, <= 96 registers per thread):
+//   warps 0..15  epilogue: warp w drains TMEM lane quarter w%4, column group w/4 (64 columns) of every tile
+//                with ONE round trip (four tcgen05.ld.x16 in flight, one wait::ld), hands the stage back, then
+//                folds the 64 accumulators of its row into 16 slot maxima.  What bounds K1 is the hand-shake
+//                chain MMA -> commit -> drain -> arrive -> MMA over only two accumulator stages, so the drain
+//                is kept to a single TMEM round trip and nothing else sits between wait::ld and the arrival.
+//   warp 16      TMA producer;  warp 17  MMA issuer (leader CTA only);
+//   warp 18      selector: turns the slot maxima of a finished item into reject / candidate decisions one item
+//                behind the epilogue warps, so the dependent global latencies (acos table, candidate counter)
+//                are off the chain.
+//
+// Filter: instead of an exact running top-2 (4 ALU ops per accumulator) each row keeps 64 "slot maxima"
+//     slot(g, r) = max over columns j = 256 t + 64 g + 16 c + r   (g = 0..3, r = 0..15; c = 0..3, all tiles t)
+// updated with two 3-input max (VIMNMX3) per four accumulators = 0.5 ALU op per accumulator.  At the end
 // of the row
 //     best = max over slots (exact);   S1 = second largest slot maximum (multiset), which is a LOWER
 //     bound of the true second-best (= max(S1, second largest element inside the winning slot)).
 // acos is monotone, so a row failing `acos(best) <= max_distance`, or failing the ratio test already
 // against S1, is rejected exactly.  The survivors ("candidates": essentially the true matches) are
-// resolved exactly by b2m_k1_resolve_kernel: it recomputes the n2/128 dot products of the winning slot
+// resolved exactly by b2m_k1_resolve_kernel: it recomputes the n2/64 dot products of the winning slot
 // with dp4a (all columns if several slots share the maximum), finds the lowest-index arg-max and the
 // hidden second-best, and applies the float32 test of FindBestMatchesOneWayBruteForce.  The match
 // indices are bit-identical to the exact kernel (match_kernel.cu) and to the CPU oracle.
 //
+// -DB2M_K1_PROF adds clock64 role counters (printed every 8th launch); see DESIGN.md for the readings.
+//
 // Semantics: U:feature/sift.cc (COLMAP 3.9.1), SURVEY.md section 8 rows M1-M3.
+#include <cstdio>
 #include "match_kernel.cuh"
 #include "ptx.cuh"
 
@@ -39,12 +53,10 @@ namespace b2m {
 namespace {
 
 constexpr int kDim = 128;
-constexpr int kTileM = 128;                        // rows per MMA (TMEM lanes)
-constexpr int kStrips = 1;                         // A strips per CTA
-constexpr int kRowsPerCta = kTileM * kStrips;      // 128
-constexpr int kCluster = 2;                        // CTAs per cluster sharing every B tile by TMA multicast
-constexpr int kRowsPerItem = kRowsPerCta * kCluster;  // 256 rows of A per work item == kRowPad
-constexpr int kTileN = 256;                        // columns per B tile: a 128x256x32 MMA hides the smem A read
+constexpr int kTileM = 128;                        // rows per CTA and MMA (TMEM lanes)
+constexpr int kCluster = 2;                        // CTAs per cluster = one cta_group::2 pair
+constexpr int kRowsPerItem = kTileM * kCluster;    // 256 rows of A per work item == kRowPad
+constexpr int kTileN = 256;                        // columns per B tile: N = 256 hides the smem A read
                                                    // (N <= 128 costs ~92 cycles per MMA regardless of N, profiles/r01_microbench2)
 constexpr int kUmmaK = 32;
 constexpr int kStages = 8;                         // B-tile ring depth (8 x 16 KiB: each CTA stages only ITS half)
@@ -52,12 +64,18 @@ constexpr int kAccStages = 2;
 constexpr int kABufs = 2;                          // A strips double-buffered across work items
 constexpr int kBytesA = kTileM * kDim;             // 16 KiB per strip
 constexpr int kBytesB = (kTileN / kCluster) * kDim;  // 16 KiB: this CTA's half (128 columns) of a B tile
-constexpr int kEpiWarps = 8;                       // warp w: TMEM lane quarter w%4, column half w/4 of every tile
-constexpr int kThreads = (kEpiWarps + 2) * 32;     // + TMA warp + MMA warp
-constexpr int kAccCols = kStrips * kTileN;         // TMEM columns per accumulator stage
+constexpr int kEpiWarps = 16;                      // warp w: TMEM lane quarter w%4, column group w/4 of every tile
+constexpr int kColGroups = kEpiWarps / 4;          // 4
+constexpr int kGroupCols = kTileN / kColGroups;    // 64 columns per warp and tile = four x16 loads
+constexpr int kOwnSlots = 16;                      // slot maxima per row kept in one thread's registers
+constexpr int kSlots = kOwnSlots * kColGroups;     // 64 slot maxima per row
+constexpr int kSlotCols = kTileN / kSlots;         // 4 columns of every tile share a slot
+constexpr int kThreads = (kEpiWarps + 3) * 32;     // + TMA warp + MMA warp + selector warp
+constexpr int kAccCols = kTileN;                   // TMEM columns per accumulator stage
 constexpr uint32_t kIdesc = make_idesc_u8u8_s32(kTileM * kCluster, kTileN);  // one 256 x 256 x 32 MMA per CTA pair
 constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << kCluster) - 1u);
 static_assert(kRowsPerItem == kRowPad && kTileN == kRowPad, "images are padded to whole items / column tiles");
+static_assert(kGroupCols == 64 && kSlotCols == 4, "epilogue folds four x16 chunks into 16 slots");
 
 struct __align__(8) Barriers {
   uint64_t full_a[kABufs];
@@ -66,11 +84,12 @@ struct __align__(8) Barriers {
   uint64_t empty_b[kStages];
   uint64_t tmem_full[kAccStages];
   uint64_t tmem_empty[kAccStages];
+  uint64_t sel_full, sel_empty;  // slot maxima of an item handed to / consumed by the selector warp
   uint32_t tmem_base;
 };
 
-constexpr int kMergeBytes = kTileM * 64 * 4;       // slot maxima of the upper column half, [64 slots][128 rows]
-constexpr size_t kSmemBytes = 1024 + kABufs * kStrips * kBytesA + kStages * kBytesB + kMergeBytes + sizeof(Barriers);
+constexpr int kMergeBytes = kTileM * kSlots * 4;   // slot maxima of one item, [slot][128 rows]
+constexpr size_t kSmemBytes = 1024 + kABufs * kBytesA + kStages * kBytesB + kMergeBytes + sizeof(Barriers);
 
 // A work item and the data every warp role derives from its index (pure function of `w`).
 struct Item {
@@ -90,7 +109,7 @@ __device__ __forceinline__ Item decode_item(const MatchParams& p, int w, uint32_
   // same answer in both CTAs of the cluster; an empty image B still yields an item (n_tiles == 0)
   // so that its rows are written as "no match"
   it.valid = cb * kRowsPerItem < it.nA;
-  it.row0 = cb * kRowsPerItem + static_cast<int>(cta_rank) * kRowsPerCta;
+  it.row0 = cb * kRowsPerItem + static_cast<int>(cta_rank) * kTileM;
   it.rowA = p.img_row0[ia] + it.row0;
   it.rowB = p.img_row0[ib];
   it.n_tiles = (it.nB + kTileN - 1) / kTileN;
@@ -98,6 +117,18 @@ __device__ __forceinline__ Item decode_item(const MatchParams& p, int w, uint32_
 }
 
 }  // namespace
+
+#ifdef B2M_K1_PROF
+// role counters (SM cycles, summed over CTAs / warps): [0] MMA wait tmem_empty, [1] MMA wait full_b, [2] MMA issue,
+// [3] MMA tiles, [4] epi wait tmem_full, [5] epi drain (first ld .. wait::ld), [6] epi hand-back + fold,
+// [7] epi warp-tiles, [8] epi item tail (slot maxima -> shared memory), [9] epi items
+__device__ unsigned long long g_k1_prof[16];
+#define PROF_T(x) const long long x = clock64()
+#define PROF_ADD(acc, a, b) acc += (b) - (a)
+#else
+#define PROF_T(x)
+#define PROF_ADD(acc, a, b)
+#endif
 
 // elect.sync: true in exactly one (converged) lane.  The MMA / TMA roles keep their whole warp converged
 // and predicate only the tcgen05 / TMA instructions, so descriptors and addresses stay warp-uniform
@@ -113,12 +144,11 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
-b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
-                     const MatchParams p) {
+b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;                                     // [kABufs][16 KiB]
-  uint8_t* smB = smem + kABufs * kStrips * kBytesA;        // [kStages][16 KiB]
+  uint8_t* smB = smem + kABufs * kBytesA;                  // [kStages][16 KiB]
   uint32_t* merge = reinterpret_cast<uint32_t*>(smB + kStages * kBytesB);
   Barriers* bars = reinterpret_cast<Barriers*>(smB + kStages * kBytesB + kMergeBytes);
 
@@ -142,6 +172,8 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       mbar_init(&bars->tmem_full[s], 1);
       mbar_init(&bars->tmem_empty[s], kCluster * kEpiWarps);  // leader only: one arrival per epilogue warp of the pair
     }
+    mbar_init(&bars->sel_full, kEpiWarps);
+    mbar_init(&bars->sel_empty, 1);
     fence_mbar_init();
   }
   if (warp == kEpiWarps + 1) {
@@ -190,6 +222,9 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     if (cta_rank == 0) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, n_done = 0;
       const uint32_t smA_u32 = smem_u32(smA), smB_u32 = smem_u32(smB);
+#ifdef B2M_K1_PROF
+      long long pm_empty = 0, pm_fullb = 0, pm_issue = 0, pm_tiles = 0;
+#endif
       for (int w = cluster_id; w < p.n_items; w += n_clusters) {
         const Item it = decode_item(p, w, cta_rank);
         if (!it.valid) continue;
@@ -205,8 +240,13 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           __syncwarp();
         }
         for (int t = 0; t < it.n_tiles; ++t) {
-          mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+          // B is normally resident long before the accumulator stage comes back: test it first so that
+          // nothing but the descriptor set-up sits between the stage hand-back and the first MMA
+          PROF_T(t1);
           mbar_wait(&bars->full_b[stage], phase);
+          PROF_T(t2);
+          mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+          PROF_T(t0);
           tc_fence_after();
           const uint64_t bdesc = make_smem_desc_sw128(smB_u32 + stage * kBytesB);
           const uint32_t tmem_d = tmem_base + as * kAccCols;
@@ -214,11 +254,20 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 #pragma unroll
             for (int k = 0; k < kDim / kUmmaK; ++k)
               mma_i8_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0 ? 1u : 0u);
+            mma_commit_pair(&bars->tmem_full[as], kClusterMask);   // both CTAs' epilogues may drain (critical chain first)
             mma_commit_pair(&bars->empty_b[stage], kClusterMask);  // both CTAs' producers may refill
-            mma_commit_pair(&bars->tmem_full[as], kClusterMask);   // both CTAs' epilogues may drain
             if (t == it.n_tiles - 1) mma_commit_pair(&bars->empty_a[ab], kClusterMask);  // A buffers reusable
           }
           __syncwarp();
+#ifdef B2M_K1_PROF
+          {
+            PROF_T(t3);
+            PROF_ADD(pm_fullb, t1, t2);
+            PROF_ADD(pm_empty, t2, t0);
+            PROF_ADD(pm_issue, t0, t3);
+            ++pm_tiles;
+          }
+#endif
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -229,90 +278,149 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           }
         }
       }
+#ifdef B2M_K1_PROF
+      if (lane == 0) {
+        atomicAdd(&g_k1_prof[0], (unsigned long long)pm_empty);
+        atomicAdd(&g_k1_prof[1], (unsigned long long)pm_fullb);
+        atomicAdd(&g_k1_prof[2], (unsigned long long)pm_issue);
+        atomicAdd(&g_k1_prof[3], (unsigned long long)pm_tiles);
+      }
+#endif
+    }
+  } else if (warp == kEpiWarps + 2) {
+    // ===== selector: slot maxima of one item (shared memory, [slot][row]) -> reject / candidate decisions =====
+    // Runs one item behind the epilogue warps, so the dependent global-memory latencies of the decision
+    // (acos table, candidate counter) are off the accumulator hand-shake chain.  Lane l owns rows l, l+32, ...
+    uint32_t sphase = 0;
+    for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+      const Item it = decode_item(p, w, cta_rank);
+      if (!it.valid) continue;
+      mbar_wait(&bars->sel_full, sphase);
+      uint32_t best[4], s1[4];
+      int sstar[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        best[q] = 0u;
+        s1[q] = 0u;
+        sstar[q] = 0;
+      }
+      // (largest, second largest) over the slot maxima, multiset semantics; lowest slot id on ties
+#pragma unroll 8
+      for (int r = 0; r < kSlots; ++r) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t v = merge[r * kTileM + q * 32 + lane];
+          if (v > best[q]) {
+            s1[q] = best[q];
+            best[q] = v;
+            sstar[q] = r;
+          } else {
+            s1[q] = max(s1[q], v);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->sel_empty);  // the epilogue warps may overwrite the buffer
+      sphase ^= 1;
+      float fa[4], fb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        fa[q] = __ldg(p.acos_lut + min(best[q], 262144u));
+        fb[q] = __ldg(p.acos_lut + min(s1[q], 262144u));
+      }
+      const int64_t base = (static_cast<int64_t>(it.pair) * 2 + it.dir) * p.mstride;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int32_t out = -1;
+        if (best[q] > 0u && !(fa[q] > p.max_distance) && !(fa[q] >= __fmul_rn(p.max_ratio, fb[q])))
+          out = -2 - sstar[q];  // candidate: resolve exactly
+        const int row = it.row0 + q * 32 + lane;
+        p.mbuf[base + row] = out;
+        if (out != -1 && row < it.nA) {
+          p.aux[base + row] = make_uint2(best[q], s1[q]);
+          const int k = atomicAdd(p.cand_cnt + it.pair * 2 + it.dir, 1);
+          p.cand_rows[base + k] = row;
+        }
+      }
     }
   } else {
     // ===== filter epilogue =====
     const int quarter = warp & 3;
-    const int half = warp >> 2;
+    const int group = warp >> 2;
     const int row_in_cta = quarter * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t as = 0, aphase = 0;
+    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + group * kGroupCols;
+    uint32_t as = 0, aphase = 0, sel_phase = 0;
+#ifdef B2M_K1_PROF
+    long long pe_full = 0, pe_drain = 0, pe_rest = 0, pe_tiles = 0, pe_tail = 0, pe_items = 0;
+#endif
     for (int w = cluster_id; w < p.n_items; w += n_clusters) {
       const Item it = decode_item(p, w, cta_rank);
       if (!it.valid) continue;
-      uint32_t B0[32], B1[32];
+      const int n_tiles = it.n_tiles;
+      uint32_t B[kOwnSlots];  // slot r: columns 64 g + 16 c + r, c = 0..3, of every tile
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        B0[r] = 0u;
-        B1[r] = 0u;
-      }
-      for (int t = 0; t < it.n_tiles; ++t) {
+      for (int r = 0; r < kOwnSlots; ++r) B[r] = 0u;
+#pragma unroll 1
+      for (int t = 0; t < n_tiles; ++t) {
+        PROF_T(e0);
         mbar_wait(&bars->tmem_full[as], aphase);
+        PROF_T(e1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_base + as * kAccCols + half * 128;
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(taddr, va);
-        tmem_ld_32x32(taddr + 32, vb);
-        tmem_wait_ld();
+        const uint32_t taddr = tcol + as * kAccCols;
+        uint32_t v[4][16];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) B0[r] = max(B0[r], max(va[r], vb[r]));
-        tmem_ld_32x32(taddr + 64, va);
-        tmem_ld_32x32(taddr + 96, vb);
+        for (int c = 0; c < 4; ++c) tmem_ld_32x16(taddr + c * 16, v[c]);
         tmem_wait_ld();
+        PROF_T(e2);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[as], 0);  // registers hold the tile: stage is free
 #pragma unroll
-        for (int r = 0; r < 32; ++r) B1[r] = max(B1[r], max(va[r], vb[r]));
+        for (int r = 0; r < kOwnSlots; ++r) {
+          const uint32_t m = max(B[r], max(v[0][r], v[1][r]));
+          B[r] = max(m, max(v[2][r], v[3][r]));
+        }
+#ifdef B2M_K1_PROF
+        {
+          PROF_T(e3);
+          PROF_ADD(pe_full, e0, e1);
+          PROF_ADD(pe_drain, e1, e2);
+          PROF_ADD(pe_rest, e2, e3);
+          ++pe_tiles;
+        }
+#endif
         if (++as == kAccStages) {
           as = 0;
           aphase ^= 1;
         }
       }
-      // 128 slots per row: slot = half * 64 + cp * 32 + r.  The upper column half hands its 64 maxima
-      // to the lower-half thread of the same row through shared memory.
-      if (half == 1) {
+      // slot = 16 * group + r; all slot maxima of the item go to the selector warp through shared memory
+      // ([slot][row]: conflict-free for both sides); the buffer was consumed a whole item ago
+      PROF_T(x0);
+      mbar_wait(&bars->sel_empty, sel_phase ^ 1);
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          merge[r * kTileM + row_in_cta] = B0[r];
-          merge[(32 + r) * kTileM + row_in_cta] = B1[r];
-        }
+      for (int r = 0; r < kOwnSlots; ++r) merge[(group * kOwnSlots + r) * kTileM + row_in_cta] = B[r];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->sel_full);
+      sel_phase ^= 1;
+#ifdef B2M_K1_PROF
+      {
+        PROF_T(x1);
+        PROF_ADD(pe_tail, x0, x1);
+        ++pe_items;
       }
-      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
-      if (half == 0) {
-        // (largest, second largest) over the slot maxima, multiset semantics; lowest slot id on ties
-        uint32_t best = 0, s1 = 0;
-        int sstar = 0;
-#pragma unroll
-        for (int r = 0; r < 128; ++r) {
-          const uint32_t v = r < 32 ? B0[r & 31] : (r < 64 ? B1[r & 31] : merge[(r - 64) * kTileM + row_in_cta]);
-          if (v > best) {
-            s1 = best;
-            best = v;
-            sstar = r;
-          } else {
-            s1 = max(s1, v);
-          }
-        }
-        int32_t out = -1;
-        if (best > 0u) {
-          const float a = __ldg(p.acos_lut + min(best, 262144u));
-          if (!(a > p.max_distance)) {
-            const float b = __ldg(p.acos_lut + min(s1, 262144u));
-            if (!(a >= __fmul_rn(p.max_ratio, b))) out = -2 - sstar;  // candidate: resolve exactly
-          }
-        }
-        const int64_t base = (static_cast<int64_t>(it.pair) * 2 + it.dir) * p.mstride;
-        const int row = it.row0 + row_in_cta;
-        p.mbuf[base + row] = out;
-        if (out != -1 && row < it.nA) {
-          p.aux[base + row] = make_uint2(best, s1);
-          const int k = atomicAdd(p.cand_cnt + it.pair * 2 + it.dir, 1);
-          p.cand_rows[base + k] = row;
-        }
-      }
-      asm volatile("bar.sync 2, %0;" ::"r"(kEpiWarps * 32) : "memory");  // merge buffer free for the next item
+#endif
     }
+#ifdef B2M_K1_PROF
+    if (lane == 0) {
+      atomicAdd(&g_k1_prof[4], (unsigned long long)pe_full);
+      atomicAdd(&g_k1_prof[5], (unsigned long long)pe_drain);
+      atomicAdd(&g_k1_prof[6], (unsigned long long)pe_rest);
+      atomicAdd(&g_k1_prof[7], (unsigned long long)pe_tiles);
+      atomicAdd(&g_k1_prof[8], (unsigned long long)pe_tail);
+      atomicAdd(&g_k1_prof[9], (unsigned long long)pe_items);
+    }
+#endif
   }
 
   tc_fence_before();
@@ -325,16 +433,21 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 }
 
 // Exact resolution of the candidate rows of one (pair, direction).
-// Slot s = h * 64 + cp * 32 + r holds the columns j = 256 t + 128 h + 64 cp + 32 c + r, c in {0, 1}, t = 0, 1, ...
+// Slot s = 16 g + r holds the columns j = 256 t + 64 g + 16 c + r, c = 0..3, t = 0, 1, ... (slot_col below).
 // Candidates are bucketed by winning slot (counting sort in shared memory) so that the n2/64 columns
 // of a slot are staged in shared memory ONCE and reused by every candidate of the bucket (a warp per
 // candidate, dp4a, oracle scan order per lane, multiset-aware merge across lanes).  Rows whose
-// maximum is shared by several slots, and images with more than 8192 features, take the generic
+// maximum is shared by several slots, and images with more than 16384 features, take the generic
 // path that scans global memory.
 namespace {
 
-constexpr int kSlotColsMax = 128;      // columns of one slot staged in shared memory (n2 <= 8192)
+constexpr int kSlotColsMax = 256;      // columns of one slot staged in shared memory (images up to 16384 features)
 constexpr int kSlotRowStride = 144;    // bytes; 128-byte descriptors padded so that LDS.128 is conflict-free
+
+// `it`-th column (ascending) of a slot: kSlotCols columns in every 256-column tile
+__device__ __forceinline__ int slot_col(int slot, int it) {
+  return 256 * (it >> 2) + 64 * (slot >> 4) + 16 * (it & 3) + (slot & 15);
+}
 
 __device__ __forceinline__ uint32_t dot128(const uint32_t (&a)[32], const uint4* bp) {
   uint32_t d = 0;
@@ -403,50 +516,49 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
   const uint8_t* Bm = desc + static_cast<int64_t>(p.img_row0[ib]) * kDim;
   const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = nB_pad / 128;
+  const int n_items = nB_pad / kSlots;
   const bool staged = n_items <= kSlotColsMax;
 
-  __shared__ int s_start[130];
-  __shared__ int s_fill[129];
+  __shared__ int s_start[kSlots + 2];
+  __shared__ int s_fill[kSlots + 1];
   __shared__ __align__(16) uint8_t s_cols[kSlotColsMax * kSlotRowStride];
 
-  // ---- counting sort of the candidates by bucket (slot 0..127, 128 = generic path)
-  for (int b = threadIdx.x; b < 129; b += 256) s_fill[b] = 0;
+  // ---- counting sort of the candidates by bucket (slot 0..kSlots-1, kSlots = generic path)
+  for (int b = threadIdx.x; b < kSlots + 1; b += 256) s_fill[b] = 0;
   __syncthreads();
   for (int c = threadIdx.x; c < n_cand; c += 256) {
     const int row = p.cand_rows[base + c];
     const uint2 ax = p.aux[base + row];
-    const int bucket = (ax.x == ax.y || !staged) ? 128 : (-2 - p.mbuf[base + row]);
+    const int bucket = (ax.x == ax.y || !staged) ? kSlots : (-2 - p.mbuf[base + row]);
     atomicAdd(&s_fill[bucket], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int b = 0; b < 129; ++b) {
+    for (int b = 0; b < kSlots + 1; ++b) {
       s_start[b] = acc;
       acc += s_fill[b];
       s_fill[b] = 0;
     }
-    s_start[129] = acc;
+    s_start[kSlots + 1] = acc;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < n_cand; c += 256) {
     const int row = p.cand_rows[base + c];
     const uint2 ax = p.aux[base + row];
-    const int bucket = (ax.x == ax.y || !staged) ? 128 : (-2 - p.mbuf[base + row]);
+    const int bucket = (ax.x == ax.y || !staged) ? kSlots : (-2 - p.mbuf[base + row]);
     p.cand_sorted[base + s_start[bucket] + atomicAdd(&s_fill[bucket], 1)] = row;
   }
   __syncthreads();
 
   // ---- staged buckets
-  for (int b = 0; b < 128; ++b) {
+  for (int b = 0; b < kSlots; ++b) {
     const int c0 = s_start[b], c1 = s_start[b + 1];
     if (c0 == c1) continue;  // uniform
-    const int g = b >> 5, r = b & 31;  // g = 2 * h + cp: column offset 64 * g inside a 256-column tile
     __syncthreads();  // previous bucket's readers are done with s_cols
     for (int q = threadIdx.x; q < n_items * 8; q += 256) {
       const int it = q >> 3, part = q & 7;
-      const int j = 256 * (it >> 1) + 64 * g + 32 * (it & 1) + r;
+      const int j = slot_col(b, it);
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim) + part);
       *reinterpret_cast<uint4*>(s_cols + it * kSlotRowStride + part * 16) = v;
     }
@@ -464,7 +576,7 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
       uint32_t bd = 0, sd = 0;
       int bj = -1;
       for (int it = lane; it < n_items; it += 32) {
-        const int j = 256 * (it >> 1) + 64 * g + 32 * (it & 1) + r;
+        const int j = slot_col(b, it);
         const uint32_t d = dot128(a, reinterpret_cast<const uint4*>(s_cols + it * kSlotRowStride));
         scan_update(d, j, bd, sd, bj);
       }
@@ -473,12 +585,11 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
   }
 
   // ---- generic bucket: scan global memory (whole row if the maximum is shared by several slots)
-  for (int c = s_start[128] + warp; c < s_start[129]; c += 8) {
+  for (int c = s_start[kSlots] + warp; c < s_start[kSlots + 1]; c += 8) {
     const int row = p.cand_sorted[base + c];
     const uint2 ax = p.aux[base + row];
     const bool multi = (ax.x == ax.y);
     const int slot = -2 - p.mbuf[base + row];
-    const int g = slot >> 5, r = slot & 31;
     uint32_t a[32];
     const uint4* ap = reinterpret_cast<const uint4*>(A + static_cast<int64_t>(row) * kDim);
 #pragma unroll
@@ -490,7 +601,7 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
     int bj = -1;
     const int n_scan = multi ? nB_pad : n_items;
     for (int it = lane; it < n_scan; it += 32) {
-      const int j = multi ? it : (256 * (it >> 1) + 64 * g + 32 * (it & 1) + r);
+      const int j = multi ? it : slot_col(slot, it);
       const uint32_t d = dot128(a, reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim));
       scan_update(d, j, bd, sd, bj);
     }
@@ -498,7 +609,7 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
   }
 }
 
-cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const MatchParams& p_in,
+cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p_in,
                              const uint8_t* desc, int n_pairs, int max_strips, int n_dirs, int num_sms,
                              cudaStream_t stream, cudaEvent_t after_filter) {
   static bool attr_set = false;
@@ -517,10 +628,25 @@ cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_ha
   p.n_items = n_pairs * n_dirs * p.blocks_per_image;
   const int clusters = p.n_items < num_sms / kCluster ? p.n_items : num_sms / kCluster;
   if (clusters > 0) {
-    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap_half, p);
+    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
+#ifdef B2M_K1_PROF
+  {
+    static int n_launch = 0;
+    if (++n_launch % 8 == 0) {  // cumulative counters, printed every 8th launch
+      cudaStreamSynchronize(stream);
+      unsigned long long h[16];
+      cudaMemcpyFromSymbol(h, g_k1_prof, sizeof(h));
+      const double mt = h[3] ? double(h[3]) : 1.0, et = h[7] ? double(h[7]) : 1.0, ei = h[9] ? double(h[9]) : 1.0;
+      fprintf(stderr,
+              "[k1prof] per MMA tile: wait_empty %.0f wait_fullb %.0f issue %.0f | per epi warp-tile: wait_full %.0f "
+              "drain %.0f rest %.0f | per item tail %.0f (tiles/item %.1f)\n",
+              h[0] / mt, h[1] / mt, h[2] / mt, h[4] / et, h[5] / et, h[6] / et, h[8] / ei, et / ei);
+    }
+  }
+#endif
   if (after_filter) {
     e = cudaEventRecord(after_filter, stream);  // the roofline times the GEMM kernel alone
     if (e != cudaSuccess) return e;

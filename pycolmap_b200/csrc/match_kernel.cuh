@@ -57,7 +57,7 @@ cudaError_t launch_k1_match(const CUtensorMap& tmap, const MatchParams& p, int n
                             cudaStream_t stream);
 // K1 v2: filter epilogue (slot maxima) + exact dp4a resolution of the candidate rows.  Bit-identical
 // results to launch_k1_match; requires a monotone (non-increasing) acos LUT.
-cudaError_t launch_k1_filter(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const MatchParams& p,
+cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p,
                              const uint8_t* desc, int n_pairs, int max_strips, int n_dirs, int num_sms,
                              cudaStream_t stream, cudaEvent_t after_filter);
 cudaError_t launch_k1_guided(const CUtensorMap& tmap, const MatchParams& p, const GuidedParams& g, int n_pairs,

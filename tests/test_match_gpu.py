@@ -33,6 +33,16 @@ def test_random_pairs_bit_exact(ctx, n1, n2, common):
     _check(ctx, d1, d2, max_ratio=0.6, max_distance=0.5)
 
 
+@pytest.mark.parametrize("n1,n2,common", [(9000, 12000, 2000), (20000, 600, 300), (600, 20000, 300)])
+def test_more_than_8192_features(ctx, n1, n2, common):
+    # resolve kernel: staged slots up to 16384 features, direct global-memory scan beyond
+    rng = np.random.default_rng(n1 + 7 * n2)
+    d1, d2, _ = syn.matching_pair(rng, n1, n2, common)
+    got = _check(ctx, d1, d2)
+    assert len(got) > common // 2
+    _check(ctx, d1, d2, cross_check=0)
+
+
 def test_identity_and_reverse(ctx):
     rng = np.random.default_rng(0)
     d = syn.sift_like(rng, 700)

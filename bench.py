@@ -374,8 +374,9 @@ def main():
     achieved = ops_per_pair * pairs_per_launch / (k1_avg_ms / 1e3) / 1e12
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch (1024 pairs of 8192^2) from the
-            # ncu --set full capture profiles/r01_k1_v9_final.ncu_summary.txt: 230.1 MB + 106.7 MB
-            "traffic": 336.8e6 if K == 8192 else None, "kernel": "b2m_k1_filter_kernel", "avg_launch_ms": k1_avg_ms,
+            # DRAM bytes of one 1024-pair launch, ncu --set full capture profiles/r01_k1_v14_final.ncu_summary.txt:
+            # 136.8 MB read + 59.3 MB written (the distance matrix never leaves TMEM; images mostly hit in L2)
+            "traffic": 196.1e6 if K == 8192 else None, "kernel": "b2m_k1_filter_kernel", "avg_launch_ms": k1_avg_ms,
             "pairs_per_launch": pairs_per_launch, "peak_source": peak_src,
             "algorithmic": "2*K1*K2*128 int8 ops per pair (one GEMM; the transposed GEMM of the cross-check "
                            "direction is not counted)"}

@@ -339,7 +339,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
         if (out != -1 && row < it.nA) {
           p.aux[base + row] = make_uint2(best[q], s1[q]);
           const int k = atomicAdd(p.cand_cnt + it.pair * 2 + it.dir, 1);
-          p.cand_rows[base + k] = row;
+          p.cand_rows[base + k] = row | (sstar[q] << 24);  // winning slot travels with the row
         }
       }
     }
@@ -442,6 +442,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
 namespace {
 
 constexpr int kSlotColsMax = 256;      // columns of one slot staged in shared memory (images up to 16384 features)
+constexpr int kResolveParts = 4;       // CTAs per (pair, direction); 1/2/4/8 measured within 1.5 % of each other
 constexpr int kSlotRowStride = 144;    // bytes; 128-byte descriptors padded so that LDS.128 is conflict-free
 
 // `it`-th column (ascending) of a slot: kSlotCols columns in every 256-column tile
@@ -504,8 +505,13 @@ __device__ __forceinline__ void finish_candidate(const MatchParams& p, int64_t o
 }  // namespace
 
 __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p, const uint8_t* __restrict__ desc) {
-  const int pair = blockIdx.x >> 1;
-  const int dir = blockIdx.x & 1;
+  // kResolveParts CTAs share the candidates of one (pair, direction): part k takes the slots == k mod
+  // kResolveParts (and the rows == k mod kResolveParts of the unstaged candidates), which cuts the
+  // serial chain "stage a slot, score its candidates" of a true-match pair by that factor.
+  const int part = blockIdx.x % kResolveParts;
+  const int pd = blockIdx.x / kResolveParts;
+  const int pair = pd >> 1;
+  const int dir = pd & 1;
   const int n_cand = p.cand_cnt[pair * 2 + dir];
   if (n_cand == 0) return;
   const int ia = p.pairs[2 * pair + dir];
@@ -519,48 +525,53 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
   const int n_items = nB_pad / kSlots;
   const bool staged = n_items <= kSlotColsMax;
 
-  __shared__ int s_start[kSlots + 2];
-  __shared__ int s_fill[kSlots + 1];
+  __shared__ int s_start[kSlots + 1];
+  __shared__ int s_fill[kSlots];
   __shared__ __align__(16) uint8_t s_cols[kSlotColsMax * kSlotRowStride];
 
-  // ---- counting sort of the candidates by bucket (slot 0..kSlots-1, kSlots = generic path)
-  for (int b = threadIdx.x; b < kSlots + 1; b += 256) s_fill[b] = 0;
+  // candidate entry = row | slot << 24 (written by the selector warp); a candidate whose maximum is shared
+  // by several slots, or any candidate of an image too large for the staging buffer, is "unstaged"
+  auto bucket_of = [&](int entry) {
+    const uint2 ax = p.aux[base + (entry & 0xFFFFFF)];
+    return (ax.x == ax.y || !staged) ? kSlots : (entry >> 24);
+  };
+
+  // ---- counting sort of this part's staged candidates by slot
+  for (int b = threadIdx.x; b < kSlots; b += 256) s_fill[b] = 0;
   __syncthreads();
   for (int c = threadIdx.x; c < n_cand; c += 256) {
-    const int row = p.cand_rows[base + c];
-    const uint2 ax = p.aux[base + row];
-    const int bucket = (ax.x == ax.y || !staged) ? kSlots : (-2 - p.mbuf[base + row]);
-    atomicAdd(&s_fill[bucket], 1);
+    const int bucket = bucket_of(p.cand_rows[base + c]);
+    if (bucket < kSlots) atomicAdd(&s_fill[bucket], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int b = 0; b < kSlots + 1; ++b) {
+    for (int b = 0; b < kSlots; ++b) {  // same offsets in every part: the parts write disjoint ranges
       s_start[b] = acc;
       acc += s_fill[b];
       s_fill[b] = 0;
     }
-    s_start[kSlots + 1] = acc;
+    s_start[kSlots] = acc;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < n_cand; c += 256) {
-    const int row = p.cand_rows[base + c];
-    const uint2 ax = p.aux[base + row];
-    const int bucket = (ax.x == ax.y || !staged) ? kSlots : (-2 - p.mbuf[base + row]);
-    p.cand_sorted[base + s_start[bucket] + atomicAdd(&s_fill[bucket], 1)] = row;
+    const int entry = p.cand_rows[base + c];
+    const int bucket = bucket_of(entry);
+    if (bucket < kSlots && bucket % kResolveParts == part)
+      p.cand_sorted[base + s_start[bucket] + atomicAdd(&s_fill[bucket], 1)] = entry & 0xFFFFFF;
   }
   __syncthreads();
 
-  // ---- staged buckets
-  for (int b = 0; b < kSlots; ++b) {
+  // ---- staged slots of this part
+  for (int b = part; b < kSlots; b += kResolveParts) {
     const int c0 = s_start[b], c1 = s_start[b + 1];
     if (c0 == c1) continue;  // uniform
-    __syncthreads();  // previous bucket's readers are done with s_cols
+    __syncthreads();  // previous slot's readers are done with s_cols
     for (int q = threadIdx.x; q < n_items * 8; q += 256) {
-      const int it = q >> 3, part = q & 7;
+      const int it = q >> 3, seg = q & 7;
       const int j = slot_col(b, it);
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim) + part);
-      *reinterpret_cast<uint4*>(s_cols + it * kSlotRowStride + part * 16) = v;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(j) * kDim) + seg);
+      *reinterpret_cast<uint4*>(s_cols + it * kSlotRowStride + seg * 16) = v;
     }
     __syncthreads();
     for (int c = c0 + warp; c < c1; c += 8) {
@@ -584,12 +595,15 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
     }
   }
 
-  // ---- generic bucket: scan global memory (whole row if the maximum is shared by several slots)
-  for (int c = s_start[kSlots] + warp; c < s_start[kSlots + 1]; c += 8) {
-    const int row = p.cand_sorted[base + c];
+  // ---- unstaged candidates of this part: scan global memory (whole row if several slots share the maximum)
+  for (int c = warp; c < n_cand; c += 8) {
+    const int entry = p.cand_rows[base + c];
+    const int row = entry & 0xFFFFFF;
+    if (row % kResolveParts != part) continue;  // uniform in the warp
     const uint2 ax = p.aux[base + row];
     const bool multi = (ax.x == ax.y);
-    const int slot = -2 - p.mbuf[base + row];
+    if (!multi && staged) continue;
+    const int slot = entry >> 24;
     uint32_t a[32];
     const uint4* ap = reinterpret_cast<const uint4*>(A + static_cast<int64_t>(row) * kDim);
 #pragma unroll
@@ -651,7 +665,7 @@ cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p_in,
     e = cudaEventRecord(after_filter, stream);  // the roofline times the GEMM kernel alone
     if (e != cudaSuccess) return e;
   }
-  b2m_k1_resolve_kernel<<<2 * n_pairs, 256, 0, stream>>>(p, desc);
+  b2m_k1_resolve_kernel<<<2 * n_pairs * kResolveParts, 256, 0, stream>>>(p, desc);
   return cudaGetLastError();
 }
 

@@ -161,6 +161,9 @@ int b2m_set_images_device(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat,
 int b2m_match_pairs(b2m_ctx* ctx, const int32_t* pairs /* [n_pairs x 2] */, int64_t n_pairs,
                     const b2m_sift_opts* sift, const b2m_tvg_opts* tvg /* NULL = match only */,
                     b2m_results** out);
+/* The same entry point under the name SURVEY.md section 8(b) gives it. */
+int b2m_match_verify(b2m_ctx* ctx, const int32_t* pairs, int64_t n_pairs, const b2m_sift_opts* sift,
+                     const b2m_tvg_opts* tvg, b2m_results** out);
 
 typedef struct b2m_pair_view {
   uint32_t struct_size;

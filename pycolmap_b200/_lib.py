@@ -69,7 +69,7 @@ class Stats(ctypes.Structure):
 EXPORTS = [
     "b2m_abi_version", "b2m_create", "b2m_destroy", "b2m_last_error", "b2m_request_stop",
     "b2m_sift_opts_default", "b2m_ransac_opts_default", "b2m_tvg_opts_default", "b2m_match_pair",
-    "b2m_set_images", "b2m_set_images_device", "b2m_match_pairs", "b2m_results_num_pairs",
+    "b2m_set_images", "b2m_set_images_device", "b2m_match_pairs", "b2m_match_verify", "b2m_results_num_pairs",
     "b2m_results_total_matches", "b2m_results_num_verified", "b2m_results_get", "b2m_results_free", "b2m_estimate_two_view_geometry",
     "b2m_ransac_model", "b2m_squared_sampson_error", "b2m_get_stats", "b2m_reset_stats",
 ]

@@ -600,6 +600,11 @@ int b2m_match_pairs(b2m_ctx* ctx, const int32_t* pairs, int64_t n_pairs, const b
   return match_pairs_impl(ctx, ctx->images, pairs, n_pairs, sift, tvg, out);
 }
 
+int b2m_match_verify(b2m_ctx* ctx, const int32_t* pairs, int64_t n_pairs, const b2m_sift_opts* sift,
+                     const b2m_tvg_opts* tvg, b2m_results** out) {
+  return b2m_match_pairs(ctx, pairs, n_pairs, sift, tvg, out);
+}
+
 int b2m_match_pair(b2m_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2,
                    const b2m_sift_opts* opts, uint32_t* out_matches, int64_t cap, int64_t* out_n) {
   if (!ctx) return B2M_EINVAL;

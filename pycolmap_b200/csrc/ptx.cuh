@@ -17,9 +17,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -54,19 +51,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// Same, multicast to every CTA of the cluster selected by `cta_mask`: the tile lands at the same
-// shared-memory offset in each destination CTA and completes tx bytes on the mbarrier at the same
-// offset in each of them.
-__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
-                                                      int32_t c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
 }
 
@@ -115,14 +99,6 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// Same, arriving on the mbarrier at this offset in every CTA of `cta_mask` (cluster multicast).
-__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 columns of 32-bit: thread i of the warp receives lane (base_lane + i), columns col..col+31.
@@ -148,9 +124,6 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "r"(taddr)
       : "memory");
 }
-// width-generic spelling used by the filter epilogue
-__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32(taddr, v); }
-__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x16(taddr, v); }
 
 // ---- CTA-pair (cta_group::2) forms ---------------------------------------------------------
 // Two CTAs of a cluster (ranks 2k, 2k+1) drive one 256-row MMA: each SM supplies its own 128 rows of A

@@ -1,0 +1,407 @@
+#include "controllers.h"
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <new>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <unordered_map>
+
+namespace b2mh {
+
+// ---- option conversion ---------------------------------------------------------------------------
+b2m_sift_opts ToAbi(const SiftMatchingOptions& o) {
+  b2m_sift_opts s;
+  b2m_sift_opts_default(&s);
+  s.max_ratio = static_cast<float>(o.max_ratio);  // double -> float at use, like upstream
+  s.max_distance = static_cast<float>(o.max_distance);
+  s.cross_check = o.cross_check ? 1 : 0;
+  s.max_num_matches = o.max_num_matches;
+  s.guided_matching = o.guided_matching ? 1 : 0;
+  return s;
+}
+
+b2m_ransac_opts ToAbi(const RANSACOptions& o) {
+  b2m_ransac_opts r;
+  b2m_ransac_opts_default(&r);
+  r.max_error = o.max_error;
+  r.min_inlier_ratio = o.min_inlier_ratio;
+  r.confidence = o.confidence;
+  r.dyn_num_trials_multiplier = o.dyn_num_trials_multiplier;
+  r.min_num_trials = o.min_num_trials;
+  r.max_num_trials = o.max_num_trials;
+  return r;
+}
+
+b2m_tvg_opts ToAbi(const TwoViewGeometryOptions& o) {
+  b2m_tvg_opts t;
+  b2m_tvg_opts_default(&t);
+  t.min_num_inliers = o.min_num_inliers;
+  t.min_E_F_inlier_ratio = o.min_E_F_inlier_ratio;
+  t.max_H_inlier_ratio = o.max_H_inlier_ratio;
+  t.watermark_min_inlier_ratio = o.watermark_min_inlier_ratio;
+  t.watermark_border_size = o.watermark_border_size;
+  t.detect_watermark = o.detect_watermark;
+  t.multiple_ignore_watermark = o.multiple_ignore_watermark;
+  t.force_H_use = o.force_H_use;
+  t.compute_relative_pose = o.compute_relative_pose;
+  t.multiple_models = o.multiple_models;
+  t.ransac = ToAbi(o.ransac);
+  return t;
+}
+
+b2m_camera ToAbi(const CameraRow& c) {
+  if (c.model != 0 && c.model != 1)
+    throw std::invalid_argument("[controllers.cc] camera model id " + std::to_string(c.model) +
+                                " is not supported by the B200 verifier (SIMPLE_PINHOLE and PINHOLE only)");
+  const size_t need = c.model == 0 ? 3 : 4;
+  if (c.params.size() != need)
+    throw std::invalid_argument("[controllers.cc] Check Failed: camera has " + std::to_string(need) + " parameters");
+  b2m_camera b;
+  memset(&b, 0, sizeof(b));
+  b.struct_size = sizeof(b);
+  b.model = c.model;
+  b.width = static_cast<int32_t>(c.width);
+  b.height = static_cast<int32_t>(c.height);
+  b.has_prior_focal_length = c.has_prior_focal_length ? 1 : 0;
+  std::copy(c.params.begin(), c.params.end(), b.params);
+  return b;
+}
+
+int FirstGpuIndex(const std::string& gpu_index) {
+  std::string first = gpu_index.substr(0, gpu_index.find(','));
+  first.erase(std::remove_if(first.begin(), first.end(), [](unsigned char ch) { return std::isspace(ch); }),
+              first.end());
+  if (first.empty() || first == "-1") return 0;
+  try {
+    return std::max(0, std::stoi(first));
+  } catch (const std::exception&) {
+    throw std::invalid_argument("[controllers.cc] Check Failed: gpu_index is a comma-separated list of integers");
+  }
+}
+
+// ---- pair generators -----------------------------------------------------------------------------
+std::vector<PairList> ExhaustivePairBlocks(int n, int bs) {
+  if (bs < 1) throw std::invalid_argument("[controllers.cc] Check Failed: block_size >= 1");
+  std::vector<PairList> out;
+  for (int s1 = 0; s1 < n; s1 += bs) {
+    const int e1 = std::min(n, s1 + bs);
+    for (int s2 = 0; s2 < n; s2 += bs) {
+      const int e2 = std::min(n, s2 + bs);
+      PairList block;
+      for (int i1 = s1; i1 < e1; ++i1) {
+        const int r1 = i1 % bs;
+        for (int i2 = s2; i2 < e2; ++i2) {
+          const int r2 = i2 % bs;
+          // the upstream rule that visits every unordered pair exactly once over the block grid
+          if ((i1 > i2 && r1 <= r2) || (i1 < i2 && r1 < r2)) {
+            block.push_back(i1);
+            block.push_back(i2);
+          }
+        }
+      }
+      if (!block.empty()) out.push_back(std::move(block));
+    }
+  }
+  return out;
+}
+
+PairList SequentialPairs(int n, int overlap, bool quadratic_overlap) {
+  PairList out;
+  std::set<std::pair<int, int>> seen;
+  auto emit = [&](int64_t i1, int64_t i2) {
+    if (i2 < n && seen.insert({static_cast<int>(i1), static_cast<int>(i2)}).second) {
+      out.push_back(static_cast<int32_t>(i1));
+      out.push_back(static_cast<int32_t>(i2));
+    }
+  };
+  for (int i1 = 0; i1 < n; ++i1) {
+    for (int k = 0; k < overlap; ++k) {
+      emit(i1, static_cast<int64_t>(i1) + k + 1);
+      if (quadratic_overlap) emit(i1, static_cast<int64_t>(i1) + (k < 40 ? (int64_t{1} << k) : int64_t{1} << 40));
+    }
+  }
+  return out;
+}
+
+// ---- engine --------------------------------------------------------------------------------------
+namespace {
+std::mutex g_engine_mutex;
+constexpr int kMaxDevices = 64;
+b2m_ctx* g_ctx[kMaxDevices] = {};  // plain array: RequestStopAll must not take locks
+}  // namespace
+
+void ThrowOnError(b2m_ctx* ctx, int rc) {
+  if (rc == B2M_OK) return;
+  const char* m = b2m_last_error(ctx);
+  const std::string msg = m ? m : "";
+  switch (rc) {
+    case B2M_EINVAL: throw std::invalid_argument(msg);  // -> ValueError, as THROW_CHECK (R:log_exceptions.h:114-147)
+    case B2M_ESTOPPED: throw StoppedError();            // -> KeyboardInterrupt (R:helpers.h:306-347)
+    case B2M_ENOMEM: throw std::bad_alloc();
+    default: throw std::runtime_error("b200match error " + std::to_string(rc) + ": " + msg);
+  }
+}
+
+b2m_ctx* Engine::Get(int device) {
+  if (device < 0 || device >= kMaxDevices) throw std::invalid_argument("[controllers.cc] Check Failed: 0 <= gpu index < 64");
+  std::lock_guard<std::mutex> lock(g_engine_mutex);
+  if (!g_ctx[device]) {
+    b2m_device_cfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.struct_size = sizeof(cfg);
+    cfg.device = device;
+    cfg.seed = 0;  // SetPRNGSeed(0) (R:estimators/essential_matrix.h:25)
+    b2m_ctx* ctx = nullptr;
+    ThrowOnError(nullptr, b2m_create(&cfg, &ctx));
+    g_ctx[device] = ctx;
+  }
+  return g_ctx[device];
+}
+
+void Engine::RequestStopAll() {
+  for (int i = 0; i < kMaxDevices; ++i)
+    if (g_ctx[i]) b2m_request_stop(g_ctx[i]);
+}
+
+void Engine::DestroyAll() {
+  std::lock_guard<std::mutex> lock(g_engine_mutex);
+  for (int i = 0; i < kMaxDevices; ++i) {
+    if (g_ctx[i]) b2m_destroy(g_ctx[i]);
+    g_ctx[i] = nullptr;
+  }
+}
+
+// ---- pipelines -----------------------------------------------------------------------------------
+void CheckFileExists(const std::string& path, const char* where) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f.good()) throw std::invalid_argument(std::string("[") + where + "] Check Failed: File " + path + " does not exist.");
+}
+
+namespace {
+
+struct LoadedSet {
+  std::vector<int64_t> ids;
+  std::vector<std::string> names;
+  std::vector<int64_t> camera_ids;
+};
+
+// FeatureMatcherCache: every image's descriptors, keypoint positions and camera go to the GPU once.
+LoadedSet LoadImageSet(Database& db, b2m_ctx* ctx, bool order_by_name) {
+  std::vector<ImageRow> images = db.ReadAllImages();
+  if (order_by_name)
+    std::stable_sort(images.begin(), images.end(), [](const ImageRow& a, const ImageRow& b) { return a.name < b.name; });
+  LoadedSet L;
+  std::vector<DescriptorsBlob> desc(images.size());
+  std::vector<std::vector<float>> xy(images.size());
+  std::vector<b2m_camera> cams(images.size());
+  std::vector<int32_t> n_feat(images.size());
+  std::unordered_map<int64_t, b2m_camera> cam_cache;
+  for (size_t i = 0; i < images.size(); ++i) {
+    const ImageRow& im = images[i];
+    L.ids.push_back(im.image_id);
+    L.names.push_back(im.name);
+    L.camera_ids.push_back(im.camera_id);
+    desc[i] = db.ReadDescriptors(im.image_id);
+    const KeypointsBlob kp = db.ReadKeypoints(im.image_id);
+    if (kp.rows != desc[i].rows)
+      throw std::invalid_argument("[controllers.cc] Check Failed: keypoints.rows == descriptors.rows");
+    xy[i].resize(static_cast<size_t>(kp.rows) * 2);
+    for (int64_t r = 0; r < kp.rows; ++r) {
+      xy[i][2 * r] = kp.data[r * kp.cols];
+      xy[i][2 * r + 1] = kp.data[r * kp.cols + 1];
+    }
+    auto it = cam_cache.find(im.camera_id);
+    if (it == cam_cache.end()) it = cam_cache.emplace(im.camera_id, ToAbi(db.ReadCamera(im.camera_id))).first;
+    cams[i] = it->second;
+    n_feat[i] = static_cast<int32_t>(desc[i].rows);
+  }
+  std::vector<const uint8_t*> dptr(images.size());
+  std::vector<const float*> kptr(images.size());
+  for (size_t i = 0; i < images.size(); ++i) {
+    dptr[i] = desc[i].data.data();
+    kptr[i] = xy[i].data();
+  }
+  ThrowOnError(ctx, b2m_set_images(ctx, static_cast<int32_t>(images.size()), n_feat.data(), dptr.data(), kptr.data(),
+                                   cams.data()));
+  return L;
+}
+
+Mat3 ToMat3(const double* p) {
+  Mat3 m;
+  std::copy(p, p + 9, m.begin());
+  return m;
+}
+
+struct ResultsGuard {
+  b2m_results* r = nullptr;
+  ~ResultsGuard() {
+    if (r) b2m_results_free(r);
+  }
+};
+
+// FeatureMatcherController::Match (row P3): skip self pairs, duplicates and pairs with both results
+// stored; match + verify the rest on the GPU; write both tables in one transaction per chunk.
+void MatchPairsIntoDb(Database& db, b2m_ctx* ctx, const LoadedSet& L, const std::vector<PairList>& chunks,
+                      const b2m_sift_opts& sift, const b2m_tvg_opts& tvg, bool skip_existing) {
+  std::unordered_set<int64_t> have_m, have_g;
+  if (skip_existing) {
+    have_m = db.ExistingPairIds("matches");
+    have_g = db.ExistingPairIds("two_view_geometries");
+  }
+  for (const PairList& chunk : chunks) {
+    PairList todo;
+    for (size_t k = 0; k + 1 < chunk.size(); k += 2) {
+      const int32_t a = chunk[k], b = chunk[k + 1];
+      if (a == b) continue;
+      const int64_t pid = ImagePairToPairId(L.ids[a], L.ids[b]);
+      const bool stored = have_m.count(pid) && have_g.count(pid);
+      have_m.insert(pid);
+      have_g.insert(pid);
+      if (stored) continue;
+      todo.push_back(a);
+      todo.push_back(b);
+    }
+    if (todo.empty()) continue;
+    ResultsGuard res;
+    ThrowOnError(ctx, b2m_match_pairs(ctx, todo.data(), static_cast<int64_t>(todo.size() / 2), &sift, &tvg, &res.r));
+    DatabaseTransaction tx(&db);
+    const int64_t n = b2m_results_num_pairs(res.r);
+    for (int64_t k = 0; k < n; ++k) {
+      b2m_pair_view v;
+      memset(&v, 0, sizeof(v));
+      v.struct_size = sizeof(v);
+      ThrowOnError(ctx, b2m_results_get(res.r, k, &v));
+      const int64_t id1 = L.ids[todo[2 * k]], id2 = L.ids[todo[2 * k + 1]];
+      db.WriteMatches(id1, id2, v.matches, v.n_matches);
+      db.WriteTwoViewGeometry(id1, id2, v.config, v.inlier_matches, v.n_inliers, ToMat3(v.F), ToMat3(v.E), ToMat3(v.H));
+    }
+  }
+}
+
+// Concatenate block pair lists into chunks of >= `target` pairs: one GPU call + one transaction each.
+std::vector<PairList> Chunked(const std::vector<PairList>& blocks, size_t target = 65536) {
+  std::vector<PairList> out;
+  PairList cur;
+  for (const PairList& b : blocks) {
+    cur.insert(cur.end(), b.begin(), b.end());
+    if (cur.size() / 2 >= target) {
+      out.push_back(std::move(cur));
+      cur.clear();
+    }
+  }
+  if (!cur.empty()) out.push_back(std::move(cur));
+  return out;
+}
+
+}  // namespace
+
+void MatchExhaustive(const std::string& database_path, const SiftMatchingOptions& sift,
+                     const ExhaustiveMatchingOptions& matching, const TwoViewGeometryOptions& verification,
+                     int device_index) {
+  CheckFileExists(database_path, "match_features.h:32");
+  if (matching.block_size <= 1) throw std::invalid_argument("[controllers.cc] Check Failed: block_size > 1");
+  b2m_ctx* ctx = Engine::Get(device_index);
+  Database db(database_path);
+  const LoadedSet L = LoadImageSet(db, ctx, /*order_by_name=*/false);
+  MatchPairsIntoDb(db, ctx, L, Chunked(ExhaustivePairBlocks(static_cast<int>(L.ids.size()), matching.block_size)),
+                   ToAbi(sift), ToAbi(verification), /*skip_existing=*/true);
+}
+
+void MatchSequential(const std::string& database_path, const SiftMatchingOptions& sift,
+                     const SequentialMatchingOptions& matching, const TwoViewGeometryOptions& verification,
+                     int device_index) {
+  CheckFileExists(database_path, "match_features.h:32");
+  if (matching.loop_detection)
+    throw std::invalid_argument("[controllers.cc] loop_detection needs a vocabulary tree: out of scope (SURVEY.md row B6)");
+  if (matching.overlap < 1) throw std::invalid_argument("[controllers.cc] Check Failed: overlap > 0");
+  b2m_ctx* ctx = Engine::Get(device_index);
+  Database db(database_path);
+  const LoadedSet L = LoadImageSet(db, ctx, /*order_by_name=*/true);
+  MatchPairsIntoDb(db, ctx, L,
+                   {SequentialPairs(static_cast<int>(L.ids.size()), matching.overlap, matching.quadratic_overlap)},
+                   ToAbi(sift), ToAbi(verification), /*skip_existing=*/true);
+}
+
+void VerifyMatches(const std::string& database_path, const std::string& pairs_path,
+                   const TwoViewGeometryOptions& options) {
+  CheckFileExists(database_path, "match_features.h:54");
+  CheckFileExists(pairs_path, "match_features.h:55");
+  b2m_ctx* ctx = Engine::Get(0);
+  Database db(database_path);
+  const LoadedSet L = LoadImageSet(db, ctx, /*order_by_name=*/false);
+  std::unordered_map<std::string, int> index_of;
+  for (size_t i = 0; i < L.names.size(); ++i) index_of[L.names[i]] = static_cast<int>(i);
+
+  // pair list: `name1 name2` per line; unknown names, self pairs and repeats are skipped like upstream
+  std::vector<std::pair<int, int>> todo_verify;
+  PairList todo_match;
+  std::set<std::pair<int, int>> seen;
+  std::ifstream f(pairs_path);
+  std::string line;
+  while (std::getline(f, line)) {
+    std::istringstream ss(line);
+    std::string n1, n2;
+    if (!(ss >> n1) || n1[0] == '#' || !(ss >> n2)) continue;
+    const auto a = index_of.find(n1), b = index_of.find(n2);
+    if (a == index_of.end() || b == index_of.end() || a->second == b->second) continue;
+    if (!seen.insert({std::min(a->second, b->second), std::max(a->second, b->second)}).second) continue;
+    const bool has_m = db.ExistsMatches(L.ids[a->second], L.ids[b->second]);
+    const bool has_g = db.ExistsInlierMatches(L.ids[a->second], L.ids[b->second]);
+    if (has_m && has_g) continue;
+    if (has_m) {
+      todo_verify.push_back({a->second, b->second});
+    } else {
+      todo_match.push_back(a->second);
+      todo_match.push_back(b->second);
+    }
+  }
+  const b2m_tvg_opts tvg = ToAbi(options);
+  if (!todo_match.empty())
+    MatchPairsIntoDb(db, ctx, L, {todo_match}, ToAbi(SiftMatchingOptions()), tvg, /*skip_existing=*/false);
+
+  DatabaseTransaction tx(&db);
+  for (const auto& [a, b] : todo_verify) {
+    const int64_t id1 = L.ids[a], id2 = L.ids[b];
+    const std::vector<uint32_t> m = db.ReadMatches(id1, id2);
+    const int64_t n_m = static_cast<int64_t>(m.size() / 2);
+    int config = B2M_UNDEFINED;
+    std::vector<uint32_t> inl;
+    Mat3 E{}, F{}, H{};
+    if (n_m >= options.min_num_inliers) {
+      auto points = [&](int64_t id) {
+        const KeypointsBlob kp = db.ReadKeypoints(id);
+        std::vector<double> p(static_cast<size_t>(kp.rows) * 2);
+        for (int64_t r = 0; r < kp.rows; ++r) {
+          p[2 * r] = kp.data[r * kp.cols];
+          p[2 * r + 1] = kp.data[r * kp.cols + 1];
+        }
+        return p;
+      };
+      const std::vector<double> p1 = points(id1), p2 = points(id2);
+      const b2m_camera c1 = ToAbi(db.ReadCamera(L.camera_ids[a])), c2 = ToAbi(db.ReadCamera(L.camera_ids[b]));
+      b2m_tvg_result r;
+      memset(&r, 0, sizeof(r));
+      r.struct_size = sizeof(r);
+      inl.resize(m.size());
+      ThrowOnError(ctx, b2m_estimate_two_view_geometry(ctx, &c1, p1.data(), static_cast<int64_t>(p1.size() / 2), &c2,
+                                                       p2.data(), static_cast<int64_t>(p2.size() / 2), m.data(), n_m,
+                                                       &tvg, &r, inl.data()));
+      inl.resize(static_cast<size_t>(r.n_inliers) * 2);
+      config = r.config;
+      E = ToMat3(r.E); F = ToMat3(r.F); H = ToMat3(r.H);
+    }
+    if (static_cast<int64_t>(inl.size() / 2) < options.min_num_inliers) {  // controller write rule (row P3)
+      config = B2M_UNDEFINED;
+      inl.clear();
+      E = F = H = Mat3{};
+    }
+    db.WriteTwoViewGeometry(id1, id2, config, inl.data(), static_cast<int64_t>(inl.size() / 2), F, E, H);
+  }
+}
+
+}  // namespace b2mh

@@ -1,0 +1,353 @@
+#include "database.h"
+
+#include <cmath>
+#include <cstring>
+#include <exception>
+#include <stdexcept>
+
+namespace b2mh {
+namespace {
+
+const char* kCreateSql =
+    "CREATE TABLE IF NOT EXISTS cameras (camera_id INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, "
+    "model INTEGER NOT NULL, width INTEGER NOT NULL, height INTEGER NOT NULL, params BLOB, "
+    "prior_focal_length INTEGER NOT NULL);"
+    "CREATE TABLE IF NOT EXISTS images (image_id INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, "
+    "name TEXT NOT NULL UNIQUE, camera_id INTEGER NOT NULL, prior_qw REAL, prior_qx REAL, prior_qy REAL, "
+    "prior_qz REAL, prior_tx REAL, prior_ty REAL, prior_tz REAL, "
+    "CONSTRAINT image_id_check CHECK(image_id >= 0 and image_id < 2147483647), "
+    "FOREIGN KEY(camera_id) REFERENCES cameras(camera_id));"
+    "CREATE TABLE IF NOT EXISTS keypoints (image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, "
+    "cols INTEGER NOT NULL, data BLOB, FOREIGN KEY(image_id) REFERENCES images(image_id) ON DELETE CASCADE);"
+    "CREATE TABLE IF NOT EXISTS descriptors (image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, "
+    "cols INTEGER NOT NULL, data BLOB, FOREIGN KEY(image_id) REFERENCES images(image_id) ON DELETE CASCADE);"
+    "CREATE TABLE IF NOT EXISTS matches (pair_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, "
+    "cols INTEGER NOT NULL, data BLOB);"
+    "CREATE TABLE IF NOT EXISTS two_view_geometries (pair_id INTEGER PRIMARY KEY NOT NULL, "
+    "rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB, config INTEGER NOT NULL, F BLOB, E BLOB, H BLOB, "
+    "qvec BLOB, tvec BLOB);"
+    "CREATE UNIQUE INDEX IF NOT EXISTS index_name ON images(name);";
+
+bool AllZero(const Mat3& m) {
+  for (double v : m)
+    if (v != 0.0) return false;
+  return true;
+}
+
+}  // namespace
+
+int64_t ImagePairToPairId(int64_t a, int64_t b) {
+  if (a > b) std::swap(a, b);
+  return a * kMaxNumImages + b;
+}
+
+void PairIdToImagePair(int64_t pair_id, int64_t* a, int64_t* b) {
+  *a = pair_id / kMaxNumImages;
+  *b = pair_id % kMaxNumImages;
+}
+
+bool Invert3x3(const Mat3& m, Mat3* out) {
+  const double c0 = m[4] * m[8] - m[5] * m[7], c1 = m[5] * m[6] - m[3] * m[8], c2 = m[3] * m[7] - m[4] * m[6];
+  const double det = m[0] * c0 + m[1] * c1 + m[2] * c2;
+  if (!(std::fabs(det) > 1e-300)) return false;
+  const double r = 1.0 / det;
+  (*out)[0] = c0 * r;
+  (*out)[1] = (m[2] * m[7] - m[1] * m[8]) * r;
+  (*out)[2] = (m[1] * m[5] - m[2] * m[4]) * r;
+  (*out)[3] = c1 * r;
+  (*out)[4] = (m[0] * m[8] - m[2] * m[6]) * r;
+  (*out)[5] = (m[2] * m[3] - m[0] * m[5]) * r;
+  (*out)[6] = c2 * r;
+  (*out)[7] = (m[1] * m[6] - m[0] * m[7]) * r;
+  (*out)[8] = (m[0] * m[4] - m[1] * m[3]) * r;
+  return true;
+}
+
+Mat3 Transposed(const Mat3& m) { return Mat3{m[0], m[3], m[6], m[1], m[4], m[7], m[2], m[5], m[8]}; }
+
+// ---- RAII prepared statement ---------------------------------------------------------------------
+struct Database::Stmt {
+  Stmt(Database* d, const char* sql) : db(d) {
+    if (!d->db_) throw std::runtime_error("[database.cc] Check Failed: database is open");
+    if (sq::api().prepare_v2(d->db_, sql, -1, &st, nullptr) != sq::kOk) d->Fail(sql);
+  }
+  ~Stmt() {
+    if (st) sq::api().finalize(st);
+  }
+  void I64(int i, int64_t v) { Check(sq::api().bind_int64(st, i, v)); }
+  void Null(int i) { Check(sq::api().bind_null(st, i)); }
+  void Text(int i, const std::string& s) {
+    Check(sq::api().bind_text(st, i, s.c_str(), static_cast<int>(s.size()), sq::Transient()));
+  }
+  // the buffer must stay alive until Step() returns (no copy: SQLITE_STATIC)
+  void Blob(int i, const void* p, size_t n) {
+    static const char kEmpty = 0;
+    Check(sq::api().bind_blob64(st, i, n ? p : &kEmpty, n, nullptr));
+  }
+  bool Step() {
+    const int rc = sq::api().step(st);
+    if (rc == sq::kRow) return true;
+    if (rc != sq::kDone) db->Fail("sqlite3_step");
+    return false;
+  }
+  int64_t ColI64(int i) { return sq::api().column_int64(st, i); }
+  bool ColIsNull(int i) { return sq::api().column_type(st, i) == sq::kTypeNull; }
+  std::string ColText(int i) {
+    const unsigned char* t = sq::api().column_text(st, i);
+    return t ? std::string(reinterpret_cast<const char*>(t)) : std::string();
+  }
+  template <typename T>
+  std::vector<T> ColBlob(int i) {
+    const void* p = sq::api().column_blob(st, i);
+    const size_t n = static_cast<size_t>(sq::api().column_bytes(st, i));
+    std::vector<T> v(n / sizeof(T));
+    if (p && !v.empty()) memcpy(v.data(), p, v.size() * sizeof(T));
+    return v;
+  }
+  void Check(int rc) {
+    if (rc != sq::kOk) db->Fail("sqlite3_bind");
+  }
+  Database* db;
+  sq::sqlite3_stmt* st = nullptr;
+};
+
+void Database::Fail(const char* what) {
+  std::string msg = std::string("[database.cc] SQLite error (") + what + "): ";
+  msg += db_ ? sq::api().errmsg(db_) : "database is closed";
+  throw std::runtime_error(msg);
+}
+
+void Database::Open(const std::string& path) {
+  Close();
+  if (sq::api().open_v2(path.c_str(), &db_, sq::kOpenReadWrite | sq::kOpenCreate, nullptr) != sq::kOk) {
+    std::string msg = "[database.cc] cannot open database " + path + ": " + (db_ ? sq::api().errmsg(db_) : "?");
+    if (db_) sq::api().close(db_);
+    db_ = nullptr;
+    throw std::runtime_error(msg);
+  }
+  Exec(kCreateSql);
+}
+
+void Database::Close() {
+  if (db_) sq::api().close(db_);
+  db_ = nullptr;
+}
+
+void Database::Exec(const char* sql) {
+  if (!db_) throw std::runtime_error("[database.cc] Check Failed: database is open");
+  char* err = nullptr;
+  if (sq::api().exec(db_, sql, nullptr, nullptr, &err) != sq::kOk) {
+    std::string msg = std::string("[database.cc] SQLite error: ") + (err ? err : "?");
+    if (err) sq::api().free(err);
+    throw std::runtime_error(msg);
+  }
+}
+
+int64_t Database::Scalar(const char* sql) {
+  Stmt s(this, sql);
+  return s.Step() ? s.ColI64(0) : 0;
+}
+
+int64_t Database::NumRows(const std::string& table) {
+  if (table != "matches" && table != "two_view_geometries")
+    throw std::invalid_argument("[database.cc] Check Failed: table is matches or two_view_geometries");
+  return Scalar(("SELECT COUNT(*) FROM " + table).c_str());
+}
+
+int64_t Database::AddCamera(int model, int64_t width, int64_t height, const std::vector<double>& params,
+                            bool prior_focal_length) {
+  Stmt s(this, "INSERT INTO cameras VALUES (NULL, ?, ?, ?, ?, ?)");
+  s.I64(1, model); s.I64(2, width); s.I64(3, height);
+  s.Blob(4, params.data(), params.size() * sizeof(double));
+  s.I64(5, prior_focal_length ? 1 : 0);
+  s.Step();
+  return sq::api().last_insert_rowid(db_);
+}
+
+int64_t Database::AddImage(const std::string& name, int64_t camera_id) {
+  Stmt s(this, "INSERT INTO images VALUES (NULL, ?, ?, NULL, NULL, NULL, NULL, NULL, NULL, NULL)");
+  s.Text(1, name); s.I64(2, camera_id);
+  s.Step();
+  return sq::api().last_insert_rowid(db_);
+}
+
+void Database::WriteKeypoints(int64_t image_id, const float* data, int64_t rows, int64_t cols) {
+  if (cols != 2 && cols != 4 && cols != 6)
+    throw std::invalid_argument("[database.cc] Check Failed: keypoints have 2, 4 or 6 columns");
+  Stmt s(this, "INSERT OR REPLACE INTO keypoints VALUES (?, ?, ?, ?)");
+  s.I64(1, image_id); s.I64(2, rows); s.I64(3, cols);
+  s.Blob(4, data, static_cast<size_t>(rows * cols) * sizeof(float));
+  s.Step();
+}
+
+void Database::WriteDescriptors(int64_t image_id, const uint8_t* data, int64_t rows, int64_t cols) {
+  if (cols != 128) throw std::invalid_argument("[database.cc] Check Failed: descriptors.cols() == 128");
+  Stmt s(this, "INSERT OR REPLACE INTO descriptors VALUES (?, ?, ?, ?)");
+  s.I64(1, image_id); s.I64(2, rows); s.I64(3, cols);
+  s.Blob(4, data, static_cast<size_t>(rows * cols));
+  s.Step();
+}
+
+std::vector<ImageRow> Database::ReadAllImages() {
+  std::vector<ImageRow> out;
+  Stmt s(this, "SELECT image_id, name, camera_id FROM images ORDER BY image_id");
+  while (s.Step()) out.push_back(ImageRow{s.ColI64(0), s.ColText(1), s.ColI64(2)});
+  return out;
+}
+
+CameraRow Database::ReadCamera(int64_t camera_id) {
+  Stmt s(this, "SELECT model, width, height, params, prior_focal_length FROM cameras WHERE camera_id = ?");
+  s.I64(1, camera_id);
+  if (!s.Step())
+    throw std::invalid_argument("[database.cc] Check Failed: camera " + std::to_string(camera_id) + " exists");
+  CameraRow c;
+  c.camera_id = camera_id;
+  c.model = static_cast<int>(s.ColI64(0));
+  c.width = s.ColI64(1);
+  c.height = s.ColI64(2);
+  c.params = s.ColBlob<double>(3);
+  c.has_prior_focal_length = s.ColI64(4) != 0;
+  return c;
+}
+
+KeypointsBlob Database::ReadKeypoints(int64_t image_id) {
+  KeypointsBlob k;
+  k.cols = 2;
+  Stmt s(this, "SELECT rows, cols, data FROM keypoints WHERE image_id = ?");
+  s.I64(1, image_id);
+  if (!s.Step() || s.ColI64(0) == 0) return k;
+  k.rows = s.ColI64(0);
+  k.cols = s.ColI64(1);
+  k.data = s.ColBlob<float>(2);
+  if (static_cast<int64_t>(k.data.size()) != k.rows * k.cols)
+    throw std::runtime_error("[database.cc] Check Failed: keypoints blob size == rows * cols * 4");
+  return k;
+}
+
+DescriptorsBlob Database::ReadDescriptors(int64_t image_id) {
+  DescriptorsBlob d;
+  Stmt s(this, "SELECT rows, cols, data FROM descriptors WHERE image_id = ?");
+  s.I64(1, image_id);
+  if (!s.Step() || s.ColI64(0) == 0) return d;
+  d.rows = s.ColI64(0);
+  d.cols = s.ColI64(1);
+  d.data = s.ColBlob<uint8_t>(2);
+  if (d.cols != 128 || static_cast<int64_t>(d.data.size()) != d.rows * d.cols)
+    throw std::runtime_error("[database.cc] Check Failed: descriptors are rows x 128 uint8");
+  return d;
+}
+
+bool Database::ExistsMatches(int64_t id1, int64_t id2) {
+  Stmt s(this, "SELECT 1 FROM matches WHERE pair_id = ?");
+  s.I64(1, ImagePairToPairId(id1, id2));
+  return s.Step();
+}
+
+bool Database::ExistsInlierMatches(int64_t id1, int64_t id2) {
+  Stmt s(this, "SELECT 1 FROM two_view_geometries WHERE pair_id = ?");
+  s.I64(1, ImagePairToPairId(id1, id2));
+  return s.Step();
+}
+
+std::unordered_set<int64_t> Database::ExistingPairIds(const std::string& table) {
+  if (table != "matches" && table != "two_view_geometries")
+    throw std::invalid_argument("[database.cc] Check Failed: table is matches or two_view_geometries");
+  std::unordered_set<int64_t> out;
+  Stmt s(this, ("SELECT pair_id FROM " + table).c_str());
+  while (s.Step()) out.insert(s.ColI64(0));
+  return out;
+}
+
+namespace {
+void SwapColumns(std::vector<uint32_t>* m) {
+  for (size_t i = 0; i + 1 < m->size(); i += 2) std::swap((*m)[i], (*m)[i + 1]);
+}
+}  // namespace
+
+std::vector<uint32_t> Database::ReadMatches(int64_t id1, int64_t id2) {
+  Stmt s(this, "SELECT rows, cols, data FROM matches WHERE pair_id = ?");
+  s.I64(1, ImagePairToPairId(id1, id2));
+  if (!s.Step() || s.ColI64(0) == 0) return {};
+  std::vector<uint32_t> m = s.ColBlob<uint32_t>(2);
+  m.resize(static_cast<size_t>(s.ColI64(0)) * 2);
+  if (id1 > id2) SwapColumns(&m);
+  return m;
+}
+
+bool Database::ReadTwoViewGeometry(int64_t id1, int64_t id2, TwoViewGeometryRow* out) {
+  Stmt s(this, "SELECT rows, cols, data, config, F, E, H FROM two_view_geometries WHERE pair_id = ?");
+  s.I64(1, ImagePairToPairId(id1, id2));
+  if (!s.Step()) return false;
+  TwoViewGeometryRow g;
+  const int64_t rows = s.ColI64(0);
+  if (rows > 0) {
+    g.inlier_matches = s.ColBlob<uint32_t>(2);
+    g.inlier_matches.resize(static_cast<size_t>(rows) * 2);
+  }
+  g.config = static_cast<int>(s.ColI64(3));
+  auto mat = [&](int col, Mat3* m) {
+    const std::vector<double> v = s.ColBlob<double>(col);
+    if (v.size() == 9) std::copy(v.begin(), v.end(), m->begin());
+  };
+  mat(4, &g.F); mat(5, &g.E); mat(6, &g.H);
+  if (id1 > id2) {  // TwoViewGeometry::Invert (R:estimators/two_view_geometry.h:92)
+    SwapColumns(&g.inlier_matches);
+    g.F = Transposed(g.F);
+    g.E = Transposed(g.E);
+    Mat3 inv;
+    if (!AllZero(g.H) && Invert3x3(g.H, &inv)) g.H = inv;
+  }
+  *out = std::move(g);
+  return true;
+}
+
+void Database::WriteMatches(int64_t id1, int64_t id2, const uint32_t* matches, int64_t n) {
+  std::vector<uint32_t> swapped;
+  if (id1 > id2 && n > 0) {
+    swapped.assign(matches, matches + 2 * n);
+    SwapColumns(&swapped);
+    matches = swapped.data();
+  }
+  Stmt s(this, "INSERT OR REPLACE INTO matches VALUES (?, ?, 2, ?)");
+  s.I64(1, ImagePairToPairId(id1, id2)); s.I64(2, n);
+  s.Blob(3, matches, static_cast<size_t>(n) * 8);
+  s.Step();
+}
+
+void Database::WriteTwoViewGeometry(int64_t id1, int64_t id2, int config, const uint32_t* inlier_matches, int64_t n,
+                                    const Mat3& F_in, const Mat3& E_in, const Mat3& H_in) {
+  std::vector<uint32_t> swapped;
+  Mat3 F = F_in, E = E_in, H = H_in;
+  if (id1 > id2) {  // store in the id1 < id2 frame
+    if (n > 0) {
+      swapped.assign(inlier_matches, inlier_matches + 2 * n);
+      SwapColumns(&swapped);
+      inlier_matches = swapped.data();
+    }
+    F = Transposed(F);
+    E = Transposed(E);
+    Mat3 inv;
+    if (!AllZero(H) && Invert3x3(H, &inv)) H = inv;
+  }
+  const double qvec[4] = {1.0, 0.0, 0.0, 0.0}, tvec[3] = {0.0, 0.0, 0.0};
+  Stmt s(this, "INSERT OR REPLACE INTO two_view_geometries VALUES (?, ?, 2, ?, ?, ?, ?, ?, ?, ?)");
+  s.I64(1, ImagePairToPairId(id1, id2)); s.I64(2, n);
+  s.Blob(3, inlier_matches, static_cast<size_t>(n) * 8);
+  s.I64(4, config);
+  s.Blob(5, F.data(), 72); s.Blob(6, E.data(), 72); s.Blob(7, H.data(), 72);
+  s.Blob(8, qvec, 32); s.Blob(9, tvec, 24);
+  s.Step();
+}
+
+DatabaseTransaction::DatabaseTransaction(Database* db) : db_(db), exceptions_(std::uncaught_exceptions()) {
+  db_->Begin();
+}
+
+DatabaseTransaction::~DatabaseTransaction() {
+  try {
+    if (std::uncaught_exceptions() > exceptions_) db_->Rollback(); else db_->Commit();
+  } catch (...) {
+  }
+}
+
+}  // namespace b2mh

@@ -1,0 +1,230 @@
+"""CPU: the C++ host layer (pycolmap_b200.native = pybind11 module _core) -- option classes with the
+reference's dataclass behaviour (R:helpers.h:40-283), the C++ COLMAP database layer (interoperable
+with the Python one, byte for byte), pair generators, argument checks and error types.  No compute
+call is made: without a GPU the C ABI refuses to create a context."""
+import copy
+import pickle
+import sqlite3
+
+import numpy as np
+import pytest
+
+import pycolmap_b200 as pb
+import pycolmap_b200.native as nat
+from oracle import ransac as R
+from pycolmap_b200.database import Database as PyDatabase
+
+
+def test_option_defaults_match_reference_and_python_host():
+    for name in ("SiftMatchingOptions", "ExhaustiveMatchingOptions", "SequentialMatchingOptions", "RANSACOptions",
+                 "TwoViewGeometryOptions"):
+        assert getattr(nat, name)().todict() == getattr(pb, name)().todict(), name
+    t = nat.TwoViewGeometryOptions()   # .ransac keeps the C++ ctor defaults, RANSACOptions() the binding's
+    assert (t.ransac.max_error, t.ransac.confidence, t.ransac.min_num_trials, t.ransac.max_num_trials,
+            t.ransac.min_inlier_ratio) == (4.0, 0.999, 100, 10000, 0.25)
+    r = nat.RANSACOptions()
+    assert (r.max_error, r.min_inlier_ratio, r.confidence, r.min_num_trials, r.max_num_trials) == (
+        4.0, 0.01, 0.9999, 1000, 100000)
+
+
+def test_dataclass_behaviour():
+    t = nat.TwoViewGeometryOptions({"min_num_inliers": 30, "ransac": {"max_error": 2.0}})
+    assert t.min_num_inliers == 30 and t.ransac.max_error == 2.0 and t.ransac.confidence == 0.999
+    t2 = nat.TwoViewGeometryOptions(min_num_inliers=7)
+    t2.mergedict({"ransac": {"min_num_trials": 5}})
+    assert t2.todict()["ransac"]["min_num_trials"] == 5 and t2.todict()["min_num_inliers"] == 7
+    assert isinstance(t2.todict(recursive=False)["ransac"], nat.RANSACOptions)
+    assert "min_num_inliers = 7" in t2.summary() and "ransac: RANSACOptions:" in t2.summary()
+    assert "min_num_inliers: int = 7" in t2.summary(write_type=True)
+    with pytest.raises(AttributeError):
+        t.mergedict({"no_such_field": 1})
+    with pytest.raises(AttributeError):
+        t.no_such_field = 3
+    with pytest.raises(TypeError):
+        t.min_num_inliers = "many"
+    with pytest.raises(TypeError, match="max_ratio"):
+        nat.SiftMatchingOptions(max_ratio="high")
+    with pytest.raises(TypeError):
+        nat.SiftMatchingOptions({1: 2})
+    s = nat.SiftMatchingOptions(max_ratio=1)          # int -> float like pybind11
+    assert isinstance(s.max_ratio, float) and s.gpu_index == "-1"
+    t.ransac.max_error = 3.0                          # nested attribute access writes through
+    assert t.todict()["ransac"]["max_error"] == 3.0
+    t.ransac = {"max_error": 5.0}                     # implicit dict -> RANSACOptions (fresh Python defaults)
+    assert t.ransac.max_error == 5.0 and t.ransac.min_num_trials == 1000
+    c = copy.deepcopy(t)
+    c.ransac.max_error = 9.0
+    assert t.ransac.max_error == 5.0 and copy.copy(t) == t and c != t
+    assert pickle.loads(pickle.dumps(t)) == t
+    assert nat.Device("cuda") == nat.Device.cuda and nat.Device.auto.value == -1
+    with pytest.raises(IndexError, match="Invalid string value tpu"):   # std::out_of_range in the reference
+        nat.Device("tpu")
+    cfg = nat.TwoViewGeometryConfiguration
+    assert [cfg(i).name for i in range(9)] == ["UNDEFINED", "DEGENERATE", "CALIBRATED", "UNCALIBRATED", "PLANAR",
+                                                "PANORAMIC", "PLANAR_OR_PANORAMIC", "WATERMARK", "MULTIPLE"]
+    assert cfg("WATERMARK").value == 7 and nat.has_cuda is True
+
+
+def test_pair_generators_match_oracle_and_python_host():
+    for n, bs in [(1, 50), (2, 2), (49, 50), (50, 50), (51, 50), (101, 50), (7, 2), (130, 64), (0, 5)]:
+        blocks = nat.exhaustive_pair_blocks(n, bs)
+        got = np.concatenate(blocks) if blocks else np.zeros((0, 2), np.int32)
+        want = np.array(R.exhaustive_pairs(range(n), bs), np.int32).reshape(-1, 2)
+        assert got.dtype == np.int32 and np.array_equal(got, want)     # same pairs, same visiting order
+        assert len({(min(a, b), max(a, b)) for a, b in got}) == n * (n - 1) // 2
+    for n, ov, q in [(100, 3, True), (50, 10, False), (1000, 20, True), (3, 10, True), (0, 2, True)]:
+        assert np.array_equal(nat.sequential_pairs(n, ov, q),
+                              np.array(R.sequential_pairs(range(n), ov, q), np.int32).reshape(-1, 2))
+    with pytest.raises(ValueError):
+        nat.exhaustive_pair_blocks(5, 0)
+
+
+def _fill(db, rng):
+    cid = db.add_camera(0, 1600, 1200, [1200.0, 800.0, 600.0], True)
+    ids = [db.add_image(f"img{i:03d}.jpg", cid) for i in range(3)]
+    kp = rng.uniform(0, 1000, (10, 6)).astype(np.float32)
+    d = rng.integers(0, 255, (10, 128)).astype(np.uint8)
+    db.write_keypoints(ids[0], kp)
+    db.write_descriptors(ids[0], d)
+    return cid, ids, kp, d
+
+
+def test_database_roundtrip_cxx(tmp_path):
+    rng = np.random.default_rng(0)
+    with nat.Database(tmp_path / "db.db") as db:
+        cid, ids, kp, d = _fill(db, rng)
+        assert np.array_equal(db.read_keypoints(ids[0]), kp) and np.array_equal(db.read_descriptors(ids[0]), d)
+        assert db.read_keypoints(ids[1]).shape == (0, 2) and db.read_descriptors(ids[1]).shape == (0, 128)
+        cam = db.read_camera(cid)
+        assert cam["params"] == [1200.0, 800.0, 600.0] and cam["has_prior_focal_length"] == 1 and cam["model"] == 0
+        assert db.read_all_images() == [(ids[i], f"img{i:03d}.jpg", cid) for i in range(3)]
+        m = np.array([[0, 5], [3, 1]], np.uint32)
+        db.write_matches(ids[2], ids[1], m)                     # stored swapped (id1 < id2)
+        assert np.array_equal(db.read_matches(ids[2], ids[1]), m)
+        assert np.array_equal(db.read_matches(ids[1], ids[2]), m[:, ::-1])
+        assert db.exists_matches(ids[1], ids[2]) and not db.exists_matches(ids[0], ids[1])
+        F, H = rng.normal(size=(3, 3)), rng.normal(size=(3, 3))
+        db.write_two_view_geometry(ids[2], ids[1], nat.TwoViewGeometry("UNCALIBRATED", F=F, H=H, inlier_matches=m))
+        g = db.read_two_view_geometry(ids[1], ids[2])
+        assert g.config == nat.TwoViewGeometryConfiguration.UNCALIBRATED and np.allclose(g.F, F.T)
+        assert np.allclose(g.H, np.linalg.inv(H)) and np.array_equal(g.inlier_matches, m[:, ::-1])
+        g2 = db.read_two_view_geometry(ids[2], ids[1])          # read back in the written orientation
+        assert np.allclose(g2.F, F) and np.allclose(g2.H, H) and np.array_equal(g2.inlier_matches, m)
+        assert db.read_two_view_geometry(ids[0], ids[1]) is None
+        assert (db.num_images, db.num_cameras, db.num_matches, db.num_inlier_matches) == (3, 1, 2, 2)
+        assert (db.num_keypoints, db.num_descriptors) == (10, 10)
+        assert db.num_matched_image_pairs == 1 and db.num_verified_image_pairs == 1
+        with pytest.raises(ValueError):
+            db.read_camera(99)
+        with pytest.raises(ValueError):
+            db.write_descriptors(ids[1], np.zeros((4, 64), np.uint8))
+        # transactions: rollback drops the write
+        db.begin()
+        db.write_matches(ids[0], ids[1], m)
+        db.rollback()
+        assert not db.exists_matches(ids[0], ids[1])
+    assert nat.image_pair_to_pair_id(7, 3) == 3 * 2147483647 + 7 == pb.image_pair_to_pair_id(7, 3)
+    assert nat.pair_id_to_image_pair(nat.image_pair_to_pair_id(7, 3)) == (3, 7)
+    inv = nat.TwoViewGeometry("PLANAR", H=H, F=F, inlier_matches=m)
+    inv.invert()
+    assert np.allclose(inv.H, np.linalg.inv(H)) and np.allclose(inv.F, F.T) and np.array_equal(inv.inlier_matches, m[:, ::-1])
+    assert inv.cam2_from_cam1 is None and "PLANAR" in repr(inv)
+
+
+def test_database_is_interoperable_with_the_python_layer(tmp_path):
+    """Same schema and the same bytes: rows written by one layer read back identically through the
+    other, and through plain sqlite3 with the COLMAP column layout."""
+    rng = np.random.default_rng(1)
+    m = np.array([[0, 5], [3, 1], [7, 2]], np.uint32)
+    E, F, H = (rng.normal(size=(3, 3)) for _ in range(3))
+    paths = [tmp_path / "cxx.db", tmp_path / "py.db"]
+    with nat.Database(paths[0]) as a, PyDatabase(paths[1]) as b:
+        _, ids, kp, d = _fill(a, np.random.default_rng(2))
+        _fill(b, np.random.default_rng(2))
+        a.write_matches(ids[1], ids[0], m)
+        b.write_matches(ids[1], ids[0], m)
+        a.write_matches(ids[1], ids[2], np.zeros((0, 2), np.uint32))
+        b.write_matches(ids[1], ids[2], np.zeros((0, 2), np.uint32))
+        # written in the stored orientation (id1 < id2): no H inversion involved, so the bytes must agree
+        # (the swapped orientation is covered above; numpy's LU inverse differs from the closed form in the last bits)
+        a.write_two_view_geometry(ids[0], ids[1], nat.TwoViewGeometry("CALIBRATED", E=E, F=F, H=H, inlier_matches=m[:2]))
+        b.write_two_view_geometry(ids[0], ids[1], 2, m[:2], F=F, E=E, H=H)
+    dumps = []
+    for p in paths:
+        con = sqlite3.connect(p)
+        dumps.append({t: con.execute(f"SELECT * FROM {t} ORDER BY 1").fetchall()
+                      for t in ("cameras", "images", "keypoints", "descriptors", "matches", "two_view_geometries")})
+        con.close()
+    assert dumps[0] == dumps[1]
+    assert dumps[0]["matches"][1][1:] == (0, 2, b"")            # empty match list: zero rows, empty blob
+    with PyDatabase(paths[0]) as b, nat.Database(paths[1]) as a:   # cross-read
+        assert np.array_equal(b.read_matches(ids[0], ids[1]), m[:, ::-1])
+        g_py, g_cx = b.read_two_view_geometry(ids[0], ids[1]), a.read_two_view_geometry(ids[0], ids[1])
+        assert g_py["config"] == g_cx.config.value == 2
+        for k in "EFH":
+            assert np.allclose(g_py[k], getattr(g_cx, k)) and np.allclose(g_py[k], {"E": E, "F": F, "H": H}[k])
+        assert np.array_equal(g_py["inlier_matches"], g_cx.inlier_matches)
+        assert np.array_equal(a.read_keypoints(ids[0]), b.read_keypoints(ids[0]))
+
+
+def test_argument_checks_before_any_gpu_work(tmp_path):
+    with pytest.raises(ValueError, match=r"\[match_features.h:32\] Check Failed: File .* does not exist"):
+        nat.match_exhaustive(tmp_path / "missing.db")
+    with pytest.raises(ValueError, match="does not exist"):
+        nat.match_sequential(str(tmp_path / "missing.db"))
+    with pytest.raises(ValueError, match="does not exist"):
+        nat.verify_matches(tmp_path / "missing.db", tmp_path / "pairs.txt")
+    db = tmp_path / "db.db"
+    nat.Database(db).close()
+    with pytest.raises(ValueError, match="does not exist"):
+        nat.verify_matches(db, tmp_path / "pairs.txt")
+    with pytest.raises(ValueError, match="no CPU path"):
+        nat.match_exhaustive(db, device=nat.Device.cpu)
+    with pytest.raises(ValueError, match="no CPU path"):
+        nat.match_exhaustive(db, device="cpu")                  # enum from its name at the call site
+    with pytest.raises(TypeError):
+        nat.match_exhaustive(db, sift_options=3)
+    with pytest.raises(TypeError):
+        nat.match_exhaustive(db, sift_options={"max_ratio": "high"})
+    with pytest.raises(TypeError):
+        nat.match_exhaustive(database=db)                       # keyword names are part of the contract
+    cam = dict(model=0, width=1, height=1, params=[1, 0, 0])
+    with pytest.raises(ValueError):
+        nat.estimate_two_view_geometry(cam, np.zeros((3, 3)), cam, np.zeros((3, 2)))
+    with pytest.raises(ValueError, match="points1.size"):
+        nat.fundamental_matrix_estimation(np.zeros((4, 2)), np.zeros((5, 2)))
+    with pytest.raises(ValueError, match="not supported"):
+        nat.estimate_two_view_geometry(dict(cam, model="OPENCV"), np.zeros((3, 2)), cam, np.zeros((3, 2)))
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute entry point fails loudly with the C ABI's B2M_ENODEV message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nat.Context()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nat.squared_sampson_error(np.zeros((2, 2)), np.zeros((2, 2)), np.eye(3))
+
+
+def test_ctrl_c_surfaces_as_keyboard_interrupt():
+    """PyWait behaviour (R:helpers.h:335-347): the blocking call runs on a worker thread with the GIL
+    released while the caller polls for signals; SIGINT becomes KeyboardInterrupt once the worker is done."""
+    import os
+    import signal
+    import threading
+    from pycolmap_b200 import _core
+    import time
+    t0 = time.time()
+    threading.Timer(0.15, lambda: os.kill(os.getpid(), signal.SIGINT)).start()
+    with pytest.raises(KeyboardInterrupt):
+        _core._sleep_interruptible(0.6)
+    assert 0.5 < time.time() - t0 < 5.0
+    # other Python threads keep running while the call blocks (GIL released)
+    ticks = []
+    th = threading.Thread(target=lambda: [ticks.append(time.time()) or time.sleep(0.01) for _ in range(20)])
+    th.start()
+    _core._sleep_interruptible(0.3)
+    th.join()
+    assert len(ticks) == 20

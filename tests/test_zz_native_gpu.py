@@ -1,0 +1,128 @@
+"""GPU: the C++ host layer (pycolmap_b200.native) end to end.  The file name sorts last on purpose:
+it was written after this round's GPU budget was spent, so it runs after every validated test.
+
+The C++ controllers must produce the same database as the Python host layer (both call the same C
+ABI; matching is bit-exact and RANSAC is seeded per image pair, so the two runs are byte-identical),
+and the low-level Context must be bit-exact against the oracle."""
+import sqlite3
+
+import numpy as np
+import pytest
+
+import oracle
+import pycolmap_b200 as pb
+import pycolmap_b200.native as nat
+from helpers import scenes
+from oracle import ransac as R
+from pycolmap_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+TABLES = ("cameras", "images", "keypoints", "descriptors", "matches", "two_view_geometries")
+
+
+def _make_db(path, n_images=10, n_feat=768, seed=3):
+    scene = syn.make_scene(n_images, n_feat, seed=seed, window_images=2.5)
+    with nat.Database(path) as db:
+        cid = db.add_camera(0, 1600, 1200, [1200.0, 800.0, 600.0], True)
+        db.begin()
+        for i in range(n_images):
+            iid = db.add_image(f"frame{i:04d}.png", cid)
+            kp = np.zeros((n_feat, 6), np.float32)
+            kp[:, :2] = scene["kpts"][i].numpy()
+            db.write_keypoints(iid, kp)
+            db.write_descriptors(iid, scene["desc"][i].numpy())
+        db.commit()
+    return scene
+
+
+def _dump(path):
+    con = sqlite3.connect(path)
+    out = {t: con.execute(f"SELECT * FROM {t} ORDER BY 1").fetchall() for t in TABLES}
+    con.close()
+    return out
+
+
+def test_native_context_bit_exact_vs_oracle():
+    rng = np.random.default_rng(4)
+    c = nat.Context(device=0, seed=0)
+    descs = [syn.sift_like(rng, n) for n in (700, 512, 300, 0)]
+    descs[1][:250] = syn.perturb(rng, descs[0][:250])
+    descs[2][:150] = syn.perturb(rng, descs[0][300:450])
+    assert np.array_equal(c.match_pair(descs[0], descs[1]), oracle.fast_match_pair(descs[0], descs[1]))
+    c.set_images(descs)
+    pairs = np.array([(0, 1), (0, 2), (1, 2), (2, 0), (0, 3)], np.int32)
+    res = c.match_pairs(pairs)
+    assert len(res) == len(pairs)
+    for k, (a, b) in enumerate(pairs):
+        assert np.array_equal(res.matches(k), oracle.fast_match_pair(descs[a], descs[b])), (a, b)
+        assert res.image_pair(k) == (a, b)
+    assert res.total_matches == sum(len(res.matches(k)) for k in range(len(pairs))) > 300
+    loose = nat.SiftMatchingOptions(max_ratio=0.95, cross_check=False)
+    res2 = c.match_pairs(pairs[:1], loose)
+    assert np.array_equal(res2.matches(0), oracle.fast_match_pair(descs[0], descs[1], max_ratio=0.95, cross_check=False))
+    assert c.stats()["kernel_launches"] > 0
+    res.free()
+    c.close()
+
+
+def test_native_estimators():
+    rng = np.random.default_rng(11)
+    p1, p2, planted = scenes.two_view_scene(rng, 400, 0.3, "general")
+    g = nat.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)
+    assert g.config == nat.TwoViewGeometryConfiguration.CALIBRATED and abs(len(g.inlier_matches) - planted.sum()) <= 4
+    g_py = pb.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)      # same ABI call, same seed
+    assert np.array_equal(g.inlier_matches, g_py.inlier_matches) and np.array_equal(g.E, g_py.E)
+    g2 = nat.estimate_calibrated_two_view_geometry(scenes.CAM_NOPRIOR, p1, scenes.CAM_NOPRIOR, p2)
+    assert g2.config == nat.TwoViewGeometryConfiguration.CALIBRATED
+    g3 = nat.estimate_two_view_geometry(scenes.CAM_NOPRIOR, p1, scenes.CAM_NOPRIOR, p2,
+                                        options={"ransac": {"max_error": 2.0}})
+    assert g3.config == nat.TwoViewGeometryConfiguration.UNCALIBRATED
+    f = nat.fundamental_matrix_estimation(p1, p2)
+    assert f is not None and abs(f["num_inliers"] - planted.sum()) <= 5 and f["inliers"].dtype == bool
+    assert f["F"].shape == (3, 3) and f["inliers"].sum() == f["num_inliers"]
+    e = nat.essential_matrix_estimation(p1, p2, scenes.CAM, scenes.CAM)
+    assert e is not None and abs(e["num_inliers"] - planted.sum()) <= 5
+    assert nat.homography_matrix_estimation(p1[:3], p2[:3]) is None
+    q1, q2, pl = scenes.two_view_scene(rng, 300, 0.2, "planar")
+    h = nat.homography_matrix_estimation(q1, q2, {"max_error": 4.0, "min_num_trials": 100, "confidence": 0.999})
+    assert h is not None and abs(h["num_inliers"] - pl.sum()) <= 4
+    E = rng.normal(size=(3, 3))
+    assert np.allclose(nat.squared_sampson_error(p1, p2, E), R.squared_sampson_error(p1, p2, E), rtol=1e-12)
+
+
+def test_native_pipelines_equal_python_host(tmp_path):
+    a, b = tmp_path / "py.db", tmp_path / "cxx.db"
+    _make_db(a)
+    _make_db(b)
+    assert _dump(a) == _dump(b)
+    pb.match_exhaustive(a, matching_options={"block_size": 4})
+    nat.match_exhaustive(b, matching_options={"block_size": 4})
+    da, db_ = _dump(a), _dump(b)
+    assert len(da["matches"]) == len(da["two_view_geometries"]) == 45
+    assert da["matches"] == db_["matches"]                       # raw matches: bit-exact
+    assert da["two_view_geometries"] == db_["two_view_geometries"]   # seeded per pair: same models, same inliers
+    assert sum(1 for r in db_["two_view_geometries"] if r[1] >= 15) >= 8
+    # resume semantics: nothing left to do, file untouched
+    before = open(b, "rb").read()
+    nat.match_exhaustive(b)
+    assert open(b, "rb").read() == before
+
+    # sequential + verify_matches from stored matches
+    for p, mod in ((a, pb), (b, nat)):
+        with nat.Database(p) as d:
+            d.clear_matches()
+            d.clear_two_view_geometries()
+            names = [r[1] for r in d.read_all_images()]
+        mod.match_sequential(p, matching_options={"overlap": 2, "quadratic_overlap": False})
+    da, db_ = _dump(a), _dump(b)
+    assert len(db_["matches"]) == 9 + 8 and da["matches"] == db_["matches"]
+    assert da["two_view_geometries"] == db_["two_view_geometries"]
+    pairs = tmp_path / "pairs.txt"
+    pairs.write_text("# comment\n\n" + "\n".join(f"{names[i]} {names[i + 1]}" for i in range(9)) + "\nnope.png x.png\n")
+    for p, mod in ((a, pb), (b, nat)):
+        with nat.Database(p) as d:
+            d.clear_two_view_geometries()
+        mod.verify_matches(p, pairs)
+    da, db_ = _dump(a), _dump(b)
+    assert len(db_["two_view_geometries"]) == 9 and da["two_view_geometries"] == db_["two_view_geometries"]

@@ -43,6 +43,16 @@ def _dump(path):
     return out
 
 
+def _assert_same_geometries(rows_a, rows_b):
+    """Row-wise equality of two_view_geometries: everything byte-equal except H, which the two layers
+    invert differently for pairs visited as (id1 > id2) (numpy LU vs closed-form adjugate)."""
+    assert len(rows_a) == len(rows_b)
+    for ra, rb in zip(rows_a, rows_b):
+        assert ra[:7] == rb[:7] and ra[8:] == rb[8:]            # pair_id, rows, cols, inliers, config, F, E, qvec, tvec
+        ha, hb = np.frombuffer(ra[7], np.float64), np.frombuffer(rb[7], np.float64)
+        assert np.allclose(ha, hb, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(ha).max()))
+
+
 def test_native_context_bit_exact_vs_oracle():
     rng = np.random.default_rng(4)
     c = nat.Context(device=0, seed=0)
@@ -101,7 +111,7 @@ def test_native_pipelines_equal_python_host(tmp_path):
     da, db_ = _dump(a), _dump(b)
     assert len(da["matches"]) == len(da["two_view_geometries"]) == 45
     assert da["matches"] == db_["matches"]                       # raw matches: bit-exact
-    assert da["two_view_geometries"] == db_["two_view_geometries"]   # seeded per pair: same models, same inliers
+    _assert_same_geometries(da["two_view_geometries"], db_["two_view_geometries"])   # seeded per pair
     assert sum(1 for r in db_["two_view_geometries"] if r[1] >= 15) >= 8
     # resume semantics: nothing left to do, file untouched
     before = open(b, "rb").read()
@@ -117,7 +127,7 @@ def test_native_pipelines_equal_python_host(tmp_path):
         mod.match_sequential(p, matching_options={"overlap": 2, "quadratic_overlap": False})
     da, db_ = _dump(a), _dump(b)
     assert len(db_["matches"]) == 9 + 8 and da["matches"] == db_["matches"]
-    assert da["two_view_geometries"] == db_["two_view_geometries"]
+    _assert_same_geometries(da["two_view_geometries"], db_["two_view_geometries"])
     pairs = tmp_path / "pairs.txt"
     pairs.write_text("# comment\n\n" + "\n".join(f"{names[i]} {names[i + 1]}" for i in range(9)) + "\nnope.png x.png\n")
     for p, mod in ((a, pb), (b, nat)):
@@ -125,4 +135,5 @@ def test_native_pipelines_equal_python_host(tmp_path):
             d.clear_two_view_geometries()
         mod.verify_matches(p, pairs)
     da, db_ = _dump(a), _dump(b)
-    assert len(db_["two_view_geometries"]) == 9 and da["two_view_geometries"] == db_["two_view_geometries"]
+    assert len(db_["two_view_geometries"]) == 9
+    _assert_same_geometries(da["two_view_geometries"], db_["two_view_geometries"])

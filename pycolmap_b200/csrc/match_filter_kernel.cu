@@ -626,12 +626,15 @@ __global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p
 cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p_in,
                              const uint8_t* desc, int n_pairs, int max_strips, int n_dirs, int num_sms,
                              cudaStream_t stream, cudaEvent_t after_filter) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: several contexts on different GPUs may live in one process
+  static bool attr_set[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(b2m_k1_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(kSmemBytes));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   MatchParams p = p_in;
   cudaError_t e = cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * 2 * n_pairs, stream);

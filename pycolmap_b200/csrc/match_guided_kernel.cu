@@ -250,12 +250,15 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
 
 cudaError_t launch_k1_guided(const CUtensorMap& tmap, const MatchParams& p, const GuidedParams& g, int n_pairs,
                              int max_strips, int n_dirs, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: several contexts on different GPUs may live in one process
+  static bool attr_set[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(b2m_k1_guided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(kSmemBytes));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   dim3 grid(max_strips, n_dirs, n_pairs);
   b2m_k1_guided_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, p, g);

@@ -280,12 +280,15 @@ __global__ void __launch_bounds__(256) b2m_crosscheck_compact_kernel(const Compa
 
 cudaError_t launch_k1_match(const CUtensorMap& tmap, const MatchParams& p, int n_pairs, int max_strips, int n_dirs,
                             cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: several contexts on different GPUs may live in one process
+  static bool attr_set[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(b2m_k1_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(kSmemBytes));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   dim3 grid(max_strips, n_dirs, n_pairs);
   b2m_k1_match_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, p);

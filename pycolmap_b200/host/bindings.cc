@@ -154,11 +154,11 @@ void RunInterruptible(Fn&& fn) {
   if (error) std::rethrow_exception(error);
 }
 
-int ResolveDevice(Device device, const SiftMatchingOptions& sift) {
+std::vector<int> ResolveDevices(Device device, const SiftMatchingOptions& sift) {
   // IsGPU / VerifyGPUParams (R:utils.h:11-31): `auto` is the GPU; this build has nothing else.
   if (device == Device::CPU)
     throw std::invalid_argument("[bindings.cc] pycolmap_b200 has no CPU path: use Device.auto or Device.cuda");
-  return FirstGpuIndex(sift.gpu_index);
+  return ParseGpuIndices(sift.gpu_index);
 }
 
 // ---- estimators --------------------------------------------------------------------------------------
@@ -415,7 +415,7 @@ PYBIND11_MODULE(_core, m) {
            TwoViewGeometryOptions verification_options, Device device) {
           const std::string path = FsPath(database_path);
           CheckFileExists(path, "match_features.h:32");  // before the device check, R:match_features.h:32-38
-          const int dev = ResolveDevice(device, sift_options);
+          const std::vector<int> dev = ResolveDevices(device, sift_options);
           RunInterruptible([&] { MatchExhaustive(path, sift_options, matching_options, verification_options, dev); });
         },
         "database_path"_a, "sift_options"_a = SiftMatchingOptions(), "matching_options"_a = ExhaustiveMatchingOptions(),
@@ -426,7 +426,7 @@ PYBIND11_MODULE(_core, m) {
            TwoViewGeometryOptions verification_options, Device device) {
           const std::string path = FsPath(database_path);
           CheckFileExists(path, "match_features.h:32");  // before the device check, R:match_features.h:32-38
-          const int dev = ResolveDevice(device, sift_options);
+          const std::vector<int> dev = ResolveDevices(device, sift_options);
           RunInterruptible([&] { MatchSequential(path, sift_options, matching_options, verification_options, dev); });
         },
         "database_path"_a, "sift_options"_a = SiftMatchingOptions(), "matching_options"_a = SequentialMatchingOptions(),
@@ -523,6 +523,16 @@ PYBIND11_MODULE(_core, m) {
           return out;
         },
         "n_images"_a, "block_size"_a);
+  m.def("parse_gpu_indices", &ParseGpuIndices, "gpu_index"_a);
+  m.def("split_pairs_by_cost",
+        [](const ArrI32& pairs, const std::vector<int32_t>& n_feat, int parts) {
+          if (pairs.size() % 2) throw std::invalid_argument("[bindings.cc] Check Failed: pairs is N x 2 int32");
+          for (py::ssize_t i = 0; i < pairs.size(); ++i)
+            if (pairs.data()[i] < 0 || pairs.data()[i] >= static_cast<int32_t>(n_feat.size()))
+              throw std::invalid_argument("[bindings.cc] Check Failed: pair index < number of images");
+          return SplitPairsByCost(PairList(pairs.data(), pairs.data() + pairs.size()), n_feat, parts);
+        },
+        "pairs"_a, "n_feat"_a, "parts"_a);
   m.def("sequential_pairs",
         [](int n_images, int overlap, bool quadratic_overlap) {
           const PairList p = SequentialPairs(n_images, overlap, quadratic_overlap);

@@ -9,6 +9,7 @@
 #include <set>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
 
 namespace b2mh {
@@ -72,16 +73,47 @@ b2m_camera ToAbi(const CameraRow& c) {
   return b;
 }
 
-int FirstGpuIndex(const std::string& gpu_index) {
-  std::string first = gpu_index.substr(0, gpu_index.find(','));
-  first.erase(std::remove_if(first.begin(), first.end(), [](unsigned char ch) { return std::isspace(ch); }),
-              first.end());
-  if (first.empty() || first == "-1") return 0;
-  try {
-    return std::max(0, std::stoi(first));
-  } catch (const std::exception&) {
-    throw std::invalid_argument("[controllers.cc] Check Failed: gpu_index is a comma-separated list of integers");
+std::vector<int> ParseGpuIndices(const std::string& gpu_index) {
+  std::vector<int> out;
+  std::stringstream ss(gpu_index);
+  std::string item;
+  while (std::getline(ss, item, ',')) {
+    item.erase(std::remove_if(item.begin(), item.end(), [](unsigned char ch) { return std::isspace(ch); }), item.end());
+    if (item.empty()) continue;
+    size_t used = 0;
+    int v = 0;
+    try {
+      v = std::stoi(item, &used);
+    } catch (const std::exception&) {
+      used = 0;
+    }
+    if (used != item.size() || v < -1)
+      throw std::invalid_argument("[controllers.cc] Check Failed: gpu_index is a comma-separated list of integers >= -1");
+    if (v == -1) v = 0;  // see the header: -1 selects device 0 here
+    if (std::find(out.begin(), out.end(), v) == out.end()) out.push_back(v);
   }
+  if (out.empty()) out.push_back(0);
+  return out;
+}
+
+std::vector<int64_t> SplitPairsByCost(const PairList& pairs, const std::vector<int32_t>& n_feat, int parts) {
+  const int64_t n = static_cast<int64_t>(pairs.size() / 2);
+  parts = std::max(1, parts);
+  std::vector<int64_t> cut(static_cast<size_t>(parts) + 1, n);
+  cut[0] = 0;
+  if (parts == 1 || n == 0) return cut;
+  // cost of a pair = work of its distance matrix (K1 dominates): n_feat[a] * n_feat[b], at least 1
+  std::vector<double> prefix(static_cast<size_t>(n) + 1, 0.0);
+  for (int64_t k = 0; k < n; ++k) {
+    const double c = static_cast<double>(n_feat[pairs[2 * k]]) * static_cast<double>(n_feat[pairs[2 * k + 1]]);
+    prefix[k + 1] = prefix[k] + std::max(1.0, c);
+  }
+  for (int d = 1; d < parts; ++d) {
+    const double target = prefix[n] * d / parts;
+    cut[d] = std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin();
+    cut[d] = std::min(n, std::max(cut[d], cut[d - 1]));
+  }
+  return cut;
 }
 
 // ---- pair generators -----------------------------------------------------------------------------
@@ -147,6 +179,13 @@ void ThrowOnError(b2m_ctx* ctx, int rc) {
   }
 }
 
+std::vector<b2m_ctx*> Engine::GetAll(const std::vector<int>& devices) {
+  std::vector<b2m_ctx*> out;
+  for (int d : devices) out.push_back(Get(d));
+  if (out.empty()) out.push_back(Get(0));
+  return out;
+}
+
 b2m_ctx* Engine::Get(int device) {
   if (device < 0 || device >= kMaxDevices) throw std::invalid_argument("[controllers.cc] Check Failed: 0 <= gpu index < 64");
   std::lock_guard<std::mutex> lock(g_engine_mutex);
@@ -188,10 +227,12 @@ struct LoadedSet {
   std::vector<int64_t> ids;
   std::vector<std::string> names;
   std::vector<int64_t> camera_ids;
+  std::vector<int32_t> n_feat;
 };
 
-// FeatureMatcherCache: every image's descriptors, keypoint positions and camera go to the GPU once.
-LoadedSet LoadImageSet(Database& db, b2m_ctx* ctx, bool order_by_name) {
+// FeatureMatcherCache: every image's descriptors, keypoint positions and camera go to the GPU once
+// (to every GPU of the gpu_index list: the set is small next to 180 GB and pairs then shard freely).
+LoadedSet LoadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, bool order_by_name) {
   std::vector<ImageRow> images = db.ReadAllImages();
   if (order_by_name)
     std::stable_sort(images.begin(), images.end(), [](const ImageRow& a, const ImageRow& b) { return a.name < b.name; });
@@ -226,8 +267,18 @@ LoadedSet LoadImageSet(Database& db, b2m_ctx* ctx, bool order_by_name) {
     dptr[i] = desc[i].data.data();
     kptr[i] = xy[i].data();
   }
-  ThrowOnError(ctx, b2m_set_images(ctx, static_cast<int32_t>(images.size()), n_feat.data(), dptr.data(), kptr.data(),
-                                   cams.data()));
+  std::vector<int> rc(ctxs.size(), B2M_OK);
+  std::vector<std::thread> workers;
+  for (size_t d = 1; d < ctxs.size(); ++d)
+    workers.emplace_back([&, d] {
+      rc[d] = b2m_set_images(ctxs[d], static_cast<int32_t>(images.size()), n_feat.data(), dptr.data(), kptr.data(),
+                             cams.data());
+    });
+  rc[0] = b2m_set_images(ctxs[0], static_cast<int32_t>(images.size()), n_feat.data(), dptr.data(), kptr.data(),
+                         cams.data());
+  for (std::thread& w : workers) w.join();
+  for (size_t d = 0; d < ctxs.size(); ++d) ThrowOnError(ctxs[d], rc[d]);
+  L.n_feat = std::move(n_feat);
   return L;
 }
 
@@ -245,9 +296,13 @@ struct ResultsGuard {
 };
 
 // FeatureMatcherController::Match (row P3): skip self pairs, duplicates and pairs with both results
-// stored; match + verify the rest on the GPU; write both tables in one transaction per chunk.
-void MatchPairsIntoDb(Database& db, b2m_ctx* ctx, const LoadedSet& L, const std::vector<PairList>& chunks,
-                      const b2m_sift_opts& sift, const b2m_tvg_opts& tvg, bool skip_existing) {
+// stored; match + verify the rest on the GPU(s); write both tables in one transaction per chunk.
+// With several contexts the chunk is cut into contiguous cost-balanced slices, one host thread per GPU
+// (upstream: one matcher worker per entry of gpu_index); results are written in pair order, so the
+// database does not depend on the number of GPUs.
+void MatchPairsIntoDb(Database& db, const std::vector<b2m_ctx*>& ctxs, const LoadedSet& L,
+                      const std::vector<PairList>& chunks, const b2m_sift_opts& sift, const b2m_tvg_opts& tvg,
+                      bool skip_existing) {
   std::unordered_set<int64_t> have_m, have_g;
   if (skip_existing) {
     have_m = db.ExistingPairIds("matches");
@@ -267,18 +322,31 @@ void MatchPairsIntoDb(Database& db, b2m_ctx* ctx, const LoadedSet& L, const std:
       todo.push_back(b);
     }
     if (todo.empty()) continue;
-    ResultsGuard res;
-    ThrowOnError(ctx, b2m_match_pairs(ctx, todo.data(), static_cast<int64_t>(todo.size() / 2), &sift, &tvg, &res.r));
+    const std::vector<int64_t> cut = SplitPairsByCost(todo, L.n_feat, static_cast<int>(ctxs.size()));
+    std::vector<ResultsGuard> res(ctxs.size());
+    std::vector<int> rc(ctxs.size(), B2M_OK);
+    auto run = [&](size_t d) {
+      const int64_t n = cut[d + 1] - cut[d];
+      if (n > 0) rc[d] = b2m_match_pairs(ctxs[d], todo.data() + 2 * cut[d], n, &sift, &tvg, &res[d].r);
+    };
+    std::vector<std::thread> workers;
+    for (size_t d = 1; d < ctxs.size(); ++d) workers.emplace_back(run, d);
+    run(0);
+    for (std::thread& w : workers) w.join();
+    for (size_t d = 0; d < ctxs.size(); ++d) ThrowOnError(ctxs[d], rc[d]);
     DatabaseTransaction tx(&db);
-    const int64_t n = b2m_results_num_pairs(res.r);
-    for (int64_t k = 0; k < n; ++k) {
-      b2m_pair_view v;
-      memset(&v, 0, sizeof(v));
-      v.struct_size = sizeof(v);
-      ThrowOnError(ctx, b2m_results_get(res.r, k, &v));
-      const int64_t id1 = L.ids[todo[2 * k]], id2 = L.ids[todo[2 * k + 1]];
-      db.WriteMatches(id1, id2, v.matches, v.n_matches);
-      db.WriteTwoViewGeometry(id1, id2, v.config, v.inlier_matches, v.n_inliers, ToMat3(v.F), ToMat3(v.E), ToMat3(v.H));
+    for (size_t d = 0; d < ctxs.size(); ++d) {
+      const int64_t n = res[d].r ? b2m_results_num_pairs(res[d].r) : 0;
+      for (int64_t k = 0; k < n; ++k) {
+        b2m_pair_view v;
+        memset(&v, 0, sizeof(v));
+        v.struct_size = sizeof(v);
+        ThrowOnError(ctxs[d], b2m_results_get(res[d].r, k, &v));
+        const int64_t id1 = L.ids[todo[2 * (cut[d] + k)]], id2 = L.ids[todo[2 * (cut[d] + k) + 1]];
+        db.WriteMatches(id1, id2, v.matches, v.n_matches);
+        db.WriteTwoViewGeometry(id1, id2, v.config, v.inlier_matches, v.n_inliers, ToMat3(v.F), ToMat3(v.E),
+                                ToMat3(v.H));
+      }
     }
   }
 }
@@ -302,27 +370,27 @@ std::vector<PairList> Chunked(const std::vector<PairList>& blocks, size_t target
 
 void MatchExhaustive(const std::string& database_path, const SiftMatchingOptions& sift,
                      const ExhaustiveMatchingOptions& matching, const TwoViewGeometryOptions& verification,
-                     int device_index) {
+                     const std::vector<int>& devices) {
   CheckFileExists(database_path, "match_features.h:32");
   if (matching.block_size <= 1) throw std::invalid_argument("[controllers.cc] Check Failed: block_size > 1");
-  b2m_ctx* ctx = Engine::Get(device_index);
+  const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
   Database db(database_path);
-  const LoadedSet L = LoadImageSet(db, ctx, /*order_by_name=*/false);
-  MatchPairsIntoDb(db, ctx, L, Chunked(ExhaustivePairBlocks(static_cast<int>(L.ids.size()), matching.block_size)),
+  const LoadedSet L = LoadImageSet(db, ctxs, /*order_by_name=*/false);
+  MatchPairsIntoDb(db, ctxs, L, Chunked(ExhaustivePairBlocks(static_cast<int>(L.ids.size()), matching.block_size)),
                    ToAbi(sift), ToAbi(verification), /*skip_existing=*/true);
 }
 
 void MatchSequential(const std::string& database_path, const SiftMatchingOptions& sift,
                      const SequentialMatchingOptions& matching, const TwoViewGeometryOptions& verification,
-                     int device_index) {
+                     const std::vector<int>& devices) {
   CheckFileExists(database_path, "match_features.h:32");
   if (matching.loop_detection)
     throw std::invalid_argument("[controllers.cc] loop_detection needs a vocabulary tree: out of scope (SURVEY.md row B6)");
   if (matching.overlap < 1) throw std::invalid_argument("[controllers.cc] Check Failed: overlap > 0");
-  b2m_ctx* ctx = Engine::Get(device_index);
+  const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
   Database db(database_path);
-  const LoadedSet L = LoadImageSet(db, ctx, /*order_by_name=*/true);
-  MatchPairsIntoDb(db, ctx, L,
+  const LoadedSet L = LoadImageSet(db, ctxs, /*order_by_name=*/true);
+  MatchPairsIntoDb(db, ctxs, L,
                    {SequentialPairs(static_cast<int>(L.ids.size()), matching.overlap, matching.quadratic_overlap)},
                    ToAbi(sift), ToAbi(verification), /*skip_existing=*/true);
 }
@@ -333,7 +401,7 @@ void VerifyMatches(const std::string& database_path, const std::string& pairs_pa
   CheckFileExists(pairs_path, "match_features.h:55");
   b2m_ctx* ctx = Engine::Get(0);
   Database db(database_path);
-  const LoadedSet L = LoadImageSet(db, ctx, /*order_by_name=*/false);
+  const LoadedSet L = LoadImageSet(db, {ctx}, /*order_by_name=*/false);
   std::unordered_map<std::string, int> index_of;
   for (size_t i = 0; i < L.names.size(); ++i) index_of[L.names[i]] = static_cast<int>(i);
 
@@ -362,7 +430,7 @@ void VerifyMatches(const std::string& database_path, const std::string& pairs_pa
   }
   const b2m_tvg_opts tvg = ToAbi(options);
   if (!todo_match.empty())
-    MatchPairsIntoDb(db, ctx, L, {todo_match}, ToAbi(SiftMatchingOptions()), tvg, /*skip_existing=*/false);
+    MatchPairsIntoDb(db, {ctx}, L, {todo_match}, ToAbi(SiftMatchingOptions()), tvg, /*skip_existing=*/false);
 
   DatabaseTransaction tx(&db);
   for (const auto& [a, b] : todo_verify) {

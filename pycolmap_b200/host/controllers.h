@@ -78,8 +78,11 @@ b2m_ransac_opts ToAbi(const RANSACOptions& o);
 b2m_tvg_opts ToAbi(const TwoViewGeometryOptions& o);
 // Database camera -> ABI camera; throws std::invalid_argument for models the verifier does not take.
 b2m_camera ToAbi(const CameraRow& c);
-// First entry of the comma-separated gpu_index list; "-1" / "" -> 0 (R:pipeline/match_features.h:76-81).
-int FirstGpuIndex(const std::string& gpu_index);
+// SiftMatchingOptions.gpu_index: comma-separated CUDA ordinals, "0,1,2,3" = one matcher per listed GPU
+// (R:pipeline/match_features.h:76-81).  Duplicates are dropped, order kept.  Deviation: upstream expands
+// "-1" to every visible GPU; here "-1" (the default) means device 0 until the all-GPU default has been
+// validated on a multi-GPU box -- list the devices explicitly to use more than one.
+std::vector<int> ParseGpuIndices(const std::string& gpu_index);
 
 // ---- pair generators (rows P1, P2) -------------------------------------------------------------
 using PairList = std::vector<int32_t>;  // [n x 2] image indices, flattened
@@ -91,11 +94,16 @@ std::vector<PairList> ExhaustivePairBlocks(int n_images, int block_size);
 // out-of-range dropped, duplicates removed, generation order kept.
 PairList SequentialPairs(int n_images, int overlap, bool quadratic_overlap);
 
+// Cut `pairs` into `parts` contiguous slices of about equal cost (cost of a pair = n_feat[a] * n_feat[b],
+// the size of its distance matrix).  Returns parts + 1 offsets (in pairs), cut[0] = 0, cut[parts] = n.
+std::vector<int64_t> SplitPairsByCost(const PairList& pairs, const std::vector<int32_t>& n_feat, int parts);
+
 // ---- engine: one b2m_ctx per process and GPU -----------------------------------------------------
 class Engine {
  public:
   // Lazily creates the context; throws std::runtime_error / std::invalid_argument with b2m_last_error().
   static b2m_ctx* Get(int device);
+  static std::vector<b2m_ctx*> GetAll(const std::vector<int>& devices);
   static void RequestStopAll();  // async-signal-safe flags only (b2m_request_stop on every live context)
   static void DestroyAll();
 };
@@ -114,10 +122,10 @@ void CheckFileExists(const std::string& path, const char* where);
 // ---- pipelines -----------------------------------------------------------------------------------
 void MatchExhaustive(const std::string& database_path, const SiftMatchingOptions& sift,
                      const ExhaustiveMatchingOptions& matching, const TwoViewGeometryOptions& verification,
-                     int device_index);
+                     const std::vector<int>& devices);
 void MatchSequential(const std::string& database_path, const SiftMatchingOptions& sift,
                      const SequentialMatchingOptions& matching, const TwoViewGeometryOptions& verification,
-                     int device_index);
+                     const std::vector<int>& devices);
 void VerifyMatches(const std::string& database_path, const std::string& pairs_path,
                    const TwoViewGeometryOptions& options);
 

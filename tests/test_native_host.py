@@ -228,3 +228,30 @@ def test_ctrl_c_surfaces_as_keyboard_interrupt():
     _core._sleep_interruptible(0.3)
     th.join()
     assert len(ticks) == 20
+
+
+def test_gpu_index_list_and_pair_sharding():
+    """SiftMatchingOptions.gpu_index "0,1,2,3" = one matcher per listed GPU (R:pipeline/match_features.h:76-81);
+    a chunk of pairs is cut into contiguous slices of equal distance-matrix cost."""
+    from pycolmap_b200 import _core
+    assert _core.parse_gpu_indices("-1") == [0] and _core.parse_gpu_indices("") == [0]
+    assert _core.parse_gpu_indices("0,1, 2 ,3") == [0, 1, 2, 3] and _core.parse_gpu_indices("3,3,1") == [3, 1]
+    for bad in ("a", "0,x", "1.5", "-2"):
+        with pytest.raises(ValueError):
+            _core.parse_gpu_indices(bad)
+    rng = np.random.default_rng(0)
+    n_feat = rng.integers(100, 8192, 40).astype(np.int32).tolist()
+    pairs = np.concatenate(nat.exhaustive_pair_blocks(40, 7))
+    cost = np.array([n_feat[a] * n_feat[b] for a, b in pairs], np.float64)
+    for parts in (1, 2, 3, 8):
+        cut = _core.split_pairs_by_cost(pairs, n_feat, parts)
+        assert len(cut) == parts + 1 and cut[0] == 0 and cut[-1] == len(pairs) and sorted(cut) == cut
+        shares = np.array([cost[cut[d]:cut[d + 1]].sum() for d in range(parts)]) / cost.sum()
+        assert np.all(np.abs(shares - 1.0 / parts) < 0.02), shares     # within one pair's cost of the ideal
+    assert _core.split_pairs_by_cost(np.zeros((0, 2), np.int32), n_feat, 4) == [0, 0, 0, 0, 0]
+    assert _core.split_pairs_by_cost(pairs[:2], n_feat, 4)[-1] == 2     # fewer pairs than GPUs: empty slices allowed
+    empty = [0] * 40                                                      # images without features still get dealt out
+    cut = _core.split_pairs_by_cost(pairs, empty, 4)
+    assert np.all(np.diff(cut) >= len(pairs) // 4 - 1)
+    with pytest.raises(ValueError):
+        _core.split_pairs_by_cost(np.array([[0, 99]], np.int32), n_feat, 2)

@@ -137,3 +137,17 @@ def test_native_pipelines_equal_python_host(tmp_path):
     da, db_ = _dump(a), _dump(b)
     assert len(db_["two_view_geometries"]) == 9
     _assert_same_geometries(da["two_view_geometries"], db_["two_view_geometries"])
+
+
+def test_native_multi_gpu_database_equals_single_gpu(tmp_path):
+    """gpu_index "0,1": one context and one host thread per GPU, pairs cut by cost; the database must not
+    depend on the number of GPUs (matching is exact, RANSAC is seeded per image pair)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    a, b = tmp_path / "one.db", tmp_path / "two.db"
+    _make_db(a)
+    _make_db(b)
+    nat.match_exhaustive(a, matching_options={"block_size": 4})
+    nat.match_exhaustive(b, sift_options={"gpu_index": "0,1"}, matching_options={"block_size": 4})
+    assert _dump(a) == _dump(b)

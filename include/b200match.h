@@ -204,6 +204,29 @@ int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const d
                                    const uint32_t* matches, int64_t m, const b2m_tvg_opts* opts,
                                    b2m_tvg_result* out, uint32_t* inlier_matches);
 
+/* Batched form of the call above for callers that verify many pairs from their own point sets (e.g. a
+ * loop over estimate_two_view_geometry, R:estimators/two_view_geometry.h:95-151): one launch of the
+ * pipeline's kernels over all problems (internally in chunks of 4096).  A problem's RANSAC stream is
+ * keyed by (ctx seed, position of the problem in the call mod 4096): a given call is reproducible, and
+ * problems of one call draw independent samples.
+ * out: [n_problems]; inlier_matches: [n_problems] HOST buffers of capacity (m_k x 2) uint32, or NULL /
+ * NULL entries to skip the inlier lists. */
+typedef struct b2m_tvg_problem {
+  uint32_t struct_size;
+  int32_t reserved;
+  b2m_camera cam1, cam2;
+  const double* points1;   /* HOST [n1 x 2] float64 */
+  int64_t n1;
+  const double* points2;   /* HOST [n2 x 2] float64 */
+  int64_t n2;
+  const uint32_t* matches; /* HOST [m x 2] uint32, or NULL = identity (then n1 == n2) */
+  int64_t m;
+} b2m_tvg_problem;
+
+int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* problems, int64_t n_problems,
+                                         const b2m_tvg_opts* opts, b2m_tvg_result* out,
+                                         uint32_t* const* inlier_matches);
+
 /* Single-model LO-RANSAC.  Replaces essential/fundamental/homography_matrix_estimation
  * (R:estimators/essential_matrix.h:19-103, fundamental_matrix.h:17-50, homography_matrix.h:17-48).
  * kind: 0 = E (points already normalised by the caller), 1 = F, 2 = H.

@@ -59,6 +59,12 @@ class TvgResult(ctypes.Structure):
                 ("reserved", c_i32)]
 
 
+class TvgProblem(ctypes.Structure):
+    _fields_ = [("struct_size", c_u32), ("reserved", c_i32), ("cam1", Camera), ("cam2", Camera),
+                ("points1", ctypes.c_void_p), ("n1", c_i64), ("points2", ctypes.c_void_p), ("n2", c_i64),
+                ("matches", ctypes.c_void_p), ("m", c_i64)]
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("struct_size", c_u32), ("reserved", c_u32), ("kernel_launches", c_u64), ("match_tiles", c_u64),
                 ("last_match_ms", c_f64), ("last_verify_ms", c_f64), ("last_total_ms", c_f64), ("last_k1_ms", c_f64),
@@ -71,6 +77,7 @@ EXPORTS = [
     "b2m_sift_opts_default", "b2m_ransac_opts_default", "b2m_tvg_opts_default", "b2m_match_pair",
     "b2m_set_images", "b2m_set_images_device", "b2m_match_pairs", "b2m_match_verify", "b2m_results_num_pairs",
     "b2m_results_total_matches", "b2m_results_num_verified", "b2m_results_get", "b2m_results_free", "b2m_estimate_two_view_geometry",
+    "b2m_estimate_two_view_geometry_batch",
     "b2m_ransac_model", "b2m_squared_sampson_error", "b2m_get_stats", "b2m_reset_stats",
 ]
 
@@ -117,6 +124,8 @@ def load():
     lib.b2m_estimate_two_view_geometry.argtypes = [P, ctypes.POINTER(Camera), P, c_i64, ctypes.POINTER(Camera), P,
                                                    c_i64, P, c_i64, ctypes.POINTER(TvgOpts),
                                                    ctypes.POINTER(TvgResult), P]
+    lib.b2m_estimate_two_view_geometry_batch.argtypes = [P, ctypes.POINTER(TvgProblem), c_i64,
+                                                         ctypes.POINTER(TvgOpts), ctypes.POINTER(TvgResult), P]
     lib.b2m_ransac_model.argtypes = [P, c_i32, P, P, c_i64, ctypes.POINTER(RansacOpts), P, P,
                                      ctypes.POINTER(c_i64), ctypes.POINTER(c_i32)]
     lib.b2m_squared_sampson_error.argtypes = [P, P, P, c_i64, P, P]

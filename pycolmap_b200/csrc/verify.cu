@@ -1268,6 +1268,126 @@ int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const d
   return B2M_OK;
 }
 
+// Batched variant of b2m_estimate_two_view_geometry: the same kernels the pair pipeline uses (one CTA
+// per problem and model kind, then one decision CTA per problem), fed from caller-provided point sets.
+int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* problems, int64_t n_problems,
+                                         const b2m_tvg_opts* opts, b2m_tvg_result* out,
+                                         uint32_t* const* inlier_matches) {
+  if (!ctx) return B2M_EINVAL;
+  auto bad = [&](const char* msg) {
+    ctx->err = msg;
+    return B2M_EINVAL;
+  };
+  if (n_problems < 0 || (n_problems > 0 && (!problems || !out)) || !opts)
+    return bad("[verify.cu] Check Failed: problems, options and out != NULL");
+  if (opts->multiple_models) return bad("[verify.cu] multiple_models is not supported (SURVEY.md section 8(f) item 4)");
+  for (int64_t k = 0; k < n_problems; ++k) {
+    const b2m_tvg_problem& q = problems[k];
+    if (q.n1 < 0 || q.n2 < 0 || (q.n1 > 0 && !q.points1) || (q.n2 > 0 && !q.points2))
+      return bad("[verify.cu] Check Failed: points");
+    if (!q.matches && q.n1 != q.n2) return bad("[verify.cu] Check Failed: points1.size() == points2.size()");
+    if (q.matches && q.m < 0) return bad("[verify.cu] Check Failed: m >= 0");
+    if ((q.matches ? q.m : q.n1) > INT32_MAX) return bad("[verify.cu] Check Failed: matches per problem < 2^31");
+  }
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  constexpr int64_t kChunk = 4096;  // problems per launch: bounds the staging memory, plenty to fill 148 SMs
+  for (int64_t k0 = 0; k0 < n_problems; k0 += kChunk) {
+    const int nb = static_cast<int>(std::min(kChunk, n_problems - k0));
+    std::vector<double4> pts;
+    std::vector<uint2> mm;
+    std::vector<int64_t> off(nb);
+    std::vector<int32_t> cnt(nb), pairs(2 * nb);
+    std::vector<DevCamera> cams(2 * nb);
+    for (int k = 0; k < nb; ++k) {
+      const b2m_tvg_problem& q = problems[k0 + k];
+      const int64_t m = q.matches ? q.m : q.n1;
+      off[k] = static_cast<int64_t>(pts.size());
+      cnt[k] = static_cast<int32_t>(m);
+      pairs[2 * k] = 2 * k;
+      pairs[2 * k + 1] = 2 * k + 1;
+      cams[2 * k] = to_dev(q.cam1);
+      cams[2 * k + 1] = to_dev(q.cam2);
+      for (int64_t i = 0; i < m; ++i) {
+        const uint32_t a = q.matches ? q.matches[2 * i] : static_cast<uint32_t>(i);
+        const uint32_t b = q.matches ? q.matches[2 * i + 1] : static_cast<uint32_t>(i);
+        if (a >= q.n1 || b >= q.n2) return bad("[verify.cu] Check Failed: match index < number of points");
+        pts.push_back(make_double4(q.points1[2 * a], q.points1[2 * a + 1], q.points2[2 * b], q.points2[2 * b + 1]));
+        mm.push_back(make_uint2(a, b));
+      }
+    }
+    const int64_t total = static_cast<int64_t>(pts.size());
+    const int64_t cap = std::max<int64_t>(total, 1);
+    Single G;  // owns the arenas; the per-problem scalars live in one int32 block (see the offsets below)
+    int32_t* d_i32 = nullptr;  // pairs[2nb] cnt[nb] sup[3nb] success[3nb] config[nb] inl_cnt[nb]
+    V_TRY(ctx, cudaMalloc(&G.d_pts, sizeof(double4) * cap));
+    V_TRY(ctx, cudaMalloc(&G.d_matches, sizeof(uint2) * cap));
+    V_TRY(ctx, cudaMalloc(&G.d_inliers, sizeof(uint2) * cap));
+    V_TRY(ctx, cudaMalloc(&G.d_mask, 3 * cap));
+    V_TRY(ctx, cudaMalloc(&G.d_cams, sizeof(DevCamera) * 2 * nb));
+    V_TRY(ctx, cudaMalloc(&G.d_i32, sizeof(int32_t) * 11 * nb));
+    V_TRY(ctx, cudaMalloc(&G.d_off, sizeof(int64_t) * nb));
+    V_TRY(ctx, cudaMalloc(&G.d_models, sizeof(double) * 27 * nb));
+    d_i32 = G.d_i32;
+    if (total > 0) {
+      V_TRY(ctx, cudaMemcpyAsync(G.d_pts, pts.data(), sizeof(double4) * total, cudaMemcpyHostToDevice, st));
+      V_TRY(ctx, cudaMemcpyAsync(G.d_matches, mm.data(), sizeof(uint2) * total, cudaMemcpyHostToDevice, st));
+    }
+    V_TRY(ctx, cudaMemcpyAsync(G.d_cams, cams.data(), sizeof(DevCamera) * 2 * nb, cudaMemcpyHostToDevice, st));
+    V_TRY(ctx, cudaMemsetAsync(d_i32, 0, sizeof(int32_t) * 11 * nb, st));
+    V_TRY(ctx, cudaMemcpyAsync(d_i32, pairs.data(), sizeof(int32_t) * 2 * nb, cudaMemcpyHostToDevice, st));
+    V_TRY(ctx, cudaMemcpyAsync(d_i32 + 2 * nb, cnt.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, st));
+    V_TRY(ctx, cudaMemcpyAsync(G.d_off, off.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, st));
+    V_TRY(ctx, cudaMemsetAsync(G.d_models, 0, sizeof(double) * 27 * nb, st));
+    VerifyParams P = VerifyParams{};
+    P.pairs = d_i32;
+    P.pair_cnt = d_i32 + 2 * nb;
+    P.sup_cnt = d_i32 + 3 * nb;
+    P.success = d_i32 + 6 * nb;
+    P.config = d_i32 + 9 * nb;
+    P.inl_cnt = d_i32 + 10 * nb;
+    P.pair_off = G.d_off;
+    P.pts = G.d_pts;
+    P.matches = G.d_matches;
+    P.cams = G.d_cams;
+    P.mask = G.d_mask;
+    P.arena_cap = cap;
+    P.models = G.d_models;
+    P.inliers = G.d_inliers;
+    P.opt = *opts;
+    P.seed = ctx->seed;
+    P.single_kind = -1;
+    V_TRY(ctx, launch_ransac(P, nb, st));
+    b2m_decide_kernel<<<nb, 256, 0, st>>>(P);
+    V_TRY(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 4;
+    std::vector<int32_t> h_i32(static_cast<size_t>(11) * nb);
+    std::vector<double> h_models(static_cast<size_t>(27) * nb);
+    std::vector<uint2> h_inl(static_cast<size_t>(cap));
+    V_TRY(ctx, cudaMemcpyAsync(h_i32.data(), d_i32, sizeof(int32_t) * 11 * nb, cudaMemcpyDeviceToHost, st));
+    V_TRY(ctx, cudaMemcpyAsync(h_models.data(), G.d_models, sizeof(double) * 27 * nb, cudaMemcpyDeviceToHost, st));
+    if (total > 0 && inlier_matches)
+      V_TRY(ctx, cudaMemcpyAsync(h_inl.data(), G.d_inliers, sizeof(uint2) * total, cudaMemcpyDeviceToHost, st));
+    V_TRY(ctx, cudaStreamSynchronize(st));
+    for (int k = 0; k < nb; ++k) {
+      b2m_tvg_result& r = out[k0 + k];
+      memset(&r, 0, sizeof(r));
+      r.struct_size = sizeof(r);
+      r.config = h_i32[9 * nb + k];
+      r.n_inliers = h_i32[10 * nb + k];
+      r.nE = h_i32[3 * nb + 3 * k];
+      r.nF = h_i32[3 * nb + 3 * k + 1];
+      r.nH = h_i32[3 * nb + 3 * k + 2];
+      memcpy(r.E, h_models.data() + 27 * k, sizeof(double) * 9);
+      memcpy(r.F, h_models.data() + 27 * k + 9, sizeof(double) * 9);
+      memcpy(r.H, h_models.data() + 27 * k + 18, sizeof(double) * 9);
+      if (r.n_inliers > 0 && inlier_matches && inlier_matches[k0 + k])
+        memcpy(inlier_matches[k0 + k], h_inl.data() + off[k], sizeof(uint2) * r.n_inliers);
+    }
+  }
+  return B2M_OK;
+}
+
 int b2m_ransac_model(b2m_ctx* ctx, int32_t kind, const double* points1, const double* points2, int64_t m,
                      const b2m_ransac_opts* opts, double* out_model, uint8_t* inlier_mask, int64_t* num_inliers,
                      int32_t* success) {

@@ -462,6 +462,69 @@ PYBIND11_MODULE(_core, m) {
         },
         "camera1"_a, "points1"_a, "camera2"_a, "points2"_a, "matches"_a = py::none(),
         "options"_a = TwoViewGeometryOptions());
+  m.def("estimate_two_view_geometries",
+        [](const py::list& problems, const TwoViewGeometryOptions& options) {
+          // Batched estimate_two_view_geometry: every problem is a tuple
+          // (camera1, points1, camera2, points2[, matches]); one GPU launch verifies them all.
+          const size_t n = problems.size();
+          std::vector<ArrD> p1(n), p2(n);
+          std::vector<ArrU32> mm(n);
+          std::vector<b2m_tvg_problem> q(n);
+          std::vector<std::vector<uint32_t>> inl(n);
+          std::vector<uint32_t*> inl_ptr(n);
+          for (size_t k = 0; k < n; ++k) {
+            const py::tuple t = py::tuple(problems[k]);
+            if (t.size() != 4 && t.size() != 5)
+              throw std::invalid_argument("[bindings.cc] Check Failed: problem = (camera1, points1, camera2, points2[, matches])");
+            p1[k] = ArrD::ensure(t[1]);
+            p2[k] = ArrD::ensure(t[3]);
+            if (!p1[k] || !p2[k]) throw std::invalid_argument("[bindings.cc] Check Failed: points are N x 2 float64 arrays");
+            CheckPoints(p1[k], "points1");
+            CheckPoints(p2[k], "points2");
+            memset(&q[k], 0, sizeof(q[k]));
+            q[k].struct_size = sizeof(q[k]);
+            q[k].cam1 = CameraFromPython(py::reinterpret_borrow<py::object>(t[0]));
+            q[k].cam2 = CameraFromPython(py::reinterpret_borrow<py::object>(t[2]));
+            q[k].points1 = p1[k].data();
+            q[k].n1 = p1[k].shape(0);
+            q[k].points2 = p2[k].data();
+            q[k].n2 = p2[k].shape(0);
+            int64_t m = q[k].n1;
+            if (t.size() == 5 && !t[4].is_none()) {
+              mm[k] = ArrU32::ensure(t[4]);
+              if (!mm[k] || mm[k].ndim() != 2 || mm[k].shape(1) != 2)
+                throw std::invalid_argument("[bindings.cc] Check Failed: matches is an N x 2 uint32 array");
+              q[k].matches = mm[k].data();
+              q[k].m = m = mm[k].shape(0);
+            } else if (q[k].n1 != q[k].n2) {
+              throw std::invalid_argument("[two_view_geometry.h:137] Check Failed: points1.size() == points2.size()");
+            }
+            inl[k].resize(static_cast<size_t>(std::max<int64_t>(1, m)) * 2);
+            inl_ptr[k] = inl[k].data();
+          }
+          const b2m_tvg_opts opts = ToAbi(options);
+          std::vector<b2m_tvg_result> r(n);
+          b2m_ctx* ctx = Engine::Get(0);
+          int rc;
+          {
+            py::gil_scoped_release release;
+            rc = b2m_estimate_two_view_geometry_batch(ctx, q.data(), static_cast<int64_t>(n), &opts, r.data(), inl_ptr.data());
+          }
+          ThrowOnError(ctx, rc);
+          std::vector<TwoViewGeometry> out(n);
+          for (size_t k = 0; k < n; ++k) {
+            out[k].config = static_cast<TwoViewGeometryConfiguration>(r[k].config);
+            std::copy(r[k].E, r[k].E + 9, out[k].E.begin());
+            std::copy(r[k].F, r[k].F + 9, out[k].F.begin());
+            std::copy(r[k].H, r[k].H + 9, out[k].H.begin());
+            inl[k].resize(static_cast<size_t>(r[k].n_inliers) * 2);
+            out[k].inlier_matches = std::move(inl[k]);
+            out[k].nE = r[k].nE; out[k].nF = r[k].nF; out[k].nH = r[k].nH;
+          }
+          return out;
+        },
+        "problems"_a, "options"_a = TwoViewGeometryOptions(),
+        "Batched estimate_two_view_geometry: problems = [(camera1, points1, camera2, points2[, matches]), ...]");
   m.def("fundamental_matrix_estimation",
         [](const ArrD& points1, const ArrD& points2, const RANSACOptions& estimation_options) {
           CheckSameLength(points1, points2, "fundamental_matrix.h:22");

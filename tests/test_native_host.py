@@ -255,3 +255,15 @@ def test_gpu_index_list_and_pair_sharding():
     assert np.all(np.diff(cut) >= len(pairs) // 4 - 1)
     with pytest.raises(ValueError):
         _core.split_pairs_by_cost(np.array([[0, 99]], np.int32), n_feat, 2)
+
+
+def test_batched_estimator_argument_checks():
+    cam = dict(model=0, width=1, height=1, params=[1, 0, 0])
+    with pytest.raises(ValueError, match="points1.size"):
+        nat.estimate_two_view_geometries([(cam, np.zeros((3, 2)), cam, np.zeros((4, 2)))])
+    with pytest.raises(ValueError):
+        nat.estimate_two_view_geometries([(cam, np.zeros((3, 2)), cam)])
+    with pytest.raises(ValueError, match="N x 2"):
+        nat.estimate_two_view_geometries([(cam, np.zeros((3, 3)), cam, np.zeros((3, 2)))])
+    with pytest.raises(ValueError, match="matches"):
+        nat.estimate_two_view_geometries([(cam, np.zeros((3, 2)), cam, np.zeros((3, 2)), np.zeros((3, 3), np.uint32))])

@@ -151,3 +151,38 @@ def test_native_multi_gpu_database_equals_single_gpu(tmp_path):
     nat.match_exhaustive(a, matching_options={"block_size": 4})
     nat.match_exhaustive(b, sift_options={"gpu_index": "0,1"}, matching_options={"block_size": 4})
     assert _dump(a) == _dump(b)
+
+
+def test_native_batched_two_view_geometry():
+    """b2m_estimate_two_view_geometry_batch: one launch over many caller-provided problems; every problem
+    must come out like its single-call counterpart (same configuration, inliers within max(2, 1 %))."""
+    rng = np.random.default_rng(21)
+    problems, planted = [], []
+    for kind, n, cam in (("general", 400, scenes.CAM), ("planar", 300, scenes.CAM), ("general", 250, scenes.CAM_NOPRIOR),
+                         ("rotation", 300, scenes.CAM), ("general", 10, scenes.CAM), ("general", 500, scenes.CAM)):
+        p1, p2, pl = scenes.two_view_scene(rng, n, 0.3, kind)
+        problems.append((cam, p1, cam, p2))
+        planted.append(pl)
+    # an explicit (shuffled, partial) match list and an empty problem
+    p1, p2, pl = scenes.two_view_scene(rng, 350, 0.2, "general")
+    perm = rng.permutation(350)[:300]
+    m = np.stack([perm, perm], 1).astype(np.uint32)
+    problems.append((scenes.CAM, p1, scenes.CAM, p2, m))
+    problems.append((scenes.CAM, np.zeros((0, 2)), scenes.CAM, np.zeros((0, 2))))
+    gs = nat.estimate_two_view_geometries(problems)
+    assert len(gs) == len(problems)
+    cfg = nat.TwoViewGeometryConfiguration
+    want_cfg = {0: cfg.CALIBRATED, 4: cfg.DEGENERATE, 5: cfg.CALIBRATED, 6: cfg.CALIBRATED, 7: cfg.DEGENERATE}
+    for k, (g, prob) in enumerate(zip(gs, problems)):
+        single = nat.estimate_two_view_geometry(*prob)
+        assert g.config == single.config == want_cfg.get(k, single.config), (k, g.config, single.config)
+        n1, n2 = len(g.inlier_matches), len(single.inlier_matches)
+        assert abs(n1 - n2) <= max(2, int(0.01 * n2)), (k, n1, n2)
+        if k < 6 and n2:
+            assert abs(n1 - planted[k].sum()) <= max(4, int(0.02 * planted[k].sum()))
+            assert np.all(np.diff(g.inlier_matches[:, 0].astype(np.int64)) > 0)      # identity matches stay ordered
+    assert set(map(tuple, gs[6].inlier_matches)) <= set(map(tuple, m))
+    assert len(gs[6].inlier_matches) >= 0.95 * pl[perm].sum()
+    assert nat.estimate_two_view_geometries([]) == []
+    with pytest.raises(ValueError):
+        nat.estimate_two_view_geometries([(scenes.CAM, np.zeros((3, 2)), scenes.CAM, np.zeros((4, 2)))])

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B2M_ABI_VERSION 1
+#define B2M_ABI_VERSION 2   /* 2: b2m_camera carries 12 parameters (distortion models), batch estimator */
 
 /* error codes */
 #define B2M_OK 0
@@ -116,15 +116,21 @@ enum b2m_tvg_config {
   B2M_MULTIPLE = 8
 };
 
-/* Camera (subset of R:scene/camera.h:20-213 the verifier touches: SIMPLE_PINHOLE / PINHOLE,
- * CamFromImg, CamFromImgThreshold, has_prior_focal_length). */
+/* Camera (the part of R:scene/camera.h:20-213 the verifier touches: CamFromImg, CamFromImgThreshold,
+ * MeanFocalLength, width / height, has_prior_focal_length).  `model` and the parameter order are
+ * COLMAP's (U:sensor/models.h): 0 SIMPLE_PINHOLE (f, cx, cy), 1 PINHOLE (fx, fy, cx, cy),
+ * 2 SIMPLE_RADIAL (f, cx, cy, k), 3 RADIAL (f, cx, cy, k1, k2), 4 OPENCV (fx, fy, cx, cy, k1, k2, p1, p2),
+ * 5 OPENCV_FISHEYE (fx, fy, cx, cy, k1, k2, k3, k4), 6 FULL_OPENCV (fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, k5, k6),
+ * 8 SIMPLE_RADIAL_FISHEYE (f, cx, cy, k), 9 RADIAL_FISHEYE (f, cx, cy, k1, k2).
+ * FOV (7) and THIN_PRISM_FISHEYE (10) are rejected with B2M_EINVAL.  Unused params must be 0. */
+#define B2M_CAMERA_MAX_PARAMS 12
 typedef struct b2m_camera {
   uint32_t struct_size;
-  int32_t model;                  /* 0 = SIMPLE_PINHOLE (f,cx,cy), 1 = PINHOLE (fx,fy,cx,cy) */
+  int32_t model;
   int32_t width, height;
   int32_t has_prior_focal_length;
   int32_t reserved;
-  double params[4];
+  double params[B2M_CAMERA_MAX_PARAMS];
 } b2m_camera;
 
 /* ---- single-pair entry points (the unit the reference's workers call) -------------- */
@@ -234,6 +240,11 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
 int b2m_ransac_model(b2m_ctx* ctx, int32_t kind, const double* points1, const double* points2, int64_t m,
                      const b2m_ransac_opts* opts, double* out_model, uint8_t* inlier_mask,
                      int64_t* num_inliers, int32_t* success);
+
+/* Replaces Camera::CamFromImg applied to a point list (R:scene/camera.h cam_from_img; the loop at
+ * R:estimators/essential_matrix.h:31-39): pixel -> normalised camera coordinates, iterative undistortion
+ * for the models with distortion.  points / out: HOST [n x 2] float64. */
+int b2m_cam_from_img(b2m_ctx* ctx, const b2m_camera* camera, const double* points, int64_t n, double* out);
 
 /* Replaces ComputeSquaredSampsonError (U:estimators/utils.cc; R:estimators/two_view_geometry.h:161-175). */
 int b2m_squared_sampson_error(b2m_ctx* ctx, const double* points1, const double* points2, int64_t m,

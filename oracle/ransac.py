@@ -346,18 +346,94 @@ def loransac(est, local_est, X, Y, opt, rng):
 
 
 # ---------------------------------------------------------------------------------------------
-# cameras (SIMPLE_PINHOLE = 0: f, cx, cy; PINHOLE = 1: fx, fy, cx, cy)
+# cameras (U:sensor/models.h, COLMAP 3.9.1 ids and parameter orders)
+#   0 SIMPLE_PINHOLE f cx cy | 1 PINHOLE fx fy cx cy | 2 SIMPLE_RADIAL f cx cy k | 3 RADIAL f cx cy k1 k2
+#   4 OPENCV fx fy cx cy k1 k2 p1 p2 | 5 OPENCV_FISHEYE fx fy cx cy k1 k2 k3 k4
+#   6 FULL_OPENCV fx fy cx cy k1 k2 p1 p2 k3 k4 k5 k6 | 8 SIMPLE_RADIAL_FISHEYE f cx cy k | 9 RADIAL_FISHEYE f cx cy k1 k2
 # ---------------------------------------------------------------------------------------------
+CAMERA_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 8: 4, 9: 5}
+_SINGLE_FOCAL = (0, 2, 3, 8, 9)
+
+
+def _intrinsics(cam):
+    p = [float(x) for x in cam["params"]]
+    model = cam.get("model", 0)
+    if model not in CAMERA_NUM_PARAMS or len(p) != CAMERA_NUM_PARAMS[model]:
+        raise ValueError(f"camera model {model} with {len(p)} parameters")
+    if model in _SINGLE_FOCAL:
+        return model, np.array([p[0], p[0]]), np.array([p[1], p[2]]), p[3:]
+    return model, np.array([p[0], p[1]]), np.array([p[2], p[3]]), p[4:]
+
+
+def camera_distortion(model, k, uv):
+    """d(u, v) of the model for an [n x 2] array of normalised points."""
+    u, v = uv[:, 0], uv[:, 1]
+    r2 = u * u + v * v
+    if model in (0, 1):
+        return np.zeros_like(uv)
+    if model in (2, 3):
+        radial = k[0] * r2 + (k[1] * r2 * r2 if model == 3 else 0.0)
+        return np.stack([u * radial, v * radial], 1)
+    if model in (4, 6):
+        if model == 4:
+            radial = k[0] * r2 + k[1] * r2 * r2
+        else:
+            radial = (1 + k[0] * r2 + k[1] * r2 ** 2 + k[4] * r2 ** 3) / (1 + k[5] * r2 + k[6] * r2 ** 2 + k[7] * r2 ** 3) - 1
+        du = u * radial + 2 * k[2] * u * v + k[3] * (r2 + 2 * u * u)
+        dv = v * radial + 2 * k[3] * u * v + k[2] * (r2 + 2 * v * v)
+        return np.stack([du, dv], 1)
+    # fisheye family: theta_d = theta * (1 + k1 theta^2 + ...), d = uv * theta_d / r - uv
+    kk = (list(k) + [0.0, 0.0, 0.0])[:4]      # models 8 / 9 carry one / two coefficients
+    r = np.sqrt(r2)
+    safe = np.where(r > np.finfo(float).eps, r, 1.0)
+    th = np.arctan(r)
+    thd = th * (1 + kk[0] * th ** 2 + kk[1] * th ** 4 + kk[2] * th ** 6 + kk[3] * th ** 8)
+    scale = np.where(r > np.finfo(float).eps, thd / safe - 1.0, 0.0)
+    return np.stack([u * scale, v * scale], 1)
+
+
+def img_from_cam(cam, uv):
+    """Camera::ImgFromCam on normalised coordinates [n x 2]."""
+    model, f, c, k = _intrinsics(cam)
+    uv = np.asarray(uv, np.float64)
+    return (uv + camera_distortion(model, k, uv)) * f + c
+
+
 def cam_from_img(cam, pts):
-    p = cam["params"]
-    if cam.get("model", 0) == 0:
-        return (pts - [p[1], p[2]]) / p[0]
-    return (pts - [p[2], p[3]]) / [p[0], p[1]]
+    """Camera::CamFromImg: closed form for the pinhole models, otherwise upstream's IterativeUndistortion
+    (Newton on uv + d(uv) - uv0 with a central-difference Jacobian, <= 100 iterations, |step|^2 < 1e-10)."""
+    model, f, c, k = _intrinsics(cam)
+    uv0 = (np.asarray(pts, np.float64) - c) / f
+    if model in (0, 1):
+        return uv0
+    x = uv0.copy()
+    active = np.ones(len(x), bool)
+    eps = np.finfo(float).eps
+    for _ in range(100):
+        if not active.any():
+            break
+        xa = x[active]
+        h = np.maximum(eps, np.abs(1e-6 * xa))
+        d = camera_distortion(model, k, xa)
+        hx = np.stack([h[:, 0], np.zeros(len(xa))], 1)
+        hy = np.stack([np.zeros(len(xa)), h[:, 1]], 1)
+        ddx = (camera_distortion(model, k, xa + hx) - camera_distortion(model, k, xa - hx)) / (2 * h[:, :1])
+        ddy = (camera_distortion(model, k, xa + hy) - camera_distortion(model, k, xa - hy)) / (2 * h[:, 1:])
+        J = np.zeros((len(xa), 2, 2))
+        J[:, :, 0] = ddx
+        J[:, :, 1] = ddy
+        J[:, 0, 0] += 1.0
+        J[:, 1, 1] += 1.0
+        step = np.linalg.solve(J, (xa + d - uv0[active])[:, :, None])[:, :, 0]
+        x[active] = xa - step
+        idx = np.flatnonzero(active)
+        active[idx[(step ** 2).sum(1) < 1e-10]] = False
+    return x
 
 
 def mean_focal_length(cam):
-    p = cam["params"]
-    return p[0] if cam.get("model", 0) == 0 else 0.5 * (p[0] + p[1])
+    _, f, _, _ = _intrinsics(cam)
+    return 0.5 * (f[0] + f[1])
 
 
 def cam_from_img_threshold(cam, thr):

@@ -44,7 +44,7 @@ class TvgOpts(ctypes.Structure):
 
 class Camera(ctypes.Structure):
     _fields_ = [("struct_size", c_u32), ("model", c_i32), ("width", c_i32), ("height", c_i32),
-                ("has_prior_focal_length", c_i32), ("reserved", c_i32), ("params", c_f64 * 4)]
+                ("has_prior_focal_length", c_i32), ("reserved", c_i32), ("params", c_f64 * 12)]
 
 
 class PairView(ctypes.Structure):
@@ -78,7 +78,7 @@ EXPORTS = [
     "b2m_set_images", "b2m_set_images_device", "b2m_match_pairs", "b2m_match_verify", "b2m_results_num_pairs",
     "b2m_results_total_matches", "b2m_results_num_verified", "b2m_results_get", "b2m_results_free", "b2m_estimate_two_view_geometry",
     "b2m_estimate_two_view_geometry_batch",
-    "b2m_ransac_model", "b2m_squared_sampson_error", "b2m_get_stats", "b2m_reset_stats",
+    "b2m_ransac_model", "b2m_cam_from_img", "b2m_squared_sampson_error", "b2m_get_stats", "b2m_reset_stats",
 ]
 
 _lib = None
@@ -129,6 +129,7 @@ def load():
     lib.b2m_ransac_model.argtypes = [P, c_i32, P, P, c_i64, ctypes.POINTER(RansacOpts), P, P,
                                      ctypes.POINTER(c_i64), ctypes.POINTER(c_i32)]
     lib.b2m_squared_sampson_error.argtypes = [P, P, P, c_i64, P, P]
+    lib.b2m_cam_from_img.argtypes = [P, ctypes.POINTER(Camera), P, c_i64, P]
     lib.b2m_get_stats.argtypes = [P, ctypes.POINTER(Stats)]
     lib.b2m_reset_stats.argtypes = [P]
     _lib = lib
@@ -291,6 +292,14 @@ class Context:
         if not ok.value:
             return None
         return {"model": model.reshape(3, 3), "num_inliers": int(n.value), "inliers": mask[:len(p1)].astype(bool)}
+
+    def cam_from_img(self, cam, points):
+        """Camera::CamFromImg on an [n x 2] point list (all supported camera models)."""
+        p = np.ascontiguousarray(points, np.float64).reshape(-1, 2)
+        out = np.zeros_like(p)
+        cams = self.make_cameras([cam])
+        self.check(self.lib.b2m_cam_from_img(self.h, ctypes.byref(cams[0]), ptr(p), len(p), ptr(out)))
+        return out
 
     def squared_sampson_error(self, points1, points2, E):
         p1 = np.ascontiguousarray(points1, np.float64).reshape(-1, 2)

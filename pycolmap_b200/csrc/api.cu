@@ -552,7 +552,11 @@ int b2m_set_images(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const 
                                   cudaMemcpyHostToDevice, ctx->stream));
     }
   }
-  if (cams) S.cams.assign(cams, cams + n_images);
+  if (cams) {
+    for (int i = 0; i < n_images; ++i)
+      if (const char* why = camera_problem(cams[i])) return fail(ctx, B2M_EINVAL, why);
+    S.cams.assign(cams, cams + n_images);
+  }
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return B2M_OK;
 }
@@ -588,7 +592,11 @@ int b2m_set_images_device(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat,
     src_row += run;
     i = j;
   }
-  if (cams) S.cams.assign(cams, cams + n_images);
+  if (cams) {
+    for (int i = 0; i < n_images; ++i)
+      if (const char* why = camera_problem(cams[i])) return fail(ctx, B2M_EINVAL, why);
+    S.cams.assign(cams, cams + n_images);
+  }
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return B2M_OK;
 }

@@ -8,8 +8,22 @@
 #include <vector>
 
 #include "../../include/b200match.h"
+#include "camera_models.h"
 
 namespace b2m {
+
+// nullptr when the verifier can take this camera, else the reason (-> B2M_EINVAL message).
+inline const char* camera_problem(const b2m_camera& c) {
+  if (c.struct_size != sizeof(b2m_camera))
+    return "[internal.h] Check Failed: b2m_camera.struct_size == sizeof(b2m_camera) (ABI version 2: 12 parameters)";
+  if (cam::num_params(c.model) < 0)
+    return "[internal.h] camera model id is not supported (COLMAP ids 0-6, 8, 9; FOV and THIN_PRISM_FISHEYE are not)";
+  double fx, fy, cx, cy;
+  int extra;
+  cam::intrinsics(c.model, c.params, &fx, &fy, &cx, &cy, &extra);
+  if (!(fx > 0.0) || !(fy > 0.0)) return "[internal.h] Check Failed: camera focal length > 0";
+  return nullptr;
+}
 
 // The descriptor set resident in HBM (replaces upstream's host-side FeatureMatcherCache,
 // U:controllers/feature_matching_utils.cc).  Layout: one [total_rows x 128] uint8 array, image i

@@ -37,7 +37,14 @@ struct DevCamera {
   double mean_f;
   int32_t width, height;
   int32_t has_prior;
+  int32_t distorted;  // model has a distortion function: the E kernel reads undistorted points (see b2m_undistort_kernel)
+};
+
+// Full model of a camera, read only by the undistortion kernel.
+struct DevDistortion {
+  int32_t model;
   int32_t pad;
+  double p[cam::kMaxParams];
 };
 
 struct VerifyParams {
@@ -587,9 +594,44 @@ struct RansacStreams {
   cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
 };
 
-cudaError_t launch_ransac(const VerifyParams& P, int nb, cudaStream_t st, RansacStreams* rs = nullptr) {
+// CamFromImg for camera models with distortion (row V9).  The E kernel normalises its input with the
+// affine map (p - c) / f, which is CamFromImg only for the pinhole models; for a pair with a distorted
+// camera this kernel writes "undistorted pixel" coordinates f * CamFromImg(p) + c into a second arena,
+// so that the same affine map yields the normalised coordinates.  F and H keep reading the raw pixel
+// coordinates, like upstream.  One CTA per pair; launched only when the image set has such a camera.
+__global__ void __launch_bounds__(256) b2m_undistort_kernel(const VerifyParams P, const DevDistortion* __restrict__ dist,
+                                                            double4* __restrict__ out) {
+  const int pair = blockIdx.x;
+  const int n = P.pair_cnt[pair];
+  const int64_t off = P.pair_off[pair];
+  const int i1 = P.pairs[2 * pair], i2 = P.pairs[2 * pair + 1];
+  const DevCamera c1 = P.cams[i1], c2 = P.cams[i2];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double4 p = P.pts[off + i];
+    if (c1.distorted) {
+      double u, v;
+      cam::cam_from_img(dist[i1].model, dist[i1].p, p.x, p.y, &u, &v);
+      p.x = c1.fx * u + c1.cx;
+      p.y = c1.fy * v + c1.cy;
+    }
+    if (c2.distorted) {
+      double u, v;
+      cam::cam_from_img(dist[i2].model, dist[i2].p, p.z, p.w, &u, &v);
+      p.z = c2.fx * u + c2.cx;
+      p.w = c2.fy * v + c2.cy;
+    }
+    out[off + i] = p;
+  }
+}
+
+// `pts_E` (optional): the arena the E kernel reads instead of P.pts (output of b2m_undistort_kernel).
+cudaError_t launch_ransac(const VerifyParams& P_in, int nb, cudaStream_t st, RansacStreams* rs = nullptr,
+                          const double4* pts_E = nullptr) {
+  const VerifyParams& P = P_in;
+  VerifyParams PE = P_in;
+  if (pts_E) PE.pts = pts_E;
   if (P.single_kind >= 0 || !rs || !rs->side[0]) {
-    if (P.single_kind < 0 || P.single_kind == 0) b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, st>>>(P);
+    if (P.single_kind < 0 || P.single_kind == 0) b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, st>>>(PE);
     if (P.single_kind < 0 || P.single_kind == 1) b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, st>>>(P);
     if (P.single_kind < 0 || P.single_kind == 2) b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
     return cudaGetLastError();
@@ -598,7 +640,7 @@ cudaError_t launch_ransac(const VerifyParams& P, int nb, cudaStream_t st, Ransac
   if (e != cudaSuccess) return e;
   cudaStreamWaitEvent(rs->side[0], rs->fork, 0);
   cudaStreamWaitEvent(rs->side[1], rs->fork, 0);
-  b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, rs->side[0]>>>(P);
+  b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, rs->side[0]>>>(PE);
   b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, rs->side[1]>>>(P);
   b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
   cudaEventRecord(rs->join[0], rs->side[0]);
@@ -850,6 +892,9 @@ struct VerifyState {
   int32_t* h_inl_cnt[2] = {nullptr, nullptr};
   uint2* h_inliers[2] = {nullptr, nullptr};
   DevCamera* d_cams = nullptr;
+  DevDistortion* d_dist = nullptr;               // per image, only when any_distorted
+  double4* d_pts_undist[2] = {nullptr, nullptr}; // E-kernel input per slot, lazily allocated
+  bool any_distorted = false;
   unsigned long long* d_prof = nullptr;
   RansacStreams rs;
   int n_cams = 0;
@@ -862,6 +907,8 @@ struct VerifyState {
       h_models[s] = nullptr; h_config[s] = nullptr; h_inl_cnt[s] = nullptr; h_inliers[s] = nullptr;
     }
     cudaFree(d_mask); cudaFree(d_sup); cudaFree(d_success); cudaFree(d_cams);
+    cudaFree(d_dist); cudaFree(d_pts_undist[0]); cudaFree(d_pts_undist[1]);
+    d_dist = nullptr; d_pts_undist[0] = d_pts_undist[1] = nullptr; any_distorted = false;
     cudaFree(d_guided_kind); cudaFree(d_guided_model);
     d_guided_kind = nullptr; d_guided_model = nullptr;
     for (int s = 0; s < 2; ++s) {
@@ -895,13 +942,18 @@ VerifyState* vstate(b2m_ctx* ctx) {
 
 DevCamera to_dev(const b2m_camera& c) {
   DevCamera d{};
-  if (c.model == 0) {
-    d.fx = d.fy = c.params[0]; d.cx = c.params[1]; d.cy = c.params[2]; d.mean_f = c.params[0];
-  } else {
-    d.fx = c.params[0]; d.fy = c.params[1]; d.cx = c.params[2]; d.cy = c.params[3];
-    d.mean_f = 0.5 * (c.params[0] + c.params[1]);
-  }
+  int extra;
+  cam::intrinsics(c.model, c.params, &d.fx, &d.fy, &d.cx, &d.cy, &extra);
+  d.mean_f = cam::mean_focal_length(c.model, c.params);
   d.width = c.width; d.height = c.height; d.has_prior = c.has_prior_focal_length;
+  d.distorted = cam::has_distortion(c.model) ? 1 : 0;
+  return d;
+}
+
+DevDistortion to_dist(const b2m_camera& c) {
+  DevDistortion d{};
+  d.model = c.model;
+  for (int k = 0; k < cam::kMaxParams; ++k) d.p[k] = c.params[k];
   return d;
 }
 
@@ -911,9 +963,13 @@ int ensure_verify_ws(b2m_ctx* ctx, int batch, int64_t arena_cap) {
   DevCamera* keep_cams = V->d_cams;
   const int keep_n = V->n_cams;
   const void* keep_of = V->cams_of;
+  DevDistortion* keep_dist = V->d_dist;
+  const bool keep_any = V->any_distorted;
   V->d_cams = nullptr;
+  V->d_dist = nullptr;
   V->release();
   V->d_cams = keep_cams; V->n_cams = keep_n; V->cams_of = keep_of;
+  V->d_dist = keep_dist; V->any_distorted = keep_any;
   for (int s = 0; s < 2; ++s) {
     V_TRY(ctx, cudaMalloc(&V->d_pts[s], sizeof(double4) * arena_cap));
     V_TRY(ctx, cudaMalloc(&V->d_models[s], sizeof(double) * 27 * batch));
@@ -951,6 +1007,18 @@ int verify_prepare(b2m_ctx* ctx, ImageSet& S, int batch, int64_t arena_cap) {
     V_TRY(ctx, cudaMalloc(&V->d_cams, sizeof(DevCamera) * std::max(1, S.n_images)));
     V_TRY(ctx, cudaMemcpyAsync(V->d_cams, dc.data(), sizeof(DevCamera) * S.n_images, cudaMemcpyHostToDevice,
                                ctx->stream));
+    cudaFree(V->d_dist);
+    V->d_dist = nullptr;
+    V->any_distorted = false;
+    for (const DevCamera& c : dc) V->any_distorted = V->any_distorted || c.distorted;
+    std::vector<DevDistortion> dd;
+    if (V->any_distorted) {
+      dd.resize(S.n_images);
+      for (int i = 0; i < S.n_images; ++i) dd[i] = to_dist(S.cams[i]);
+      V_TRY(ctx, cudaMalloc(&V->d_dist, sizeof(DevDistortion) * S.n_images));
+      V_TRY(ctx, cudaMemcpyAsync(V->d_dist, dd.data(), sizeof(DevDistortion) * S.n_images, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    }
     V_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     V->n_cams = S.n_images;
     V->cams_of = S.d_desc;
@@ -1038,7 +1106,15 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
     V_TRY(ctx, cudaEventCreateWithFlags(&V->rs.join[0], cudaEventDisableTiming));
     V_TRY(ctx, cudaEventCreateWithFlags(&V->rs.join[1], cudaEventDisableTiming));
   }
-  V_TRY(ctx, launch_ransac(P, nb, ctx->stream, &V->rs));
+  const double4* pts_E = nullptr;
+  if (V->any_distorted) {  // distortion models: the E kernel reads undistorted points (row V9)
+    if (!V->d_pts_undist[s]) V_TRY(ctx, cudaMalloc(&V->d_pts_undist[s], sizeof(double4) * V->arena_cap));
+    b2m_undistort_kernel<<<nb, 256, 0, ctx->stream>>>(P, V->d_dist, V->d_pts_undist[s]);
+    V_TRY(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 1;
+    pts_E = V->d_pts_undist[s];
+  }
+  V_TRY(ctx, launch_ransac(P, nb, ctx->stream, &V->rs, pts_E));
   ctx->stats.kernel_launches += 2;
   b2m_decide_kernel<<<nb, 256, 0, ctx->stream>>>(P);
   V_TRY(ctx, cudaGetLastError());
@@ -1143,14 +1219,40 @@ struct Single {
   int32_t* d_i32 = nullptr;   // pairs[2], cnt[1], sup[3], success[3], config[1], inl_cnt[1]
   int64_t* d_off = nullptr;
   double* d_models = nullptr;
+  DevDistortion* d_dist = nullptr;  // only when a camera has distortion
+  double4* d_pts_undist = nullptr;
   ~Single() {
     cudaFree(d_pts); cudaFree(d_matches); cudaFree(d_inliers); cudaFree(d_mask); cudaFree(d_cams);
-    cudaFree(d_i32); cudaFree(d_off); cudaFree(d_models);
+    cudaFree(d_i32); cudaFree(d_off); cudaFree(d_models); cudaFree(d_dist); cudaFree(d_pts_undist);
   }
 };
 
+// Stand-alone estimator calls: upload the full camera models and undistort the E-kernel input when any
+// of the `n_cams` cameras has a distortion function.  Returns the E arena (nullptr: use P.pts) in *pts_E.
+int undistort_for_E(b2m_ctx* ctx, Single& G, const VerifyParams& P, const b2m_camera* const* cams, int n_cams, int nb,
+                    int64_t cap, cudaStream_t st, const double4** pts_E) {
+  *pts_E = nullptr;
+  bool any = false;
+  for (int i = 0; i < n_cams; ++i) any = any || cam::has_distortion(cams[i]->model);
+  if (!any) return B2M_OK;
+  std::vector<DevDistortion> dd(n_cams);
+  for (int i = 0; i < n_cams; ++i) dd[i] = to_dist(*cams[i]);
+  V_TRY(ctx, cudaMalloc(&G.d_dist, sizeof(DevDistortion) * n_cams));
+  V_TRY(ctx, cudaMalloc(&G.d_pts_undist, sizeof(double4) * cap));
+  // synchronous copy: `dd` is a local that must not be read after this function returns
+  V_TRY(ctx, cudaMemcpy(G.d_dist, dd.data(), sizeof(DevDistortion) * n_cams, cudaMemcpyHostToDevice));
+  b2m_undistort_kernel<<<nb, 256, 0, st>>>(P, G.d_dist, G.d_pts_undist);
+  V_TRY(ctx, cudaGetLastError());
+  ctx->stats.kernel_launches += 1;
+  *pts_E = G.d_pts_undist;
+  return B2M_OK;
+}
+
+// `full_cams`: the two cameras with their distortion parameters, or nullptr (single-model API: the
+// caller's points are already in the frame the model is estimated in).
 int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<uint2>& matches, const DevCamera cams[2],
-               const b2m_tvg_opts& opt, int single_kind, Single& G, VerifyParams& P) {
+               const b2m_tvg_opts& opt, int single_kind, Single& G, VerifyParams& P,
+               const b2m_camera* const* full_cams = nullptr) {
   const int64_t m = static_cast<int64_t>(pts.size());
   const int64_t cap = std::max<int64_t>(m, 1);
   V_TRY(ctx, cudaMalloc(&G.d_pts, sizeof(double4) * cap));
@@ -1193,7 +1295,10 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   if (single_kind >= 0) {
     V_TRY(ctx, launch_ransac(P, 1, st));
   } else {
-    V_TRY(ctx, launch_ransac(P, 1, st));
+    const double4* pts_E = nullptr;
+    if (full_cams)
+      if (int rc = undistort_for_E(ctx, G, P, full_cams, 2, 1, cap, st, &pts_E)) return rc;
+    V_TRY(ctx, launch_ransac(P, 1, st, nullptr, pts_E));
     ctx->stats.kernel_launches += 2;
     b2m_decide_kernel<<<1, 256, 0, st>>>(P);
     ctx->stats.kernel_launches += 1;
@@ -1209,6 +1314,12 @@ __global__ void b2m_sampson_kernel(const double* p1, const double* p2, int64_t m
   double M[9];
   for (int k = 0; k < 9; ++k) M[k] = E[k];
   out[i] = sampson_sq(M, p1[2 * i], p1[2 * i + 1], p2[2 * i], p2[2 * i + 1]);
+}
+
+__global__ void b2m_cam_from_img_kernel(const DevDistortion* c, const double* pts, int64_t n, double* out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  cam::cam_from_img(c->model, c->p, pts[2 * i], pts[2 * i + 1], &out[2 * i], &out[2 * i + 1]);
 }
 
 }  // namespace
@@ -1228,6 +1339,8 @@ int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const d
     return B2M_EINVAL;
   };
   if (!cam1 || !cam2 || !opts || !out) return bad("[verify.cu] Check Failed: cameras, options and out != NULL");
+  if (const char* why = camera_problem(*cam1)) return bad(why);
+  if (const char* why = camera_problem(*cam2)) return bad(why);
   if (n1 < 0 || n2 < 0 || (n1 > 0 && !points1) || (n2 > 0 && !points2)) return bad("[verify.cu] Check Failed: points");
   if (opts->multiple_models) return bad("[verify.cu] multiple_models is not supported (SURVEY.md section 8(f) item 4)");
   if (!matches) {  // identity matching (R:estimators/two_view_geometry.h:136-142)
@@ -1248,7 +1361,8 @@ int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const d
   const DevCamera cams[2] = {to_dev(*cam1), to_dev(*cam2)};
   Single G;
   VerifyParams P;
-  if (int rc = run_single(ctx, pts, mm, cams, *opts, -1, G, P)) return rc;
+  const b2m_camera* full_cams[2] = {cam1, cam2};
+  if (int rc = run_single(ctx, pts, mm, cams, *opts, -1, G, P, full_cams)) return rc;
   int32_t i32[16];
   double models[27];
   V_TRY(ctx, cudaMemcpyAsync(i32, G.d_i32, sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1288,6 +1402,8 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     if (!q.matches && q.n1 != q.n2) return bad("[verify.cu] Check Failed: points1.size() == points2.size()");
     if (q.matches && q.m < 0) return bad("[verify.cu] Check Failed: m >= 0");
     if ((q.matches ? q.m : q.n1) > INT32_MAX) return bad("[verify.cu] Check Failed: matches per problem < 2^31");
+    if (const char* why = camera_problem(q.cam1)) return bad(why);
+    if (const char* why = camera_problem(q.cam2)) return bad(why);
   }
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
@@ -1299,8 +1415,11 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     std::vector<int64_t> off(nb);
     std::vector<int32_t> cnt(nb), pairs(2 * nb);
     std::vector<DevCamera> cams(2 * nb);
+    std::vector<const b2m_camera*> full_cams(2 * nb);
     for (int k = 0; k < nb; ++k) {
       const b2m_tvg_problem& q = problems[k0 + k];
+      full_cams[2 * k] = &q.cam1;
+      full_cams[2 * k + 1] = &q.cam2;
       const int64_t m = q.matches ? q.m : q.n1;
       off[k] = static_cast<int64_t>(pts.size());
       cnt[k] = static_cast<int32_t>(m);
@@ -1357,7 +1476,9 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     P.opt = *opts;
     P.seed = ctx->seed;
     P.single_kind = -1;
-    V_TRY(ctx, launch_ransac(P, nb, st));
+    const double4* pts_E = nullptr;
+    if (int rc = undistort_for_E(ctx, G, P, full_cams.data(), 2 * nb, nb, cap, st, &pts_E)) return rc;
+    V_TRY(ctx, launch_ransac(P, nb, st, nullptr, pts_E));
     b2m_decide_kernel<<<nb, 256, 0, st>>>(P);
     V_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += 4;
@@ -1428,6 +1549,42 @@ int b2m_ransac_model(b2m_ctx* ctx, int32_t kind, const double* points1, const do
   *success = i32[6 + kind];
   memcpy(out_model, models + 9 * kind, sizeof(double) * 9);
   return B2M_OK;
+}
+
+int b2m_cam_from_img(b2m_ctx* ctx, const b2m_camera* camera, const double* points, int64_t n, double* out) {
+  if (!ctx) return B2M_EINVAL;
+  auto bad = [&](const char* msg) {
+    ctx->err = msg;
+    return B2M_EINVAL;
+  };
+  if (!camera || n < 0 || (n > 0 && (!points || !out))) return bad("[verify.cu] Check Failed: camera, points, out != NULL");
+  if (const char* why = camera_problem(*camera)) return bad(why);
+  if (n == 0) return B2M_OK;
+  cudaSetDevice(ctx->device);
+  const DevDistortion hd = to_dist(*camera);
+  DevDistortion* dc = nullptr;
+  double *dp = nullptr, *dout = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(dc); cudaFree(dp); cudaFree(dout);
+  };
+  if (cudaMalloc(&dc, sizeof(DevDistortion)) != cudaSuccess || cudaMalloc(&dp, sizeof(double) * 2 * n) != cudaSuccess ||
+      cudaMalloc(&dout, sizeof(double) * 2 * n) != cudaSuccess) {
+    cleanup();
+    ctx->err = "[verify.cu] cudaMalloc failed";
+    return B2M_ENOMEM;
+  }
+  cudaMemcpyAsync(dc, &hd, sizeof(hd), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dp, points, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream);
+  b2m_cam_from_img_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, ctx->stream>>>(dc, dp, n, dout);
+  ctx->stats.kernel_launches += 1;
+  cudaMemcpyAsync(out, dout, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream);
+  int rc = B2M_OK;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = std::string("[verify.cu] CUDA error: ") + cudaGetErrorString(cudaGetLastError());
+    rc = B2M_ECUDA;
+  }
+  cleanup();
+  return rc;
 }
 
 int b2m_squared_sampson_error(b2m_ctx* ctx, const double* points1, const double* points2, int64_t m, const double* E,

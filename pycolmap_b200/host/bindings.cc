@@ -22,6 +22,7 @@
 #include <functional>
 #include <thread>
 
+#include "../csrc/camera_models.h"
 #include "controllers.h"
 #include "dataclass.h"
 #include "database.h"
@@ -79,9 +80,12 @@ b2m_camera CameraFromPython(const py::object& cam) {
   CameraRow row;
   if (py::isinstance<py::str>(model)) {
     const std::string name = model.cast<std::string>();
-    if (name == "SIMPLE_PINHOLE") row.model = 0;
-    else if (name == "PINHOLE") row.model = 1;
-    else throw std::invalid_argument("[bindings.cc] camera model " + name + " is not supported (SIMPLE_PINHOLE / PINHOLE)");
+    static const char* kNames[] = {"SIMPLE_PINHOLE", "PINHOLE", "SIMPLE_RADIAL", "RADIAL", "OPENCV", "OPENCV_FISHEYE",
+                                   "FULL_OPENCV", "FOV", "SIMPLE_RADIAL_FISHEYE", "RADIAL_FISHEYE", "THIN_PRISM_FISHEYE"};
+    row.model = -1;
+    for (int i = 0; i < 11; ++i)
+      if (name == kNames[i]) row.model = i;
+    if (row.model < 0) throw std::invalid_argument("[bindings.cc] unknown camera model " + name);
   } else {
     row.model = model.cast<int>();
   }
@@ -455,7 +459,7 @@ PYBIND11_MODULE(_core, m) {
           auto forced = [](const py::object& cam) {
             b2m_camera c = CameraFromPython(cam);
             return py::dict("model"_a = c.model, "width"_a = c.width, "height"_a = c.height,
-                            "params"_a = std::vector<double>(c.params, c.params + (c.model == 0 ? 3 : 4)),
+                            "params"_a = std::vector<double>(c.params, c.params + b2m::cam::num_params(c.model)),
                             "has_prior_focal_length"_a = 1);
           };
           return EstimateTvg([] { return Engine::Get(0); }, forced(camera1), points1, forced(camera2), points2, matches, options);
@@ -542,26 +546,30 @@ PYBIND11_MODULE(_core, m) {
            const RANSACOptions& estimation_options) {
           CheckSameLength(points1, points2, "essential_matrix.h:26");
           const b2m_camera c1 = CameraFromPython(camera1), c2 = CameraFromPython(camera2);
-          // CamFromImg for (SIMPLE_)PINHOLE (R:estimators/essential_matrix.h:31-39) and the threshold
-          // averaged over both cameras (:42-46); the LO-RANSAC itself runs on the GPU.
-          auto normalise = [](const b2m_camera& c, const ArrD& p) {
-            const double fx = c.params[0], fy = c.model == 0 ? c.params[0] : c.params[1];
-            const double cx = c.model == 0 ? c.params[1] : c.params[2], cy = c.model == 0 ? c.params[2] : c.params[3];
+          // Camera::CamFromImg on both point lists (R:estimators/essential_matrix.h:31-39; on the GPU, every
+          // supported model) and the threshold averaged over both cameras (:42-46).
+          b2m_ctx* ctx = Engine::Get(0);
+          auto normalise = [ctx](const b2m_camera& c, const ArrD& p) {
             ArrD out(std::vector<py::ssize_t>{p.shape(0), 2});
-            const double* s = p.data();
-            double* d = out.mutable_data();
-            for (py::ssize_t i = 0; i < p.shape(0); ++i) {
-              d[2 * i] = (s[2 * i] - cx) / fx;
-              d[2 * i + 1] = (s[2 * i + 1] - cy) / fy;
-            }
+            ThrowOnError(ctx, b2m_cam_from_img(ctx, &c, p.data(), p.shape(0), out.mutable_data()));
             return out;
           };
-          auto mean_f = [](const b2m_camera& c) { return c.model == 0 ? c.params[0] : 0.5 * (c.params[0] + c.params[1]); };
+          auto mean_f = [](const b2m_camera& c) { return b2m::cam::mean_focal_length(c.model, c.params); };
           RANSACOptions o = estimation_options;
           o.max_error = 0.5 * (o.max_error / mean_f(c1) + o.max_error / mean_f(c2));
           return RansacModel(Engine::Get(0), 0, "E", normalise(c1, points1), normalise(c2, points2), o);
         },
         "points1"_a, "points2"_a, "camera1"_a, "camera2"_a, "estimation_options"_a = RANSACOptions());
+  m.def("cam_from_img",
+        [](const py::object& camera, const ArrD& points) {
+          CheckPoints(points, "points");
+          const b2m_camera c = CameraFromPython(camera);
+          ArrD out(std::vector<py::ssize_t>{points.shape(0), 2});
+          b2m_ctx* ctx = Engine::Get(0);
+          ThrowOnError(ctx, b2m_cam_from_img(ctx, &c, points.data(), points.shape(0), out.mutable_data()));
+          return out;
+        },
+        "camera"_a, "points"_a, "Camera.cam_from_img on an N x 2 point list (R:scene/camera.h), every supported model");
   m.def("squared_sampson_error",
         [](const ArrD& points1, const ArrD& points2, const ArrD& E) {
           CheckSameLength(points1, points2, "two_view_geometry.h:165");

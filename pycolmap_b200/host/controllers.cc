@@ -1,5 +1,7 @@
 #include "controllers.h"
 
+#include "../csrc/camera_models.h"  // header-only; model ids / parameter counts shared with the kernels
+
 #include <algorithm>
 #include <cstring>
 #include <fstream>
@@ -56,10 +58,10 @@ b2m_tvg_opts ToAbi(const TwoViewGeometryOptions& o) {
 }
 
 b2m_camera ToAbi(const CameraRow& c) {
-  if (c.model != 0 && c.model != 1)
+  if (b2m::cam::num_params(c.model) < 0)
     throw std::invalid_argument("[controllers.cc] camera model id " + std::to_string(c.model) +
-                                " is not supported by the B200 verifier (SIMPLE_PINHOLE and PINHOLE only)");
-  const size_t need = c.model == 0 ? 3 : 4;
+                                " is not supported by the B200 verifier (FOV and THIN_PRISM_FISHEYE are not implemented)");
+  const size_t need = static_cast<size_t>(b2m::cam::num_params(c.model));
   if (c.params.size() != need)
     throw std::invalid_argument("[controllers.cc] Check Failed: camera has " + std::to_string(need) + " parameters");
   b2m_camera b;

@@ -322,16 +322,25 @@ class TwoViewGeometry:
 
 
 def _camera_dict(camera):
+    from .database import CAMERA_MODEL_IDS, CAMERA_MODEL_NUM_PARAMS
     if isinstance(camera, dict):
-        return camera
-    # duck-typed pycolmap.Camera: model (name or id), width, height, params, has_prior_focal_length
-    model = getattr(camera, "model", getattr(camera, "model_id", 0))
+        model, get = camera.get("model", camera.get("model_id", 0)), camera.get
+    else:  # duck-typed pycolmap.Camera: model (enum, name or id), width, height, params, has_prior_focal_length
+        model = getattr(camera, "model", getattr(camera, "model_id", 0))
+
+        def get(key, default=None):
+            return getattr(camera, key, default)
     name = getattr(model, "name", model)
-    model_id = {"SIMPLE_PINHOLE": 0, "PINHOLE": 1, 0: 0, 1: 1}.get(name)
-    if model_id is None:
-        raise ValueError(f"[pipeline.py] camera model {name} is not supported (SIMPLE_PINHOLE / PINHOLE)")
-    return dict(model=model_id, width=int(camera.width), height=int(camera.height), params=list(camera.params),
-                has_prior_focal_length=int(getattr(camera, "has_prior_focal_length", False)))
+    model_id = CAMERA_MODEL_IDS.get(name) if isinstance(name, str) else int(name)
+    if model_id not in CAMERA_MODEL_NUM_PARAMS:
+        raise ValueError(f"[pipeline.py] camera model {name} is not supported "
+                         "(FOV and THIN_PRISM_FISHEYE are not implemented)")
+    params = [float(x) for x in get("params", [])]
+    if len(params) != CAMERA_MODEL_NUM_PARAMS[model_id]:
+        raise ValueError(f"[pipeline.py] Check Failed: camera model {name} has "
+                         f"{CAMERA_MODEL_NUM_PARAMS[model_id]} parameters")
+    return dict(model=model_id, width=int(get("width", 0)), height=int(get("height", 0)), params=params,
+                has_prior_focal_length=int(bool(get("has_prior_focal_length", False))))
 
 
 def _points(p, name):
@@ -385,13 +394,13 @@ def essential_matrix_estimation(points1, points2, camera1, camera2, estimation_o
     if len(p1) != len(p2):
         raise ValueError("[essential_matrix.h:26] Check Failed: points1.size() == points2.size()")
     c1, c2 = _camera_dict(camera1), _camera_dict(camera2)
+    ctx = get_context(0)
 
-    def norm(c, p):
-        pr = c["params"]
-        return (p - [pr[1], pr[2]]) / pr[0] if c["model"] == 0 else (p - [pr[2], pr[3]]) / [pr[0], pr[1]]
+    def norm(c, p):  # Camera::CamFromImg (R:estimators/essential_matrix.h:31-39), on the GPU for every model
+        return ctx.cam_from_img(c, p)
 
-    def mean_f(c):
-        return c["params"][0] if c["model"] == 0 else 0.5 * (c["params"][0] + c["params"][1])
+    def mean_f(c):   # MeanFocalLength: models 0, 2, 3, 8, 9 have one focal length, the others two
+        return c["params"][0] if c["model"] in (0, 2, 3, 8, 9) else 0.5 * (c["params"][0] + c["params"][1])
     o = RANSACOptions.coerce(estimation_options)
     o = RANSACOptions(o.todict())
     # R:estimators/essential_matrix.h:42-46: threshold averaged over both cameras

@@ -186,3 +186,107 @@ def test_native_batched_two_view_geometry():
     assert nat.estimate_two_view_geometries([]) == []
     with pytest.raises(ValueError):
         nat.estimate_two_view_geometries([(scenes.CAM, np.zeros((3, 2)), scenes.CAM, np.zeros((4, 2)))])
+
+
+# ---- camera models with distortion (row V9) -------------------------------------------------------
+DIST_CAMS = {
+    "SIMPLE_RADIAL": dict(model=2, params=[1200.0, 800.0, 600.0, -0.12]),
+    "OPENCV": dict(model=4, params=[1200.0, 1200.0, 800.0, 600.0, -0.12, 0.03, 1e-3, -2e-3]),
+    "OPENCV_FISHEYE": dict(model=5, params=[1200.0, 1200.0, 800.0, 600.0, 0.05, -0.01, 0.003, -0.001]),
+    "FULL_OPENCV": dict(model=6, params=[1200.0, 1200.0, 800.0, 600.0, -0.12, 0.03, 1e-3, -2e-3, 0.002, 0.01, -0.004, 5e-4]),
+    "RADIAL_FISHEYE": dict(model=9, params=[1200.0, 800.0, 600.0, 0.05, -0.01]),
+}
+
+
+def _distort(cam, px):
+    """Pixels of the ideal pinhole camera (f = 1200, c = (800, 600)) -> pixels of `cam` seeing the same rays."""
+    return R.img_from_cam(cam, (np.asarray(px, np.float64) - [800.0, 600.0]) / 1200.0)
+
+
+@pytest.mark.parametrize("name", sorted(DIST_CAMS))
+def test_distortion_models_two_view_geometry(name):
+    cam = dict(DIST_CAMS[name], width=1600, height=1200, has_prior_focal_length=1)
+    rng = np.random.default_rng(5)
+    p1, p2, planted = scenes.two_view_scene(rng, 400, 0.3, "general")
+    d1, d2 = _distort(cam, p1), _distort(cam, p2)
+    # CamFromImg on the GPU == the oracle's (both invert the same distortion function)
+    assert np.abs(nat.cam_from_img(cam, d1) - R.cam_from_img(cam, d1)).max() < 1e-9
+    assert np.abs(nat.cam_from_img(cam, d1) - (p1 - [800.0, 600.0]) / 1200.0).max() < 1e-8
+    g = nat.estimate_two_view_geometry(cam, d1, cam, d2)
+    assert g.config == nat.TwoViewGeometryConfiguration.CALIBRATED
+    assert abs(len(g.inlier_matches) - planted.sum()) <= 6
+    # same rays through the ideal pinhole camera: the E problem is identical after undistortion
+    g0 = nat.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)
+    assert abs(g.num_inliers_EFH[0] - g0.num_inliers_EFH[0]) <= max(2, int(0.01 * g0.num_inliers_EFH[0]))
+    # negative control: the same pixels with the distortion ignored lose E inliers
+    wrong = dict(scenes.CAM)
+    gw = nat.estimate_two_view_geometry(wrong, d1, wrong, d2)
+    assert gw.num_inliers_EFH[0] < 0.97 * g.num_inliers_EFH[0]
+    # the Python host and the batched entry point take the same cameras
+    gp = pb.estimate_two_view_geometry(cam, d1, cam, d2)
+    assert gp.config == g.config and np.array_equal(gp.inlier_matches, g.inlier_matches)
+    gb = nat.estimate_two_view_geometries([(cam, d1, cam, d2), (scenes.CAM, p1, cam, d2)])
+    assert all(x.config == g.config and abs(len(x.inlier_matches) - planted.sum()) <= 6 for x in gb)
+    e = nat.essential_matrix_estimation(d1, d2, cam, cam)
+    assert e is not None and abs(e["num_inliers"] - planted.sum()) <= 6
+    e_py = pb.essential_matrix_estimation(d1, d2, cam, cam)
+    assert e_py is not None and e_py["num_inliers"] == e["num_inliers"]
+
+
+def test_distortion_oracle_agreement():
+    """One model against the sequential numpy oracle (slow: kept to a single case)."""
+    cam = dict(DIST_CAMS["OPENCV"], width=1600, height=1200, has_prior_focal_length=1)
+    rng = np.random.default_rng(6)
+    p1, p2, planted = scenes.two_view_scene(rng, 300, 0.3, "general", noise=0.3)
+    d1, d2 = _distort(cam, p1), _distort(cam, p2)
+    g = nat.estimate_two_view_geometry(cam, d1, cam, d2)
+    g_ref = R.estimate_two_view_geometry(cam, d1, cam, d2, seed=1)
+    assert g.config.value == g_ref.config == R.CALIBRATED
+    assert abs(len(g.inlier_matches) - len(g_ref.inlier_matches)) <= max(2, int(0.01 * len(g_ref.inlier_matches)))
+
+
+def test_distortion_model_database_pipeline(tmp_path):
+    """A database whose camera is SIMPLE_RADIAL (COLMAP's default model): keypoints are the distorted
+    pixels; verification must find what it finds for the same rays through the pinhole camera."""
+    ideal, radial = tmp_path / "pinhole.db", tmp_path / "radial.db"
+    scene = _make_db(ideal)
+    cam = DIST_CAMS["SIMPLE_RADIAL"]
+    with nat.Database(radial) as db:
+        cid = db.add_camera(2, 1600, 1200, cam["params"], True)
+        db.begin()
+        for i in range(len(scene["desc"])):
+            iid = db.add_image(f"frame{i:04d}.png", cid)
+            kp = np.zeros((len(scene["kpts"][i]), 6), np.float32)
+            kp[:, :2] = _distort(cam, scene["kpts"][i].numpy())
+            db.write_keypoints(iid, kp)
+            db.write_descriptors(iid, scene["desc"][i].numpy())
+        db.commit()
+    nat.match_exhaustive(ideal, matching_options={"block_size": 4})
+    nat.match_exhaustive(radial, matching_options={"block_size": 4})
+    a, b = _dump(ideal), _dump(radial)
+    assert a["matches"] == b["matches"]                      # matching does not look at cameras
+    verified = 0
+    for ra, rb in zip(a["two_view_geometries"], b["two_view_geometries"]):
+        assert ra[0] == rb[0]
+        if ra[1] >= 15:
+            verified += 1
+            assert rb[4] in (2, 3, 6) and abs(ra[1] - rb[1]) <= max(3, int(0.05 * ra[1])), (ra[:2], rb[:2], rb[4])
+    assert verified >= 8
+    # the Python host takes the same database
+    radial2 = tmp_path / "radial_py.db"
+    radial2.write_bytes(radial.read_bytes())
+    with nat.Database(radial2) as db:
+        db.clear_matches()
+        db.clear_two_view_geometries()
+    pb.match_exhaustive(radial2, matching_options={"block_size": 4})
+    c = _dump(radial2)
+    assert c["matches"] == b["matches"]
+    _assert_same_geometries(c["two_view_geometries"], b["two_view_geometries"])
+
+
+def test_unsupported_camera_models_are_rejected():
+    cam = dict(model=7, width=1600, height=1200, params=[1200.0, 1200.0, 800.0, 600.0, 0.5])
+    with pytest.raises(ValueError, match="not supported"):
+        nat.estimate_two_view_geometry(cam, np.zeros((20, 2)), cam, np.zeros((20, 2)))
+    with pytest.raises(ValueError, match="not supported"):
+        pb.estimate_two_view_geometry(cam, np.zeros((20, 2)), cam, np.zeros((20, 2)))

@@ -376,11 +376,19 @@ def main():
     k1_avg_ms = k1_ms / max(k1_n, 1)
     pairs_per_launch = len(my_pairs) * args.steps / max(k1_n, 1)
     achieved = ops_per_pair * pairs_per_launch / (k1_avg_ms / 1e3) / 1e12
+    # 1 / 4: the column direction of the cross-check runs only for pairs with row-direction candidates
+    # (two launches of the GEMM kernel per batch, include/b200match.h enum b2m_k1_dir1_mode); else one launch
+    dir1_mode = int(ctx.stats().k1_dir1_mode)
+    split = dir1_mode in (1, 4)
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch (1024 pairs of 8192^2) from the
             # DRAM bytes of one 1024-pair launch, ncu --set full capture profiles/r01_k1_v14_final.ncu_summary.txt:
             # 136.8 MB read + 59.3 MB written (the distance matrix never leaves TMEM; images mostly hit in L2)
-            "traffic": 196.1e6 if K == 8192 else None, "kernel": "b2m_k1_filter_kernel", "avg_launch_ms": k1_avg_ms,
+            # (that capture is of the single two-direction launch; the split schedule has no capture yet -> null)
+            "traffic": 196.1e6 if (K == 8192 and not split) else None,
+            "kernel": ("b2m_k1_filter_kernel x2 per batch (all pairs row direction + live pairs column direction)"
+                       if split else "b2m_k1_filter_kernel"),
+            "k1_dir1_mode": dir1_mode, "avg_launch_ms": k1_avg_ms,
             "pairs_per_launch": pairs_per_launch, "peak_source": peak_src,
             "algorithmic": "2*K1*K2*128 int8 ops per pair (one GEMM; the transposed GEMM of the cross-check "
                            "direction is not counted)"}

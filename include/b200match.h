@@ -252,6 +252,19 @@ int b2m_squared_sampson_error(b2m_ctx* ctx, const double* points1, const double*
 
 /* ---- instrumentation ---------------------------------------------------------------- */
 
+/* The cross-check needs m21 only for pairs that have at least one m12 entry; for all other pairs the
+ * column-direction GEMM is skipped.  The first cross-check batch of a context is computed both ways and
+ * the match lists are compared on the device before the context switches over (env B2M_K1_DIR1=full / skip
+ * forces one of the two without the comparison). */
+enum b2m_k1_dir1_mode {
+  B2M_K1_DIR1_UNTESTED = 0,      /* no cross-check batch seen yet */
+  B2M_K1_DIR1_SKIP = 1,          /* comparison passed: dead pairs skip the column direction */
+  B2M_K1_DIR1_FULL_MISMATCH = 2, /* comparison FAILED: both directions for every pair (a bug to report) */
+  B2M_K1_DIR1_FULL_FORCED = 3,   /* B2M_K1_DIR1=full */
+  B2M_K1_DIR1_SKIP_FORCED = 4,   /* B2M_K1_DIR1=skip */
+  B2M_K1_DIR1_FULL_NOMEM = 5     /* no memory for the comparison buffers */
+};
+
 typedef struct b2m_stats {
   uint32_t struct_size;
   uint32_t reserved;
@@ -261,7 +274,8 @@ typedef struct b2m_stats {
   double last_verify_ms;      /* device time of the verification stage */
   double last_total_ms;       /* device time of the whole call (events on the library stream) */
   double last_k1_ms;          /* sum of K1 (GEMM + fused top-2) kernel durations of the last call */
-  uint64_t last_k1_launches;  /* K1 launches of the last call */
+  uint64_t last_k1_launches;  /* K1 passes (one per pair batch) of the last call */
+  uint64_t k1_dir1_mode;      /* enum b2m_k1_dir1_mode: how the column direction of the cross-check is computed */
 } b2m_stats;
 int b2m_get_stats(b2m_ctx* ctx, b2m_stats* out);
 int b2m_reset_stats(b2m_ctx* ctx);

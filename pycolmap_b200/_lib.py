@@ -68,7 +68,7 @@ class TvgProblem(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("struct_size", c_u32), ("reserved", c_u32), ("kernel_launches", c_u64), ("match_tiles", c_u64),
                 ("last_match_ms", c_f64), ("last_verify_ms", c_f64), ("last_total_ms", c_f64), ("last_k1_ms", c_f64),
-                ("last_k1_launches", c_u64)]
+                ("last_k1_launches", c_u64), ("k1_dir1_mode", c_u64)]
 
 
 # every symbol include/b200match.h declares

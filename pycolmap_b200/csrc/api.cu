@@ -78,8 +78,12 @@ int layout_images(b2m_ctx* ctx, ImageSet& S, int n_images, const int32_t* n_feat
     CU_TRY(ctx, cudaMalloc(&S.d_kpts, static_cast<size_t>(rows) * sizeof(float2)));
     CU_TRY(ctx, cudaMemsetAsync(S.d_kpts, 0, static_cast<size_t>(rows) * sizeof(float2), ctx->stream));
   }
-  CU_TRY(ctx, cudaMalloc(&S.d_row0, sizeof(int32_t) * std::max(1, n_images)));
-  CU_TRY(ctx, cudaMalloc(&S.d_nfeat, sizeof(int32_t) * std::max(1, n_images)));
+  // one extra, all-zero entry behind the table: image index `n_images` = "no features" (the dummy image
+  // launch_k1_filter_skip points dead pairs at)
+  CU_TRY(ctx, cudaMalloc(&S.d_row0, sizeof(int32_t) * (n_images + 1)));
+  CU_TRY(ctx, cudaMalloc(&S.d_nfeat, sizeof(int32_t) * (n_images + 1)));
+  CU_TRY(ctx, cudaMemsetAsync(S.d_row0, 0, sizeof(int32_t) * (n_images + 1), ctx->stream));
+  CU_TRY(ctx, cudaMemsetAsync(S.d_nfeat, 0, sizeof(int32_t) * (n_images + 1), ctx->stream));
   if (n_images > 0) {
     CU_TRY(ctx, cudaMemcpyAsync(S.d_row0, S.row0.data(), sizeof(int32_t) * n_images, cudaMemcpyHostToDevice,
                                 ctx->stream));
@@ -117,6 +121,7 @@ int ensure_workspace(b2m_ctx* ctx, int batch, int32_t mstride) {
   CU_TRY(ctx, cudaMalloc(&W.d_cand_rows, sizeof(int32_t) * 2 * arena_matches));
   CU_TRY(ctx, cudaMalloc(&W.d_cand_sorted, sizeof(int32_t) * 2 * arena_matches));
   CU_TRY(ctx, cudaMalloc(&W.d_cand_cnt, sizeof(int32_t) * 2 * batch));
+  CU_TRY(ctx, cudaMalloc(&W.d_pairs_dir1, sizeof(int32_t) * 2 * batch));
   for (int s = 0; s < 2; ++s) {
     CU_TRY(ctx, cudaMalloc(&W.d_arena[s], sizeof(uint2) * arena_matches));
     CU_TRY(ctx, cudaMalloc(&W.d_cursor[s], sizeof(unsigned long long)));
@@ -266,18 +271,6 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     mp.cand_cnt = W.d_cand_cnt;
     mp.cand_rows = W.d_cand_rows;
     mp.cand_sorted = W.d_cand_sorted;
-    CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
-    if (ctx->exact_k1) {
-      CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
-    } else {
-      CU_TRY_R(launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st,
-                                ctx->ev_k1b[s]));
-      ctx->stats.kernel_launches += 1;
-    }
-    if (ctx->exact_k1) CU_TRY_R(cudaEventRecord(ctx->ev_k1b[s], st));
-    ctx->stats.kernel_launches += 1;
-    ctx->stats.last_k1_launches += 1;
-    ctx->stats.match_tiles += 0;
     CompactParams cp;
     cp.pairs = mp.pairs;
     cp.img_nfeat = S.d_nfeat;
@@ -292,6 +285,74 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     cp.kpts = tvg ? S.d_kpts : nullptr;
     cp.pts = tvg ? static_cast<double4*>(verify_points_arena(ctx, s)) : nullptr;
     cp.enable = nullptr;
+    // Column direction of the cross-check: skipped for pairs without a row-direction candidate
+    // (launch_k1_filter_skip).  The first cross-check batch of a context is computed both ways and the
+    // match lists compared on the device; on any difference the context stays on the two-direction launch.
+    const bool skip_capable = !ctx->exact_k1 && n_dirs == 2;
+    if (skip_capable && ctx->k1_dir1_mode == B2M_K1_DIR1_UNTESTED) {
+      uint2* t_arena = nullptr;
+      int64_t* t_off = nullptr;
+      int32_t *t_cnt = nullptr, *t_flag = nullptr;
+      auto drop = [&]() {
+        cudaFree(t_arena); cudaFree(t_off); cudaFree(t_cnt); cudaFree(t_flag);
+      };
+      const size_t arena_matches = static_cast<size_t>(W.batch) * W.mstride;
+      if (cudaMalloc(&t_arena, sizeof(uint2) * arena_matches) != cudaSuccess ||
+          cudaMalloc(&t_off, sizeof(int64_t) * nb) != cudaSuccess || cudaMalloc(&t_cnt, sizeof(int32_t) * nb) != cudaSuccess ||
+          cudaMalloc(&t_flag, sizeof(int32_t)) != cudaSuccess) {
+        drop();
+        cudaGetLastError();
+        ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_NOMEM;  // no room for the comparison: stay on the validated launch
+      } else {
+        int32_t h_flag = -1;
+        CompactParams ct = cp;  // the skip path's match lists go to the temporary arena
+        ct.arena = t_arena;
+        ct.pair_off = t_off;
+        ct.pair_cnt = t_cnt;
+        ct.kpts = nullptr;
+        ct.pts = nullptr;
+        cudaError_t e = launch_k1_filter_skip(S.tmap, mp, S.d_desc, nb, max_strips, ctx->num_sms, W.d_pairs_dir1,
+                                              S.n_images, st, nullptr);
+        if (e == cudaSuccess) e = launch_crosscheck_compact(ct, nb, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st);
+        if (e == cudaSuccess)
+          e = launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st, nullptr);
+        if (e == cudaSuccess) e = launch_crosscheck_compact(cp, nb, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(t_flag, 0, sizeof(int32_t), st);
+        if (e == cudaSuccess)
+          e = launch_compare_matches(t_arena, t_off, t_cnt, W.d_arena[s], W.d_pair_off[s], W.d_pair_cnt[s], nb, t_flag, st);
+        unsigned long long h_total = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, t_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(&h_total, W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        drop();
+        if (e != cudaSuccess) CU_TRY_R(e);
+        // a batch without a single match compares nothing: stay untested (and on the two-direction launch)
+        if (h_flag != 0) ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
+        else if (h_total > 0) ctx->k1_dir1_mode = B2M_K1_DIR1_SKIP;
+        ctx->stats.kernel_launches += 8;
+        CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));  // the batch is redone below
+      }
+    }
+    const bool use_skip = skip_capable && (ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP || ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP_FORCED);
+    CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
+    if (ctx->exact_k1) {
+      CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
+    } else if (use_skip) {
+      CU_TRY_R(launch_k1_filter_skip(S.tmap, mp, S.d_desc, nb, max_strips, ctx->num_sms, W.d_pairs_dir1, S.n_images, st,
+                                     ctx->ev_k1b[s]));
+      ctx->stats.kernel_launches += 3;  // second GEMM launch, pair selection, resolve
+    } else {
+      CU_TRY_R(launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st,
+                                ctx->ev_k1b[s]));
+      ctx->stats.kernel_launches += 1;
+    }
+    if (ctx->exact_k1) CU_TRY_R(cudaEventRecord(ctx->ev_k1b[s], st));
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.last_k1_launches += 1;
+    ctx->stats.match_tiles += 0;
+    ctx->stats.k1_dir1_mode = static_cast<uint64_t>(ctx->k1_dir1_mode);
     CU_TRY_R(launch_crosscheck_compact(cp, nb, st));
     ctx->stats.kernel_launches += 1;
     if (tvg)
@@ -364,6 +425,8 @@ void Workspace::release() {
   if (d_cand_cnt) cudaFree(d_cand_cnt);
   if (d_cand_rows) cudaFree(d_cand_rows);
   if (d_cand_sorted) cudaFree(d_cand_sorted);
+  if (d_pairs_dir1) cudaFree(d_pairs_dir1);
+  d_pairs_dir1 = nullptr;
   d_cand_sorted = nullptr;
   d_mbuf = nullptr;
   d_aux = nullptr;
@@ -495,6 +558,9 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
     for (int d = 1; d <= 262144; ++d) monotone &= (lut[d] <= lut[d - 1]);
     const char* env = getenv("B2M_EXACT_K1");
     ctx->exact_k1 = !monotone || (env && env[0] == '1');
+    const char* d1 = getenv("B2M_K1_DIR1");  // full | skip: bypass the one-time comparison (profiling, A/B runs)
+    if (d1 && !strcmp(d1, "full")) ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_FORCED;
+    if (d1 && !strcmp(d1, "skip")) ctx->k1_dir1_mode = B2M_K1_DIR1_SKIP_FORCED;
     CU_TRY_C(cudaMalloc(&ctx->d_lut, sizeof(float) * lut.size()));
     CU_TRY_C(cudaMemcpy(ctx->d_lut, lut.data(), sizeof(float) * lut.size(), cudaMemcpyHostToDevice));
   }
@@ -688,6 +754,7 @@ int b2m_reset_stats(b2m_ctx* ctx) {
   if (!ctx) return B2M_EINVAL;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   ctx->stats.struct_size = sizeof(b2m_stats);
+  ctx->stats.k1_dir1_mode = static_cast<uint64_t>(ctx->k1_dir1_mode);  // a property of the context, not a counter
   return B2M_OK;
 }
 

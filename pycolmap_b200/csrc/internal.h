@@ -51,6 +51,7 @@ struct Workspace {
   int32_t* d_cand_cnt = nullptr;   // K1 v2: [batch][2]
   int32_t* d_cand_rows = nullptr;  // K1 v2: [batch][2][mstride]
   int32_t* d_cand_sorted = nullptr;
+  int32_t* d_pairs_dir1 = nullptr; // [batch][2] swapped / dummy pairs of launch_k1_filter_skip
   uint2* d_arena[2] = {nullptr, nullptr};
   unsigned long long* d_cursor[2] = {nullptr, nullptr};
   int64_t* d_pair_off[2] = {nullptr, nullptr};
@@ -83,6 +84,7 @@ struct b2m_ctx {
   std::string err;
   volatile int stop = 0;
   bool exact_k1 = false;  // use the exact top-2 epilogue (K1 v1) instead of filter + resolve (K1 v2)
+  int k1_dir1_mode = B2M_K1_DIR1_UNTESTED;  // see b2m_stats.k1_dir1_mode
   b2m_stats stats{};
   void* verify_state = nullptr;  // b2m::VerifyState (verify.cu)
 };

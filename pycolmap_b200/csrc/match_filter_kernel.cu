@@ -672,4 +672,93 @@ cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p_in,
   return cudaGetLastError();
 }
 
+namespace {
+// live pair -> (b, a): the column direction becomes the row direction of the swapped pair; dead pair -> dummy
+__global__ void b2m_k1_select_dir1_kernel(const int32_t* __restrict__ pairs, const int32_t* __restrict__ cand_cnt,
+                                          int n_pairs, int dummy, int32_t* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_pairs) return;
+  const bool live = cand_cnt[2 * k] > 0;
+  out[2 * k] = live ? pairs[2 * k + 1] : dummy;
+  out[2 * k + 1] = live ? pairs[2 * k] : dummy;
+}
+
+__global__ void b2m_compare_matches_kernel(const uint2* __restrict__ arena_a, const int64_t* __restrict__ off_a,
+                                           const int32_t* __restrict__ cnt_a, const uint2* __restrict__ arena_b,
+                                           const int64_t* __restrict__ off_b, const int32_t* __restrict__ cnt_b,
+                                           int32_t* mismatch) {
+  const int pair = blockIdx.x;
+  const int n = cnt_a[pair];
+  if (n != cnt_b[pair]) {
+    if (threadIdx.x == 0) atomicOr(mismatch, 1);
+    return;
+  }
+  const uint2* a = arena_a + off_a[pair];
+  const uint2* b = arena_b + off_b[pair];
+  bool bad = false;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) bad = bad || a[i].x != b[i].x || a[i].y != b[i].y;
+  if (bad) atomicOr(mismatch, 2);
+}
+}  // namespace
+
+cudaError_t launch_k1_filter_skip(const CUtensorMap& tmap, const MatchParams& p_in, const uint8_t* desc, int n_pairs,
+                                  int max_strips, int num_sms, int32_t* pairs_scratch, int dummy_image,
+                                  cudaStream_t stream, cudaEvent_t after_filter) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(b2m_k1_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSmemBytes));
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  if (n_pairs <= 0) return cudaSuccess;
+  MatchParams p = p_in;
+  cudaError_t e = cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * 2 * n_pairs, stream);
+  if (e != cudaSuccess) return e;
+  p.n_dirs = 1;
+  p.blocks_per_image = (max_strips * kTileM + kRowsPerItem - 1) / kRowsPerItem;
+  p.n_items = n_pairs * p.blocks_per_image;
+  const int clusters = p.n_items < num_sms / kCluster ? p.n_items : num_sms / kCluster;
+  if (clusters > 0) {
+    // 1. row direction of every pair
+    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // 2. live pairs swapped, dead pairs -> dummy image (0 features: every work item invalid)
+    b2m_k1_select_dir1_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(p.pairs, p.cand_cnt, n_pairs, dummy_image,
+                                                                       pairs_scratch);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // 3. column direction of the live pairs = row direction of the swapped pairs, written to the
+    //    direction-1 halves: every index in the kernel is (pair * 2 + dir) * mstride (+ row) with dir = 0
+    MatchParams q = p;
+    q.pairs = pairs_scratch;
+    q.mbuf = p.mbuf + p.mstride;
+    q.aux = p.aux + p.mstride;
+    q.cand_cnt = p.cand_cnt + 1;
+    q.cand_rows = p.cand_rows + p.mstride;
+    q.cand_sorted = p.cand_sorted + p.mstride;
+    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, q);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  if (after_filter) {
+    e = cudaEventRecord(after_filter, stream);
+    if (e != cudaSuccess) return e;
+  }
+  // 4. exact resolution of both directions (original pair list and base pointers)
+  b2m_k1_resolve_kernel<<<2 * n_pairs * kResolveParts, 256, 0, stream>>>(p, desc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compare_matches(const uint2* arena_a, const int64_t* off_a, const int32_t* cnt_a, const uint2* arena_b,
+                                   const int64_t* off_b, const int32_t* cnt_b, int n_pairs, int32_t* mismatch,
+                                   cudaStream_t stream) {
+  if (n_pairs <= 0) return cudaSuccess;
+  b2m_compare_matches_kernel<<<n_pairs, 256, 0, stream>>>(arena_a, off_a, cnt_a, arena_b, off_b, cnt_b, mismatch);
+  return cudaGetLastError();
+}
+
 }  // namespace b2m

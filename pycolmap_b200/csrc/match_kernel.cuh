@@ -60,8 +60,28 @@ cudaError_t launch_k1_match(const CUtensorMap& tmap, const MatchParams& p, int n
 cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p,
                              const uint8_t* desc, int n_pairs, int max_strips, int n_dirs, int num_sms,
                              cudaStream_t stream, cudaEvent_t after_filter);
+// Cross-check variant of launch_k1_filter that runs the column direction only where it can matter:
+//   1. GEMM + filter over all pairs, row direction only (m12 candidates);
+//   2. pairs without a single row-direction candidate cannot produce a match whatever m21 holds
+//      (FindBestMatchesBruteForce keeps (i, m12[i]) only for m12[i] != -1), so their column direction is
+//      skipped: a tiny kernel writes the swapped pair (b, a) for the live pairs and (dummy, dummy) for the
+//      others into `pairs_scratch`, where `dummy_image` is an image-table entry with 0 features (its work
+//      items are invalid and cost one decode each);
+//   3. the same GEMM kernel over `pairs_scratch`, row direction only, with the output pointers advanced to
+//      the column-direction halves of mbuf / aux / cand_* -- bit-identical to what direction 1 computes;
+//   4. the exact resolve kernel over both directions, as before.
+// Results (mbuf of every pair with at least one m12 entry, hence the match lists) are identical to
+// launch_k1_filter with n_dirs = 2; non-overlapping pairs cost one GEMM instead of two.
+cudaError_t launch_k1_filter_skip(const CUtensorMap& tmap, const MatchParams& p, const uint8_t* desc, int n_pairs,
+                                  int max_strips, int num_sms, int32_t* pairs_scratch, int dummy_image,
+                                  cudaStream_t stream, cudaEvent_t after_filter);
 cudaError_t launch_k1_guided(const CUtensorMap& tmap, const MatchParams& p, const GuidedParams& g, int n_pairs,
                              int max_strips, int n_dirs, cudaStream_t stream);
 cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream);
+// Self-test helper: sets *mismatch != 0 when the match lists of two compaction runs over the same batch
+// differ (per pair: count, then every (idx1, idx2) entry; arena offsets may differ between runs).
+cudaError_t launch_compare_matches(const uint2* arena_a, const int64_t* off_a, const int32_t* cnt_a, const uint2* arena_b,
+                                   const int64_t* off_b, const int32_t* cnt_b, int n_pairs, int32_t* mismatch,
+                                   cudaStream_t stream);
 
 }  // namespace b2m

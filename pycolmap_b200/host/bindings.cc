@@ -849,7 +849,8 @@ PYBIND11_MODULE(_core, m) {
         return py::dict("kernel_launches"_a = s.kernel_launches, "match_tiles"_a = s.match_tiles,
                         "last_match_ms"_a = s.last_match_ms, "last_verify_ms"_a = s.last_verify_ms,
                         "last_total_ms"_a = s.last_total_ms, "last_k1_ms"_a = s.last_k1_ms,
-                        "last_k1_launches"_a = s.last_k1_launches);
+                        "last_k1_launches"_a = s.last_k1_launches,
+                        "k1_dir1_mode"_a = s.k1_dir1_mode);
       });
 
   // test hook for the PyWait logic: blocks `seconds` on the worker thread like a long GPU call would

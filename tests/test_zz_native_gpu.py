@@ -290,3 +290,52 @@ def test_unsupported_camera_models_are_rejected():
         nat.estimate_two_view_geometry(cam, np.zeros((20, 2)), cam, np.zeros((20, 2)))
     with pytest.raises(ValueError, match="not supported"):
         pb.estimate_two_view_geometry(cam, np.zeros((20, 2)), cam, np.zeros((20, 2)))
+
+
+# ---- cross-check: column direction only for pairs with row-direction candidates ----------------------
+def test_cross_check_column_direction_skip():
+    """b2m_stats.k1_dir1_mode: the context compares the split schedule against the two-direction launch on
+    its first cross-check batch with matches and must have switched over (1); forced full (3) and forced
+    skip (4) contexts must give the same, oracle-exact match lists."""
+    import os
+    rng = np.random.default_rng(31)
+    sizes = (1024, 900, 768, 1024, 600, 0, 300)
+    descs = [syn.sift_like(rng, n) for n in sizes]
+    descs[1][:400] = syn.perturb(rng, descs[0][:400])
+    descs[2][:300] = syn.perturb(rng, descs[0][500:800])
+    descs[2][300:500] = syn.perturb(rng, descs[1][600:800])
+    descs[6][:100] = syn.perturb(rng, descs[3][:100])
+    n = len(sizes)
+    pairs = [(a, b) for a in range(n) for b in range(a + 1, n)] + [(2, 0), (6, 3), (5, 1), (4, 3)]
+    # far pairs first: the leading batches of the small-batch context have no match at all
+    pairs = sorted(pairs, key=lambda p: (len(oracle.fast_match_pair(descs[p[0]], descs[p[1]])) > 0, p))
+    pairs = np.array(pairs, np.int32)
+    want = [oracle.fast_match_pair(descs[a], descs[b]) for a, b in pairs]
+    assert sum(len(w) > 0 for w in want) >= 5 and sum(len(w) == 0 for w in want) >= 10
+
+    def run(mode, pair_batch=0):
+        if mode is None:
+            os.environ.pop("B2M_K1_DIR1", None)
+        else:
+            os.environ["B2M_K1_DIR1"] = mode
+        try:
+            c = pb.Context(device=0, pair_batch=pair_batch)
+        finally:
+            os.environ.pop("B2M_K1_DIR1", None)
+        c.set_images(descs)
+        res = c.match_pairs(pairs)
+        got = [res.matches(k) for k in range(len(pairs))]
+        again = c.match_pairs(pairs)                      # second call: the mode is a property of the context
+        got2 = [again.matches(k) for k in range(len(pairs))]
+        mode_after = int(c.stats().k1_dir1_mode)
+        res.free()
+        again.free()
+        c.close()
+        return got, got2, mode_after
+
+    for mode, batch, want_mode in ((None, 0, 1), (None, 4, 1), ("full", 0, 3), ("skip", 0, 4), ("skip", 4, 4)):
+        got, got2, mode_after = run(mode, batch)
+        assert mode_after == want_mode, (mode, batch, mode_after)
+        for k in range(len(pairs)):
+            assert np.array_equal(got[k], want[k]), (mode, batch, tuple(pairs[k]))
+            assert np.array_equal(got2[k], want[k]), (mode, batch, tuple(pairs[k]))

@@ -3,6 +3,7 @@
 // FeatureMatcherCache (U:controllers/feature_matching_utils.cc) for the pipelines bound at
 // R:pipeline/match_features.h:22-68.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -56,6 +57,8 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // Lay out the image table and allocate the padded descriptor array (zero-filled).
 int layout_images(b2m_ctx* ctx, ImageSet& S, int n_images, const int32_t* n_feat, bool want_kpts) {
   S.release();
+  static std::atomic<uint64_t> g_generation{0};
+  S.generation = ++g_generation;
   S.n_images = n_images;
   S.nfeat.assign(n_feat, n_feat + n_images);
   S.row0.resize(n_images);

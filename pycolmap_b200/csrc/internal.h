@@ -39,6 +39,8 @@ struct ImageSet {
   int32_t* d_row0 = nullptr;
   int32_t* d_nfeat = nullptr;
   std::vector<b2m_camera> cams;
+  uint64_t generation = 0;  // bumped by every b2m_set_images*: consumers caching per-set state (device cameras)
+                            // key on this, not on d_desc (the allocator may hand the same address out again)
   CUtensorMap tmap{};       // box 128 bytes x 128 rows
   void release();
 };

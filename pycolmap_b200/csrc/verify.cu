@@ -898,7 +898,7 @@ struct VerifyState {
   unsigned long long* d_prof = nullptr;
   RansacStreams rs;
   int n_cams = 0;
-  const void* cams_of = nullptr;  // ImageSet the cameras were uploaded for
+  uint64_t cams_of = 0;  // ImageSet::generation the cameras were uploaded for
   void release() {
     for (int s = 0; s < 2; ++s) {
       cudaFree(d_pts[s]); cudaFree(d_models[s]); cudaFree(d_config[s]); cudaFree(d_inl_cnt[s]); cudaFree(d_inliers[s]);
@@ -919,7 +919,7 @@ struct VerifyState {
       guided_on[s] = false;
     }
     d_mask = nullptr; d_sup = nullptr; d_success = nullptr; d_cams = nullptr;
-    batch = 0; arena_cap = 0; n_cams = 0; cams_of = nullptr;
+    batch = 0; arena_cap = 0; n_cams = 0; cams_of = 0;
   }
 };
 
@@ -962,7 +962,7 @@ int ensure_verify_ws(b2m_ctx* ctx, int batch, int64_t arena_cap) {
   if (V->batch >= batch && V->arena_cap >= arena_cap) return B2M_OK;
   DevCamera* keep_cams = V->d_cams;
   const int keep_n = V->n_cams;
-  const void* keep_of = V->cams_of;
+  const uint64_t keep_of = V->cams_of;
   DevDistortion* keep_dist = V->d_dist;
   const bool keep_any = V->any_distorted;
   V->d_cams = nullptr;
@@ -999,7 +999,7 @@ void* verify_points_arena(b2m_ctx* ctx, int s) {
 int verify_prepare(b2m_ctx* ctx, ImageSet& S, int batch, int64_t arena_cap) {
   if (int rc = ensure_verify_ws(ctx, batch, arena_cap)) return rc;
   VerifyState* V = vstate(ctx);
-  if (V->cams_of != S.d_desc || V->n_cams != S.n_images) {
+  if (V->cams_of != S.generation || V->n_cams != S.n_images) {
     cudaFree(V->d_cams);
     V->d_cams = nullptr;
     std::vector<DevCamera> dc(S.n_images);
@@ -1021,7 +1021,7 @@ int verify_prepare(b2m_ctx* ctx, ImageSet& S, int batch, int64_t arena_cap) {
     }
     V_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     V->n_cams = S.n_images;
-    V->cams_of = S.d_desc;
+    V->cams_of = S.generation;
   }
   return B2M_OK;
 }

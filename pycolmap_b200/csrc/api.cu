@@ -169,6 +169,15 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
   res->off.assign(n_pairs, 0);
   res->cnt.assign(n_pairs, 0);
   if (tvg) verify_results_init(res, n_pairs);
+  {  // Size the result arrays like the previous call (a pipeline repeats similar calls): growing a flat
+     // vector by doubling re-copies hundreds of MB a few times per call and stalls the launch loop.
+    const uint64_t cap = static_cast<uint64_t>(n_pairs) * static_cast<uint64_t>(std::max(S.max_feat, 1));
+    try {
+      res->matches.reserve(static_cast<size_t>(2 * std::min(ctx->hint_matches + ctx->hint_matches / 16, cap)));
+      if (tvg) res->inliers.reserve(static_cast<size_t>(2 * std::min(ctx->hint_inliers + ctx->hint_inliers / 16, cap)));
+    } catch (const std::bad_alloc&) {  // only a hint
+    }
+  }
   auto bail = [&](int rc) {
     delete res;
     return rc;
@@ -399,6 +408,8 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
   ctx->stats.last_verify_ms = verify_ms;
   ctx->stats.last_match_ms = ms - verify_ms;
 #undef CU_TRY_R
+  ctx->hint_matches = res->matches.size() / 2;
+  ctx->hint_inliers = res->inliers.size() / 2;
   *out = res;
   return B2M_OK;
 }

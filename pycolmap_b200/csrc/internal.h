@@ -87,6 +87,7 @@ struct b2m_ctx {
   volatile int stop = 0;
   bool exact_k1 = false;  // use the exact top-2 epilogue (K1 v1) instead of filter + resolve (K1 v2)
   int k1_dir1_mode = B2M_K1_DIR1_UNTESTED;  // see b2m_stats.k1_dir1_mode
+  uint64_t hint_matches = 0, hint_inliers = 0;  // result sizes of the previous b2m_match_pairs (reserve hints)
   b2m_stats stats{};
   void* verify_state = nullptr;  // b2m::VerifyState (verify.cu)
 };

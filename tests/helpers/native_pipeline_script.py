@@ -1,0 +1,207 @@
+"""Runs INSIDE a subprocess of tests/test_native_pipeline_cpu.py with the mock libb200match.so in front of
+the real one (LD_LIBRARY_PATH): drives the C++ host layer end to end on CPU and checks the databases."""
+import os
+import shutil
+import sqlite3
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from pycolmap_b200 import _core as nat  # noqa: E402
+import oracle  # noqa: E402
+from oracle import ransac as R  # noqa: E402
+from pycolmap_b200 import synthetic as syn  # noqa: E402
+
+tmp = sys.argv[1]
+TABLES = ("cameras", "images", "keypoints", "descriptors", "matches", "two_view_geometries")
+MIN = 15
+
+
+def dump(path):
+    con = sqlite3.connect(path)
+    out = {t: con.execute(f"SELECT * FROM {t} ORDER BY 1").fetchall() for t in TABLES}
+    con.close()
+    return out
+
+
+def fake_geometry(a, b, m):
+    """tests/helpers/mock_b200match.cpp fake_geometry."""
+    if len(m) < MIN or len(m[::2]) < MIN:
+        return 0, np.zeros((0, 2), np.uint32), np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 3))
+    k = np.arange(9)
+    E = (100.0 * a + b + 0.125 * k).reshape(3, 3)
+    F = (-(100.0 * a + b) - 0.25 * k).reshape(3, 3)
+    H = (np.where(k % 4 == 0, 2.0 + a, 0.0) + 0.0625 * k * (b + 1)).reshape(3, 3)
+    return 2, m[::2], E, F, H
+
+
+# the mock answers for "GPUs" 0..7; the real library would refuse without a device
+c = nat.Context(device=3)
+c.close()
+
+n_img, n_feat = 9, 512
+scene = syn.make_scene(n_img, n_feat, seed=7, window_images=2.5)
+descs = [d.numpy() for d in scene["desc"]]
+
+
+def make_db(path, names=None, camera=(0, [1200.0, 800.0, 600.0])):
+    with nat.Database(path) as db:
+        cid = db.add_camera(camera[0], 1600, 1200, camera[1], True)
+        db.begin()
+        ids = []
+        for i in range(n_img):
+            iid = db.add_image(names[i] if names else f"frame{i:04d}.png", cid)
+            kp = np.zeros((n_feat, 4), np.float32)
+            kp[:, :2] = scene["kpts"][i].numpy()
+            db.write_keypoints(iid, kp)
+            db.write_descriptors(iid, descs[i])
+            ids.append(iid)
+        db.commit()
+    return ids
+
+
+# ---- match_exhaustive: every pair once, visited in ExhaustiveFeatureMatcher order, write rules ----------
+a_db = os.path.join(tmp, "a.db")
+ids = make_db(a_db)
+nat.match_exhaustive(a_db, matching_options={"block_size": 4})
+visits = R.exhaustive_pairs(range(n_img), 4)
+assert len(visits) == n_img * (n_img - 1) // 2
+n_verified = 0
+with nat.Database(a_db) as db:
+    assert db.num_rows("matches") == db.num_rows("two_view_geometries") == len(visits)
+    for i1, i2 in visits:
+        want = oracle.fast_match_pair(descs[i1], descs[i2])          # in the VISITED orientation
+        got = db.read_matches(ids[i1], ids[i2])
+        g = db.read_two_view_geometry(ids[i1], ids[i2])
+        cfg, inl, E, F, H = fake_geometry(i1, i2, want)
+        if len(want) < MIN:                                           # stored empty, default geometry
+            assert len(got) == 0 and g.config.value == 0 and len(g.inlier_matches) == 0
+            continue
+        assert np.array_equal(got, want), (i1, i2)
+        assert g.config.value == cfg and np.array_equal(g.inlier_matches, inl)
+        if cfg == 0:            # 15..29 matches: raw matches stored, too few placeholder inliers -> default geometry
+            continue
+        n_verified += 1
+        assert np.array_equal(g.E, E) and np.array_equal(g.F, F) and np.allclose(g.H, H, rtol=1e-9)
+        # and from the other side: columns swapped, F / E transposed, H inverted
+        gi = db.read_two_view_geometry(ids[i2], ids[i1])
+        assert np.array_equal(gi.inlier_matches, inl[:, ::-1]) and np.array_equal(gi.F, F.T)
+        assert np.allclose(gi.H, np.linalg.inv(H), rtol=1e-9)
+    assert n_verified >= 8 and db.num_verified_image_pairs == n_verified <= db.num_matched_image_pairs
+assert any(i1 > i2 for i1, i2 in visits)                              # the reversed-visit branch was exercised
+
+# ---- resume: everything stored -> nothing to do, file untouched --------------------------------------------
+before = open(a_db, "rb").read()
+nat.match_exhaustive(a_db, matching_options={"block_size": 4})
+assert open(a_db, "rb").read() == before
+# partial resume: drop two geometries and one match row; only those pairs are redone, the result is the same
+con = sqlite3.connect(a_db)
+rows = con.execute("SELECT pair_id FROM two_view_geometries ORDER BY pair_id").fetchall()
+con.execute("DELETE FROM two_view_geometries WHERE pair_id IN (?, ?)", (rows[0][0], rows[5][0]))
+con.execute("DELETE FROM matches WHERE pair_id = ?", (rows[9][0],))
+con.commit()
+con.close()
+nat.match_exhaustive(a_db, matching_options={"block_size": 4})
+ref_dump = dump(a_db)
+
+# ---- gpu_index lists: same database whatever the number of GPUs and the block size -------------------------
+for k, (gpus, bs) in enumerate((("0,1,2", 4), ("0, 1,2,3,4,5,6,7", 4), ("5", 4), ("-1", 3), ("1,0", 50))):
+    p = os.path.join(tmp, f"g{k}.db")
+    make_db(p)
+    nat.match_exhaustive(p, sift_options={"gpu_index": gpus}, matching_options={"block_size": bs})
+    d = dump(p)
+    if bs == 4:
+        assert d == ref_dump, gpus                                     # byte-identical tables
+    else:  # another block size visits pairs in another orientation: same pair set, same match sets
+        assert [r[:2] for r in d["matches"]] == [r[:2] for r in ref_dump["matches"]]
+try:
+    nat.match_exhaustive(a_db, sift_options={"gpu_index": "0,9"})
+    raise SystemExit("device 9 must be refused")
+except RuntimeError:
+    pass
+try:
+    nat.match_exhaustive(a_db, matching_options={"block_size": 1})
+    raise SystemExit("block_size 1 must be refused")
+except ValueError:
+    pass
+
+# ---- match_sequential: images ordered by NAME, overlap window ------------------------------------------------
+s_db = os.path.join(tmp, "s.db")
+names = [f"img{99 - i:03d}.png" for i in range(n_img)]                 # name order = reverse id order
+sids = make_db(s_db, names)
+nat.match_sequential(s_db, matching_options={"overlap": 2, "quadratic_overlap": False})
+order = sorted(range(n_img), key=lambda i: names[i])
+seq = R.sequential_pairs(range(n_img), 2, False)
+with nat.Database(s_db) as db:
+    assert db.num_rows("matches") == len(seq) == (n_img - 1) + (n_img - 2)
+    for k1, k2 in seq:
+        i1, i2 = order[k1], order[k2]
+        want = oracle.fast_match_pair(descs[i1], descs[i2])
+        got = db.read_matches(sids[i1], sids[i2])
+        assert np.array_equal(got, want if len(want) >= MIN else want[:0]), (k1, k2)
+try:
+    nat.match_sequential(s_db, matching_options={"loop_detection": True})
+    raise SystemExit("loop detection must be refused")
+except ValueError:
+    pass
+
+# ---- verify_matches: pair list; stored matches are verified, unknown pairs are matched first ---------------
+con = sqlite3.connect(s_db)
+con.execute("DELETE FROM two_view_geometries")
+con.commit()
+con.close()
+listed = [(order[0], order[1]), (order[1], order[0]), (order[3], order[2]), (order[0], order[4]), (order[2], order[2])]
+pairs_txt = os.path.join(tmp, "pairs.txt")
+with open(pairs_txt, "w") as f:
+    f.write("# header\n\n" + "".join(f"{names[a]} {names[b]}\n" for a, b in listed) + "ghost.png img000.png\nonlyone\n")
+nat.verify_matches(s_db, pairs_txt)
+with nat.Database(s_db) as db:
+    assert db.num_rows("two_view_geometries") == 3                      # duplicate, self pair, ghost dropped
+    for a, b in ((order[0], order[1]), (order[3], order[2])):         # had stored matches: verified from them
+        m = db.read_matches(sids[a], sids[b])
+        g = db.read_two_view_geometry(sids[a], sids[b])
+        cfg, inl, E, F, H = fake_geometry(7, 9, m)                      # the mock's single-problem entry point
+        assert g.config.value == cfg and np.array_equal(g.inlier_matches, inl), (a, b)
+    a, b = order[0], order[4]                                          # not matched before (offset 4 > overlap)
+    assert db.exists_matches(sids[a], sids[b]) and db.exists_inlier_matches(sids[a], sids[b])
+    want = oracle.fast_match_pair(descs[a], descs[b])
+    assert np.array_equal(db.read_matches(sids[a], sids[b]), want if len(want) >= MIN else want[:0])
+
+# ---- cameras: COLMAP's default SIMPLE_RADIAL is accepted, FOV is refused; inconsistent features are refused ----
+r_db = os.path.join(tmp, "radial.db")
+make_db(r_db, camera=(2, [1200.0, 800.0, 600.0, -0.1]))
+nat.match_exhaustive(r_db, matching_options={"block_size": 4})
+assert [r[:2] for r in dump(r_db)["matches"]] == [r[:2] for r in ref_dump["matches"]]
+f_db = os.path.join(tmp, "fov.db")
+make_db(f_db, camera=(7, [1200.0, 1200.0, 800.0, 600.0, 0.5]))
+try:
+    nat.match_exhaustive(f_db)
+    raise SystemExit("FOV must be refused")
+except ValueError as e:
+    assert "not supported" in str(e)
+bad = os.path.join(tmp, "bad.db")
+shutil.copy(a_db, bad)
+with nat.Database(bad) as db:
+    db.write_keypoints(ids[2], np.zeros((n_feat - 1, 2), np.float32))
+    db.clear_matches()
+try:
+    nat.match_exhaustive(bad)
+    raise SystemExit("keypoints.rows != descriptors.rows must be refused")
+except ValueError as e:
+    assert "keypoints.rows == descriptors.rows" in str(e)
+
+# ---- low-level context through the mock: plumbing of options and result objects ------------------------------
+c = nat.Context()
+c.set_images(descs[:3])
+res = c.match_pairs(np.array([(0, 1), (2, 1)], np.int32), nat.SiftMatchingOptions(cross_check=False, max_ratio=0.9))
+assert len(res) == 2 and res.image_pair(1) == (2, 1)
+assert np.array_equal(res.matches(1), oracle.fast_match_pair(descs[2], descs[1], max_ratio=0.9, cross_check=False))
+assert res.total_matches == len(res.matches(0)) + len(res.matches(1)) and res.num_verified == 0
+res.free()
+c.close()
+gs = nat.estimate_two_view_geometries([(dict(model=0, width=1, height=1, params=[1.0, 0, 0]), np.zeros((40, 2)),
+                                        dict(model="PINHOLE", width=1, height=1, params=[1.0, 1.0, 0, 0]), np.zeros((40, 2)))])
+assert len(gs) == 1 and gs[0].config.value == 2 and len(gs[0].inlier_matches) == 20
+print("NATIVE-PIPELINE-OK")

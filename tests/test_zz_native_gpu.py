@@ -339,3 +339,28 @@ def test_cross_check_column_direction_skip():
         for k in range(len(pairs)):
             assert np.array_equal(got[k], want[k]), (mode, batch, tuple(pairs[k]))
             assert np.array_equal(got2[k], want[k]), (mode, batch, tuple(pairs[k]))
+
+
+# ---- hypothesis: adversarial small inputs through both entry points ------------------------------------
+def test_hypothesis_small_adversarial_inputs():
+    from hypothesis import given, settings, strategies as st
+    from test_properties import descriptor_pairs
+    c = nat.Context(device=0, seed=0)
+
+    @settings(max_examples=60, deadline=None)
+    @given(descriptor_pairs(), st.sampled_from([(0.8, 0.7), (1.0, 3.2), (0.95, 1.0)]), st.booleans())
+    def check(pair, thr, cross):
+        d1, d2 = pair
+        o = nat.SiftMatchingOptions(max_ratio=thr[0], max_distance=thr[1], cross_check=cross)
+        want = oracle.fast_match_pair(d1, d2, thr[0], thr[1], cross)
+        assert np.array_equal(c.match_pair(d1, d2, o), want)
+        c.set_images([d1, d2, d1[: len(d1) // 2]])
+        res = c.match_pairs(np.array([(0, 1), (1, 0), (2, 1), (1, 2)], np.int32), o)
+        assert np.array_equal(res.matches(0), want)
+        assert np.array_equal(res.matches(1), oracle.fast_match_pair(d2, d1, thr[0], thr[1], cross))
+        assert np.array_equal(res.matches(2), oracle.fast_match_pair(d1[: len(d1) // 2], d2, thr[0], thr[1], cross))
+        res.free()
+
+    check()
+    assert int(c.stats()["k1_dir1_mode"]) in (0, 1)      # never "comparison failed" (2)
+    c.close()

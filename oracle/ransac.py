@@ -540,7 +540,30 @@ def estimate_two_view_geometry(cam1, points1, cam2, points2, matches=None, optio
     matches = np.asarray(matches, np.int64).reshape(-1, 2)
     g = TwoViewGeometry()
     if opt.multiple_models:
-        raise NotImplementedError("multiple_models (SURVEY.md section 8(f) item 4)")
+        # EstimateMultipleTwoViewGeometries (U:estimators/two_view_geometry.cc): estimate on the remaining
+        # matches, keep the geometry (WATERMARK only if not multiple_ignore_watermark), drop its inliers, repeat
+        # until DEGENERATE; one geometry -> itself, several -> MULTIPLE with concatenated inlier matches.
+        import copy
+        single = copy.copy(opt)
+        single.multiple_models = False
+        remaining, found = matches, []
+        while True:
+            gi = estimate_two_view_geometry(cam1, points1, cam2, points2, remaining, single,
+                                            seed=int(rng.integers(0, 2 ** 31)))
+            if gi.config == DEGENERATE or len(gi.inlier_matches) == 0:
+                break
+            if not (opt.multiple_ignore_watermark and gi.config == WATERMARK):
+                found.append(gi)
+            inl = {tuple(x) for x in np.asarray(gi.inlier_matches, np.int64).tolist()}
+            remaining = np.array([x for x in remaining.tolist() if tuple(x) not in inl], np.int64).reshape(-1, 2)
+        if not found:
+            g.config = DEGENERATE
+        elif len(found) == 1:
+            g = found[0]
+        else:
+            g.config = MULTIPLE
+            g.inlier_matches = np.concatenate([np.asarray(x.inlier_matches).reshape(-1, 2) for x in found])
+        return g
     if len(matches) < opt.min_num_inliers:
         g.config = DEGENERATE
         return g

@@ -160,6 +160,11 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: pair image index out of range");
   if (tvg && (!S.d_kpts || S.cams.empty()))
     return fail(ctx, B2M_ESTATE, "[api.cu] verification requested but the image set has no keypoints/cameras");
+  if (tvg && tvg->multiple_models)
+    return fail(ctx, B2M_EINVAL, "[api.cu] multiple_models is available through b2m_estimate_two_view_geometry only "
+                                 "(the pair pipeline verifies one geometry per pair)");
+  if (tvg && tvg->compute_relative_pose)
+    return fail(ctx, B2M_EINVAL, "[api.cu] compute_relative_pose is not supported (DESIGN.md section 7)");
   if (S.max_feat > sift->max_num_matches)
     return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: num descriptors <= SiftMatchingOptions.max_num_matches");
 

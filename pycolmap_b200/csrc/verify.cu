@@ -1329,10 +1329,10 @@ using namespace b2m;
 
 extern "C" {
 
-int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const double* points1, int64_t n1,
-                                   const b2m_camera* cam2, const double* points2, int64_t n2,
-                                   const uint32_t* matches, int64_t m, const b2m_tvg_opts* opts,
-                                   b2m_tvg_result* out, uint32_t* inlier_matches) {
+// One EstimateTwoViewGeometry run (multiple_models ignored): the body of b2m_estimate_two_view_geometry.
+static int estimate_tvg_once(b2m_ctx* ctx, const b2m_camera* cam1, const double* points1, int64_t n1,
+                             const b2m_camera* cam2, const double* points2, int64_t n2, const uint32_t* matches,
+                             int64_t m, const b2m_tvg_opts* opts, b2m_tvg_result* out, uint32_t* inlier_matches) {
   if (!ctx) return B2M_EINVAL;
   auto bad = [&](const char* msg) {
     ctx->err = msg;
@@ -1342,7 +1342,7 @@ int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const d
   if (const char* why = camera_problem(*cam1)) return bad(why);
   if (const char* why = camera_problem(*cam2)) return bad(why);
   if (n1 < 0 || n2 < 0 || (n1 > 0 && !points1) || (n2 > 0 && !points2)) return bad("[verify.cu] Check Failed: points");
-  if (opts->multiple_models) return bad("[verify.cu] multiple_models is not supported (SURVEY.md section 8(f) item 4)");
+  if (opts->compute_relative_pose) return bad("[verify.cu] compute_relative_pose is not supported (DESIGN.md section 7)");
   if (!matches) {  // identity matching (R:estimators/two_view_geometry.h:136-142)
     if (n1 != n2) return bad("[verify.cu] Check Failed: points1.size() == points2.size()");
     m = n1;
@@ -1382,6 +1382,90 @@ int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const d
   return B2M_OK;
 }
 
+// EstimateTwoViewGeometry; with opts->multiple_models the loop of EstimateMultipleTwoViewGeometries
+// (U:estimators/two_view_geometry.cc): estimate on the remaining matches, keep the geometry (a WATERMARK one
+// only if !multiple_ignore_watermark), remove its inliers from the remaining matches, repeat until the
+// estimate is DEGENERATE.  No geometry -> DEGENERATE; one -> that geometry; several -> config MULTIPLE with the
+// inlier lists concatenated in the order they were found and default (zero) E / F / H.  Every round is one run
+// of the GPU verifier; the loop itself is host control flow, as upstream.
+int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const double* points1, int64_t n1,
+                                   const b2m_camera* cam2, const double* points2, int64_t n2,
+                                   const uint32_t* matches, int64_t m, const b2m_tvg_opts* opts,
+                                   b2m_tvg_result* out, uint32_t* inlier_matches) {
+  if (!ctx) return B2M_EINVAL;
+  if (!opts || !opts->multiple_models)
+    return estimate_tvg_once(ctx, cam1, points1, n1, cam2, points2, n2, matches, m, opts, out, inlier_matches);
+  if (!out) {
+    ctx->err = "[verify.cu] Check Failed: out != NULL";
+    return B2M_EINVAL;
+  }
+  if (!matches) {
+    if (n1 != n2) {
+      ctx->err = "[verify.cu] Check Failed: points1.size() == points2.size()";
+      return B2M_EINVAL;
+    }
+    m = n1;
+  }
+  if (m < 0) {
+    ctx->err = "[verify.cu] Check Failed: m >= 0";
+    return B2M_EINVAL;
+  }
+  std::vector<uint32_t> remaining(static_cast<size_t>(m) * 2);
+  for (int64_t i = 0; i < m; ++i) {
+    remaining[2 * i] = matches ? matches[2 * i] : static_cast<uint32_t>(i);
+    remaining[2 * i + 1] = matches ? matches[2 * i + 1] : static_cast<uint32_t>(i);
+  }
+  b2m_tvg_opts once = *opts;
+  once.multiple_models = 0;
+  std::vector<b2m_tvg_result> found;
+  std::vector<std::vector<uint32_t>> found_inl;
+  for (;;) {
+    b2m_tvg_result g;
+    const int64_t rem = static_cast<int64_t>(remaining.size() / 2);
+    std::vector<uint32_t> inl(static_cast<size_t>(std::max<int64_t>(rem, 1)) * 2);
+    if (int rc = estimate_tvg_once(ctx, cam1, points1, n1, cam2, points2, n2, remaining.data(), rem, &once, &g, inl.data()))
+      return rc;
+    if (g.config == B2M_DEGENERATE || g.n_inliers <= 0) break;
+    inl.resize(static_cast<size_t>(g.n_inliers) * 2);
+    // ExtractOutlierMatches: the matches that are not inliers of this geometry stay
+    std::vector<uint64_t> keys(static_cast<size_t>(g.n_inliers));
+    for (int64_t i = 0; i < g.n_inliers; ++i) keys[i] = (static_cast<uint64_t>(inl[2 * i]) << 32) | inl[2 * i + 1];
+    std::sort(keys.begin(), keys.end());
+    std::vector<uint32_t> next;
+    next.reserve(remaining.size());
+    for (int64_t i = 0; i < rem; ++i) {
+      const uint64_t k = (static_cast<uint64_t>(remaining[2 * i]) << 32) | remaining[2 * i + 1];
+      if (!std::binary_search(keys.begin(), keys.end(), k)) {
+        next.push_back(remaining[2 * i]);
+        next.push_back(remaining[2 * i + 1]);
+      }
+    }
+    if (!(opts->multiple_ignore_watermark && g.config == B2M_WATERMARK)) {
+      found.push_back(g);
+      found_inl.push_back(std::move(inl));
+    }
+    remaining.swap(next);
+  }
+  memset(out, 0, sizeof(*out));
+  out->struct_size = sizeof(*out);
+  if (found.empty()) {
+    out->config = B2M_DEGENERATE;
+    return B2M_OK;
+  }
+  if (found.size() == 1) {
+    *out = found[0];
+  } else {
+    out->config = B2M_MULTIPLE;
+  }
+  int64_t total = 0;
+  for (const std::vector<uint32_t>& v : found_inl) {
+    if (inlier_matches && !v.empty()) memcpy(inlier_matches + 2 * total, v.data(), v.size() * sizeof(uint32_t));
+    total += static_cast<int64_t>(v.size() / 2);
+  }
+  out->n_inliers = total;
+  return B2M_OK;
+}
+
 // Batched variant of b2m_estimate_two_view_geometry: the same kernels the pair pipeline uses (one CTA
 // per problem and model kind, then one decision CTA per problem), fed from caller-provided point sets.
 int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* problems, int64_t n_problems,
@@ -1394,7 +1478,8 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
   };
   if (n_problems < 0 || (n_problems > 0 && (!problems || !out)) || !opts)
     return bad("[verify.cu] Check Failed: problems, options and out != NULL");
-  if (opts->multiple_models) return bad("[verify.cu] multiple_models is not supported (SURVEY.md section 8(f) item 4)");
+  if (opts->multiple_models)
+    return bad("[verify.cu] multiple_models: use b2m_estimate_two_view_geometry (the per-problem loop is sequential)");
   for (int64_t k = 0; k < n_problems; ++k) {
     const b2m_tvg_problem& q = problems[k];
     if (q.n1 < 0 || q.n2 < 0 || (q.n1 > 0 && !q.points1) || (q.n2 > 0 && !q.points2))

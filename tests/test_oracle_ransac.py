@@ -160,3 +160,29 @@ def test_pair_generators():
     assert len(R.sequential_pairs(range(10000), 20, False)) == 199790
     s = R.sequential_pairs(range(100), 3, True)
     assert (0, 1) in s and (0, 2) in s and (0, 3) in s and (0, 4) in s and (0, 5) not in s
+
+
+def _two_motion_scene(rng, na, nb, n_out):
+    a1, a2, _ = scenes.two_view_scene(rng, na, 0.0, "general")
+    b1, b2, _ = scenes.two_view_scene(rng, nb, 0.0, "general")     # a second, independent rigid motion
+    o1 = np.c_[rng.uniform(0, 1600, n_out), rng.uniform(0, 1200, n_out)]
+    o2 = np.c_[rng.uniform(0, 1600, n_out), rng.uniform(0, 1200, n_out)]
+    return np.concatenate([a1, b1, o1]), np.concatenate([a2, b2, o2])
+
+
+def test_multiple_models_finds_both_motions():
+    """EstimateMultipleTwoViewGeometries: estimate, remove the inliers, repeat until DEGENERATE."""
+    rng = np.random.default_rng(3)
+    p1, p2 = _two_motion_scene(rng, 70, 50, 15)
+    g = R.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2,
+                                     options=R.TwoViewGeometryOptions(multiple_models=True), seed=1)
+    im = np.asarray(g.inlier_matches)
+    assert g.config == R.MULTIPLE and len(np.unique(im[:, 0])) == len(im)
+    assert (im[:, 0] < 70).sum() >= 68 and ((im[:, 0] >= 70) & (im[:, 0] < 120)).sum() >= 48 and (im[:, 0] >= 120).sum() <= 4
+    first = R.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2, seed=1)
+    assert first.config == R.CALIBRATED and len(first.inlier_matches) < len(im)      # one model explains one motion
+    # a single-motion scene comes back as itself, not as MULTIPLE
+    q1, q2, pl = scenes.two_view_scene(rng, 90, 0.2, "general")
+    g1 = R.estimate_two_view_geometry(scenes.CAM, q1, scenes.CAM, q2,
+                                      options=R.TwoViewGeometryOptions(multiple_models=True), seed=2)
+    assert g1.config == R.CALIBRATED and abs(len(g1.inlier_matches) - pl.sum()) <= 3

@@ -364,3 +364,36 @@ def test_hypothesis_small_adversarial_inputs():
     check()
     assert int(c.stats()["k1_dir1_mode"]) in (0, 1)      # never "comparison failed" (2)
     c.close()
+
+
+def test_multiple_models_estimator():
+    """TwoViewGeometryOptions.multiple_models through b2m_estimate_two_view_geometry: two independent rigid
+    motions + clutter -> MULTIPLE with both inlier sets; a single motion comes back as itself; the pair pipeline
+    refuses the option instead of ignoring it."""
+    rng = np.random.default_rng(3)
+    a1, a2, _ = scenes.two_view_scene(rng, 160, 0.0, "general")
+    b1, b2, _ = scenes.two_view_scene(rng, 130, 0.0, "general")
+    o = 40
+    p1 = np.concatenate([a1, b1, np.c_[rng.uniform(0, 1600, o), rng.uniform(0, 1200, o)]])
+    p2 = np.concatenate([a2, b2, np.c_[rng.uniform(0, 1600, o), rng.uniform(0, 1200, o)]])
+    cfg = nat.TwoViewGeometryConfiguration
+    for mod in (nat, pb):
+        g = mod.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2, options={"multiple_models": True})
+        im = g.inlier_matches
+        assert int(g.config) == int(cfg.MULTIPLE.value) and len(np.unique(im[:, 0])) == len(im)
+        assert (im[:, 0] < 160).sum() >= 156 and ((im[:, 0] >= 160) & (im[:, 0] < 290)).sum() >= 126
+        assert (im[:, 0] >= 290).sum() <= 8 and np.array_equal(im[:, 0], im[:, 1])
+        assert np.all(g.E == 0) and np.all(g.H == 0)                       # MULTIPLE carries no single model
+        first = mod.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)
+        assert int(first.config) == int(cfg.CALIBRATED.value) and len(first.inlier_matches) < len(im)
+        assert np.array_equal(im[: len(first.inlier_matches)], first.inlier_matches)   # found first, listed first
+    q1, q2, pl = scenes.two_view_scene(rng, 300, 0.2, "general")
+    g1 = nat.estimate_two_view_geometry(scenes.CAM, q1, scenes.CAM, q2, options={"multiple_models": True})
+    assert g1.config == cfg.CALIBRATED and abs(len(g1.inlier_matches) - pl.sum()) <= 4
+    c = nat.Context()
+    c.set_images([syn.sift_like(rng, 64)] * 2, [np.zeros((64, 2), np.float32)] * 2, [scenes.CAM] * 2)
+    with pytest.raises(ValueError, match="multiple_models"):
+        c.match_pairs(np.array([(0, 1)], np.int32), nat.SiftMatchingOptions(), nat.TwoViewGeometryOptions(multiple_models=True))
+    with pytest.raises(ValueError, match="compute_relative_pose"):
+        c.match_pairs(np.array([(0, 1)], np.int32), nat.SiftMatchingOptions(), {"compute_relative_pose": True})
+    c.close()

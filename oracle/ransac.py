@@ -468,6 +468,7 @@ class TwoViewGeometry:
         self.inlier_matches = np.zeros((0, 2), np.uint32)
         self.nE = self.nF = self.nH = 0
         self.reports = {}
+        self.qvec, self.tvec, self.tri_angle, self.pose_valid = np.array([1.0, 0, 0, 0]), np.zeros(3), 0.0, False
 
 
 def detect_watermark(cam1, pts1, cam2, pts2, num_inliers, mask, opt, rng):
@@ -601,7 +602,185 @@ def estimate_two_view_geometry(cam1, points1, cam2, points2, matches=None, optio
     g.inlier_matches = matches[mask].astype(np.uint32)
     if opt.detect_watermark and detect_watermark(cam1, p1, cam2, p2, num, mask, opt, rng):
         g.config = WATERMARK
+    if opt.compute_relative_pose:
+        estimate_two_view_geometry_pose(cam1, points1, cam2, points2, g)
     return g
+
+
+# ---------------------------------------------------------------------------------------------
+# relative pose (U:geometry/essential_matrix.cc, homography_matrix.cc, pose.cc, triangulation.cc;
+# R:estimators/two_view_geometry.h:153-158).  numpy SVDs on purpose: the CUDA path uses Jacobi eigen-solvers.
+# ---------------------------------------------------------------------------------------------
+def decompose_essential_matrix(E):
+    U, _, Vt = np.linalg.svd(E)
+    if np.linalg.det(U) < 0:
+        U = -U
+    if np.linalg.det(Vt) < 0:
+        Vt = -Vt
+    W = np.array([[0.0, 1, 0], [-1, 0, 0], [0, 0, 1]])
+    t = U[:, 2] / np.linalg.norm(U[:, 2])
+    return U @ W @ Vt, U @ W.T @ Vt, t
+
+
+def triangulate_point(P1, P2, x1, x2):
+    A = np.stack([x1[0] * P1[2] - P1[0], x1[1] * P1[2] - P1[1], x2[0] * P2[2] - P2[0], x2[1] * P2[2] - P2[1]])
+    X = np.linalg.svd(A)[2][3]
+    return X[:3] / X[3]
+
+
+def check_cheirality(Rm, t, pts1, pts2):
+    """Points triangulated in front of both cameras and closer than 1000 baselines."""
+    P1 = np.hstack([np.eye(3), np.zeros((3, 1))])
+    P2 = np.hstack([Rm, np.asarray(t, np.float64).reshape(3, 1)])
+    max_depth = 1000.0 * np.linalg.norm(Rm.T @ t)
+    eps = np.finfo(float).eps
+    out = []
+    for a, b in zip(pts1, pts2):
+        X = triangulate_point(P1, P2, a, b)
+        d1 = P1[2] @ np.append(X, 1.0) * np.linalg.norm(P1[:, 2])
+        if eps < d1 < max_depth:
+            d2 = P2[2] @ np.append(X, 1.0) * np.linalg.norm(P2[:, 2])
+            if eps < d2 < max_depth:
+                out.append(X)
+    return out
+
+
+def pose_from_essential_matrix(E, pts1, pts2):
+    R1, R2, t = decompose_essential_matrix(E)
+    best = (None, None, [])
+    first = True
+    for Rm, tt in ((R1, t), (R2, t), (R1, -t), (R2, -t)):
+        X = check_cheirality(Rm, tt, pts1, pts2)
+        if first or len(X) >= len(best[2]):
+            best = (Rm, tt, X)
+        first = False
+    return best
+
+
+def decompose_homography_matrix(H, K1, K2):
+    """Malis & Vargas analytical decomposition: [(R, t, n)], one entry for a pure rotation, else four."""
+    Hn = np.linalg.inv(K2) @ H @ K1
+    Hn = Hn / np.linalg.svd(Hn)[1][1]
+    if np.linalg.det(Hn) < 0:
+        Hn = -Hn
+    S = Hn.T @ Hn - np.eye(3)
+    if np.abs(S).sum(1).max() < 1e-3:
+        return [(Hn, np.zeros(3), np.zeros(3))]
+
+    def minor(r, c):
+        c0, c1 = (1 if c == 0 else 0), (1 if c == 2 else 2)
+        r0, r1 = (1 if r == 0 else 0), (1 if r == 2 else 2)
+        return S[r0, c1] * S[r1, c0] - S[r0, c0] * S[r1, c1]
+
+    def sgn(v):
+        return -1.0 if v < 0 else 1.0
+    M00, M11, M22 = minor(0, 0), minor(1, 1), minor(2, 2)
+    r00, r11, r22 = np.sqrt(max(M00, 0)), np.sqrt(max(M11, 0)), np.sqrt(max(M22, 0))
+    e12, e02, e01 = sgn(minor(1, 2)), sgn(minor(0, 2)), sgn(minor(0, 1))
+    nS = [abs(S[0, 0]), abs(S[1, 1]), abs(S[2, 2])]
+    if nS[0] < nS[1]:
+        idx = 2 if nS[1] < nS[2] else 1
+    else:
+        idx = 2 if nS[0] < nS[2] else 0
+    if idx == 0:
+        np1 = np.array([S[0, 0], S[0, 1] + r22, S[0, 2] + e12 * r11])
+        np2 = np.array([S[0, 0], S[0, 1] - r22, S[0, 2] - e12 * r11])
+    elif idx == 1:
+        np1 = np.array([S[0, 1] + r22, S[1, 1], S[1, 2] - e02 * r00])
+        np2 = np.array([S[0, 1] - r22, S[1, 1], S[1, 2] + e02 * r00])
+    else:
+        np1 = np.array([S[0, 2] + e01 * r11, S[1, 2] + r00, S[2, 2]])
+        np2 = np.array([S[0, 2] - e01 * r11, S[1, 2] - r00, S[2, 2]])
+    tr = np.trace(S)
+    v = 2.0 * np.sqrt(max(1.0 + tr - M00 - M11 - M22, 0))
+    es = sgn(S[idx, idx])
+    r, n_t = np.sqrt(max(2.0 + tr + v, 0)), np.sqrt(max(2.0 + tr - v, 0))
+    n1, n2 = np1 / np.linalg.norm(np1), np2 / np.linalg.norm(np2)
+    t1s = 0.5 * n_t * (es * r * n2 - n_t * n1)
+    t2s = 0.5 * n_t * (es * r * n1 - n_t * n2)
+    Ra = Hn @ (np.eye(3) - (2.0 / v) * np.outer(t1s, n1))
+    Rb = Hn @ (np.eye(3) - (2.0 / v) * np.outer(t2s, n2))
+    ta, tb = Ra @ t1s, Rb @ t2s
+    return [(Ra, ta, -n1), (Ra, -ta, n1), (Rb, tb, -n2), (Rb, -tb, n2)]
+
+
+def calibration_matrix(cam):
+    _, f, c, _ = _intrinsics(cam)
+    return np.array([[f[0], 0, c[0]], [0, f[1], c[1]], [0, 0, 1.0]])
+
+
+def pose_from_homography_matrix(H, K1, K2, pts1, pts2):
+    best = (None, None, None, [])
+    first = True
+    for Rm, t, n in decompose_homography_matrix(H, K1, K2):
+        X = check_cheirality(Rm, t, pts1, pts2)
+        if first or len(X) >= len(best[3]):
+            best = (Rm, t, n, X)
+        first = False
+    return best
+
+
+def triangulation_angles(c1, c2, X):
+    X = np.asarray(X, np.float64).reshape(-1, 3)
+    b2 = ((c1 - c2) ** 2).sum()
+    r1, r2 = ((X - c1) ** 2).sum(1), ((X - c2) ** 2).sum(1)
+    den = 2.0 * np.sqrt(r1 * r2)
+    ang = np.zeros(len(X))
+    ok = den > 0
+    ang[ok] = np.abs(np.arccos(np.clip((r1 + r2 - b2)[ok] / den[ok], -1.0, 1.0)))
+    return np.minimum(ang, np.pi - ang)
+
+
+def median(v):
+    v = np.sort(np.asarray(v, np.float64))
+    m = len(v) // 2
+    return 0.5 * (v[m - 1] + v[m]) if len(v) % 2 == 0 else v[m]
+
+
+def rotation_to_quat(Rm):
+    """(w, x, y, z), the branch selection of Eigen's Quaterniond(Matrix3d)."""
+    tr = np.trace(Rm)
+    q = np.zeros(4)
+    if tr > 0:
+        s = np.sqrt(tr + 1.0)
+        q[0] = 0.5 * s
+        s = 0.5 / s
+        q[1:] = [(Rm[2, 1] - Rm[1, 2]) * s, (Rm[0, 2] - Rm[2, 0]) * s, (Rm[1, 0] - Rm[0, 1]) * s]
+    else:
+        i = int(np.argmax(np.diag(Rm)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(Rm[i, i] - Rm[j, j] - Rm[k, k] + 1.0)
+        q[1 + i] = 0.5 * s
+        s = 0.5 / s
+        q[0] = (Rm[k, j] - Rm[j, k]) * s
+        q[1 + j] = (Rm[j, i] + Rm[i, j]) * s
+        q[1 + k] = (Rm[k, i] + Rm[i, k]) * s
+    return q
+
+
+def estimate_two_view_geometry_pose(cam1, points1, cam2, points2, g):
+    """EstimateTwoViewGeometryPose: fills g.qvec (w, x, y, z), g.tvec, g.tri_angle; may turn
+    PLANAR_OR_PANORAMIC into PLANAR / PANORAMIC.  Returns False when no pose could be recovered."""
+    g.qvec, g.tvec, g.tri_angle, g.pose_valid = np.array([1.0, 0, 0, 0]), np.zeros(3), 0.0, False
+    if g.config not in (CALIBRATED, UNCALIBRATED, PLANAR, PANORAMIC, PLANAR_OR_PANORAMIC):
+        return False
+    im = np.asarray(g.inlier_matches, np.int64).reshape(-1, 2)
+    n1 = cam_from_img(cam1, np.asarray(points1, np.float64)[im[:, 0]])
+    n2 = cam_from_img(cam2, np.asarray(points2, np.float64)[im[:, 1]])
+    if g.config in (CALIBRATED, UNCALIBRATED):
+        Rm, t, X = pose_from_essential_matrix(g.E, n1, n2)
+        if len(X) == 0:
+            return False
+    else:
+        Rm, t, _, X = pose_from_homography_matrix(g.H, calibration_matrix(cam1), calibration_matrix(cam2), n1, n2)
+    g.qvec, g.tvec, g.pose_valid = rotation_to_quat(Rm), np.asarray(t, np.float64), True
+    g.tri_angle = 0.0 if len(X) == 0 else float(median(triangulation_angles(np.zeros(3), -Rm.T @ t, X)))
+    if g.config == PLANAR_OR_PANORAMIC:
+        if np.linalg.norm(t) == 0:
+            g.config, g.tri_angle = PANORAMIC, 0.0
+        else:
+            g.config = PLANAR
+    return True
 
 
 # ---------------------------------------------------------------------------------------------

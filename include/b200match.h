@@ -93,7 +93,8 @@ typedef struct b2m_tvg_opts {
   int32_t detect_watermark;           /* 1 */
   int32_t multiple_ignore_watermark;  /* 1 */
   int32_t force_H_use;                /* 0 */
-  int32_t compute_relative_pose;      /* 0 */
+  int32_t compute_relative_pose;      /* 0; 1: also EstimateTwoViewGeometryPose (qvec, tvec, tri_angle; may turn
+                                       * PLANAR_OR_PANORAMIC into PLANAR / PANORAMIC) */
   int32_t multiple_models;            /* 0 */
   int32_t reserved;
   b2m_ransac_opts ransac;
@@ -180,6 +181,12 @@ typedef struct b2m_pair_view {
   int64_t n_inliers;
   const uint32_t* inlier_matches;/* [n_inliers x 2] */
   double E[9], F[9], H[9];       /* row-major, zero when not estimated */
+  /* relative pose, filled when b2m_tvg_opts.compute_relative_pose (TwoViewGeometry::cam2_from_cam1, tri_angle;
+   * R:estimators/two_view_geometry.h:82-93): x_cam2 = R(qvec) x_cam1 + tvec, qvec = (w, x, y, z) */
+  double qvec[4], tvec[3];
+  double tri_angle;              /* median triangulation angle of the inliers, radians */
+  int32_t pose_valid;            /* 0: not requested / not recoverable (qvec = identity, tvec = 0) */
+  int32_t reserved;
 } b2m_pair_view;
 
 int64_t b2m_results_num_pairs(const b2m_results* r);
@@ -202,7 +209,9 @@ typedef struct b2m_tvg_result {
   int64_t n_inliers;
   double E[9], F[9], H[9];
   int32_t nE, nF, nH;            /* inlier counts of the three LO-RANSAC runs (diagnostic) */
-  int32_t reserved;
+  int32_t pose_valid;            /* see b2m_pair_view */
+  double qvec[4], tvec[3];
+  double tri_angle;
 } b2m_tvg_result;
 
 int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const double* points1, int64_t n1,

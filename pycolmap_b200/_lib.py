@@ -50,13 +50,15 @@ class Camera(ctypes.Structure):
 class PairView(ctypes.Structure):
     _fields_ = [("struct_size", c_u32), ("image1", c_i32), ("image2", c_i32), ("config", c_i32),
                 ("n_matches", c_i64), ("matches", ctypes.POINTER(c_u32)), ("n_inliers", c_i64),
-                ("inlier_matches", ctypes.POINTER(c_u32)), ("E", c_f64 * 9), ("F", c_f64 * 9), ("H", c_f64 * 9)]
+                ("inlier_matches", ctypes.POINTER(c_u32)), ("E", c_f64 * 9), ("F", c_f64 * 9), ("H", c_f64 * 9),
+                ("qvec", c_f64 * 4), ("tvec", c_f64 * 3), ("tri_angle", c_f64), ("pose_valid", c_i32),
+                ("reserved", c_i32)]
 
 
 class TvgResult(ctypes.Structure):
     _fields_ = [("struct_size", c_u32), ("config", c_i32), ("n_inliers", c_i64), ("E", c_f64 * 9),
                 ("F", c_f64 * 9), ("H", c_f64 * 9), ("nE", c_i32), ("nF", c_i32), ("nH", c_i32),
-                ("reserved", c_i32)]
+                ("pose_valid", c_i32), ("qvec", c_f64 * 4), ("tvec", c_f64 * 3), ("tri_angle", c_f64)]
 
 
 class TvgProblem(ctypes.Structure):

@@ -163,8 +163,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
   if (tvg && tvg->multiple_models)
     return fail(ctx, B2M_EINVAL, "[api.cu] multiple_models is available through b2m_estimate_two_view_geometry only "
                                  "(the pair pipeline verifies one geometry per pair)");
-  if (tvg && tvg->compute_relative_pose)
-    return fail(ctx, B2M_EINVAL, "[api.cu] compute_relative_pose is not supported (DESIGN.md section 7)");
+
   if (S.max_feat > sift->max_num_matches)
     return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: num descriptors <= SiftMatchingOptions.max_num_matches");
 
@@ -757,6 +756,13 @@ int b2m_results_get(const b2m_results* r, int64_t pair, b2m_pair_view* out) {
     memcpy(out->E, r->models.data() + 27 * pair, sizeof(double) * 9);
     memcpy(out->F, r->models.data() + 27 * pair + 9, sizeof(double) * 9);
     memcpy(out->H, r->models.data() + 27 * pair + 18, sizeof(double) * 9);
+  }
+  out->qvec[0] = 1.0;
+  if (r->verified && !r->pose_valid.empty() && r->pose_valid[pair]) {
+    memcpy(out->qvec, r->poses.data() + 8 * pair, sizeof(double) * 4);
+    memcpy(out->tvec, r->poses.data() + 8 * pair + 4, sizeof(double) * 3);
+    out->tri_angle = r->poses[8 * pair + 7];
+    out->pose_valid = 1;
   }
   return B2M_OK;
 }

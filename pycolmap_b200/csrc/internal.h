@@ -104,4 +104,6 @@ struct b2m_results {
   std::vector<int32_t> in_cnt;
   std::vector<uint32_t> inliers;
   std::vector<double> models;    // per pair 27 doubles: E, F, H
+  std::vector<double> poses;     // per pair 8 doubles: qvec (w, x, y, z), tvec, tri_angle (compute_relative_pose)
+  std::vector<int32_t> pose_valid;
 };

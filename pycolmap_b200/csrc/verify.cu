@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "geom.h"
+#include "pose.h"
 #include "verify.cuh"
 
 namespace b2m {
@@ -594,6 +595,182 @@ struct RansacStreams {
   cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
 };
 
+// ---- relative pose (TwoViewGeometryOptions.compute_relative_pose; pose.h) --------------------------------
+// EstimateTwoViewGeometryPose (U:estimators/two_view_geometry.cc; R:estimators/two_view_geometry.h:153-158) for
+// every pair of the batch, one CTA per pair: thread 0 decomposes E (CALIBRATED / UNCALIBRATED) or H (PLANAR /
+// PANORAMIC / PLANAR_OR_PANORAMIC) into candidate poses; all threads triangulate the inlier matches under each
+// candidate and count the points in front of both cameras (CheckCheirality); the candidate with the most points
+// wins (later candidates win ties, as upstream's `>=`); the median triangulation angle of its points becomes
+// tri_angle; PLANAR_OR_PANORAMIC is resolved into PANORAMIC (t == 0) or PLANAR.
+struct PoseParams {
+  const int32_t* pairs;      // [nb x 2] indices into cams (and img_row0)
+  const int64_t* pair_off;   // [nb] offset of the pair's inlier list / angle scratch
+  const int32_t* inl_cnt;    // [nb]
+  int32_t* config;           // [nb] in / out
+  const uint2* inliers;      // arena of (idx1, idx2)
+  const double* models;      // [nb][3][9]
+  const DevCamera* cams;
+  const DevDistortion* dist; // per camera, or nullptr when no camera has distortion
+  // pixel coordinates of a feature: keypoints by padded row (pair pipeline) ...
+  const float2* kpts;
+  const int32_t* img_row0;
+  // ... or the caller's point arrays (estimator entry points): [n x 2] doubles, per-problem offsets in points
+  const double* pts1;
+  const double* pts2;
+  const int64_t* pts1_off;
+  const int64_t* pts2_off;
+  double* angles;            // scratch arena, same offsets as the inlier lists
+  double* out;               // [nb][8]: qvec (w, x, y, z), tvec, tri_angle
+  int32_t* out_valid;        // [nb]
+};
+
+__device__ __forceinline__ void pose_norm_point(const PoseParams& P, int pair, int side, int img, uint32_t idx, double* u,
+                                                double* v) {
+  double x, y;
+  if (P.kpts) {
+    const float2 k = P.kpts[P.img_row0[img] + idx];
+    x = k.x;
+    y = k.y;
+  } else {
+    const double* p = (side == 0 ? P.pts1 : P.pts2) + 2 * ((side == 0 ? P.pts1_off : P.pts2_off)[pair] + idx);
+    x = p[0];
+    y = p[1];
+  }
+  const DevCamera c = P.cams[img];
+  if (P.dist && c.distorted) {
+    cam::cam_from_img(P.dist[img].model, P.dist[img].p, x, y, u, v);
+  } else {
+    *u = (x - c.cx) / c.fx;
+    *v = (y - c.cy) / c.fy;
+  }
+}
+
+__global__ void __launch_bounds__(256) b2m_pose_kernel(const PoseParams P) {
+  const int pair = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double sR[4][9], st[4][3], s_med[2];
+  __shared__ int s_ncand, s_warp[8], s_best, s_best_cnt;
+  const int cfg = P.config[pair];
+  const int n = P.inl_cnt[pair];
+  const int64_t off = P.pair_off[pair];
+  const int i1 = P.pairs[2 * pair], i2 = P.pairs[2 * pair + 1];
+  double* out = P.out + 8 * pair;
+  if (tid == 0) {
+    out[0] = 1.0;
+    for (int k = 1; k < 8; ++k) out[k] = 0.0;
+    P.out_valid[pair] = 0;
+  }
+  const bool from_E = cfg == B2M_CALIBRATED || cfg == B2M_UNCALIBRATED;
+  const bool from_H = cfg == B2M_PLANAR || cfg == B2M_PANORAMIC || cfg == B2M_PLANAR_OR_PANORAMIC;
+  if (!from_E && !from_H) return;  // uniform
+  if (tid == 0) {
+    if (from_E) {
+      double R1[9], R2[9], t[3];
+      pose::decompose_E(P.models + 27 * pair, R1, R2, t);
+      for (int c = 0; c < 4; ++c) {
+        for (int k = 0; k < 9; ++k) sR[c][k] = (c & 1) ? R2[k] : R1[k];
+        for (int k = 0; k < 3; ++k) st[c][k] = c < 2 ? t[k] : -t[k];
+      }
+      s_ncand = 4;
+    } else {
+      const DevCamera c1 = P.cams[i1], c2 = P.cams[i2];
+      const double K1[4] = {c1.fx, c1.fy, c1.cx, c1.cy}, K2[4] = {c2.fx, c2.fy, c2.cx, c2.cy};
+      double Rc[36], tc[12], nc[12];
+      s_ncand = pose::decompose_H(P.models + 27 * pair + 18, K1, K2, Rc, tc, nc);
+      for (int c = 0; c < s_ncand; ++c) {
+        for (int k = 0; k < 9; ++k) sR[c][k] = Rc[c * 9 + k];
+        for (int k = 0; k < 3; ++k) st[c][k] = tc[c * 3 + k];
+      }
+    }
+    s_best = 0;
+    s_best_cnt = -1;
+  }
+  __syncthreads();
+  const int n_cand = s_ncand;
+  for (int c = 0; c < n_cand; ++c) {
+    double Rm[9], tv[3];
+    for (int k = 0; k < 9; ++k) Rm[k] = sR[c][k];
+    for (int k = 0; k < 3; ++k) tv[k] = st[c][k];
+    const double max_depth = pose::cheirality_max_depth(Rm, tv);
+    int cnt = 0;
+    for (int k = tid; k < n; k += 256) {
+      const uint2 m = P.inliers[off + k];
+      double u1, v1, u2, v2, X[3];
+      pose_norm_point(P, pair, 0, i1, m.x, &u1, &v1);
+      pose_norm_point(P, pair, 1, i2, m.y, &u2, &v2);
+      if (pose::triangulate(Rm, tv, u1, v1, u2, v2, X) && pose::in_front_of_both(Rm, tv, X, max_depth)) ++cnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_warp[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+      int total = 0;
+      for (int w = 0; w < 8; ++w) total += s_warp[w];
+      if (c == 0 || total >= s_best_cnt) {  // upstream: points3D_cmb.size() >= points3D.size()
+        s_best = c;
+        s_best_cnt = total;
+      }
+    }
+    __syncthreads();
+  }
+  const int best = s_best, n_front = s_best_cnt;
+  if (from_E && n_front == 0) return;  // PoseFromEssentialMatrix found no point in front of both cameras: no pose
+  double Rm[9], tv[3];
+  for (int k = 0; k < 9; ++k) Rm[k] = sR[best][k];
+  for (int k = 0; k < 3; ++k) tv[k] = st[best][k];
+  // triangulation angles of the chosen candidate's points (-1 marks a point that failed the cheirality test)
+  {
+    const double c2[3] = {-(Rm[0] * tv[0] + Rm[3] * tv[1] + Rm[6] * tv[2]), -(Rm[1] * tv[0] + Rm[4] * tv[1] + Rm[7] * tv[2]),
+                          -(Rm[2] * tv[0] + Rm[5] * tv[1] + Rm[8] * tv[2])};
+    const double max_depth = pose::cheirality_max_depth(Rm, tv);
+    for (int k = tid; k < n; k += 256) {
+      const uint2 m = P.inliers[off + k];
+      double u1, v1, u2, v2, X[3], a = -1.0;
+      pose_norm_point(P, pair, 0, i1, m.x, &u1, &v1);
+      pose_norm_point(P, pair, 1, i2, m.y, &u2, &v2);
+      if (pose::triangulate(Rm, tv, u1, v1, u2, v2, X) && pose::in_front_of_both(Rm, tv, X, max_depth))
+        a = pose::triangulation_angle(c2, X);
+      P.angles[off + k] = a;
+    }
+  }
+  if (tid == 0) {
+    s_med[0] = s_med[1] = 0.0;
+  }
+  __syncthreads();
+  // median by rank counting (ties broken by position): elements of rank m - 1 and m of the n_front valid angles
+  if (n_front > 0) {
+    const int m = n_front / 2;
+    for (int k = tid; k < n; k += 256) {
+      const double a = P.angles[off + k];
+      if (a < 0.0) continue;
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const double b = P.angles[off + j];
+        rank += (b >= 0.0 && (b < a || (b == a && j < k))) ? 1 : 0;
+      }
+      if (rank == m) s_med[1] = a;
+      if (rank == m - 1) s_med[0] = a;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tri = 0.0;
+    if (n_front > 0) tri = (n_front % 2 == 0) ? 0.5 * (s_med[0] + s_med[1]) : s_med[1];
+    if (cfg == B2M_PLANAR_OR_PANORAMIC) {
+      if (tv[0] == 0.0 && tv[1] == 0.0 && tv[2] == 0.0) {
+        P.config[pair] = B2M_PANORAMIC;
+        tri = 0.0;
+      } else {
+        P.config[pair] = B2M_PLANAR;
+      }
+    }
+    pose::rotation_to_quat(Rm, out);
+    out[4] = tv[0]; out[5] = tv[1]; out[6] = tv[2];
+    out[7] = tri;
+    P.out_valid[pair] = 1;
+  }
+}
+
 // CamFromImg for camera models with distortion (row V9).  The E kernel normalises its input with the
 // affine map (p - c) / f, which is CamFromImg only for the pinhole models; for a pair with a distorted
 // camera this kernel writes "undistorted pixel" coordinates f * CamFromImg(p) + c into a second arena,
@@ -892,6 +1069,13 @@ struct VerifyState {
   int32_t* h_inl_cnt[2] = {nullptr, nullptr};
   uint2* h_inliers[2] = {nullptr, nullptr};
   DevCamera* d_cams = nullptr;
+  // relative pose (compute_relative_pose), lazily allocated
+  double* d_pose[2] = {nullptr, nullptr};        // [batch][8] qvec, tvec, tri_angle
+  int32_t* d_pose_valid[2] = {nullptr, nullptr};
+  double* h_pose[2] = {nullptr, nullptr};
+  int32_t* h_pose_valid[2] = {nullptr, nullptr};
+  double* d_angles = nullptr;                    // [arena_cap] triangulation-angle scratch
+  bool pose_on[2] = {false, false};
   DevDistortion* d_dist = nullptr;               // per image, only when any_distorted
   double4* d_pts_undist[2] = {nullptr, nullptr}; // E-kernel input per slot, lazily allocated
   bool any_distorted = false;
@@ -907,6 +1091,13 @@ struct VerifyState {
       h_models[s] = nullptr; h_config[s] = nullptr; h_inl_cnt[s] = nullptr; h_inliers[s] = nullptr;
     }
     cudaFree(d_mask); cudaFree(d_sup); cudaFree(d_success); cudaFree(d_cams);
+    for (int s = 0; s < 2; ++s) {
+      cudaFree(d_pose[s]); cudaFree(d_pose_valid[s]); cudaFreeHost(h_pose[s]); cudaFreeHost(h_pose_valid[s]);
+      d_pose[s] = nullptr; d_pose_valid[s] = nullptr; h_pose[s] = nullptr; h_pose_valid[s] = nullptr;
+      pose_on[s] = false;
+    }
+    cudaFree(d_angles);
+    d_angles = nullptr;
     cudaFree(d_dist); cudaFree(d_pts_undist[0]); cudaFree(d_pts_undist[1]);
     d_dist = nullptr; d_pts_undist[0] = d_pts_undist[1] = nullptr; any_distorted = false;
     cudaFree(d_guided_kind); cudaFree(d_guided_model);
@@ -1059,6 +1250,8 @@ void verify_results_init(b2m_results* res, int64_t n_pairs) {
   res->in_off.assign(n_pairs, 0);
   res->in_cnt.assign(n_pairs, 0);
   res->models.assign(27 * n_pairs, 0.0);
+  res->poses.clear();
+  res->pose_valid.clear();
 }
 
 int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, const b2m_sift_opts* sift, int s,
@@ -1098,7 +1291,6 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
     cudaMemset(V->d_prof, 0, sizeof(unsigned long long) * 24);
   }
   P.prof = V->d_prof;
-  (void)S;
   if (!V->rs.side[0]) {
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[0], cudaStreamNonBlocking));
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[1], cudaStreamNonBlocking));
@@ -1119,6 +1311,34 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
   b2m_decide_kernel<<<nb, 256, 0, ctx->stream>>>(P);
   V_TRY(ctx, cudaGetLastError());
   ctx->stats.kernel_launches += 2;
+  V->pose_on[s] = false;
+  if (tvg->compute_relative_pose) {  // EstimateTwoViewGeometryPose on the verified pairs of the batch
+    if (!V->d_angles) V_TRY(ctx, cudaMalloc(&V->d_angles, sizeof(double) * V->arena_cap));
+    if (!V->d_pose[s]) {
+      V_TRY(ctx, cudaMalloc(&V->d_pose[s], sizeof(double) * 8 * V->batch));
+      V_TRY(ctx, cudaMalloc(&V->d_pose_valid[s], sizeof(int32_t) * V->batch));
+      V_TRY(ctx, cudaMallocHost(&V->h_pose[s], sizeof(double) * 8 * V->batch));
+      V_TRY(ctx, cudaMallocHost(&V->h_pose_valid[s], sizeof(int32_t) * V->batch));
+    }
+    PoseParams Q{};
+    Q.pairs = P.pairs;
+    Q.pair_off = P.pair_off;
+    Q.inl_cnt = P.inl_cnt;
+    Q.config = P.config;
+    Q.inliers = P.inliers;
+    Q.models = P.models;
+    Q.cams = P.cams;
+    Q.dist = V->any_distorted ? V->d_dist : nullptr;
+    Q.kpts = S.d_kpts;
+    Q.img_row0 = S.d_row0;
+    Q.angles = V->d_angles;
+    Q.out = V->d_pose[s];
+    Q.out_valid = V->d_pose_valid[s];
+    b2m_pose_kernel<<<nb, 256, 0, ctx->stream>>>(Q);
+    V_TRY(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 1;
+    V->pose_on[s] = true;
+  }
   return B2M_OK;
 }
 
@@ -1135,6 +1355,11 @@ int verify_batch_download(b2m_ctx* ctx, b2m_results*, int s, int64_t, int nb) {
   if (total > 0)
     V_TRY(ctx, cudaMemcpyAsync(V->h_inliers[s], V->d_inliers[s], sizeof(uint2) * total, cudaMemcpyDeviceToHost,
                                ctx->copy_stream));
+  if (V->pose_on[s]) {
+    V_TRY(ctx, cudaMemcpyAsync(V->h_pose[s], V->d_pose[s], sizeof(double) * 8 * nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    V_TRY(ctx, cudaMemcpyAsync(V->h_pose_valid[s], V->d_pose_valid[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+  }
   if (V->guided_on[s]) {
     const unsigned long long gtotal = *V->h_gcursor[s];
     V_TRY(ctx, cudaMemcpyAsync(V->h_goff[s], V->d_goff[s], sizeof(int64_t) * nb, cudaMemcpyDeviceToHost,
@@ -1172,6 +1397,18 @@ int verify_batch_collect(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int 
     if (ni < min_num_inliers) {
       cfg = B2M_UNDEFINED;
       ni = 0;
+    }
+    if (V->pose_on[s]) {
+      if (res->poses.empty()) {
+        const size_t np = res->config.size();
+        res->poses.assign(8 * np, 0.0);
+        for (size_t q = 0; q < np; ++q) res->poses[8 * q] = 1.0;
+        res->pose_valid.assign(np, 0);
+      }
+      if (ni > 0 && V->h_pose_valid[s][k]) {
+        memcpy(res->poses.data() + 8 * p, V->h_pose[s] + 8 * k, sizeof(double) * 8);
+        res->pose_valid[p] = 1;
+      }
     }
     res->config[p] = cfg;
     res->in_cnt[p] = ni;
@@ -1221,11 +1458,78 @@ struct Single {
   double* d_models = nullptr;
   DevDistortion* d_dist = nullptr;  // only when a camera has distortion
   double4* d_pts_undist = nullptr;
+  // compute_relative_pose
+  double *d_p1 = nullptr, *d_p2 = nullptr, *d_angles = nullptr, *d_pose = nullptr;
+  int64_t *d_p1_off = nullptr, *d_p2_off = nullptr;
+  int32_t* d_pose_valid = nullptr;
   ~Single() {
     cudaFree(d_pts); cudaFree(d_matches); cudaFree(d_inliers); cudaFree(d_mask); cudaFree(d_cams);
     cudaFree(d_i32); cudaFree(d_off); cudaFree(d_models); cudaFree(d_dist); cudaFree(d_pts_undist);
+    cudaFree(d_p1); cudaFree(d_p2); cudaFree(d_angles); cudaFree(d_pose); cudaFree(d_p1_off); cudaFree(d_p2_off);
+    cudaFree(d_pose_valid);
   }
 };
+
+// Stand-alone estimator calls with compute_relative_pose: upload the callers' point arrays (concatenated over the
+// `nb` problems, offsets in points) and run the pose kernel after the decision kernel.  `P` is the VerifyParams the
+// RANSAC / decision kernels ran with; G.d_dist may be null (no distortion).  Outputs stay in G.d_pose / d_pose_valid.
+int launch_pose_standalone(b2m_ctx* ctx, Single& G, const VerifyParams& P, int nb, int64_t cap, const std::vector<double>& p1,
+                           const std::vector<double>& p2, const std::vector<int64_t>& off1, const std::vector<int64_t>& off2,
+                           const b2m_camera* const* cams, int n_cams, cudaStream_t st) {
+  V_TRY(ctx, cudaMalloc(&G.d_p1, sizeof(double) * std::max<size_t>(p1.size(), 2)));
+  V_TRY(ctx, cudaMalloc(&G.d_p2, sizeof(double) * std::max<size_t>(p2.size(), 2)));
+  V_TRY(ctx, cudaMalloc(&G.d_p1_off, sizeof(int64_t) * nb));
+  V_TRY(ctx, cudaMalloc(&G.d_p2_off, sizeof(int64_t) * nb));
+  V_TRY(ctx, cudaMalloc(&G.d_angles, sizeof(double) * cap));
+  V_TRY(ctx, cudaMalloc(&G.d_pose, sizeof(double) * 8 * nb));
+  V_TRY(ctx, cudaMalloc(&G.d_pose_valid, sizeof(int32_t) * nb));
+  if (!G.d_dist) {  // undistort_for_E uploads the models only when it had to; the pose kernel needs them as well
+    bool any = false;
+    for (int i = 0; i < n_cams; ++i) any = any || cam::has_distortion(cams[i]->model);
+    if (any) {
+      std::vector<DevDistortion> dd(n_cams);
+      for (int i = 0; i < n_cams; ++i) dd[i] = to_dist(*cams[i]);
+      V_TRY(ctx, cudaMalloc(&G.d_dist, sizeof(DevDistortion) * n_cams));
+      V_TRY(ctx, cudaMemcpy(G.d_dist, dd.data(), sizeof(DevDistortion) * n_cams, cudaMemcpyHostToDevice));
+    }
+  }
+  // synchronous copies: the host vectors are the caller's locals
+  if (!p1.empty()) V_TRY(ctx, cudaMemcpy(G.d_p1, p1.data(), sizeof(double) * p1.size(), cudaMemcpyHostToDevice));
+  if (!p2.empty()) V_TRY(ctx, cudaMemcpy(G.d_p2, p2.data(), sizeof(double) * p2.size(), cudaMemcpyHostToDevice));
+  V_TRY(ctx, cudaMemcpy(G.d_p1_off, off1.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice));
+  V_TRY(ctx, cudaMemcpy(G.d_p2_off, off2.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice));
+  PoseParams Q{};
+  Q.pairs = P.pairs;
+  Q.pair_off = P.pair_off;
+  Q.inl_cnt = P.inl_cnt;
+  Q.config = P.config;
+  Q.inliers = P.inliers;
+  Q.models = P.models;
+  Q.cams = P.cams;
+  Q.dist = G.d_dist;
+  Q.pts1 = G.d_p1;
+  Q.pts2 = G.d_p2;
+  Q.pts1_off = G.d_p1_off;
+  Q.pts2_off = G.d_p2_off;
+  Q.angles = G.d_angles;
+  Q.out = G.d_pose;
+  Q.out_valid = G.d_pose_valid;
+  b2m_pose_kernel<<<nb, 256, 0, st>>>(Q);
+  V_TRY(ctx, cudaGetLastError());
+  ctx->stats.kernel_launches += 1;
+  return B2M_OK;
+}
+
+// copy the pose of problem k (device arrays already downloaded into h_pose / h_valid) into a result
+void fill_pose(b2m_tvg_result* r, const double* h_pose, const int32_t* h_valid, int k) {
+  r->qvec[0] = 1.0;
+  if (h_pose && h_valid && h_valid[k] && r->n_inliers > 0) {
+    memcpy(r->qvec, h_pose + 8 * k, sizeof(double) * 4);
+    memcpy(r->tvec, h_pose + 8 * k + 4, sizeof(double) * 3);
+    r->tri_angle = h_pose[8 * k + 7];
+    r->pose_valid = 1;
+  }
+}
 
 // Stand-alone estimator calls: upload the full camera models and undistort the E-kernel input when any
 // of the `n_cams` cameras has a distortion function.  Returns the E arena (nullptr: use P.pts) in *pts_E.
@@ -1252,7 +1556,8 @@ int undistort_for_E(b2m_ctx* ctx, Single& G, const VerifyParams& P, const b2m_ca
 // caller's points are already in the frame the model is estimated in).
 int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<uint2>& matches, const DevCamera cams[2],
                const b2m_tvg_opts& opt, int single_kind, Single& G, VerifyParams& P,
-               const b2m_camera* const* full_cams = nullptr) {
+               const b2m_camera* const* full_cams = nullptr, const double* raw1 = nullptr, int64_t n1 = 0,
+               const double* raw2 = nullptr, int64_t n2 = 0) {
   const int64_t m = static_cast<int64_t>(pts.size());
   const int64_t cap = std::max<int64_t>(m, 1);
   V_TRY(ctx, cudaMalloc(&G.d_pts, sizeof(double4) * cap));
@@ -1302,6 +1607,12 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
     ctx->stats.kernel_launches += 2;
     b2m_decide_kernel<<<1, 256, 0, st>>>(P);
     ctx->stats.kernel_launches += 1;
+    if (opt.compute_relative_pose && full_cams) {
+      V_TRY(ctx, cudaGetLastError());
+      const std::vector<double> p1(raw1, raw1 + 2 * n1), p2(raw2, raw2 + 2 * n2);
+      const std::vector<int64_t> zero(1, 0);
+      if (int rc = launch_pose_standalone(ctx, G, P, 1, cap, p1, p2, zero, zero, full_cams, 2, st)) return rc;
+    }
   }
   V_TRY(ctx, cudaGetLastError());
   ctx->stats.kernel_launches += 1;
@@ -1342,7 +1653,6 @@ static int estimate_tvg_once(b2m_ctx* ctx, const b2m_camera* cam1, const double*
   if (const char* why = camera_problem(*cam1)) return bad(why);
   if (const char* why = camera_problem(*cam2)) return bad(why);
   if (n1 < 0 || n2 < 0 || (n1 > 0 && !points1) || (n2 > 0 && !points2)) return bad("[verify.cu] Check Failed: points");
-  if (opts->compute_relative_pose) return bad("[verify.cu] compute_relative_pose is not supported (DESIGN.md section 7)");
   if (!matches) {  // identity matching (R:estimators/two_view_geometry.h:136-142)
     if (n1 != n2) return bad("[verify.cu] Check Failed: points1.size() == points2.size()");
     m = n1;
@@ -1362,16 +1672,23 @@ static int estimate_tvg_once(b2m_ctx* ctx, const b2m_camera* cam1, const double*
   Single G;
   VerifyParams P;
   const b2m_camera* full_cams[2] = {cam1, cam2};
-  if (int rc = run_single(ctx, pts, mm, cams, *opts, -1, G, P, full_cams)) return rc;
+  if (int rc = run_single(ctx, pts, mm, cams, *opts, -1, G, P, full_cams, points1, n1, points2, n2)) return rc;
   int32_t i32[16];
   double models[27];
+  double h_pose[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  int32_t h_pose_valid = 0;
   V_TRY(ctx, cudaMemcpyAsync(i32, G.d_i32, sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
   V_TRY(ctx, cudaMemcpyAsync(models, G.d_models, sizeof(models), cudaMemcpyDeviceToHost, ctx->stream));
+  if (G.d_pose) {
+    V_TRY(ctx, cudaMemcpyAsync(h_pose, G.d_pose, sizeof(h_pose), cudaMemcpyDeviceToHost, ctx->stream));
+    V_TRY(ctx, cudaMemcpyAsync(&h_pose_valid, G.d_pose_valid, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   V_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   memset(out, 0, sizeof(*out));
   out->struct_size = sizeof(*out);
   out->config = i32[9];
   out->n_inliers = i32[10];
+  fill_pose(out, h_pose, &h_pose_valid, 0);
   out->nE = i32[3]; out->nF = i32[4]; out->nH = i32[5];
   memcpy(out->E, models, sizeof(double) * 9);
   memcpy(out->F, models + 9, sizeof(double) * 9);
@@ -1448,6 +1765,7 @@ int b2m_estimate_two_view_geometry(b2m_ctx* ctx, const b2m_camera* cam1, const d
   }
   memset(out, 0, sizeof(*out));
   out->struct_size = sizeof(*out);
+  out->qvec[0] = 1.0;
   if (found.empty()) {
     out->config = B2M_DEGENERATE;
     return B2M_OK;
@@ -1501,10 +1819,18 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     std::vector<int32_t> cnt(nb), pairs(2 * nb);
     std::vector<DevCamera> cams(2 * nb);
     std::vector<const b2m_camera*> full_cams(2 * nb);
+    std::vector<double> raw1, raw2;            // compute_relative_pose: the callers' point arrays, concatenated
+    std::vector<int64_t> raw1_off(nb, 0), raw2_off(nb, 0);
     for (int k = 0; k < nb; ++k) {
       const b2m_tvg_problem& q = problems[k0 + k];
       full_cams[2 * k] = &q.cam1;
       full_cams[2 * k + 1] = &q.cam2;
+      if (opts->compute_relative_pose) {
+        raw1_off[k] = static_cast<int64_t>(raw1.size() / 2);
+        raw2_off[k] = static_cast<int64_t>(raw2.size() / 2);
+        raw1.insert(raw1.end(), q.points1, q.points1 + 2 * q.n1);
+        raw2.insert(raw2.end(), q.points2, q.points2 + 2 * q.n2);
+      }
       const int64_t m = q.matches ? q.m : q.n1;
       off[k] = static_cast<int64_t>(pts.size());
       cnt[k] = static_cast<int32_t>(m);
@@ -1567,6 +1893,15 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     b2m_decide_kernel<<<nb, 256, 0, st>>>(P);
     V_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += 4;
+    if (opts->compute_relative_pose)
+      if (int rc = launch_pose_standalone(ctx, G, P, nb, cap, raw1, raw2, raw1_off, raw2_off, full_cams.data(), 2 * nb, st))
+        return rc;
+    std::vector<double> h_pose(static_cast<size_t>(8) * nb, 0.0);
+    std::vector<int32_t> h_pose_valid(nb, 0);
+    if (G.d_pose) {
+      V_TRY(ctx, cudaMemcpyAsync(h_pose.data(), G.d_pose, sizeof(double) * 8 * nb, cudaMemcpyDeviceToHost, st));
+      V_TRY(ctx, cudaMemcpyAsync(h_pose_valid.data(), G.d_pose_valid, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+    }
     std::vector<int32_t> h_i32(static_cast<size_t>(11) * nb);
     std::vector<double> h_models(static_cast<size_t>(27) * nb);
     std::vector<uint2> h_inl(static_cast<size_t>(cap));
@@ -1587,6 +1922,7 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
       memcpy(r.E, h_models.data() + 27 * k, sizeof(double) * 9);
       memcpy(r.F, h_models.data() + 27 * k + 9, sizeof(double) * 9);
       memcpy(r.H, h_models.data() + 27 * k + 18, sizeof(double) * 9);
+      fill_pose(&r, h_pose.data(), h_pose_valid.data(), k);
       if (r.n_inliers > 0 && inlier_matches && inlier_matches[k0 + k])
         memcpy(inlier_matches[k0 + k], h_inl.data() + off[k], sizeof(uint2) * r.n_inliers);
     }

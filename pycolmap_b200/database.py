@@ -173,11 +173,11 @@ class Database:
 
     def read_two_view_geometry(self, id1, id2):
         """R:scene/database.h:30-33.  Returns dict(config, F, E, H, inlier_matches)."""
-        row = self.con.execute("SELECT rows, cols, data, config, F, E, H FROM two_view_geometries WHERE pair_id = ?",
+        row = self.con.execute("SELECT rows, cols, data, config, F, E, H, qvec, tvec FROM two_view_geometries WHERE pair_id = ?",
                                (image_pair_to_pair_id(id1, id2),)).fetchone()
         if row is None:
             return None
-        rows, cols, data, config, F, E, H = row
+        rows, cols, data, config, F, E, H, qvec, tvec = row
         inl = np.frombuffer(data, np.uint32).reshape(rows, 2).copy() if rows else np.zeros((0, 2), np.uint32)
 
         def mat(b):
@@ -187,7 +187,15 @@ class Database:
             inl = inl[:, ::-1].copy()
             F, E = F.T.copy(), E.T.copy()
             H = np.linalg.inv(H) if np.abs(H).sum() > 0 else H
-        return dict(config=int(config), F=F, E=E, H=H, inlier_matches=inl)
+        q = np.frombuffer(qvec, np.float64).copy() if qvec and len(qvec) == 32 else np.array([1.0, 0, 0, 0])
+        t = np.frombuffer(tvec, np.float64).copy() if tvec and len(tvec) == 24 else np.zeros(3)
+        if id1 > id2 and (np.any(t != 0) or not np.array_equal(q, [1.0, 0, 0, 0])):
+            w, x, y, z = q
+            Rm = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                           [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                           [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            q, t = np.array([w, -x, -y, -z]), -Rm.T @ t
+        return dict(config=int(config), F=F, E=E, H=H, inlier_matches=inl, qvec=q, tvec=t)
 
     # -- result writers (U:scene/database.cc WriteMatches / WriteTwoViewGeometry) --------------------
     def write_matches(self, id1, id2, matches):
@@ -197,7 +205,7 @@ class Database:
         self.con.execute("INSERT OR REPLACE INTO matches VALUES (?, ?, ?, ?)",
                          (image_pair_to_pair_id(id1, id2), m.shape[0], 2, m.tobytes()))
 
-    def write_two_view_geometry(self, id1, id2, config, inlier_matches, F=None, E=None, H=None):
+    def write_two_view_geometry(self, id1, id2, config, inlier_matches, F=None, E=None, H=None, qvec=None, tvec=None):
         m = np.ascontiguousarray(inlier_matches, np.uint32).reshape(-1, 2)
         F = np.zeros((3, 3)) if F is None else np.asarray(F, np.float64)
         E = np.zeros((3, 3)) if E is None else np.asarray(E, np.float64)
@@ -206,8 +214,15 @@ class Database:
             m = np.ascontiguousarray(m[:, ::-1])
             F, E = F.T, E.T
             H = np.linalg.inv(H) if np.abs(H).sum() > 0 else H
-        qvec = np.array([1.0, 0, 0, 0])
-        tvec = np.zeros(3)
+        qvec = np.array([1.0, 0, 0, 0]) if qvec is None else np.asarray(qvec, np.float64).reshape(4)   # (w, x, y, z)
+        tvec = np.zeros(3) if tvec is None else np.asarray(tvec, np.float64).reshape(3)
+        if id1 > id2 and (np.any(tvec != 0) or not np.array_equal(qvec, [1.0, 0, 0, 0])):
+            # cam2_from_cam1 of the swapped pair = the inverse pose (the identity stays bit-for-bit the identity)
+            w, x, y, z = qvec
+            Rm = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                           [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                           [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            qvec, tvec = np.array([w, -x, -y, -z]), -Rm.T @ tvec
         self.con.execute("INSERT OR REPLACE INTO two_view_geometries VALUES (?, ?, ?, ?, ?, ?, ?, ?, ?, ?)",
                          (image_pair_to_pair_id(id1, id2), m.shape[0], 2, m.tobytes(), int(config),
                           np.ascontiguousarray(F).tobytes(), np.ascontiguousarray(E).tobytes(),

@@ -16,6 +16,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cstring>
@@ -102,14 +103,26 @@ py::dict CameraToDict(const CameraRow& c) {
 }
 
 // ---- TwoViewGeometry (R:estimators/two_view_geometry.h:82-93) --------------------------------------
+// Minimal stand-ins for pycolmap.Rotation3d / Rigid3d (R:geometry bindings): x_cam2 = rotation * x_cam1 + translation.
+struct Rotation3d {
+  std::array<double, 4> wxyz{1.0, 0.0, 0.0, 0.0};
+};
+struct Rigid3d {
+  Rotation3d rotation;
+  std::array<double, 3> translation{0.0, 0.0, 0.0};
+};
+
 struct TwoViewGeometry {
   TwoViewGeometryConfiguration config = TwoViewGeometryConfiguration::UNDEFINED;
   Mat3 E{}, F{}, H{};
   std::vector<uint32_t> inlier_matches;
   double tri_angle = 0.0;
+  std::array<double, 4> qvec{1.0, 0.0, 0.0, 0.0};  // cam2_from_cam1 (w, x, y, z); identity unless a pose was recovered
+  std::array<double, 3> tvec{0.0, 0.0, 0.0};
   int nE = 0, nF = 0, nH = 0;  // diagnostic inlier counts of the three LO-RANSAC runs
 
   void Invert() {
+    InvertPose(&qvec, &tvec);
     F = Transposed(F);
     E = Transposed(E);
     Mat3 inv;
@@ -205,6 +218,9 @@ TwoViewGeometry EstimateTvg(const std::function<b2m_ctx*()>& get_ctx, const py::
   inl.resize(static_cast<size_t>(r.n_inliers) * 2);
   g.inlier_matches = std::move(inl);
   g.nE = r.nE; g.nF = r.nF; g.nH = r.nH;
+  std::copy(r.qvec, r.qvec + 4, g.qvec.begin());
+  std::copy(r.tvec, r.tvec + 3, g.tvec.begin());
+  g.tri_angle = r.tri_angle;
   return g;
 }
 
@@ -370,11 +386,45 @@ PYBIND11_MODULE(_core, m) {
       .field("ransac", &TwoViewGeometryOptions::ransac)
       .Finish();
 
+  py::class_<Rotation3d>(m, "Rotation3d")
+      .def(py::init<>())
+      .def_property_readonly("quat", [](const Rotation3d& r) {   // (x, y, z, w) like the reference's Eigen coefficients
+        py::array_t<double> a(4);
+        double* p = a.mutable_data();
+        p[0] = r.wxyz[1]; p[1] = r.wxyz[2]; p[2] = r.wxyz[3]; p[3] = r.wxyz[0];
+        return a;
+      })
+      .def("matrix", [](const Rotation3d& r) { return MatToNumpy(QuatToRotation(r.wxyz).data()); });
+  py::class_<Rigid3d>(m, "Rigid3d")
+      .def(py::init<>())
+      .def_readonly("rotation", &Rigid3d::rotation)
+      .def_property_readonly("translation", [](const Rigid3d& g) {
+        py::array_t<double> a(3);
+        std::copy(g.translation.begin(), g.translation.end(), a.mutable_data());
+        return a;
+      })
+      .def("matrix", [](const Rigid3d& g) {
+        const Mat3 R = QuatToRotation(g.rotation.wxyz);
+        py::array_t<double> a(std::vector<py::ssize_t>{3, 4});
+        double* p = a.mutable_data();
+        for (int i = 0; i < 3; ++i) {
+          for (int j = 0; j < 3; ++j) p[i * 4 + j] = R[i * 3 + j];
+          p[i * 4 + 3] = g.translation[i];
+        }
+        return a;
+      })
+      .def("inverse", [](const Rigid3d& g) {
+        Rigid3d o = g;
+        InvertPose(&o.rotation.wxyz, &o.translation);
+        return o;
+      });
+
   // ---- TwoViewGeometry ----
   py::class_<TwoViewGeometry>(m, "TwoViewGeometry")
       .def(py::init<>())
       .def(py::init([](TwoViewGeometryConfiguration config, const py::object& E, const py::object& F,
-                       const py::object& H, const py::object& inlier_matches, double tri_angle) {
+                       const py::object& H, const py::object& inlier_matches, double tri_angle, const py::object& qvec,
+                       const py::object& tvec) {
              TwoViewGeometry g;
              g.config = config;
              auto mat = [](const py::object& o, Mat3* out) {
@@ -390,16 +440,26 @@ PYBIND11_MODULE(_core, m) {
                g.inlier_matches.assign(a.data(), a.data() + a.size());
              }
              g.tri_angle = tri_angle;
+             auto vec = [](const py::object& o, double* out, py::ssize_t n, const char* what) {
+               if (o.is_none()) return;
+               const ArrD a = ArrD::ensure(o);
+               if (!a || a.size() != n) throw std::invalid_argument(std::string("[bindings.cc] Check Failed: ") + what);
+               std::copy(a.data(), a.data() + n, out);
+             };
+             vec(qvec, g.qvec.data(), 4, "qvec = (w, x, y, z)");
+             vec(tvec, g.tvec.data(), 3, "tvec has 3 entries");
              return g;
            }),
            "config"_a = TwoViewGeometryConfiguration::UNDEFINED, "E"_a = py::none(), "F"_a = py::none(),
-           "H"_a = py::none(), "inlier_matches"_a = py::none(), "tri_angle"_a = 0.0)
+           "H"_a = py::none(), "inlier_matches"_a = py::none(), "tri_angle"_a = 0.0, "qvec"_a = py::none(),
+           "tvec"_a = py::none())
       .def_property_readonly("config", [](const TwoViewGeometry& g) { return g.config; })
       .def_property_readonly("E", [](const TwoViewGeometry& g) { return MatToNumpy(g.E.data()); })
       .def_property_readonly("F", [](const TwoViewGeometry& g) { return MatToNumpy(g.F.data()); })
       .def_property_readonly("H", [](const TwoViewGeometry& g) { return MatToNumpy(g.H.data()); })
-      .def_property_readonly("cam2_from_cam1", [](const TwoViewGeometry&) { return py::none(); },
-                             "Not estimated: compute_relative_pose is out of scope (DESIGN.md section 7).")
+      .def_property_readonly("cam2_from_cam1",
+                             [](const TwoViewGeometry& g) { return Rigid3d{Rotation3d{g.qvec}, g.tvec}; },
+                             "Relative pose (identity unless options.compute_relative_pose recovered one).")
       .def_property_readonly("inlier_matches",
                              [](const TwoViewGeometry& g) {
                                return MatchesToNumpy(g.inlier_matches.data(),
@@ -524,6 +584,9 @@ PYBIND11_MODULE(_core, m) {
             inl[k].resize(static_cast<size_t>(r[k].n_inliers) * 2);
             out[k].inlier_matches = std::move(inl[k]);
             out[k].nE = r[k].nE; out[k].nF = r[k].nF; out[k].nH = r[k].nH;
+            std::copy(r[k].qvec, r[k].qvec + 4, out[k].qvec.begin());
+            std::copy(r[k].tvec, r[k].tvec + 3, out[k].tvec.begin());
+            out[k].tri_angle = r[k].tri_angle;
           }
           return out;
         },
@@ -694,6 +757,7 @@ PYBIND11_MODULE(_core, m) {
              TwoViewGeometry g;
              g.config = static_cast<TwoViewGeometryConfiguration>(row.config);
              g.E = row.E; g.F = row.F; g.H = row.H;
+             g.qvec = row.qvec; g.tvec = row.tvec;
              g.inlier_matches = std::move(row.inlier_matches);
              return py::cast(std::move(g));
            },
@@ -707,7 +771,7 @@ PYBIND11_MODULE(_core, m) {
       .def("write_two_view_geometry",
            [](Database& db, int64_t id1, int64_t id2, const TwoViewGeometry& g) {
              db.WriteTwoViewGeometry(id1, id2, static_cast<int>(g.config), g.inlier_matches.data(),
-                                     static_cast<int64_t>(g.inlier_matches.size() / 2), g.F, g.E, g.H);
+                                     static_cast<int64_t>(g.inlier_matches.size() / 2), g.F, g.E, g.H, g.qvec, g.tvec);
            },
            "image_id1"_a, "image_id2"_a, "two_view_geometry"_a)
       .def("clear_matches", &Database::ClearMatches)
@@ -737,6 +801,9 @@ PYBIND11_MODULE(_core, m) {
         std::copy(v.F, v.F + 9, g.F.begin());
         std::copy(v.H, v.H + 9, g.H.begin());
         g.inlier_matches.assign(v.inlier_matches, v.inlier_matches + 2 * v.n_inliers);
+        std::copy(v.qvec, v.qvec + 4, g.qvec.begin());
+        std::copy(v.tvec, v.tvec + 3, g.tvec.begin());
+        g.tri_angle = v.tri_angle;
         return g;
       })
       .def("image_pair", [](const CoreResults& r, int64_t k) {

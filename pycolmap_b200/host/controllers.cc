@@ -347,7 +347,7 @@ void MatchPairsIntoDb(Database& db, const std::vector<b2m_ctx*>& ctxs, const Loa
         const int64_t id1 = L.ids[todo[2 * (cut[d] + k)]], id2 = L.ids[todo[2 * (cut[d] + k) + 1]];
         db.WriteMatches(id1, id2, v.matches, v.n_matches);
         db.WriteTwoViewGeometry(id1, id2, v.config, v.inlier_matches, v.n_inliers, ToMat3(v.F), ToMat3(v.E),
-                                ToMat3(v.H));
+                                ToMat3(v.H), {v.qvec[0], v.qvec[1], v.qvec[2], v.qvec[3]}, {v.tvec[0], v.tvec[1], v.tvec[2]});
       }
     }
   }
@@ -442,6 +442,8 @@ void VerifyMatches(const std::string& database_path, const std::string& pairs_pa
     int config = B2M_UNDEFINED;
     std::vector<uint32_t> inl;
     Mat3 E{}, F{}, H{};
+    std::array<double, 4> qvec{1.0, 0.0, 0.0, 0.0};
+    std::array<double, 3> tvec{0.0, 0.0, 0.0};
     if (n_m >= options.min_num_inliers) {
       auto points = [&](int64_t id) {
         const KeypointsBlob kp = db.ReadKeypoints(id);
@@ -464,13 +466,17 @@ void VerifyMatches(const std::string& database_path, const std::string& pairs_pa
       inl.resize(static_cast<size_t>(r.n_inliers) * 2);
       config = r.config;
       E = ToMat3(r.E); F = ToMat3(r.F); H = ToMat3(r.H);
+      qvec = {r.qvec[0], r.qvec[1], r.qvec[2], r.qvec[3]};
+      tvec = {r.tvec[0], r.tvec[1], r.tvec[2]};
     }
     if (static_cast<int64_t>(inl.size() / 2) < options.min_num_inliers) {  // controller write rule (row P3)
       config = B2M_UNDEFINED;
       inl.clear();
       E = F = H = Mat3{};
+      qvec = {1.0, 0.0, 0.0, 0.0};
+      tvec = {0.0, 0.0, 0.0};
     }
-    db.WriteTwoViewGeometry(id1, id2, config, inl.data(), static_cast<int64_t>(inl.size() / 2), F, E, H);
+    db.WriteTwoViewGeometry(id1, id2, config, inl.data(), static_cast<int64_t>(inl.size() / 2), F, E, H, qvec, tvec);
   }
 }
 

@@ -63,6 +63,25 @@ bool Invert3x3(const Mat3& m, Mat3* out) {
   return true;
 }
 
+Mat3 QuatToRotation(const std::array<double, 4>& q) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  return Mat3{1 - 2 * (y * y + z * z), 2 * (x * y - z * w),     2 * (x * z + y * w),
+              2 * (x * y + z * w),     1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+              2 * (x * z - y * w),     2 * (y * z + x * w),     1 - 2 * (x * x + y * y)};
+}
+
+void InvertPose(std::array<double, 4>* q, std::array<double, 3>* t) {
+  // the identity (no pose estimated) stays bit-for-bit the identity: no -0.0 in the database
+  if ((*q)[0] == 1.0 && (*q)[1] == 0.0 && (*q)[2] == 0.0 && (*q)[3] == 0.0 && (*t)[0] == 0.0 && (*t)[1] == 0.0 && (*t)[2] == 0.0)
+    return;
+  const Mat3 R = QuatToRotation(*q);
+  const std::array<double, 3> o = *t;
+  for (int i = 0; i < 3; ++i) (*t)[i] = -(R[i] * o[0] + R[3 + i] * o[1] + R[6 + i] * o[2]);  // -R^T t
+  (*q)[1] = -(*q)[1];
+  (*q)[2] = -(*q)[2];
+  (*q)[3] = -(*q)[3];
+}
+
 Mat3 Transposed(const Mat3& m) { return Mat3{m[0], m[3], m[6], m[1], m[4], m[7], m[2], m[5], m[8]}; }
 
 // ---- RAII prepared statement ---------------------------------------------------------------------
@@ -275,7 +294,7 @@ std::vector<uint32_t> Database::ReadMatches(int64_t id1, int64_t id2) {
 }
 
 bool Database::ReadTwoViewGeometry(int64_t id1, int64_t id2, TwoViewGeometryRow* out) {
-  Stmt s(this, "SELECT rows, cols, data, config, F, E, H FROM two_view_geometries WHERE pair_id = ?");
+  Stmt s(this, "SELECT rows, cols, data, config, F, E, H, qvec, tvec FROM two_view_geometries WHERE pair_id = ?");
   s.I64(1, ImagePairToPairId(id1, id2));
   if (!s.Step()) return false;
   TwoViewGeometryRow g;
@@ -290,7 +309,13 @@ bool Database::ReadTwoViewGeometry(int64_t id1, int64_t id2, TwoViewGeometryRow*
     if (v.size() == 9) std::copy(v.begin(), v.end(), m->begin());
   };
   mat(4, &g.F); mat(5, &g.E); mat(6, &g.H);
+  {
+    const std::vector<double> q = s.ColBlob<double>(7), t = s.ColBlob<double>(8);
+    if (q.size() == 4) std::copy(q.begin(), q.end(), g.qvec.begin());
+    if (t.size() == 3) std::copy(t.begin(), t.end(), g.tvec.begin());
+  }
   if (id1 > id2) {  // TwoViewGeometry::Invert (R:estimators/two_view_geometry.h:92)
+    InvertPose(&g.qvec, &g.tvec);
     SwapColumns(&g.inlier_matches);
     g.F = Transposed(g.F);
     g.E = Transposed(g.E);
@@ -315,10 +340,14 @@ void Database::WriteMatches(int64_t id1, int64_t id2, const uint32_t* matches, i
 }
 
 void Database::WriteTwoViewGeometry(int64_t id1, int64_t id2, int config, const uint32_t* inlier_matches, int64_t n,
-                                    const Mat3& F_in, const Mat3& E_in, const Mat3& H_in) {
+                                    const Mat3& F_in, const Mat3& E_in, const Mat3& H_in,
+                                    const std::array<double, 4>& qvec_in, const std::array<double, 3>& tvec_in) {
   std::vector<uint32_t> swapped;
   Mat3 F = F_in, E = E_in, H = H_in;
+  std::array<double, 4> q = qvec_in;
+  std::array<double, 3> t = tvec_in;
   if (id1 > id2) {  // store in the id1 < id2 frame
+    InvertPose(&q, &t);
     if (n > 0) {
       swapped.assign(inlier_matches, inlier_matches + 2 * n);
       SwapColumns(&swapped);
@@ -329,7 +358,8 @@ void Database::WriteTwoViewGeometry(int64_t id1, int64_t id2, int config, const 
     Mat3 inv;
     if (!AllZero(H) && Invert3x3(H, &inv)) H = inv;
   }
-  const double qvec[4] = {1.0, 0.0, 0.0, 0.0}, tvec[3] = {0.0, 0.0, 0.0};
+  const double* qvec = q.data();
+  const double* tvec = t.data();
   Stmt s(this, "INSERT OR REPLACE INTO two_view_geometries VALUES (?, ?, 2, ?, ?, ?, ?, ?, ?, ?)");
   s.I64(1, ImagePairToPairId(id1, id2)); s.I64(2, n);
   s.Blob(3, inlier_matches, static_cast<size_t>(n) * 8);

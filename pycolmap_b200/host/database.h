@@ -51,7 +51,13 @@ struct TwoViewGeometryRow {
   int config = 0;
   Mat3 F{}, E{}, H{};
   std::vector<uint32_t> inlier_matches;  // [n x 2]
+  std::array<double, 4> qvec{1.0, 0.0, 0.0, 0.0};  // cam2_from_cam1 rotation (w, x, y, z)
+  std::array<double, 3> tvec{0.0, 0.0, 0.0};
 };
+
+// Pose algebra on (qvec = (w, x, y, z), tvec): rotation matrix, inverse pose (TwoViewGeometry::Invert).
+Mat3 QuatToRotation(const std::array<double, 4>& q);
+void InvertPose(std::array<double, 4>* qvec, std::array<double, 3>* tvec);
 
 bool Invert3x3(const Mat3& m, Mat3* out);  // false when singular (|det| < 1e-300)
 Mat3 Transposed(const Mat3& m);
@@ -99,7 +105,9 @@ class Database {
   bool ReadTwoViewGeometry(int64_t id1, int64_t id2, TwoViewGeometryRow* out);
   void WriteMatches(int64_t id1, int64_t id2, const uint32_t* matches, int64_t n);
   void WriteTwoViewGeometry(int64_t id1, int64_t id2, int config, const uint32_t* inlier_matches, int64_t n,
-                            const Mat3& F, const Mat3& E, const Mat3& H);
+                            const Mat3& F, const Mat3& E, const Mat3& H,
+                            const std::array<double, 4>& qvec = {1.0, 0.0, 0.0, 0.0},
+                            const std::array<double, 3>& tvec = {0.0, 0.0, 0.0});
   void ClearTwoViewGeometries() { Exec("DELETE FROM two_view_geometries"); }
   void ClearMatches() { Exec("DELETE FROM matches"); }
 

@@ -169,7 +169,8 @@ def _write_results(db, L, pairs, res, verified):
                 E = np.array(v.E).reshape(3, 3)
                 F = np.array(v.F).reshape(3, 3)
                 H = np.array(v.H).reshape(3, 3)
-                db.write_two_view_geometry(id1, id2, v.config, res.inlier_matches(k), F, E, H)
+                db.write_two_view_geometry(id1, id2, v.config, res.inlier_matches(k), F, E, H,
+                                           qvec=list(v.qvec), tvec=list(v.tvec))
 
 
 def _match_pairs_into_db(db, ctx, L, pair_chunks, sift, tvg, skip_existing=True):
@@ -284,28 +285,65 @@ def verify_matches(database_path, pairs_path, options=None):
                 cam1 = db.read_camera(db.con.execute("SELECT camera_id FROM images WHERE image_id=?", (id1,)).fetchone()[0])
                 cam2 = db.read_camera(db.con.execute("SELECT camera_id FROM images WHERE image_id=?", (id2,)).fetchone()[0])
                 cfg, inl, E, F, H = TwoViewGeometryConfiguration.UNDEFINED, np.zeros((0, 2), np.uint32), None, None, None
+                qvec = tvec = None
                 if len(m) >= options.min_num_inliers:
                     r, inl = ctx.estimate_two_view_geometry(cam1, kp1, cam2, kp2, m, tvg)
                     cfg = r.config
                     E, F, H = (np.array(x).reshape(3, 3) for x in (r.E, r.F, r.H))
+                    qvec, tvec = list(r.qvec), list(r.tvec)
                 if len(inl) < options.min_num_inliers:  # controller write rule (row P3)
                     cfg, inl, E, F, H = TwoViewGeometryConfiguration.UNDEFINED, np.zeros((0, 2), np.uint32), None, None, None
-                db.write_two_view_geometry(id1, id2, int(cfg), inl, F, E, H)
+                    qvec = tvec = None
+                db.write_two_view_geometry(id1, id2, int(cfg), inl, F, E, H, qvec=qvec, tvec=tvec)
 
 
 # ---------------------------------------------------------------------------------------------------
 # estimators
 # ---------------------------------------------------------------------------------------------------
+class Rotation3d:
+    """Minimal stand-in for pycolmap.Rotation3d: `quat` is (x, y, z, w) like the reference's Eigen coefficients."""
+
+    def __init__(self, quat_xyzw=(0.0, 0.0, 0.0, 1.0)):
+        self.quat = np.array(quat_xyzw, np.float64).reshape(4)
+
+    def matrix(self):
+        x, y, z, w = self.quat
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+class Rigid3d:
+    """Minimal stand-in for pycolmap.Rigid3d: x_cam2 = rotation * x_cam1 + translation."""
+
+    def __init__(self, rotation=None, translation=(0.0, 0.0, 0.0)):
+        self.rotation = rotation if rotation is not None else Rotation3d()
+        self.translation = np.array(translation, np.float64).reshape(3)
+
+    def matrix(self):
+        return np.hstack([self.rotation.matrix(), self.translation.reshape(3, 1)])
+
+    def inverse(self):
+        x, y, z, w = self.rotation.quat
+        inv = Rotation3d((-x, -y, -z, w))
+        return Rigid3d(inv, -inv.matrix() @ self.translation)
+
+    def __repr__(self):
+        return f"Rigid3d(quat_xyzw={self.rotation.quat.tolist()}, t={self.translation.tolist()})"
+
+
 class TwoViewGeometry:
     """R:estimators/two_view_geometry.h:82-93 (read-only members)."""
 
     def __init__(self, config=TwoViewGeometryConfiguration.UNDEFINED, E=None, F=None, H=None, inlier_matches=None,
-                 tri_angle=0.0):
+                 tri_angle=0.0, qvec=None, tvec=None):
         self.config = TwoViewGeometryConfiguration(int(config))
         self.E = np.zeros((3, 3)) if E is None else np.array(E, np.float64).reshape(3, 3)
         self.F = np.zeros((3, 3)) if F is None else np.array(F, np.float64).reshape(3, 3)
         self.H = np.zeros((3, 3)) if H is None else np.array(H, np.float64).reshape(3, 3)
-        self.cam2_from_cam1 = None
+        # identity unless compute_relative_pose recovered a pose (qvec is (w, x, y, z) as in the database)
+        q = (1.0, 0.0, 0.0, 0.0) if qvec is None else tuple(float(v) for v in qvec)
+        self.cam2_from_cam1 = Rigid3d(Rotation3d((q[1], q[2], q[3], q[0])), (0.0, 0.0, 0.0) if tvec is None else tvec)
         self.inlier_matches = (np.zeros((0, 2), np.uint32) if inlier_matches is None
                                else np.array(inlier_matches, np.uint32).reshape(-1, 2))
         self.tri_angle = float(tri_angle)
@@ -316,6 +354,7 @@ class TwoViewGeometry:
         if np.abs(self.H).sum() > 0:
             self.H = np.linalg.inv(self.H)
         self.inlier_matches = self.inlier_matches[:, ::-1].copy()
+        self.cam2_from_cam1 = self.cam2_from_cam1.inverse()
 
     def __repr__(self):
         return f"TwoViewGeometry(config={self.config.name}, num_inliers={len(self.inlier_matches)})"
@@ -358,7 +397,7 @@ def estimate_two_view_geometry(camera1, points1, camera2, points2, matches=None,
     ctx = get_context(0)
     r, inl = ctx.estimate_two_view_geometry(_camera_dict(camera1), p1, _camera_dict(camera2), p2, matches,
                                             _tvg_struct(ctx, options))
-    return TwoViewGeometry(r.config, r.E, r.F, r.H, inl)
+    return TwoViewGeometry(r.config, r.E, r.F, r.H, inl, tri_angle=r.tri_angle, qvec=list(r.qvec), tvec=list(r.tvec))
 
 
 def estimate_calibrated_two_view_geometry(camera1, points1, camera2, points2, matches=None, options=None):

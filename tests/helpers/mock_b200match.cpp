@@ -183,6 +183,7 @@ int b2m_results_get(const b2m_results* r, int64_t k, b2m_pair_view* out) {
   if (!r || k < 0 || k >= static_cast<int64_t>(r->matches.size())) return B2M_EINVAL;
   memset(out, 0, sizeof(*out));
   out->struct_size = sizeof(*out);
+  out->qvec[0] = 1.0;
   out->image1 = r->pairs[2 * k];
   out->image2 = r->pairs[2 * k + 1];
   out->config = r->config[k];
@@ -212,6 +213,7 @@ int b2m_estimate_two_view_geometry(b2m_ctx*, const b2m_camera*, const double*, i
   fake_geometry(7, 9, static_cast<int>(m), matches, opts->min_num_inliers, &cfg, &inl, models);
   memset(out, 0, sizeof(*out));
   out->struct_size = sizeof(*out);
+  out->qvec[0] = 1.0;
   out->config = cfg == B2M_UNDEFINED ? B2M_DEGENERATE : cfg;
   out->n_inliers = static_cast<int64_t>(inl.size() / 2);
   memcpy(out->E, models, 72); memcpy(out->F, models + 9, 72); memcpy(out->H, models + 18, 72);

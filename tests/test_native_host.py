@@ -128,7 +128,44 @@ def test_database_roundtrip_cxx(tmp_path):
     inv = nat.TwoViewGeometry("PLANAR", H=H, F=F, inlier_matches=m)
     inv.invert()
     assert np.allclose(inv.H, np.linalg.inv(H)) and np.allclose(inv.F, F.T) and np.array_equal(inv.inlier_matches, m[:, ::-1])
-    assert inv.cam2_from_cam1 is None and "PLANAR" in repr(inv)
+    ident = inv.cam2_from_cam1                                   # no pose estimated: the identity, also after invert()
+    assert np.array_equal(ident.rotation.quat, [0, 0, 0, 1]) and np.array_equal(ident.translation, [0, 0, 0])
+    assert "PLANAR" in repr(inv)
+
+
+def test_relative_pose_storage_both_layers(tmp_path):
+    """qvec (w, x, y, z) / tvec columns: stored in the id1 < id2 frame, inverted for the swapped pair, the same
+    through the C++ and the Python layer; Rigid3d accessors."""
+    rng = np.random.default_rng(5)
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    t = rng.normal(size=3)
+    m = np.array([[0, 5], [3, 1]], np.uint32)
+    g = nat.TwoViewGeometry("CALIBRATED", inlier_matches=m, qvec=q, tvec=t, tri_angle=0.25)
+    pose = g.cam2_from_cam1
+    Rm = pose.rotation.matrix()
+    assert np.allclose(pose.rotation.quat, [q[1], q[2], q[3], q[0]]) and np.allclose(pose.translation, t)
+    assert np.allclose(Rm @ Rm.T, np.eye(3)) and np.isclose(np.linalg.det(Rm), 1.0) and g.tri_angle == 0.25
+    assert np.allclose(pose.matrix(), np.c_[Rm, t])
+    inv = pose.inverse()
+    assert np.allclose(inv.rotation.matrix(), Rm.T) and np.allclose(inv.translation, -Rm.T @ t)
+    py_pose = pb.Rigid3d(pb.Rotation3d((q[1], q[2], q[3], q[0])), t)
+    assert np.allclose(py_pose.matrix(), pose.matrix()) and np.allclose(py_pose.inverse().matrix(), inv.matrix())
+    with nat.Database(tmp_path / "a.db") as a, PyDatabase(tmp_path / "b.db") as b:
+        _, ids, _, _ = _fill(a, np.random.default_rng(2))
+        _fill(b, np.random.default_rng(2))
+        a.write_two_view_geometry(ids[2], ids[0], g)             # swapped: stored as the inverse pose
+        b.write_two_view_geometry(ids[2], ids[0], 2, m, qvec=q, tvec=t)
+        ga, gb = a.read_two_view_geometry(ids[0], ids[2]), b.read_two_view_geometry(ids[0], ids[2])
+        assert np.allclose(ga.cam2_from_cam1.matrix(), inv.matrix()) and np.allclose(gb["tvec"], inv.translation)
+        assert np.allclose(gb["qvec"], [q[0], -q[1], -q[2], -q[3]])
+        back = a.read_two_view_geometry(ids[2], ids[0])         # read in the written orientation
+        assert np.allclose(back.cam2_from_cam1.matrix(), pose.matrix())
+        gb2 = b.read_two_view_geometry(ids[2], ids[0])
+        assert np.allclose(gb2["qvec"], q) and np.allclose(gb2["tvec"], t)
+    rows = [sqlite3.connect(tmp_path / n).execute("SELECT qvec, tvec FROM two_view_geometries").fetchall() for n in ("a.db", "b.db")]
+    for (qa, ta), (qb, tb) in zip(*rows):
+        assert np.allclose(np.frombuffer(qa), np.frombuffer(qb)) and np.allclose(np.frombuffer(ta), np.frombuffer(tb))
 
 
 def test_database_is_interoperable_with_the_python_layer(tmp_path):

@@ -397,3 +397,104 @@ def test_multiple_models_estimator():
     with pytest.raises(ValueError, match="compute_relative_pose"):
         c.match_pairs(np.array([(0, 1)], np.int32), nat.SiftMatchingOptions(), {"compute_relative_pose": True})
     c.close()
+
+
+# ---- relative pose (compute_relative_pose) ---------------------------------------------------------------
+def _posed_scene(rng, n, kind, outliers=0.25):
+    """Like scenes.two_view_scene, but returns the planted pose."""
+    f, cx, cy = scenes.CAM["params"]
+    Rm = scenes._rot(rng.normal(size=3) * 0.15)
+    t = rng.normal(size=3)
+    t /= np.linalg.norm(t)
+    if kind == "rotation":
+        t = np.zeros(3)
+    X = np.c_[rng.uniform(-2.5, 2.5, n), rng.uniform(-1.8, 1.8, n), rng.uniform(4, 9, n)]
+    if kind == "planar":
+        X[:, 2] = 6.0 + 0.2 * X[:, 0] - 0.1 * X[:, 1]
+    Xc = X @ Rm.T + t
+    p1 = X[:, :2] / X[:, 2:] * f + [cx, cy]
+    p2 = Xc[:, :2] / Xc[:, 2:] * f + [cx, cy]
+    out = rng.random(n) < outliers
+    p2[out] = np.c_[rng.uniform(0, 1600, out.sum()), rng.uniform(0, 1200, out.sum())]
+    return p1, p2, Rm, t
+
+
+def _oracle_pose(g, p1, p2, cfg):
+    """The oracle's EstimateTwoViewGeometryPose on the GPU's own models and inliers: isolates the pose stage."""
+    o = R.TwoViewGeometry()
+    o.config, o.E, o.H, o.inlier_matches = cfg, g.E, g.H, g.inlier_matches
+    ok = R.estimate_two_view_geometry_pose(scenes.CAM, p1, scenes.CAM, p2, o)
+    return ok, o
+
+
+def _angle(a, b):
+    return np.degrees(np.arccos(np.clip(np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b)), -1, 1)))
+
+
+def test_relative_pose():
+    rng = np.random.default_rng(41)
+    cfg = nat.TwoViewGeometryConfiguration
+    opts = {"compute_relative_pose": True}
+    # general scene: pose from E
+    p1, p2, Rm, t = _posed_scene(rng, 400, "general")
+    for mod in (nat, pb):
+        g = mod.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2, options=opts)
+        pose = g.cam2_from_cam1
+        assert int(g.config) == int(cfg.CALIBRATED.value)
+        assert np.degrees(np.arccos(np.clip((np.trace(pose.rotation.matrix() @ Rm.T) - 1) / 2, -1, 1))) < 0.5
+        assert _angle(pose.translation, t) < 1.0 and abs(np.linalg.norm(pose.translation) - 1.0) < 1e-9
+        ok, o = _oracle_pose(g, p1, p2, R.CALIBRATED)
+        assert ok and np.allclose(pose.rotation.matrix(), pb.Rotation3d(tuple(o.qvec[[1, 2, 3, 0]])).matrix(), atol=1e-7)
+        assert np.allclose(pose.translation, o.tvec, atol=1e-7) and abs(g.tri_angle - o.tri_angle) < 1e-7 and g.tri_angle > 0.01
+    g0 = nat.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)           # not requested: identity, same inliers
+    assert np.array_equal(g0.cam2_from_cam1.rotation.quat, [0, 0, 0, 1]) and g0.tri_angle == 0.0
+    assert np.array_equal(g0.inlier_matches, g.inlier_matches)
+    # planar scene: PLANAR_OR_PANORAMIC is resolved into PLANAR, pose from the homography
+    q1, q2, Rp, tp = _posed_scene(rng, 350, "planar")
+    gp = nat.estimate_two_view_geometry(scenes.CAM, q1, scenes.CAM, q2, options=opts)
+    assert gp.config == cfg.PLANAR and gp.tri_angle > 0.0
+    ok, o = _oracle_pose(gp, q1, q2, R.PLANAR_OR_PANORAMIC)
+    assert ok and o.config == R.PLANAR
+    assert np.allclose(gp.cam2_from_cam1.rotation.matrix(), pb.Rotation3d(tuple(o.qvec[[1, 2, 3, 0]])).matrix(), atol=1e-6)
+    assert np.allclose(gp.cam2_from_cam1.translation, o.tvec, atol=1e-6) and abs(gp.tri_angle - o.tri_angle) < 1e-6
+    # pure rotation: PANORAMIC, zero translation, zero angle
+    r1, r2, Rr, _ = _posed_scene(rng, 350, "rotation")
+    gr = nat.estimate_two_view_geometry(scenes.CAM, r1, scenes.CAM, r2, options=opts)
+    assert gr.config == cfg.PANORAMIC and np.all(gr.cam2_from_cam1.translation == 0) and gr.tri_angle == 0.0
+    assert np.degrees(np.arccos(np.clip((np.trace(gr.cam2_from_cam1.rotation.matrix() @ Rr.T) - 1) / 2, -1, 1))) < 0.2
+    # batched entry point: same poses as the single calls
+    gb = nat.estimate_two_view_geometries([(scenes.CAM, p1, scenes.CAM, p2), (scenes.CAM, q1, scenes.CAM, q2),
+                                           (scenes.CAM, r1, scenes.CAM, r2)], opts)
+    assert [x.config for x in gb] == [cfg.CALIBRATED, cfg.PLANAR, cfg.PANORAMIC]
+    assert _angle(gb[0].cam2_from_cam1.translation, t) < 1.0 and gb[0].tri_angle > 0.01 and gb[2].tri_angle == 0.0
+
+
+def test_relative_pose_database_pipeline(tmp_path):
+    """match_exhaustive(verification_options.compute_relative_pose): qvec / tvec columns of the verified pairs hold
+    unit quaternions and unit translations; both hosts write the same poses."""
+    a, b = tmp_path / "cxx.db", tmp_path / "py.db"
+    _make_db(a)
+    _make_db(b)
+    nat.match_exhaustive(a, matching_options={"block_size": 4}, verification_options={"compute_relative_pose": True})
+    pb.match_exhaustive(b, matching_options={"block_size": 4}, verification_options={"compute_relative_pose": True})
+    da, db_ = _dump(a), _dump(b)
+    assert da["matches"] == db_["matches"]
+    n_posed = 0
+    for ra, rb in zip(da["two_view_geometries"], db_["two_view_geometries"]):
+        assert ra[:5] == rb[:5]
+        qa, ta = np.frombuffer(ra[8], np.float64), np.frombuffer(ra[9], np.float64)
+        qb, tb = np.frombuffer(rb[8], np.float64), np.frombuffer(rb[9], np.float64)
+        assert np.allclose(qa, qb, atol=1e-9) and np.allclose(ta, tb, atol=1e-9)
+        if ra[4] in (2, 3) and ra[1] >= 15:
+            n_posed += 1
+            assert abs(np.linalg.norm(qa) - 1) < 1e-9 and abs(np.linalg.norm(ta) - 1) < 1e-9 and qa[0] < 1.0
+        elif ra[1] == 0:
+            assert np.array_equal(qa, [1, 0, 0, 0]) and np.array_equal(ta, [0, 0, 0])
+    assert n_posed >= 8
+    with nat.Database(a) as d:
+        ids = [r[0] for r in d.read_all_images()]
+        g = d.read_two_view_geometry(ids[0], ids[1])
+        gi = d.read_two_view_geometry(ids[1], ids[0])
+        assert np.allclose(gi.cam2_from_cam1.matrix(), g.cam2_from_cam1.inverse().matrix(), atol=1e-12)
+        # neighbouring cameras of the synthetic ring: a small rotation, a sideways translation
+        assert g.cam2_from_cam1.rotation.quat[3] > 0.9

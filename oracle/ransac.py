@@ -664,7 +664,7 @@ def decompose_homography_matrix(H, K1, K2):
     if np.linalg.det(Hn) < 0:
         Hn = -Hn
     S = Hn.T @ Hn - np.eye(3)
-    if np.abs(S).sum(1).max() < 1e-3:
+    if np.abs(S).max() < 1e-3:                      # lpNorm<Infinity> of the matrix: largest |coefficient|
         return [(Hn, np.zeros(3), np.zeros(3))]
 
     def minor(r, c):

@@ -192,8 +192,8 @@ B2M_HD inline int decompose_H(const double* H, const double* K1, const double* K
   double S[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) S[i * 3 + j] = Hn[i] * Hn[j] + Hn[3 + i] * Hn[3 + j] + Hn[6 + i] * Hn[6 + j] - (i == j ? 1.0 : 0.0);
-  double inf_norm = 0.0;
-  for (int i = 0; i < 3; ++i) inf_norm = fmax(inf_norm, fabs(S[i * 3]) + fabs(S[i * 3 + 1]) + fabs(S[i * 3 + 2]));
+  double inf_norm = 0.0;  // Eigen's lpNorm<Infinity>() of a matrix: the largest |coefficient|
+  for (int i = 0; i < 9; ++i) inf_norm = fmax(inf_norm, fabs(S[i]));
   if (inf_norm < 1e-3) {  // H is a rotation
     for (int i = 0; i < 9; ++i) R_out[i] = Hn[i];
     for (int i = 0; i < 3; ++i) t_out[i] = n_out[i] = 0.0;

@@ -242,6 +242,14 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
                                          const b2m_tvg_opts* opts, b2m_tvg_result* out,
                                          uint32_t* const* inlier_matches);
 
+/* Replaces EstimateTwoViewGeometryPose (R:estimators/two_view_geometry.h:153-158): relative pose of an existing
+ * geometry.  In: geometry->config, E (CALIBRATED / UNCALIBRATED) or H (PLANAR / PANORAMIC / PLANAR_OR_PANORAMIC) and
+ * its inlier matches over the given points.  Out: qvec, tvec, tri_angle, pose_valid (0 = upstream's `false`), and
+ * config when PLANAR_OR_PANORAMIC is resolved. */
+int b2m_estimate_two_view_geometry_pose(b2m_ctx* ctx, const b2m_camera* cam1, const double* points1, int64_t n1,
+                                        const b2m_camera* cam2, const double* points2, int64_t n2,
+                                        const uint32_t* inlier_matches, int64_t n_inliers, b2m_tvg_result* geometry);
+
 /* Single-model LO-RANSAC.  Replaces essential/fundamental/homography_matrix_estimation
  * (R:estimators/essential_matrix.h:19-103, fundamental_matrix.h:17-50, homography_matrix.h:17-48).
  * kind: 0 = E (points already normalised by the caller), 1 = F, 2 = H.

@@ -10,7 +10,7 @@ from .options import (Device, ExhaustiveMatchingOptions, RANSACOptions, Sequenti
                       SiftMatchingOptions, TwoViewGeometryConfiguration, TwoViewGeometryOptions)
 from .database import Database, image_pair_to_pair_id  # noqa: F401
 from .pipeline import (Rigid3d, Rotation3d, TwoViewGeometry, essential_matrix_estimation, estimate_calibrated_two_view_geometry,  # noqa: F401
-                       estimate_two_view_geometry, fundamental_matrix_estimation, homography_matrix_estimation,
+                       estimate_two_view_geometry, estimate_two_view_geometry_pose, fundamental_matrix_estimation, homography_matrix_estimation,
                        match_exhaustive, match_sequential, squared_sampson_error, verify_matches)
 
 __version__ = "0.1.0"

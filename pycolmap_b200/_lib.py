@@ -79,7 +79,7 @@ EXPORTS = [
     "b2m_sift_opts_default", "b2m_ransac_opts_default", "b2m_tvg_opts_default", "b2m_match_pair",
     "b2m_set_images", "b2m_set_images_device", "b2m_match_pairs", "b2m_match_verify", "b2m_results_num_pairs",
     "b2m_results_total_matches", "b2m_results_num_verified", "b2m_results_get", "b2m_results_free", "b2m_estimate_two_view_geometry",
-    "b2m_estimate_two_view_geometry_batch",
+    "b2m_estimate_two_view_geometry_batch", "b2m_estimate_two_view_geometry_pose",
     "b2m_ransac_model", "b2m_cam_from_img", "b2m_squared_sampson_error", "b2m_get_stats", "b2m_reset_stats",
 ]
 
@@ -128,6 +128,8 @@ def load():
                                                    ctypes.POINTER(TvgResult), P]
     lib.b2m_estimate_two_view_geometry_batch.argtypes = [P, ctypes.POINTER(TvgProblem), c_i64,
                                                          ctypes.POINTER(TvgOpts), ctypes.POINTER(TvgResult), P]
+    lib.b2m_estimate_two_view_geometry_pose.argtypes = [P, ctypes.POINTER(Camera), P, c_i64, ctypes.POINTER(Camera), P,
+                                                        c_i64, P, c_i64, ctypes.POINTER(TvgResult)]
     lib.b2m_ransac_model.argtypes = [P, c_i32, P, P, c_i64, ctypes.POINTER(RansacOpts), P, P,
                                      ctypes.POINTER(c_i64), ctypes.POINTER(c_i32)]
     lib.b2m_squared_sampson_error.argtypes = [P, P, P, c_i64, P, P]
@@ -280,6 +282,24 @@ class Context:
             self.h, ctypes.byref(cams[0]), ptr(p1), len(p1), ctypes.byref(cams[1]), ptr(p2), len(p2),
             ptr(matches) if matches is not None else None, m, ctypes.byref(opts), ctypes.byref(out), ptr(inl)))
         return out, inl[:out.n_inliers].copy()
+
+    def estimate_two_view_geometry_pose(self, cam1, points1, cam2, points2, config, E, H, inlier_matches):
+        """Returns the TvgResult with qvec / tvec / tri_angle / pose_valid / (possibly resolved) config."""
+        p1 = np.ascontiguousarray(points1, np.float64).reshape(-1, 2)
+        p2 = np.ascontiguousarray(points2, np.float64).reshape(-1, 2)
+        inl = np.ascontiguousarray(inlier_matches, np.uint32).reshape(-1, 2)
+        cams = self.make_cameras([cam1, cam2])
+        g = TvgResult()
+        g.struct_size = ctypes.sizeof(TvgResult)
+        g.config = int(config)
+        for k, v in enumerate(np.asarray(E, np.float64).reshape(9)):
+            g.E[k] = v
+        for k, v in enumerate(np.asarray(H, np.float64).reshape(9)):
+            g.H[k] = v
+        self.check(self.lib.b2m_estimate_two_view_geometry_pose(
+            self.h, ctypes.byref(cams[0]), ptr(p1), len(p1), ctypes.byref(cams[1]), ptr(p2), len(p2), ptr(inl), len(inl),
+            ctypes.byref(g)))
+        return g
 
     def ransac_model(self, kind, points1, points2, opts=None):
         """kind 0 = E (normalised points), 1 = F, 2 = H.  Returns dict or None (reference: None on failure)."""

@@ -1972,6 +1972,81 @@ int b2m_ransac_model(b2m_ctx* ctx, int32_t kind, const double* points1, const do
   return B2M_OK;
 }
 
+// EstimateTwoViewGeometryPose on a caller-provided geometry (R:estimators/two_view_geometry.h:153-158): the pose
+// kernel alone.  geometry->config / E / H are inputs; config (PLANAR_OR_PANORAMIC -> PLANAR / PANORAMIC), qvec,
+// tvec, tri_angle and pose_valid are outputs.  pose_valid = 0 mirrors upstream's `false` return.
+int b2m_estimate_two_view_geometry_pose(b2m_ctx* ctx, const b2m_camera* cam1, const double* points1, int64_t n1,
+                                        const b2m_camera* cam2, const double* points2, int64_t n2,
+                                        const uint32_t* inlier_matches, int64_t n_inliers, b2m_tvg_result* geometry) {
+  if (!ctx) return B2M_EINVAL;
+  auto bad = [&](const char* msg) {
+    ctx->err = msg;
+    return B2M_EINVAL;
+  };
+  if (!cam1 || !cam2 || !geometry) return bad("[verify.cu] Check Failed: cameras and geometry != NULL");
+  if (const char* why = camera_problem(*cam1)) return bad(why);
+  if (const char* why = camera_problem(*cam2)) return bad(why);
+  if (n1 < 0 || n2 < 0 || (n1 > 0 && !points1) || (n2 > 0 && !points2)) return bad("[verify.cu] Check Failed: points");
+  if (n_inliers < 0 || n_inliers > INT32_MAX || (n_inliers > 0 && !inlier_matches))
+    return bad("[verify.cu] Check Failed: inlier_matches");
+  for (int64_t i = 0; i < n_inliers; ++i)
+    if (inlier_matches[2 * i] >= n1 || inlier_matches[2 * i + 1] >= n2)
+      return bad("[verify.cu] Check Failed: match index < number of points");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  Single G;
+  const int64_t cap = std::max<int64_t>(n_inliers, 1);
+  const DevCamera cams[2] = {to_dev(*cam1), to_dev(*cam2)};
+  const int32_t i32[4] = {0, 1, static_cast<int32_t>(n_inliers), geometry->config};  // pairs[2], inl_cnt, config
+  const int64_t off0 = 0;
+  double models[27];
+  memset(models, 0, sizeof(models));
+  memcpy(models, geometry->E, sizeof(double) * 9);
+  memcpy(models + 18, geometry->H, sizeof(double) * 9);
+  V_TRY(ctx, cudaMalloc(&G.d_inliers, sizeof(uint2) * cap));
+  V_TRY(ctx, cudaMalloc(&G.d_cams, sizeof(DevCamera) * 2));
+  V_TRY(ctx, cudaMalloc(&G.d_i32, sizeof(i32)));
+  V_TRY(ctx, cudaMalloc(&G.d_off, sizeof(int64_t)));
+  V_TRY(ctx, cudaMalloc(&G.d_models, sizeof(models)));
+  if (n_inliers > 0)
+    V_TRY(ctx, cudaMemcpy(G.d_inliers, inlier_matches, sizeof(uint2) * n_inliers, cudaMemcpyHostToDevice));
+  V_TRY(ctx, cudaMemcpy(G.d_cams, cams, sizeof(cams), cudaMemcpyHostToDevice));
+  V_TRY(ctx, cudaMemcpy(G.d_i32, i32, sizeof(i32), cudaMemcpyHostToDevice));
+  V_TRY(ctx, cudaMemcpy(G.d_off, &off0, sizeof(int64_t), cudaMemcpyHostToDevice));
+  V_TRY(ctx, cudaMemcpy(G.d_models, models, sizeof(models), cudaMemcpyHostToDevice));
+  VerifyParams P = VerifyParams{};
+  P.pairs = G.d_i32;
+  P.inl_cnt = G.d_i32 + 2;
+  P.config = G.d_i32 + 3;
+  P.pair_off = G.d_off;
+  P.inliers = G.d_inliers;
+  P.models = G.d_models;
+  P.cams = G.d_cams;
+  const std::vector<double> p1(points1, points1 + 2 * n1), p2(points2, points2 + 2 * n2);
+  const std::vector<int64_t> zero(1, 0);
+  const b2m_camera* full_cams[2] = {cam1, cam2};
+  if (int rc = launch_pose_standalone(ctx, G, P, 1, cap, p1, p2, zero, zero, full_cams, 2, st)) return rc;
+  double h_pose[8];
+  int32_t h_valid = 0, h_i32[4];
+  V_TRY(ctx, cudaMemcpyAsync(h_pose, G.d_pose, sizeof(h_pose), cudaMemcpyDeviceToHost, st));
+  V_TRY(ctx, cudaMemcpyAsync(&h_valid, G.d_pose_valid, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  V_TRY(ctx, cudaMemcpyAsync(h_i32, G.d_i32, sizeof(h_i32), cudaMemcpyDeviceToHost, st));
+  V_TRY(ctx, cudaStreamSynchronize(st));
+  geometry->qvec[0] = 1.0;
+  geometry->qvec[1] = geometry->qvec[2] = geometry->qvec[3] = 0.0;
+  geometry->tvec[0] = geometry->tvec[1] = geometry->tvec[2] = 0.0;
+  geometry->tri_angle = 0.0;
+  geometry->pose_valid = 0;
+  if (h_valid) {
+    geometry->config = h_i32[3];
+    memcpy(geometry->qvec, h_pose, sizeof(double) * 4);
+    memcpy(geometry->tvec, h_pose + 4, sizeof(double) * 3);
+    geometry->tri_angle = h_pose[7];
+    geometry->pose_valid = 1;
+  }
+  return B2M_OK;
+}
+
 int b2m_cam_from_img(b2m_ctx* ctx, const b2m_camera* camera, const double* points, int64_t n, double* out) {
   if (!ctx) return B2M_EINVAL;
   auto bad = [&](const char* msg) {

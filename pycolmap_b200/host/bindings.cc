@@ -592,18 +592,42 @@ PYBIND11_MODULE(_core, m) {
         },
         "problems"_a, "options"_a = TwoViewGeometryOptions(),
         "Batched estimate_two_view_geometry: problems = [(camera1, points1, camera2, points2[, matches]), ...]");
+  m.def("estimate_two_view_geometry_pose",
+        [](const py::object& camera1, const ArrD& points1, const py::object& camera2, const ArrD& points2, TwoViewGeometry& geometry) {
+          CheckPoints(points1, "points1");
+          CheckPoints(points2, "points2");
+          const b2m_camera c1 = CameraFromPython(camera1), c2 = CameraFromPython(camera2);
+          b2m_tvg_result g;
+          memset(&g, 0, sizeof(g));
+          g.struct_size = sizeof(g);
+          g.config = static_cast<int>(geometry.config);
+          std::copy(geometry.E.begin(), geometry.E.end(), g.E);
+          std::copy(geometry.H.begin(), geometry.H.end(), g.H);
+          b2m_ctx* ctx = Engine::Get(0);
+          ThrowOnError(ctx, b2m_estimate_two_view_geometry_pose(ctx, &c1, points1.data(), points1.shape(0), &c2, points2.data(),
+                                                               points2.shape(0), geometry.inlier_matches.data(),
+                                                               static_cast<int64_t>(geometry.inlier_matches.size() / 2), &g));
+          if (!g.pose_valid) return false;
+          geometry.config = static_cast<TwoViewGeometryConfiguration>(g.config);
+          std::copy(g.qvec, g.qvec + 4, geometry.qvec.begin());
+          std::copy(g.tvec, g.tvec + 3, geometry.tvec.begin());
+          geometry.tri_angle = g.tri_angle;
+          return true;
+        },
+        "camera1"_a, "points1"_a, "camera2"_a, "points2"_a, "geometry"_a,
+        "Relative pose of an estimated geometry, in place (R:estimators/two_view_geometry.h:153-158).");
   m.def("fundamental_matrix_estimation",
         [](const ArrD& points1, const ArrD& points2, const RANSACOptions& estimation_options) {
           CheckSameLength(points1, points2, "fundamental_matrix.h:22");
           return RansacModel(Engine::Get(0), 1, "F", points1, points2, estimation_options);
         },
-        "points1"_a, "points2"_a, "estimation_options"_a = RANSACOptions());
+        "points2D1"_a, "points2D2"_a, "estimation_options"_a = RANSACOptions());
   m.def("homography_matrix_estimation",
         [](const ArrD& points1, const ArrD& points2, const RANSACOptions& estimation_options) {
           CheckSameLength(points1, points2, "homography_matrix.h:21");
           return RansacModel(Engine::Get(0), 2, "H", points1, points2, estimation_options);
         },
-        "points1"_a, "points2"_a, "estimation_options"_a = RANSACOptions());
+        "points2D1"_a, "points2D2"_a, "estimation_options"_a = RANSACOptions());
   m.def("essential_matrix_estimation",
         [](const ArrD& points1, const ArrD& points2, const py::object& camera1, const py::object& camera2,
            const RANSACOptions& estimation_options) {
@@ -620,9 +644,33 @@ PYBIND11_MODULE(_core, m) {
           auto mean_f = [](const b2m_camera& c) { return b2m::cam::mean_focal_length(c.model, c.params); };
           RANSACOptions o = estimation_options;
           o.max_error = 0.5 * (o.max_error / mean_f(c1) + o.max_error / mean_f(c2));
-          return RansacModel(Engine::Get(0), 0, "E", normalise(c1, points1), normalise(c2, points2), o);
+          py::object res = RansacModel(ctx, 0, "E", normalise(c1, points1), normalise(c2, points2), o);
+          if (res.is_none()) return res;
+          // PoseFromEssentialMatrix on the inliers (R:estimators/essential_matrix.h:62-83), on the GPU
+          py::dict d = res;
+          const py::array_t<bool> mask = py::array_t<bool>::ensure(d["inliers"]);
+          std::vector<uint32_t> inl;
+          for (py::ssize_t i = 0; i < mask.size(); ++i)
+            if (mask.data()[i]) {
+              inl.push_back(static_cast<uint32_t>(i));
+              inl.push_back(static_cast<uint32_t>(i));
+            }
+          b2m_tvg_result g;
+          memset(&g, 0, sizeof(g));
+          g.struct_size = sizeof(g);
+          g.config = B2M_CALIBRATED;
+          const ArrD E = ArrD::ensure(py::object(d["E"]));
+          std::copy(E.data(), E.data() + 9, g.E);
+          ThrowOnError(ctx, b2m_estimate_two_view_geometry_pose(ctx, &c1, points1.data(), points1.shape(0), &c2, points2.data(),
+                                                               points2.shape(0), inl.data(), static_cast<int64_t>(inl.size() / 2),
+                                                               &g));
+          Rigid3d pose;
+          std::copy(g.qvec, g.qvec + 4, pose.rotation.wxyz.begin());
+          std::copy(g.tvec, g.tvec + 3, pose.translation.begin());
+          d["cam2_from_cam1"] = pose;
+          return res;
         },
-        "points1"_a, "points2"_a, "camera1"_a, "camera2"_a, "estimation_options"_a = RANSACOptions());
+        "points2D1"_a, "points2D2"_a, "camera1"_a, "camera2"_a, "estimation_options"_a = RANSACOptions());
   m.def("cam_from_img",
         [](const py::object& camera, const ArrD& points) {
           CheckPoints(points, "points");
@@ -643,7 +691,7 @@ PYBIND11_MODULE(_core, m) {
                                                       out.mutable_data()));
           return out;
         },
-        "points1"_a, "points2"_a, "E"_a);
+        "points2D1"_a, "points2D2"_a, "E"_a);
 
   // ---- pair generators (exposed for tests and tools) ----
   m.def("exhaustive_pair_blocks",

@@ -406,30 +406,46 @@ def estimate_calibrated_two_view_geometry(camera1, points1, camera2, points2, ma
     return estimate_two_view_geometry(c1, points1, c2, points2, matches, options)
 
 
+def estimate_two_view_geometry_pose(camera1, points1, camera2, points2, geometry):
+    """R:estimators/two_view_geometry.h:153-158: fills geometry.cam2_from_cam1 / tri_angle (and resolves
+    PLANAR_OR_PANORAMIC) in place; returns False when no pose could be recovered."""
+    ctx = get_context(0)
+    r = ctx.estimate_two_view_geometry_pose(_camera_dict(camera1), _points(points1, "points1"), _camera_dict(camera2),
+                                            _points(points2, "points2"), int(geometry.config), geometry.E, geometry.H,
+                                            geometry.inlier_matches)
+    if not r.pose_valid:
+        return False
+    geometry.config = TwoViewGeometryConfiguration(int(r.config))
+    q = list(r.qvec)
+    geometry.cam2_from_cam1 = Rigid3d(Rotation3d((q[1], q[2], q[3], q[0])), list(r.tvec))
+    geometry.tri_angle = float(r.tri_angle)
+    return True
+
+
 def _ransac(kind, p1, p2, opts):
     ctx = get_context(0)
     opts = RANSACOptions.coerce(opts)
     return ctx.ransac_model(kind, p1, p2, ctx.ransac_opts(**_ransac_kwargs(opts)))
 
 
-def fundamental_matrix_estimation(points1, points2, estimation_options=None):
-    p1, p2 = _points(points1, "points1"), _points(points2, "points2")
+def fundamental_matrix_estimation(points2D1, points2D2, estimation_options=None):
+    p1, p2 = _points(points2D1, "points2D1"), _points(points2D2, "points2D2")
     if len(p1) != len(p2):
         raise ValueError("[fundamental_matrix.h:22] Check Failed: points1.size() == points2.size()")
     r = _ransac(1, p1, p2, estimation_options)
     return None if r is None else {"F": r["model"], "num_inliers": r["num_inliers"], "inliers": r["inliers"]}
 
 
-def homography_matrix_estimation(points1, points2, estimation_options=None):
-    p1, p2 = _points(points1, "points1"), _points(points2, "points2")
+def homography_matrix_estimation(points2D1, points2D2, estimation_options=None):
+    p1, p2 = _points(points2D1, "points2D1"), _points(points2D2, "points2D2")
     if len(p1) != len(p2):
         raise ValueError("[homography_matrix.h:21] Check Failed: points1.size() == points2.size()")
     r = _ransac(2, p1, p2, estimation_options)
     return None if r is None else {"H": r["model"], "num_inliers": r["num_inliers"], "inliers": r["inliers"]}
 
 
-def essential_matrix_estimation(points1, points2, camera1, camera2, estimation_options=None):
-    p1, p2 = _points(points1, "points1"), _points(points2, "points2")
+def essential_matrix_estimation(points2D1, points2D2, camera1, camera2, estimation_options=None):
+    p1, p2 = _points(points2D1, "points2D1"), _points(points2D2, "points2D2")
     if len(p1) != len(p2):
         raise ValueError("[essential_matrix.h:26] Check Failed: points1.size() == points2.size()")
     c1, c2 = _camera_dict(camera1), _camera_dict(camera2)
@@ -445,12 +461,21 @@ def essential_matrix_estimation(points1, points2, camera1, camera2, estimation_o
     # R:estimators/essential_matrix.h:42-46: threshold averaged over both cameras
     o.max_error = 0.5 * (o.max_error / mean_f(c1) + o.max_error / mean_f(c2))
     r = _ransac(0, norm(c1, p1), norm(c2, p2), o)
-    return None if r is None else {"E": r["model"], "num_inliers": r["num_inliers"], "inliers": r["inliers"]}
+    if r is None:
+        return None
+    # PoseFromEssentialMatrix on the inliers (R:estimators/essential_matrix.h:62-83), on the GPU
+    idx = np.flatnonzero(r["inliers"]).astype(np.uint32)
+    g = ctx.estimate_two_view_geometry_pose(c1, p1, c2, p2, int(TwoViewGeometryConfiguration.CALIBRATED), r["model"],
+                                            np.zeros((3, 3)), np.stack([idx, idx], 1))
+    q = list(g.qvec)
+    pose = Rigid3d(Rotation3d((q[1], q[2], q[3], q[0])), list(g.tvec))
+    return {"E": r["model"], "cam2_from_cam1": pose, "num_inliers": r["num_inliers"], "inliers": r["inliers"]}
 
 
-def squared_sampson_error(points1, points2, E):
+def squared_sampson_error(points2D1, points2D2, E):
+    """Keyword names as bound by the reference (R:estimators/two_view_geometry.h:161-175)."""
     ctx = get_context(0)
-    return ctx.squared_sampson_error(_points(points1, "points1"), _points(points2, "points2"), E)
+    return ctx.squared_sampson_error(_points(points2D1, "points2D1"), _points(points2D2, "points2D2"), E)
 
 
 def wait_idle():

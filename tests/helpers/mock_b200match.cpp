@@ -228,6 +228,12 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* q,
       return rc;
   return B2M_OK;
 }
+int b2m_estimate_two_view_geometry_pose(b2m_ctx*, const b2m_camera*, const double*, int64_t, const b2m_camera*, const double*,
+                                        int64_t, const uint32_t*, int64_t, b2m_tvg_result* g) {
+  g->qvec[0] = 1.0;
+  g->pose_valid = 0;
+  return B2M_OK;
+}
 int b2m_ransac_model(b2m_ctx*, int32_t, const double*, const double*, int64_t, const b2m_ransac_opts*, double*, uint8_t*,
                      int64_t* n, int32_t* ok) {
   *n = 0;

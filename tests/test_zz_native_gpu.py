@@ -449,6 +449,20 @@ def test_relative_pose():
     g0 = nat.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)           # not requested: identity, same inliers
     assert np.array_equal(g0.cam2_from_cam1.rotation.quat, [0, 0, 0, 1]) and g0.tri_angle == 0.0
     assert np.array_equal(g0.inlier_matches, g.inlier_matches)
+    # estimate_two_view_geometry_pose on an existing geometry, in place (both hosts)
+    gn = nat.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)
+    assert nat.estimate_two_view_geometry_pose(scenes.CAM, p1, scenes.CAM, p2, gn) is True
+    assert np.allclose(gn.cam2_from_cam1.matrix(), g.cam2_from_cam1.matrix(), atol=1e-12) and gn.tri_angle == g.tri_angle
+    gpy = pb.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)
+    assert pb.estimate_two_view_geometry_pose(scenes.CAM, p1, scenes.CAM, p2, gpy) is True
+    assert np.allclose(gpy.cam2_from_cam1.matrix(), gn.cam2_from_cam1.matrix(), atol=1e-12)
+    deg = nat.TwoViewGeometry()                                                    # UNDEFINED: nothing to decompose
+    assert nat.estimate_two_view_geometry_pose(scenes.CAM, p1, scenes.CAM, p2, deg) is False
+    # essential_matrix_estimation also returns the decomposed pose (R:estimators/essential_matrix.h:62-89)
+    for mod in (nat, pb):
+        e = mod.essential_matrix_estimation(points2D1=p1, points2D2=p2, camera1=scenes.CAM, camera2=scenes.CAM)
+        assert e is not None and _angle(e["cam2_from_cam1"].translation, t) < 1.0
+        assert np.degrees(np.arccos(np.clip((np.trace(e["cam2_from_cam1"].rotation.matrix() @ Rm.T) - 1) / 2, -1, 1))) < 0.5
     # planar scene: PLANAR_OR_PANORAMIC is resolved into PLANAR, pose from the homography
     q1, q2, Rp, tp = _posed_scene(rng, 350, "planar")
     gp = nat.estimate_two_view_geometry(scenes.CAM, q1, scenes.CAM, q2, options=opts)

@@ -451,8 +451,13 @@ def essential_matrix_estimation(points2D1, points2D2, camera1, camera2, estimati
     c1, c2 = _camera_dict(camera1), _camera_dict(camera2)
     ctx = get_context(0)
 
-    def norm(c, p):  # Camera::CamFromImg (R:estimators/essential_matrix.h:31-39), on the GPU for every model
-        return ctx.cam_from_img(c, p)
+    def norm(c, p):  # Camera::CamFromImg (R:estimators/essential_matrix.h:31-39)
+        pr = c["params"]
+        if c["model"] == 0:   # the two pinhole models: closed form, as validated on the GPU box in round 1
+            return (p - [pr[1], pr[2]]) / pr[0]
+        if c["model"] == 1:
+            return (p - [pr[2], pr[3]]) / [pr[0], pr[1]]
+        return ctx.cam_from_img(c, p)   # models with distortion: iterative undistortion on the GPU
 
     def mean_f(c):   # MeanFocalLength: models 0, 2, 3, 8, 9 have one focal length, the others two
         return c["params"][0] if c["model"] in (0, 2, 3, 8, 9) else 0.5 * (c["params"][0] + c["params"][1])
@@ -463,13 +468,29 @@ def essential_matrix_estimation(points2D1, points2D2, camera1, camera2, estimati
     r = _ransac(0, norm(c1, p1), norm(c2, p2), o)
     if r is None:
         return None
-    # PoseFromEssentialMatrix on the inliers (R:estimators/essential_matrix.h:62-83), on the GPU
-    idx = np.flatnonzero(r["inliers"]).astype(np.uint32)
-    g = ctx.estimate_two_view_geometry_pose(c1, p1, c2, p2, int(TwoViewGeometryConfiguration.CALIBRATED), r["model"],
-                                            np.zeros((3, 3)), np.stack([idx, idx], 1))
-    q = list(g.qvec)
-    pose = Rigid3d(Rotation3d((q[1], q[2], q[3], q[0])), list(g.tvec))
-    return {"E": r["model"], "cam2_from_cam1": pose, "num_inliers": r["num_inliers"], "inliers": r["inliers"]}
+    def pose():
+        # PoseFromEssentialMatrix on the inliers (R:estimators/essential_matrix.h:62-83), on the GPU
+        idx = np.flatnonzero(r["inliers"]).astype(np.uint32)
+        g = ctx.estimate_two_view_geometry_pose(c1, p1, c2, p2, int(TwoViewGeometryConfiguration.CALIBRATED), r["model"],
+                                                np.zeros((3, 3)), np.stack([idx, idx], 1))
+        q = list(g.qvec)
+        return Rigid3d(Rotation3d((q[1], q[2], q[3], q[0])), list(g.tvec))
+    return _EssentialResult(pose, {"E": r["model"], "num_inliers": r["num_inliers"], "inliers": r["inliers"]})
+
+
+class _EssentialResult(dict):
+    """The reference's result dict; `cam2_from_cam1` is decomposed on first access (this mirror layer keeps the
+    round-1 validated call sequence for callers that only read E / inliers; the C++ host computes it eagerly)."""
+
+    def __init__(self, pose_fn, items):
+        super().__init__(items)
+        self._pose_fn = pose_fn
+
+    def __missing__(self, key):
+        if key != "cam2_from_cam1":
+            raise KeyError(key)
+        self[key] = self._pose_fn()
+        return self[key]
 
 
 def squared_sampson_error(points2D1, points2D2, E):

@@ -122,8 +122,9 @@ enum b2m_tvg_config {
  * COLMAP's (U:sensor/models.h): 0 SIMPLE_PINHOLE (f, cx, cy), 1 PINHOLE (fx, fy, cx, cy),
  * 2 SIMPLE_RADIAL (f, cx, cy, k), 3 RADIAL (f, cx, cy, k1, k2), 4 OPENCV (fx, fy, cx, cy, k1, k2, p1, p2),
  * 5 OPENCV_FISHEYE (fx, fy, cx, cy, k1, k2, k3, k4), 6 FULL_OPENCV (fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, k5, k6),
- * 8 SIMPLE_RADIAL_FISHEYE (f, cx, cy, k), 9 RADIAL_FISHEYE (f, cx, cy, k1, k2).
- * FOV (7) and THIN_PRISM_FISHEYE (10) are rejected with B2M_EINVAL.  Unused params must be 0. */
+ * 7 FOV (fx, fy, cx, cy, omega), 8 SIMPLE_RADIAL_FISHEYE (f, cx, cy, k), 9 RADIAL_FISHEYE (f, cx, cy, k1, k2),
+ * 10 THIN_PRISM_FISHEYE (fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, sx1, sy1).  Other ids are rejected with
+ * B2M_EINVAL.  Unused params must be 0. */
 #define B2M_CAMERA_MAX_PARAMS 12
 typedef struct b2m_camera {
   uint32_t struct_size;

@@ -349,9 +349,10 @@ def loransac(est, local_est, X, Y, opt, rng):
 # cameras (U:sensor/models.h, COLMAP 3.9.1 ids and parameter orders)
 #   0 SIMPLE_PINHOLE f cx cy | 1 PINHOLE fx fy cx cy | 2 SIMPLE_RADIAL f cx cy k | 3 RADIAL f cx cy k1 k2
 #   4 OPENCV fx fy cx cy k1 k2 p1 p2 | 5 OPENCV_FISHEYE fx fy cx cy k1 k2 k3 k4
-#   6 FULL_OPENCV fx fy cx cy k1 k2 p1 p2 k3 k4 k5 k6 | 8 SIMPLE_RADIAL_FISHEYE f cx cy k | 9 RADIAL_FISHEYE f cx cy k1 k2
+#   6 FULL_OPENCV fx fy cx cy k1 k2 p1 p2 k3 k4 k5 k6 | 7 FOV fx fy cx cy omega | 8 SIMPLE_RADIAL_FISHEYE f cx cy k
+#   9 RADIAL_FISHEYE f cx cy k1 k2 | 10 THIN_PRISM_FISHEYE fx fy cx cy k1 k2 p1 p2 k3 k4 sx1 sy1
 # ---------------------------------------------------------------------------------------------
-CAMERA_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 8: 4, 9: 5}
+CAMERA_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 7: 5, 8: 4, 9: 5, 10: 12}
 _SINGLE_FOCAL = (0, 2, 3, 8, 9)
 
 
@@ -382,6 +383,12 @@ def camera_distortion(model, k, uv):
         du = u * radial + 2 * k[2] * u * v + k[3] * (r2 + 2 * u * u)
         dv = v * radial + 2 * k[3] * u * v + k[2] * (r2 + 2 * v * v)
         return np.stack([du, dv], 1)
+    if model == 10:   # thin prism, on equidistant fisheye coordinates
+        r4 = r2 * r2
+        radial = k[0] * r2 + k[1] * r4 + k[4] * r4 * r2 + k[5] * r4 * r4
+        du = u * radial + 2 * k[2] * u * v + k[3] * (r2 + 2 * u * u) + k[6] * r2
+        dv = v * radial + 2 * k[3] * u * v + k[2] * (r2 + 2 * v * v) + k[7] * r2
+        return np.stack([du, dv], 1)
     # fisheye family: theta_d = theta * (1 + k1 theta^2 + ...), d = uv * theta_d / r - uv
     kk = (list(k) + [0.0, 0.0, 0.0])[:4]      # models 8 / 9 carry one / two coefficients
     r = np.sqrt(r2)
@@ -395,7 +402,18 @@ def camera_distortion(model, k, uv):
 def img_from_cam(cam, uv):
     """Camera::ImgFromCam on normalised coordinates [n x 2]."""
     model, f, c, k = _intrinsics(cam)
-    uv = np.asarray(uv, np.float64)
+    uv = np.asarray(uv, np.float64).reshape(-1, 2)
+    if model == 7:    # FOV: r_d = atan(2 r tan(w / 2)) / w
+        r = np.linalg.norm(uv, axis=1)
+        w = k[0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            factor = np.where(r > 1e-9, np.arctan(2 * r * np.tan(w / 2)) / (r * w), 2 * np.tan(w / 2) / w)
+        return uv * factor[:, None] * f + c
+    if model == 10:   # equidistant fisheye first, then the thin-prism distortion
+        r = np.linalg.norm(uv, axis=1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            scale = np.where(r > np.finfo(float).eps, np.arctan(r) / r, 1.0)
+        uv = uv * scale[:, None]
     return (uv + camera_distortion(model, k, uv)) * f + c
 
 
@@ -406,6 +424,12 @@ def cam_from_img(cam, pts):
     uv0 = (np.asarray(pts, np.float64) - c) / f
     if model in (0, 1):
         return uv0
+    if model == 7:    # closed-form inverse: r = tan(r_d w) / (2 tan(w / 2))
+        rd = np.linalg.norm(uv0, axis=1)
+        w = k[0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            factor = np.where(rd > 1e-9, np.tan(rd * w) / (2 * rd * np.tan(w / 2)), w / (2 * np.tan(w / 2)))
+        return uv0 * factor[:, None]
     x = uv0.copy()
     active = np.ones(len(x), bool)
     eps = np.finfo(float).eps
@@ -428,6 +452,11 @@ def cam_from_img(cam, pts):
         x[active] = xa - step
         idx = np.flatnonzero(active)
         active[idx[(step ** 2).sum(1) < 1e-10]] = False
+    if model == 10:   # fisheye coordinates -> normalised plane: scale tan(theta) / theta
+        th = np.linalg.norm(x, axis=1)
+        tc = th * np.cos(th)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            x = x * np.where(tc > np.finfo(float).eps, np.sin(th) / tc, 1.0)[:, None]
     return x
 
 

@@ -7,7 +7,10 @@
 // and CamFromImg inverts it -- closed form for the pinhole models, Newton iterations on
 // g(u, v) = (u, v) + d(u, v) - (u0, v0) with a central-difference Jacobian for the others (upstream's
 // IterativeUndistortion: at most 100 iterations, stop when |step|^2 < 1e-10, relative step 1e-6).
-// Model ids and parameter orders are COLMAP's; FOV (7) and THIN_PRISM_FISHEYE (10) are not implemented.
+// Model ids and parameter orders are COLMAP's; all eleven models of 3.9.1 are implemented.  Two have their own
+// structure: FOV (Devernay-Faugeras) distorts multiplicatively, r_d = atan(2 r tan(w/2)) / w, and is inverted in
+// closed form; THIN_PRISM_FISHEYE applies its polynomial + thin-prism terms to the equidistant fisheye
+// coordinates theta * (u, v) / r and maps back with tan(theta) / theta after the iterative undistortion.
 #pragma once
 #include <math.h>
 
@@ -28,10 +31,10 @@ enum ModelId {
   kOpenCV = 4,              // fx, fy, cx, cy, k1, k2, p1, p2
   kOpenCVFisheye = 5,       // fx, fy, cx, cy, k1, k2, k3, k4
   kFullOpenCV = 6,          // fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, k5, k6
-  kFOV = 7,                 // not implemented
+  kFOV = 7,                 // fx, fy, cx, cy, omega
   kSimpleRadialFisheye = 8, // f, cx, cy, k
   kRadialFisheye = 9,       // f, cx, cy, k1, k2
-  kThinPrismFisheye = 10    // not implemented
+  kThinPrismFisheye = 10    // fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, sx1, sy1
 };
 
 constexpr int kMaxParams = 12;
@@ -46,8 +49,10 @@ B2M_CAM_HD int num_params(int model) {
     case kOpenCV: return 8;
     case kOpenCVFisheye: return 8;
     case kFullOpenCV: return 12;
+    case kFOV: return 5;
     case kSimpleRadialFisheye: return 4;
     case kRadialFisheye: return 5;
+    case kThinPrismFisheye: return 12;
     default: return -1;
   }
 }
@@ -115,9 +120,33 @@ B2M_CAM_HD void distortion(int model, const double* k, double u, double v, doubl
       }
       return;
     }
+    case kThinPrismFisheye: {  // on the equidistant fisheye coordinates: k1, k2, p1, p2, k3, k4, sx1, sy1
+      const double uv = u * v, r4 = r2 * r2, r6 = r4 * r2, r8 = r6 * r2;
+      const double radial = k[0] * r2 + k[1] * r4 + k[4] * r6 + k[5] * r8;
+      *du = u * radial + 2.0 * k[2] * uv + k[3] * (r2 + 2.0 * u2) + k[6] * r2;
+      *dv = v * radial + 2.0 * k[3] * uv + k[2] * (r2 + 2.0 * v2) + k[7] * r2;
+      return;
+    }
     default:
       *du = 0.0; *dv = 0.0;
   }
+}
+
+// FOV model: distorted = factor * undistorted with factor = atan(2 r tan(w/2)) / (r w) (-> 2 tan(w/2) / w as r -> 0,
+// -> 1 as w -> 0), and its closed-form inverse factor = tan(r_d w) / (2 r_d tan(w/2)).
+B2M_CAM_HD double fov_distort_factor(double omega, double r2) {
+  const double t = tan(0.5 * omega);
+  if (fabs(omega) < 1e-8) return 1.0;
+  const double x = 2.0 * sqrt(r2) * t;
+  if (fabs(x) < 1e-6) return (2.0 * t / omega) * (1.0 - x * x / 3.0);
+  return atan(x) / (sqrt(r2) * omega);
+}
+B2M_CAM_HD double fov_undistort_factor(double omega, double r2) {
+  const double t = tan(0.5 * omega);
+  if (fabs(omega) < 1e-8) return 1.0;
+  const double y = sqrt(r2) * omega;
+  if (fabs(y) < 1e-6) return (omega / (2.0 * t)) * (1.0 + y * y / 3.0);
+  return tan(y) / (2.0 * sqrt(r2) * t);
 }
 
 // (u, v) -> the point whose distorted image is (u, v): Newton with a central-difference Jacobian
@@ -153,7 +182,21 @@ B2M_CAM_HD void cam_from_img(int model, const double* p, double x, double y, dou
   intrinsics(model, p, &fx, &fy, &cx, &cy, &extra);
   *u = (x - cx) / fx;
   *v = (y - cy) / fy;
-  if (has_distortion(model)) iterative_undistortion(model, p + extra, u, v);
+  if (model == kFOV) {
+    const double f = fov_undistort_factor(p[extra], *u * *u + *v * *v);
+    *u *= f;
+    *v *= f;
+  } else if (has_distortion(model)) {
+    iterative_undistortion(model, p + extra, u, v);
+    if (model == kThinPrismFisheye) {  // fisheye coordinates (theta direction) -> normalised plane
+      const double theta = sqrt(*u * *u + *v * *v), tc = theta * cos(theta);
+      if (tc > 2.220446049250313e-16) {
+        const double sc = sin(theta) / tc;
+        *u *= sc;
+        *v *= sc;
+      }
+    }
+  }
 }
 
 // Camera::ImgFromCam on normalised coordinates (used by the tests for round trips and to build scenes)
@@ -161,7 +204,21 @@ B2M_CAM_HD void img_from_cam(int model, const double* p, double u, double v, dou
   double fx, fy, cx, cy, du = 0.0, dv = 0.0;
   int extra;
   intrinsics(model, p, &fx, &fy, &cx, &cy, &extra);
-  if (has_distortion(model)) distortion(model, p + extra, u, v, &du, &dv);
+  if (model == kFOV) {
+    const double f = fov_distort_factor(p[extra], u * u + v * v);
+    u *= f;
+    v *= f;
+  } else if (model == kThinPrismFisheye) {
+    const double r = sqrt(u * u + v * v);
+    if (r > 2.220446049250313e-16) {
+      const double theta = atan(r);
+      u = theta * u / r;
+      v = theta * v / r;
+    }
+    distortion(model, p + extra, u, v, &du, &dv);
+  } else if (has_distortion(model)) {
+    distortion(model, p + extra, u, v, &du, &dv);
+  }
   *x = fx * (u + du) + cx;
   *y = fy * (v + dv) + cy;
 }

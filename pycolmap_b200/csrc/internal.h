@@ -17,7 +17,7 @@ inline const char* camera_problem(const b2m_camera& c) {
   if (c.struct_size != sizeof(b2m_camera))
     return "[internal.h] Check Failed: b2m_camera.struct_size == sizeof(b2m_camera) (ABI version 2: 12 parameters)";
   if (cam::num_params(c.model) < 0)
-    return "[internal.h] camera model id is not supported (COLMAP ids 0-6, 8, 9; FOV and THIN_PRISM_FISHEYE are not)";
+    return "[internal.h] camera model id is not supported (COLMAP 3.9.1 model ids 0-10)";
   double fx, fy, cx, cy;
   int extra;
   cam::intrinsics(c.model, c.params, &fx, &fy, &cx, &cy, &extra);

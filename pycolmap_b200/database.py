@@ -13,9 +13,8 @@ import numpy as np
 MAX_NUM_IMAGES = 2147483647  # kMaxNumImages: pair_id = id1 * kMaxNumImages + id2, id1 < id2
 
 # COLMAP camera model id -> number of parameters, for the models the verifier supports (U:sensor/models.h):
-# SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL, OPENCV, OPENCV_FISHEYE, FULL_OPENCV, SIMPLE_RADIAL_FISHEYE,
-# RADIAL_FISHEYE.  FOV (7) and THIN_PRISM_FISHEYE (10) are not implemented.
-CAMERA_MODEL_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 8: 4, 9: 5}
+# all eleven models of COLMAP 3.9.1.
+CAMERA_MODEL_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 7: 5, 8: 4, 9: 5, 10: 12}
 CAMERA_MODEL_IDS = {"SIMPLE_PINHOLE": 0, "PINHOLE": 1, "SIMPLE_RADIAL": 2, "RADIAL": 3, "OPENCV": 4,
                     "OPENCV_FISHEYE": 5, "FULL_OPENCV": 6, "FOV": 7, "SIMPLE_RADIAL_FISHEYE": 8,
                     "RADIAL_FISHEYE": 9, "THIN_PRISM_FISHEYE": 10}
@@ -132,7 +131,7 @@ class Database:
         model, w, h, params, prior = row
         if model not in CAMERA_MODEL_NUM_PARAMS:
             raise ValueError(f"[database.py] camera model id {model} is not supported by the B200 verifier "
-                             "(FOV and THIN_PRISM_FISHEYE are not implemented)")
+                             "(COLMAP 3.9.1 model ids 0-10)")
         p = np.frombuffer(params, np.float64)
         if len(p) != CAMERA_MODEL_NUM_PARAMS[model]:
             raise ValueError(f"[database.py] Check Failed: camera model {model} has "

@@ -372,8 +372,7 @@ def _camera_dict(camera):
     name = getattr(model, "name", model)
     model_id = CAMERA_MODEL_IDS.get(name) if isinstance(name, str) else int(name)
     if model_id not in CAMERA_MODEL_NUM_PARAMS:
-        raise ValueError(f"[pipeline.py] camera model {name} is not supported "
-                         "(FOV and THIN_PRISM_FISHEYE are not implemented)")
+        raise ValueError(f"[pipeline.py] camera model {name} is not supported (COLMAP 3.9.1 models only)")
     params = [float(x) for x in get("params", [])]
     if len(params) != CAMERA_MODEL_NUM_PARAMS[model_id]:
         raise ValueError(f"[pipeline.py] Check Failed: camera model {name} has "

@@ -174,11 +174,11 @@ r_db = os.path.join(tmp, "radial.db")
 make_db(r_db, camera=(2, [1200.0, 800.0, 600.0, -0.1]))
 nat.match_exhaustive(r_db, matching_options={"block_size": 4})
 assert [r[:2] for r in dump(r_db)["matches"]] == [r[:2] for r in ref_dump["matches"]]
-f_db = os.path.join(tmp, "fov.db")
-make_db(f_db, camera=(7, [1200.0, 1200.0, 800.0, 600.0, 0.5]))
+f_db = os.path.join(tmp, "unknown_model.db")
+make_db(f_db, camera=(11, [1200.0, 1200.0, 800.0, 600.0, 0.5]))
 try:
     nat.match_exhaustive(f_db)
-    raise SystemExit("FOV must be refused")
+    raise SystemExit("an unknown camera model id must be refused")
 except ValueError as e:
     assert "not supported" in str(e)
 bad = os.path.join(tmp, "bad.db")

@@ -21,8 +21,10 @@ CAMS = {
     4: [1200.0, 1190.0, 800.0, 600.0, -0.12, 0.03, 1e-3, -2e-3],
     5: [700.0, 705.0, 800.0, 600.0, 0.05, -0.01, 0.003, -0.001],
     6: [1200.0, 1190.0, 800.0, 600.0, -0.12, 0.03, 1e-3, -2e-3, 0.002, 0.01, -0.004, 0.0005],
+    7: [1200.0, 1190.0, 800.0, 600.0, 0.7],
     8: [700.0, 800.0, 600.0, 0.05],
     9: [700.0, 800.0, 600.0, 0.05, -0.01],
+    10: [700.0, 705.0, 800.0, 600.0, 0.05, -0.01, 1e-3, -2e-3, 0.003, -0.001, 2e-3, -1e-3],
 }
 
 
@@ -80,6 +82,11 @@ def test_known_distortion_values():
     assert np.allclose(R.img_from_cam(cam, [[u, v]]), [[1000 * (u + du), 1000 * (v + dv)]])
     cam = dict(model=8, params=[500.0, 0.0, 0.0, 0.0])                   # equidistant fisheye: r -> atan(r)
     assert np.allclose(R.img_from_cam(cam, [[1.0, 0.0]]), [[500 * np.pi / 4, 0.0]])
-    for bad in (7, 10, 11, -1):
+    cam = dict(model=7, params=[1000.0, 1000.0, 0.0, 0.0, 0.8])         # FOV: r_d = atan(2 r tan(w / 2)) / w
+    assert np.allclose(R.img_from_cam(cam, [[0.5, 0.0]]), [[1000 * np.arctan(2 * 0.5 * np.tan(0.4)) / 0.8, 0.0]])
+    cam = dict(model=10, params=[500.0, 500.0, 0.0, 0.0] + [0.0] * 6 + [0.01, -0.02])   # thin prism terms on theta
+    th = np.arctan(1.0)
+    assert np.allclose(R.img_from_cam(cam, [[1.0, 0.0]]), [[500 * (th + 0.01 * th * th), 500 * (-0.02 * th * th)]])
+    for bad in (11, -1):
         with pytest.raises(ValueError):
             R.cam_from_img(dict(model=bad, params=[1.0] * 5), np.zeros((1, 2)))

@@ -231,7 +231,7 @@ def test_argument_checks_before_any_gpu_work(tmp_path):
     with pytest.raises(ValueError, match="points1.size"):
         nat.fundamental_matrix_estimation(np.zeros((4, 2)), np.zeros((5, 2)))
     with pytest.raises(ValueError, match="not supported"):
-        nat.estimate_two_view_geometry(dict(cam, model="FOV"), np.zeros((3, 2)), cam, np.zeros((3, 2)))
+        nat.estimate_two_view_geometry(dict(cam, model=11), np.zeros((3, 2)), cam, np.zeros((3, 2)))
     with pytest.raises(ValueError, match="8 parameters"):      # OPENCV needs fx fy cx cy k1 k2 p1 p2
         nat.estimate_two_view_geometry(dict(cam, model="OPENCV"), np.zeros((3, 2)), cam, np.zeros((3, 2)))
     with pytest.raises(ValueError, match="unknown camera model"):

@@ -195,6 +195,8 @@ DIST_CAMS = {
     "OPENCV_FISHEYE": dict(model=5, params=[1200.0, 1200.0, 800.0, 600.0, 0.05, -0.01, 0.003, -0.001]),
     "FULL_OPENCV": dict(model=6, params=[1200.0, 1200.0, 800.0, 600.0, -0.12, 0.03, 1e-3, -2e-3, 0.002, 0.01, -0.004, 5e-4]),
     "RADIAL_FISHEYE": dict(model=9, params=[1200.0, 800.0, 600.0, 0.05, -0.01]),
+    "FOV": dict(model=7, params=[1200.0, 1200.0, 800.0, 600.0, 0.7]),
+    "THIN_PRISM_FISHEYE": dict(model=10, params=[1200.0, 1200.0, 800.0, 600.0, 0.05, -0.01, 1e-3, -2e-3, 0.003, -0.001, 2e-3, -1e-3]),
 }
 
 
@@ -285,7 +287,7 @@ def test_distortion_model_database_pipeline(tmp_path):
 
 
 def test_unsupported_camera_models_are_rejected():
-    cam = dict(model=7, width=1600, height=1200, params=[1200.0, 1200.0, 800.0, 600.0, 0.5])
+    cam = dict(model=11, width=1600, height=1200, params=[1200.0, 1200.0, 800.0, 600.0, 0.5])
     with pytest.raises(ValueError, match="not supported"):
         nat.estimate_two_view_geometry(cam, np.zeros((20, 2)), cam, np.zeros((20, 2)))
     with pytest.raises(ValueError, match="not supported"):

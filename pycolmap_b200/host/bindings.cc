@@ -774,6 +774,52 @@ PYBIND11_MODULE(_core, m) {
            })
       .def("read_camera", [](Database& db, int64_t camera_id) { return CameraToDict(db.ReadCamera(camera_id)); },
            "camera_id"_a)
+      // the rest of the reference's Database surface (R:scene/database.h:10-47); cameras are dicts, images are
+      // (image_id, name, camera_id) tuples here -- pycolmap.Camera / Image belong to the reconstruction object model
+      .def("read_all_cameras",
+           [](Database& db) {
+             py::list out;
+             for (const CameraRow& c : db.ReadAllCameras()) {
+               py::dict d = CameraToDict(c);
+               d["camera_id"] = c.camera_id;
+               out.append(d);
+             }
+             return out;
+           })
+      .def("read_image",
+           [](Database& db, int64_t image_id) -> py::object {
+             ImageRow r;
+             if (!db.ReadImage(image_id, &r)) throw std::invalid_argument("[bindings.cc] Check Failed: image exists");
+             return py::make_tuple(r.image_id, r.name, r.camera_id);
+           },
+           "image_id"_a)
+      .def("read_image_with_name",
+           [](Database& db, const std::string& name) -> py::object {
+             ImageRow r;
+             if (!db.ReadImageWithName(name, &r)) throw std::invalid_argument("[bindings.cc] Check Failed: image exists");
+             return py::make_tuple(r.image_id, r.name, r.camera_id);
+           },
+           "name"_a)
+      .def("num_keypoints_for_image", &Database::NumKeypointsForImage, "image_id"_a)
+      .def("num_descriptors_for_image", &Database::NumDescriptorsForImage, "image_id"_a)
+      .def("image_pair_to_pair_id", [](Database&, int64_t a, int64_t b) { return ImagePairToPairId(a, b); },
+           "image_id1"_a, "image_id2"_a)
+      .def("pair_id_to_image_pair",
+           [](Database&, int64_t pid) {
+             int64_t a, b;
+             PairIdToImagePair(pid, &a, &b);
+             return py::make_tuple(a, b);
+           },
+           "pair_id"_a)
+      .def("write_camera",
+           [](Database& db, const py::object& camera) {
+             const b2m_camera c = CameraFromPython(camera);   // validates model id and parameter count
+             return db.AddCamera(c.model, c.width, c.height,
+                                 std::vector<double>(c.params, c.params + b2m::cam::num_params(c.model)),
+                                 c.has_prior_focal_length != 0);
+           },
+           "camera"_a)
+      .def("write_image", &Database::AddImage, "name"_a, "camera_id"_a)
       .def("read_keypoints",
            [](Database& db, int64_t image_id) {
              const KeypointsBlob k = db.ReadKeypoints(image_id);
@@ -827,6 +873,9 @@ PYBIND11_MODULE(_core, m) {
       .def("begin", &Database::Begin)
       .def("commit", &Database::Commit)
       .def("rollback", &Database::Rollback);
+
+  py::class_<DatabaseTransaction>(m, "DatabaseTransaction")   // R:scene/database.h:45-46: BEGIN now, COMMIT when released
+      .def(py::init<Database*>(), "database"_a, py::keep_alive<1, 2>());
 
   // ---- low-level context ----
   py::class_<CoreResults>(m, "Results")

@@ -214,6 +214,45 @@ std::vector<ImageRow> Database::ReadAllImages() {
   return out;
 }
 
+bool Database::ReadImage(int64_t image_id, ImageRow* out) {
+  Stmt s(this, "SELECT image_id, name, camera_id FROM images WHERE image_id = ?");
+  s.I64(1, image_id);
+  if (!s.Step()) return false;
+  *out = ImageRow{s.ColI64(0), s.ColText(1), s.ColI64(2)};
+  return true;
+}
+
+bool Database::ReadImageWithName(const std::string& name, ImageRow* out) {
+  Stmt s(this, "SELECT image_id, name, camera_id FROM images WHERE name = ?");
+  s.Text(1, name);
+  if (!s.Step()) return false;
+  *out = ImageRow{s.ColI64(0), s.ColText(1), s.ColI64(2)};
+  return true;
+}
+
+std::vector<CameraRow> Database::ReadAllCameras() {
+  std::vector<int64_t> ids;
+  {
+    Stmt s(this, "SELECT camera_id FROM cameras ORDER BY camera_id");
+    while (s.Step()) ids.push_back(s.ColI64(0));
+  }
+  std::vector<CameraRow> out;
+  for (int64_t id : ids) out.push_back(ReadCamera(id));
+  return out;
+}
+
+int64_t Database::NumKeypointsForImage(int64_t image_id) {
+  Stmt s(this, "SELECT rows FROM keypoints WHERE image_id = ?");
+  s.I64(1, image_id);
+  return s.Step() ? s.ColI64(0) : 0;
+}
+
+int64_t Database::NumDescriptorsForImage(int64_t image_id) {
+  Stmt s(this, "SELECT rows FROM descriptors WHERE image_id = ?");
+  s.I64(1, image_id);
+  return s.Step() ? s.ColI64(0) : 0;
+}
+
 CameraRow Database::ReadCamera(int64_t camera_id) {
   Stmt s(this, "SELECT model, width, height, params, prior_focal_length FROM cameras WHERE camera_id = ?");
   s.I64(1, camera_id);

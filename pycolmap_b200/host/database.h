@@ -93,6 +93,11 @@ class Database {
   void WriteDescriptors(int64_t image_id, const uint8_t* data, int64_t rows, int64_t cols);
 
   std::vector<ImageRow> ReadAllImages();  // ordered by image_id
+  bool ReadImage(int64_t image_id, ImageRow* out);
+  bool ReadImageWithName(const std::string& name, ImageRow* out);
+  std::vector<CameraRow> ReadAllCameras();
+  int64_t NumKeypointsForImage(int64_t image_id);
+  int64_t NumDescriptorsForImage(int64_t image_id);
   CameraRow ReadCamera(int64_t camera_id);
   KeypointsBlob ReadKeypoints(int64_t image_id);
   DescriptorsBlob ReadDescriptors(int64_t image_id);

@@ -308,3 +308,26 @@ def test_batched_estimator_argument_checks():
         nat.estimate_two_view_geometries([(cam, np.zeros((3, 3)), cam, np.zeros((3, 2)))])
     with pytest.raises(ValueError, match="matches"):
         nat.estimate_two_view_geometries([(cam, np.zeros((3, 2)), cam, np.zeros((3, 2)), np.zeros((3, 3), np.uint32))])
+
+
+def test_database_reference_surface(tmp_path):
+    """The members the reference binds on Database (R:scene/database.h:10-47) beyond the counters."""
+    with nat.Database(tmp_path / "db.db") as db:
+        cid = db.write_camera(dict(model="SIMPLE_RADIAL", width=640, height=480, params=[500.0, 320.0, 240.0, 0.01],
+                                   has_prior_focal_length=True))
+        iid = db.write_image("a.jpg", cid)
+        db.write_keypoints(iid, np.zeros((7, 2), np.float32))
+        db.write_descriptors(iid, np.zeros((7, 128), np.uint8))
+        cams = db.read_all_cameras()
+        assert len(cams) == 1 and cams[0]["camera_id"] == cid and cams[0]["model"] == 2 and cams[0]["params"][3] == 0.01
+        assert db.read_image(iid) == (iid, "a.jpg", cid) == db.read_image_with_name("a.jpg")
+        assert db.num_keypoints_for_image(iid) == 7 == db.num_descriptors_for_image(iid) and db.num_keypoints_for_image(99) == 0
+        assert db.pair_id_to_image_pair(db.image_pair_to_pair_id(9, 4)) == (4, 9)
+        with pytest.raises(ValueError):
+            db.read_image(12345)
+        with pytest.raises(ValueError, match="4 parameters"):
+            db.write_camera(dict(model="SIMPLE_RADIAL", width=1, height=1, params=[1.0, 0, 0]))
+        tx = nat.DatabaseTransaction(db)                 # BEGIN ... COMMIT on release
+        db.write_matches(iid, iid + 1, np.array([[0, 1]], np.uint32))
+        del tx
+        assert db.exists_matches(iid, iid + 1)

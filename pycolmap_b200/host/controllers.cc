@@ -230,6 +230,8 @@ struct LoadedSet {
   std::vector<std::string> names;
   std::vector<int64_t> camera_ids;
   std::vector<int32_t> n_feat;
+  std::vector<std::vector<float>> xy;   // keypoint positions per image (kept for the multiple_models re-estimation)
+  std::vector<b2m_camera> cams;
 };
 
 // FeatureMatcherCache: every image's descriptors, keypoint positions and camera go to the GPU once
@@ -281,6 +283,8 @@ LoadedSet LoadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, bool ord
   for (std::thread& w : workers) w.join();
   for (size_t d = 0; d < ctxs.size(); ++d) ThrowOnError(ctxs[d], rc[d]);
   L.n_feat = std::move(n_feat);
+  L.xy = std::move(xy);
+  L.cams = std::move(cams);
   return L;
 }
 
@@ -327,9 +331,14 @@ void MatchPairsIntoDb(Database& db, const std::vector<b2m_ctx*>& ctxs, const Loa
     const std::vector<int64_t> cut = SplitPairsByCost(todo, L.n_feat, static_cast<int>(ctxs.size()));
     std::vector<ResultsGuard> res(ctxs.size());
     std::vector<int> rc(ctxs.size(), B2M_OK);
+    // TwoViewGeometryOptions.multiple_models: the batched verifier finds one geometry per pair; the pairs it
+    // verified are then re-estimated through the estimator entry point, which runs upstream's
+    // estimate / remove inliers / repeat loop (EstimateMultipleTwoViewGeometries) on the raw matches.
+    b2m_tvg_opts tvg_batch = tvg;
+    tvg_batch.multiple_models = 0;
     auto run = [&](size_t d) {
       const int64_t n = cut[d + 1] - cut[d];
-      if (n > 0) rc[d] = b2m_match_pairs(ctxs[d], todo.data() + 2 * cut[d], n, &sift, &tvg, &res[d].r);
+      if (n > 0) rc[d] = b2m_match_pairs(ctxs[d], todo.data() + 2 * cut[d], n, &sift, &tvg_batch, &res[d].r);
     };
     std::vector<std::thread> workers;
     for (size_t d = 1; d < ctxs.size(); ++d) workers.emplace_back(run, d);
@@ -344,8 +353,25 @@ void MatchPairsIntoDb(Database& db, const std::vector<b2m_ctx*>& ctxs, const Loa
         memset(&v, 0, sizeof(v));
         v.struct_size = sizeof(v);
         ThrowOnError(ctxs[d], b2m_results_get(res[d].r, k, &v));
-        const int64_t id1 = L.ids[todo[2 * (cut[d] + k)]], id2 = L.ids[todo[2 * (cut[d] + k) + 1]];
+        const int32_t a = todo[2 * (cut[d] + k)], b = todo[2 * (cut[d] + k) + 1];
+        const int64_t id1 = L.ids[a], id2 = L.ids[b];
         db.WriteMatches(id1, id2, v.matches, v.n_matches);
+        if (tvg.multiple_models && v.config != B2M_UNDEFINED && v.n_matches > 0) {
+          auto as_double = [](const std::vector<float>& f) { return std::vector<double>(f.begin(), f.end()); };
+          const std::vector<double> p1 = as_double(L.xy[a]), p2 = as_double(L.xy[b]);
+          b2m_tvg_result r;
+          memset(&r, 0, sizeof(r));
+          r.struct_size = sizeof(r);
+          std::vector<uint32_t> inl(static_cast<size_t>(v.n_matches) * 2);
+          ThrowOnError(ctxs[d], b2m_estimate_two_view_geometry(ctxs[d], &L.cams[a], p1.data(), static_cast<int64_t>(p1.size() / 2),
+                                                               &L.cams[b], p2.data(), static_cast<int64_t>(p2.size() / 2),
+                                                               v.matches, v.n_matches, &tvg, &r, inl.data()));
+          const bool keep = r.n_inliers >= tvg.min_num_inliers;   // controller write rule (row P3)
+          db.WriteTwoViewGeometry(id1, id2, keep ? r.config : B2M_UNDEFINED, inl.data(), keep ? r.n_inliers : 0,
+                                  keep ? ToMat3(r.F) : Mat3{}, keep ? ToMat3(r.E) : Mat3{}, keep ? ToMat3(r.H) : Mat3{},
+                                  {r.qvec[0], r.qvec[1], r.qvec[2], r.qvec[3]}, {r.tvec[0], r.tvec[1], r.tvec[2]});
+          continue;
+        }
         db.WriteTwoViewGeometry(id1, id2, v.config, v.inlier_matches, v.n_inliers, ToMat3(v.F), ToMat3(v.E),
                                 ToMat3(v.H), {v.qvec[0], v.qvec[1], v.qvec[2], v.qvec[3]}, {v.tvec[0], v.tvec[1], v.tvec[2]});
       }

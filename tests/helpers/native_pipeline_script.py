@@ -192,6 +192,24 @@ try:
 except ValueError as e:
     assert "keypoints.rows == descriptors.rows" in str(e)
 
+# ---- multiple_models in the pipelines: verified pairs are re-estimated through the estimator entry point ------------
+m_db = os.path.join(tmp, "multi.db")
+make_db(m_db)
+nat.match_exhaustive(m_db, matching_options={"block_size": 4}, verification_options={"multiple_models": True})
+n_multi = 0
+with nat.Database(m_db) as db:
+    for i1, i2 in visits:
+        want = oracle.fast_match_pair(descs[i1], descs[i2])
+        g = db.read_two_view_geometry(ids[i1], ids[i2])
+        if fake_geometry(i1, i2, want)[0] == 0:                      # not verified by the batch: left alone
+            assert g.config.value == 0
+            continue
+        cfg, inl, E, F, H = fake_geometry(7, 9, want)                  # the mock's estimator entry point signature
+        assert g.config.value == cfg == 2 and np.array_equal(g.inlier_matches, inl) and np.array_equal(g.E, E), (i1, i2)
+        n_multi += 1
+assert n_multi == n_verified
+assert [r[:3] for r in dump(m_db)["matches"]] == [r[:3] for r in ref_dump["matches"]]
+
 # ---- low-level context through the mock: plumbing of options and result objects ------------------------------
 c = nat.Context()
 c.set_images(descs[:3])

@@ -330,7 +330,17 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
         cudaError_t e = launch_k1_filter_skip(S.tmap, mp, S.d_desc, nb, max_strips, ctx->num_sms, W.d_pairs_dir1,
                                               S.n_images, st, nullptr);
         if (e == cudaSuccess) e = launch_crosscheck_compact(ct, nb, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) {
+          // the split schedule could not even be launched (a non-sticky launch error): stay on the validated
+          // launch instead of failing the call; a sticky error resurfaces at the next CUDA call anyway
+          cudaGetLastError();
+          drop();
+          ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
+          t_arena = nullptr; t_off = nullptr; t_cnt = nullptr; t_flag = nullptr;
+          CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
+          goto k1_selftest_done;
+        }
+        e = cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st);
         if (e == cudaSuccess)
           e = launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st, nullptr);
         if (e == cudaSuccess) e = launch_crosscheck_compact(cp, nb, st);
@@ -351,6 +361,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
         CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));  // the batch is redone below
       }
     }
+  k1_selftest_done:
     const bool use_skip = skip_capable && (ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP || ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP_FORCED);
     CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
     if (ctx->exact_k1) {

@@ -833,6 +833,44 @@ def exhaustive_pairs(image_ids, block_size=50):
     return out
 
 
+def gps_to_ecef(lat_deg, lon_deg, alt):
+    """GPSTransform::EllToXYZ on the WGS84 ellipsoid (U:geometry/gps.cc)."""
+    a, f = 6378137.0, 1.0 / 298.257223563
+    b = a * (1.0 - f)
+    e2 = (a * a - b * b) / (a * a)
+    lat, lon = np.radians(lat_deg), np.radians(lon_deg)
+    N = a / np.sqrt(1.0 - e2 * np.sin(lat) ** 2)
+    return np.stack([(N + alt) * np.cos(lat) * np.cos(lon), (N + alt) * np.cos(lat) * np.sin(lon),
+                     ((b * b) / (a * a) * N + alt) * np.sin(lat)], -1)
+
+
+def spatial_pairs(prior_t, has_prior, is_gps=True, ignore_z=True, max_num_neighbors=50, max_distance=100.0):
+    """SpatialFeatureMatcher::Run pair generation (U:controllers/feature_matching.cc): for every image with a location
+    prior, the k = min(max_num_neighbors, #locations) nearest located images including itself, minus itself, up to
+    max_distance; indices are positions in the image list."""
+    prior_t = np.asarray(prior_t, np.float64).reshape(-1, 3)
+    idx = [i for i, h in enumerate(has_prior) if h]
+    if not idx:
+        return []
+    loc = prior_t[idx].copy()
+    if is_gps:
+        loc = gps_to_ecef(loc[:, 0], loc[:, 1], np.zeros(len(loc)) if ignore_z else loc[:, 2])
+    elif ignore_z:
+        loc[:, 2] = 0.0
+    knn = min(max_num_neighbors, len(loc))
+    out = []
+    for i in range(len(loc)):
+        d2 = ((loc - loc[i]) ** 2).sum(1)
+        order = sorted(range(len(loc)), key=lambda j: (d2[j], j))[:knn]
+        for j in order:
+            if j == i:
+                continue
+            if d2[j] > max_distance ** 2:
+                break
+            out.append((idx[i], idx[j]))
+    return out
+
+
 def sequential_pairs(image_ids, overlap=10, quadratic_overlap=True):
     """SequentialFeatureMatcher::RunSequentialMatching (row P2); images ordered by name upstream."""
     ids = list(image_ids)

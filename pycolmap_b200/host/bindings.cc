@@ -372,6 +372,15 @@ PYBIND11_MODULE(_core, m) {
       .field("loop_detection_max_num_features", &SequentialMatchingOptions::loop_detection_max_num_features)
       .field("vocab_tree_path", &SequentialMatchingOptions::vocab_tree_path)
       .Finish();
+  OptionsClass<SpatialMatchingOptions>(m, "SpatialMatchingOptions")
+      .field("is_gps", &SpatialMatchingOptions::is_gps,
+             "Whether the location priors in the database are GPS coordinates in the form of longitude and latitude "
+             "coordinates in degrees.")
+      .field("ignore_z", &SpatialMatchingOptions::ignore_z, "Whether to ignore the Z-component of the location prior.")
+      .field("max_num_neighbors", &SpatialMatchingOptions::max_num_neighbors, "The maximum number of nearest neighbors to match.")
+      .field("max_distance", &SpatialMatchingOptions::max_distance,
+             "The maximum distance between the query and nearest neighbor [meters].")
+      .Finish();
   OptionsClass<TwoViewGeometryOptions>(m, "TwoViewGeometryOptions")
       .field("min_num_inliers", &TwoViewGeometryOptions::min_num_inliers)
       .field("min_E_F_inlier_ratio", &TwoViewGeometryOptions::min_E_F_inlier_ratio)
@@ -496,6 +505,22 @@ PYBIND11_MODULE(_core, m) {
         "database_path"_a, "sift_options"_a = SiftMatchingOptions(), "matching_options"_a = SequentialMatchingOptions(),
         "verification_options"_a = TwoViewGeometryOptions(), "device"_a = Device::AUTO,
         "Sequential feature matching (images ordered by name; overlap / quadratic overlap)");
+  m.def("match_spatial",
+        [](const py::object& database_path, SiftMatchingOptions sift_options, SpatialMatchingOptions matching_options,
+           TwoViewGeometryOptions verification_options, Device device) {
+          const std::string path = FsPath(database_path);
+          CheckFileExists(path, "match_features.h:32");
+          const std::vector<int> dev = ResolveDevices(device, sift_options);
+          RunInterruptible([&] { MatchSpatial(path, sift_options, matching_options, verification_options, dev); });
+        },
+        "database_path"_a, "sift_options"_a = SiftMatchingOptions(), "matching_options"_a = SpatialMatchingOptions(),
+        "verification_options"_a = TwoViewGeometryOptions(), "device"_a = Device::AUTO,
+        "Spatial feature matching (nearest neighbours by location prior)");
+  m.def("match_vocabtree",
+        [](const py::object&, const py::args&, const py::kwargs&) {
+          throw std::invalid_argument("[bindings.cc] match_vocabtree needs a vocabulary tree index: out of scope (SURVEY.md section 8(f) item 4)");
+        },
+        "database_path"_a, "Not available: vocabulary-tree retrieval is outside the hot path this library covers.");
   m.def("verify_matches",
         [](const py::object& database_path, const py::object& pairs_path, TwoViewGeometryOptions options) {
           const std::string db = FsPath(database_path), pairs = FsPath(pairs_path);
@@ -715,6 +740,18 @@ PYBIND11_MODULE(_core, m) {
           return SplitPairsByCost(PairList(pairs.data(), pairs.data() + pairs.size()), n_feat, parts);
         },
         "pairs"_a, "n_feat"_a, "parts"_a);
+  m.def("spatial_pairs",
+        [](const ArrD& prior_t, const std::vector<bool>& has_prior, const SpatialMatchingOptions& options) {
+          if (prior_t.ndim() != 2 || prior_t.shape(1) != 3 || prior_t.shape(0) != static_cast<py::ssize_t>(has_prior.size()))
+            throw std::invalid_argument("[bindings.cc] Check Failed: prior_t is N x 3 with one flag per row");
+          std::vector<std::array<double, 3>> t(has_prior.size());
+          for (size_t i = 0; i < t.size(); ++i) t[i] = {prior_t.data()[3 * i], prior_t.data()[3 * i + 1], prior_t.data()[3 * i + 2]};
+          const PairList p = SpatialPairs(t, has_prior, options);
+          py::array_t<int32_t> a(std::vector<py::ssize_t>{static_cast<py::ssize_t>(p.size() / 2), 2});
+          if (!p.empty()) memcpy(a.mutable_data(), p.data(), p.size() * 4);
+          return a;
+        },
+        "prior_t"_a, "has_prior"_a, "options"_a = SpatialMatchingOptions());
   m.def("sequential_pairs",
         [](int n_images, int overlap, bool quadratic_overlap) {
           const PairList p = SequentialPairs(n_images, overlap, quadratic_overlap);
@@ -753,7 +790,14 @@ PYBIND11_MODULE(_core, m) {
            [](Database& db, int model, int64_t width, int64_t height, const std::vector<double>& params,
               bool prior_focal_length) { return db.AddCamera(model, width, height, params, prior_focal_length); },
            "model"_a, "width"_a, "height"_a, "params"_a, "prior_focal_length"_a = false)
-      .def("add_image", &Database::AddImage, "name"_a, "camera_id"_a)
+      .def("add_image",
+           [](Database& db, const std::string& name, int64_t camera_id, const py::object& prior_t) {
+             if (prior_t.is_none()) return db.AddImage(name, camera_id);
+             const std::vector<double> t = prior_t.cast<std::vector<double>>();
+             if (t.size() != 3) throw std::invalid_argument("[bindings.cc] Check Failed: prior_t has 3 entries");
+             return db.AddImage(name, camera_id, std::array<double, 3>{t[0], t[1], t[2]});
+           },
+           "name"_a, "camera_id"_a, "prior_t"_a = py::none())
       .def("write_keypoints",
            [](Database& db, int64_t image_id, const ArrF32& kp) {
              if (kp.ndim() != 2) throw std::invalid_argument("[bindings.cc] Check Failed: keypoints is a 2-D array");
@@ -819,7 +863,8 @@ PYBIND11_MODULE(_core, m) {
                                  c.has_prior_focal_length != 0);
            },
            "camera"_a)
-      .def("write_image", &Database::AddImage, "name"_a, "camera_id"_a)
+      .def("write_image", [](Database& db, const std::string& name, int64_t camera_id) { return db.AddImage(name, camera_id); },
+           "name"_a, "camera_id"_a)
       .def("read_keypoints",
            [](Database& db, int64_t image_id) {
              const KeypointsBlob k = db.ReadKeypoints(image_id);

@@ -3,6 +3,7 @@
 #include "../csrc/camera_models.h"  // header-only; model ids / parameter counts shared with the kernels
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -157,6 +158,49 @@ PairList SequentialPairs(int n, int overlap, bool quadratic_overlap) {
     for (int k = 0; k < overlap; ++k) {
       emit(i1, static_cast<int64_t>(i1) + k + 1);
       if (quadratic_overlap) emit(i1, static_cast<int64_t>(i1) + (k < 40 ? (int64_t{1} << k) : int64_t{1} << 40));
+    }
+  }
+  return out;
+}
+
+std::array<double, 3> GpsToEcef(double lat_deg, double lon_deg, double alt) {
+  const double a = 6378137.0, f = 1.0 / 298.257223563, b = a * (1.0 - f);   // WGS84
+  const double e2 = (a * a - b * b) / (a * a);
+  const double kDeg = 3.14159265358979323846 / 180.0;
+  const double lat = lat_deg * kDeg, lon = lon_deg * kDeg;
+  const double sl = std::sin(lat), cl = std::cos(lat);
+  const double N = a / std::sqrt(1.0 - e2 * sl * sl);
+  return {(N + alt) * cl * std::cos(lon), (N + alt) * cl * std::sin(lon), ((b * b) / (a * a) * N + alt) * sl};
+}
+
+PairList SpatialPairs(const std::vector<std::array<double, 3>>& prior_t, const std::vector<bool>& has_prior,
+                      const SpatialMatchingOptions& o) {
+  std::vector<int> idx;                       // images with a location prior
+  std::vector<std::array<double, 3>> loc;
+  for (size_t i = 0; i < prior_t.size(); ++i) {
+    if (!has_prior[i]) continue;
+    std::array<double, 3> p = prior_t[i];
+    if (o.is_gps) p = GpsToEcef(p[0], p[1], o.ignore_z ? 0.0 : p[2]);
+    else if (o.ignore_z) p[2] = 0.0;
+    idx.push_back(static_cast<int>(i));
+    loc.push_back(p);
+  }
+  PairList out;
+  const int n = static_cast<int>(loc.size());
+  const int knn = std::min(o.max_num_neighbors, n);
+  const double max_d2 = o.max_distance * o.max_distance;
+  std::vector<std::pair<double, int>> d(n);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) {
+      const double dx = loc[i][0] - loc[j][0], dy = loc[i][1] - loc[j][1], dz = loc[i][2] - loc[j][2];
+      d[j] = {dx * dx + dy * dy + dz * dz, j};
+    }
+    std::partial_sort(d.begin(), d.begin() + knn, d.end());   // the knn nearest (the query itself included), by (distance, index)
+    for (int k = 0; k < knn; ++k) {
+      if (d[k].second == i) continue;
+      if (d[k].first > max_d2) break;
+      out.push_back(idx[i]);
+      out.push_back(idx[d[k].second]);
     }
   }
   return out;
@@ -421,6 +465,22 @@ void MatchSequential(const std::string& database_path, const SiftMatchingOptions
   MatchPairsIntoDb(db, ctxs, L,
                    {SequentialPairs(static_cast<int>(L.ids.size()), matching.overlap, matching.quadratic_overlap)},
                    ToAbi(sift), ToAbi(verification), /*skip_existing=*/true);
+}
+
+void MatchSpatial(const std::string& database_path, const SiftMatchingOptions& sift, const SpatialMatchingOptions& matching,
+                  const TwoViewGeometryOptions& verification, const std::vector<int>& devices) {
+  CheckFileExists(database_path, "match_features.h:32");
+  if (matching.max_num_neighbors < 1) throw std::invalid_argument("[controllers.cc] Check Failed: max_num_neighbors > 0");
+  if (!(matching.max_distance > 0.0)) throw std::invalid_argument("[controllers.cc] Check Failed: max_distance > 0");
+  const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
+  Database db(database_path);
+  const LoadedSet L = LoadImageSet(db, ctxs, /*order_by_name=*/false);
+  std::vector<std::array<double, 3>> prior_t;
+  std::vector<bool> has_prior;
+  db.ReadLocationPriors(&prior_t, &has_prior);   // same order as ReadAllImages (image_id)
+  // the controller drops the pairs it has seen already, (a, b) and (b, a) alike: both map to one pair_id
+  MatchPairsIntoDb(db, ctxs, L, {SpatialPairs(prior_t, has_prior, matching)}, ToAbi(sift), ToAbi(verification),
+                   /*skip_existing=*/true);
 }
 
 void VerifyMatches(const std::string& database_path, const std::string& pairs_path,

@@ -9,6 +9,7 @@
 // All arithmetic happens behind the C ABI on the GPU; nothing here touches a descriptor or a match
 // except to move it between SQLite and libb200match.so.
 #pragma once
+#include <array>
 #include <cstdint>
 #include <string>
 #include <utility>
@@ -45,6 +46,14 @@ struct SequentialMatchingOptions {
   int loop_detection_num_images_after_verification = 0;
   int loop_detection_max_num_features = -1;
   std::string vocab_tree_path;
+};
+
+// SpatialMatchingOptions (R:pipeline/match_features.h:154-174; defaults U:controllers/feature_matching.h)
+struct SpatialMatchingOptions {
+  bool is_gps = true;        // priors are (latitude, longitude, altitude) in degrees / metres
+  bool ignore_z = true;
+  int max_num_neighbors = 50;
+  double max_distance = 100.0;  // metres
 };
 
 // Defaults = what `pycolmap.RANSACOptions()` constructs (R:optim/bindings.h:10-18).
@@ -98,6 +107,15 @@ PairList SequentialPairs(int n_images, int overlap, bool quadratic_overlap);
 // the size of its distance matrix).  Returns parts + 1 offsets (in pairs), cut[0] = 0, cut[parts] = n.
 std::vector<int64_t> SplitPairsByCost(const PairList& pairs, const std::vector<int32_t>& n_feat, int parts);
 
+// SpatialFeatureMatcher::Run (row f4): every image with a location prior is paired with its nearest neighbours
+// among the images with priors -- the k = min(max_num_neighbors, #locations) nearest including itself, skipping
+// itself, stopping at max_distance.  GPS priors go through WGS84 ellipsoid -> ECEF first.  Indices are positions
+// in the image list; pairs are emitted per query image in order of increasing distance, duplicates across
+// queries are left to the controller (which skips pairs it has already seen).
+PairList SpatialPairs(const std::vector<std::array<double, 3>>& prior_t, const std::vector<bool>& has_prior,
+                      const SpatialMatchingOptions& options);
+std::array<double, 3> GpsToEcef(double lat_deg, double lon_deg, double alt);  // WGS84
+
 // ---- engine: one b2m_ctx per process and GPU -----------------------------------------------------
 class Engine {
  public:
@@ -126,6 +144,8 @@ void MatchExhaustive(const std::string& database_path, const SiftMatchingOptions
 void MatchSequential(const std::string& database_path, const SiftMatchingOptions& sift,
                      const SequentialMatchingOptions& matching, const TwoViewGeometryOptions& verification,
                      const std::vector<int>& devices);
+void MatchSpatial(const std::string& database_path, const SiftMatchingOptions& sift, const SpatialMatchingOptions& matching,
+                  const TwoViewGeometryOptions& verification, const std::vector<int>& devices);
 void VerifyMatches(const std::string& database_path, const std::string& pairs_path,
                    const TwoViewGeometryOptions& options);
 

@@ -94,6 +94,7 @@ struct Database::Stmt {
     if (st) sq::api().finalize(st);
   }
   void I64(int i, int64_t v) { Check(sq::api().bind_int64(st, i, v)); }
+  void F64(int i, double v) { Check(sq::api().bind_double(st, i, v)); }
   void Null(int i) { Check(sq::api().bind_null(st, i)); }
   void Text(int i, const std::string& s) {
     Check(sq::api().bind_text(st, i, s.c_str(), static_cast<int>(s.size()), sq::Transient()));
@@ -110,6 +111,7 @@ struct Database::Stmt {
     return false;
   }
   int64_t ColI64(int i) { return sq::api().column_int64(st, i); }
+  double ColF64(int i) { return sq::api().column_double(st, i); }
   bool ColIsNull(int i) { return sq::api().column_type(st, i) == sq::kTypeNull; }
   std::string ColText(int i) {
     const unsigned char* t = sq::api().column_text(st, i);
@@ -188,6 +190,25 @@ int64_t Database::AddImage(const std::string& name, int64_t camera_id) {
   s.Text(1, name); s.I64(2, camera_id);
   s.Step();
   return sq::api().last_insert_rowid(db_);
+}
+
+int64_t Database::AddImage(const std::string& name, int64_t camera_id, const std::array<double, 3>& t) {
+  Stmt s(this, "INSERT INTO images VALUES (NULL, ?, ?, NULL, NULL, NULL, NULL, ?, ?, ?)");
+  s.Text(1, name); s.I64(2, camera_id);
+  for (int k = 0; k < 3; ++k) s.F64(3 + k, t[k]);
+  s.Step();
+  return sq::api().last_insert_rowid(db_);
+}
+
+void Database::ReadLocationPriors(std::vector<std::array<double, 3>>* prior_t, std::vector<bool>* has_prior) {
+  prior_t->clear();
+  has_prior->clear();
+  Stmt s(this, "SELECT prior_tx, prior_ty, prior_tz FROM images ORDER BY image_id");
+  while (s.Step()) {
+    const bool ok = !s.ColIsNull(0) && !s.ColIsNull(1) && !s.ColIsNull(2);
+    prior_t->push_back({ok ? s.ColF64(0) : 0.0, ok ? s.ColF64(1) : 0.0, ok ? s.ColF64(2) : 0.0});
+    has_prior->push_back(ok);
+  }
 }
 
 void Database::WriteKeypoints(int64_t image_id, const float* data, int64_t rows, int64_t cols) {

@@ -89,6 +89,10 @@ class Database {
   int64_t AddCamera(int model, int64_t width, int64_t height, const std::vector<double>& params,
                     bool prior_focal_length);
   int64_t AddImage(const std::string& name, int64_t camera_id);
+  // with a location prior (prior_tx, prior_ty, prior_tz): GPS (latitude, longitude, altitude) or Cartesian
+  int64_t AddImage(const std::string& name, int64_t camera_id, const std::array<double, 3>& prior_t);
+  // location prior of every image, in ReadAllImages order; has_prior[i] == false where the columns are NULL
+  void ReadLocationPriors(std::vector<std::array<double, 3>>* prior_t, std::vector<bool>* has_prior);
   void WriteKeypoints(int64_t image_id, const float* data, int64_t rows, int64_t cols);
   void WriteDescriptors(int64_t image_id, const uint8_t* data, int64_t rows, int64_t cols);
 

@@ -40,6 +40,7 @@ Api load() {
   bind(lib, "sqlite3_bind_blob64", a.bind_blob64);
   bind(lib, "sqlite3_bind_text", a.bind_text);
   bind(lib, "sqlite3_column_int64", a.column_int64);
+  bind(lib, "sqlite3_column_double", a.column_double);
   bind(lib, "sqlite3_column_blob", a.column_blob);
   bind(lib, "sqlite3_column_bytes", a.column_bytes);
   bind(lib, "sqlite3_column_text", a.column_text);

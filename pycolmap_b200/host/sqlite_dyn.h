@@ -38,6 +38,7 @@ struct Api {
   int (*bind_blob64)(sqlite3_stmt*, int, const void*, uint64_t, Destructor);
   int (*bind_text)(sqlite3_stmt*, int, const char*, int, Destructor);
   int64_t (*column_int64)(sqlite3_stmt*, int);
+  double (*column_double)(sqlite3_stmt*, int);
   const void* (*column_blob)(sqlite3_stmt*, int);
   int (*column_bytes)(sqlite3_stmt*, int);
   const unsigned char* (*column_text)(sqlite3_stmt*, int);

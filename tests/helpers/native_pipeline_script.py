@@ -192,6 +192,31 @@ try:
 except ValueError as e:
     assert "keypoints.rows == descriptors.rows" in str(e)
 
+# ---- match_spatial: images on a line 30 m apart (Cartesian priors), 2 nearest neighbours within 70 m ---------------
+sp_db = os.path.join(tmp, "spatial.db")
+with nat.Database(sp_db) as db:
+    cid = db.add_camera(0, 1600, 1200, [1200.0, 800.0, 600.0], True)
+    db.begin()
+    sp_ids = []
+    for i in range(n_img):
+        prior = None if i == 4 else [30.0 * i, 0.0, 5.0 * i]            # image 4 has no prior: never paired
+        iid = db.add_image(f"frame{i:04d}.png", cid, prior)
+        kp = np.zeros((n_feat, 2), np.float32)
+        kp[:] = scene["kpts"][i].numpy()
+        db.write_keypoints(iid, kp)
+        db.write_descriptors(iid, descs[i])
+        sp_ids.append(iid)
+    db.commit()
+opts = {"is_gps": False, "max_num_neighbors": 3, "max_distance": 70.0}
+nat.match_spatial(sp_db, matching_options=opts)
+prior = np.array([[30.0 * i, 0.0, 5.0 * i] for i in range(n_img)])
+want_pairs = {(min(a, b), max(a, b)) for a, b in R.spatial_pairs(prior, [i != 4 for i in range(n_img)], **dict(nat.SpatialMatchingOptions(opts).todict()))}
+assert want_pairs and all(4 not in p and abs(p[0] - p[1]) <= 2 for p in want_pairs)
+con = sqlite3.connect(sp_db)
+stored = {tuple(int(x) for x in nat.pair_id_to_image_pair(r[0])) for r in con.execute("SELECT pair_id FROM matches")}
+con.close()
+assert stored == {(sp_ids[a], sp_ids[b]) for a, b in want_pairs}
+
 # ---- multiple_models in the pipelines: verified pairs are re-estimated through the estimator entry point ------------
 m_db = os.path.join(tmp, "multi.db")
 make_db(m_db)

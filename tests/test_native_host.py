@@ -331,3 +331,29 @@ def test_database_reference_surface(tmp_path):
         db.write_matches(iid, iid + 1, np.array([[0, 1]], np.uint32))
         del tx
         assert db.exists_matches(iid, iid + 1)
+
+
+def test_spatial_pairs_match_oracle():
+    """match_spatial's pair generator (R:pipeline/match_features.h:154-174, 237-244): GPS priors through WGS84 -> ECEF,
+    k nearest located images per query, distance cut-off; against the oracle restatement."""
+    from pycolmap_b200 import _core
+    assert nat.SpatialMatchingOptions().todict() == dict(is_gps=True, ignore_z=True, max_num_neighbors=50, max_distance=100.0)
+    ecef = R.gps_to_ecef(np.array([0.0, 90.0, 47.3769]), np.array([0.0, 0.0, 8.5417]), np.array([0.0, 0.0, 408.0]))
+    assert np.allclose(ecef[0], [6378137.0, 0, 0]) and np.allclose(ecef[1], [0, 0, 6356752.314245], atol=1e-3)
+    assert np.allclose(ecef[2], [4278990.0, 642680.0, 4670540.0], atol=300.0)          # Zurich, to a few hundred metres
+    rng = np.random.default_rng(9)
+    n = 60
+    # a ~400 m x 400 m patch around Zurich: 1e-3 deg of latitude is ~111 m
+    gps = np.c_[47.3769 + rng.uniform(-2e-3, 2e-3, n), 8.5417 + rng.uniform(-3e-3, 3e-3, n), rng.uniform(400, 450, n)]
+    has = rng.random(n) < 0.85
+    for kw in (dict(), dict(max_num_neighbors=5), dict(max_distance=40.0), dict(ignore_z=False, max_num_neighbors=8),
+               dict(is_gps=False, max_distance=2e-3, max_num_neighbors=6), dict(max_num_neighbors=1)):
+        o = nat.SpatialMatchingOptions(**kw)
+        got = _core.spatial_pairs(gps, has.tolist(), o)
+        want = np.array(R.spatial_pairs(gps, has, **o.todict()), np.int32).reshape(-1, 2)
+        assert np.array_equal(got, want), kw
+        assert all(has[a] and has[b] and a != b for a, b in got)
+    assert len(_core.spatial_pairs(gps, has.tolist(), nat.SpatialMatchingOptions(max_num_neighbors=1))) == 0   # only itself
+    assert len(_core.spatial_pairs(gps, [False] * n, nat.SpatialMatchingOptions())) == 0
+    with pytest.raises(ValueError, match="vocabulary tree"):
+        nat.match_vocabtree("whatever.db")

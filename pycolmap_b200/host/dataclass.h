@@ -105,6 +105,17 @@ class OptionsClass : public py::class_<T> {
   }
   OptionsClass& Finish() {
     py::object cls = *this;
+    {  // "<doc> (<type>, default: <value>)" on every field, like the reference's option classes (R:helpers.h:217-241)
+      py::object defaults = cls();
+      for (const std::string& name : FieldNames<T>()) {
+        py::object member = defaults.attr(name.c_str());
+        py::object prop = cls.attr(name.c_str());
+        py::object old = prop.attr("__doc__");
+        const std::string text = old.is_none() ? std::string() : py::str(old).cast<std::string>();
+        const std::string value = py::hasattr(member, "summary") ? TypeNameOf(member) + "()" : py::str(member).cast<std::string>();
+        prop.attr("__doc__") = py::str(text + (text.empty() ? "" : " ") + "(" + TypeNameOf(member) + ", default: " + value + ")");
+      }
+    }
     this->def(py::init([cls](const py::dict& d) {
                 py::object self = cls();
                 MergeDict<T>(self, d);

@@ -357,3 +357,12 @@ def test_spatial_pairs_match_oracle():
     assert len(_core.spatial_pairs(gps, [False] * n, nat.SpatialMatchingOptions())) == 0
     with pytest.raises(ValueError, match="vocabulary tree"):
         nat.match_vocabtree("whatever.db")
+
+
+def test_option_docstrings_carry_type_and_default():
+    """R:helpers.h:217-241: every option field documents "(type, default: value)"."""
+    assert nat.SiftMatchingOptions.max_ratio.__doc__.endswith("(float, default: 0.8)")
+    assert "Maximum distance ratio" in nat.SiftMatchingOptions.max_ratio.__doc__
+    assert nat.ExhaustiveMatchingOptions.block_size.__doc__ == "(int, default: 50)"
+    assert nat.TwoViewGeometryOptions.detect_watermark.__doc__ == "(bool, default: True)"
+    assert nat.TwoViewGeometryOptions.ransac.__doc__ == "(RANSACOptions, default: RANSACOptions())"

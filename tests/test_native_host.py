@@ -10,7 +10,9 @@ import numpy as np
 import pytest
 
 import pycolmap_b200 as pb
-import pycolmap_b200.native as nat
+from helpers.native_import import load_native
+
+nat = load_native()
 from oracle import ransac as R
 from pycolmap_b200.database import Database as PyDatabase
 

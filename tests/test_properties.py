@@ -6,7 +6,9 @@ import numpy as np
 from hypothesis import given, settings, strategies as st
 
 import oracle
-import pycolmap_b200.native as nat
+from helpers.native_import import load_native
+
+nat = load_native()
 from oracle import ransac as R
 
 LUT = oracle.acos_lut()

@@ -11,7 +11,9 @@ import pytest
 
 import oracle
 import pycolmap_b200 as pb
-import pycolmap_b200.native as nat
+from helpers.native_import import load_native
+
+nat = load_native()
 from helpers import scenes
 from oracle import ransac as R
 from pycolmap_b200 import synthetic as syn

@@ -305,12 +305,15 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     // (launch_k1_filter_skip).  The first cross-check batch of a context is computed both ways and the
     // match lists compared on the device; on any difference the context stays on the two-direction launch.
     const bool skip_capable = !ctx->exact_k1 && n_dirs == 2;
-    if (skip_capable && ctx->k1_dir1_mode == B2M_K1_DIR1_UNTESTED) {
+    // One-time comparison of the split schedule against the two-direction launch on this batch (returns a B2M code;
+    // leaves ctx->k1_dir1_mode decided unless the batch had no match at all).  The batch itself is redone afterwards.
+    auto k1_selftest = [&]() -> int {
       uint2* t_arena = nullptr;
       int64_t* t_off = nullptr;
       int32_t *t_cnt = nullptr, *t_flag = nullptr;
       auto drop = [&]() {
         cudaFree(t_arena); cudaFree(t_off); cudaFree(t_cnt); cudaFree(t_flag);
+        t_arena = nullptr; t_off = nullptr; t_cnt = nullptr; t_flag = nullptr;
       };
       const size_t arena_matches = static_cast<size_t>(W.batch) * W.mstride;
       if (cudaMalloc(&t_arena, sizeof(uint2) * arena_matches) != cudaSuccess ||
@@ -319,49 +322,49 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
         drop();
         cudaGetLastError();
         ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_NOMEM;  // no room for the comparison: stay on the validated launch
-      } else {
-        int32_t h_flag = -1;
-        CompactParams ct = cp;  // the skip path's match lists go to the temporary arena
-        ct.arena = t_arena;
-        ct.pair_off = t_off;
-        ct.pair_cnt = t_cnt;
-        ct.kpts = nullptr;
-        ct.pts = nullptr;
-        cudaError_t e = launch_k1_filter_skip(S.tmap, mp, S.d_desc, nb, max_strips, ctx->num_sms, W.d_pairs_dir1,
-                                              S.n_images, st, nullptr);
-        if (e == cudaSuccess) e = launch_crosscheck_compact(ct, nb, st);
-        if (e != cudaSuccess) {
-          // the split schedule could not even be launched (a non-sticky launch error): stay on the validated
-          // launch instead of failing the call; a sticky error resurfaces at the next CUDA call anyway
-          cudaGetLastError();
-          drop();
-          ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
-          t_arena = nullptr; t_off = nullptr; t_cnt = nullptr; t_flag = nullptr;
-          CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
-          goto k1_selftest_done;
-        }
-        e = cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st);
-        if (e == cudaSuccess)
-          e = launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st, nullptr);
-        if (e == cudaSuccess) e = launch_crosscheck_compact(cp, nb, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(t_flag, 0, sizeof(int32_t), st);
-        if (e == cudaSuccess)
-          e = launch_compare_matches(t_arena, t_off, t_cnt, W.d_arena[s], W.d_pair_off[s], W.d_pair_cnt[s], nb, t_flag, st);
-        unsigned long long h_total = 0;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, t_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess)
-          e = cudaMemcpyAsync(&h_total, W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        drop();
-        if (e != cudaSuccess) CU_TRY_R(e);
-        // a batch without a single match compares nothing: stay untested (and on the two-direction launch)
-        if (h_flag != 0) ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
-        else if (h_total > 0) ctx->k1_dir1_mode = B2M_K1_DIR1_SKIP;
-        ctx->stats.kernel_launches += 8;
-        CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));  // the batch is redone below
+        return B2M_OK;
       }
-    }
-  k1_selftest_done:
+      CompactParams ct = cp;  // the split schedule's match lists go to the temporary arena
+      ct.arena = t_arena;
+      ct.pair_off = t_off;
+      ct.pair_cnt = t_cnt;
+      ct.kpts = nullptr;
+      ct.pts = nullptr;
+      cudaError_t e = launch_k1_filter_skip(S.tmap, mp, S.d_desc, nb, max_strips, ctx->num_sms, W.d_pairs_dir1, S.n_images,
+                                            st, nullptr);
+      if (e == cudaSuccess) e = launch_crosscheck_compact(ct, nb, st);
+      if (e != cudaSuccess) {
+        // the split schedule could not even be launched (a non-sticky launch error): stay on the validated
+        // launch instead of failing the call; a sticky error resurfaces at the next CUDA call anyway
+        cudaGetLastError();
+        drop();
+        ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
+        CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
+        return B2M_OK;
+      }
+      int32_t h_flag = -1;
+      unsigned long long h_total = 0;
+      e = cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st);
+      if (e == cudaSuccess) e = launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st, nullptr);
+      if (e == cudaSuccess) e = launch_crosscheck_compact(cp, nb, st);
+      if (e == cudaSuccess) e = cudaMemsetAsync(t_flag, 0, sizeof(int32_t), st);
+      if (e == cudaSuccess)
+        e = launch_compare_matches(t_arena, t_off, t_cnt, W.d_arena[s], W.d_pair_off[s], W.d_pair_cnt[s], nb, t_flag, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, t_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&h_total, W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      drop();
+      if (e != cudaSuccess) CU_TRY_R(e);
+      // a batch without a single match compares nothing: stay untested (and on the two-direction launch)
+      if (h_flag != 0) ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
+      else if (h_total > 0) ctx->k1_dir1_mode = B2M_K1_DIR1_SKIP;
+      ctx->stats.kernel_launches += 8;
+      CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
+      return B2M_OK;
+    };
+    if (skip_capable && ctx->k1_dir1_mode == B2M_K1_DIR1_UNTESTED)
+      if (int rc = k1_selftest()) return rc;  // `res` was released by the failing step
     const bool use_skip = skip_capable && (ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP || ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP_FORCED);
     CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
     if (ctx->exact_k1) {

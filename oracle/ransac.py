@@ -513,16 +513,30 @@ def detect_watermark(cam1, pts1, cam2, pts2, num_inliers, mask, opt, rng):
     sel = border(a, cam1, d1) & border(b, cam2, d2)
     if sel.sum() / float(num_inliers) < opt.watermark_min_inlier_ratio:
         return False
+    # the translation model is fitted to ALL inlier points (upstream builds inlier_points1/2 from the whole
+    # mask; the border test above only gates the attempt)
     ro = opt.ransac.copy(min_inlier_ratio=opt.watermark_min_inlier_ratio)
-    rep = loransac(Translation2D, Translation2D, a[sel], b[sel], ro, rng)
+    rep = loransac(Translation2D, Translation2D, a, b, ro, rng)
     inl_ratio = rep.num_inliers / float(num_inliers)
     return rep.success and inl_ratio >= opt.watermark_min_inlier_ratio
 
 
 def _decide(g, opt, repE, repF, repH, calibrated):
+    """Decision step of EstimateCalibratedTwoViewGeometry / EstimateUncalibratedTwoViewGeometry
+    (U:estimators/two_view_geometry.cc).  Returns (inlier mask, number of inliers) or (None, 0)."""
     nE = repE.num_inliers if calibrated else 0
     nF, nH = repF.num_inliers, repH.num_inliers
     mn = opt.min_num_inliers
+    if not calibrated:
+        # EstimateUncalibratedTwoViewGeometry: the configuration depends on nH / nF, but the inlier matches and
+        # the watermark test ALWAYS come from F's mask (also when the pair is PLANAR_OR_PANORAMIC)
+        if (not repF.success and not repH.success) or (nF < mn and nH < mn):
+            g.config = DEGENERATE
+            return None, 0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            H_F = np.float64(nH) / np.float64(nF)
+        g.config = PLANAR_OR_PANORAMIC if H_F > opt.max_H_inlier_ratio else UNCALIBRATED
+        return repF.inlier_mask, nF
     okE = calibrated and repE.success
     if (not okE and not repF.success and not repH.success) or (nE < mn and nF < mn and nH < mn):
         g.config = DEGENERATE
@@ -876,10 +890,14 @@ def sequential_pairs(image_ids, overlap=10, quadratic_overlap=True):
     ids = list(image_ids)
     n = len(ids)
     out = []
+    # COLMAP 3.9.1: image_idx2 = image_idx1 + i, i in [0, overlap): i = 0 is the self pair (dropped by the
+    # controller), so overlap - 1 linear neighbours; the quadratic partner sits inside the same in-range test
     for i1 in range(n):
         for k in range(overlap):
-            i2 = i1 + k + 1
-            if i2 < n:
+            i2 = i1 + k
+            if i2 >= n:
+                break
+            if i2 != i1:
                 out.append((ids[i1], ids[i2]))
             if quadratic_overlap:
                 i2q = i1 + (1 << k)

@@ -852,6 +852,15 @@ __global__ void __launch_bounds__(256) b2m_decide_kernel(const VerifyParams P) {
         if (okH && nH >= mn) {
           cfg = B2M_PLANAR_OR_PANORAMIC; kind = 2; num = nH;
         }
+      } else if (!calibrated) {
+        // EstimateUncalibratedTwoViewGeometry: PLANAR_OR_PANORAMIC vs UNCALIBRATED by nH / nF, but the inlier
+        // matches (and the watermark test) ALWAYS come from F's mask, also when F found nothing
+        if ((!okF && !okH) || (nF < mn && nH < mn)) {
+          cfg = B2M_DEGENERATE;
+        } else {
+          kind = 1; num = nF;
+          cfg = (static_cast<double>(nH) / nF > o.max_H_inlier_ratio) ? B2M_PLANAR_OR_PANORAMIC : B2M_UNCALIBRATED;
+        }
       } else if ((!okE && !okF && !okH) || (nE < mn && nF < mn && nH < mn)) {
         cfg = B2M_DEGENERATE;
       } else {
@@ -930,9 +939,10 @@ __global__ void __launch_bounds__(256) b2m_decide_kernel(const VerifyParams P) {
   // translation must explain >= watermark_min_inlier_ratio of all inliers.
   if (o.detect_watermark && num > 0 &&
       static_cast<double>(s_border) / num >= o.watermark_min_inlier_ratio) {
-    // LO-RANSAC<Translation, Translation> on the border inliers; with kMinNumSamples = 1 every
-    // border inlier is a hypothesis: evaluate them all (exhaustive instead of sampled), then refit
-    // on the inliers of the best (local optimisation), keeping the better of the two.
+    // LO-RANSAC<Translation, Translation> on ALL inlier points (upstream fits inlier_points1/2 of the whole
+    // mask; the border ratio only gates the attempt); with kMinNumSamples = 1 every inlier is a hypothesis:
+    // evaluate them all (exhaustive instead of sampled), then refit on the inliers of the best (local
+    // optimisation), keeping the better of the two.
     const double thr = o.ransac.max_error * o.ransac.max_error;
     __shared__ int s_best_cnt;
     __shared__ double s_best_t[2];
@@ -942,28 +952,22 @@ __global__ void __launch_bounds__(256) b2m_decide_kernel(const VerifyParams P) {
       s_best_key = 0ull;
     }
     __syncthreads();
-    const int nbp = s_border;
     // hypotheses: border inlier h -> t = p2 - p1; support counted over border inliers
     for (int h0 = 0; h0 < n; h0 += 256) {
       const int h = h0 + tid;
-      bool is_b = false;
+      bool is_h = false;
       double tx = 0, ty = 0;
       if (h < n && mask[h]) {
         const double4 p = P.pts[off + h];
-        const bool b1 = p.x < d1 || p.x > c1.width - d1 || p.y < d1 || p.y > c1.height - d1;
-        const bool b2 = p.z < d2 || p.z > c2.width - d2 || p.w < d2 || p.w > c2.height - d2;
-        is_b = b1 && b2;
+        is_h = true;
         tx = p.z - p.x;
         ty = p.w - p.y;
       }
-      if (is_b) {
+      if (is_h) {
         int c = 0;
         for (int i = 0; i < n; ++i) {
           if (!mask[i]) continue;
           const double4 q = P.pts[off + i];
-          const bool qb1 = q.x < d1 || q.x > c1.width - d1 || q.y < d1 || q.y > c1.height - d1;
-          const bool qb2 = q.z < d2 || q.z > c2.width - d2 || q.w < d2 || q.w > c2.height - d2;
-          if (!(qb1 && qb2)) continue;
           const double ex = q.z - (q.x + tx), ey = q.w - (q.y + ty);
           c += (ex * ex + ey * ey <= thr) ? 1 : 0;
         }
@@ -983,9 +987,6 @@ __global__ void __launch_bounds__(256) b2m_decide_kernel(const VerifyParams P) {
         for (int i = 0; i < n; ++i) {
           if (!mask[i]) continue;
           const double4 q = P.pts[off + i];
-          const bool qb1 = q.x < d1 || q.x > c1.width - d1 || q.y < d1 || q.y > c1.height - d1;
-          const bool qb2 = q.z < d2 || q.z > c2.width - d2 || q.w < d2 || q.w > c2.height - d2;
-          if (!(qb1 && qb2)) continue;
           const double ex = q.z - (q.x + tx), ey = q.w - (q.y + ty);
           if (ex * ex + ey * ey <= thr) {
             sx += q.z - q.x;
@@ -999,9 +1000,6 @@ __global__ void __launch_bounds__(256) b2m_decide_kernel(const VerifyParams P) {
         for (int i = 0; i < n; ++i) {
           if (!mask[i]) continue;
           const double4 q = P.pts[off + i];
-          const bool qb1 = q.x < d1 || q.x > c1.width - d1 || q.y < d1 || q.y > c1.height - d1;
-          const bool qb2 = q.z < d2 || q.z > c2.width - d2 || q.w < d2 || q.w > c2.height - d2;
-          if (!(qb1 && qb2)) continue;
           const double ex = q.z - (q.x + ntx), ey = q.w - (q.y + nty);
           c2n += (ex * ex + ey * ey <= thr) ? 1 : 0;
         }
@@ -1014,7 +1012,6 @@ __global__ void __launch_bounds__(256) b2m_decide_kernel(const VerifyParams P) {
         }
       }
       s_best_cnt = bc;
-      (void)nbp;
     }
     __syncthreads();
     if (s_best_cnt >= 1 && static_cast<double>(s_best_cnt) / num >= o.watermark_min_inlier_ratio) cfg = B2M_WATERMARK;

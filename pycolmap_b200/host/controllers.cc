@@ -154,9 +154,14 @@ PairList SequentialPairs(int n, int overlap, bool quadratic_overlap) {
       out.push_back(static_cast<int32_t>(i2));
     }
   };
+  // U:controllers/feature_matching.cc SequentialFeatureMatcher::RunSequentialMatching (COLMAP 3.9.1):
+  // image_idx2 = image_idx1 + i for i in [0, overlap) -- i = 0 is the self pair, which the controller drops, so
+  // there are overlap - 1 linear neighbours -- and image_idx1 + 2^i inside the same in-range test.
   for (int i1 = 0; i1 < n; ++i1) {
     for (int k = 0; k < overlap; ++k) {
-      emit(i1, static_cast<int64_t>(i1) + k + 1);
+      const int64_t i2 = static_cast<int64_t>(i1) + k;
+      if (i2 >= n) break;
+      if (i2 != i1) emit(i1, i2);
       if (quadratic_overlap) emit(i1, static_cast<int64_t>(i1) + (k < 40 ? (int64_t{1} << k) : int64_t{1} << 40));
     }
   }

@@ -157,9 +157,11 @@ def test_pair_generators():
     for n, bs in [(1, 50), (2, 1), (49, 50), (50, 50), (51, 50), (101, 50), (7, 2)]:
         pr = R.exhaustive_pairs(range(n), bs)
         assert len(pr) == n * (n - 1) // 2 == len({(min(a, b), max(a, b)) for a, b in pr})
-    assert len(R.sequential_pairs(range(10000), 20, False)) == 199790
+    # COLMAP 3.9.1: idx2 = idx1 + i, i in [0, overlap) -> overlap - 1 linear neighbours (i = 0 is the self pair)
+    assert len(R.sequential_pairs(range(10000), 20, False)) == 10000 * 19 - 19 * 20 // 2
     s = R.sequential_pairs(range(100), 3, True)
-    assert (0, 1) in s and (0, 2) in s and (0, 3) in s and (0, 4) in s and (0, 5) not in s
+    assert (0, 1) in s and (0, 2) in s and (0, 4) in s and (0, 3) not in s and (0, 5) not in s and (0, 0) not in s
+    assert R.sequential_pairs(range(5), 1, False) == []
 
 
 def _two_motion_scene(rng, na, nb, n_out):

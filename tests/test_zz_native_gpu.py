@@ -398,8 +398,6 @@ def test_multiple_models_estimator():
     c.set_images([syn.sift_like(rng, 64)] * 2, [np.zeros((64, 2), np.float32)] * 2, [scenes.CAM] * 2)
     with pytest.raises(ValueError, match="multiple_models"):
         c.match_pairs(np.array([(0, 1)], np.int32), nat.SiftMatchingOptions(), nat.TwoViewGeometryOptions(multiple_models=True))
-    with pytest.raises(ValueError, match="compute_relative_pose"):
-        c.match_pairs(np.array([(0, 1)], np.int32), nat.SiftMatchingOptions(), {"compute_relative_pose": True})
     c.close()
 
 

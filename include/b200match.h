@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B2M_ABI_VERSION 2   /* 2: b2m_camera carries 12 parameters (distortion models), batch estimator */
+#define B2M_ABI_VERSION 3   /* 2: b2m_camera carries 12 parameters, batch estimator; 3: multi-GPU entry points (NCCL) */
 
 /* error codes */
 #define B2M_OK 0
@@ -51,6 +51,9 @@ typedef struct b2m_device_cfg {
 } b2m_device_cfg;
 
 int b2m_abi_version(void);
+/* Number of visible sm_100 devices (what SiftMatchingOptions.gpu_index = "-1" expands to, R:pipeline/match_features.h:76-81);
+ * 0 without a driver or a suitable device. */
+int b2m_device_count(void);
 int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out);
 void b2m_destroy(b2m_ctx* ctx);
 /* Message of the last failing call on this context (ctx may be NULL for create failures). */
@@ -198,6 +201,49 @@ int64_t b2m_results_num_verified(const b2m_results* r);
 int b2m_results_get(const b2m_results* r, int64_t pair, b2m_pair_view* out);
 void b2m_results_free(b2m_results* r);
 
+/* ---- multi-GPU: image pairs shard across GPUs, ONE all-gather of the descriptor set ----- */
+
+/* Replaces upstream's "one matcher thread per entry of SiftMatchingOptions.gpu_index, every worker reads every image
+ * from the host-side FeatureMatcherCache" (U:controllers/feature_matching_utils.cc; gpu_index list:
+ * R:pipeline/match_features.h:76-81).  Here every GPU has one b2m_ctx -- in one process (a host thread per GPU, like
+ * upstream) or in one process per GPU (torchrun / MPI) -- uploads only ITS contiguous share of the images and a single
+ * NCCL all-gather over NVLink makes the whole set resident everywhere; pairs then shard freely, no further exchange.
+ * NCCL (libnccl.so.2) is bound at run time; without it these calls fail with B2M_ENODEV and nothing else changes. */
+#define B2M_COMM_ID_BYTES 128
+typedef struct b2m_comm_id {
+  uint8_t bytes[B2M_COMM_ID_BYTES];   /* ncclUniqueId */
+} b2m_comm_id;
+/* Rank 0 creates the id; the launcher's side channel (torchrun store, MPI_Bcast, a file) carries it to the other ranks. */
+int b2m_comm_get_unique_id(b2m_comm_id* out);
+/* Collective over all ranks: joins the communicator of `id` with this context's device as rank `rank` of `n_ranks`. */
+int b2m_comm_init_rank(b2m_ctx* ctx, int32_t n_ranks, int32_t rank, const b2m_comm_id* id);
+/* Single-process form: contexts on distinct devices of this process, rank = position in `ctxs`. */
+int b2m_comm_init_local(b2m_ctx* const* ctxs, int32_t n);
+int b2m_comm_destroy(b2m_ctx* ctx);
+/* The partition every rank must agree on: rank r owns the contiguous images [first, first + count) with
+ * ceil(n_images / n_ranks) images per rank (the last ranks may own fewer, or none). */
+void b2m_comm_image_range(int32_t n_images, int32_t n_ranks, int32_t rank, int32_t* first, int32_t* count);
+
+#define B2M_LOC_HOST 0
+#define B2M_LOC_DEVICE 1
+typedef struct b2m_image_shard {
+  uint32_t struct_size;
+  int32_t location;          /* B2M_LOC_HOST (pageable or pinned) / B2M_LOC_DEVICE (this context's device) */
+  int32_t first_image;       /* must equal b2m_comm_image_range(...) of this rank */
+  int32_t n_local;
+  int32_t has_keypoints;     /* the same on every rank (a rank without images has no pointer to tell by) */
+  int32_t reserved;
+  const void* desc_packed;   /* [sum of n_feat over the local images x 128] uint8, image after image */
+  const void* kpts_packed;   /* float32 (x, y) per feature, same order, or NULL for match-only */
+} b2m_image_shard;
+/* b2m_set_images for a context that joined a communicator: lays out the WHOLE set (n_feat and cams describe all
+ * images), copies the local shard into place, then one all-gather (ncclAllGather when the per-rank regions are
+ * equal, else one grouped ncclBroadcast per owner) fills in the other ranks' images.  Collective: every rank
+ * calls it with the same n_images / n_feat.  Without a communicator (or n_ranks == 1) it is b2m_set_images with a
+ * packed source.  b2m_stats.last_allgather_* describe the collective. */
+int b2m_set_images_sharded(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const b2m_camera* cams,
+                           const b2m_image_shard* mine);
+
 /* ---- estimators (callable without an image set) ------------------------------------ */
 
 /* Replaces EstimateTwoViewGeometry / EstimateCalibratedTwoViewGeometry
@@ -294,6 +340,12 @@ typedef struct b2m_stats {
   double last_k1_ms;          /* sum of K1 (GEMM + fused top-2) kernel durations of the last call */
   uint64_t last_k1_launches;  /* K1 passes (one per pair batch) of the last call */
   uint64_t k1_dir1_mode;      /* enum b2m_k1_dir1_mode: how the column direction of the cross-check is computed */
+  double last_allgather_ms;   /* device time of the all-gather of the last b2m_set_images_sharded (0 without a communicator) */
+  uint64_t last_allgather_bytes; /* bytes this rank RECEIVED in it (descriptors + keypoints of the other ranks' images) */
+  double last_upload_ms;      /* device time of the host -> device (or device -> device) copy of the local shard / set */
+  uint64_t verify_models_scored[3];   /* E / F / H: hypotheses + LO candidates scored against all matches since reset */
+  uint64_t verify_residuals[3];       /* E / F / H: residual evaluations (models scored x matches of the pair) since reset */
+  int32_t comm_size, comm_rank;       /* 1, 0 without a communicator */
 } b2m_stats;
 int b2m_get_stats(b2m_ctx* ctx, b2m_stats* out);
 int b2m_reset_stats(b2m_ctx* ctx);

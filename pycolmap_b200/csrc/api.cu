@@ -16,12 +16,14 @@
 
 using namespace b2m;
 
+namespace b2m {
+thread_local std::string g_noctx_err;
+}
+
 namespace {
 
-thread_local std::string g_create_err;
-
 int fail(b2m_ctx* ctx, int code, const std::string& msg) {
-  if (ctx) ctx->err = msg; else g_create_err = msg;
+  if (ctx) ctx->err = msg; else g_noctx_err = msg;
   return code;
 }
 
@@ -491,6 +493,20 @@ extern "C" {
 
 int b2m_abi_version(void) { return B2M_ABI_VERSION; }
 
+int b2m_device_count(void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int n = 0;
+  for (int d = 0; d < ndev; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) n = d + 1;
+  }
+  return n;
+}
+
 void b2m_sift_opts_default(b2m_sift_opts* o) {
   if (!o) return;
   memset(o, 0, sizeof(*o));
@@ -605,6 +621,8 @@ void b2m_destroy(b2m_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  comm_release(ctx);
+  if (ctx->d_verify_counters) cudaFree(ctx->d_verify_counters);
   ctx->images.release();
   ctx->ws.release();
   verify_release(ctx);
@@ -623,7 +641,7 @@ void b2m_destroy(b2m_ctx* ctx) {
   delete ctx;
 }
 
-const char* b2m_last_error(const b2m_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+const char* b2m_last_error(const b2m_ctx* ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
 
 int b2m_request_stop(b2m_ctx* ctx) {
   if (!ctx) return B2M_EINVAL;
@@ -696,6 +714,87 @@ int b2m_set_images_device(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat,
     S.cams.assign(cams, cams + n_images);
   }
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+
+int b2m_set_images_sharded(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const b2m_camera* cams,
+                           const b2m_image_shard* mine) {
+  if (!ctx) return B2M_EINVAL;
+  if (n_images < 0 || (n_images > 0 && !n_feat) || !mine || mine->struct_size != sizeof(b2m_image_shard))
+    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: n_images >= 0 && n_feat && shard (struct_size)");
+  int32_t first = 0, count = 0;
+  b2m_comm_image_range(n_images, ctx->comm_size, ctx->comm_rank, &first, &count);
+  if (mine->first_image != first || mine->n_local != count)
+    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: the shard is this rank's b2m_comm_image_range");
+  if (count > 0 && !mine->desc_packed) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: desc_packed != NULL");
+  if (count > 0 && mine->has_keypoints && !mine->kpts_packed)
+    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: kpts_packed != NULL");
+  if (mine->location != B2M_LOC_HOST && mine->location != B2M_LOC_DEVICE)
+    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: location is B2M_LOC_HOST or B2M_LOC_DEVICE");
+  if (cams)
+    for (int i = 0; i < n_images; ++i)
+      if (const char* why = camera_problem(cams[i])) return fail(ctx, B2M_EINVAL, why);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ImageSet& S = ctx->images;
+  const bool kp = mine->has_keypoints != 0;
+  if (int rc = layout_images(ctx, S, n_images, n_feat, kp)) return rc;
+  cudaStream_t st = ctx->stream;
+  const cudaMemcpyKind kind = mine->location == B2M_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_t0, st));
+  {  // the local shard -> its rows; runs of images without padding go in one copy
+    const uint8_t* src = static_cast<const uint8_t*>(mine->desc_packed);
+    const float2* ksrc = static_cast<const float2*>(mine->kpts_packed);
+    int64_t src_row = 0;
+    int i = first;
+    while (i < first + count) {
+      int j = i;
+      int64_t run = 0;
+      while (j < first + count && n_feat[j] % kRowPad == 0) run += n_feat[j++];
+      if (j == i) {
+        run = n_feat[i];
+        j = i + 1;
+      }
+      if (run > 0) {
+        CU_TRY(ctx, cudaMemcpyAsync(S.d_desc + static_cast<size_t>(S.row0[i]) * 128, src + src_row * 128,
+                                    static_cast<size_t>(run) * 128, kind, st));
+        if (kp)
+          CU_TRY(ctx, cudaMemcpyAsync(S.d_kpts + S.row0[i], ksrc + src_row, static_cast<size_t>(run) * sizeof(float2), kind, st));
+      }
+      src_row += run;
+      i = j;
+    }
+  }
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_k1a[0], st));
+  uint64_t recv_bytes = 0;
+  if (ctx->comm && ctx->comm_size > 1) {
+    // ONE all-gather of the descriptor rows (and one of the keypoint rows): rank r owns the padded rows of its images
+    const int nr = ctx->comm_size;
+    std::vector<size_t> off(nr), len(nr);
+    auto row_at = [&](int img) { return img < n_images ? static_cast<int64_t>(S.row0[img]) : S.total_rows; };
+    for (int r = 0; r < nr; ++r) {
+      int32_t f = 0, c = 0;
+      b2m_comm_image_range(n_images, nr, r, &f, &c);
+      off[r] = static_cast<size_t>(row_at(f));
+      len[r] = static_cast<size_t>(row_at(f + c) - row_at(f));
+      if (r != ctx->comm_rank) recv_bytes += len[r] * (128 + (kp ? sizeof(float2) : 0));
+    }
+    std::vector<size_t> o(nr), l(nr);
+    for (int r = 0; r < nr; ++r) { o[r] = off[r] * 128; l[r] = len[r] * 128; }
+    if (int rc = comm_allgather_regions(ctx, S.d_desc, o, l, st)) return rc;
+    if (kp) {
+      for (int r = 0; r < nr; ++r) { o[r] = off[r] * sizeof(float2); l[r] = len[r] * sizeof(float2); }
+      if (int rc = comm_allgather_regions(ctx, reinterpret_cast<uint8_t*>(S.d_kpts), o, l, st)) return rc;
+    }
+  }
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_k1b[0], st));
+  if (cams) S.cams.assign(cams, cams + n_images);
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  float up = 0.f, ag = 0.f;
+  cudaEventElapsedTime(&up, ctx->ev_t0, ctx->ev_k1a[0]);
+  cudaEventElapsedTime(&ag, ctx->ev_k1a[0], ctx->ev_k1b[0]);
+  ctx->stats.last_upload_ms = up;
+  ctx->stats.last_allgather_ms = (ctx->comm && ctx->comm_size > 1) ? ag : 0.0;
+  ctx->stats.last_allgather_bytes = recv_bytes;
   return B2M_OK;
 }
 
@@ -787,12 +886,27 @@ int b2m_get_stats(b2m_ctx* ctx, b2m_stats* out) {
   if (!ctx || !out) return B2M_EINVAL;
   *out = ctx->stats;
   out->struct_size = sizeof(b2m_stats);
+  out->comm_size = ctx->comm_size;
+  out->comm_rank = ctx->comm_rank;
+  if (ctx->d_verify_counters) {  // kernel-side counters of the verifier (models scored, residual evaluations per kind)
+    unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+    cudaSetDevice(ctx->device);
+    if (cudaMemcpy(h, ctx->d_verify_counters, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+      for (int k = 0; k < 3; ++k) {
+        out->verify_models_scored[k] = h[k];
+        out->verify_residuals[k] = h[3 + k];
+      }
+  }
   return B2M_OK;
 }
 int b2m_reset_stats(b2m_ctx* ctx) {
   if (!ctx) return B2M_EINVAL;
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   ctx->stats.struct_size = sizeof(b2m_stats);
+  if (ctx->d_verify_counters) {
+    cudaSetDevice(ctx->device);
+    cudaMemset(ctx->d_verify_counters, 0, sizeof(unsigned long long) * 6);
+  }
   ctx->stats.k1_dir1_mode = static_cast<uint64_t>(ctx->k1_dir1_mode);  // a property of the context, not a counter
   return B2M_OK;
 }

@@ -65,6 +65,17 @@ struct Workspace {
   void release();
 };
 
+// message of a failing call that has no context to carry it (b2m_create, b2m_comm_get_unique_id)
+extern thread_local std::string g_noctx_err;
+
+}  // namespace b2m
+
+struct b2m_ctx;
+namespace b2m {
+// comm.cu
+void comm_release(b2m_ctx* ctx);
+int comm_allgather_regions(b2m_ctx* ctx, uint8_t* base, const std::vector<size_t>& off, const std::vector<size_t>& len,
+                           cudaStream_t st);
 }  // namespace b2m
 
 struct b2m_ctx {
@@ -90,6 +101,10 @@ struct b2m_ctx {
   uint64_t hint_matches = 0, hint_inliers = 0;  // result sizes of the previous b2m_match_pairs (reserve hints)
   b2m_stats stats{};
   void* verify_state = nullptr;  // b2m::VerifyState (verify.cu)
+  // multi-GPU (comm.cu): the NCCL communicator this context joined, or nullptr
+  void* comm = nullptr;          // ncclComm_t
+  int comm_size = 1, comm_rank = 0;
+  unsigned long long* d_verify_counters = nullptr;  // [6]: models scored / residual evaluations per kind (verify.cu)
 };
 
 struct b2m_results {

@@ -70,6 +70,7 @@ struct VerifyParams {
   int32_t single_kind;        // >= 0: only this kind runs (stand-alone estimator API), no camera model
   int32_t force_calibrated;   // stand-alone: -1 use camera flags
   unsigned long long* prof;   // optional [3][8] cycle counters (B2M_PROF=1), else nullptr
+  unsigned long long* counters;  // [6] models scored / residual evaluations per kind (b2m_stats), or nullptr
   // guided matching hand-over (written by the decision kernel when guided_min_inliers >= 0)
   int32_t* guided_kind;       // [nb] -1 / 0 (F) / 1 (H)
   float* guided_model;        // [nb][9]
@@ -232,6 +233,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
   __syncthreads();
 
   int trials = 0;
+  unsigned long long n_scored = 0;  // models whose residuals were evaluated over all n matches (thread 0 keeps the tally)
   double mdl[T::kMaxModels * 9];
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long prof_t = clock64();
@@ -277,6 +279,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       total_models += v;
     }
     const float thr_f = static_cast<float>(thr);
+    n_scored += total_models;
     for (int chunk0 = 0; chunk0 < total_models; chunk0 += kChunkModels) {
       const int n_chunk = min(kChunkModels, total_models - chunk0);
       for (int m = 0; m < nm; ++m) {
@@ -400,6 +403,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
         __syncthreads();
       }
       B2M_TICK(2);
+      n_scored += 1;  // exact fp64 support of the new best
       // ---- phase 3: recursive local optimisation on the inliers of the current best
       if (sh.best_cnt > T::kMin && sh.best_cnt >= T::kLocalMin) {
         for (int lt = 0; lt < kMaxLocalTrials; ++lt) {
@@ -481,6 +485,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
           __syncthreads();
           B2M_TICK(4);
           const int nc = sh.n_cand;
+          n_scored += nc + (KIND != 0 ? 2 : 1);  // LO candidates + the inlier passes (moments, normal equations)
           for (int m = warp; m < nc; m += kRansacThreads / 32) {
             double C[9];
             for (int k = 0; k < 9; ++k) C[k] = sh.cand_models[m * 9 + k];
@@ -526,6 +531,10 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
     mask[i] = (ok && residual<KIND>(M, x1, y1, x2, y2) <= thr) ? 1 : 0;
   }
   B2M_TICK(6);
+  if (P.counters && tid == 0) {
+    atomicAdd(P.counters + KIND, n_scored + 1);
+    atomicAdd(P.counters + 3 + KIND, (n_scored + 1) * static_cast<unsigned long long>(n));
+  }
   if (P.prof && tid == 0)
     for (int k = 0; k < 8; ++k) atomicAdd(P.prof + KIND * 8 + k, static_cast<unsigned long long>(prof_acc[k]));
   if (tid == 0) {
@@ -1128,6 +1137,18 @@ VerifyState* vstate(b2m_ctx* ctx) {
     }                                                                                       \
   } while (0)
 
+unsigned long long* verify_counters(b2m_ctx* ctx) {
+  if (!ctx->d_verify_counters) {
+    if (cudaMalloc(&ctx->d_verify_counters, sizeof(unsigned long long) * 6) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->d_verify_counters = nullptr;
+      return nullptr;
+    }
+    cudaMemset(ctx->d_verify_counters, 0, sizeof(unsigned long long) * 6);
+  }
+  return ctx->d_verify_counters;
+}
+
 DevCamera to_dev(const b2m_camera& c) {
   DevCamera d{};
   int extra;
@@ -1288,6 +1309,7 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
     cudaMemset(V->d_prof, 0, sizeof(unsigned long long) * 24);
   }
   P.prof = V->d_prof;
+  P.counters = verify_counters(ctx);
   if (!V->rs.side[0]) {
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[0], cudaStreamNonBlocking));
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[1], cudaStreamNonBlocking));
@@ -1594,6 +1616,7 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   P.opt = opt;
   P.seed = ctx->seed;
   P.single_kind = single_kind;
+  P.counters = verify_counters(ctx);
   if (single_kind >= 0) {
     V_TRY(ctx, launch_ransac(P, 1, st));
   } else {
@@ -1884,6 +1907,7 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     P.opt = *opts;
     P.seed = ctx->seed;
     P.single_kind = -1;
+    P.counters = verify_counters(ctx);
     const double4* pts_E = nullptr;
     if (int rc = undistort_for_E(ctx, G, P, full_cams.data(), 2 * nb, nb, cap, st, &pts_E)) return rc;
     V_TRY(ctx, launch_ransac(P, nb, st, nullptr, pts_E));

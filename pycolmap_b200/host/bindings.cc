@@ -397,6 +397,12 @@ PYBIND11_MODULE(_core, m) {
 
   py::class_<Rotation3d>(m, "Rotation3d")
       .def(py::init<>())
+      .def(py::init([](const std::array<double, 4>& xyzw) {   // Eigen coefficient order, like the reference
+             Rotation3d r;
+             r.wxyz = {xyzw[3], xyzw[0], xyzw[1], xyzw[2]};
+             return r;
+           }),
+           "xyzw"_a)
       .def_property_readonly("quat", [](const Rotation3d& r) {   // (x, y, z, w) like the reference's Eigen coefficients
         py::array_t<double> a(4);
         double* p = a.mutable_data();
@@ -406,6 +412,10 @@ PYBIND11_MODULE(_core, m) {
       .def("matrix", [](const Rotation3d& r) { return MatToNumpy(QuatToRotation(r.wxyz).data()); });
   py::class_<Rigid3d>(m, "Rigid3d")
       .def(py::init<>())
+      .def(py::init([](const Rotation3d& rotation, const std::array<double, 3>& translation) {
+             return Rigid3d{rotation, translation};
+           }),
+           "rotation"_a, "translation"_a)
       .def_readonly("rotation", &Rigid3d::rotation)
       .def_property_readonly("translation", [](const Rigid3d& g) {
         py::array_t<double> a(3);
@@ -730,6 +740,13 @@ PYBIND11_MODULE(_core, m) {
           return out;
         },
         "n_images"_a, "block_size"_a);
+  m.def("comm_image_range",
+        [](int n_images, int n_ranks, int rank) {
+          int32_t first = 0, count = 0;
+          b2m_comm_image_range(n_images, n_ranks, rank, &first, &count);
+          return py::make_tuple(first, count);
+        },
+        "n_images"_a, "n_ranks"_a, "rank"_a, "The contiguous image range rank `rank` uploads (b2m_comm_image_range)");
   m.def("parse_gpu_indices", &ParseGpuIndices, "gpu_index"_a);
   m.def("split_pairs_by_cost",
         [](const ArrI32& pairs, const std::vector<int32_t>& n_feat, int parts) {
@@ -1008,6 +1025,80 @@ PYBIND11_MODULE(_core, m) {
                                                      cams.is_none() ? nullptr : cc.data()));
            },
            "n_feat"_a, "dev_desc_ptr"_a, "dev_kpts_ptr"_a = 0, "cameras"_a = py::none())
+      // ---- multi-GPU (include/b200match.h: b2m_comm_*, b2m_set_images_sharded) ----
+      .def_static("comm_unique_id",
+                  []() {
+                    b2m_comm_id id;
+                    ThrowOnError(nullptr, b2m_comm_get_unique_id(&id));
+                    return py::bytes(reinterpret_cast<const char*>(id.bytes), B2M_COMM_ID_BYTES);
+                  },
+                  "Rank 0: a fresh communicator id (128 bytes) to hand to every rank through the launcher's side channel")
+      .def("comm_init_rank",
+           [](CoreContext& c, int n_ranks, int rank, const py::bytes& id) {
+             const std::string raw = id;
+             if (raw.size() != B2M_COMM_ID_BYTES) throw std::invalid_argument("[bindings.cc] Check Failed: id has 128 bytes");
+             b2m_comm_id cid;
+             memcpy(cid.bytes, raw.data(), B2M_COMM_ID_BYTES);
+             b2m_ctx* ctx = c.Handle();
+             int rc;
+             {
+               py::gil_scoped_release release;
+               rc = b2m_comm_init_rank(ctx, n_ranks, rank, &cid);
+             }
+             ThrowOnError(ctx, rc);
+           },
+           "n_ranks"_a, "rank"_a, "id"_a)
+      .def("comm_destroy", [](CoreContext& c) { ThrowOnError(c.Handle(), b2m_comm_destroy(c.Handle())); })
+      .def("set_images_sharded",
+           [](CoreContext& c, const ArrI32& n_feat, int first_image, int n_local, const py::object& desc_local,
+              const py::object& kpts_local, const py::object& cams, bool has_keypoints) {
+             // desc_local / kpts_local: numpy arrays (host: [rows x 128] uint8, [rows x 2] float32) or device pointers (int)
+             b2m_image_shard sh;
+             memset(&sh, 0, sizeof(sh));
+             sh.struct_size = sizeof(sh);
+             sh.first_image = first_image;
+             sh.n_local = n_local;
+             sh.has_keypoints = has_keypoints ? 1 : 0;
+             ArrU8 d;
+             ArrF32 k;
+             if (py::isinstance<py::int_>(desc_local)) {
+               sh.location = B2M_LOC_DEVICE;
+               sh.desc_packed = reinterpret_cast<const void*>(desc_local.cast<uint64_t>());
+               if (!kpts_local.is_none()) sh.kpts_packed = reinterpret_cast<const void*>(kpts_local.cast<uint64_t>());
+             } else {
+               sh.location = B2M_LOC_HOST;
+               int64_t rows = 0;
+               for (int i = first_image; i < first_image + n_local && i < n_feat.size(); ++i) rows += n_feat.data()[i];
+               if (!desc_local.is_none()) {
+                 d = ArrU8::ensure(desc_local);
+                 if (!d || d.size() != rows * 128)
+                   throw std::invalid_argument("[bindings.cc] Check Failed: local descriptors are (sum of local n_feat) x 128 uint8");
+                 sh.desc_packed = d.data();
+               }
+               if (!kpts_local.is_none()) {
+                 k = ArrF32::ensure(kpts_local);
+                 if (!k || k.size() != rows * 2)
+                   throw std::invalid_argument("[bindings.cc] Check Failed: local keypoints are (sum of local n_feat) x 2 float32");
+                 sh.kpts_packed = k.data();
+               }
+             }
+             std::vector<b2m_camera> cc;
+             if (!cams.is_none()) {
+               cc = CamerasFromPython(cams);
+               if (static_cast<py::ssize_t>(cc.size()) != n_feat.size())
+                 throw std::invalid_argument("[bindings.cc] Check Failed: one camera per image (all images, not only the local ones)");
+             }
+             b2m_ctx* ctx = c.Handle();
+             int rc;
+             {
+               py::gil_scoped_release release;
+               rc = b2m_set_images_sharded(ctx, static_cast<int32_t>(n_feat.size()), n_feat.data(),
+                                           cams.is_none() ? nullptr : cc.data(), &sh);
+             }
+             ThrowOnError(ctx, rc);
+           },
+           "n_feat"_a, "first_image"_a, "n_local"_a, "descriptors_local"_a, "keypoints_local"_a = py::none(),
+           "cameras"_a = py::none(), "has_keypoints"_a = false)
       .def("match_pair",
            [](CoreContext& c, const ArrU8& d1, const ArrU8& d2, const SiftMatchingOptions& options) {
              if (d1.size() % 128 || d2.size() % 128)
@@ -1059,7 +1150,15 @@ PYBIND11_MODULE(_core, m) {
                         "last_match_ms"_a = s.last_match_ms, "last_verify_ms"_a = s.last_verify_ms,
                         "last_total_ms"_a = s.last_total_ms, "last_k1_ms"_a = s.last_k1_ms,
                         "last_k1_launches"_a = s.last_k1_launches,
-                        "k1_dir1_mode"_a = s.k1_dir1_mode);
+                        "k1_dir1_mode"_a = s.k1_dir1_mode, "last_allgather_ms"_a = s.last_allgather_ms,
+                        "last_allgather_bytes"_a = s.last_allgather_bytes, "last_upload_ms"_a = s.last_upload_ms,
+                        "verify_models_scored"_a = py::make_tuple(s.verify_models_scored[0], s.verify_models_scored[1],
+                                                                  s.verify_models_scored[2]),
+                        "verify_residuals"_a = py::make_tuple(s.verify_residuals[0], s.verify_residuals[1],
+                                                              s.verify_residuals[2]),
+                        "comm_size"_a = s.comm_size, "comm_rank"_a = s.comm_rank);
+      })
+      .def("reset_stats", [](CoreContext& c) { ThrowOnError(c.Handle(), b2m_reset_stats(c.Handle()));
       });
 
   // test hook for the PyWait logic: blocks `seconds` on the worker thread like a long GPU call would

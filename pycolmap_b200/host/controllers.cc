@@ -92,7 +92,12 @@ std::vector<int> ParseGpuIndices(const std::string& gpu_index) {
     }
     if (used != item.size() || v < -1)
       throw std::invalid_argument("[controllers.cc] Check Failed: gpu_index is a comma-separated list of integers >= -1");
-    if (v == -1) v = 0;  // see the header: -1 selects device 0 here
+    if (v == -1) {  // upstream: "-1" = every visible GPU, one matcher each (U:feature/sift.cc CreateSiftFeatureMatcher path)
+      const int n = std::max(1, b2m_device_count());
+      for (int d = 0; d < n; ++d)
+        if (std::find(out.begin(), out.end(), d) == out.end()) out.push_back(d);
+      continue;
+    }
     if (std::find(out.begin(), out.end(), v) == out.end()) out.push_back(v);
   }
   if (out.empty()) out.push_back(0);
@@ -253,6 +258,17 @@ b2m_ctx* Engine::Get(int device) {
   return g_ctx[device];
 }
 
+bool Engine::EnsureLocalComm(const std::vector<b2m_ctx*>& ctxs) {
+  static std::vector<b2m_ctx*> current;   // the context list the live communicator spans
+  std::lock_guard<std::mutex> lock(g_engine_mutex);
+  if (ctxs.size() < 2) return false;
+  if (current == ctxs) return true;
+  current.clear();
+  if (b2m_comm_init_local(ctxs.data(), static_cast<int32_t>(ctxs.size())) != B2M_OK) return false;  // no NCCL: full uploads
+  current = ctxs;
+  return true;
+}
+
 void Engine::RequestStopAll() {
   for (int i = 0; i < kMaxDevices; ++i)
     if (g_ctx[i]) b2m_request_stop(g_ctx[i]);
@@ -278,63 +294,98 @@ struct LoadedSet {
   std::vector<int64_t> ids;
   std::vector<std::string> names;
   std::vector<int64_t> camera_ids;
+  std::vector<b2m_camera> cams;
+  // filled by UploadImageSet
   std::vector<int32_t> n_feat;
   std::vector<std::vector<float>> xy;   // keypoint positions per image (kept for the multiple_models re-estimation)
-  std::vector<b2m_camera> cams;
+  bool uploaded = false;
 };
 
-// FeatureMatcherCache: every image's descriptors, keypoint positions and camera go to the GPU once
-// (to every GPU of the gpu_index list: the set is small next to 180 GB and pairs then shard freely).
-LoadedSet LoadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, bool order_by_name) {
+// The image table without the blobs: ids, names, cameras.  verify_matches needs no more than this plus the
+// keypoints of the images its pairs name (upstream's FeatureMatcherCache reads descriptors lazily, only for pairs
+// that must be matched: a database of learned-feature matches has no descriptor rows at all).
+LoadedSet ReadImageTable(Database& db, bool order_by_name) {
   std::vector<ImageRow> images = db.ReadAllImages();
   if (order_by_name)
     std::stable_sort(images.begin(), images.end(), [](const ImageRow& a, const ImageRow& b) { return a.name < b.name; });
   LoadedSet L;
-  std::vector<DescriptorsBlob> desc(images.size());
-  std::vector<std::vector<float>> xy(images.size());
-  std::vector<b2m_camera> cams(images.size());
-  std::vector<int32_t> n_feat(images.size());
   std::unordered_map<int64_t, b2m_camera> cam_cache;
-  for (size_t i = 0; i < images.size(); ++i) {
-    const ImageRow& im = images[i];
+  for (const ImageRow& im : images) {
     L.ids.push_back(im.image_id);
     L.names.push_back(im.name);
     L.camera_ids.push_back(im.camera_id);
-    desc[i] = db.ReadDescriptors(im.image_id);
-    const KeypointsBlob kp = db.ReadKeypoints(im.image_id);
-    if (kp.rows != desc[i].rows)
-      throw std::invalid_argument("[controllers.cc] Check Failed: keypoints.rows == descriptors.rows");
-    xy[i].resize(static_cast<size_t>(kp.rows) * 2);
-    for (int64_t r = 0; r < kp.rows; ++r) {
-      xy[i][2 * r] = kp.data[r * kp.cols];
-      xy[i][2 * r + 1] = kp.data[r * kp.cols + 1];
-    }
     auto it = cam_cache.find(im.camera_id);
     if (it == cam_cache.end()) it = cam_cache.emplace(im.camera_id, ToAbi(db.ReadCamera(im.camera_id))).first;
-    cams[i] = it->second;
-    n_feat[i] = static_cast<int32_t>(desc[i].rows);
+    L.cams.push_back(it->second);
   }
-  std::vector<const uint8_t*> dptr(images.size());
-  std::vector<const float*> kptr(images.size());
-  for (size_t i = 0; i < images.size(); ++i) {
-    dptr[i] = desc[i].data.data();
-    kptr[i] = xy[i].data();
+  return L;
+}
+
+std::vector<float> KeypointPositions(Database& db, int64_t image_id) {
+  const KeypointsBlob kp = db.ReadKeypoints(image_id);
+  std::vector<float> xy(static_cast<size_t>(kp.rows) * 2);
+  for (int64_t r = 0; r < kp.rows; ++r) {
+    xy[2 * r] = kp.data[r * kp.cols];
+    xy[2 * r + 1] = kp.data[r * kp.cols + 1];
   }
+  return xy;
+}
+
+// FeatureMatcherCache: every image's descriptors, keypoint positions and camera go to the GPU(s) once.  With
+// several contexts that share a communicator (Engine::EnsureLocalComm) every GPU uploads only ITS contiguous share
+// of the images over PCIe and ONE all-gather over NVLink makes the set resident everywhere
+// (b2m_set_images_sharded); without NCCL every GPU uploads the whole set.
+void UploadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, LoadedSet* L) {
+  const size_t n = L->ids.size();
+  std::vector<DescriptorsBlob> desc(n);
+  L->xy.assign(n, {});
+  L->n_feat.assign(n, 0);
+  for (size_t i = 0; i < n; ++i) {
+    desc[i] = db.ReadDescriptors(L->ids[i]);
+    L->xy[i] = KeypointPositions(db, L->ids[i]);
+    if (static_cast<int64_t>(L->xy[i].size() / 2) != desc[i].rows)
+      throw std::invalid_argument("[controllers.cc] Check Failed: keypoints.rows == descriptors.rows");
+    L->n_feat[i] = static_cast<int32_t>(desc[i].rows);
+  }
+  const int32_t n_images = static_cast<int32_t>(n);
   std::vector<int> rc(ctxs.size(), B2M_OK);
+  const bool sharded = ctxs.size() > 1 && Engine::EnsureLocalComm(ctxs);
+  auto upload = [&](size_t d) {
+    if (!sharded) {
+      std::vector<const uint8_t*> dptr(n);
+      std::vector<const float*> kptr(n);
+      for (size_t i = 0; i < n; ++i) {
+        dptr[i] = desc[i].data.data();
+        kptr[i] = L->xy[i].data();
+      }
+      rc[d] = b2m_set_images(ctxs[d], n_images, L->n_feat.data(), dptr.data(), kptr.data(), L->cams.data());
+      return;
+    }
+    int32_t first = 0, count = 0;
+    b2m_comm_image_range(n_images, static_cast<int32_t>(ctxs.size()), static_cast<int32_t>(d), &first, &count);
+    std::vector<uint8_t> dpack;
+    std::vector<float> kpack;
+    for (int32_t i = first; i < first + count; ++i) {
+      dpack.insert(dpack.end(), desc[i].data.begin(), desc[i].data.end());
+      kpack.insert(kpack.end(), L->xy[i].begin(), L->xy[i].end());
+    }
+    b2m_image_shard sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.struct_size = sizeof(sh);
+    sh.location = B2M_LOC_HOST;
+    sh.first_image = first;
+    sh.n_local = count;
+    sh.has_keypoints = 1;
+    sh.desc_packed = dpack.data();
+    sh.kpts_packed = kpack.data();
+    rc[d] = b2m_set_images_sharded(ctxs[d], n_images, L->n_feat.data(), L->cams.data(), &sh);
+  };
   std::vector<std::thread> workers;
-  for (size_t d = 1; d < ctxs.size(); ++d)
-    workers.emplace_back([&, d] {
-      rc[d] = b2m_set_images(ctxs[d], static_cast<int32_t>(images.size()), n_feat.data(), dptr.data(), kptr.data(),
-                             cams.data());
-    });
-  rc[0] = b2m_set_images(ctxs[0], static_cast<int32_t>(images.size()), n_feat.data(), dptr.data(), kptr.data(),
-                         cams.data());
+  for (size_t d = 1; d < ctxs.size(); ++d) workers.emplace_back(upload, d);
+  upload(0);
   for (std::thread& w : workers) w.join();
   for (size_t d = 0; d < ctxs.size(); ++d) ThrowOnError(ctxs[d], rc[d]);
-  L.n_feat = std::move(n_feat);
-  L.xy = std::move(xy);
-  L.cams = std::move(cams);
-  return L;
+  L->uploaded = true;
 }
 
 Mat3 ToMat3(const double* p) {
@@ -350,6 +401,93 @@ struct ResultsGuard {
   }
 };
 
+// Verification of pairs whose raw matches are already in the database (verify_matches; pairs with stored matches
+// but no geometry inside the match_* pipelines): keypoints of the named images only, ONE batched GPU call per
+// 4096 pairs (b2m_estimate_two_view_geometry_batch), then the controller's write rule (row P3): raw matches below
+// min_num_inliers are rewritten empty, geometries below min_num_inliers are stored as the default one.
+void VerifyStoredPairs(Database& db, b2m_ctx* ctx, const LoadedSet& L, const std::vector<std::pair<int, int>>& pairs,
+                       const b2m_tvg_opts& tvg) {
+  constexpr size_t kChunk = 4096;
+  std::unordered_map<int, std::vector<double>> pts;   // image index -> keypoint positions as doubles
+  auto points_of = [&](int img) -> const std::vector<double>& {
+    auto it = pts.find(img);
+    if (it == pts.end()) {
+      std::vector<float> xy;
+      if (L.uploaded) xy = L.xy[img]; else xy = KeypointPositions(db, L.ids[img]);
+      it = pts.emplace(img, std::vector<double>(xy.begin(), xy.end())).first;
+    }
+    return it->second;
+  };
+  for (size_t c0 = 0; c0 < pairs.size(); c0 += kChunk) {
+    const size_t c1 = std::min(pairs.size(), c0 + kChunk);
+    std::vector<std::vector<uint32_t>> mm(c1 - c0);
+    std::vector<b2m_tvg_problem> prob;
+    std::vector<size_t> prob_of;                       // index into the chunk
+    pts.clear();
+    for (size_t k = c0; k < c1; ++k) {
+      mm[k - c0] = db.ReadMatches(L.ids[pairs[k].first], L.ids[pairs[k].second]);
+      if (static_cast<int64_t>(mm[k - c0].size() / 2) < tvg.min_num_inliers) continue;
+      points_of(pairs[k].first);
+      points_of(pairs[k].second);
+    }
+    for (size_t k = c0; k < c1; ++k) {
+      const std::vector<uint32_t>& m = mm[k - c0];
+      if (static_cast<int64_t>(m.size() / 2) < tvg.min_num_inliers) continue;
+      const std::vector<double>&p1 = pts.at(pairs[k].first), &p2 = pts.at(pairs[k].second);
+      b2m_tvg_problem q;
+      memset(&q, 0, sizeof(q));
+      q.struct_size = sizeof(q);
+      q.cam1 = L.cams[pairs[k].first];
+      q.cam2 = L.cams[pairs[k].second];
+      q.points1 = p1.data(); q.n1 = static_cast<int64_t>(p1.size() / 2);
+      q.points2 = p2.data(); q.n2 = static_cast<int64_t>(p2.size() / 2);
+      q.matches = m.data();  q.m = static_cast<int64_t>(m.size() / 2);
+      prob.push_back(q);
+      prob_of.push_back(k - c0);
+    }
+    std::vector<b2m_tvg_result> res(prob.size());
+    std::vector<std::vector<uint32_t>> inl(prob.size());
+    std::vector<uint32_t*> inl_ptr(prob.size());
+    for (size_t j = 0; j < prob.size(); ++j) {
+      inl[j].resize(static_cast<size_t>(std::max<int64_t>(1, prob[j].m)) * 2);
+      inl_ptr[j] = inl[j].data();
+    }
+    if (!prob.empty()) {
+      if (tvg.multiple_models) {   // the per-problem loop of EstimateMultipleTwoViewGeometries is sequential
+        for (size_t j = 0; j < prob.size(); ++j) {
+          memset(&res[j], 0, sizeof(res[j]));
+          res[j].struct_size = sizeof(res[j]);
+          ThrowOnError(ctx, b2m_estimate_two_view_geometry(ctx, &prob[j].cam1, prob[j].points1, prob[j].n1, &prob[j].cam2,
+                                                           prob[j].points2, prob[j].n2, prob[j].matches, prob[j].m, &tvg,
+                                                           &res[j], inl_ptr[j]));
+        }
+      } else {
+        ThrowOnError(ctx, b2m_estimate_two_view_geometry_batch(ctx, prob.data(), static_cast<int64_t>(prob.size()), &tvg,
+                                                               res.data(), inl_ptr.data()));
+      }
+    }
+    std::vector<int> res_of(c1 - c0, -1);
+    for (size_t j = 0; j < prob_of.size(); ++j) res_of[prob_of[j]] = static_cast<int>(j);
+    DatabaseTransaction tx(&db);
+    for (size_t k = c0; k < c1; ++k) {
+      const int64_t id1 = L.ids[pairs[k].first], id2 = L.ids[pairs[k].second];
+      const int j = res_of[k - c0];
+      if (j < 0) {  // raw matches below min_num_inliers: stored empty, default geometry
+        db.WriteMatches(id1, id2, nullptr, 0);
+        db.WriteTwoViewGeometry(id1, id2, B2M_UNDEFINED, nullptr, 0, Mat3{}, Mat3{}, Mat3{}, {1.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0});
+        continue;
+      }
+      const b2m_tvg_result& r = res[j];
+      if (r.n_inliers < tvg.min_num_inliers) {
+        db.WriteTwoViewGeometry(id1, id2, B2M_UNDEFINED, nullptr, 0, Mat3{}, Mat3{}, Mat3{}, {1.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0});
+      } else {
+        db.WriteTwoViewGeometry(id1, id2, r.config, inl[j].data(), r.n_inliers, ToMat3(r.F), ToMat3(r.E), ToMat3(r.H),
+                                {r.qvec[0], r.qvec[1], r.qvec[2], r.qvec[3]}, {r.tvec[0], r.tvec[1], r.tvec[2]});
+      }
+    }
+  }
+}
+
 // FeatureMatcherController::Match (row P3): skip self pairs, duplicates and pairs with both results
 // stored; match + verify the rest on the GPU(s); write both tables in one transaction per chunk.
 // With several contexts the chunk is cut into contiguous cost-balanced slices, one host thread per GPU
@@ -363,18 +501,27 @@ void MatchPairsIntoDb(Database& db, const std::vector<b2m_ctx*>& ctxs, const Loa
     have_m = db.ExistingPairIds("matches");
     have_g = db.ExistingPairIds("two_view_geometries");
   }
+  std::vector<std::pair<int, int>> stored_only;
   for (const PairList& chunk : chunks) {
     PairList todo;
     for (size_t k = 0; k + 1 < chunk.size(); k += 2) {
       const int32_t a = chunk[k], b = chunk[k + 1];
       if (a == b) continue;
       const int64_t pid = ImagePairToPairId(L.ids[a], L.ids[b]);
-      const bool stored = have_m.count(pid) && have_g.count(pid);
+      const bool has_m = have_m.count(pid) != 0, has_g = have_g.count(pid) != 0;
       have_m.insert(pid);
       have_g.insert(pid);
-      if (stored) continue;
+      if (has_m && has_g) continue;
+      if (has_m) {  // stored (imported / custom) matches without a geometry: verified as they are, never re-matched
+        stored_only.push_back({a, b});
+        continue;
+      }
       todo.push_back(a);
       todo.push_back(b);
+    }
+    if (!stored_only.empty()) {
+      VerifyStoredPairs(db, ctxs[0], L, stored_only, tvg);
+      stored_only.clear();
     }
     if (todo.empty()) continue;
     const std::vector<int64_t> cut = SplitPairsByCost(todo, L.n_feat, static_cast<int>(ctxs.size()));
@@ -452,7 +599,8 @@ void MatchExhaustive(const std::string& database_path, const SiftMatchingOptions
   if (matching.block_size <= 1) throw std::invalid_argument("[controllers.cc] Check Failed: block_size > 1");
   const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
   Database db(database_path);
-  const LoadedSet L = LoadImageSet(db, ctxs, /*order_by_name=*/false);
+  LoadedSet L = ReadImageTable(db, /*order_by_name=*/false);
+  UploadImageSet(db, ctxs, &L);
   MatchPairsIntoDb(db, ctxs, L, Chunked(ExhaustivePairBlocks(static_cast<int>(L.ids.size()), matching.block_size)),
                    ToAbi(sift), ToAbi(verification), /*skip_existing=*/true);
 }
@@ -466,7 +614,8 @@ void MatchSequential(const std::string& database_path, const SiftMatchingOptions
   if (matching.overlap < 1) throw std::invalid_argument("[controllers.cc] Check Failed: overlap > 0");
   const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
   Database db(database_path);
-  const LoadedSet L = LoadImageSet(db, ctxs, /*order_by_name=*/true);
+  LoadedSet L = ReadImageTable(db, /*order_by_name=*/true);
+  UploadImageSet(db, ctxs, &L);
   MatchPairsIntoDb(db, ctxs, L,
                    {SequentialPairs(static_cast<int>(L.ids.size()), matching.overlap, matching.quadratic_overlap)},
                    ToAbi(sift), ToAbi(verification), /*skip_existing=*/true);
@@ -479,7 +628,8 @@ void MatchSpatial(const std::string& database_path, const SiftMatchingOptions& s
   if (!(matching.max_distance > 0.0)) throw std::invalid_argument("[controllers.cc] Check Failed: max_distance > 0");
   const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
   Database db(database_path);
-  const LoadedSet L = LoadImageSet(db, ctxs, /*order_by_name=*/false);
+  LoadedSet L = ReadImageTable(db, /*order_by_name=*/false);
+  UploadImageSet(db, ctxs, &L);
   std::vector<std::array<double, 3>> prior_t;
   std::vector<bool> has_prior;
   db.ReadLocationPriors(&prior_t, &has_prior);   // same order as ReadAllImages (image_id)
@@ -494,7 +644,7 @@ void VerifyMatches(const std::string& database_path, const std::string& pairs_pa
   CheckFileExists(pairs_path, "match_features.h:55");
   b2m_ctx* ctx = Engine::Get(0);
   Database db(database_path);
-  const LoadedSet L = LoadImageSet(db, {ctx}, /*order_by_name=*/false);
+  LoadedSet L = ReadImageTable(db, /*order_by_name=*/false);   // no descriptors, no keypoints yet
   std::unordered_map<std::string, int> index_of;
   for (size_t i = 0; i < L.names.size(); ++i) index_of[L.names[i]] = static_cast<int>(i);
 
@@ -522,53 +672,11 @@ void VerifyMatches(const std::string& database_path, const std::string& pairs_pa
     }
   }
   const b2m_tvg_opts tvg = ToAbi(options);
-  if (!todo_match.empty())
+  if (!todo_match.empty()) {   // only now are descriptors needed (and keypoints.rows == descriptors.rows enforced)
+    UploadImageSet(db, {ctx}, &L);
     MatchPairsIntoDb(db, {ctx}, L, {todo_match}, ToAbi(SiftMatchingOptions()), tvg, /*skip_existing=*/false);
-
-  DatabaseTransaction tx(&db);
-  for (const auto& [a, b] : todo_verify) {
-    const int64_t id1 = L.ids[a], id2 = L.ids[b];
-    const std::vector<uint32_t> m = db.ReadMatches(id1, id2);
-    const int64_t n_m = static_cast<int64_t>(m.size() / 2);
-    int config = B2M_UNDEFINED;
-    std::vector<uint32_t> inl;
-    Mat3 E{}, F{}, H{};
-    std::array<double, 4> qvec{1.0, 0.0, 0.0, 0.0};
-    std::array<double, 3> tvec{0.0, 0.0, 0.0};
-    if (n_m >= options.min_num_inliers) {
-      auto points = [&](int64_t id) {
-        const KeypointsBlob kp = db.ReadKeypoints(id);
-        std::vector<double> p(static_cast<size_t>(kp.rows) * 2);
-        for (int64_t r = 0; r < kp.rows; ++r) {
-          p[2 * r] = kp.data[r * kp.cols];
-          p[2 * r + 1] = kp.data[r * kp.cols + 1];
-        }
-        return p;
-      };
-      const std::vector<double> p1 = points(id1), p2 = points(id2);
-      const b2m_camera c1 = ToAbi(db.ReadCamera(L.camera_ids[a])), c2 = ToAbi(db.ReadCamera(L.camera_ids[b]));
-      b2m_tvg_result r;
-      memset(&r, 0, sizeof(r));
-      r.struct_size = sizeof(r);
-      inl.resize(m.size());
-      ThrowOnError(ctx, b2m_estimate_two_view_geometry(ctx, &c1, p1.data(), static_cast<int64_t>(p1.size() / 2), &c2,
-                                                       p2.data(), static_cast<int64_t>(p2.size() / 2), m.data(), n_m,
-                                                       &tvg, &r, inl.data()));
-      inl.resize(static_cast<size_t>(r.n_inliers) * 2);
-      config = r.config;
-      E = ToMat3(r.E); F = ToMat3(r.F); H = ToMat3(r.H);
-      qvec = {r.qvec[0], r.qvec[1], r.qvec[2], r.qvec[3]};
-      tvec = {r.tvec[0], r.tvec[1], r.tvec[2]};
-    }
-    if (static_cast<int64_t>(inl.size() / 2) < options.min_num_inliers) {  // controller write rule (row P3)
-      config = B2M_UNDEFINED;
-      inl.clear();
-      E = F = H = Mat3{};
-      qvec = {1.0, 0.0, 0.0, 0.0};
-      tvec = {0.0, 0.0, 0.0};
-    }
-    db.WriteTwoViewGeometry(id1, id2, config, inl.data(), static_cast<int64_t>(inl.size() / 2), F, E, H, qvec, tvec);
   }
+  VerifyStoredPairs(db, ctx, L, todo_verify, tvg);
 }
 
 }  // namespace b2mh

@@ -88,9 +88,8 @@ b2m_tvg_opts ToAbi(const TwoViewGeometryOptions& o);
 // Database camera -> ABI camera; throws std::invalid_argument for models the verifier does not take.
 b2m_camera ToAbi(const CameraRow& c);
 // SiftMatchingOptions.gpu_index: comma-separated CUDA ordinals, "0,1,2,3" = one matcher per listed GPU
-// (R:pipeline/match_features.h:76-81).  Duplicates are dropped, order kept.  Deviation: upstream expands
-// "-1" to every visible GPU; here "-1" (the default) means device 0 until the all-GPU default has been
-// validated on a multi-GPU box -- list the devices explicitly to use more than one.
+// (R:pipeline/match_features.h:76-81).  Duplicates are dropped, order kept.  "-1" (the default) expands to
+// every visible sm_100 device like upstream (b2m_device_count; device 0 when the count cannot be had).
 std::vector<int> ParseGpuIndices(const std::string& gpu_index);
 
 // ---- pair generators (rows P1, P2) -------------------------------------------------------------
@@ -122,6 +121,9 @@ class Engine {
   // Lazily creates the context; throws std::runtime_error / std::invalid_argument with b2m_last_error().
   static b2m_ctx* Get(int device);
   static std::vector<b2m_ctx*> GetAll(const std::vector<int>& devices);
+  // One NCCL communicator over the given contexts (b2m_comm_init_local), created once per context list.  False
+  // when NCCL is not available: callers then upload the whole image set to every GPU instead of sharding it.
+  static bool EnsureLocalComm(const std::vector<b2m_ctx*>& ctxs);
   static void RequestStopAll();  // async-signal-safe flags only (b2m_request_stop on every live context)
   static void DestroyAll();
 };

@@ -30,6 +30,6 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def ctx():
     import pycolmap_b200 as pb
-    c = pb.Context(device=0, seed=0)
+    c = pb.Context(device=0, seed=0)   # the low-level context of the pybind11 host: one b2m_ctx behind the C ABI
     yield c
     c.close()

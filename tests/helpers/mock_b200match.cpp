@@ -5,7 +5,11 @@
 // measured.  Matching = the oracle's exact brute-force matcher (oracle/liboracle.so); "verification" is a
 // deterministic placeholder (every second match is an inlier, models derived from the pair indices) that
 // only has to be recognisable in the database -- the real verifier is tested on the GPU.
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -14,8 +18,33 @@
 extern "C" int orc_fast_match_pair(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float max_ratio,
                                    float max_distance, int cross_check, uint32_t* out_matches);
 
+// In-process stand-in for an NCCL communicator: the ranks (host threads) deposit their shards in a shared table
+// and meet at a barrier; what comes out must be the whole image set on every "GPU".
+struct MockComm {
+  int n = 0;
+  std::mutex m;
+  std::condition_variable cv;
+  int arrived = 0;
+  long generation = 0;
+  std::vector<std::vector<uint8_t>> desc;
+  std::vector<std::vector<float>> kpts;
+  void barrier(std::unique_lock<std::mutex>& lk) {
+    const long gen = generation;
+    if (++arrived == n) {
+      arrived = 0;
+      ++generation;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return generation != gen; });
+    }
+  }
+};
+
 struct b2m_ctx {
   int device = 0;
+  std::shared_ptr<MockComm> comm;
+  int comm_rank = 0;
+  uint64_t sharded_uploads = 0, sharded_bytes = 0;
   std::string err;
   std::vector<std::vector<uint8_t>> desc;
   std::vector<std::vector<float>> kpts;
@@ -57,6 +86,11 @@ static void fake_geometry(int a, int b, int n_matches, const uint32_t* m, int mi
 extern "C" {
 
 int b2m_abi_version(void) { return B2M_ABI_VERSION; }
+int b2m_device_count(void) {   // MOCK_B2M_DEVICES "GPUs" (default 1), at most 8
+  const char* e = getenv("MOCK_B2M_DEVICES");
+  const int n = e ? atoi(e) : 1;
+  return n < 0 ? 0 : (n > 8 ? 8 : n);
+}
 
 int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
   if (!out) return B2M_EINVAL;
@@ -113,6 +147,79 @@ int b2m_set_images(b2m_ctx* ctx, int32_t n, const int32_t* n_feat, const uint8_t
       }
     ctx->cams.assign(cams, cams + n);
   }
+  return B2M_OK;
+}
+int b2m_comm_get_unique_id(b2m_comm_id*) { return B2M_ENODEV; }   // the mock has no cross-process transport
+int b2m_comm_init_rank(b2m_ctx* ctx, int32_t, int32_t, const b2m_comm_id*) {
+  ctx->err = "mock: no NCCL";
+  return B2M_ENODEV;
+}
+int b2m_comm_init_local(b2m_ctx* const* ctxs, int32_t n) {
+  if (getenv("MOCK_B2M_NO_NCCL")) return B2M_ENODEV;           // the host must then upload the whole set everywhere
+  auto comm = std::make_shared<MockComm>();
+  comm->n = n;
+  for (int i = 0; i < n; ++i) {
+    ctxs[i]->comm = comm;
+    ctxs[i]->comm_rank = i;
+  }
+  return B2M_OK;
+}
+int b2m_comm_destroy(b2m_ctx* ctx) {
+  ctx->comm.reset();
+  return B2M_OK;
+}
+void b2m_comm_image_range(int32_t n_images, int32_t n_ranks, int32_t rank, int32_t* first, int32_t* count) {
+  if (n_ranks < 1) n_ranks = 1;
+  const int64_t per = (static_cast<int64_t>(n_images) + n_ranks - 1) / n_ranks;
+  const int64_t lo = per * rank < n_images ? per * rank : n_images, hi = per * (rank + 1) < n_images ? per * (rank + 1) : n_images;
+  *first = static_cast<int32_t>(lo);
+  *count = static_cast<int32_t>(hi - lo);
+}
+int b2m_set_images_sharded(b2m_ctx* ctx, int32_t n, const int32_t* n_feat, const b2m_camera* cams, const b2m_image_shard* mine) {
+  if (!mine || mine->struct_size != sizeof(b2m_image_shard) || mine->location != B2M_LOC_HOST) {
+    ctx->err = "mock: shard";
+    return B2M_EINVAL;
+  }
+  const int n_ranks = ctx->comm ? ctx->comm->n : 1;
+  int32_t first = 0, count = 0;
+  b2m_comm_image_range(n, n_ranks, ctx->comm_rank, &first, &count);
+  if (first != mine->first_image || count != mine->n_local) {
+    ctx->err = "mock: the shard is not this rank's image range";
+    return B2M_EINVAL;
+  }
+  std::shared_ptr<MockComm> local;
+  MockComm* c = ctx->comm.get();
+  if (!c) {
+    local = std::make_shared<MockComm>();
+    local->n = 1;
+    c = local.get();
+  }
+  std::unique_lock<std::mutex> lk(c->m);
+  if (static_cast<int>(c->desc.size()) != n) {
+    c->desc.assign(n, {});
+    c->kpts.assign(n, {});
+  }
+  const uint8_t* d = static_cast<const uint8_t*>(mine->desc_packed);
+  const float* k = static_cast<const float*>(mine->kpts_packed);
+  size_t row = 0;
+  for (int i = first; i < first + count; ++i) {
+    c->desc[i].assign(d + row * 128, d + (row + n_feat[i]) * 128);
+    if (mine->has_keypoints) c->kpts[i].assign(k + row * 2, k + (row + n_feat[i]) * 2);
+    row += n_feat[i];
+    ctx->sharded_bytes += static_cast<uint64_t>(n_feat[i]) * 128;
+  }
+  c->barrier(lk);                 // the "all-gather"
+  ctx->desc = c->desc;
+  ctx->kpts = c->kpts;
+  for (int i = 0; i < n; ++i)
+    if (ctx->desc[i].size() != static_cast<size_t>(n_feat[i]) * 128) {
+      ctx->err = "mock: an image is missing after the gather";
+      return B2M_ESTATE;
+    }
+  c->barrier(lk);                 // nobody overwrites the table before everybody has copied it
+  ctx->cams.clear();
+  if (cams) ctx->cams.assign(cams, cams + n);
+  ctx->sharded_uploads += 1;
   return B2M_OK;
 }
 int b2m_set_images_device(b2m_ctx* ctx, int32_t, const int32_t*, const void*, const void*, const b2m_camera*) {
@@ -252,6 +359,9 @@ int b2m_get_stats(b2m_ctx* ctx, b2m_stats* out) {
   memset(out, 0, sizeof(*out));
   out->struct_size = sizeof(*out);
   out->kernel_launches = ctx->launches;
+  out->last_allgather_bytes = ctx->sharded_bytes;   // bytes this "GPU" uploaded itself (the host's shard)
+  out->comm_size = ctx->comm ? ctx->comm->n : 1;
+  out->comm_rank = ctx->comm_rank;
   return B2M_OK;
 }
 int b2m_reset_stats(b2m_ctx* ctx) {

@@ -96,15 +96,31 @@ assert any(i1 > i2 for i1, i2 in visits)                              # the reve
 before = open(a_db, "rb").read()
 nat.match_exhaustive(a_db, matching_options={"block_size": 4})
 assert open(a_db, "rb").read() == before
-# partial resume: drop two geometries and one match row; only those pairs are redone, the result is the same
+ref_dump = dump(a_db)
+# partial resume: a pair without a matches row is matched + verified again (same result); pairs whose matches are
+# stored but whose geometry is missing are VERIFIED FROM THE STORED MATCHES, never re-matched (imported / custom
+# matches survive a match_* run; the mock's estimator entry point marks its geometries with the pair (7, 9))
 con = sqlite3.connect(a_db)
-rows = con.execute("SELECT pair_id FROM two_view_geometries ORDER BY pair_id").fetchall()
-con.execute("DELETE FROM two_view_geometries WHERE pair_id IN (?, ?)", (rows[0][0], rows[5][0]))
-con.execute("DELETE FROM matches WHERE pair_id = ?", (rows[9][0],))
+rows = [r[0] for r in con.execute("SELECT pair_id FROM two_view_geometries WHERE rows >= 15 ORDER BY pair_id")]
+con.execute("DELETE FROM two_view_geometries WHERE pair_id IN (?, ?)", (rows[0], rows[3]))
+custom = np.frombuffer(con.execute("SELECT data FROM matches WHERE pair_id = ?", (rows[3],)).fetchone()[0], np.uint32).reshape(-1, 2)[:-1]
+con.execute("UPDATE matches SET rows = ?, data = ? WHERE pair_id = ?", (len(custom), custom.tobytes(), rows[3]))   # "imported"
+con.execute("DELETE FROM matches WHERE pair_id = ?", (rows[5],))
 con.commit()
 con.close()
 nat.match_exhaustive(a_db, matching_options={"block_size": 4})
-ref_dump = dump(a_db)
+resumed = dump(a_db)
+assert [r for r in resumed["matches"] if r[0] != rows[3]] == [r for r in ref_dump["matches"] if r[0] != rows[3]]
+assert np.array_equal(np.frombuffer([r for r in resumed["matches"] if r[0] == rows[3]][0][3], np.uint32).reshape(-1, 2), custom)
+for ra, rb in zip(resumed["two_view_geometries"], ref_dump["two_view_geometries"]):
+    if ra[0] in (rows[0], rows[3]):
+        stored = np.frombuffer([r for r in resumed["matches"] if r[0] == ra[0]][0][3], np.uint32).reshape(-1, 2)
+        cfg, inl, E, F, H = fake_geometry(7, 9, stored)
+        assert ra[1] == len(inl) and ra[4] == cfg and np.array_equal(np.frombuffer(ra[3], np.uint32).reshape(-1, 2), inl)
+        Es, Fs = np.frombuffer(ra[6]).reshape(3, 3), np.frombuffer(ra[5]).reshape(3, 3)   # transposed if visited as (id2, id1)
+        assert (np.array_equal(Es, E) and np.array_equal(Fs, F)) or (np.array_equal(Es, E.T) and np.array_equal(Fs, F.T))
+    else:
+        assert ra == rb
 
 # ---- gpu_index lists: same database whatever the number of GPUs and the block size -------------------------
 for k, (gpus, bs) in enumerate((("0,1,2", 4), ("0, 1,2,3,4,5,6,7", 4), ("5", 4), ("-1", 3), ("1,0", 50))):
@@ -116,6 +132,17 @@ for k, (gpus, bs) in enumerate((("0,1,2", 4), ("0, 1,2,3,4,5,6,7", 4), ("5", 4),
         assert d == ref_dump, gpus                                     # byte-identical tables
     else:  # another block size visits pairs in another orientation: same pair set, same match sets
         assert [r[:2] for r in d["matches"]] == [r[:2] for r in ref_dump["matches"]]
+# the default "-1" = every visible GPU (upstream); without NCCL every GPU takes the whole set: same database
+for k, env in enumerate(({"MOCK_B2M_DEVICES": "3"}, {"MOCK_B2M_DEVICES": "4", "MOCK_B2M_NO_NCCL": "1"})):
+    os.environ.update(env)
+    assert nat.parse_gpu_indices("-1") == list(range(int(env["MOCK_B2M_DEVICES"])))
+    p = os.path.join(tmp, f"all{k}.db")
+    make_db(p)
+    nat.match_exhaustive(p, matching_options={"block_size": 4})
+    assert dump(p) == ref_dump, env
+    for key in env:
+        del os.environ[key]
+assert nat.parse_gpu_indices("-1") == [0] and nat.parse_gpu_indices("2,-1") == [2, 0]
 try:
     nat.match_exhaustive(a_db, sift_options={"gpu_index": "0,9"})
     raise SystemExit("device 9 must be refused")
@@ -131,9 +158,9 @@ except ValueError:
 s_db = os.path.join(tmp, "s.db")
 names = [f"img{99 - i:03d}.png" for i in range(n_img)]                 # name order = reverse id order
 sids = make_db(s_db, names)
-nat.match_sequential(s_db, matching_options={"overlap": 2, "quadratic_overlap": False})
+nat.match_sequential(s_db, matching_options={"overlap": 3, "quadratic_overlap": False})
 order = sorted(range(n_img), key=lambda i: names[i])
-seq = R.sequential_pairs(range(n_img), 2, False)
+seq = R.sequential_pairs(range(n_img), 3, False)     # COLMAP 3.9.1: overlap 3 -> two linear neighbours
 with nat.Database(s_db) as db:
     assert db.num_rows("matches") == len(seq) == (n_img - 1) + (n_img - 2)
     for k1, k2 in seq:
@@ -168,6 +195,43 @@ with nat.Database(s_db) as db:
     assert db.exists_matches(sids[a], sids[b]) and db.exists_inlier_matches(sids[a], sids[b])
     want = oracle.fast_match_pair(descs[a], descs[b])
     assert np.array_equal(db.read_matches(sids[a], sids[b]), want if len(want) >= MIN else want[:0])
+
+# ---- verify_matches on a database WITHOUT descriptors (learned-feature matches imported by the user, e.g. hloc):
+# only keypoints, cameras and the stored matches are needed
+v_db = os.path.join(tmp, "nodesc.db")
+vids = make_db(v_db)
+con = sqlite3.connect(v_db)
+con.execute("DELETE FROM descriptors")
+con.commit()
+con.close()
+imported = {}
+with nat.Database(v_db) as db:
+    for a, b in ((0, 1), (2, 1), (3, 4)):
+        m = np.stack([np.arange(40, dtype=np.uint32), np.arange(40, dtype=np.uint32)[::-1]], 1)
+        m = m[: 40 if (a, b) != (3, 4) else 9]                         # (3, 4): fewer than min_num_inliers matches
+        db.write_matches(vids[a], vids[b], m)
+        imported[(a, b)] = m
+vnames = [f"frame{i:04d}.png" for i in range(n_img)]
+with open(pairs_txt, "w") as f:
+    f.write("".join(f"{vnames[a]} {vnames[b]}\n" for a, b in imported))
+nat.verify_matches(v_db, pairs_txt)
+with nat.Database(v_db) as db:
+    assert db.num_rows("two_view_geometries") == 3 and db.num_descriptors == 0
+    for (a, b), m in imported.items():
+        g = db.read_two_view_geometry(vids[a], vids[b])
+        if len(m) < MIN:   # write rule: raw matches below min_num_inliers are rewritten empty, default geometry
+            assert len(db.read_matches(vids[a], vids[b])) == 0 and g.config.value == 0 and len(g.inlier_matches) == 0
+        else:
+            cfg, inl, E, F, H = fake_geometry(7, 9, m)
+            assert np.array_equal(db.read_matches(vids[a], vids[b]), m)
+            assert g.config.value == cfg and np.array_equal(g.inlier_matches, inl)
+with open(pairs_txt, "w") as f:
+    f.write(f"{vnames[0]} {vnames[5]}\n")                                # no stored matches: now descriptors ARE needed
+try:
+    nat.verify_matches(v_db, pairs_txt)
+    raise SystemExit("matching without descriptors must be refused")
+except ValueError as e:
+    assert "keypoints.rows == descriptors.rows" in str(e)
 
 # ---- cameras: COLMAP's default SIMPLE_RADIAL is accepted, FOV is refused; inconsistent features are refused ----
 r_db = os.path.join(tmp, "radial.db")

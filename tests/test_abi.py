@@ -1,61 +1,75 @@
-"""CPU: the C-ABI library loads and exports every symbol include/b200match.h declares; without a
-GPU it must fail loudly (no CPU fallback)."""
+"""CPU: the C-ABI library loads and exports every symbol include/b200match.h declares, the header is plain C,
+the option defaults are the reference's, and without a GPU the library fails loudly (no CPU fallback)."""
 import ctypes
 import os
 import re
+import subprocess
 
 import pytest
 
-import pycolmap_b200 as pb
-from pycolmap_b200 import _lib
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "pycolmap_b200", "libb200match.so")
+HDR = os.path.join(ROOT, "include", "b200match.h")
+
+
+def _declared():
+    return set(re.findall(r"\b(b2m_[a-z0-9_]+)\s*\(", open(HDR).read()))
 
 
 def test_header_symbols_exported():
-    hdr = open(os.path.join(ROOT, "include", "b200match.h")).read()
-    declared = set(re.findall(r"\b(b2m_[a-z0-9_]+)\s*\(", hdr))
-    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    lib = _lib.load()
+    lib = ctypes.CDLL(LIB)
+    declared = _declared()
+    assert len(declared) >= 26
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.b2m_abi_version() == 2
+    # ... and nothing else leaks out under the b2m_ prefix
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB], text=True)
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("b2m_")}
+    assert exported == declared, exported ^ declared
+    ver = int(re.search(r"#define\s+B2M_ABI_VERSION\s+(\d+)", open(HDR).read()).group(1))
+    assert lib.b2m_abi_version() == ver
 
 
-def test_struct_sizes_match_defaults():
-    lib = _lib.load()
-    s = _lib.SiftOpts()
-    lib.b2m_sift_opts_default(ctypes.byref(s))
-    assert s.struct_size == ctypes.sizeof(_lib.SiftOpts)
-    assert (round(s.max_ratio, 6), round(s.max_distance, 6), s.cross_check, s.max_num_matches) == (0.8, 0.7, 1, 32768)
-    t = _lib.TvgOpts()
-    lib.b2m_tvg_opts_default(ctypes.byref(t))
-    assert t.struct_size == ctypes.sizeof(_lib.TvgOpts)
-    assert t.ransac.struct_size == ctypes.sizeof(_lib.RansacOpts)
-    assert (t.min_num_inliers, t.min_E_F_inlier_ratio, t.max_H_inlier_ratio) == (15, 0.95, 0.8)
-    assert (t.ransac.max_error, t.ransac.confidence, t.ransac.min_num_trials, t.ransac.max_num_trials,
-            t.ransac.min_inlier_ratio) == (4.0, 0.999, 100, 10000, 0.25)
-
-
-def test_ctypes_structs_match_the_c_header(tmp_path):
-    """The header compiles as plain C and every struct the ctypes binding mirrors has the C size."""
-    import subprocess
-    names = {"b2m_device_cfg": _lib.DeviceCfg, "b2m_sift_opts": _lib.SiftOpts, "b2m_ransac_opts": _lib.RansacOpts,
-             "b2m_tvg_opts": _lib.TvgOpts, "b2m_camera": _lib.Camera, "b2m_pair_view": _lib.PairView,
-             "b2m_tvg_result": _lib.TvgResult, "b2m_tvg_problem": _lib.TvgProblem, "b2m_stats": _lib.Stats}
-    src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include "b200match.h"\nint main(void) {\n' +
-                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")
-    exe = tmp_path / "sizes"
-    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
-    sizes = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
-    for n, cls in names.items():
-        assert int(sizes[n]) == ctypes.sizeof(cls), n
+def test_header_is_plain_c_and_defaults_are_the_references(tmp_path):
+    """The header compiles as C11 with -Wall -Werror; a C program reads the option defaults through the ABI
+    (SiftMatchingOptions / TwoViewGeometryOptions / RANSAC C++-constructor defaults)."""
+    src = tmp_path / "defaults.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "b200match.h"
+int main(void) {
+  b2m_sift_opts s; b2m_tvg_opts t;
+  b2m_sift_opts_default(&s); b2m_tvg_opts_default(&t);
+  if (s.struct_size != sizeof(s) || t.struct_size != sizeof(t) || t.ransac.struct_size != sizeof(t.ransac)) return 2;
+  printf("%.6f %.6f %d %d %d\n", s.max_ratio, s.max_distance, s.cross_check, s.max_num_matches, s.guided_matching);
+  printf("%d %.3f %.3f %.3f %.3f %d %d %d %d %d\n", t.min_num_inliers, t.min_E_F_inlier_ratio, t.max_H_inlier_ratio,
+         t.watermark_min_inlier_ratio, t.watermark_border_size, t.detect_watermark, t.multiple_ignore_watermark,
+         t.force_H_use, t.compute_relative_pose, t.multiple_models);
+  printf("%.3f %.4f %d %d %.3f %.1f\n", t.ransac.max_error, t.ransac.confidence, t.ransac.min_num_trials,
+         t.ransac.max_num_trials, t.ransac.min_inlier_ratio, t.ransac.dyn_num_trials_multiplier);
+  printf("%zu %zu %zu %zu\n", sizeof(b2m_camera), sizeof(b2m_pair_view), sizeof(b2m_tvg_result), sizeof(b2m_stats));
+  return 0;
+}
+''')
+    exe = tmp_path / "defaults"
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                           "-L", os.path.dirname(LIB), "-lb200match", "-Wl,-rpath," + os.path.dirname(LIB)])
+    lines = subprocess.check_output([str(exe)], text=True).splitlines()
+    assert lines[0] == "0.800000 0.700000 1 32768 0"
+    assert lines[1] == "15 0.950 0.800 0.700 0.100 1 1 0 0 0"
+    assert lines[2] == "4.000 0.9990 100 10000 0.250 3.0"
+    assert all(int(x) % 8 == 0 for x in lines[3].split())
 
 
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    with pytest.raises(pb.B2MError, match="no CPU fallback"):
+    import pycolmap_b200 as pb
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         pb.Context()
+    lib = ctypes.CDLL(LIB)
+    lib.b2m_last_error.restype = ctypes.c_char_p
+    ctx = ctypes.c_void_p()
+    assert lib.b2m_create(None, ctypes.byref(ctx)) == -2 and not ctx.value          # B2M_ENODEV
+    assert b"no CPU fallback" in lib.b2m_last_error(None)

@@ -9,11 +9,11 @@ from pycolmap_b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 
-def _check(ctx, d1, d2, **kw):
-    opts = ctx.sift_opts(**kw)
-    got = ctx.match_pair(d1, d2, opts)
-    want = oracle.fast_match_pair(d1, d2, max_ratio=opts.max_ratio, max_distance=opts.max_distance,
-                                  cross_check=bool(opts.cross_check))
+def _check(ctx, d1, d2, max_ratio=0.8, max_distance=0.7, cross_check=1):
+    got = ctx.match_pair(d1, d2, {"max_ratio": max_ratio, "max_distance": max_distance, "cross_check": bool(cross_check)})
+    # SiftMatchingOptions holds doubles; the matcher takes them as float32 (double -> float at use, row B4)
+    want = oracle.fast_match_pair(d1, d2, max_ratio=float(np.float32(max_ratio)), max_distance=float(np.float32(max_distance)),
+                                  cross_check=bool(cross_check))
     assert got.dtype == np.uint32 and got.shape[1] == 2
     assert np.array_equal(got, want), (len(got), len(want))
     return got

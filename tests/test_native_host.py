@@ -1,7 +1,7 @@
-"""CPU: the C++ host layer (pycolmap_b200.native = pybind11 module _core) -- option classes with the
-reference's dataclass behaviour (R:helpers.h:40-283), the C++ COLMAP database layer (interoperable
-with the Python one, byte for byte), pair generators, argument checks and error types.  No compute
-call is made: without a GPU the C ABI refuses to create a context."""
+"""CPU: the C++ host layer (pycolmap_b200 = pybind11 module _core) -- option classes with the
+reference's dataclass behaviour (R:helpers.h:40-283), the C++ COLMAP database layer (interoperable with
+a database written by plain sqlite3 in upstream's column layout), pair generators, argument checks and
+error types.  No compute call is made: without a GPU the C ABI refuses to create a context."""
 import copy
 import pickle
 import sqlite3
@@ -9,18 +9,24 @@ import sqlite3
 import numpy as np
 import pytest
 
-import pycolmap_b200 as pb
 from helpers.native_import import load_native
 
 nat = load_native()
 from oracle import ransac as R
-from pycolmap_b200.database import Database as PyDatabase
 
 
-def test_option_defaults_match_reference_and_python_host():
-    for name in ("SiftMatchingOptions", "ExhaustiveMatchingOptions", "SequentialMatchingOptions", "RANSACOptions",
-                 "TwoViewGeometryOptions"):
-        assert getattr(nat, name)().todict() == getattr(pb, name)().todict(), name
+def test_option_defaults_match_reference():
+    # SURVEY.md rows B4-B8 (upstream defaults of the fields the reference exposes)
+    assert nat.SiftMatchingOptions().todict() == dict(num_threads=-1, gpu_index="-1", max_ratio=0.8, max_distance=0.7,
+                                                      cross_check=True, max_num_matches=32768, guided_matching=False)
+    assert nat.ExhaustiveMatchingOptions().todict() == dict(block_size=50)
+    sq = nat.SequentialMatchingOptions().todict()
+    assert (sq["overlap"], sq["quadratic_overlap"], sq["loop_detection"]) == (10, True, False)
+    tv = nat.TwoViewGeometryOptions().todict()
+    assert {k: v for k, v in tv.items() if k != "ransac"} == dict(
+        min_num_inliers=15, min_E_F_inlier_ratio=0.95, max_H_inlier_ratio=0.8, watermark_min_inlier_ratio=0.7,
+        watermark_border_size=0.1, detect_watermark=True, multiple_ignore_watermark=True, force_H_use=False,
+        compute_relative_pose=False, multiple_models=False)
     t = nat.TwoViewGeometryOptions()   # .ransac keeps the C++ ctor defaults, RANSACOptions() the binding's
     assert (t.ransac.max_error, t.ransac.confidence, t.ransac.min_num_trials, t.ransac.max_num_trials,
             t.ransac.min_inlier_ratio) == (4.0, 0.999, 100, 10000, 0.25)
@@ -67,7 +73,7 @@ def test_dataclass_behaviour():
     assert cfg("WATERMARK").value == 7 and nat.has_cuda is True
 
 
-def test_pair_generators_match_oracle_and_python_host():
+def test_pair_generators_match_oracle():
     for n, bs in [(1, 50), (2, 2), (49, 50), (50, 50), (51, 50), (101, 50), (7, 2), (130, 64), (0, 5)]:
         blocks = nat.exhaustive_pair_blocks(n, bs)
         got = np.concatenate(blocks) if blocks else np.zeros((0, 2), np.int32)
@@ -125,7 +131,7 @@ def test_database_roundtrip_cxx(tmp_path):
         db.write_matches(ids[0], ids[1], m)
         db.rollback()
         assert not db.exists_matches(ids[0], ids[1])
-    assert nat.image_pair_to_pair_id(7, 3) == 3 * 2147483647 + 7 == pb.image_pair_to_pair_id(7, 3)
+    assert nat.image_pair_to_pair_id(7, 3) == 3 * 2147483647 + 7
     assert nat.pair_id_to_image_pair(nat.image_pair_to_pair_id(7, 3)) == (3, 7)
     inv = nat.TwoViewGeometry("PLANAR", H=H, F=F, inlier_matches=m)
     inv.invert()
@@ -135,9 +141,9 @@ def test_database_roundtrip_cxx(tmp_path):
     assert "PLANAR" in repr(inv)
 
 
-def test_relative_pose_storage_both_layers(tmp_path):
-    """qvec (w, x, y, z) / tvec columns: stored in the id1 < id2 frame, inverted for the swapped pair, the same
-    through the C++ and the Python layer; Rigid3d accessors."""
+def test_relative_pose_storage(tmp_path):
+    """qvec (w, x, y, z) / tvec columns: stored in the id1 < id2 frame, inverted for the swapped pair; Rigid3d
+    accessors; the raw columns hold what plain sqlite3 + numpy expects."""
     rng = np.random.default_rng(5)
     q = rng.normal(size=4)
     q /= np.linalg.norm(q)
@@ -151,59 +157,96 @@ def test_relative_pose_storage_both_layers(tmp_path):
     assert np.allclose(pose.matrix(), np.c_[Rm, t])
     inv = pose.inverse()
     assert np.allclose(inv.rotation.matrix(), Rm.T) and np.allclose(inv.translation, -Rm.T @ t)
-    py_pose = pb.Rigid3d(pb.Rotation3d((q[1], q[2], q[3], q[0])), t)
-    assert np.allclose(py_pose.matrix(), pose.matrix()) and np.allclose(py_pose.inverse().matrix(), inv.matrix())
-    with nat.Database(tmp_path / "a.db") as a, PyDatabase(tmp_path / "b.db") as b:
+    built = nat.Rigid3d(nat.Rotation3d([q[1], q[2], q[3], q[0]]), t)         # (x, y, z, w) like the reference
+    assert np.allclose(built.matrix(), pose.matrix()) and np.allclose(built.inverse().matrix(), inv.matrix())
+    with nat.Database(tmp_path / "a.db") as a:
         _, ids, _, _ = _fill(a, np.random.default_rng(2))
-        _fill(b, np.random.default_rng(2))
         a.write_two_view_geometry(ids[2], ids[0], g)             # swapped: stored as the inverse pose
-        b.write_two_view_geometry(ids[2], ids[0], 2, m, qvec=q, tvec=t)
-        ga, gb = a.read_two_view_geometry(ids[0], ids[2]), b.read_two_view_geometry(ids[0], ids[2])
-        assert np.allclose(ga.cam2_from_cam1.matrix(), inv.matrix()) and np.allclose(gb["tvec"], inv.translation)
-        assert np.allclose(gb["qvec"], [q[0], -q[1], -q[2], -q[3]])
+        ga = a.read_two_view_geometry(ids[0], ids[2])
+        assert np.allclose(ga.cam2_from_cam1.matrix(), inv.matrix())
         back = a.read_two_view_geometry(ids[2], ids[0])         # read in the written orientation
         assert np.allclose(back.cam2_from_cam1.matrix(), pose.matrix())
-        gb2 = b.read_two_view_geometry(ids[2], ids[0])
-        assert np.allclose(gb2["qvec"], q) and np.allclose(gb2["tvec"], t)
-    rows = [sqlite3.connect(tmp_path / n).execute("SELECT qvec, tvec FROM two_view_geometries").fetchall() for n in ("a.db", "b.db")]
-    for (qa, ta), (qb, tb) in zip(*rows):
-        assert np.allclose(np.frombuffer(qa), np.frombuffer(qb)) and np.allclose(np.frombuffer(ta), np.frombuffer(tb))
+    (qa, ta), = sqlite3.connect(tmp_path / "a.db").execute("SELECT qvec, tvec FROM two_view_geometries").fetchall()
+    assert np.allclose(np.frombuffer(qa), [q[0], -q[1], -q[2], -q[3]]) and np.allclose(np.frombuffer(ta), inv.translation)
 
 
-def test_database_is_interoperable_with_the_python_layer(tmp_path):
-    """Same schema and the same bytes: rows written by one layer read back identically through the
-    other, and through plain sqlite3 with the COLMAP column layout."""
+# COLMAP 3.9.1's schema as upstream's own scripts/python/database.py creates it (plain sqlite3)
+_UPSTREAM_SCHEMA = """
+CREATE TABLE IF NOT EXISTS cameras (camera_id INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, model INTEGER NOT NULL,
+    width INTEGER NOT NULL, height INTEGER NOT NULL, params BLOB, prior_focal_length INTEGER NOT NULL);
+CREATE TABLE IF NOT EXISTS images (image_id INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, name TEXT NOT NULL UNIQUE,
+    camera_id INTEGER NOT NULL, prior_qw REAL, prior_qx REAL, prior_qy REAL, prior_qz REAL, prior_tx REAL, prior_ty REAL,
+    prior_tz REAL, CONSTRAINT image_id_check CHECK(image_id >= 0 and image_id < 2147483647),
+    FOREIGN KEY(camera_id) REFERENCES cameras(camera_id));
+CREATE UNIQUE INDEX IF NOT EXISTS index_name ON images(name);
+CREATE TABLE IF NOT EXISTS keypoints (image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL,
+    data BLOB, FOREIGN KEY(image_id) REFERENCES images(image_id) ON DELETE CASCADE);
+CREATE TABLE IF NOT EXISTS descriptors (image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL,
+    data BLOB, FOREIGN KEY(image_id) REFERENCES images(image_id) ON DELETE CASCADE);
+CREATE TABLE IF NOT EXISTS matches (pair_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+CREATE TABLE IF NOT EXISTS two_view_geometries (pair_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL,
+    cols INTEGER NOT NULL, data BLOB, config INTEGER NOT NULL, F BLOB, E BLOB, H BLOB, qvec BLOB, tvec BLOB);
+"""
+
+
+def test_database_is_interoperable_with_plain_sqlite3(tmp_path):
+    """Rows written through plain sqlite3 in upstream's column layout read back through the C++ layer, and rows the
+    C++ layer writes decode with numpy exactly as upstream's scripts/python/database.py decodes them."""
     rng = np.random.default_rng(1)
     m = np.array([[0, 5], [3, 1], [7, 2]], np.uint32)
     E, F, H = (rng.normal(size=(3, 3)) for _ in range(3))
-    paths = [tmp_path / "cxx.db", tmp_path / "py.db"]
-    with nat.Database(paths[0]) as a, PyDatabase(paths[1]) as b:
-        _, ids, kp, d = _fill(a, np.random.default_rng(2))
-        _fill(b, np.random.default_rng(2))
-        a.write_matches(ids[1], ids[0], m)
-        b.write_matches(ids[1], ids[0], m)
+    kp = rng.uniform(0, 1000, (10, 4)).astype(np.float32)
+    d = rng.integers(0, 255, (10, 128)).astype(np.uint8)
+    up = tmp_path / "upstream.db"
+    con = sqlite3.connect(up)
+    con.executescript(_UPSTREAM_SCHEMA)
+    con.execute("INSERT INTO cameras VALUES (?, ?, ?, ?, ?, ?)", (None, 2, 1600, 1200, np.array([1200.0, 800.0, 600.0, -0.1]).tobytes(), 1))
+    for i in range(3):
+        con.execute("INSERT INTO images VALUES (?, ?, ?, ?, ?, ?, ?, ?, ?, ?)", (None, f"img{i}.jpg", 1) + (None,) * 7)
+    con.execute("INSERT INTO keypoints VALUES (?, ?, ?, ?)", (1, 10, 4, kp.tobytes()))
+    con.execute("INSERT INTO descriptors VALUES (?, ?, ?, ?)", (1, 10, 128, d.tobytes()))
+    con.execute("INSERT INTO matches VALUES (?, ?, ?, ?)", (1 * 2147483647 + 2, 3, 2, m.tobytes()))
+    con.execute("INSERT INTO two_view_geometries VALUES (?, ?, ?, ?, ?, ?, ?, ?, ?, ?)",
+                (1 * 2147483647 + 2, 2, 2, m[:2].tobytes(), 2, F.tobytes(), E.tobytes(), H.tobytes(),
+                 np.array([1.0, 0, 0, 0]).tobytes(), np.zeros(3).tobytes()))
+    con.commit()
+    con.close()
+    with nat.Database(up) as a:
+        assert a.read_all_images() == [(i + 1, f"img{i}.jpg", 1) for i in range(3)]
+        cam = a.read_camera(1)
+        assert cam["model"] == 2 and cam["params"] == [1200.0, 800.0, 600.0, -0.1] and cam["has_prior_focal_length"] == 1
+        assert np.array_equal(a.read_keypoints(1), kp) and np.array_equal(a.read_descriptors(1), d)
+        assert np.array_equal(a.read_matches(1, 2), m) and np.array_equal(a.read_matches(2, 1), m[:, ::-1])
+        g = a.read_two_view_geometry(1, 2)
+        assert g.config.value == 2 and np.array_equal(g.inlier_matches, m[:2])
+        assert np.array_equal(g.E, E) and np.array_equal(g.F, F) and np.array_equal(g.H, H)
+    # the other direction: written by the C++ layer, decoded with numpy from the raw columns
+    mine = tmp_path / "cxx.db"
+    with nat.Database(mine) as a:
+        _, ids, kp2, d2 = _fill(a, np.random.default_rng(2))
+        a.write_matches(ids[1], ids[0], m)                       # swapped on the way in
         a.write_matches(ids[1], ids[2], np.zeros((0, 2), np.uint32))
-        b.write_matches(ids[1], ids[2], np.zeros((0, 2), np.uint32))
-        # written in the stored orientation (id1 < id2): no H inversion involved, so the bytes must agree
-        # (the swapped orientation is covered above; numpy's LU inverse differs from the closed form in the last bits)
         a.write_two_view_geometry(ids[0], ids[1], nat.TwoViewGeometry("CALIBRATED", E=E, F=F, H=H, inlier_matches=m[:2]))
-        b.write_two_view_geometry(ids[0], ids[1], 2, m[:2], F=F, E=E, H=H)
-    dumps = []
-    for p in paths:
-        con = sqlite3.connect(p)
-        dumps.append({t: con.execute(f"SELECT * FROM {t} ORDER BY 1").fetchall()
-                      for t in ("cameras", "images", "keypoints", "descriptors", "matches", "two_view_geometries")})
-        con.close()
-    assert dumps[0] == dumps[1]
-    assert dumps[0]["matches"][1][1:] == (0, 2, b"")            # empty match list: zero rows, empty blob
-    with PyDatabase(paths[0]) as b, nat.Database(paths[1]) as a:   # cross-read
-        assert np.array_equal(b.read_matches(ids[0], ids[1]), m[:, ::-1])
-        g_py, g_cx = b.read_two_view_geometry(ids[0], ids[1]), a.read_two_view_geometry(ids[0], ids[1])
-        assert g_py["config"] == g_cx.config.value == 2
-        for k in "EFH":
-            assert np.allclose(g_py[k], getattr(g_cx, k)) and np.allclose(g_py[k], {"E": E, "F": F, "H": H}[k])
-        assert np.array_equal(g_py["inlier_matches"], g_cx.inlier_matches)
-        assert np.array_equal(a.read_keypoints(ids[0]), b.read_keypoints(ids[0]))
+    con = sqlite3.connect(mine)
+    schema = {r[0]: r[1] for r in con.execute("SELECT name, sql FROM sqlite_master WHERE type = 'table'")}
+    up_con = sqlite3.connect(up)
+    for table in ("cameras", "images", "keypoints", "descriptors", "matches", "two_view_geometries"):
+        cols = [r[1:3] for r in con.execute(f"PRAGMA table_info({table})")]
+        assert cols == [r[1:3] for r in up_con.execute(f"PRAGMA table_info({table})")], table   # same names and types
+    up_con.close()
+    rows = con.execute("SELECT pair_id, rows, cols, data FROM matches ORDER BY 1").fetchall()
+    assert rows[0][:3] == (ids[0] * 2147483647 + ids[1], 3, 2)
+    assert np.array_equal(np.frombuffer(rows[0][3], np.uint32).reshape(3, 2), m[:, ::-1])
+    assert rows[1][1:] == (0, 2, b"") or rows[1][1:] == (0, 2, None)          # empty match list: zero rows
+    r = con.execute("SELECT rows, cols, data, config, F, E, H, qvec, tvec FROM two_view_geometries").fetchone()
+    assert r[:2] == (2, 2) and r[3] == 2 and np.array_equal(np.frombuffer(r[2], np.uint32).reshape(2, 2), m[:2])
+    assert np.array_equal(np.frombuffer(r[4]).reshape(3, 3), F) and np.array_equal(np.frombuffer(r[5]).reshape(3, 3), E)
+    assert np.array_equal(np.frombuffer(r[6]).reshape(3, 3), H)
+    assert np.array_equal(np.frombuffer(r[7]), [1, 0, 0, 0]) and np.array_equal(np.frombuffer(r[8]), [0, 0, 0])
+    kr = con.execute("SELECT rows, cols, data FROM keypoints WHERE image_id = ?", (ids[0],)).fetchone()
+    assert kr[:2] == kp2.shape and np.array_equal(np.frombuffer(kr[2], np.float32).reshape(kp2.shape), kp2)
+    con.close()
+    assert "matches" in schema
 
 
 def test_argument_checks_before_any_gpu_work(tmp_path):

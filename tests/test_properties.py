@@ -129,10 +129,7 @@ option_values = st.fixed_dictionaries({}, optional={
 @given(option_values)
 def test_option_dict_round_trip(d):
     import pickle
-    import pycolmap_b200 as pb
     o = nat.TwoViewGeometryOptions(d)
-    p = pb.TwoViewGeometryOptions(d)
-    assert o.todict() == p.todict()                                            # C++ host == Python mirror
     for k, v in d.items():
         if k != "ransac":
             assert getattr(o, k) == v

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import oracle
+import pycolmap_b200 as pb
 from oracle import ransac as R
 from helpers import scenes
 from pycolmap_b200 import synthetic as syn
@@ -24,9 +25,10 @@ def _mask(inl, n):
 def test_planted_scene(ctx, kind, cam, expect, n, noise):
     rng = np.random.default_rng(n + len(kind))
     p1, p2, planted = scenes.two_view_scene(rng, n, 0.3, kind, noise)
-    res, inl = ctx.estimate_two_view_geometry(cam, p1, cam, p2)
+    res = ctx.estimate_two_view_geometry(cam, p1, cam, p2)
+    inl, (nE, nF, nH) = res.inlier_matches, res.num_inliers_EFH
     g = R.estimate_two_view_geometry(cam, p1, cam, p2, seed=3)
-    assert res.config == expect == g.config
+    assert int(res.config) == expect == g.config
     got = _mask(inl, n)
     assert (np.diff(inl[:, 0].astype(np.int64)) > 0).all() and np.array_equal(inl[:, 0], inl[:, 1])
     tol = max(2, int(0.01 * planted.sum()))
@@ -38,24 +40,30 @@ def test_planted_scene(ctx, kind, cam, expect, n, noise):
         # epipolar model, in the reference too): every planted inlier must still be found
         assert (got & planted).sum() >= 0.99 * planted.sum()
         assert (got & ~planted).sum() <= (3 if kind == "general" else max(6, int(0.05 * n)))
-    slack = 1 if kind == "general" else 4     # degenerate F on planes varies run to run upstream as well
-    assert abs(int(res.n_inliers) - len(g.inlier_matches)) <= slack * max(tol, int(0.01 * len(g.inlier_matches))), (
-        res.n_inliers, len(g.inlier_matches), planted.sum())
-    # per-model inlier counts agree with the oracle's LO-RANSAC runs
-    for a, b in ((res.nE, g.nE), (res.nF, g.nF)):
-        assert abs(a - b) <= slack * max(3, int(0.02 * max(a, b))), (res.nE, res.nF, res.nH, g.nE, g.nF, g.nH)
+    # north_star gate: the stored inlier set agrees with the sequential reference within +-1 % (at least 2 matches)
+    assert abs(len(inl) - len(g.inlier_matches)) <= max(tol, int(0.01 * len(g.inlier_matches))), (
+        len(inl), len(g.inlier_matches), planted.sum())
+    # per-model inlier counts of the LO-RANSAC runs.  E (and F on general scenes) are well-posed: +-1 %.  F on a
+    # planar or purely rotating scene is a DEGENERATE estimation problem (a two-parameter family of F fits every
+    # on-plane match exactly, and each member picks up a different handful of the 30 % uniform outliers), so nF
+    # varies by those few outliers between any two sample sequences -- between two runs of the reference as well;
+    # it never decides the outcome there (H wins): bounded by the outlier count that can fit, 5 % of n.
+    assert abs(nE - g.nE) <= max(3, int(0.01 * max(nE, g.nE))), (nE, nF, nH, g.nE, g.nF, g.nH)
+    assert abs(nF - g.nF) <= (max(3, int(0.01 * max(nF, g.nF))) if kind == "general" else max(6, int(0.05 * n))), (
+        nE, nF, nH, g.nE, g.nF, g.nH)
+    assert abs(nH - g.nH) <= max(3, int(0.01 * max(nH, g.nH))) or kind == "general", (nE, nF, nH, g.nE, g.nF, g.nH)
 
 
 def test_degenerate_and_random(ctx):
     rng = np.random.default_rng(1)
     p1, p2, _ = scenes.two_view_scene(rng, 10, 0.0)
-    res, inl = ctx.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)
-    assert res.config == R.DEGENERATE and len(inl) == 0
+    res = ctx.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)
+    assert int(res.config) == R.DEGENERATE and len(res.inlier_matches) == 0
     a, b = rng.uniform(0, 1000, (40, 2)), rng.uniform(0, 1000, (40, 2))
-    res, inl = ctx.estimate_two_view_geometry(scenes.CAM, a, scenes.CAM, b)
-    assert res.config == R.DEGENERATE and len(inl) == 0
-    res, inl = ctx.estimate_two_view_geometry(scenes.CAM, np.zeros((0, 2)), scenes.CAM, np.zeros((0, 2)))
-    assert res.config == R.DEGENERATE
+    res = ctx.estimate_two_view_geometry(scenes.CAM, a, scenes.CAM, b)
+    assert int(res.config) == R.DEGENERATE and len(res.inlier_matches) == 0
+    res = ctx.estimate_two_view_geometry(scenes.CAM, np.zeros((0, 2)), scenes.CAM, np.zeros((0, 2)))
+    assert int(res.config) == R.DEGENERATE
 
 
 def test_matches_argument_and_errors(ctx):
@@ -65,8 +73,9 @@ def test_matches_argument_and_errors(ctx):
     matches = np.stack([np.arange(300), perm], 1).astype(np.uint32)
     p2s = np.empty_like(p2)
     p2s[perm] = p2
-    res, inl = ctx.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2s, matches)
-    assert res.config == R.CALIBRATED and abs(int(res.n_inliers) - planted.sum()) <= 3
+    res = ctx.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2s, matches)
+    inl = res.inlier_matches
+    assert int(res.config) == R.CALIBRATED and abs(len(inl) - planted.sum()) <= 3
     assert all(perm[a] == b for a, b in inl)
     with pytest.raises(ValueError):
         ctx.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2[:10])          # identity needs equal sizes
@@ -79,28 +88,36 @@ def test_watermark(ctx):
     n = 200
     p1 = np.c_[rng.uniform(0, 1600, n), rng.uniform(0, 100, n)]
     p2 = p1 + [7.0, 3.0]
-    res, _ = ctx.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)
-    assert res.config == R.WATERMARK
-    res, _ = ctx.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2, opts=ctx.tvg_opts(detect_watermark=0))
-    assert res.config == R.PLANAR_OR_PANORAMIC
+    res = ctx.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2)
+    assert int(res.config) == R.WATERMARK
+    res = ctx.estimate_two_view_geometry(scenes.CAM, p1, scenes.CAM, p2, options={"detect_watermark": False})
+    assert int(res.config) == R.PLANAR_OR_PANORAMIC
+    # DetectWatermark fits the translation to ALL inliers: a border strip that moves rigidly plus as many interior
+    # matches of a different motion is no watermark (the translation explains < 70 % of the inliers)
+    q1 = np.c_[rng.uniform(200, 1400, n), rng.uniform(300, 900, n)]
+    H = np.array([[1.02, 0.01, 5.0], [-0.01, 0.98, -3.0], [1e-5, -2e-5, 1.0]])
+    q2h = np.c_[q1, np.ones(n)] @ H.T
+    both1, both2 = np.concatenate([p1[:60], q1]), np.concatenate([p2[:60], q2h[:, :2] / q2h[:, 2:]])
+    res = ctx.estimate_two_view_geometry(scenes.CAM, both1, scenes.CAM, both2)
+    assert int(res.config) != R.WATERMARK
 
 
 def test_single_model_estimators(ctx):
     rng = np.random.default_rng(6)
     p1, p2, planted = scenes.two_view_scene(rng, 500, 0.3, "general")
-    r = ctx.ransac_model(1, p1, p2)
+    tvg_ransac = {"max_error": 4.0, "min_inlier_ratio": 0.25, "confidence": 0.999, "min_num_trials": 100, "max_num_trials": 10000}
+    r = pb.fundamental_matrix_estimation(p1, p2, tvg_ransac)
     assert r is not None and abs(r["num_inliers"] - planted.sum()) <= 5
     assert (r["inliers"] & planted).sum() >= 0.99 * planted.sum()
-    assert (ctx.squared_sampson_error(p1[planted], p2[planted], r["model"]) < 16.0 + 1e-9).mean() > 0.99
-    n1, n2 = R.cam_from_img(scenes.CAM, p1), R.cam_from_img(scenes.CAM, p2)
-    r = ctx.ransac_model(0, n1, n2, ctx.ransac_opts(max_error=4.0 / 1200))
+    assert (pb.squared_sampson_error(p1[planted], p2[planted], r["F"]) < 16.0 + 1e-9).mean() > 0.99
+    r = pb.essential_matrix_estimation(p1, p2, scenes.CAM, scenes.CAM, tvg_ransac)     # normalises with CamFromImg itself
     assert r is not None and abs(r["num_inliers"] - planted.sum()) <= 5
     q1, q2, pl = scenes.two_view_scene(rng, 500, 0.4, "planar")
-    r = ctx.ransac_model(2, q1, q2)
+    r = pb.homography_matrix_estimation(q1, q2, tvg_ransac)
     assert r is not None and abs(r["num_inliers"] - pl.sum()) <= 5
-    assert ctx.ransac_model(2, q1[:3], q2[:3]) is None          # fewer than the minimal sample -> None
+    assert pb.homography_matrix_estimation(q1[:3], q2[:3]) is None          # fewer than the minimal sample -> None
     E = rng.normal(size=(3, 3))
-    assert np.allclose(ctx.squared_sampson_error(p1, p2, E), R.squared_sampson_error(p1, p2, E), rtol=1e-12)
+    assert np.allclose(pb.squared_sampson_error(p1, p2, E), R.squared_sampson_error(p1, p2, E), rtol=1e-12)
 
 
 def test_pipeline_match_and_verify(ctx):
@@ -112,14 +129,14 @@ def test_pipeline_match_and_verify(ctx):
     cams = scene["cameras"]
     ctx.set_images(descs, kpts, cams)
     pairs = syn.exhaustive_pairs(16)
-    res = ctx.match_pairs(pairs, tvg=ctx.tvg_opts())
+    res = ctx.match_pairs(pairs, verification_options=pb.TwoViewGeometryOptions())
     want = oracle.fast_match_pairs(np.concatenate(descs), [len(d) for d in descs], pairs)
     n_verified = n_checked = 0
     for k, (i, j) in enumerate(pairs):
-        v = res.view(k)
+        v = res.two_view_geometry(k)
         raw = want[k]
         if len(raw) < 15:
-            assert v.n_matches == 0 and v.config == R.UNDEFINED and v.n_inliers == 0
+            assert len(res.matches(k)) == 0 and int(v.config) == R.UNDEFINED and len(v.inlier_matches) == 0
             continue
         assert np.array_equal(res.matches(k), raw)
         n_verified += 1
@@ -128,8 +145,8 @@ def test_pipeline_match_and_verify(ctx):
             g = R.estimate_two_view_geometry(cams[i], kpts[i].astype(np.float64), cams[j],
                                              kpts[j].astype(np.float64), raw, seed=k)
             exp_cfg = g.config if len(g.inlier_matches) >= 15 else R.UNDEFINED
-            assert v.config == exp_cfg, (k, v.config, g.config)
-            assert abs(int(v.n_inliers) - (len(g.inlier_matches) if exp_cfg else 0)) <= max(
+            assert int(v.config) == exp_cfg, (k, v.config, g.config)
+            assert abs(len(v.inlier_matches) - (len(g.inlier_matches) if exp_cfg else 0)) <= max(
                 2, int(0.01 * len(g.inlier_matches)))
             inl = res.inlier_matches(k)
             rawset = {tuple(x) for x in raw.tolist()}
@@ -146,15 +163,15 @@ def test_guided_matching_replaces_inliers(ctx):
     kpts = [k.numpy() for k in scene["kpts"]]
     ctx.set_images(descs, kpts, scene["cameras"])
     pairs = syn.exhaustive_pairs(10)
-    plain = ctx.match_pairs(pairs, tvg=ctx.tvg_opts())
-    guided = ctx.match_pairs(pairs, sift=ctx.sift_opts(guided_matching=1), tvg=ctx.tvg_opts())
+    plain = ctx.match_pairs(pairs, verification_options=pb.TwoViewGeometryOptions())
+    guided = ctx.match_pairs(pairs, {"guided_matching": True}, pb.TwoViewGeometryOptions())
     n_guided = 0
     for k, (i, j) in enumerate(pairs):
-        vp, vg = plain.view(k), guided.view(k)
+        vp, vg = plain.two_view_geometry(k), guided.two_view_geometry(k)
         assert np.array_equal(plain.matches(k), guided.matches(k))          # raw matches are untouched
-        if vp.config in (R.CALIBRATED, R.UNCALIBRATED, R.PLANAR_OR_PANORAMIC) and vp.n_inliers >= 15:
+        if int(vp.config) in (R.CALIBRATED, R.UNCALIBRATED, R.PLANAR_OR_PANORAMIC) and len(vp.inlier_matches) >= 15:
             assert vg.config == vp.config
-            kind = 1 if vp.config == R.PLANAR_OR_PANORAMIC else 0
+            kind = 1 if int(vp.config) == R.PLANAR_OR_PANORAMIC else 0
             model = np.array(vg.H if kind else vg.F).reshape(3, 3)
             want = oracle.match_guided(descs[i], kpts[i], descs[j], kpts[j], kind, model, 4.0)
             got = guided.inlier_matches(k)
@@ -162,7 +179,7 @@ def test_guided_matching_replaces_inliers(ctx):
                 assert np.array_equal(got, want), (k, len(got), len(want))
                 n_guided += 1
                 # the geometric filter removes ambiguous second-best candidates: never fewer than ~the inliers
-                assert len(got) >= 0.9 * vp.n_inliers
+                assert len(got) >= 0.9 * len(vp.inlier_matches)
         else:
-            assert vg.n_inliers == vp.n_inliers
+            assert len(vg.inlier_matches) == len(vp.inlier_matches)
     assert n_guided >= 5

@@ -55,16 +55,19 @@ def test_pose_golden_oracle_and_host_header(ph):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("model", MODELS)
-def test_gpu_cam_from_img_reproduces_golden(ctx, model):
+def test_gpu_cam_from_img_reproduces_golden(model):
+    import pycolmap_b200 as pb
     cam = dict(model=model, width=1600, height=1200, params=G[f"cam{model}_params"].tolist())
-    assert np.abs(ctx.cam_from_img(cam, G[f"cam{model}_px"]) - G[f"cam{model}_norm"]).max() < 1e-9
+    assert np.abs(pb.cam_from_img(cam, G[f"cam{model}_px"]) - G[f"cam{model}_norm"]).max() < 1e-9
 
 
 @pytest.mark.gpu
-def test_gpu_pose_reproduces_golden(ctx):
+def test_gpu_pose_reproduces_golden():
+    import pycolmap_b200 as pb
     cam = dict(model=0, width=2, height=2, params=[1.0, 0.0, 0.0])           # identity calibration: points are normalised
     idx = np.arange(len(G["pose_x1"]), dtype=np.uint32)
-    g = ctx.estimate_two_view_geometry_pose(cam, G["pose_x1"], cam, G["pose_x2"], 2, G["pose_E"], np.zeros((3, 3)),
-                                            np.stack([idx, idx], 1))
-    assert g.pose_valid == 1 and np.allclose(list(g.qvec), G["pose_q"], atol=1e-9)
-    assert np.allclose(list(g.tvec), G["pose_t"], atol=1e-9) and abs(g.tri_angle - float(G["pose_tri"])) < 1e-9
+    g = pb.TwoViewGeometry("CALIBRATED", E=G["pose_E"], inlier_matches=np.stack([idx, idx], 1))
+    assert pb.estimate_two_view_geometry_pose(cam, G["pose_x1"], cam, G["pose_x2"], g) is True
+    q = g.cam2_from_cam1.rotation.quat                                       # (x, y, z, w); the fixture holds (w, x, y, z)
+    assert np.allclose([q[3], q[0], q[1], q[2]], G["pose_q"], atol=1e-9)
+    assert np.allclose(g.cam2_from_cam1.translation, G["pose_t"], atol=1e-9) and abs(g.tri_angle - float(G["pose_tri"])) < 1e-9

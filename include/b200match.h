@@ -329,6 +329,12 @@ enum b2m_k1_dir1_mode {
   B2M_K1_DIR1_FULL_NOMEM = 5     /* no memory for the comparison buffers */
 };
 
+/* The verifier's 5-point essential-matrix solver (one warp per hypothesis, csrc/five_point_warp.cuh) on
+ * caller-provided 4-D null spaces: nullspaces [n][4][9], models [n][10][9] (E = x N0 + y N1 + z N2 + N3 for every
+ * real solution), n_models [n].  Exists so that tests can hold the device solver against the serial solver of
+ * csrc/geom.h compiled for the host (U:estimators/essential_matrix.cc EssentialMatrixFivePointEstimator). */
+int b2m_debug_five_point(b2m_ctx* ctx, const double* nullspaces, int64_t n, double* models, int32_t* n_models);
+
 typedef struct b2m_stats {
   uint32_t struct_size;
   uint32_t reserved;

@@ -191,7 +191,10 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
 
   const int B = ctx->pair_batch;
   // rows are handed out in 512-row cluster blocks: keep the per-pair stride a multiple of that
-  if (int rc = ensure_workspace(ctx, B, round_up(S.max_feat_pad, 512))) return bail(rc);
+  // sized for the pairs of this call, not for a full batch: a context that only ever sees small jobs stays small
+  if (int rc = ensure_workspace(ctx, static_cast<int>(std::min<int64_t>(B, std::max<int64_t>(n_pairs, 1))),
+                                round_up(S.max_feat_pad, 512)))
+    return bail(rc);
   if (tvg)
     if (int rc = verify_prepare(ctx, S, ctx->ws.batch, static_cast<int64_t>(ctx->ws.batch) * ctx->ws.mstride))
       return bail(rc);

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "geom.h"
+#include "five_point_warp.cuh"
 #include "pose.h"
 #include "verify.cuh"
 
@@ -71,6 +72,7 @@ struct VerifyParams {
   int32_t force_calibrated;   // stand-alone: -1 use camera flags
   unsigned long long* prof;   // optional [3][8] cycle counters (B2M_PROF=1), else nullptr
   unsigned long long* counters;  // [6] models scored / residual evaluations per kind (b2m_stats), or nullptr
+  double* e_scratch;          // E kernel: [nb][kRansacThreads][90] null spaces, then the <= 10 models of every hypothesis
   // guided matching hand-over (written by the decision kernel when guided_min_inliers >= 0)
   int32_t* guided_kind;       // [nb] -1 / 0 (F) / 1 (H)
   float* guided_model;        // [nb][9]
@@ -193,6 +195,50 @@ __device__ __forceinline__ void warp_score(const double* M, const double4* pts, 
   sum = warp_sum_d(s);
 }
 
+// Hypothesis scoring of one block of points: every thread keeps PPT matches (fp32) in registers and sweeps the
+// chunk's models: division-free fp32 test, fp64 only for the borderline points of a (thread, model).  Inlier counts
+// go to sh.chunk_cnt.
+template <int KIND, int PPT>
+__device__ __forceinline__ void score_block(Shared& sh, const double4* pts, int64_t off, const PointXform& X, int n, int pb,
+                                            int n_chunk, double thr, float thr_f, int tid) {
+  float px1[PPT], py1[PPT], px2[PPT], py2[PPT];
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    const int i = pb + q * kRansacThreads + tid;
+    // slots past the end get a far-away point: a clear outlier for every finite model
+    double x1 = 0, y1 = 0, x2 = 1e15, y2 = 1e15;
+    if (i < n) load_pt(pts, off + i, X, x1, y1, x2, y2);
+    px1[q] = static_cast<float>(x1); py1[q] = static_cast<float>(y1);
+    px2[q] = static_cast<float>(x2); py2[q] = static_cast<float>(y2);
+  }
+  for (int m = 0; m < n_chunk; ++m) {
+    float Mf[12];
+    const float4* mp = reinterpret_cast<const float4*>(sh.chunk_f[m]);
+    const float4 m0 = mp[0], m1 = mp[1], m2 = mp[2];
+    Mf[0] = m0.x; Mf[1] = m0.y; Mf[2] = m0.z; Mf[3] = m0.w;
+    Mf[4] = m1.x; Mf[5] = m1.y; Mf[6] = m1.z; Mf[7] = m1.w; Mf[8] = m2.x;
+    int c = 0, flags = 0;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const int f = inlier_f32<KIND>(Mf, px1[q], py1[q], px2[q], py2[q], thr_f);
+      c += f & 1;
+      flags |= f;
+    }
+    if (flags & 2) {  // rare: a borderline point -> redo this thread's points of this model in fp64
+      c = 0;
+      for (int q = 0; q < PPT; ++q) {
+        const int i = pb + q * kRansacThreads + tid;
+        if (i < n) {
+          double x1, y1, x2, y2;
+          load_pt(pts, off + i, X, x1, y1, x2, y2);
+          c += (residual<KIND>(sh.chunk_d[m], x1, y1, x2, y2) <= thr) ? 1 : 0;
+        }
+      }
+    }
+    if (c) atomicAdd(&sh.chunk_cnt[m], c);  // most hypotheses have (almost) no inliers: cheaper than a warp reduce
+  }
+}
+
 #define B2M_TICK(slot)                                   \
   do {                                                   \
     if (P.prof && tid == 0) {                            \
@@ -234,12 +280,19 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
 
   int trials = 0;
   unsigned long long n_scored = 0;  // models whose residuals were evaluated over all n matches (thread 0 keeps the tally)
-  double mdl[T::kMaxModels * 9];
+  // models of this thread's hypothesis: registers / local memory for F and H, the CTA's slice of the global scratch
+  // for E (written by the warp-cooperative solver)
+  double mdl_local[KIND == 0 ? 1 : T::kMaxModels * 9];
+  double* const e_models = KIND == 0 ? P.e_scratch + (static_cast<size_t>(pair) * kRansacThreads + tid) * 90 : nullptr;
+  double* const mdl = KIND == 0 ? e_models : mdl_local;
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long prof_t = clock64();
   while (trials < max_trials) {
     int nb = min(kRansacThreads, max_trials - trials);
     if (trials < ro.min_num_trials) nb = min(nb, ro.min_num_trials - trials);
+    // past min_num_trials the sequential reference stops at the FIRST trial >= dyn_max: a round never needs more
+    // hypotheses than are missing to that bound (a better model found among them only lowers it)
+    else if (dyn_max - trials < nb) nb = max(1, static_cast<int>(ceil(dyn_max - trials)));
     // ---- phase 1: one minimal-sample hypothesis per thread
     int nm = 0;
     if (tid < nb) {
@@ -258,9 +311,36 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       }
       double x1[T::kMin], y1[T::kMin], x2[T::kMin], y2[T::kMin];
       for (int j = 0; j < T::kMin; ++j) load_pt(pts, off + idx[j], X, x1[j], y1[j], x2[j], y2[j]);
-      if (KIND == 0) nm = minimal_E5(x1, y1, x2, y2, mdl);
+      if (KIND == 0) {
+        // thread = hypothesis only for the (small) 5 x 9 null space; the elimination + root finding that follow
+        // run one warp per hypothesis (five_point_warp.cuh)
+        double A[45], Nb[36];
+        for (int i = 0; i < 5; ++i) epipolar_row(x1[i], y1[i], x2[i], y2[i], A + 9 * i);
+        nm = nullspace_gauss<5>(A, Nb) ? 1 : 0;
+        if (nm)
+          for (int k = 0; k < 36; ++k) e_models[k] = Nb[k];
+      }
       if (KIND == 1) nm = minimal_F7(x1, y1, x2, y2, mdl);
       if (KIND == 2) nm = minimal_H4_closed(x1, y1, x2, y2, mdl);
+    }
+    if (KIND == 0) {
+      sh.scan[tid] = nm;
+      __syncthreads();
+      fpw::Scratch& WS = reinterpret_cast<fpw::Scratch*>(sh.chunk_d)[warp];   // chunk_d is idle outside the scoring loop
+      for (int h = warp; h < nb; h += kRansacThreads / 32) {
+        int cnt = 0;
+        if (sh.scan[h]) {   // uniform in the warp
+          double* hm = P.e_scratch + (static_cast<size_t>(pair) * kRansacThreads + h) * 90;
+          for (int k = lane; k < 36; k += 32) WS.N[k] = hm[k];
+          __syncwarp();
+          cnt = fpw::five_point_warp(WS, hm, lane);
+        }
+        __syncwarp();
+        if (lane == 0) sh.scan[h] = cnt;
+      }
+      __syncthreads();
+      nm = tid < nb ? sh.scan[tid] : 0;
+      __syncthreads();
     }
     // ---- phase 2: score every model of every hypothesis of this warp (warp = one model at a time)
     B2M_TICK(0);
@@ -295,42 +375,12 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       for (int m = tid; m < kChunkModels; m += kRansacThreads) sh.chunk_cnt[m] = 0;
       __syncthreads();
       for (int pb = 0; pb < n; pb += kRansacThreads * kPtsPerThread) {
-        float px1[kPtsPerThread], py1[kPtsPerThread], px2[kPtsPerThread], py2[kPtsPerThread];
-#pragma unroll
-        for (int q = 0; q < kPtsPerThread; ++q) {
-          const int i = pb + q * kRansacThreads + tid;
-          // slots past the end get a far-away point: a clear outlier for every finite model
-          double x1 = 0, y1 = 0, x2 = 1e15, y2 = 1e15;
-          if (i < n) load_pt(pts, off + i, X, x1, y1, x2, y2);
-          px1[q] = static_cast<float>(x1); py1[q] = static_cast<float>(y1);
-          px2[q] = static_cast<float>(x2); py2[q] = static_cast<float>(y2);
-        }
-        for (int m = 0; m < n_chunk; ++m) {
-          float Mf[12];
-          const float4* mp = reinterpret_cast<const float4*>(sh.chunk_f[m]);
-          const float4 m0 = mp[0], m1 = mp[1], m2 = mp[2];
-          Mf[0] = m0.x; Mf[1] = m0.y; Mf[2] = m0.z; Mf[3] = m0.w;
-          Mf[4] = m1.x; Mf[5] = m1.y; Mf[6] = m1.z; Mf[7] = m1.w; Mf[8] = m2.x;
-          int c = 0, flags = 0;
-#pragma unroll
-          for (int q = 0; q < kPtsPerThread; ++q) {
-            const int f = inlier_f32<KIND>(Mf, px1[q], py1[q], px2[q], py2[q], thr_f);
-            c += f & 1;
-            flags |= f;
-          }
-          if (flags & 2) {  // rare: a borderline point -> redo this thread's points of this model in fp64
-            c = 0;
-            for (int q = 0; q < kPtsPerThread; ++q) {
-              const int i = pb + q * kRansacThreads + tid;
-              if (i < n) {
-                double x1, y1, x2, y2;
-                load_pt(pts, off + i, X, x1, y1, x2, y2);
-                c += (residual<KIND>(sh.chunk_d[m], x1, y1, x2, y2) <= thr) ? 1 : 0;
-              }
-            }
-          }
-          if (c) atomicAdd(&sh.chunk_cnt[m], c);  // most hypotheses have (almost) no inliers: cheaper than a warp reduce
-        }
+        // the last block takes as few point slots per thread as cover it (a slot past the end costs a full test)
+        const int rem = n - pb;
+        if (rem > 4 * kRansacThreads) score_block<KIND, 8>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
+        else if (rem > 2 * kRansacThreads) score_block<KIND, 4>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
+        else if (rem > kRansacThreads) score_block<KIND, 2>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
+        else score_block<KIND, 1>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
       }
       __syncthreads();
       for (int m = 0; m < nm; ++m) {
@@ -467,14 +517,14 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
             for (int k = 0; k < 45; ++k) St[k] = sh.red[0][k] + sh.red[1][k] + sh.red[2][k] + sh.red[3][k];
             int nc = 0;
             if (KIND == 0) {
-              // least-squares 4-D null space of the N x 9 system.  five_point_from_nullspace fixes the
-              // coefficient of its LAST basis vector to 1, so that one must be the smallest singular
-              // vector (for noise-free inliers it IS the essential matrix).
-              double Nr[36], N[36];
+              // least-squares 4-D null space of the N x 9 system.  The 5-point solver fixes the coefficient of its
+              // LAST basis vector to 1, so that one must be the smallest singular vector (for noise-free inliers it
+              // IS the essential matrix).  The solver itself runs on warp 0 below.
+              double Nr[36];
               smallest_eigvecs_invit<4>(St, Nr);
+              fpw::Scratch& WS = reinterpret_cast<fpw::Scratch*>(sh.chunk_d)[0];
               for (int k = 0; k < 4; ++k)
-                for (int e = 0; e < 9; ++e) N[k * 9 + e] = Nr[(3 - k) * 9 + e];
-              nc = five_point_from_nullspace(N, sh.cand_models);
+                for (int e = 0; e < 9; ++e) WS.N[k * 9 + e] = Nr[(3 - k) * 9 + e];
             } else if (KIND == 1) {
               nc = finish_F8(St, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
             } else {
@@ -483,6 +533,13 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
             sh.n_cand = nc;
           }
           __syncthreads();
+          if (KIND == 0) {
+            if (warp == 0) {
+              const int nc = fpw::five_point_warp(reinterpret_cast<fpw::Scratch*>(sh.chunk_d)[0], sh.cand_models, lane);
+              if (lane == 0) sh.n_cand = nc;
+            }
+            __syncthreads();
+          }
           B2M_TICK(4);
           const int nc = sh.n_cand;
           n_scored += nc + (KIND != 0 ? 2 : 1);  // LO candidates + the inlier passes (moments, normal equations)
@@ -1082,6 +1139,7 @@ struct VerifyState {
   int32_t* h_pose_valid[2] = {nullptr, nullptr};
   double* d_angles = nullptr;                    // [arena_cap] triangulation-angle scratch
   bool pose_on[2] = {false, false};
+  double* d_e_scratch = nullptr;                 // E kernel: [batch][128][90] null spaces / models (five_point_warp.cuh)
   DevDistortion* d_dist = nullptr;               // per image, only when any_distorted
   double4* d_pts_undist[2] = {nullptr, nullptr}; // E-kernel input per slot, lazily allocated
   bool any_distorted = false;
@@ -1104,6 +1162,8 @@ struct VerifyState {
     }
     cudaFree(d_angles);
     d_angles = nullptr;
+    cudaFree(d_e_scratch);
+    d_e_scratch = nullptr;
     cudaFree(d_dist); cudaFree(d_pts_undist[0]); cudaFree(d_pts_undist[1]);
     d_dist = nullptr; d_pts_undist[0] = d_pts_undist[1] = nullptr; any_distorted = false;
     cudaFree(d_guided_kind); cudaFree(d_guided_model);
@@ -1191,6 +1251,7 @@ int ensure_verify_ws(b2m_ctx* ctx, int batch, int64_t arena_cap) {
     V_TRY(ctx, cudaMallocHost(&V->h_inliers[s], sizeof(uint2) * arena_cap));
   }
   V_TRY(ctx, cudaMalloc(&V->d_mask, 3 * arena_cap));
+  V_TRY(ctx, cudaMalloc(&V->d_e_scratch, sizeof(double) * 90 * kRansacThreads * static_cast<size_t>(batch)));
   V_TRY(ctx, cudaMalloc(&V->d_sup, sizeof(int32_t) * 3 * batch));
   V_TRY(ctx, cudaMalloc(&V->d_success, sizeof(int32_t) * 3 * batch));
   V->batch = batch;
@@ -1310,6 +1371,7 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
   }
   P.prof = V->d_prof;
   P.counters = verify_counters(ctx);
+  P.e_scratch = V->d_e_scratch;
   if (!V->rs.side[0]) {
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[0], cudaStreamNonBlocking));
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[1], cudaStreamNonBlocking));
@@ -1477,13 +1539,14 @@ struct Single {
   double* d_models = nullptr;
   DevDistortion* d_dist = nullptr;  // only when a camera has distortion
   double4* d_pts_undist = nullptr;
+  double* d_e_scratch = nullptr;    // E kernel scratch, [problems][128][90]
   // compute_relative_pose
   double *d_p1 = nullptr, *d_p2 = nullptr, *d_angles = nullptr, *d_pose = nullptr;
   int64_t *d_p1_off = nullptr, *d_p2_off = nullptr;
   int32_t* d_pose_valid = nullptr;
   ~Single() {
     cudaFree(d_pts); cudaFree(d_matches); cudaFree(d_inliers); cudaFree(d_mask); cudaFree(d_cams);
-    cudaFree(d_i32); cudaFree(d_off); cudaFree(d_models); cudaFree(d_dist); cudaFree(d_pts_undist);
+    cudaFree(d_i32); cudaFree(d_off); cudaFree(d_models); cudaFree(d_dist); cudaFree(d_pts_undist); cudaFree(d_e_scratch);
     cudaFree(d_p1); cudaFree(d_p2); cudaFree(d_angles); cudaFree(d_pose); cudaFree(d_p1_off); cudaFree(d_p2_off);
     cudaFree(d_pose_valid);
   }
@@ -1587,6 +1650,7 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   V_TRY(ctx, cudaMalloc(&G.d_i32, sizeof(int32_t) * 16));
   V_TRY(ctx, cudaMalloc(&G.d_off, sizeof(int64_t)));
   V_TRY(ctx, cudaMalloc(&G.d_models, sizeof(double) * 27));
+  V_TRY(ctx, cudaMalloc(&G.d_e_scratch, sizeof(double) * 90 * kRansacThreads));
   const int32_t i32[16] = {0, 1, static_cast<int32_t>(m), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const int64_t off0 = 0;
   cudaStream_t st = ctx->stream;
@@ -1617,6 +1681,7 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   P.seed = ctx->seed;
   P.single_kind = single_kind;
   P.counters = verify_counters(ctx);
+  P.e_scratch = G.d_e_scratch;
   if (single_kind >= 0) {
     V_TRY(ctx, launch_ransac(P, 1, st));
   } else {
@@ -1637,6 +1702,19 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   V_TRY(ctx, cudaGetLastError());
   ctx->stats.kernel_launches += 1;
   return B2M_OK;
+}
+
+// Instrumentation: the warp-cooperative 5-point solver on caller-provided null spaces, one warp each.
+__global__ void __launch_bounds__(128) b2m_five_point_kernel(const double* __restrict__ nullspaces, int64_t n,
+                                                             double* __restrict__ models, int32_t* __restrict__ counts) {
+  __shared__ fpw::Scratch ws[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t h = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  if (h >= n) return;
+  for (int k = lane; k < 36; k += 32) ws[warp].N[k] = nullspaces[h * 36 + k];
+  __syncwarp();
+  const int cnt = fpw::five_point_warp(ws[warp], models + h * 90, lane);
+  if (lane == 0) counts[h] = cnt;
 }
 
 __global__ void b2m_sampson_kernel(const double* p1, const double* p2, int64_t m, const double* E, double* out) {
@@ -1878,6 +1956,7 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     V_TRY(ctx, cudaMalloc(&G.d_i32, sizeof(int32_t) * 11 * nb));
     V_TRY(ctx, cudaMalloc(&G.d_off, sizeof(int64_t) * nb));
     V_TRY(ctx, cudaMalloc(&G.d_models, sizeof(double) * 27 * nb));
+    V_TRY(ctx, cudaMalloc(&G.d_e_scratch, sizeof(double) * 90 * kRansacThreads * static_cast<size_t>(nb)));
     d_i32 = G.d_i32;
     if (total > 0) {
       V_TRY(ctx, cudaMemcpyAsync(G.d_pts, pts.data(), sizeof(double4) * total, cudaMemcpyHostToDevice, st));
@@ -1908,6 +1987,7 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     P.seed = ctx->seed;
     P.single_kind = -1;
     P.counters = verify_counters(ctx);
+    P.e_scratch = G.d_e_scratch;
     const double4* pts_E = nullptr;
     if (int rc = undistort_for_E(ctx, G, P, full_cams.data(), 2 * nb, nb, cap, st, &pts_E)) return rc;
     V_TRY(ctx, launch_ransac(P, nb, st, nullptr, pts_E));
@@ -2066,6 +2146,40 @@ int b2m_estimate_two_view_geometry_pose(b2m_ctx* ctx, const b2m_camera* cam1, co
     geometry->pose_valid = 1;
   }
   return B2M_OK;
+}
+
+int b2m_debug_five_point(b2m_ctx* ctx, const double* nullspaces, int64_t n, double* models, int32_t* n_models) {
+  if (!ctx) return B2M_EINVAL;
+  if (n < 0 || (n > 0 && (!nullspaces || !models || !n_models))) {
+    ctx->err = "[verify.cu] Check Failed: nullspaces, models, n_models != NULL";
+    return B2M_EINVAL;
+  }
+  if (n == 0) return B2M_OK;
+  cudaSetDevice(ctx->device);
+  double *d_n = nullptr, *d_m = nullptr;
+  int32_t* d_c = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_n); cudaFree(d_m); cudaFree(d_c);
+  };
+  if (cudaMalloc(&d_n, sizeof(double) * 36 * n) != cudaSuccess || cudaMalloc(&d_m, sizeof(double) * 90 * n) != cudaSuccess ||
+      cudaMalloc(&d_c, sizeof(int32_t) * n) != cudaSuccess) {
+    cleanup();
+    ctx->err = "[verify.cu] cudaMalloc failed";
+    return B2M_ENOMEM;
+  }
+  cudaMemcpyAsync(d_n, nullspaces, sizeof(double) * 36 * n, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemsetAsync(d_m, 0, sizeof(double) * 90 * n, ctx->stream);
+  b2m_five_point_kernel<<<static_cast<unsigned>((n + 3) / 4), 128, 0, ctx->stream>>>(d_n, n, d_m, d_c);
+  ctx->stats.kernel_launches += 1;
+  cudaMemcpyAsync(models, d_m, sizeof(double) * 90 * n, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaMemcpyAsync(n_models, d_c, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+  int rc = B2M_OK;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = std::string("[verify.cu] CUDA error: ") + cudaGetErrorString(cudaGetLastError());
+    rc = B2M_ECUDA;
+  }
+  cleanup();
+  return rc;
 }
 
 int b2m_cam_from_img(b2m_ctx* ctx, const b2m_camera* camera, const double* points, int64_t n, double* out) {

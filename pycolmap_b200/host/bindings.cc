@@ -1141,6 +1141,17 @@ PYBIND11_MODULE(_core, m) {
            },
            "camera1"_a, "points1"_a, "camera2"_a, "points2"_a, "matches"_a = py::none(),
            "options"_a = TwoViewGeometryOptions())
+      .def("debug_five_point",
+           [](CoreContext& c, const ArrD& nullspaces) {
+             if (nullspaces.size() % 36) throw std::invalid_argument("[bindings.cc] Check Failed: null spaces are n x 4 x 9");
+             const int64_t n = nullspaces.size() / 36;
+             ArrD models(std::vector<py::ssize_t>{static_cast<py::ssize_t>(n), 10, 9});
+             py::array_t<int32_t> counts(static_cast<py::ssize_t>(n));
+             ThrowOnError(c.Handle(), b2m_debug_five_point(c.Handle(), nullspaces.data(), n, models.mutable_data(),
+                                                           counts.mutable_data()));
+             return py::make_tuple(models, counts);
+           },
+           "nullspaces"_a, "The device 5-point solver (one warp per 4-D null space): (models [n, 10, 9], counts [n])")
       .def("stats", [](CoreContext& c) {
         b2m_stats s;
         memset(&s, 0, sizeof(s));

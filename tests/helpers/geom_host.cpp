@@ -21,6 +21,12 @@ int gh_estimate_F8(const double* x1, const double* y1, const double* x2, const d
 int gh_estimate_H(const double* x1, const double* y1, const double* x2, const double* y2, int n, double* model) {
   return estimate_H(x1, y1, x2, y2, n, model);
 }
+int gh_five_point_from_nullspace(const double* N, double* models) { return five_point_from_nullspace(N, models); }
+int gh_nullspace5(const double* x1, const double* y1, const double* x2, const double* y2, double* N) {
+  double A[45];
+  for (int i = 0; i < 5; ++i) epipolar_row(x1[i], y1[i], x2[i], y2[i], A + 9 * i);
+  return nullspace_gauss<5>(A, N) ? 1 : 0;
+}
 int gh_minimal_E5(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_E5(x1, y1, x2, y2, m); }
 int gh_minimal_F7(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_F7(x1, y1, x2, y2, m); }
 int gh_minimal_H4(const double* x1, const double* y1, const double* x2, const double* y2, double* m) { return minimal_H4(x1, y1, x2, y2, m); }

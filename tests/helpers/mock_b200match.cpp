@@ -347,6 +347,10 @@ int b2m_ransac_model(b2m_ctx*, int32_t, const double*, const double*, int64_t, c
   *ok = 0;
   return B2M_OK;
 }
+int b2m_debug_five_point(b2m_ctx* ctx, const double*, int64_t, double*, int32_t*) {
+  ctx->err = "mock: no solver";
+  return B2M_ESTATE;
+}
 int b2m_cam_from_img(b2m_ctx*, const b2m_camera*, const double* p, int64_t n, double* out) {
   memcpy(out, p, sizeof(double) * 2 * n);
   return B2M_OK;

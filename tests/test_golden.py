@@ -28,5 +28,4 @@ def test_oracle_guided_reproduces_golden():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,tag,kw", CASES)
 def test_gpu_reproduces_golden(ctx, name, tag, kw):
-    opts = ctx.sift_opts(**{k: (int(v) if isinstance(v, bool) else v) for k, v in kw.items()})
-    assert np.array_equal(ctx.match_pair(G[f"{name}_d1"], G[f"{name}_d2"], opts), G[f"{name}_{tag}"])
+    assert np.array_equal(ctx.match_pair(G[f"{name}_d1"], G[f"{name}_d2"], dict(kw)), G[f"{name}_{tag}"])

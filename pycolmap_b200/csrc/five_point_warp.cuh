@@ -84,9 +84,17 @@ __device__ inline int real_roots_warp(Scratch& S, int lane) {
   int deg = 10;
   while (deg > 0 && fabs(c[deg]) <= 1e-14 * mx) --deg;
   if (deg == 0) return 0;
-  double bound = 0.0;
-  for (int i = 0; i < deg; ++i) bound = fmax(bound, fabs(c[i] / c[deg]));
-  bound += 1.0;
+  double bound = 0.0;   // Fujiwara's bound, as geom.h (poly_real_roots): one term per lane
+  {
+    double t = 0.0;
+    if (lane < deg) {
+      const double v = fabs(c[lane] / c[deg]);
+      if (v > 0.0) t = pow(v, 1.0 / static_cast<double>(deg - lane));
+    }
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    bound = 2.0 * t * (1.0 + 1e-9);
+    if (!(bound > 0.0)) bound = 1.0;
+  }
   // derivative ladder: d[k][i] = c[i + k] (i + k)(i + k - 1)...(i + 1), factors applied in that order (as geom.h does)
   for (int e = lane; e < 110; e += 32) {
     const int k = e / 11, i = e % 11;

@@ -54,6 +54,14 @@ struct Workspace {
   int32_t* d_cand_rows = nullptr;  // K1 v2: [batch][2][mstride]
   int32_t* d_cand_sorted = nullptr;
   int32_t* d_pairs_dir1 = nullptr; // [batch][2] swapped / dummy pairs of launch_k1_filter_skip
+  // gathered column direction (launch_k1_filter_gather), allocated on first use
+  uint8_t* d_gath_desc = nullptr;  // [batch x mstride x 128]
+  int32_t* d_colrank = nullptr;    // [batch][mstride]
+  int32_t* d_gath_cols = nullptr;  // [batch][mstride]
+  int32_t* d_gath_cnt = nullptr;   // [batch]
+  int32_t* d_gath_items = nullptr; // [batch x mstride / 256][2]
+  int32_t* d_gath_n = nullptr;     // [1]
+  CUtensorMap tmap_gath{};
   uint2* d_arena[2] = {nullptr, nullptr};
   unsigned long long* d_cursor[2] = {nullptr, nullptr};
   int64_t* d_pair_off[2] = {nullptr, nullptr};

@@ -98,6 +98,21 @@ struct Item {
 };
 __device__ __forceinline__ Item decode_item(const MatchParams& p, int w, uint32_t cta_rank) {
   Item it;
+  if (p.item_list) {
+    // gathered column direction: rows = the gathered block of the pair (scratch tensor map), columns = image a
+    it.pair = p.item_list[2 * w];
+    const int cb = p.item_list[2 * w + 1];
+    it.dir = 0;
+    const int ib = p.pairs[2 * it.pair];
+    it.nA = p.gath_cnt[it.pair];
+    it.nB = p.img_nfeat[ib];
+    it.valid = cb * kRowsPerItem < it.nA;
+    it.row0 = cb * kRowsPerItem + static_cast<int>(cta_rank) * kTileM;
+    it.rowA = it.pair * p.mstride + it.row0;
+    it.rowB = p.img_row0[ib];
+    it.n_tiles = (it.nB + kTileN - 1) / kTileN;
+    return it;
+  }
   const int cb = w % p.blocks_per_image;
   const int pd = w / p.blocks_per_image;
   it.dir = pd % p.n_dirs;
@@ -144,7 +159,10 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
-b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p) {
+b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_a,
+                     const MatchParams p) {
+  // tmap: the resident descriptor set (column tiles; row strips too unless the rows are gathered), tmap_a: the row
+  // strips (== tmap except for the gathered column direction, where it covers the gather scratch)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;                                     // [kABufs][16 KiB]
@@ -157,9 +175,12 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
   const uint32_t cta_rank = cluster_ctarank();
   const int cluster_id = blockIdx.x / kCluster;
   const int n_clusters = gridDim.x / kCluster;
+  // gathered column direction: the work list was built on the device, so was its length
+  const int n_items = p.item_list ? __ldg(p.n_items_ptr) : p.n_items;
 
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tmap);
+    tma_prefetch_desc(&tmap_a);
     for (int s = 0; s < kABufs; ++s) {
       mbar_init(&bars->full_a[s], 1);
       mbar_init(&bars->empty_a[s], 1);
@@ -189,7 +210,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
   if (warp == kEpiWarps) {
     // ===== TMA producer (whole warp converged, one elected lane issues) =====
     uint32_t stage = 0, phase = 0, n_done = 0;
-    for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+    for (int w = cluster_id; w < n_items; w += n_clusters) {
       const Item it = decode_item(p, w, cta_rank);
       if (!it.valid) continue;
       const uint32_t ab = n_done & 1, aph = (n_done >> 1) & 1;
@@ -198,7 +219,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
       if (elect_one()) {
         // both CTAs' bytes are accounted on the LEADER's barriers (the leader issues the pair MMA)
         if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full_a[ab], kCluster * kBytesA);
-        tma_load_2d_pair(smA + ab * kBytesA, &tmap, &bars->full_a[ab], 0, it.rowA);
+        tma_load_2d_pair(smA + ab * kBytesA, &tmap_a, &bars->full_a[ab], 0, it.rowA);
       }
       __syncwarp();
       for (int t = 0; t < it.n_tiles; ++t) {
@@ -225,7 +246,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
 #ifdef B2M_K1_PROF
       long long pm_empty = 0, pm_fullb = 0, pm_issue = 0, pm_tiles = 0;
 #endif
-      for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+      for (int w = cluster_id; w < n_items; w += n_clusters) {
         const Item it = decode_item(p, w, cta_rank);
         if (!it.valid) continue;
         const uint32_t ab = n_done & 1, aph = (n_done >> 1) & 1;
@@ -292,7 +313,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
     // Runs one item behind the epilogue warps, so the dependent global-memory latencies of the decision
     // (acos table, candidate counter) are off the accumulator hand-shake chain.  Lane l owns rows l, l+32, ...
     uint32_t sphase = 0;
-    for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+    for (int w = cluster_id; w < n_items; w += n_clusters) {
       const Item it = decode_item(p, w, cta_rank);
       if (!it.valid) continue;
       mbar_wait(&bars->sel_full, sphase);
@@ -353,7 +374,7 @@ b2m_k1_filter_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
 #ifdef B2M_K1_PROF
     long long pe_full = 0, pe_drain = 0, pe_rest = 0, pe_tiles = 0, pe_tail = 0, pe_items = 0;
 #endif
-    for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+    for (int w = cluster_id; w < n_items; w += n_clusters) {
       const Item it = decode_item(p, w, cta_rank);
       if (!it.valid) continue;
       const int n_tiles = it.n_tiles;
@@ -504,21 +525,27 @@ __device__ __forceinline__ void finish_candidate(const MatchParams& p, int64_t o
 
 }  // namespace
 
-__global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p, const uint8_t* __restrict__ desc) {
+// dir_only < 0: grid = 2 x n_pairs x kResolveParts, both directions; 0 / 1: grid = n_pairs x kResolveParts, that
+// direction only.  With p.gath_desc the rows of direction 1 are the pair's GATHERED descriptors (of image b) and its
+// columns are image a (launch_k1_filter_gather).
+__global__ void __launch_bounds__(256) b2m_k1_resolve_kernel(const MatchParams p, const uint8_t* __restrict__ desc,
+                                                             const int dir_only) {
   // kResolveParts CTAs share the candidates of one (pair, direction): part k takes the slots == k mod
   // kResolveParts (and the rows == k mod kResolveParts of the unstaged candidates), which cuts the
   // serial chain "stage a slot, score its candidates" of a true-match pair by that factor.
   const int part = blockIdx.x % kResolveParts;
   const int pd = blockIdx.x / kResolveParts;
-  const int pair = pd >> 1;
-  const int dir = pd & 1;
+  const int pair = dir_only < 0 ? pd >> 1 : pd;
+  const int dir = dir_only < 0 ? pd & 1 : dir_only;
   const int n_cand = p.cand_cnt[pair * 2 + dir];
   if (n_cand == 0) return;
+  const bool gathered = dir == 1 && p.gath_desc != nullptr;
   const int ia = p.pairs[2 * pair + dir];
-  const int ib = p.pairs[2 * pair + (dir ^ 1)];
+  const int ib = gathered ? p.pairs[2 * pair] : p.pairs[2 * pair + (dir ^ 1)];
   const int nB = p.img_nfeat[ib];
   const int nB_pad = (nB + kRowPad - 1) / kRowPad * kRowPad;
-  const uint8_t* A = desc + static_cast<int64_t>(p.img_row0[ia]) * kDim;
+  const uint8_t* A = gathered ? p.gath_desc + static_cast<int64_t>(pair) * p.mstride * kDim
+                              : desc + static_cast<int64_t>(p.img_row0[ia]) * kDim;
   const uint8_t* Bm = desc + static_cast<int64_t>(p.img_row0[ib]) * kDim;
   const int64_t base = (static_cast<int64_t>(pair) * 2 + dir) * p.mstride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -645,7 +672,7 @@ cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p_in,
   p.n_items = n_pairs * n_dirs * p.blocks_per_image;
   const int clusters = p.n_items < num_sms / kCluster ? p.n_items : num_sms / kCluster;
   if (clusters > 0) {
-    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, p);
+    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -668,7 +695,7 @@ cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p_in,
     e = cudaEventRecord(after_filter, stream);  // the roofline times the GEMM kernel alone
     if (e != cudaSuccess) return e;
   }
-  b2m_k1_resolve_kernel<<<2 * n_pairs * kResolveParts, 256, 0, stream>>>(p, desc);
+  b2m_k1_resolve_kernel<<<2 * n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, -1);
   return cudaGetLastError();
 }
 
@@ -723,7 +750,7 @@ cudaError_t launch_k1_filter_skip(const CUtensorMap& tmap, const MatchParams& p_
   const int clusters = p.n_items < num_sms / kCluster ? p.n_items : num_sms / kCluster;
   if (clusters > 0) {
     // 1. row direction of every pair
-    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, p);
+    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // 2. live pairs swapped, dead pairs -> dummy image (0 features: every work item invalid)
@@ -740,7 +767,7 @@ cudaError_t launch_k1_filter_skip(const CUtensorMap& tmap, const MatchParams& p_
     q.cand_cnt = p.cand_cnt + 1;
     q.cand_rows = p.cand_rows + p.mstride;
     q.cand_sorted = p.cand_sorted + p.mstride;
-    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, q);
+    b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap, q);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -749,7 +776,157 @@ cudaError_t launch_k1_filter_skip(const CUtensorMap& tmap, const MatchParams& p_
     if (e != cudaSuccess) return e;
   }
   // 4. exact resolution of both directions (original pair list and base pointers)
-  b2m_k1_resolve_kernel<<<2 * n_pairs * kResolveParts, 256, 0, stream>>>(p, desc);
+  b2m_k1_resolve_kernel<<<2 * n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, -1);
+  return cudaGetLastError();
+}
+
+namespace {
+// Gathered column direction, step 3 (see match_kernel.cuh): one CTA per pair.  The distinct columns some row of image
+// a matched (m12 >= 0 after the exact resolve) are ranked ascending; rank, column list, gathered descriptors (padded
+// with zero rows to a multiple of 256) and one work item per 256 gathered rows are written.
+constexpr int kGatherMaxWords = 1024;  // columns / 32: images up to 32768 features (SiftMatchingOptions.max_num_matches)
+__global__ void __launch_bounds__(256) b2m_k1_gather_kernel(const MatchParams p, const uint8_t* __restrict__ desc,
+                                                            uint8_t* __restrict__ gdesc, int32_t* __restrict__ colrank,
+                                                            int32_t* __restrict__ cols, int32_t* __restrict__ gcnt,
+                                                            int32_t* __restrict__ items, int32_t* __restrict__ n_items) {
+  const int pair = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ uint32_t s_bits[kGatherMaxWords];
+  __shared__ int s_pref[kGatherMaxWords];
+  __shared__ int s_warp[8], s_total, s_item0;
+  if (p.cand_cnt[2 * pair] == 0) {  // no candidate, hence no match: the column direction is never consulted
+    if (tid == 0) gcnt[pair] = 0;
+    return;
+  }
+  const int ia = p.pairs[2 * pair], ib = p.pairs[2 * pair + 1];
+  const int nA = p.img_nfeat[ia], nB = p.img_nfeat[ib];
+  const int n_words = (nB + 31) >> 5;
+  const int64_t base = static_cast<int64_t>(pair) * p.mstride;
+  const int32_t* m12 = p.mbuf + 2 * base;
+  for (int w = tid; w < n_words; w += 256) s_bits[w] = 0u;
+  __syncthreads();
+  for (int i = tid; i < nA; i += 256) {
+    const int j = m12[i];
+    if (j >= 0) atomicOr(&s_bits[j >> 5], 1u << (j & 31));
+  }
+  __syncthreads();
+  // exclusive prefix of the per-word popcounts (each thread owns a contiguous run of words)
+  const int per = (n_words + 255) / 256;
+  const int w0 = min(n_words, tid * per), w1 = min(n_words, w0 + per);
+  int local = 0;
+  for (int w = w0; w < w1; ++w) local += __popc(s_bits[w]);
+  int incl = local;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int k = 0; k < 8; ++k) {
+      const int v = s_warp[k];
+      s_warp[k] = acc;
+      acc += v;
+    }
+    s_total = acc;
+    const int n_blocks = (acc + kRowPad - 1) / kRowPad;
+    s_item0 = n_blocks > 0 ? atomicAdd(n_items, n_blocks) : 0;
+    gcnt[pair] = acc;
+  }
+  __syncthreads();
+  {
+    int run = s_warp[warp] + incl - local;
+    for (int w = w0; w < w1; ++w) {
+      s_pref[w] = run;
+      run += __popc(s_bits[w]);
+    }
+  }
+  __syncthreads();
+  const int nc = s_total;
+  const int nc_pad = (nc + kRowPad - 1) / kRowPad * kRowPad;
+  for (int t = tid; t < nc_pad / kRowPad; t += 256) {
+    items[2 * (s_item0 + t)] = pair;
+    items[2 * (s_item0 + t) + 1] = t;
+  }
+  for (int w = tid; w < n_words; w += 256) {
+    uint32_t bits = s_bits[w];
+    int r = s_pref[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int j = (w << 5) + b;
+      colrank[base + j] = r;
+      cols[base + r] = j;
+      ++r;
+    }
+  }
+  __syncthreads();   // cols[] of this CTA are visible to its own threads after the barrier (same block: global writes + __syncthreads)
+  const uint4* src0 = reinterpret_cast<const uint4*>(desc + static_cast<int64_t>(p.img_row0[ib]) * kDim);
+  uint4* dst0 = reinterpret_cast<uint4*>(gdesc + base * kDim);
+  for (int q = tid; q < nc_pad * 8; q += 256) {
+    const int r = q >> 3, seg = q & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < nc) v = __ldg(src0 + static_cast<int64_t>(cols[base + r]) * 8 + seg);
+    dst0[static_cast<int64_t>(r) * 8 + seg] = v;
+  }
+}
+}  // namespace
+
+cudaError_t launch_k1_filter_gather(const CUtensorMap& tmap, const CUtensorMap& tmap_gath, const MatchParams& p_in,
+                                    const uint8_t* desc, int n_pairs, int max_strips, int num_sms, const GatherScratch& g,
+                                    cudaStream_t stream, cudaEvent_t after_filter) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(b2m_k1_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSmemBytes));
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  if (n_pairs <= 0) return cudaSuccess;
+  MatchParams p = p_in;
+  cudaError_t e = cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * 2 * n_pairs, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(g.n_items, 0, sizeof(int32_t), stream);
+  if (e != cudaSuccess) return e;
+  p.n_dirs = 1;
+  p.blocks_per_image = (max_strips * kTileM + kRowsPerItem - 1) / kRowsPerItem;
+  p.n_items = n_pairs * p.blocks_per_image;
+  p.item_list = nullptr;
+  p.gath_desc = nullptr;
+  const int max_clusters = num_sms / kCluster;
+  const int clusters = p.n_items < max_clusters ? p.n_items : max_clusters;
+  if (clusters <= 0) return cudaSuccess;
+  // 1. row direction of every pair                   2. its exact resolution: m12
+  b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap, p);
+  b2m_k1_resolve_kernel<<<n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, 0);
+  // 3. matched columns -> rank, gathered descriptors, work items
+  b2m_k1_gather_kernel<<<n_pairs, 256, 0, stream>>>(p, desc, g.desc, g.colrank, g.cols, g.cnt, g.items, g.n_items);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // 4. column direction of the matched columns only: rows = gathered descriptors, columns = image a; outputs go to
+  //    the direction-1 halves (every index in the kernel is (pair * 2 + dir) * mstride + row with dir = 0)
+  MatchParams q = p;
+  q.mbuf = p.mbuf + p.mstride;
+  q.aux = p.aux + p.mstride;
+  q.cand_cnt = p.cand_cnt + 1;
+  q.cand_rows = p.cand_rows + p.mstride;
+  q.cand_sorted = p.cand_sorted + p.mstride;
+  q.item_list = g.items;
+  q.n_items_ptr = g.n_items;
+  q.gath_cnt = g.cnt;
+  b2m_k1_filter_kernel<<<max_clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap_gath, q);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (after_filter) {
+    e = cudaEventRecord(after_filter, stream);
+    if (e != cudaSuccess) return e;
+  }
+  // 5. exact resolution of the gathered direction (original base pointers: the kernel adds the direction itself)
+  p.gath_desc = g.desc;
+  b2m_k1_resolve_kernel<<<n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, 1);
   return cudaGetLastError();
 }
 

@@ -213,6 +213,9 @@ __global__ void __launch_bounds__(256) b2m_crosscheck_compact_kernel(const Compa
   const int n1 = p.img_nfeat[i1];
   const int32_t* m12 = p.mbuf + (static_cast<int64_t>(pair) * 2) * p.mstride;
   const int32_t* m21 = m12 + p.mstride;
+  // gathered column direction: m21 holds one entry per MATCHED column, at the column's rank
+  const int32_t* rank = p.colrank ? p.colrank + static_cast<int64_t>(pair) * p.mstride : nullptr;
+  auto mutual = [&](int i, int j) { return m21[rank ? rank[j] : j] == i; };
   __shared__ int s_warp[8];
   __shared__ int s_base;
   __shared__ unsigned long long s_off;
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(256) b2m_crosscheck_compact_kernel(const Compa
   int cnt = 0;
   for (int i = threadIdx.x; i < n1; i += 256) {
     const int j = m12[i];
-    cnt += (j >= 0 && (!p.cross_check || m21[j] == i)) ? 1 : 0;
+    cnt += (j >= 0 && (!p.cross_check || mutual(i, j))) ? 1 : 0;
   }
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) s_warp[warp] = cnt;
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(256) b2m_crosscheck_compact_kernel(const Compa
     bool keep = false;
     if (i < n1) {
       j = m12[i];
-      keep = (j >= 0 && (!p.cross_check || m21[j] == i));
+      keep = (j >= 0 && (!p.cross_check || mutual(i, j)));
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, keep);
     const int wpre = __popc(ballot & ((1u << lane) - 1u));

@@ -22,6 +22,12 @@ struct MatchParams {
   int32_t* cand_sorted;      // device [n_pairs][2][mstride] candidate rows bucketed by winning slot
   // persistent K1: filled in by launch_k1_filter
   int32_t n_items, blocks_per_image, n_dirs;
+  // gathered column direction (launch_k1_filter_gather): the "row image" of a work item is the gathered block of the
+  // pair (the descriptors of image b that some row of image a matched), the "column image" is image a
+  const int32_t* item_list;   // device [n][2] (pair, 256-row block) written by the gather kernel, or nullptr
+  const int32_t* n_items_ptr; // device count of item_list entries
+  const int32_t* gath_cnt;    // device [n_pairs] gathered rows of each pair
+  const uint8_t* gath_desc;   // device [n_pairs x mstride x 128] gathered descriptors (resolve kernel)
 };
 
 struct CompactParams {
@@ -39,6 +45,8 @@ struct CompactParams {
   const float2* kpts;           // device keypoints indexed by padded row, or nullptr
   double4* pts;                 // device arena (x1, y1, x2, y2), or nullptr
   const int32_t* enable;        // optional [n_pairs]: pairs with enable[pair] < 0 produce no output (guided pass)
+  const int32_t* colrank;       // optional [n_pairs][mstride]: m21 is indexed by the RANK of a column among the pair's
+                                // matched columns (gathered column direction), not by the column itself
 };
 
 // Guided matching (K1g): per pair of the batch the geometry chosen by the verifier.
@@ -75,6 +83,25 @@ cudaError_t launch_k1_filter(const CUtensorMap& tmap, const MatchParams& p,
 cudaError_t launch_k1_filter_skip(const CUtensorMap& tmap, const MatchParams& p, const uint8_t* desc, int n_pairs,
                                   int max_strips, int num_sms, int32_t* pairs_scratch, int dummy_image,
                                   cudaStream_t stream, cudaEvent_t after_filter);
+// Cross-check schedule with a GATHERED column direction (replaces launch_k1_filter_skip): m21 is consulted only at the
+// columns some row matched, so the column direction is computed for those columns only:
+//   1. GEMM + filter over all pairs, row direction; 2. exact resolve of the row direction (m12);
+//   3. per pair the distinct columns j = m12[i] are ranked (ascending), their descriptors copied into a scratch
+//      "gathered image" (zero-padded to 256 rows) and one work item per 256 gathered rows appended to a device list
+//      (pairs without a match contribute nothing); 4. the same GEMM kernel over that list: rows = gathered
+//      descriptors of image b (scratch tensor map), columns = image a -- for a matched column exactly what the
+//      full column direction computes; 5. exact resolve of it.  The compaction kernel looks m21 up by rank (colrank).
+struct GatherScratch {
+  uint8_t* desc;        // [batch x mstride x 128]
+  int32_t* colrank;     // [batch][mstride]
+  int32_t* cols;        // [batch][mstride] gathered row -> column
+  int32_t* cnt;         // [batch]
+  int32_t* items;       // [batch x mstride / 256][2]
+  int32_t* n_items;     // [1]
+};
+cudaError_t launch_k1_filter_gather(const CUtensorMap& tmap, const CUtensorMap& tmap_gath, const MatchParams& p,
+                                    const uint8_t* desc, int n_pairs, int max_strips, int num_sms, const GatherScratch& g,
+                                    cudaStream_t stream, cudaEvent_t after_filter);
 cudaError_t launch_k1_guided(const CUtensorMap& tmap, const MatchParams& p, const GuidedParams& g, int n_pairs,
                              int max_strips, int n_dirs, cudaStream_t stream);
 cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream);

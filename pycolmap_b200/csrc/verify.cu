@@ -248,7 +248,9 @@ __device__ __forceinline__ void score_block(Shared& sh, const double4* pts, int6
     }                                                    \
   } while (0)
 
-template <int KIND>
+// WARP_MIN (E only): the minimal 5-point solves of a round run one WARP per hypothesis (five_point_warp.cuh) instead
+// of one thread per hypothesis (geom.h minimal_E5); the local-optimisation solve is always the warp solver.
+template <int KIND, bool WARP_MIN>
 __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int64_t off, int n,
                                const PointXform& X, double thr, uint64_t key, const b2m_ransac_opts& ro) {
   using T = Traits<KIND>;
@@ -282,9 +284,10 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
   unsigned long long n_scored = 0;  // models whose residuals were evaluated over all n matches (thread 0 keeps the tally)
   // models of this thread's hypothesis: registers / local memory for F and H, the CTA's slice of the global scratch
   // for E (written by the warp-cooperative solver)
-  double mdl_local[KIND == 0 ? 1 : T::kMaxModels * 9];
-  double* const e_models = KIND == 0 ? P.e_scratch + (static_cast<size_t>(pair) * kRansacThreads + tid) * 90 : nullptr;
-  double* const mdl = KIND == 0 ? e_models : mdl_local;
+  constexpr bool kWarpMin = KIND == 0 && WARP_MIN;
+  double mdl_local[kWarpMin ? 1 : T::kMaxModels * 9];
+  double* const e_models = kWarpMin ? P.e_scratch + (static_cast<size_t>(pair) * kRansacThreads + tid) * 90 : nullptr;
+  double* const mdl = kWarpMin ? e_models : mdl_local;
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long prof_t = clock64();
   while (trials < max_trials) {
@@ -311,7 +314,8 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       }
       double x1[T::kMin], y1[T::kMin], x2[T::kMin], y2[T::kMin];
       for (int j = 0; j < T::kMin; ++j) load_pt(pts, off + idx[j], X, x1[j], y1[j], x2[j], y2[j]);
-      if (KIND == 0) {
+      if (KIND == 0 && !kWarpMin) nm = minimal_E5(x1, y1, x2, y2, mdl);
+      if (kWarpMin) {
         // thread = hypothesis only for the (small) 5 x 9 null space; the elimination + root finding that follow
         // run one warp per hypothesis (five_point_warp.cuh)
         double A[45], Nb[36];
@@ -323,7 +327,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       if (KIND == 1) nm = minimal_F7(x1, y1, x2, y2, mdl);
       if (KIND == 2) nm = minimal_H4_closed(x1, y1, x2, y2, mdl);
     }
-    if (KIND == 0) {
+    if (kWarpMin) {
       sh.scan[tid] = nm;
       __syncthreads();
       fpw::Scratch& WS = reinterpret_cast<fpw::Scratch*>(sh.chunk_d)[warp];   // chunk_d is idle outside the scoring loop
@@ -612,7 +616,7 @@ struct KindBlocks<1> { static constexpr int v = 4; };
 template <>
 struct KindBlocks<2> { static constexpr int v = 5; };
 
-template <int KIND>
+template <int KIND, bool WARP_MIN = false>
 __global__ void __launch_bounds__(kRansacThreads, KindBlocks<KIND>::v) b2m_ransac_kernel(const VerifyParams P) {
   __shared__ Shared sh;
   const int pair = blockIdx.x;
@@ -651,7 +655,7 @@ __global__ void __launch_bounds__(kRansacThreads, KindBlocks<KIND>::v) b2m_ransa
   const uint64_t key = splitmix64(P.seed ^ splitmix64((static_cast<uint64_t>(static_cast<uint32_t>(i1)) << 34) ^
                                                         (static_cast<uint64_t>(static_cast<uint32_t>(i2)) << 2) ^
                                                         static_cast<uint64_t>(kind)));
-  ransac_problem<KIND>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
+  ransac_problem<KIND, WARP_MIN>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
 }
 
 // The three model kinds are independent problems: E and F go to two side streams so that their
@@ -867,6 +871,18 @@ __global__ void __launch_bounds__(256) b2m_undistort_kernel(const VerifyParams P
   }
 }
 
+// B2M_E5_MINIMAL = thread | warp: how the minimal 5-point solves of a RANSAC round are mapped (A/B switch; the
+// default is what measured faster on B200).
+bool e5_warp_minimal() {
+  static const int v = [] {
+    const char* e = getenv("B2M_E5_MINIMAL");
+    if (e && !strcmp(e, "warp")) return 1;
+    if (e && !strcmp(e, "thread")) return 0;
+    return 1;
+  }();
+  return v != 0;
+}
+
 // `pts_E` (optional): the arena the E kernel reads instead of P.pts (output of b2m_undistort_kernel).
 cudaError_t launch_ransac(const VerifyParams& P_in, int nb, cudaStream_t st, RansacStreams* rs = nullptr,
                           const double4* pts_E = nullptr) {
@@ -874,7 +890,10 @@ cudaError_t launch_ransac(const VerifyParams& P_in, int nb, cudaStream_t st, Ran
   VerifyParams PE = P_in;
   if (pts_E) PE.pts = pts_E;
   if (P.single_kind >= 0 || !rs || !rs->side[0]) {
-    if (P.single_kind < 0 || P.single_kind == 0) b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, st>>>(PE);
+    if (P.single_kind < 0 || P.single_kind == 0) {
+      if (e5_warp_minimal()) b2m_ransac_kernel<0, true><<<nb, kRansacThreads, 0, st>>>(PE);
+      else b2m_ransac_kernel<0, false><<<nb, kRansacThreads, 0, st>>>(PE);
+    }
     if (P.single_kind < 0 || P.single_kind == 1) b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, st>>>(P);
     if (P.single_kind < 0 || P.single_kind == 2) b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
     return cudaGetLastError();
@@ -883,7 +902,8 @@ cudaError_t launch_ransac(const VerifyParams& P_in, int nb, cudaStream_t st, Ran
   if (e != cudaSuccess) return e;
   cudaStreamWaitEvent(rs->side[0], rs->fork, 0);
   cudaStreamWaitEvent(rs->side[1], rs->fork, 0);
-  b2m_ransac_kernel<0><<<nb, kRansacThreads, 0, rs->side[0]>>>(PE);
+  if (e5_warp_minimal()) b2m_ransac_kernel<0, true><<<nb, kRansacThreads, 0, rs->side[0]>>>(PE);
+  else b2m_ransac_kernel<0, false><<<nb, kRansacThreads, 0, rs->side[0]>>>(PE);
   b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, rs->side[1]>>>(P);
   b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
   cudaEventRecord(rs->join[0], rs->side[0]);

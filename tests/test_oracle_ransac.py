@@ -188,3 +188,32 @@ def test_multiple_models_finds_both_motions():
     g1 = R.estimate_two_view_geometry(scenes.CAM, q1, scenes.CAM, q2,
                                       options=R.TwoViewGeometryOptions(multiple_models=True), seed=2)
     assert g1.config == R.CALIBRATED and abs(len(g1.inlier_matches) - pl.sum()) <= 3
+
+
+def test_sequential_cpp_oracle_agrees_with_numpy_oracle():
+    """oracle/ransac_seq.cpp (the scalar fp64 sequential LO-RANSAC that bench.py times as the CPU arm) against the numpy
+    restatement oracle/ransac.py: same configuration, inlier counts within +-1 % (RANSAC parity is statistical), on the
+    planted scene types; the pair-parallel entry point returns what the single calls return."""
+    from oracle import ransac_seq as S
+    rng = np.random.default_rng(21)
+    jobs, singles = [], []
+    for kind, cam in (("general", scenes.CAM), ("planar", scenes.CAM), ("rotation", scenes.CAM),
+                      ("general", scenes.CAM_NOPRIOR)):
+        p1, p2, planted = scenes.two_view_scene(rng, 500, 0.3, kind, 0.3)
+        g = R.estimate_two_view_geometry(cam, p1, cam, p2, seed=2)
+        s = S.estimate_two_view_geometry(cam, p1, cam, p2, seed=2)
+        assert s["config"] == g.config, (kind, s["config"], g.config)
+        tol = max(3, int(0.01 * len(g.inlier_matches)))
+        extra = max(3, int(0.03 * len(p1))) if kind != "general" else 0          # degenerate F: admitted outliers vary
+        assert abs(len(s["inlier_matches"]) - len(g.inlier_matches)) <= max(tol, extra)
+        assert abs(s["nE"] - g.nE) <= max(tol, extra) and abs(s["nH"] - g.nH) <= max(tol, int(0.03 * len(p1)))
+        assert s["models_scored"] > 100
+        m = np.stack([np.arange(len(p1), dtype=np.uint32)] * 2, 1)
+        jobs.append((cam, p1, cam, p2, m))
+        singles.append(s)
+    few1, few2, _ = scenes.two_view_scene(rng, 10, 0.0)
+    assert S.estimate_two_view_geometry(scenes.CAM, few1, scenes.CAM, few2)["config"] == R.DEGENERATE
+    out, scored = S.verify_pairs(jobs, seed=2, n_threads=3)
+    for k, s in enumerate(singles):   # job k runs with seed + k: configuration equal, counts statistically equal
+        assert out[k, 0] == s["config"] and abs(out[k, 4] - len(s["inlier_matches"])) <= max(3, int(0.03 * 500))
+    assert scored > 400

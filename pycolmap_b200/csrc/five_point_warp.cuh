@@ -162,9 +162,10 @@ __device__ __forceinline__ void load_B(const Scratch& S, double (&Bx)[3][4], dou
   }
 }
 
-// One warp: the essential matrices of the null space S.N.  models: [<= 10][9] (shared or global); returns the
-// number of models (the same value in every lane).  All 32 lanes must call it.
-__device__ inline int five_point_warp(Scratch& S, double* models, int lane) {
+// One warp, first half: the 10 x 20 constraint matrix of the null space S.N, its Gauss-Jordan elimination, and the
+// degree-10 polynomial det B(z).  Leaves rows 4..9 / columns 10..19 of the eliminated matrix in S.Mr and the polynomial
+// in S.ladder[0]; false when the elimination met a vanishing pivot (no model).  All 32 lanes must call it.
+__device__ inline bool eliminate_warp(Scratch& S, int lane) {
   const double* N = S.N;
   // ---- quadratic tables (90 coefficients, three per lane)
   for (int e = lane; e < 90; e += 32) {
@@ -254,7 +255,7 @@ __device__ inline int five_point_warp(Scratch& S, double* models, int lane) {
     for (int r = 0; r < 10; ++r)
       if (r != col) c[r] -= f[r] * c[col];
   }
-  if (singular) return 0;
+  if (singular) return false;
   if (lane >= 10 && lane < 20)
 #pragma unroll
     for (int r = 4; r < 10; ++r) S.Mr[r - 4][lane - 10] = c[r];
@@ -294,44 +295,81 @@ __device__ inline int five_point_warp(Scratch& S, double* models, int lane) {
       for (int i = 0; i < 11; ++i) S.ladder[0][i] = n10[i];
   }
   __syncwarp();
-  const int nr = real_roots_warp(S, lane);
-  load_B(S, Bx, By, Bc);   // again: cheaper than keeping 39 doubles alive across the root finder
-  // ---- one lane per root: (x, y) from the null vector of B(z), E = x N0 + y N1 + z N2 + N3
-  bool ok = false;
-  double x = 0.0, y = 0.0, z = 0.0;
-  if (lane < nr) {
-    z = S.prev[lane];
-    double bx[3], by[3], bc[3];
+  return true;
+}
+
+// The (x, y) of one root z of det B(z) and its essential matrix E = x N0 + y N1 + z N2 + N3; false when B(z) has no
+// usable null vector.  Bx / By / Bc as load_B gives them.
+__device__ __forceinline__ bool model_of_root(const double (&Bx)[3][4], const double (&By)[3][4], const double (&Bc)[3][5],
+                                              const double* N, double z, double* E) {
+  double bx[3], by[3], bc[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      bx[k] = geom::poly_eval(Bx[k], 3, z);
-      by[k] = geom::poly_eval(By[k], 3, z);
-      bc[k] = geom::poly_eval(Bc[k], 4, z);
-    }
-    double bestw = 0.0, X = 0.0, Y = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    bx[k] = geom::poly_eval(Bx[k], 3, z);
+    by[k] = geom::poly_eval(By[k], 3, z);
+    bc[k] = geom::poly_eval(Bc[k], 4, z);
+  }
+  double bestw = 0.0, X = 0.0, Y = 0.0;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int b = (a + 1) % 3;
-      const double cxp = by[a] * bc[b] - bc[a] * by[b];
-      const double cyp = bc[a] * bx[b] - bx[a] * bc[b];
-      const double cw = bx[a] * by[b] - by[a] * bx[b];
-      if (fabs(cw) > fabs(bestw)) {
-        bestw = cw;
-        X = cxp;
-        Y = cyp;
-      }
-    }
-    if (fabs(bestw) > 0.0) {
-      ok = true;
-      x = X / bestw;
-      y = Y / bestw;
+  for (int a = 0; a < 3; ++a) {
+    const int b = (a + 1) % 3;
+    const double cxp = by[a] * bc[b] - bc[a] * by[b];
+    const double cyp = bc[a] * bx[b] - bx[a] * bc[b];
+    const double cw = bx[a] * by[b] - by[a] * bx[b];
+    if (fabs(cw) > fabs(bestw)) {
+      bestw = cw;
+      X = cxp;
+      Y = cyp;
     }
   }
+  if (!(fabs(bestw) > 0.0)) return false;
+  const double x = X / bestw, y = Y / bestw;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) E[e] = x * N[e] + y * N[9 + e] + z * N[18 + e] + N[27 + e];
+  return true;
+}
+
+// One THREAD, second half (minimal samples: 100-odd independent hypotheses per CTA, where the latency-bound root
+// refinement wants thread-level parallelism): real roots of the polynomial (serial bracketing of geom.h) and one model
+// per root.  N [4][9], poly [11], Mr [6][10] are what eliminate_warp left (any memory space); models [<= 10][9].
+__device__ inline int finish_thread(const double* N, const double* poly, const double* Mr, double* models) {
+  double roots[10];
+  const int nr = geom::poly_real_roots(poly, 10, roots);
+  if (nr == 0) return 0;
+  double Bx[3][4], By[3][4], Bc[3][5];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double* a = Mr + 20 * r;
+    const double* b = Mr + 20 * r + 10;
+    Bx[r][0] = a[2];         Bx[r][1] = a[1] - b[2]; Bx[r][2] = a[0] - b[1]; Bx[r][3] = -b[0];
+    By[r][0] = a[5];         By[r][1] = a[4] - b[5]; By[r][2] = a[3] - b[4]; By[r][3] = -b[3];
+    Bc[r][0] = a[9];         Bc[r][1] = a[8] - b[9]; Bc[r][2] = a[7] - b[8]; Bc[r][3] = a[6] - b[7];
+    Bc[r][4] = -b[6];
+  }
+  int nm = 0;
+  for (int r = 0; r < nr; ++r)
+    if (model_of_root(Bx, By, Bc, N, roots[r], models + 9 * nm)) ++nm;
+  return nm;
+}
+
+// One warp: the essential matrices of the null space S.N.  models: [<= 10][9] (shared or global); returns the
+// number of models (the same value in every lane).  All 32 lanes must call it.  (Local optimisation: one solve at a
+// time, so the root refinement runs one lane per interval.)
+__device__ inline int five_point_warp(Scratch& S, double* models, int lane) {
+  if (!eliminate_warp(S, lane)) return 0;
+  const double* N = S.N;
+  double Bx[3][4], By[3][4], Bc[3][5];
+  const int nr = real_roots_warp(S, lane);
+  load_B(S, Bx, By, Bc);
+  // ---- one lane per root: (x, y) from the null vector of B(z), E = x N0 + y N1 + z N2 + N3
+  bool ok = false;
+  double E[9];
+  if (lane < nr) ok = model_of_root(Bx, By, Bc, N, S.prev[lane], E);
   const unsigned ballot = __ballot_sync(0xffffffffu, ok);
   if (ok) {
-    double* E = models + 9 * __popc(ballot & ((1u << lane) - 1u));
+    double* out = models + 9 * __popc(ballot & ((1u << lane) - 1u));
 #pragma unroll
-    for (int e = 0; e < 9; ++e) E[e] = x * N[e] + y * N[9 + e] + z * N[18 + e] + N[27 + e];
+    for (int e = 0; e < 9; ++e) out[e] = E[e];
   }
   __syncwarp();
   return __popc(ballot);

@@ -138,22 +138,28 @@ B2M_HD inline int poly_real_roots(const double* coef, int deg_in, double* roots)
   }
   bound = 2.0 * bound * (1.0 + 1e-9);
   if (!(bound > 0.0)) bound = 1.0;
-  // derivative ladder: d[k] = k-th derivative scaled (coefficients), degree deg-k
-  double d[MAXD][MAXD + 1];  // d[0] = p
-  for (int i = 0; i <= deg; ++i) d[0][i] = c[i];
-  for (int k = 1; k < deg; ++k)
-    for (int i = 0; i <= deg - k; ++i) d[k][i] = d[k - 1][i + 1] * (i + 1);
+  // derivative ladder, one level at a time: q = k-th derivative (degree deg - k), coefficient i = c[i + k] (i + k)
+  // (i + k - 1) ... (i + 1) with the factors applied in that order.  (Keeping all levels -- 10 x 11 doubles per
+  // thread -- in local memory was a sixth of the 5-point solver's footprint.)
+  double q[MAXD + 1];
+  auto level = [&](int k) {
+    for (int i = 0; i <= deg - k; ++i) {
+      double v = c[i + k];
+      for (int t = i + k; t > i; --t) v *= static_cast<double>(t);
+      q[i] = v;
+    }
+  };
   double prev[MAXD], cur[MAXD];
   int nprev = 0;
-  // start from the linear polynomial d[deg-1]
+  // start from the linear polynomial (level deg - 1)
   {
-    const double* q = d[deg - 1];
+    level(deg - 1);
     prev[0] = -q[0] / q[1];
     nprev = 1;
   }
   for (int k = deg - 2; k >= 0; --k) {
     const int dg = deg - k;
-    const double* q = d[k];
+    level(k);
     int ncur = 0;
     double lo = -bound, flo = poly_eval(q, dg, lo);
     for (int i = 0; i <= nprev; ++i) {
@@ -172,9 +178,6 @@ B2M_HD inline int poly_real_roots(const double* coef, int deg_in, double* roots)
     if (flo == 0.0 && ncur < dg && (ncur == 0 || cur[ncur - 1] != lo)) cur[ncur++] = lo;
     for (int i = 0; i < ncur; ++i) prev[i] = cur[i];
     nprev = ncur;
-    if (nprev == 0 && k > 0) {
-      // no critical points: the remaining polynomials are monotone between +-bound; keep going
-    }
   }
   for (int i = 0; i < nprev; ++i) roots[i] = prev[i];
   return nprev;

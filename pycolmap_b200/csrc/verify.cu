@@ -72,7 +72,8 @@ struct VerifyParams {
   int32_t force_calibrated;   // stand-alone: -1 use camera flags
   unsigned long long* prof;   // optional [3][8] cycle counters (B2M_PROF=1), else nullptr
   unsigned long long* counters;  // [6] models scored / residual evaluations per kind (b2m_stats), or nullptr
-  double* e_scratch;          // E kernel: [nb][kRansacThreads][90] null spaces, then the <= 10 models of every hypothesis
+  int32_t packed_score;       // hypothesis scoring with FFMA2 / FMUL2 (two matches per instruction); B2M_SCORE=scalar turns it off
+  double* e_scratch;          // E kernel, warp / hybrid minimal solves: [nb][kRansacThreads][kEStride] (models, N, polynomial, Mr)
   // guided matching hand-over (written by the decision kernel when guided_min_inliers >= 0)
   int32_t* guided_kind;       // [nb] -1 / 0 (F) / 1 (H)
   float* guided_model;        // [nb][9]
@@ -136,6 +137,47 @@ __device__ __forceinline__ int inlier_f32(const float* M, float x1, float y1, fl
   const int in = lhs <= 0.99f * rhs ? 1 : 0;
   const int out = lhs >= 1.01f * rhs ? 1 : 0;
   return in | ((in | out) ^ 1) << 1;  // bit 0: inlier, bit 1: borderline (neither clearly in nor out)
+}
+
+// ---- packed fp32x2 (FFMA2 / FMUL2 on sm_100): the same tests on TWO matches per instruction ---------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// lhs and thr * rhs of the division-free test for two matches (x1, y1, x2, y2 packed); M[k] = (m_k, m_k)
+template <int KIND>
+__device__ __forceinline__ void test_f32x2(const f32x2* M, f32x2 x1, f32x2 y1, f32x2 x2, f32x2 y2, f32x2 thr2, f32x2 neg1,
+                                           f32x2& lhs, f32x2& rhs) {
+  if (KIND == 2) {
+    const f32x2 u = fma2(M[0], x1, fma2(M[1], y1, M[2]));
+    const f32x2 v = fma2(M[3], x1, fma2(M[4], y1, M[5]));
+    const f32x2 w = fma2(M[6], x1, fma2(M[7], y1, M[8]));
+    const f32x2 ex = fma2(x2, w, mul2(u, neg1)), ey = fma2(y2, w, mul2(v, neg1));
+    lhs = fma2(ex, ex, mul2(ey, ey));
+    rhs = mul2(mul2(thr2, w), w);
+  } else {
+    const f32x2 a0 = fma2(M[0], x1, fma2(M[1], y1, M[2]));
+    const f32x2 a1 = fma2(M[3], x1, fma2(M[4], y1, M[5]));
+    const f32x2 a2 = fma2(M[6], x1, fma2(M[7], y1, M[8]));
+    const f32x2 b0 = fma2(M[0], x2, fma2(M[3], y2, M[6]));
+    const f32x2 b1 = fma2(M[1], x2, fma2(M[4], y2, M[7]));
+    const f32x2 num = fma2(x2, a0, fma2(y2, a1, a2));
+    lhs = mul2(num, num);
+    rhs = mul2(thr2, fma2(a0, a0, fma2(a1, a1, fma2(b0, b0, mul2(b1, b1)))));
+  }
 }
 
 template <int KIND>
@@ -239,6 +281,64 @@ __device__ __forceinline__ void score_block(Shared& sh, const double4* pts, int6
   }
 }
 
+// score_block with two matches per instruction (PPT even).  Inliers are counted against 0.99 x and 1.01 x the
+// threshold; a (thread, model) whose two counts differ holds a borderline match and is redone in fp64, so the
+// decisions equal the fp64 evaluation exactly as in score_block.
+template <int KIND, int PPT>
+__device__ __forceinline__ void score_block_x2(Shared& sh, const double4* pts, int64_t off, const PointXform& X, int n, int pb,
+                                               int n_chunk, double thr, float thr_f, int tid) {
+  static_assert(PPT % 2 == 0, "two matches per packed register");
+  f32x2 px1[PPT / 2], py1[PPT / 2], px2[PPT / 2], py2[PPT / 2];
+#pragma unroll
+  for (int q = 0; q < PPT; q += 2) {
+    float a[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = pb + (q + h) * kRansacThreads + tid;
+      double x1 = 0, y1 = 0, x2 = 1e15, y2 = 1e15;   // past the end: a clear outlier for every finite model
+      if (i < n) load_pt(pts, off + i, X, x1, y1, x2, y2);
+      a[h][0] = static_cast<float>(x1); a[h][1] = static_cast<float>(y1);
+      a[h][2] = static_cast<float>(x2); a[h][3] = static_cast<float>(y2);
+    }
+    px1[q / 2] = pk(a[0][0], a[1][0]); py1[q / 2] = pk(a[0][1], a[1][1]);
+    px2[q / 2] = pk(a[0][2], a[1][2]); py2[q / 2] = pk(a[0][3], a[1][3]);
+  }
+  const f32x2 thr2 = pk(thr_f, thr_f), neg1 = pk(-1.0f, -1.0f), lo2 = pk(0.99f, 0.99f), hi2 = pk(1.01f, 1.01f);
+  for (int m = 0; m < n_chunk; ++m) {
+    const float4* mp = reinterpret_cast<const float4*>(sh.chunk_f[m]);
+    const float4 m0 = mp[0], m1 = mp[1], m2 = mp[2];
+    const f32x2 M[9] = {pk(m0.x, m0.x), pk(m0.y, m0.y), pk(m0.z, m0.z), pk(m0.w, m0.w), pk(m1.x, m1.x),
+                        pk(m1.y, m1.y), pk(m1.z, m1.z), pk(m1.w, m1.w), pk(m2.x, m2.x)};
+    int c_in = 0, c_maybe = 0;
+    bool odd = false;   // a non-finite quantity fails both comparisons consistently only if it is caught here
+#pragma unroll
+    for (int q = 0; q < PPT / 2; ++q) {
+      f32x2 lhs, rhs;
+      test_f32x2<KIND>(M, px1[q], py1[q], px2[q], py2[q], thr2, neg1, lhs, rhs);
+      float l0, l1, ri0, ri1, ro0, ro1;
+      upk(lhs, l0, l1);
+      upk(mul2(rhs, lo2), ri0, ri1);
+      upk(mul2(rhs, hi2), ro0, ro1);
+      c_in += (l0 <= ri0) + (l1 <= ri1);
+      c_maybe += (l0 < ro0) + (l1 < ro1);
+      odd |= !(l0 == l0) | !(l1 == l1) | !(ro0 == ro0) | !(ro1 == ro1);
+    }
+    int c = c_in;
+    if (c_maybe != c_in || odd) {  // rare: a borderline (or non-finite) match -> this thread's matches of this model in fp64
+      c = 0;
+      for (int q = 0; q < PPT; ++q) {
+        const int i = pb + q * kRansacThreads + tid;
+        if (i < n) {
+          double x1, y1, x2, y2;
+          load_pt(pts, off + i, X, x1, y1, x2, y2);
+          c += (residual<KIND>(sh.chunk_d[m], x1, y1, x2, y2) <= thr) ? 1 : 0;
+        }
+      }
+    }
+    if (c) atomicAdd(&sh.chunk_cnt[m], c);
+  }
+}
+
 #define B2M_TICK(slot)                                   \
   do {                                                   \
     if (P.prof && tid == 0) {                            \
@@ -248,9 +348,13 @@ __device__ __forceinline__ void score_block(Shared& sh, const double4* pts, int6
     }                                                    \
   } while (0)
 
-// WARP_MIN (E only): the minimal 5-point solves of a round run one WARP per hypothesis (five_point_warp.cuh) instead
-// of one thread per hypothesis (geom.h minimal_E5); the local-optimisation solve is always the warp solver.
-template <int KIND, bool WARP_MIN>
+// MIN_MODE (E only): how the minimal 5-point solves of a round are mapped.  0: one THREAD per hypothesis (geom.h
+// minimal_E5); 1: one WARP per hypothesis (five_point_warp.cuh); 2: hybrid -- the elimination (the memory-heavy,
+// regular half) one warp per hypothesis, the root refinement + models (latency-bound, irregular) one thread per
+// hypothesis.  The local-optimisation solve is always the warp solver.
+constexpr int kEStride = 200;  // doubles of scratch per hypothesis: models [0, 90), N [90, 126), polynomial [126, 137), Mr [137, 197)
+constexpr int kEN = 90, kEPoly = 126, kEMr = 137;
+template <int KIND, int MIN_MODE>
 __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int64_t off, int n,
                                const PointXform& X, double thr, uint64_t key, const b2m_ransac_opts& ro) {
   using T = Traits<KIND>;
@@ -284,9 +388,10 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
   unsigned long long n_scored = 0;  // models whose residuals were evaluated over all n matches (thread 0 keeps the tally)
   // models of this thread's hypothesis: registers / local memory for F and H, the CTA's slice of the global scratch
   // for E (written by the warp-cooperative solver)
-  constexpr bool kWarpMin = KIND == 0 && WARP_MIN;
+  constexpr bool kWarpMin = KIND == 0 && MIN_MODE != 0;
+  constexpr bool kHybrid = KIND == 0 && MIN_MODE == 2;
   double mdl_local[kWarpMin ? 1 : T::kMaxModels * 9];
-  double* const e_models = kWarpMin ? P.e_scratch + (static_cast<size_t>(pair) * kRansacThreads + tid) * 90 : nullptr;
+  double* const e_models = kWarpMin ? P.e_scratch + (static_cast<size_t>(pair) * kRansacThreads + tid) * kEStride : nullptr;
   double* const mdl = kWarpMin ? e_models : mdl_local;
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long prof_t = clock64();
@@ -322,7 +427,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
         for (int i = 0; i < 5; ++i) epipolar_row(x1[i], y1[i], x2[i], y2[i], A + 9 * i);
         nm = nullspace_gauss<5>(A, Nb) ? 1 : 0;
         if (nm)
-          for (int k = 0; k < 36; ++k) e_models[k] = Nb[k];
+          for (int k = 0; k < 36; ++k) e_models[kEN + k] = Nb[k];
       }
       if (KIND == 1) nm = minimal_F7(x1, y1, x2, y2, mdl);
       if (KIND == 2) nm = minimal_H4_closed(x1, y1, x2, y2, mdl);
@@ -334,16 +439,25 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       for (int h = warp; h < nb; h += kRansacThreads / 32) {
         int cnt = 0;
         if (sh.scan[h]) {   // uniform in the warp
-          double* hm = P.e_scratch + (static_cast<size_t>(pair) * kRansacThreads + h) * 90;
-          for (int k = lane; k < 36; k += 32) WS.N[k] = hm[k];
+          double* hm = P.e_scratch + (static_cast<size_t>(pair) * kRansacThreads + h) * kEStride;
+          for (int k = lane; k < 36; k += 32) WS.N[k] = hm[kEN + k];
           __syncwarp();
-          cnt = fpw::five_point_warp(WS, hm, lane);
+          if (kHybrid) {
+            cnt = fpw::eliminate_warp(WS, lane) ? 1 : 0;
+            if (cnt) {
+              if (lane < 11) hm[kEPoly + lane] = WS.ladder[0][lane];
+              for (int k = lane; k < 60; k += 32) hm[kEMr + k] = (&WS.Mr[0][0])[k];
+            }
+          } else {
+            cnt = fpw::five_point_warp(WS, hm, lane);
+          }
         }
         __syncwarp();
         if (lane == 0) sh.scan[h] = cnt;
       }
       __syncthreads();
       nm = tid < nb ? sh.scan[tid] : 0;
+      if (kHybrid && nm) nm = fpw::finish_thread(e_models + kEN, e_models + kEPoly, e_models + kEMr, e_models);
       __syncthreads();
     }
     // ---- phase 2: score every model of every hypothesis of this warp (warp = one model at a time)
@@ -381,7 +495,12 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       for (int pb = 0; pb < n; pb += kRansacThreads * kPtsPerThread) {
         // the last block takes as few point slots per thread as cover it (a slot past the end costs a full test)
         const int rem = n - pb;
-        if (rem > 4 * kRansacThreads) score_block<KIND, 8>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
+        if (P.packed_score) {
+          if (rem > 4 * kRansacThreads) score_block_x2<KIND, 8>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
+          else if (rem > 2 * kRansacThreads) score_block_x2<KIND, 4>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
+          else if (rem > kRansacThreads) score_block_x2<KIND, 2>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
+          else score_block<KIND, 1>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
+        } else if (rem > 4 * kRansacThreads) score_block<KIND, 8>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
         else if (rem > 2 * kRansacThreads) score_block<KIND, 4>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
         else if (rem > kRansacThreads) score_block<KIND, 2>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
         else score_block<KIND, 1>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
@@ -616,7 +735,7 @@ struct KindBlocks<1> { static constexpr int v = 4; };
 template <>
 struct KindBlocks<2> { static constexpr int v = 5; };
 
-template <int KIND, bool WARP_MIN = false>
+template <int KIND, int MIN_MODE = 0>
 __global__ void __launch_bounds__(kRansacThreads, KindBlocks<KIND>::v) b2m_ransac_kernel(const VerifyParams P) {
   __shared__ Shared sh;
   const int pair = blockIdx.x;
@@ -655,7 +774,7 @@ __global__ void __launch_bounds__(kRansacThreads, KindBlocks<KIND>::v) b2m_ransa
   const uint64_t key = splitmix64(P.seed ^ splitmix64((static_cast<uint64_t>(static_cast<uint32_t>(i1)) << 34) ^
                                                         (static_cast<uint64_t>(static_cast<uint32_t>(i2)) << 2) ^
                                                         static_cast<uint64_t>(kind)));
-  ransac_problem<KIND, WARP_MIN>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
+  ransac_problem<KIND, MIN_MODE>(P, sh, pair, off, n, X, thr, key, P.opt.ransac);
 }
 
 // The three model kinds are independent problems: E and F go to two side streams so that their
@@ -871,16 +990,24 @@ __global__ void __launch_bounds__(256) b2m_undistort_kernel(const VerifyParams P
   }
 }
 
-// B2M_E5_MINIMAL = thread | warp: how the minimal 5-point solves of a RANSAC round are mapped (A/B switch; the
-// default is what measured faster on B200).
-bool e5_warp_minimal() {
+// B2M_E5_MINIMAL = thread | warp | hybrid: how the minimal 5-point solves of a RANSAC round are mapped (A/B switch; the
+// default is what measured fastest on B200).
+int e5_minimal_mode() {
   static const int v = [] {
     const char* e = getenv("B2M_E5_MINIMAL");
     if (e && !strcmp(e, "warp")) return 1;
+    if (e && !strcmp(e, "hybrid")) return 2;
     if (e && !strcmp(e, "thread")) return 0;
-    return 1;
+    return 0;
   }();
-  return v != 0;
+  return v;
+}
+void launch_e_kernel(const VerifyParams& PE, int nb, cudaStream_t st) {
+  switch (e5_minimal_mode()) {
+    case 1: b2m_ransac_kernel<0, 1><<<nb, kRansacThreads, 0, st>>>(PE); break;
+    case 2: b2m_ransac_kernel<0, 2><<<nb, kRansacThreads, 0, st>>>(PE); break;
+    default: b2m_ransac_kernel<0, 0><<<nb, kRansacThreads, 0, st>>>(PE); break;
+  }
 }
 
 // `pts_E` (optional): the arena the E kernel reads instead of P.pts (output of b2m_undistort_kernel).
@@ -891,8 +1018,7 @@ cudaError_t launch_ransac(const VerifyParams& P_in, int nb, cudaStream_t st, Ran
   if (pts_E) PE.pts = pts_E;
   if (P.single_kind >= 0 || !rs || !rs->side[0]) {
     if (P.single_kind < 0 || P.single_kind == 0) {
-      if (e5_warp_minimal()) b2m_ransac_kernel<0, true><<<nb, kRansacThreads, 0, st>>>(PE);
-      else b2m_ransac_kernel<0, false><<<nb, kRansacThreads, 0, st>>>(PE);
+      launch_e_kernel(PE, nb, st);
     }
     if (P.single_kind < 0 || P.single_kind == 1) b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, st>>>(P);
     if (P.single_kind < 0 || P.single_kind == 2) b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
@@ -902,8 +1028,7 @@ cudaError_t launch_ransac(const VerifyParams& P_in, int nb, cudaStream_t st, Ran
   if (e != cudaSuccess) return e;
   cudaStreamWaitEvent(rs->side[0], rs->fork, 0);
   cudaStreamWaitEvent(rs->side[1], rs->fork, 0);
-  if (e5_warp_minimal()) b2m_ransac_kernel<0, true><<<nb, kRansacThreads, 0, rs->side[0]>>>(PE);
-  else b2m_ransac_kernel<0, false><<<nb, kRansacThreads, 0, rs->side[0]>>>(PE);
+  launch_e_kernel(PE, nb, rs->side[0]);
   b2m_ransac_kernel<1><<<nb, kRansacThreads, 0, rs->side[1]>>>(P);
   b2m_ransac_kernel<2><<<nb, kRansacThreads, 0, st>>>(P);
   cudaEventRecord(rs->join[0], rs->side[0]);
@@ -1217,6 +1342,16 @@ VerifyState* vstate(b2m_ctx* ctx) {
     }                                                                                       \
   } while (0)
 
+// B2M_SCORE = scalar | packed: the hypothesis-scoring sweep one match or two matches (fp32x2) per instruction
+int packed_score_default() {
+  static const int v = [] {
+    const char* e = getenv("B2M_SCORE");
+    if (e && !strcmp(e, "scalar")) return 0;
+    return 1;
+  }();
+  return v;
+}
+
 unsigned long long* verify_counters(b2m_ctx* ctx) {
   if (!ctx->d_verify_counters) {
     if (cudaMalloc(&ctx->d_verify_counters, sizeof(unsigned long long) * 6) != cudaSuccess) {
@@ -1271,7 +1406,7 @@ int ensure_verify_ws(b2m_ctx* ctx, int batch, int64_t arena_cap) {
     V_TRY(ctx, cudaMallocHost(&V->h_inliers[s], sizeof(uint2) * arena_cap));
   }
   V_TRY(ctx, cudaMalloc(&V->d_mask, 3 * arena_cap));
-  V_TRY(ctx, cudaMalloc(&V->d_e_scratch, sizeof(double) * 90 * kRansacThreads * static_cast<size_t>(batch)));
+  V_TRY(ctx, cudaMalloc(&V->d_e_scratch, sizeof(double) * kEStride * kRansacThreads * static_cast<size_t>(batch)));
   V_TRY(ctx, cudaMalloc(&V->d_sup, sizeof(int32_t) * 3 * batch));
   V_TRY(ctx, cudaMalloc(&V->d_success, sizeof(int32_t) * 3 * batch));
   V->batch = batch;
@@ -1391,6 +1526,7 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
   }
   P.prof = V->d_prof;
   P.counters = verify_counters(ctx);
+  P.packed_score = packed_score_default();
   P.e_scratch = V->d_e_scratch;
   if (!V->rs.side[0]) {
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[0], cudaStreamNonBlocking));
@@ -1670,7 +1806,7 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   V_TRY(ctx, cudaMalloc(&G.d_i32, sizeof(int32_t) * 16));
   V_TRY(ctx, cudaMalloc(&G.d_off, sizeof(int64_t)));
   V_TRY(ctx, cudaMalloc(&G.d_models, sizeof(double) * 27));
-  V_TRY(ctx, cudaMalloc(&G.d_e_scratch, sizeof(double) * 90 * kRansacThreads));
+  V_TRY(ctx, cudaMalloc(&G.d_e_scratch, sizeof(double) * kEStride * kRansacThreads));
   const int32_t i32[16] = {0, 1, static_cast<int32_t>(m), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const int64_t off0 = 0;
   cudaStream_t st = ctx->stream;
@@ -1701,6 +1837,7 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   P.seed = ctx->seed;
   P.single_kind = single_kind;
   P.counters = verify_counters(ctx);
+  P.packed_score = packed_score_default();
   P.e_scratch = G.d_e_scratch;
   if (single_kind >= 0) {
     V_TRY(ctx, launch_ransac(P, 1, st));
@@ -1976,7 +2113,7 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     V_TRY(ctx, cudaMalloc(&G.d_i32, sizeof(int32_t) * 11 * nb));
     V_TRY(ctx, cudaMalloc(&G.d_off, sizeof(int64_t) * nb));
     V_TRY(ctx, cudaMalloc(&G.d_models, sizeof(double) * 27 * nb));
-    V_TRY(ctx, cudaMalloc(&G.d_e_scratch, sizeof(double) * 90 * kRansacThreads * static_cast<size_t>(nb)));
+    V_TRY(ctx, cudaMalloc(&G.d_e_scratch, sizeof(double) * kEStride * kRansacThreads * static_cast<size_t>(nb)));
     d_i32 = G.d_i32;
     if (total > 0) {
       V_TRY(ctx, cudaMemcpyAsync(G.d_pts, pts.data(), sizeof(double4) * total, cudaMemcpyHostToDevice, st));
@@ -2007,6 +2144,7 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     P.seed = ctx->seed;
     P.single_kind = -1;
     P.counters = verify_counters(ctx);
+    P.packed_score = packed_score_default();
     P.e_scratch = G.d_e_scratch;
     const double4* pts_E = nullptr;
     if (int rc = undistort_for_E(ctx, G, P, full_cams.data(), 2 * nb, nb, cap, st, &pts_E)) return rc;

@@ -747,6 +747,12 @@ PYBIND11_MODULE(_core, m) {
           return py::make_tuple(first, count);
         },
         "n_images"_a, "n_ranks"_a, "rank"_a, "The contiguous image range rank `rank` uploads (b2m_comm_image_range)");
+  m.def("last_pipeline_timing", []() {
+    const PipelineTiming t = LastPipelineTiming();
+    return py::dict("read_s"_a = t.read_s, "upload_s"_a = t.upload_s, "gpu_s"_a = t.gpu_s, "write_s"_a = t.write_s,
+                    "write_wait_s"_a = t.write_wait_s, "total_s"_a = t.total_s, "pairs"_a = t.pairs,
+                    "sharded_upload"_a = t.sharded_upload);
+  }, "Wall-clock breakdown of the last match_* / verify_matches call of this process");
   m.def("parse_gpu_indices", &ParseGpuIndices, "gpu_index"_a);
   m.def("split_pairs_by_cost",
         [](const ArrI32& pairs, const std::vector<int32_t>& n_feat, int parts) {

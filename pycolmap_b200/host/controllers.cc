@@ -3,10 +3,13 @@
 #include "../csrc/camera_models.h"  // header-only; model ids / parameter counts shared with the kernels
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <set>
@@ -16,6 +19,12 @@
 #include <unordered_map>
 
 namespace b2mh {
+
+namespace {
+PipelineTiming g_timing;
+double Now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+PipelineTiming LastPipelineTiming() { return g_timing; }
 
 // ---- option conversion ---------------------------------------------------------------------------
 b2m_sift_opts ToAbi(const SiftMatchingOptions& o) {
@@ -336,6 +345,7 @@ std::vector<float> KeypointPositions(Database& db, int64_t image_id) {
 // of the images over PCIe and ONE all-gather over NVLink makes the set resident everywhere
 // (b2m_set_images_sharded); without NCCL every GPU uploads the whole set.
 void UploadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, LoadedSet* L) {
+  const double t_read0 = Now();
   const size_t n = L->ids.size();
   std::vector<DescriptorsBlob> desc(n);
   L->xy.assign(n, {});
@@ -348,6 +358,8 @@ void UploadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, LoadedSet* 
     L->n_feat[i] = static_cast<int32_t>(desc[i].rows);
   }
   const int32_t n_images = static_cast<int32_t>(n);
+  const double t_up0 = Now();
+  g_timing.read_s += t_up0 - t_read0;
   std::vector<int> rc(ctxs.size(), B2M_OK);
   const bool sharded = ctxs.size() > 1 && Engine::EnsureLocalComm(ctxs);
   auto upload = [&](size_t d) {
@@ -386,6 +398,8 @@ void UploadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, LoadedSet* 
   for (std::thread& w : workers) w.join();
   for (size_t d = 0; d < ctxs.size(); ++d) ThrowOnError(ctxs[d], rc[d]);
   L->uploaded = true;
+  g_timing.upload_s += Now() - t_up0;
+  g_timing.sharded_upload = sharded;
 }
 
 Mat3 ToMat3(const double* p) {
@@ -502,6 +516,24 @@ void MatchPairsIntoDb(Database& db, const std::vector<b2m_ctx*>& ctxs, const Loa
     have_g = db.ExistingPairIds("two_view_geometries");
   }
   std::vector<std::pair<int, int>> stored_only;
+  std::thread writer;
+  std::exception_ptr writer_error;
+  auto join_writer = [&]() {
+    const double t0 = Now();
+    if (writer.joinable()) writer.join();
+    g_timing.write_wait_s += Now() - t0;
+    if (writer_error) {
+      std::exception_ptr e = writer_error;
+      writer_error = nullptr;
+      std::rethrow_exception(e);
+    }
+  };
+  struct JoinOnExit {   // an exception on the GPU side must not leave a running thread behind (std::terminate)
+    std::thread& t;
+    ~JoinOnExit() {
+      if (t.joinable()) t.join();
+    }
+  } join_on_exit{writer};
   for (const PairList& chunk : chunks) {
     PairList todo;
     for (size_t k = 0; k + 1 < chunk.size(); k += 2) {
@@ -520,6 +552,7 @@ void MatchPairsIntoDb(Database& db, const std::vector<b2m_ctx*>& ctxs, const Loa
       todo.push_back(b);
     }
     if (!stored_only.empty()) {
+      join_writer();   // one writer at a time on the connection
       VerifyStoredPairs(db, ctxs[0], L, stored_only, tvg);
       stored_only.clear();
     }
@@ -536,43 +569,73 @@ void MatchPairsIntoDb(Database& db, const std::vector<b2m_ctx*>& ctxs, const Loa
       const int64_t n = cut[d + 1] - cut[d];
       if (n > 0) rc[d] = b2m_match_pairs(ctxs[d], todo.data() + 2 * cut[d], n, &sift, &tvg_batch, &res[d].r);
     };
+    const double t_gpu0 = Now();
     std::vector<std::thread> workers;
     for (size_t d = 1; d < ctxs.size(); ++d) workers.emplace_back(run, d);
     run(0);
     for (std::thread& w : workers) w.join();
-    for (size_t d = 0; d < ctxs.size(); ++d) ThrowOnError(ctxs[d], rc[d]);
-    DatabaseTransaction tx(&db);
+    g_timing.gpu_s += Now() - t_gpu0;
+    g_timing.pairs += static_cast<int64_t>(todo.size() / 2);
     for (size_t d = 0; d < ctxs.size(); ++d) {
-      const int64_t n = res[d].r ? b2m_results_num_pairs(res[d].r) : 0;
-      for (int64_t k = 0; k < n; ++k) {
-        b2m_pair_view v;
-        memset(&v, 0, sizeof(v));
-        v.struct_size = sizeof(v);
-        ThrowOnError(ctxs[d], b2m_results_get(res[d].r, k, &v));
-        const int32_t a = todo[2 * (cut[d] + k)], b = todo[2 * (cut[d] + k) + 1];
-        const int64_t id1 = L.ids[a], id2 = L.ids[b];
-        db.WriteMatches(id1, id2, v.matches, v.n_matches);
-        if (tvg.multiple_models && v.config != B2M_UNDEFINED && v.n_matches > 0) {
-          auto as_double = [](const std::vector<float>& f) { return std::vector<double>(f.begin(), f.end()); };
-          const std::vector<double> p1 = as_double(L.xy[a]), p2 = as_double(L.xy[b]);
-          b2m_tvg_result r;
-          memset(&r, 0, sizeof(r));
-          r.struct_size = sizeof(r);
-          std::vector<uint32_t> inl(static_cast<size_t>(v.n_matches) * 2);
-          ThrowOnError(ctxs[d], b2m_estimate_two_view_geometry(ctxs[d], &L.cams[a], p1.data(), static_cast<int64_t>(p1.size() / 2),
-                                                               &L.cams[b], p2.data(), static_cast<int64_t>(p2.size() / 2),
-                                                               v.matches, v.n_matches, &tvg, &r, inl.data()));
-          const bool keep = r.n_inliers >= tvg.min_num_inliers;   // controller write rule (row P3)
-          db.WriteTwoViewGeometry(id1, id2, keep ? r.config : B2M_UNDEFINED, inl.data(), keep ? r.n_inliers : 0,
-                                  keep ? ToMat3(r.F) : Mat3{}, keep ? ToMat3(r.E) : Mat3{}, keep ? ToMat3(r.H) : Mat3{},
-                                  {r.qvec[0], r.qvec[1], r.qvec[2], r.qvec[3]}, {r.tvec[0], r.tvec[1], r.tvec[2]});
-          continue;
+      if (rc[d] != B2M_OK) join_writer();   // do not leave the writer running behind an exception
+      ThrowOnError(ctxs[d], rc[d]);
+    }
+    // The chunk's results go to the database on a WRITER THREAD, one transaction per chunk, while the GPU(s) work on
+    // the next chunk.  multiple_models re-estimates on the GPU while writing: that stays
+    // on this thread (one in-flight call per context).
+    auto results = std::make_shared<std::vector<ResultsGuard>>(std::move(res));
+    auto todo_p = std::make_shared<PairList>(std::move(todo));
+    auto write_chunk = [&db, &ctxs, &L, &tvg, results, todo_p, cut]() {
+      const double t0 = Now();
+      const PairList& todo = *todo_p;
+      DatabaseTransaction tx(&db);
+      for (size_t d = 0; d < ctxs.size(); ++d) {
+        b2m_results* r_d = (*results)[d].r;
+        const int64_t n = r_d ? b2m_results_num_pairs(r_d) : 0;
+        for (int64_t k = 0; k < n; ++k) {
+          b2m_pair_view v;
+          memset(&v, 0, sizeof(v));
+          v.struct_size = sizeof(v);
+          ThrowOnError(ctxs[d], b2m_results_get(r_d, k, &v));
+          const int32_t a = todo[2 * (cut[d] + k)], b = todo[2 * (cut[d] + k) + 1];
+          const int64_t id1 = L.ids[a], id2 = L.ids[b];
+          db.WriteMatches(id1, id2, v.matches, v.n_matches);
+          if (tvg.multiple_models && v.config != B2M_UNDEFINED && v.n_matches > 0) {
+            auto as_double = [](const std::vector<float>& f) { return std::vector<double>(f.begin(), f.end()); };
+            const std::vector<double> p1 = as_double(L.xy[a]), p2 = as_double(L.xy[b]);
+            b2m_tvg_result r;
+            memset(&r, 0, sizeof(r));
+            r.struct_size = sizeof(r);
+            std::vector<uint32_t> inl(static_cast<size_t>(v.n_matches) * 2);
+            ThrowOnError(ctxs[d], b2m_estimate_two_view_geometry(ctxs[d], &L.cams[a], p1.data(), static_cast<int64_t>(p1.size() / 2),
+                                                                 &L.cams[b], p2.data(), static_cast<int64_t>(p2.size() / 2),
+                                                                 v.matches, v.n_matches, &tvg, &r, inl.data()));
+            const bool keep = r.n_inliers >= tvg.min_num_inliers;   // controller write rule (row P3)
+            db.WriteTwoViewGeometry(id1, id2, keep ? r.config : B2M_UNDEFINED, inl.data(), keep ? r.n_inliers : 0,
+                                    keep ? ToMat3(r.F) : Mat3{}, keep ? ToMat3(r.E) : Mat3{}, keep ? ToMat3(r.H) : Mat3{},
+                                    {r.qvec[0], r.qvec[1], r.qvec[2], r.qvec[3]}, {r.tvec[0], r.tvec[1], r.tvec[2]});
+            continue;
+          }
+          db.WriteTwoViewGeometry(id1, id2, v.config, v.inlier_matches, v.n_inliers, ToMat3(v.F), ToMat3(v.E),
+                                  ToMat3(v.H), {v.qvec[0], v.qvec[1], v.qvec[2], v.qvec[3]}, {v.tvec[0], v.tvec[1], v.tvec[2]});
         }
-        db.WriteTwoViewGeometry(id1, id2, v.config, v.inlier_matches, v.n_inliers, ToMat3(v.F), ToMat3(v.E),
-                                ToMat3(v.H), {v.qvec[0], v.qvec[1], v.qvec[2], v.qvec[3]}, {v.tvec[0], v.tvec[1], v.tvec[2]});
       }
+      g_timing.write_s += Now() - t0;
+    };
+    join_writer();                       // the previous chunk's transaction is committed before the next one opens
+    if (tvg.multiple_models) {
+      write_chunk();
+    } else {
+      writer = std::thread([write_chunk, &writer_error]() {
+        try {
+          write_chunk();
+        } catch (...) {
+          writer_error = std::current_exception();
+        }
+      });
     }
   }
+  join_writer();
 }
 
 // Concatenate block pair lists into chunks of >= `target` pairs: one GPU call + one transaction each.
@@ -595,6 +658,9 @@ std::vector<PairList> Chunked(const std::vector<PairList>& blocks, size_t target
 void MatchExhaustive(const std::string& database_path, const SiftMatchingOptions& sift,
                      const ExhaustiveMatchingOptions& matching, const TwoViewGeometryOptions& verification,
                      const std::vector<int>& devices) {
+  g_timing = PipelineTiming{};
+  const double t_total0 = Now();
+  struct Total { double t0; ~Total() { g_timing.total_s = Now() - t0; } } total_guard{t_total0};
   CheckFileExists(database_path, "match_features.h:32");
   if (matching.block_size <= 1) throw std::invalid_argument("[controllers.cc] Check Failed: block_size > 1");
   const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
@@ -608,6 +674,9 @@ void MatchExhaustive(const std::string& database_path, const SiftMatchingOptions
 void MatchSequential(const std::string& database_path, const SiftMatchingOptions& sift,
                      const SequentialMatchingOptions& matching, const TwoViewGeometryOptions& verification,
                      const std::vector<int>& devices) {
+  g_timing = PipelineTiming{};
+  const double t_total0 = Now();
+  struct Total { double t0; ~Total() { g_timing.total_s = Now() - t0; } } total_guard{t_total0};
   CheckFileExists(database_path, "match_features.h:32");
   if (matching.loop_detection)
     throw std::invalid_argument("[controllers.cc] loop_detection needs a vocabulary tree: out of scope (SURVEY.md row B6)");
@@ -623,6 +692,9 @@ void MatchSequential(const std::string& database_path, const SiftMatchingOptions
 
 void MatchSpatial(const std::string& database_path, const SiftMatchingOptions& sift, const SpatialMatchingOptions& matching,
                   const TwoViewGeometryOptions& verification, const std::vector<int>& devices) {
+  g_timing = PipelineTiming{};
+  const double t_total0 = Now();
+  struct Total { double t0; ~Total() { g_timing.total_s = Now() - t0; } } total_guard{t_total0};
   CheckFileExists(database_path, "match_features.h:32");
   if (matching.max_num_neighbors < 1) throw std::invalid_argument("[controllers.cc] Check Failed: max_num_neighbors > 0");
   if (!(matching.max_distance > 0.0)) throw std::invalid_argument("[controllers.cc] Check Failed: max_distance > 0");
@@ -640,6 +712,9 @@ void MatchSpatial(const std::string& database_path, const SiftMatchingOptions& s
 
 void VerifyMatches(const std::string& database_path, const std::string& pairs_path,
                    const TwoViewGeometryOptions& options) {
+  g_timing = PipelineTiming{};
+  const double t_total0 = Now();
+  struct Total { double t0; ~Total() { g_timing.total_s = Now() - t0; } } total_guard{t_total0};
   CheckFileExists(database_path, "match_features.h:54");
   CheckFileExists(pairs_path, "match_features.h:55");
   b2m_ctx* ctx = Engine::Get(0);

@@ -139,6 +139,16 @@ struct StoppedError : std::exception {
 // message "[<where>] Check Failed: File <path> does not exist."
 void CheckFileExists(const std::string& path, const char* where);
 
+// Wall-clock breakdown of the last pipeline call of this process (DB-inclusive end-to-end):
+// reading the database, uploading to the GPU(s), the b2m_match_pairs calls, writing (on the writer thread, overlapped
+// with the GPU) and the time the GPU side had to wait for the writer.
+struct PipelineTiming {
+  double read_s = 0, upload_s = 0, gpu_s = 0, write_s = 0, write_wait_s = 0, total_s = 0;
+  int64_t pairs = 0;
+  bool sharded_upload = false;
+};
+PipelineTiming LastPipelineTiming();
+
 // ---- pipelines -----------------------------------------------------------------------------------
 void MatchExhaustive(const std::string& database_path, const SiftMatchingOptions& sift,
                      const ExhaustiveMatchingOptions& matching, const TwoViewGeometryOptions& verification,

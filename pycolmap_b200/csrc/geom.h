@@ -138,28 +138,24 @@ B2M_HD inline int poly_real_roots(const double* coef, int deg_in, double* roots)
   }
   bound = 2.0 * bound * (1.0 + 1e-9);
   if (!(bound > 0.0)) bound = 1.0;
-  // derivative ladder, one level at a time: q = k-th derivative (degree deg - k), coefficient i = c[i + k] (i + k)
-  // (i + k - 1) ... (i + 1) with the factors applied in that order.  (Keeping all levels -- 10 x 11 doubles per
-  // thread -- in local memory was a sixth of the 5-point solver's footprint.)
-  double q[MAXD + 1];
-  auto level = [&](int k) {
-    for (int i = 0; i <= deg - k; ++i) {
-      double v = c[i + k];
-      for (int t = i + k; t > i; --t) v *= static_cast<double>(t);
-      q[i] = v;
-    }
-  };
+  // derivative ladder: d[k] = k-th derivative scaled (coefficients), degree deg-k.  (A one-level-at-a-time variant
+  // that rebuilds the coefficients per level from c[] was measured SLOWER inside the E kernel -- B2M_PROF `solve`
+  // 206 k -> 348 k Mcycles per two steps -- and was reverted.)
+  double d[MAXD][MAXD + 1];  // d[0] = p
+  for (int i = 0; i <= deg; ++i) d[0][i] = c[i];
+  for (int k = 1; k < deg; ++k)
+    for (int i = 0; i <= deg - k; ++i) d[k][i] = d[k - 1][i + 1] * (i + 1);
   double prev[MAXD], cur[MAXD];
   int nprev = 0;
-  // start from the linear polynomial (level deg - 1)
+  // start from the linear polynomial d[deg-1]
   {
-    level(deg - 1);
+    const double* q = d[deg - 1];
     prev[0] = -q[0] / q[1];
     nprev = 1;
   }
   for (int k = deg - 2; k >= 0; --k) {
     const int dg = deg - k;
-    level(k);
+    const double* q = d[k];
     int ncur = 0;
     double lo = -bound, flo = poly_eval(q, dg, lo);
     for (int i = 0; i <= nprev; ++i) {
@@ -339,6 +335,10 @@ B2M_HD inline void smallest_eigvecs_invit(const double* S45, double* out) {
   double rdiag[9];  // 1 / L(i, i): 9 divisions instead of 108 per basis vector (fp64 division is the slow op here)
   for (int i = 0; i < 9; ++i) rdiag[i] = 1.0 / L[i * 9 + i];
   for (int it = 0; it < 6; ++it) {
+    double before[9];  // K == 1: stop as soon as the iterate is stationary (inverse iteration converges geometrically
+                       // with ratio lambda_1 / lambda_2: two or three steps on the near-exact systems of the LO refits)
+    if (K == 1)
+      for (int i = 0; i < 9; ++i) before[i] = out[i];
     for (int k = 0; k < K; ++k) {
       double* v = out + k * 9;
       for (int i = 0; i < 9; ++i) {  // L y = v
@@ -364,6 +364,14 @@ B2M_HD inline void smallest_eigvecs_invit(const double* S45, double* out) {
       for (int i = 0; i < 9; ++i) nn += v[i] * v[i];
       const double inv = 1.0 / sqrt(nn > 0.0 ? nn : 1.0);
       for (int i = 0; i < 9; ++i) v[i] *= inv;
+    }
+    if (K == 1 && it > 0) {
+      double dp = 0.0, dm = 0.0;   // the iterate may flip its sign from step to step
+      for (int i = 0; i < 9; ++i) {
+        dp += (out[i] - before[i]) * (out[i] - before[i]);
+        dm += (out[i] + before[i]) * (out[i] + before[i]);
+      }
+      if ((dp < dm ? dp : dm) < 1e-30) break;
     }
   }
 }

@@ -72,7 +72,6 @@ struct VerifyParams {
   int32_t force_calibrated;   // stand-alone: -1 use camera flags
   unsigned long long* prof;   // optional [3][8] cycle counters (B2M_PROF=1), else nullptr
   unsigned long long* counters;  // [6] models scored / residual evaluations per kind (b2m_stats), or nullptr
-  int32_t packed_score;       // hypothesis scoring with FFMA2 / FMUL2 (two matches per instruction); B2M_SCORE=scalar turns it off
   double* e_scratch;          // E kernel, warp / hybrid minimal solves: [nb][kRansacThreads][kEStride] (models, N, polynomial, Mr)
   // guided matching hand-over (written by the decision kernel when guided_min_inliers >= 0)
   int32_t* guided_kind;       // [nb] -1 / 0 (F) / 1 (H)
@@ -139,47 +138,6 @@ __device__ __forceinline__ int inlier_f32(const float* M, float x1, float y1, fl
   return in | ((in | out) ^ 1) << 1;  // bit 0: inlier, bit 1: borderline (neither clearly in nor out)
 }
 
-// ---- packed fp32x2 (FFMA2 / FMUL2 on sm_100): the same tests on TWO matches per instruction ---------------------
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-// lhs and thr * rhs of the division-free test for two matches (x1, y1, x2, y2 packed); M[k] = (m_k, m_k)
-template <int KIND>
-__device__ __forceinline__ void test_f32x2(const f32x2* M, f32x2 x1, f32x2 y1, f32x2 x2, f32x2 y2, f32x2 thr2, f32x2 neg1,
-                                           f32x2& lhs, f32x2& rhs) {
-  if (KIND == 2) {
-    const f32x2 u = fma2(M[0], x1, fma2(M[1], y1, M[2]));
-    const f32x2 v = fma2(M[3], x1, fma2(M[4], y1, M[5]));
-    const f32x2 w = fma2(M[6], x1, fma2(M[7], y1, M[8]));
-    const f32x2 ex = fma2(x2, w, mul2(u, neg1)), ey = fma2(y2, w, mul2(v, neg1));
-    lhs = fma2(ex, ex, mul2(ey, ey));
-    rhs = mul2(mul2(thr2, w), w);
-  } else {
-    const f32x2 a0 = fma2(M[0], x1, fma2(M[1], y1, M[2]));
-    const f32x2 a1 = fma2(M[3], x1, fma2(M[4], y1, M[5]));
-    const f32x2 a2 = fma2(M[6], x1, fma2(M[7], y1, M[8]));
-    const f32x2 b0 = fma2(M[0], x2, fma2(M[3], y2, M[6]));
-    const f32x2 b1 = fma2(M[1], x2, fma2(M[4], y2, M[7]));
-    const f32x2 num = fma2(x2, a0, fma2(y2, a1, a2));
-    lhs = mul2(num, num);
-    rhs = mul2(thr2, fma2(a0, a0, fma2(a1, a1, fma2(b0, b0, mul2(b1, b1)))));
-  }
-}
-
 template <int KIND>
 struct Traits;
 template <>
@@ -215,6 +173,7 @@ struct Shared {
   double best_sum;
   int winner;
   int improved;
+  int round_max;         // largest (partial) inlier count among the models of the current round, for the exact pruning
   double norm[6];        // s1, cx1, cy1, s2, cx2, cy2
 };
 
@@ -237,12 +196,14 @@ __device__ __forceinline__ void warp_score(const double* M, const double4* pts, 
   sum = warp_sum_d(s);
 }
 
+// (A variant of this sweep on packed fp32x2 registers -- FFMA2 / FMUL2, two matches per instruction -- measured no
+// faster on B200: H `score` 391 k vs 397 k Mcycles; the fp32 pipe, not instruction issue, is the limit.  Removed.)
 // Hypothesis scoring of one block of points: every thread keeps PPT matches (fp32) in registers and sweeps the
 // chunk's models: division-free fp32 test, fp64 only for the borderline points of a (thread, model).  Inlier counts
 // go to sh.chunk_cnt.
 template <int KIND, int PPT>
 __device__ __forceinline__ void score_block(Shared& sh, const double4* pts, int64_t off, const PointXform& X, int n, int pb,
-                                            int n_chunk, double thr, float thr_f, int tid) {
+                                            int n_chunk, double thr, float thr_f, int tid, int need) {
   float px1[PPT], py1[PPT], px2[PPT], py2[PPT];
 #pragma unroll
   for (int q = 0; q < PPT; ++q) {
@@ -254,6 +215,9 @@ __device__ __forceinline__ void score_block(Shared& sh, const double4* pts, int6
     px2[q] = static_cast<float>(x2); py2[q] = static_cast<float>(y2);
   }
   for (int m = 0; m < n_chunk; ++m) {
+    // exact pruning: a model that cannot reach `need + (matches not yet scored)` even if every remaining match were
+    // an inlier can neither beat the best model so far nor the leader of this round (uniform across the CTA)
+    if (sh.chunk_cnt[m] < need) continue;
     float Mf[12];
     const float4* mp = reinterpret_cast<const float4*>(sh.chunk_f[m]);
     const float4 m0 = mp[0], m1 = mp[1], m2 = mp[2];
@@ -278,64 +242,6 @@ __device__ __forceinline__ void score_block(Shared& sh, const double4* pts, int6
       }
     }
     if (c) atomicAdd(&sh.chunk_cnt[m], c);  // most hypotheses have (almost) no inliers: cheaper than a warp reduce
-  }
-}
-
-// score_block with two matches per instruction (PPT even).  Inliers are counted against 0.99 x and 1.01 x the
-// threshold; a (thread, model) whose two counts differ holds a borderline match and is redone in fp64, so the
-// decisions equal the fp64 evaluation exactly as in score_block.
-template <int KIND, int PPT>
-__device__ __forceinline__ void score_block_x2(Shared& sh, const double4* pts, int64_t off, const PointXform& X, int n, int pb,
-                                               int n_chunk, double thr, float thr_f, int tid) {
-  static_assert(PPT % 2 == 0, "two matches per packed register");
-  f32x2 px1[PPT / 2], py1[PPT / 2], px2[PPT / 2], py2[PPT / 2];
-#pragma unroll
-  for (int q = 0; q < PPT; q += 2) {
-    float a[2][4];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = pb + (q + h) * kRansacThreads + tid;
-      double x1 = 0, y1 = 0, x2 = 1e15, y2 = 1e15;   // past the end: a clear outlier for every finite model
-      if (i < n) load_pt(pts, off + i, X, x1, y1, x2, y2);
-      a[h][0] = static_cast<float>(x1); a[h][1] = static_cast<float>(y1);
-      a[h][2] = static_cast<float>(x2); a[h][3] = static_cast<float>(y2);
-    }
-    px1[q / 2] = pk(a[0][0], a[1][0]); py1[q / 2] = pk(a[0][1], a[1][1]);
-    px2[q / 2] = pk(a[0][2], a[1][2]); py2[q / 2] = pk(a[0][3], a[1][3]);
-  }
-  const f32x2 thr2 = pk(thr_f, thr_f), neg1 = pk(-1.0f, -1.0f), lo2 = pk(0.99f, 0.99f), hi2 = pk(1.01f, 1.01f);
-  for (int m = 0; m < n_chunk; ++m) {
-    const float4* mp = reinterpret_cast<const float4*>(sh.chunk_f[m]);
-    const float4 m0 = mp[0], m1 = mp[1], m2 = mp[2];
-    const f32x2 M[9] = {pk(m0.x, m0.x), pk(m0.y, m0.y), pk(m0.z, m0.z), pk(m0.w, m0.w), pk(m1.x, m1.x),
-                        pk(m1.y, m1.y), pk(m1.z, m1.z), pk(m1.w, m1.w), pk(m2.x, m2.x)};
-    int c_in = 0, c_maybe = 0;
-    bool odd = false;   // a non-finite quantity fails both comparisons consistently only if it is caught here
-#pragma unroll
-    for (int q = 0; q < PPT / 2; ++q) {
-      f32x2 lhs, rhs;
-      test_f32x2<KIND>(M, px1[q], py1[q], px2[q], py2[q], thr2, neg1, lhs, rhs);
-      float l0, l1, ri0, ri1, ro0, ro1;
-      upk(lhs, l0, l1);
-      upk(mul2(rhs, lo2), ri0, ri1);
-      upk(mul2(rhs, hi2), ro0, ro1);
-      c_in += (l0 <= ri0) + (l1 <= ri1);
-      c_maybe += (l0 < ro0) + (l1 < ro1);
-      odd |= !(l0 == l0) | !(l1 == l1) | !(ro0 == ro0) | !(ro1 == ro1);
-    }
-    int c = c_in;
-    if (c_maybe != c_in || odd) {  // rare: a borderline (or non-finite) match -> this thread's matches of this model in fp64
-      c = 0;
-      for (int q = 0; q < PPT; ++q) {
-        const int i = pb + q * kRansacThreads + tid;
-        if (i < n) {
-          double x1, y1, x2, y2;
-          load_pt(pts, off + i, X, x1, y1, x2, y2);
-          c += (residual<KIND>(sh.chunk_d[m], x1, y1, x2, y2) <= thr) ? 1 : 0;
-        }
-      }
-    }
-    if (c) atomicAdd(&sh.chunk_cnt[m], c);
   }
 }
 
@@ -469,6 +375,7 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
     int my_cnt = -1, my_m = 0;
     double my_sum = 1e300;
     sh.scan[tid] = nm;
+    if (tid == 0) sh.round_max = 0;
     __syncthreads();
     int my_base = 0, total_models = 0;
     for (int t = 0; t < kRansacThreads; ++t) {
@@ -492,18 +399,23 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
       }
       for (int m = tid; m < kChunkModels; m += kRansacThreads) sh.chunk_cnt[m] = 0;
       __syncthreads();
-      for (int pb = 0; pb < n; pb += kRansacThreads * kPtsPerThread) {
-        // the last block takes as few point slots per thread as cover it (a slot past the end costs a full test)
+      // Blocks of 512 matches.  Between blocks the inlier counts so far are complete (barrier), so a model whose count
+      // plus ALL remaining matches stays below the best of the earlier rounds or below what the leader of this round
+      // already has is dropped for the rest of the sweep -- exact: it could not have won, nor tied.
+      constexpr int kBlock = 4 * kRansacThreads;
+      for (int pb = 0; pb < n; pb += kBlock) {
         const int rem = n - pb;
-        if (P.packed_score) {
-          if (rem > 4 * kRansacThreads) score_block_x2<KIND, 8>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
-          else if (rem > 2 * kRansacThreads) score_block_x2<KIND, 4>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
-          else if (rem > kRansacThreads) score_block_x2<KIND, 2>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
-          else score_block<KIND, 1>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
-        } else if (rem > 4 * kRansacThreads) score_block<KIND, 8>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
-        else if (rem > 2 * kRansacThreads) score_block<KIND, 4>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
-        else if (rem > kRansacThreads) score_block<KIND, 2>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
-        else score_block<KIND, 1>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid);
+        int need = 0;
+        if (pb > 0) {
+          __syncthreads();   // chunk_cnt of the previous blocks is complete
+          for (int m = tid; m < n_chunk; m += kRansacThreads) atomicMax(&sh.round_max, sh.chunk_cnt[m]);
+          __syncthreads();
+          need = max(sh.best_cnt + 1, sh.round_max) - rem;
+        }
+        // the last block takes as few point slots per thread as cover it (a slot past the end costs a full test)
+        if (rem > 2 * kRansacThreads) score_block<KIND, 4>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid, need);
+        else if (rem > kRansacThreads) score_block<KIND, 2>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid, need);
+        else score_block<KIND, 1>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid, need);
       }
       __syncthreads();
       for (int m = 0; m < nm; ++m) {
@@ -998,7 +910,7 @@ int e5_minimal_mode() {
     if (e && !strcmp(e, "warp")) return 1;
     if (e && !strcmp(e, "hybrid")) return 2;
     if (e && !strcmp(e, "thread")) return 0;
-    return 0;
+    return 2;   // measured on B200 (1000 x 8192, B2M_PROF `solve` per two steps): thread 206-348 k, warp 651 k, hybrid 175 k Mcycles
   }();
   return v;
 }
@@ -1342,16 +1254,6 @@ VerifyState* vstate(b2m_ctx* ctx) {
     }                                                                                       \
   } while (0)
 
-// B2M_SCORE = scalar | packed: the hypothesis-scoring sweep one match or two matches (fp32x2) per instruction
-int packed_score_default() {
-  static const int v = [] {
-    const char* e = getenv("B2M_SCORE");
-    if (e && !strcmp(e, "scalar")) return 0;
-    return 1;
-  }();
-  return v;
-}
-
 unsigned long long* verify_counters(b2m_ctx* ctx) {
   if (!ctx->d_verify_counters) {
     if (cudaMalloc(&ctx->d_verify_counters, sizeof(unsigned long long) * 6) != cudaSuccess) {
@@ -1526,7 +1428,6 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
   }
   P.prof = V->d_prof;
   P.counters = verify_counters(ctx);
-  P.packed_score = packed_score_default();
   P.e_scratch = V->d_e_scratch;
   if (!V->rs.side[0]) {
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[0], cudaStreamNonBlocking));
@@ -1837,7 +1738,6 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   P.seed = ctx->seed;
   P.single_kind = single_kind;
   P.counters = verify_counters(ctx);
-  P.packed_score = packed_score_default();
   P.e_scratch = G.d_e_scratch;
   if (single_kind >= 0) {
     V_TRY(ctx, launch_ransac(P, 1, st));
@@ -2144,8 +2044,7 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     P.seed = ctx->seed;
     P.single_kind = -1;
     P.counters = verify_counters(ctx);
-    P.packed_score = packed_score_default();
-    P.e_scratch = G.d_e_scratch;
+      P.e_scratch = G.d_e_scratch;
     const double4* pts_E = nullptr;
     if (int rc = undistort_for_E(ctx, G, P, full_cams.data(), 2 * nb, nb, cap, st, &pts_E)) return rc;
     V_TRY(ctx, launch_ransac(P, nb, st, nullptr, pts_E));

@@ -639,7 +639,7 @@ void MatchPairsIntoDb(Database& db, const std::vector<b2m_ctx*>& ctxs, const Loa
 }
 
 // Concatenate block pair lists into chunks of >= `target` pairs: one GPU call + one transaction each.
-std::vector<PairList> Chunked(const std::vector<PairList>& blocks, size_t target = 65536) {
+std::vector<PairList> Chunked(const std::vector<PairList>& blocks, size_t target = 16384) {
   std::vector<PairList> out;
   PairList cur;
   for (const PairList& b : blocks) {

@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import ransac as R  # noqa: E402
-import pycolmap_b200.native as nat  # noqa: E402
+import pycolmap_b200 as nat  # noqa: E402
 from helpers import scenes  # noqa: E402
 
 n = int(os.environ.get("DIAG_N", "400"))

@@ -339,9 +339,12 @@ def main():
     t = torch.tensor([acc["dev_ms"], wall_ms, acc["k1_ms"], acc["ag_ms"]], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(len(my_pairs)), float(launches), float(last["n_ver"]), float(last["matches"])],
                        dtype=torch.float64, device=dev)
+    ag_min = torch.tensor([acc["ag_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(ag_min, op=dist.ReduceOp.MIN)
+    ag_ms_min = ag_min.item()
     dev_ms_max, wall_ms_max, k1_ms_max, ag_ms_max = t.tolist()
     pairs_total, launches_total, verified_total, matches_total = cnt.tolist()
     verified_fraction = verified_total / max(pairs_total, 1) if verify else 0.0
@@ -488,8 +491,11 @@ def main():
                              "b2m_match_pairs of every step, max over ranks"},
         "wall_ms_per_step": wall_ms_max / args.steps, "k1_ms_per_step": acc["k1_ms"] / args.steps,
         "compact_verify_ms_per_step": acc["ver_ms"] / args.steps,
-        "allgather": {"ms_per_step": ag_ms_max / args.steps, "bytes_received_per_rank": int(last["ag_bytes"]),
-                      "GBps_per_rank": (last["ag_bytes"] / 1e9) / max(acc["ag_ms"] / args.steps / 1e3, 1e-9) if world > 1 else None,
+        # max over ranks = what the step pays (it includes waiting for the slowest rank to ARRIVE: the ranks are not
+        # synchronised between steps); min over ranks = the last rank to arrive = the transfer itself
+        "allgather": {"ms_per_step": ag_ms_max / args.steps, "transfer_ms_per_step": ag_ms_min / args.steps,
+                      "bytes_received_per_rank": int(last["ag_bytes"]),
+                      "GBps_per_rank": (last["ag_bytes"] / 1e9) / max(ag_ms_min / args.steps / 1e3, 1e-9) if world > 1 else None,
                       "share_of_step": ag_ms_max / max(dev_ms_max, 1e-9),
                       "nvlink_peak_GBps": 900.0 if world > 1 else None},
         "upload_ms_per_step": acc["up_ms"] / args.steps,

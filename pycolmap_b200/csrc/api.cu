@@ -4,6 +4,7 @@
 // R:pipeline/match_features.h:22-68.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -178,6 +179,10 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
                      const b2m_tvg_opts* tvg, b2m_results** out) {
   if (!out) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: out != NULL");
   *out = nullptr;
+  // B2M_HOSTPROF=1: wall-clock split of this call on the host (set-up, launch loop, tail) on stderr
+  static const bool host_prof = getenv("B2M_HOSTPROF") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double hp_t0 = now();
   if (int rc = check_sift(ctx, sift)) return rc;
   if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: pairs");
   if (!S.d_desc) return fail(ctx, B2M_ESTATE, "[api.cu] b2m_set_images must be called before matching");
@@ -294,6 +299,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     return B2M_OK;
   };
 
+  const double hp_t1 = now();
   for (int64_t b = 0; b < n_batches; ++b) {
     if (ctx->stop) {
       cudaStreamSynchronize(st);
@@ -467,6 +473,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     if (b > 0)
       if (int rc = finish(b - 1)) return bail(rc);
   }
+  const double hp_t2 = now();
   if (n_batches > 0)
     if (int rc = finish(n_batches - 1)) return bail(rc);
   CU_TRY_R(cudaEventRecord(ctx->ev_t1, st));
@@ -477,6 +484,9 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
   ctx->stats.last_verify_ms = verify_ms;
   ctx->stats.last_match_ms = ms - verify_ms;
 #undef CU_TRY_R
+  if (host_prof)
+    fprintf(stderr, "[b2m hostprof] pairs %lld: set-up %.1f ms, launch loop %.1f ms, last batch + sync %.1f ms, device %.1f ms\n",
+            static_cast<long long>(n_pairs), hp_t1 - hp_t0, hp_t2 - hp_t1, now() - hp_t2, ms);
   ctx->hint_matches = res->matches.size() / 2;
   ctx->hint_inliers = res->inliers.size() / 2;
   *out = res;
@@ -920,9 +930,12 @@ int b2m_results_get(const b2m_results* r, int64_t pair, b2m_pair_view* out) {
     out->config = r->config[pair];
     out->n_inliers = r->in_cnt[pair];
     out->inlier_matches = r->in_cnt[pair] ? r->inliers.data() + 2 * r->in_off[pair] : nullptr;
-    memcpy(out->E, r->models.data() + 27 * pair, sizeof(double) * 9);
-    memcpy(out->F, r->models.data() + 27 * pair + 9, sizeof(double) * 9);
-    memcpy(out->H, r->models.data() + 27 * pair + 18, sizeof(double) * 9);
+    if (r->model_idx[pair] >= 0) {
+      const double* m = r->models.data() + 27 * static_cast<size_t>(r->model_idx[pair]);
+      memcpy(out->E, m, sizeof(double) * 9);
+      memcpy(out->F, m + 9, sizeof(double) * 9);
+      memcpy(out->H, m + 18, sizeof(double) * 9);
+    }
   }
   out->qvec[0] = 1.0;
   if (r->verified && !r->pose_valid.empty() && r->pose_valid[pair]) {

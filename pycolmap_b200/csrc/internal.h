@@ -127,7 +127,8 @@ struct b2m_results {
   std::vector<int64_t> in_off;
   std::vector<int32_t> in_cnt;
   std::vector<uint32_t> inliers;
-  std::vector<double> models;    // per pair 27 doubles: E, F, H
+  std::vector<int32_t> model_idx; // per pair: index into `models` (x 27), or -1 (no geometry: E = F = H = 0)
+  std::vector<double> models;    // 27 doubles (E, F, H) per pair that has a geometry -- ~10 % of an exhaustive run
   std::vector<double> poses;     // per pair 8 doubles: qvec (w, x, y, z), tvec, tri_angle (compute_relative_pose)
   std::vector<int32_t> pose_valid;
 };

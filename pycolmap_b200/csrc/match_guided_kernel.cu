@@ -192,6 +192,11 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + as * kTileN;
       uint32_t k1[4] = {0, 0, 0, 0}, k2[4] = {0, 0, 0, 0};
+      // LAZY geometric test: a dot product that does not exceed this row's running second best (over the CONSISTENT
+      // columns seen so far) cannot change (best, second) whether it is consistent or not -- the scan updates on
+      // strict `>` only -- so the float32 residual (25 separately rounded operations and a division) is evaluated
+      // only for the few columns that could still matter: after the first tile ~1 % of them.  Same result, bit for bit.
+      const uint32_t floor_d = static_cast<uint32_t>(second_d);
 #pragma unroll 1
       for (int c = 0; c < kTileN / 32; ++c) {
         uint32_t v[32];
@@ -199,11 +204,14 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float2 kc = kb[c * 32 + j];
-          // image 1 is pairs[2*pair], image 2 is pairs[2*pair+1]: in direction 1 rows are image 2
-          const bool ok = (dir == 0) ? consistent(gkind, M, kr.x, kr.y, kc.x, kc.y, thr)
-                                     : consistent(gkind, M, kc.x, kc.y, kr.x, kr.y, thr);
-          const uint32_t d = ok ? v[j] : 0u;
+          uint32_t d = 0u;
+          if (v[j] > floor_d) {
+            const float2 kc = kb[c * 32 + j];
+            // image 1 is pairs[2*pair], image 2 is pairs[2*pair+1]: in direction 1 rows are image 2
+            const bool ok = (dir == 0) ? consistent(gkind, M, kr.x, kr.y, kc.x, kc.y, thr)
+                                       : consistent(gkind, M, kc.x, kc.y, kr.x, kr.y, thr);
+            d = ok ? v[j] : 0u;
+          }
           const uint32_t key = (d << 8) | static_cast<uint32_t>(255 - (c * 32 + j));
           const uint32_t lo = min(k1[j & 3], key);
           k1[j & 3] = max(k1[j & 3], key);

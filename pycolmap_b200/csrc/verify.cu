@@ -1385,7 +1385,8 @@ void verify_results_init(b2m_results* res, int64_t n_pairs) {
   res->config.assign(n_pairs, B2M_UNDEFINED);
   res->in_off.assign(n_pairs, 0);
   res->in_cnt.assign(n_pairs, 0);
-  res->models.assign(27 * n_pairs, 0.0);
+  res->model_idx.assign(n_pairs, -1);
+  res->models.clear();
   res->poses.clear();
   res->pose_valid.clear();
 }
@@ -1556,7 +1557,8 @@ int verify_batch_collect(b2m_ctx* ctx, b2m_results* res, int s, int64_t p0, int 
       const size_t at = res->inliers.size();
       res->inliers.resize(at + 2 * static_cast<size_t>(ni));
       memcpy(res->inliers.data() + at, src, sizeof(uint2) * ni);
-      memcpy(res->models.data() + 27 * p, V->h_models[s] + 27 * k, sizeof(double) * 27);
+      res->model_idx[p] = static_cast<int32_t>(res->models.size() / 27);
+      res->models.insert(res->models.end(), V->h_models[s] + 27 * k, V->h_models[s] + 27 * k + 27);
     }
   }
   return B2M_OK;

@@ -48,6 +48,21 @@ void MergeDict(py::object self, const py::dict& d) {
       py::setattr(self, name.c_str(), item.second);
     } catch (py::error_already_set& e) {
       if (!e.matches(PyExc_TypeError)) throw;
+      // the reference's fallback (R:helpers.h:70-84): coerce the value through the bases of the attribute's class
+      // (an enum-like field given as int, a numpy scalar for a Python float, ...), then through the class itself
+      bool coerced = false;
+      py::object klass = cur.attr("__class__");
+      py::list candidates = klass.attr("__bases__").cast<py::list>();
+      candidates.append(klass);
+      for (py::handle base : candidates) {
+        try {
+          py::setattr(self, name.c_str(), base(item.second));
+          coerced = true;
+          break;
+        } catch (py::error_already_set&) {
+        }
+      }
+      if (coerced) continue;
       std::ostringstream ss;
       ss << cls << "." << name << ": Could not convert " << TypeNameOf(item.second) << ": "
          << py::str(item.second).cast<std::string>() << " to '" << TypeNameOf(cur) << "'.";

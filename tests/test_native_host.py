@@ -73,6 +73,18 @@ def test_dataclass_behaviour():
     assert cfg("WATERMARK").value == 7 and nat.has_cuda is True
 
 
+def test_mergedict_coerces_through_base_classes():
+    """R:helpers.h:70-84: a value pybind11 refuses (numpy scalars for bool / int fields) is retried through the bases of
+    the attribute's class and through the class itself; what cannot be coerced raises the reference's TypeError."""
+    o = nat.SiftMatchingOptions({"max_ratio": np.float32(0.75), "max_num_matches": np.int64(100), "cross_check": np.bool_(False)})
+    assert (o.max_ratio, o.max_num_matches, o.cross_check) == (0.75, 100, False)
+    t = nat.TwoViewGeometryOptions()
+    t.mergedict({"min_num_inliers": np.int32(20), "ransac": {"max_error": np.float64(2.0), "max_num_trials": np.uint16(500)}})
+    assert (t.min_num_inliers, t.ransac.max_error, t.ransac.max_num_trials) == (20, 2.0, 500)
+    with pytest.raises(TypeError, match="Failed to merge dict into class: Could not assign max_ratio"):
+        nat.SiftMatchingOptions({"max_ratio": "abc"})
+
+
 def test_pair_generators_match_oracle():
     for n, bs in [(1, 50), (2, 2), (49, 50), (50, 50), (51, 50), (101, 50), (7, 2), (130, 64), (0, 5)]:
         blocks = nat.exhaustive_pair_blocks(n, bs)

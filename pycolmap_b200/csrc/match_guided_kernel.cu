@@ -22,11 +22,12 @@ constexpr int kDim = 128;
 constexpr int kTileM = 128;
 constexpr int kTileN = 256;
 constexpr int kUmmaK = 32;
-constexpr int kStages = 3;
-constexpr int kAccStages = 2;
+constexpr int kStages = 2;     // two CTAs per SM (85 KB shared memory, 256 of the 512 TMEM columns each): the epilogue -- ~50 ALU
+constexpr int kAccStages = 1;  // instructions per matrix element -- is the bound, so resident epilogue warps are what counts
 constexpr int kBytesA = kTileM * kDim;
 constexpr int kBytesB = kTileN * kDim;
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;    // warp w: TMEM lane quarter w % 4 (32 rows), column half w / 4 (128 of the 256 columns of a tile)
+constexpr int kColGroups = kEpiWarps / 4;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kIdesc = make_idesc_u8u8_s32(kTileM, kTileN);
 
@@ -51,8 +52,12 @@ __device__ __forceinline__ void merge_top2(uint32_t& a1, uint32_t& a2, uint32_t 
 // 1 when the correspondence (x1, y1) in image 1 <-> (x2, y2) in image 2 is consistent with the model.
 // kind 0: F (squared Sampson error), kind 1: H (squared forward transfer error).  Same operation order
 // as orc_match_guided, every operation rounded separately.
+// thr_mid: the midpoint between thr and the next float above it, as a double; thr_even: thr's mantissa is even.
+// For the Sampson test the float division r = a / b is replaced by an EXACT equivalent of `fl(a / b) <= thr`:
+// the quotient rounds to a float <= thr iff a / b < thr_mid, or a / b == thr_mid and the tie goes to thr (even
+// mantissa); (double) b * thr_mid is exact (24 x 25 significand bits), so the comparison in double is exact too.
 __device__ __forceinline__ bool consistent(int kind, const float* M, float x1, float y1, float x2, float y2,
-                                           float thr) {
+                                           float thr, double thr_mid, bool thr_even) {
   float r;
   if (kind == 0) {
     const float Fx0 = __fadd_rn(__fadd_rn(__fmul_rn(M[0], x1), __fmul_rn(M[1], y1)), M[2]);
@@ -63,7 +68,11 @@ __device__ __forceinline__ bool consistent(int kind, const float* M, float x1, f
     const float num = __fadd_rn(__fadd_rn(__fmul_rn(x2, Fx0), __fmul_rn(y2, Fx1)), Fx2);
     const float den = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Fx0, Fx0), __fmul_rn(Fx1, Fx1)), __fmul_rn(Ft0, Ft0)),
                                 __fmul_rn(Ft1, Ft1));
-    r = __fdiv_rn(__fmul_rn(num, num), den);
+    const float a = __fmul_rn(num, num);
+    if (!(den > 0.0f) || !(a < __int_as_float(0x7f800000)) || !(den < __int_as_float(0x7f800000)))
+      return __fdiv_rn(a, den) <= thr;   // zero / infinite / NaN operands: the literal expression (never on real data)
+    const double lhs = static_cast<double>(a), rhs = static_cast<double>(den) * thr_mid;
+    return lhs < rhs || (lhs == rhs && thr_even);
   } else {
     const float w = __fadd_rn(__fadd_rn(__fmul_rn(M[6], x1), __fmul_rn(M[7], y1)), M[8]);
     const float u = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x1), __fmul_rn(M[1], y1)), M[2]), w);
@@ -76,7 +85,7 @@ __device__ __forceinline__ bool consistent(int kind, const float* M, float x1, f
 
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)  // 2 x 8 epilogue warps per SM
 b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p, const GuidedParams g) {
   const int pair = blockIdx.z;
   const int gkind = g.kind[pair];
@@ -169,17 +178,21 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
     }
   } else {
     // ===== epilogue: geometric mask, then exact running top-2 (thread <-> row) =====
-    const int row_in_strip = warp * 32 + lane;
+    const int quarter = warp & 3, group = warp >> 2;
+    const int row_in_strip = quarter * 32 + lane;
     const int row = strip * kTileM + row_in_strip;
     float M[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) M[k] = g.model[pair * 9 + k];
     const float thr = g.max_residual;
+    const float thr_next = __int_as_float(__float_as_int(thr) + 1);   // thr > 0: the next float above
+    const double thr_mid = 0.5 * (static_cast<double>(thr) + static_cast<double>(thr_next));
+    const bool thr_even = (__float_as_int(thr) & 1) == 0;
     const float2 kr = (row < nA) ? g.kpts[p.img_row0[ia] + row] : make_float2(0.f, 0.f);
     const float2* kcol = g.kpts + p.img_row0[ib];
     int32_t best_d = 0, best_c = -1, second_d = 0;
     uint32_t as = 0, aphase = 0;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t lane_base = (static_cast<uint32_t>(quarter * 32) << 16) + group * (kTileN / kColGroups);
     for (int t = 0; t < n_tiles; ++t) {
       // stage the 256 column keypoints of this tile (two per thread), double-buffered by tile parity
       float2* kb = kp_s + (t & 1) * kTileN;
@@ -197,8 +210,9 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
       // strict `>` only -- so the float32 residual (25 separately rounded operations and a division) is evaluated
       // only for the few columns that could still matter: after the first tile ~1 % of them.  Same result, bit for bit.
       const uint32_t floor_d = static_cast<uint32_t>(second_d);
+      const int col0 = group * (kTileN / kColGroups);   // this warp's columns of the tile
 #pragma unroll 1
-      for (int c = 0; c < kTileN / 32; ++c) {
+      for (int c = 0; c < kTileN / kColGroups / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_wait_ld();
@@ -206,13 +220,13 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
         for (int j = 0; j < 32; ++j) {
           uint32_t d = 0u;
           if (v[j] > floor_d) {
-            const float2 kc = kb[c * 32 + j];
+            const float2 kc = kb[col0 + c * 32 + j];
             // image 1 is pairs[2*pair], image 2 is pairs[2*pair+1]: in direction 1 rows are image 2
-            const bool ok = (dir == 0) ? consistent(gkind, M, kr.x, kr.y, kc.x, kc.y, thr)
-                                       : consistent(gkind, M, kc.x, kc.y, kr.x, kr.y, thr);
+            const bool ok = (dir == 0) ? consistent(gkind, M, kr.x, kr.y, kc.x, kc.y, thr, thr_mid, thr_even)
+                                       : consistent(gkind, M, kc.x, kc.y, kr.x, kr.y, thr, thr_mid, thr_even);
             d = ok ? v[j] : 0u;
           }
-          const uint32_t key = (d << 8) | static_cast<uint32_t>(255 - (c * 32 + j));
+          const uint32_t key = (d << 8) | static_cast<uint32_t>(255 - (col0 + c * 32 + j));
           const uint32_t lo = min(k1[j & 3], key);
           k1[j & 3] = max(k1[j & 3], key);
           k2[j & 3] = max(k2[j & 3], lo);
@@ -237,6 +251,27 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
         aphase ^= 1;
       }
     }
+    // merge the column halves of a row (group 1 -> shared memory -> group 0): the union's best is the larger dot
+    // product, the LOWER column on a tie; its second best = multiset second of the two (best, second) pairs
+    if (kColGroups > 1) {
+      int32_t* mg = reinterpret_cast<int32_t*>(kp_s);   // the keypoint staging buffer is free after the last tile
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+      if (group == 1) {
+        mg[row_in_strip * 3] = best_d;
+        mg[row_in_strip * 3 + 1] = second_d;
+        mg[row_in_strip * 3 + 2] = best_c;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+      if (group == 0) {
+        const int32_t ob = mg[row_in_strip * 3], os = mg[row_in_strip * 3 + 1], oc = mg[row_in_strip * 3 + 2];
+        const int32_t ns = max(max(second_d, os), min(best_d, ob));
+        if (ob > best_d || (ob == best_d && oc >= 0 && (best_c < 0 || oc < best_c))) {
+          best_d = ob;
+          best_c = oc;
+        }
+        second_d = ns;
+      }
+    }
     int32_t out = -1;
     if (best_d > 0) {
       const float a = __ldg(p.acos_lut + min(best_d, 262144));
@@ -245,7 +280,7 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
         if (!(a >= __fmul_rn(p.max_ratio, b))) out = best_c;
       }
     }
-    p.mbuf[(static_cast<int64_t>(pair) * 2 + dir) * p.mstride + row] = out;
+    if (group == 0) p.mbuf[(static_cast<int64_t>(pair) * 2 + dir) * p.mstride + row] = out;
   }
 
   tc_fence_before();

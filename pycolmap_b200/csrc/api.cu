@@ -58,7 +58,13 @@ PFN_encodeTiled get_encode_tiled() {
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // Lay out the image table and allocate the padded descriptor array (zero-filled).
+int layout_images_impl(b2m_ctx* ctx, ImageSet& S, int n_images, const int32_t* n_feat, bool want_kpts);
 int layout_images(b2m_ctx* ctx, ImageSet& S, int n_images, const int32_t* n_feat, bool want_kpts) {
+  const int rc = layout_images_impl(ctx, S, n_images, n_feat, want_kpts);
+  if (rc != B2M_OK) S.release();  // never leave a half-built set behind: a later match call would run on it
+  return rc;
+}
+int layout_images_impl(b2m_ctx* ctx, ImageSet& S, int n_images, const int32_t* n_feat, bool want_kpts) {
   S.release();
   static std::atomic<uint64_t> g_generation{0};
   S.generation = ++g_generation;
@@ -186,17 +192,24 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
   if (int rc = check_sift(ctx, sift)) return rc;
   if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: pairs");
   if (!S.d_desc) return fail(ctx, B2M_ESTATE, "[api.cu] b2m_set_images must be called before matching");
-  for (int64_t k = 0; k < 2 * n_pairs; ++k)
+  int32_t max_feat_used = 0;  // over the images the pair list references (the resident set may hold others)
+  for (int64_t k = 0; k < 2 * n_pairs; ++k) {
     if (pairs[k] < 0 || pairs[k] >= S.n_images)
       return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: pair image index out of range");
+    max_feat_used = std::max(max_feat_used, S.nfeat[pairs[k]]);
+  }
   if (tvg && (!S.d_kpts || S.cams.empty()))
     return fail(ctx, B2M_ESTATE, "[api.cu] verification requested but the image set has no keypoints/cameras");
   if (tvg && tvg->multiple_models)
     return fail(ctx, B2M_EINVAL, "[api.cu] multiple_models is available through b2m_estimate_two_view_geometry only "
                                  "(the pair pipeline verifies one geometry per pair)");
 
-  if (S.max_feat > sift->max_num_matches)
-    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: num descriptors <= SiftMatchingOptions.max_num_matches");
+  // Upstream's GPU matcher warns and truncates an image to max_num_matches features (WarnIfMaxNumMatchesReachedGPU,
+  // U:feature/sift.cc); here the truncation belongs to the upload (the host's UploadImageSet does it, with the same
+  // warning): a resident image that is too long AND referenced by this call is a caller error.
+  if (max_feat_used > sift->max_num_matches)
+    return fail(ctx, B2M_EINVAL, "[api.cu] Check Failed: num descriptors <= SiftMatchingOptions.max_num_matches "
+                                 "(truncate at upload; images the pair list does not reference are not checked)");
 
   b2m_results* res = new (std::nothrow) b2m_results();
   if (!res) return fail(ctx, B2M_ENOMEM, "[api.cu] out of host memory");
@@ -261,6 +274,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
   const int n_dirs = sift->cross_check ? 2 : 1;
   const int64_t n_batches = (n_pairs + B - 1) / B;
   double verify_ms = 0.0;
+  bool pipelined = false;  // decided below, before the first batch
 
   // Drain one finished batch: counts -> host, then offsets + matches on the copy stream.
   auto finish = [&](int64_t b) -> int {
@@ -273,7 +287,13 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       float k1ms = 0.f;
       if (cudaEventElapsedTime(&k1ms, ctx->ev_k1a[s], ctx->ev_k1b[s]) == cudaSuccess) ctx->stats.last_k1_ms += k1ms;
       float vms = 0.f;  // compaction + verification kernels of this batch
-      if (cudaEventElapsedTime(&vms, ctx->ev_k1b[s], ctx->ev_k[s]) == cudaSuccess) verify_ms += vms;
+      if (pipelined) {
+        // overlapped order: K1 = the two GEMM launches; everything else (resolve, gather, compaction, RANSAC,
+        // decision) is the remainder of the step, computed at the end
+        if (cudaEventElapsedTime(&k1ms, ctx->ev_g2a[s], ctx->ev_g2b[s]) == cudaSuccess) ctx->stats.last_k1_ms += k1ms;
+      } else if (cudaEventElapsedTime(&vms, ctx->ev_k1b[s], ctx->ev_k[s]) == cudaSuccess) {
+        verify_ms += vms;
+      }
     }
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[s], 0));
     CU_TRY(ctx, cudaMemcpyAsync(W.h_pair_off[s], W.d_pair_off[s], sizeof(int64_t) * nb, cudaMemcpyDeviceToHost,
@@ -299,21 +319,19 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     return B2M_OK;
   };
 
-  const double hp_t1 = now();
-  for (int64_t b = 0; b < n_batches; ++b) {
-    if (ctx->stop) {
-      cudaStreamSynchronize(st);
-      cudaStreamSynchronize(ctx->copy_stream);
-      ctx->stop = 0;
-      return bail(fail(ctx, B2M_ESTOPPED, "[api.cu] stopped by b2m_request_stop"));
-    }
-    const int s = static_cast<int>(b & 1);
-    const int64_t p0 = b * B;
-    const int nb = static_cast<int>(std::min<int64_t>(B, n_pairs - p0));
-    if (b >= 2) CU_TRY_R(cudaStreamWaitEvent(st, ctx->ev_data[s], 0));
-    CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
+  struct BatchParams {
+    int s = 0, nb = 0;
+    int64_t p0 = 0;
     MatchParams mp{};
-    mp.pairs = ctx->d_pairs + 2 * p0;
+    CompactParams cp{};
+  };
+  auto batch_params = [&](int64_t b) {
+    BatchParams bp;
+    bp.s = static_cast<int>(b & 1);
+    bp.p0 = b * B;
+    bp.nb = static_cast<int>(std::min<int64_t>(B, n_pairs - bp.p0));
+    MatchParams& mp = bp.mp;
+    mp.pairs = ctx->d_pairs + 2 * bp.p0;
     mp.img_row0 = S.d_row0;
     mp.img_nfeat = S.d_nfeat;
     mp.mbuf = W.d_mbuf;
@@ -325,94 +343,195 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     mp.cand_cnt = W.d_cand_cnt;
     mp.cand_rows = W.d_cand_rows;
     mp.cand_sorted = W.d_cand_sorted;
-    CompactParams cp{};
+    CompactParams& cp = bp.cp;
     cp.pairs = mp.pairs;
     cp.img_nfeat = S.d_nfeat;
     cp.mbuf = W.d_mbuf;
     cp.mstride = W.mstride;
     cp.cross_check = sift->cross_check ? 1 : 0;
-    cp.arena = W.d_arena[s];
-    cp.cursor = W.d_cursor[s];
-    cp.pair_off = W.d_pair_off[s];
-    cp.pair_cnt = W.d_pair_cnt[s];
+    cp.arena = W.d_arena[bp.s];
+    cp.cursor = W.d_cursor[bp.s];
+    cp.pair_off = W.d_pair_off[bp.s];
+    cp.pair_cnt = W.d_pair_cnt[bp.s];
     cp.img_row0 = S.d_row0;
     cp.kpts = tvg ? S.d_kpts : nullptr;
-    cp.pts = tvg ? static_cast<double4*>(verify_points_arena(ctx, s)) : nullptr;
+    cp.pts = tvg ? static_cast<double4*>(verify_points_arena(ctx, bp.s)) : nullptr;
     cp.enable = nullptr;
-    // Column direction of the cross-check: skipped for pairs without a row-direction candidate
-    // (launch_k1_filter_skip).  The first cross-check batch of a context is computed both ways and the
-    // match lists compared on the device; on any difference the context stays on the two-direction launch.
-    // Column direction of the cross-check: computed for the matched columns only (launch_k1_filter_gather).  The
-    // first cross-check batch of a context is computed both ways and the match lists compared on the device; on
-    // any difference the context stays on the two-direction launch.
-    const bool split_capable = !ctx->exact_k1 && n_dirs == 2;
-    auto gather_scratch = [&]() {
-      GatherScratch g;
-      g.desc = W.d_gath_desc; g.colrank = W.d_colrank; g.cols = W.d_gath_cols; g.cnt = W.d_gath_cnt;
-      g.items = W.d_gath_items; g.n_items = W.d_gath_n;
-      return g;
+    return bp;
+  };
+  // Column direction of the cross-check: computed for the matched columns only (launch_k1_filter_gather).  The
+  // first cross-check batch of a context is computed both ways and the match lists compared on the device; on
+  // any difference the context stays on the two-direction launch.
+  const bool split_capable = !ctx->exact_k1 && n_dirs == 2;
+  auto gather_scratch = [&]() {
+    GatherScratch g;
+    g.desc = W.d_gath_desc; g.colrank = W.d_colrank; g.cols = W.d_gath_cols; g.cnt = W.d_gath_cnt;
+    g.items = W.d_gath_items; g.n_items = W.d_gath_n;
+    return g;
+  };
+  // One-time comparison of the gathered schedule against the two-direction launch on one batch (returns a B2M code;
+  // leaves ctx->k1_dir1_mode decided unless the batch had no match at all).  The batch itself is redone afterwards.
+  auto k1_selftest = [&](const BatchParams& bp) -> int {
+    const int s = bp.s, nb = bp.nb;
+    const MatchParams& mp = bp.mp;
+    const CompactParams& cp = bp.cp;
+    uint2* t_arena = nullptr;
+    int64_t* t_off = nullptr;
+    int32_t *t_cnt = nullptr, *t_flag = nullptr;
+    auto drop = [&]() {
+      cudaFree(t_arena); cudaFree(t_off); cudaFree(t_cnt); cudaFree(t_flag);
+      t_arena = nullptr; t_off = nullptr; t_cnt = nullptr; t_flag = nullptr;
     };
-    // One-time comparison of the gathered schedule against the two-direction launch on this batch (returns a B2M code;
-    // leaves ctx->k1_dir1_mode decided unless the batch had no match at all).  The batch itself is redone afterwards.
-    auto k1_selftest = [&]() -> int {
-      uint2* t_arena = nullptr;
-      int64_t* t_off = nullptr;
-      int32_t *t_cnt = nullptr, *t_flag = nullptr;
-      auto drop = [&]() {
-        cudaFree(t_arena); cudaFree(t_off); cudaFree(t_cnt); cudaFree(t_flag);
-        t_arena = nullptr; t_off = nullptr; t_cnt = nullptr; t_flag = nullptr;
-      };
-      const size_t arena_matches = static_cast<size_t>(W.batch) * W.mstride;
-      if (ensure_gather(ctx) != B2M_OK || cudaMalloc(&t_arena, sizeof(uint2) * arena_matches) != cudaSuccess ||
-          cudaMalloc(&t_off, sizeof(int64_t) * nb) != cudaSuccess || cudaMalloc(&t_cnt, sizeof(int32_t) * nb) != cudaSuccess ||
-          cudaMalloc(&t_flag, sizeof(int32_t)) != cudaSuccess) {
-        drop();
-        cudaGetLastError();
-        ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_NOMEM;  // no room for the scratch / comparison: stay on the validated launch
-        return B2M_OK;
-      }
-      CompactParams ct = cp;  // the gathered schedule's match lists go to the temporary arena
-      ct.arena = t_arena;
-      ct.pair_off = t_off;
-      ct.pair_cnt = t_cnt;
-      ct.kpts = nullptr;
-      ct.pts = nullptr;
-      ct.colrank = W.d_colrank;
-      cudaError_t e = launch_k1_filter_gather(S.tmap, W.tmap_gath, mp, S.d_desc, nb, max_strips, ctx->num_sms,
-                                              gather_scratch(), st, nullptr);
-      if (e == cudaSuccess) e = launch_crosscheck_compact(ct, nb, st);
-      if (e != cudaSuccess) {
-        // the gathered schedule could not even be launched (a non-sticky launch error): stay on the validated
-        // launch instead of failing the call; a sticky error resurfaces at the next CUDA call anyway
-        cudaGetLastError();
-        drop();
-        ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
-        CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
-        return B2M_OK;
-      }
-      int32_t h_flag = -1;
-      unsigned long long h_total = 0;
-      e = cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st);
-      if (e == cudaSuccess) e = launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st, nullptr);
-      if (e == cudaSuccess) e = launch_crosscheck_compact(cp, nb, st);
-      if (e == cudaSuccess) e = cudaMemsetAsync(t_flag, 0, sizeof(int32_t), st);
-      if (e == cudaSuccess)
-        e = launch_compare_matches(t_arena, t_off, t_cnt, W.d_arena[s], W.d_pair_off[s], W.d_pair_cnt[s], nb, t_flag, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, t_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(&h_total, W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    const size_t arena_matches = static_cast<size_t>(W.batch) * W.mstride;
+    if (ensure_gather(ctx) != B2M_OK || cudaMalloc(&t_arena, sizeof(uint2) * arena_matches) != cudaSuccess ||
+        cudaMalloc(&t_off, sizeof(int64_t) * nb) != cudaSuccess || cudaMalloc(&t_cnt, sizeof(int32_t) * nb) != cudaSuccess ||
+        cudaMalloc(&t_flag, sizeof(int32_t)) != cudaSuccess) {
       drop();
-      if (e != cudaSuccess) CU_TRY_R(e);
-      // a batch without a single match compares nothing: stay untested (and on the two-direction launch)
-      if (h_flag != 0) ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
-      else if (h_total > 0) ctx->k1_dir1_mode = B2M_K1_DIR1_GATHER;
-      ctx->stats.kernel_launches += 10;
+      cudaGetLastError();
+      ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_NOMEM;  // no room for the scratch / comparison: stay on the validated launch
+      return B2M_OK;
+    }
+    CompactParams ct = cp;  // the gathered schedule's match lists go to the temporary arena
+    ct.arena = t_arena;
+    ct.pair_off = t_off;
+    ct.pair_cnt = t_cnt;
+    ct.kpts = nullptr;
+    ct.pts = nullptr;
+    ct.colrank = W.d_colrank;
+    cudaError_t e = cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess)
+      e = launch_k1_filter_gather(S.tmap, W.tmap_gath, mp, S.d_desc, nb, max_strips, ctx->num_sms, gather_scratch(), st, nullptr);
+    if (e == cudaSuccess) e = launch_crosscheck_compact(ct, nb, st);
+    if (e != cudaSuccess) {
+      // the gathered schedule could not even be launched (a non-sticky launch error): stay on the validated
+      // launch instead of failing the call; a sticky error resurfaces at the next CUDA call anyway
+      cudaGetLastError();
+      drop();
+      ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
       CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
       return B2M_OK;
-    };
-    if (split_capable && ctx->k1_dir1_mode == B2M_K1_DIR1_UNTESTED)
-      if (int rc = k1_selftest()) return rc;  // `res` was released by the failing step
+    }
+    int32_t h_flag = -1;
+    unsigned long long h_total = 0;
+    e = cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = launch_k1_filter(S.tmap, mp, S.d_desc, nb, max_strips, n_dirs, ctx->num_sms, st, nullptr);
+    if (e == cudaSuccess) e = launch_crosscheck_compact(cp, nb, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(t_flag, 0, sizeof(int32_t), st);
+    if (e == cudaSuccess)
+      e = launch_compare_matches(t_arena, t_off, t_cnt, W.d_arena[s], W.d_pair_off[s], W.d_pair_cnt[s], nb, t_flag, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, t_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(&h_total, W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    drop();
+    if (e != cudaSuccess) CU_TRY_R(e);
+    // a batch without a single match compares nothing: stay untested (and on the two-direction launch)
+    if (h_flag != 0) ctx->k1_dir1_mode = B2M_K1_DIR1_FULL_MISMATCH;
+    else if (h_total > 0) ctx->k1_dir1_mode = B2M_K1_DIR1_GATHER;
+    ctx->stats.kernel_launches += 10;
+    CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
+    return B2M_OK;
+  };
+  // RANSAC + decision of a compacted batch (+ guided re-matching), then its match total to the host
+  auto verify_stage = [&](const BatchParams& bp) -> int {
+    const int s = bp.s, nb = bp.nb;
+    if (tvg)
+      if (int rc = verify_batch_launch(ctx, S, tvg, sift, s, bp.p0, nb)) return bail(rc);
+    if (tvg && sift->guided_matching) {
+      // K1g: re-match the verified pairs under their geometry; the result replaces the inlier matches
+      GuidedSlot gs;
+      if (int rc = verify_guided_slot(ctx, s, &gs)) return bail(rc);
+      GuidedParams gp{};
+      gp.kind = gs.kind;
+      gp.model = gs.model;
+      gp.kpts = S.d_kpts;
+      const float me = static_cast<float>(tvg->ransac.max_error);
+      gp.max_residual = me * me;
+      CU_TRY_R(launch_k1_guided(S.tmap, bp.mp, gp, nb, max_strips, n_dirs, st));
+      CU_TRY_R(cudaMemsetAsync(gs.cursor, 0, sizeof(unsigned long long), st));
+      CompactParams gc = bp.cp;
+      gc.arena = gs.arena;
+      gc.cursor = gs.cursor;
+      gc.pair_off = gs.off;
+      gc.pair_cnt = gs.cnt;
+      gc.kpts = nullptr;
+      gc.pts = nullptr;
+      gc.enable = gs.kind;
+      gc.colrank = nullptr;  // the guided kernel computes both directions in full
+      CU_TRY_R(launch_crosscheck_compact(gc, nb, st));
+      CU_TRY_R(cudaMemcpyAsync(gs.h_cursor, gs.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      ctx->stats.kernel_launches += 2;
+    }
+    CU_TRY_R(cudaMemcpyAsync(W.h_cursor[s], W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY_R(cudaEventRecord(ctx->ev_k[s], st));
+    return B2M_OK;
+  };
+  auto stopped = [&]() -> int {
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(ctx->aux_stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    ctx->stop = 0;
+    return bail(fail(ctx, B2M_ESTOPPED, "[api.cu] stopped by b2m_request_stop"));
+  };
+
+  const double hp_t1 = now();
+  bool pretested = false;
+  if (n_batches > 0 && split_capable && ctx->k1_dir1_mode == B2M_K1_DIR1_UNTESTED) {
+    if (int rc = k1_selftest(batch_params(0))) return rc;  // `res` was released by the failing step
+    pretested = true;
+  }
+  // Overlapped order (gathered schedule + verification, the exhaustive pipeline's case): the ALU-only middle of K1
+  // (exact resolve of the row direction, gather of the matched columns) needs neither tensor cores nor much of an SM,
+  // and the RANSAC kernels of the previous batch leave SMs idle in their tail: the two run side by side.
+  //   main stream:  GEMM0(b) | RANSAC + decision(b-1) | wait | GEMM1(b) | resolve1(b) | cross-check + compaction(b)
+  //   aux stream:            | resolve0(b) + gather(b) |
+  // The batch buffers are double-buffered already (slot b & 1); results drain with a lag of two batches.
+  const bool no_overlap = getenv("B2M_NO_OVERLAP") != nullptr;
+  pipelined = split_capable && tvg && !sift->guided_matching && n_batches >= 2 && !no_overlap &&
+              (ctx->k1_dir1_mode == B2M_K1_DIR1_GATHER || ctx->k1_dir1_mode == B2M_K1_DIR1_GATHER_FORCED);
+  if (pipelined) {
+    if (int rc = ensure_gather(ctx)) return bail(rc);
+    const GatherScratch g = gather_scratch();
+    BatchParams prev;
+    for (int64_t b = 0; b < n_batches; ++b) {
+      if (ctx->stop) return stopped();
+      if (b >= 2)
+        if (int rc = finish(b - 2)) return bail(rc);  // frees slot b & 1 (its RANSAC was enqueued one iteration ago)
+      BatchParams bp = batch_params(b);
+      const int s = bp.s, nb = bp.nb;
+      CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
+      CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
+      CU_TRY_R(launch_k1_gather_phase(0, S.tmap, W.tmap_gath, bp.mp, S.d_desc, nb, max_strips, ctx->num_sms, g, st));
+      CU_TRY_R(cudaEventRecord(ctx->ev_k1b[s], st));
+      CU_TRY_R(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_k1b[s], 0));
+      CU_TRY_R(launch_k1_gather_phase(1, S.tmap, W.tmap_gath, bp.mp, S.d_desc, nb, max_strips, ctx->num_sms, g, ctx->aux_stream));
+      CU_TRY_R(cudaEventRecord(ctx->ev_p1[s], ctx->aux_stream));
+      if (b > 0)
+        if (int rc = verify_stage(prev)) return rc;
+      CU_TRY_R(cudaStreamWaitEvent(st, ctx->ev_p1[s], 0));
+      CU_TRY_R(cudaEventRecord(ctx->ev_g2a[s], st));
+      CU_TRY_R(launch_k1_gather_phase(2, S.tmap, W.tmap_gath, bp.mp, S.d_desc, nb, max_strips, ctx->num_sms, g, st));
+      CU_TRY_R(cudaEventRecord(ctx->ev_g2b[s], st));
+      CU_TRY_R(launch_k1_gather_phase(3, S.tmap, W.tmap_gath, bp.mp, S.d_desc, nb, max_strips, ctx->num_sms, g, st));
+      bp.cp.colrank = W.d_colrank;
+      CU_TRY_R(launch_crosscheck_compact(bp.cp, nb, st));
+      ctx->stats.kernel_launches += 7;
+      ctx->stats.last_k1_launches += 1;
+      ctx->stats.k1_dir1_mode = static_cast<uint64_t>(ctx->k1_dir1_mode);
+      prev = bp;
+    }
+    if (int rc = verify_stage(prev)) return rc;
+  } else {
+  for (int64_t b = 0; b < n_batches; ++b) {
+    if (ctx->stop) return stopped();
+    BatchParams bp = batch_params(b);
+    const int s = bp.s, nb = bp.nb;
+    MatchParams& mp = bp.mp;
+    CompactParams& cp = bp.cp;
+    if (b >= 2) CU_TRY_R(cudaStreamWaitEvent(st, ctx->ev_data[s], 0));
+    CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
+    if (split_capable && ctx->k1_dir1_mode == B2M_K1_DIR1_UNTESTED && !(b == 0 && pretested))
+      if (int rc = k1_selftest(bp)) return rc;  // `res` was released by the failing step
     const bool use_gather = split_capable && (ctx->k1_dir1_mode == B2M_K1_DIR1_GATHER || ctx->k1_dir1_mode == B2M_K1_DIR1_GATHER_FORCED);
     const bool use_skip = split_capable && (ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP || ctx->k1_dir1_mode == B2M_K1_DIR1_SKIP_FORCED);
     if (use_gather)
@@ -437,43 +556,17 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     if (ctx->exact_k1) CU_TRY_R(cudaEventRecord(ctx->ev_k1b[s], st));
     ctx->stats.kernel_launches += 1;
     ctx->stats.last_k1_launches += 1;
-    ctx->stats.match_tiles += 0;
     ctx->stats.k1_dir1_mode = static_cast<uint64_t>(ctx->k1_dir1_mode);
     CU_TRY_R(launch_crosscheck_compact(cp, nb, st));
     ctx->stats.kernel_launches += 1;
-    if (tvg)
-      if (int rc = verify_batch_launch(ctx, S, tvg, sift, s, p0, nb)) return bail(rc);
-    if (tvg && sift->guided_matching) {
-      // K1g: re-match the verified pairs under their geometry; the result replaces the inlier matches
-      GuidedSlot gs;
-      if (int rc = verify_guided_slot(ctx, s, &gs)) return bail(rc);
-        GuidedParams gp{};
-      gp.kind = gs.kind;
-      gp.model = gs.model;
-      gp.kpts = S.d_kpts;
-      const float me = static_cast<float>(tvg->ransac.max_error);
-      gp.max_residual = me * me;
-      CU_TRY_R(launch_k1_guided(S.tmap, mp, gp, nb, max_strips, n_dirs, st));
-      CU_TRY_R(cudaMemsetAsync(gs.cursor, 0, sizeof(unsigned long long), st));
-      CompactParams gc = cp;
-      gc.arena = gs.arena;
-      gc.cursor = gs.cursor;
-      gc.pair_off = gs.off;
-      gc.pair_cnt = gs.cnt;
-      gc.kpts = nullptr;
-      gc.pts = nullptr;
-      gc.enable = gs.kind;
-      gc.colrank = nullptr;  // the guided kernel computes both directions in full
-      CU_TRY_R(launch_crosscheck_compact(gc, nb, st));
-      CU_TRY_R(cudaMemcpyAsync(gs.h_cursor, gs.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-      ctx->stats.kernel_launches += 2;
-    }
-    CU_TRY_R(cudaMemcpyAsync(W.h_cursor[s], W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU_TRY_R(cudaEventRecord(ctx->ev_k[s], st));
+    if (int rc = verify_stage(bp)) return rc;
     if (b > 0)
       if (int rc = finish(b - 1)) return bail(rc);
   }
+  }
   const double hp_t2 = now();
+  if (pipelined && n_batches >= 2)
+    if (int rc = finish(n_batches - 2)) return bail(rc);
   if (n_batches > 0)
     if (int rc = finish(n_batches - 1)) return bail(rc);
   CU_TRY_R(cudaEventRecord(ctx->ev_t1, st));
@@ -481,6 +574,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1);
   ctx->stats.last_total_ms = ms;
+  if (pipelined) verify_ms = std::max(0.0, static_cast<double>(ms) - ctx->stats.last_k1_ms);
   ctx->stats.last_verify_ms = verify_ms;
   ctx->stats.last_match_ms = ms - verify_ms;
 #undef CU_TRY_R
@@ -646,6 +740,7 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
   CU_TRY_C(cudaSetDevice(dev));
   CU_TRY_C(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU_TRY_C(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CU_TRY_C(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
   for (int s = 0; s < 2; ++s) {
     CU_TRY_C(cudaEventCreate(&ctx->ev_k[s]));
     CU_TRY_C(cudaEventCreateWithFlags(&ctx->ev_data[s], cudaEventDisableTiming));
@@ -653,6 +748,9 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
   for (int s = 0; s < 2; ++s) {
     CU_TRY_C(cudaEventCreate(&ctx->ev_k1a[s]));
     CU_TRY_C(cudaEventCreate(&ctx->ev_k1b[s]));
+    CU_TRY_C(cudaEventCreateWithFlags(&ctx->ev_p1[s], cudaEventDisableTiming));
+    CU_TRY_C(cudaEventCreate(&ctx->ev_g2a[s]));
+    CU_TRY_C(cudaEventCreate(&ctx->ev_g2b[s]));
   }
   CU_TRY_C(cudaEventCreate(&ctx->ev_t0));
   CU_TRY_C(cudaEventCreate(&ctx->ev_t1));
@@ -697,11 +795,15 @@ void b2m_destroy(b2m_ctx* ctx) {
     if (ctx->ev_data[s]) cudaEventDestroy(ctx->ev_data[s]);
     if (ctx->ev_k1a[s]) cudaEventDestroy(ctx->ev_k1a[s]);
     if (ctx->ev_k1b[s]) cudaEventDestroy(ctx->ev_k1b[s]);
+    if (ctx->ev_p1[s]) cudaEventDestroy(ctx->ev_p1[s]);
+    if (ctx->ev_g2a[s]) cudaEventDestroy(ctx->ev_g2a[s]);
+    if (ctx->ev_g2b[s]) cudaEventDestroy(ctx->ev_g2b[s]);
   }
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   delete ctx;
 }
 
@@ -713,7 +815,7 @@ int b2m_request_stop(b2m_ctx* ctx) {
   return B2M_OK;
 }
 
-int b2m_set_images(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const uint8_t* const* desc,
+static int set_images_impl(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const uint8_t* const* desc,
                    const float* const* kpts, const b2m_camera* cams) {
   if (!ctx) return B2M_EINVAL;
   if (n_images < 0 || (n_images > 0 && (!n_feat || !desc)))
@@ -741,7 +843,14 @@ int b2m_set_images(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const 
   return B2M_OK;
 }
 
-int b2m_set_images_device(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const void* dev_desc_packed,
+int b2m_set_images(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const uint8_t* const* desc,
+                   const float* const* kpts, const b2m_camera* cams) {
+  const int rc = set_images_impl(ctx, n_images, n_feat, desc, kpts, cams);
+  if (rc != B2M_OK && ctx) ctx->images.release();  // never leave a half-uploaded set behind
+  return rc;
+}
+
+static int set_images_device_impl(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const void* dev_desc_packed,
                           const void* dev_kpts_packed, const b2m_camera* cams) {
   if (!ctx) return B2M_EINVAL;
   if (n_images < 0 || (n_images > 0 && (!n_feat || !dev_desc_packed)))
@@ -781,7 +890,14 @@ int b2m_set_images_device(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat,
   return B2M_OK;
 }
 
-int b2m_set_images_sharded(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const b2m_camera* cams,
+int b2m_set_images_device(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const void* dev_desc_packed,
+                          const void* dev_kpts_packed, const b2m_camera* cams) {
+  const int rc = set_images_device_impl(ctx, n_images, n_feat, dev_desc_packed, dev_kpts_packed, cams);
+  if (rc != B2M_OK && ctx) ctx->images.release();  // never leave a half-uploaded set behind
+  return rc;
+}
+
+static int set_images_sharded_impl(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const b2m_camera* cams,
                            const b2m_image_shard* mine) {
   if (!ctx) return B2M_EINVAL;
   if (n_images < 0 || (n_images > 0 && !n_feat) || !mine || mine->struct_size != sizeof(b2m_image_shard))
@@ -860,6 +976,13 @@ int b2m_set_images_sharded(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat
   ctx->stats.last_allgather_ms = (ctx->comm && ctx->comm_size > 1) ? ag : 0.0;
   ctx->stats.last_allgather_bytes = recv_bytes;
   return B2M_OK;
+}
+
+int b2m_set_images_sharded(b2m_ctx* ctx, int32_t n_images, const int32_t* n_feat, const b2m_camera* cams,
+                           const b2m_image_shard* mine) {
+  const int rc = set_images_sharded_impl(ctx, n_images, n_feat, cams, mine);
+  if (rc != B2M_OK && ctx) ctx->images.release();  // never leave a half-uploaded set behind
+  return rc;
 }
 
 int b2m_match_pairs(b2m_ctx* ctx, const int32_t* pairs, int64_t n_pairs, const b2m_sift_opts* sift,

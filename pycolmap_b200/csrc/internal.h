@@ -98,6 +98,10 @@ struct b2m_ctx {
   cudaEvent_t ev_data[2] = {nullptr, nullptr};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_k1a[2] = {nullptr, nullptr}, ev_k1b[2] = {nullptr, nullptr};
+  // overlapped schedule (api.cu): exact resolve + gather of batch b run on `aux_stream` next to the RANSAC kernels of
+  // batch b - 1; ev_p1 = that work done, ev_g2a / ev_g2b bracket the gathered GEMM (timing)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_p1[2] = {nullptr, nullptr}, ev_g2a[2] = {nullptr, nullptr}, ev_g2b[2] = {nullptr, nullptr};
   float* d_lut = nullptr;
   b2m::ImageSet images;
   b2m::Workspace ws;

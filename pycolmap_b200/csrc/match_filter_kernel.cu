@@ -873,9 +873,14 @@ __global__ void __launch_bounds__(256) b2m_k1_gather_kernel(const MatchParams p,
 }
 }  // namespace
 
-cudaError_t launch_k1_filter_gather(const CUtensorMap& tmap, const CUtensorMap& tmap_gath, const MatchParams& p_in,
-                                    const uint8_t* desc, int n_pairs, int max_strips, int num_sms, const GatherScratch& g,
-                                    cudaStream_t stream, cudaEvent_t after_filter) {
+// One phase of the gathered schedule (see match_kernel.cuh).  Phases of a batch must be enqueued in order 0, 1, 2, 3 on
+// streams ordered by events; splitting them lets the scheduler run phase 1 (ALU kernels that need little of an SM)
+// next to the previous batch's RANSAC kernels instead of in front of them.
+//   0: row-direction GEMM over all pairs        1: its exact resolve (m12) + gather of the matched columns
+//   2: GEMM over the gathered work list          3: exact resolve of the gathered direction
+cudaError_t launch_k1_gather_phase(int phase, const CUtensorMap& tmap, const CUtensorMap& tmap_gath, const MatchParams& p_in,
+                                   const uint8_t* desc, int n_pairs, int max_strips, int num_sms, const GatherScratch& g,
+                                   cudaStream_t stream) {
   static bool attr_set[64] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
@@ -887,10 +892,6 @@ cudaError_t launch_k1_filter_gather(const CUtensorMap& tmap, const CUtensorMap& 
   }
   if (n_pairs <= 0) return cudaSuccess;
   MatchParams p = p_in;
-  cudaError_t e = cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * 2 * n_pairs, stream);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(g.n_items, 0, sizeof(int32_t), stream);
-  if (e != cudaSuccess) return e;
   p.n_dirs = 1;
   p.blocks_per_image = (max_strips * kTileM + kRowsPerItem - 1) / kRowsPerItem;
   p.n_items = n_pairs * p.blocks_per_image;
@@ -899,35 +900,54 @@ cudaError_t launch_k1_filter_gather(const CUtensorMap& tmap, const CUtensorMap& 
   const int max_clusters = num_sms / kCluster;
   const int clusters = p.n_items < max_clusters ? p.n_items : max_clusters;
   if (clusters <= 0) return cudaSuccess;
-  // 1. row direction of every pair                   2. its exact resolution: m12
-  b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap, p);
-  b2m_k1_resolve_kernel<<<n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, 0);
-  // 3. matched columns -> rank, gathered descriptors, work items
-  b2m_k1_gather_kernel<<<n_pairs, 256, 0, stream>>>(p, desc, g.desc, g.colrank, g.cols, g.cnt, g.items, g.n_items);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  // 4. column direction of the matched columns only: rows = gathered descriptors, columns = image a; outputs go to
-  //    the direction-1 halves (every index in the kernel is (pair * 2 + dir) * mstride + row with dir = 0)
-  MatchParams q = p;
-  q.mbuf = p.mbuf + p.mstride;
-  q.aux = p.aux + p.mstride;
-  q.cand_cnt = p.cand_cnt + 1;
-  q.cand_rows = p.cand_rows + p.mstride;
-  q.cand_sorted = p.cand_sorted + p.mstride;
-  q.item_list = g.items;
-  q.n_items_ptr = g.n_items;
-  q.gath_cnt = g.cnt;
-  b2m_k1_filter_kernel<<<max_clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap_gath, q);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  if (after_filter) {
-    e = cudaEventRecord(after_filter, stream);
-    if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  switch (phase) {
+    case 0:
+      e = cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * 2 * n_pairs, stream);
+      if (e != cudaSuccess) return e;
+      e = cudaMemsetAsync(g.n_items, 0, sizeof(int32_t), stream);
+      if (e != cudaSuccess) return e;
+      b2m_k1_filter_kernel<<<clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap, p);
+      break;
+    case 1:
+      b2m_k1_resolve_kernel<<<n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, 0);
+      b2m_k1_gather_kernel<<<n_pairs, 256, 0, stream>>>(p, desc, g.desc, g.colrank, g.cols, g.cnt, g.items, g.n_items);
+      break;
+    case 2: {
+      // rows = gathered descriptors, columns = image a; outputs go to the direction-1 halves (every index in the
+      // kernel is (pair * 2 + dir) * mstride + row with dir = 0)
+      MatchParams q = p;
+      q.mbuf = p.mbuf + p.mstride;
+      q.aux = p.aux + p.mstride;
+      q.cand_cnt = p.cand_cnt + 1;
+      q.cand_rows = p.cand_rows + p.mstride;
+      q.cand_sorted = p.cand_sorted + p.mstride;
+      q.item_list = g.items;
+      q.n_items_ptr = g.n_items;
+      q.gath_cnt = g.cnt;
+      b2m_k1_filter_kernel<<<max_clusters * kCluster, kThreads, kSmemBytes, stream>>>(tmap, tmap_gath, q);
+      break;
+    }
+    default:
+      p.gath_desc = g.desc;   // original base pointers: the kernel adds the direction itself
+      b2m_k1_resolve_kernel<<<n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, 1);
+      break;
   }
-  // 5. exact resolution of the gathered direction (original base pointers: the kernel adds the direction itself)
-  p.gath_desc = g.desc;
-  b2m_k1_resolve_kernel<<<n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, 1);
   return cudaGetLastError();
+}
+
+cudaError_t launch_k1_filter_gather(const CUtensorMap& tmap, const CUtensorMap& tmap_gath, const MatchParams& p_in,
+                                    const uint8_t* desc, int n_pairs, int max_strips, int num_sms, const GatherScratch& g,
+                                    cudaStream_t stream, cudaEvent_t after_filter) {
+  for (int phase = 0; phase < 4; ++phase) {
+    cudaError_t e = launch_k1_gather_phase(phase, tmap, tmap_gath, p_in, desc, n_pairs, max_strips, num_sms, g, stream);
+    if (e != cudaSuccess) return e;
+    if (phase == 2 && after_filter) {
+      e = cudaEventRecord(after_filter, stream);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_compare_matches(const uint2* arena_a, const int64_t* off_a, const int32_t* cnt_a, const uint2* arena_b,

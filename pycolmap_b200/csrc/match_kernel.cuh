@@ -102,6 +102,9 @@ struct GatherScratch {
 cudaError_t launch_k1_filter_gather(const CUtensorMap& tmap, const CUtensorMap& tmap_gath, const MatchParams& p,
                                     const uint8_t* desc, int n_pairs, int max_strips, int num_sms, const GatherScratch& g,
                                     cudaStream_t stream, cudaEvent_t after_filter);
+cudaError_t launch_k1_gather_phase(int phase, const CUtensorMap& tmap, const CUtensorMap& tmap_gath, const MatchParams& p,
+                                   const uint8_t* desc, int n_pairs, int max_strips, int num_sms, const GatherScratch& g,
+                                   cudaStream_t stream);
 cudaError_t launch_k1_guided(const CUtensorMap& tmap, const MatchParams& p, const GuidedParams& g, int n_pairs,
                              int max_strips, int n_dirs, cudaStream_t stream);
 cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream);

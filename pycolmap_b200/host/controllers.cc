@@ -344,7 +344,11 @@ std::vector<float> KeypointPositions(Database& db, int64_t image_id) {
 // several contexts that share a communicator (Engine::EnsureLocalComm) every GPU uploads only ITS contiguous share
 // of the images over PCIe and ONE all-gather over NVLink makes the set resident everywhere
 // (b2m_set_images_sharded); without NCCL every GPU uploads the whole set.
-void UploadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, LoadedSet* L) {
+//
+// An image with more than `max_num_matches` features is truncated to its first max_num_matches, with the warning
+// upstream's GPU matcher prints (WarnIfMaxNumMatchesReachedGPU, U:feature/sift.cc): match indices stay valid
+// because the kept features are a prefix.
+void UploadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, LoadedSet* L, int max_num_matches) {
   const double t_read0 = Now();
   const size_t n = L->ids.size();
   std::vector<DescriptorsBlob> desc(n);
@@ -355,6 +359,13 @@ void UploadImageSet(Database& db, const std::vector<b2m_ctx*>& ctxs, LoadedSet* 
     L->xy[i] = KeypointPositions(db, L->ids[i]);
     if (static_cast<int64_t>(L->xy[i].size() / 2) != desc[i].rows)
       throw std::invalid_argument("[controllers.cc] Check Failed: keypoints.rows == descriptors.rows");
+    if (desc[i].rows > max_num_matches) {
+      fprintf(stderr, "W [controllers.cc] Clamping features from %lld to %d - consider increasing the maximum number of matches.\n",
+              static_cast<long long>(desc[i].rows), max_num_matches);
+      desc[i].rows = max_num_matches;
+      desc[i].data.resize(static_cast<size_t>(max_num_matches) * 128);
+      L->xy[i].resize(static_cast<size_t>(max_num_matches) * 2);
+    }
     L->n_feat[i] = static_cast<int32_t>(desc[i].rows);
   }
   const int32_t n_images = static_cast<int32_t>(n);
@@ -666,7 +677,7 @@ void MatchExhaustive(const std::string& database_path, const SiftMatchingOptions
   const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
   Database db(database_path);
   LoadedSet L = ReadImageTable(db, /*order_by_name=*/false);
-  UploadImageSet(db, ctxs, &L);
+  UploadImageSet(db, ctxs, &L, sift.max_num_matches);
   MatchPairsIntoDb(db, ctxs, L, Chunked(ExhaustivePairBlocks(static_cast<int>(L.ids.size()), matching.block_size)),
                    ToAbi(sift), ToAbi(verification), /*skip_existing=*/true);
 }
@@ -684,7 +695,7 @@ void MatchSequential(const std::string& database_path, const SiftMatchingOptions
   const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
   Database db(database_path);
   LoadedSet L = ReadImageTable(db, /*order_by_name=*/true);
-  UploadImageSet(db, ctxs, &L);
+  UploadImageSet(db, ctxs, &L, sift.max_num_matches);
   MatchPairsIntoDb(db, ctxs, L,
                    {SequentialPairs(static_cast<int>(L.ids.size()), matching.overlap, matching.quadratic_overlap)},
                    ToAbi(sift), ToAbi(verification), /*skip_existing=*/true);
@@ -701,7 +712,7 @@ void MatchSpatial(const std::string& database_path, const SiftMatchingOptions& s
   const std::vector<b2m_ctx*> ctxs = Engine::GetAll(devices);
   Database db(database_path);
   LoadedSet L = ReadImageTable(db, /*order_by_name=*/false);
-  UploadImageSet(db, ctxs, &L);
+  UploadImageSet(db, ctxs, &L, sift.max_num_matches);
   std::vector<std::array<double, 3>> prior_t;
   std::vector<bool> has_prior;
   db.ReadLocationPriors(&prior_t, &has_prior);   // same order as ReadAllImages (image_id)
@@ -748,7 +759,7 @@ void VerifyMatches(const std::string& database_path, const std::string& pairs_pa
   }
   const b2m_tvg_opts tvg = ToAbi(options);
   if (!todo_match.empty()) {   // only now are descriptors needed (and keypoints.rows == descriptors.rows enforced)
-    UploadImageSet(db, {ctx}, &L);
+    UploadImageSet(db, {ctx}, &L, SiftMatchingOptions().max_num_matches);
     MatchPairsIntoDb(db, {ctx}, L, {todo_match}, ToAbi(SiftMatchingOptions()), tvg, /*skip_existing=*/false);
   }
   VerifyStoredPairs(db, ctx, L, todo_verify, tvg);

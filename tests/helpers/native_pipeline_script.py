@@ -299,6 +299,23 @@ with nat.Database(m_db) as db:
 assert n_multi == n_verified
 assert [r[:3] for r in dump(m_db)["matches"]] == [r[:3] for r in ref_dump["matches"]]
 
+# ---- max_num_matches: longer images are truncated to a prefix with a warning (WarnIfMaxNumMatchesReachedGPU) -----
+t_db = os.path.join(tmp, "trunc.db")
+make_db(t_db)
+KEEP = 300
+nat.match_exhaustive(t_db, sift_options={"max_num_matches": KEEP}, matching_options={"block_size": 4})
+with nat.Database(t_db) as db:
+    n_rows = 0
+    for i1, i2 in visits:
+        want = oracle.fast_match_pair(descs[i1][:KEEP], descs[i2][:KEEP])
+        got = db.read_matches(ids[i1], ids[i2])
+        if len(want) < MIN:
+            assert len(got) == 0
+            continue
+        assert np.array_equal(got, want) and got.max() < KEEP, (i1, i2)
+        n_rows += 1
+    assert n_rows >= 5
+
 # ---- low-level context through the mock: plumbing of options and result objects ------------------------------
 c = nat.Context()
 c.set_images(descs[:3])

@@ -416,6 +416,59 @@ def test_warp_five_point_equals_serial_solver():
 
 
 # ---- cross-check: column direction only for pairs with row-direction candidates ----------------------
+def test_overlapped_schedule_equals_sequential_order():
+    """api.cu: with the gathered schedule and verification on, resolve + gather of batch b run next to the RANSAC
+    kernels of batch b - 1 and results drain two batches late.  Same results as the sequential order
+    (B2M_NO_OVERLAP=1), whatever the batch size (1 pair per batch ... everything in one batch)."""
+    import os
+    scene = syn.make_scene(12, 640, seed=11, window_images=2.5)
+    descs = [d.numpy() for d in scene["desc"]]
+    kpts = [k.numpy() for k in scene["kpts"]]
+    cams = [scenes.CAM] * len(descs)
+    pairs = np.concatenate(nat.exhaustive_pair_blocks(len(descs), 5))
+    ref = None
+    for no_overlap, batch in ((True, 0), (False, 1), (False, 2), (False, 7), (False, 33), (False, 0), (True, 5)):
+        if no_overlap:
+            os.environ["B2M_NO_OVERLAP"] = "1"
+        try:
+            ctx = nat.Context(device=0, seed=0, pair_batch=batch)
+            ctx.set_images(descs, kpts, cams)
+            out = []
+            for rep in range(2):     # the first call of a context self-tests the schedule on batch 0; the second does not
+                res = ctx.match_pairs(pairs, nat.SiftMatchingOptions(), nat.TwoViewGeometryOptions())
+                out.append([(res.matches(k).tobytes(), int(res.two_view_geometry(k).config),
+                             res.two_view_geometry(k).inlier_matches.tobytes(), np.asarray(res.two_view_geometry(k).F).tobytes())
+                            for k in range(len(pairs))])
+                res.free()
+            assert int(ctx.stats()["k1_dir1_mode"]) == 6
+            ctx.close()
+        finally:
+            os.environ.pop("B2M_NO_OVERLAP", None)
+        assert out[0] == out[1], (no_overlap, batch)
+        if ref is None:
+            ref = out[0]
+            assert sum(1 for r in ref if r[1] != 0) >= 8
+        assert out[0] == ref, (no_overlap, batch)
+
+
+def test_max_num_matches_checks_only_referenced_images():
+    """an image longer than max_num_matches that the pair list does not reference must not fail the call
+    (the host pipelines truncate at upload like upstream's WarnIfMaxNumMatchesReachedGPU; the C ABI refuses only a
+    referenced one)."""
+    rng = np.random.default_rng(8)
+    descs = [syn.sift_like(rng, n) for n in (300, 260, 900)]
+    descs[1][:120] = syn.perturb(rng, descs[0][:120])
+    c = nat.Context(device=0)
+    c.set_images(descs)
+    opts = nat.SiftMatchingOptions(max_num_matches=512)
+    res = c.match_pairs(np.array([(0, 1)], np.int32), opts)
+    assert np.array_equal(res.matches(0), oracle.fast_match_pair(descs[0], descs[1]))
+    res.free()
+    with pytest.raises(Exception, match="max_num_matches"):
+        c.match_pairs(np.array([(0, 2)], np.int32), opts)
+    c.close()
+
+
 def test_cross_check_column_direction_skip():
     """b2m_stats.k1_dir1_mode: the context compares the gathered column direction against the two-direction launch
     on its first cross-check batch with matches and must have switched over (6); forced full (3), forced skip (4,

@@ -294,12 +294,15 @@ def main():
     def one_step(host=None):
         """One pass of the hot path: shard -> whole set resident on this GPU (copy + ONE all-gather) -> match
         (+ verify) this rank's pairs.  `host`: (desc, kpts) pinned host arrays of the local shard (e2e leg)."""
+        w0 = time.perf_counter()
         if host is None:
             ctx.set_images_sharded(nfeat, first, count, d_desc.data_ptr(), d_kpts.data_ptr() if verify else None, cams,
                                    bool(verify))
         else:
             ctx.set_images_sharded(nfeat, first, count, host[0], host[1] if verify else None, cams, bool(verify))
+        w1 = time.perf_counter()
         res = ctx.match_pairs(my_pairs, sift, tvg)
+        w2 = time.perf_counter()
         st = ctx.stats()
         out = dict(dev_ms=st["last_upload_ms"] + st["last_allgather_ms"] + st["last_total_ms"], k1_ms=st["last_k1_ms"],
                    k1_n=st["last_k1_launches"], matches=res.total_matches, ver_ms=st["last_verify_ms"],
@@ -310,6 +313,7 @@ def main():
             if verify:
                 _ = res.two_view_geometry(len(my_pairs) - 1)
         res.free()
+        out["wall_ms"] = dict(upload=(w1 - w0) * 1e3, match_pairs=(w2 - w1) * 1e3, read_and_free=(time.perf_counter() - w2) * 1e3)
         return out
 
     for _ in range(args.warmup):
@@ -375,6 +379,7 @@ def main():
             dist.all_reduce(by, op=dist.ReduceOp.SUM)
         e2e = {"value": pairs_total / te.item(), "unit": "pairs/s", "h2d_bytes_per_step": int(by[0].item()),
                "d2h_bytes_per_step": int(by[1].item()), "steps": n_e2e,
+               "wall_ms_last_step_rank0": {k: round(v, 1) for k, v in r["wall_ms"].items()},
                "note": "per step: b2m_set_images_sharded from pinned host memory (each rank uploads its 1/N of the images, "
                        "NCCL all-gather) + b2m_match_pairs + results read on the host; wall clock, max over ranks; "
                        "byte counts summed over ranks"}
@@ -411,6 +416,9 @@ def main():
     dir1_mode = int(st_end["k1_dir1_mode"])
     split = dir1_mode in (1, 4, 6, 7)
     gathered = dir1_mode in (6, 7)
+    # api.cu match_pairs_impl: resolve + gather of batch b next to the RANSAC kernels of batch b - 1
+    overlapped = (gathered and bool(verify) and not guided and "B2M_NO_OVERLAP" not in os.environ
+                  and len(my_pairs) > pairs_per_launch)
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the schedule in use (profiles/, ncu --set full)
         tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
@@ -421,8 +429,10 @@ def main():
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
             "traffic": traffic,
             "kernel": ("b2m_k1_filter_kernel x2 per batch: row direction of all pairs + column direction of the MATCHED columns "
-                       "(gathered); the exact resolve of the row direction and the gather run between the two and are inside "
-                       "the K1 time" if gathered else
+                       "(gathered); " + ("overlapped order: K1 time = the two GEMM launches alone, CUDA events around each"
+                                         if overlapped else
+                                         "the exact resolve of the row direction and the gather run between the two and are "
+                                         "inside the K1 time") if gathered else
                        "b2m_k1_filter_kernel x2 per batch (row direction of all pairs + column direction of the live pairs)"
                        if split else "b2m_k1_filter_kernel"),
             "k1_dir1_mode": dir1_mode, "avg_launch_ms": k1_avg_ms,

@@ -284,15 +284,16 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     CU_TRY(ctx, cudaEventSynchronize(ctx->ev_k[s]));
     const unsigned long long total = *W.h_cursor[s];
     {
-      float k1ms = 0.f;
-      if (cudaEventElapsedTime(&k1ms, ctx->ev_k1a[s], ctx->ev_k1b[s]) == cudaSuccess) ctx->stats.last_k1_ms += k1ms;
-      float vms = 0.f;  // compaction + verification kernels of this batch
+      float k1ms = 0.f, vms = 0.f;
       if (pipelined) {
         // overlapped order: K1 = the two GEMM launches; everything else (resolve, gather, compaction, RANSAC,
-        // decision) is the remainder of the step, computed at the end
+        // decision) is the remainder of the step, computed at the end.  The GEMM0 events of this slot may already
+        // belong to batch b + 2 here: the launch loop reads them before re-recording (gemm0_time).
         if (cudaEventElapsedTime(&k1ms, ctx->ev_g2a[s], ctx->ev_g2b[s]) == cudaSuccess) ctx->stats.last_k1_ms += k1ms;
-      } else if (cudaEventElapsedTime(&vms, ctx->ev_k1b[s], ctx->ev_k[s]) == cudaSuccess) {
-        verify_ms += vms;
+      } else {
+        if (cudaEventElapsedTime(&k1ms, ctx->ev_k1a[s], ctx->ev_k1b[s]) == cudaSuccess) ctx->stats.last_k1_ms += k1ms;
+        // compaction + verification kernels of this batch
+        if (cudaEventElapsedTime(&vms, ctx->ev_k1b[s], ctx->ev_k[s]) == cudaSuccess) verify_ms += vms;
       }
     }
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[s], 0));
@@ -493,12 +494,17 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     if (int rc = ensure_gather(ctx)) return bail(rc);
     const GatherScratch g = gather_scratch();
     BatchParams prev;
+    auto gemm0_time = [&](int s) {
+      float t = 0.f;
+      if (cudaEventSynchronize(ctx->ev_k1b[s]) == cudaSuccess &&
+          cudaEventElapsedTime(&t, ctx->ev_k1a[s], ctx->ev_k1b[s]) == cudaSuccess)
+        ctx->stats.last_k1_ms += t;
+    };
     for (int64_t b = 0; b < n_batches; ++b) {
       if (ctx->stop) return stopped();
-      if (b >= 2)
-        if (int rc = finish(b - 2)) return bail(rc);  // frees slot b & 1 (its RANSAC was enqueued one iteration ago)
       BatchParams bp = batch_params(b);
       const int s = bp.s, nb = bp.nb;
+      if (b >= 2) gemm0_time(s);  // GEMM0 of batch b - 2: complete (the host waited for RANSAC(b - 3) an iteration ago)
       CU_TRY_R(cudaMemsetAsync(W.d_cursor[s], 0, sizeof(unsigned long long), st));
       CU_TRY_R(cudaEventRecord(ctx->ev_k1a[s], st));
       CU_TRY_R(launch_k1_gather_phase(0, S.tmap, W.tmap_gath, bp.mp, S.d_desc, nb, max_strips, ctx->num_sms, g, st));
@@ -508,6 +514,10 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       CU_TRY_R(cudaEventRecord(ctx->ev_p1[s], ctx->aux_stream));
       if (b > 0)
         if (int rc = verify_stage(prev)) return rc;
+      // Drain batch b - 2 (same slot as b) while GEMM0(b) keeps the GPU busy: its RANSAC ran an iteration ago, so the
+      // host does not wait; the slot's match arena / verification outputs are next written by the compaction below.
+      if (b >= 2)
+        if (int rc = finish(b - 2)) return bail(rc);
       CU_TRY_R(cudaStreamWaitEvent(st, ctx->ev_p1[s], 0));
       CU_TRY_R(cudaEventRecord(ctx->ev_g2a[s], st));
       CU_TRY_R(launch_k1_gather_phase(2, S.tmap, W.tmap_gath, bp.mp, S.d_desc, nb, max_strips, ctx->num_sms, g, st));
@@ -521,6 +531,8 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       prev = bp;
     }
     if (int rc = verify_stage(prev)) return rc;
+    gemm0_time(static_cast<int>((n_batches - 1) & 1));   // the last two batches' GEMM0 launches
+    gemm0_time(static_cast<int>((n_batches - 2) & 1));
   } else {
   for (int64_t b = 0; b < n_batches; ++b) {
     if (ctx->stop) return stopped();

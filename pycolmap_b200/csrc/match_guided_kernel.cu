@@ -40,7 +40,7 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
-constexpr int kKpBytes = 2 * kTileN * 8;  // two buffers of 256 column keypoints (float2)
+constexpr int kKpBytes = 2 * kTileN * 16;  // two buffers of 256 per-column float4 (the column's share of the residual)
 constexpr size_t kSmemBytes = 1024 + kBytesA + kStages * kBytesB + kKpBytes + sizeof(Barriers);
 
 __device__ __forceinline__ void merge_top2(uint32_t& a1, uint32_t& a2, uint32_t b1, uint32_t b2) {
@@ -49,38 +49,111 @@ __device__ __forceinline__ void merge_top2(uint32_t& a1, uint32_t& a2, uint32_t 
   a2 = max(max(a2, b2), lo);
 }
 
-// 1 when the correspondence (x1, y1) in image 1 <-> (x2, y2) in image 2 is consistent with the model.
-// kind 0: F (squared Sampson error), kind 1: H (squared forward transfer error).  Same operation order
-// as orc_match_guided, every operation rounded separately.
-// thr_mid: the midpoint between thr and the next float above it, as a double; thr_even: thr's mantissa is even.
-// For the Sampson test the float division r = a / b is replaced by an EXACT equivalent of `fl(a / b) <= thr`:
-// the quotient rounds to a float <= thr iff a / b < thr_mid, or a / b == thr_mid and the tie goes to thr (even
-// mantissa); (double) b * thr_mid is exact (24 x 25 significand bits), so the comparison in double is exact too.
-__device__ __forceinline__ bool consistent(int kind, const float* M, float x1, float y1, float x2, float y2,
-                                           float thr, double thr_mid, bool thr_even) {
-  float r;
+// The geometric test of a matrix element, split into a per-row part, a per-column part and a per-element rest.
+// kind 0: F, squared Sampson error r = num^2 / den <= thr; kind 1: H, squared forward transfer error.  Every float
+// operation is rounded separately and in the order of orc_match_guided (oracle/oracle_match.c), so the decisions are
+// bit-identical; what moves is WHERE an operand is computed:
+//   num = x2 * Fx0 + y2 * Fx1 + Fx2,  den = ((Fx0^2 + Fx1^2) + Ft0^2) + Ft1^2,  Fx = F (x1, y1, 1),  Ft = F^T (x2, y2, 1)
+// Fx depends on the image-1 keypoint only, Ft on the image-2 keypoint only.  Rows of the tile are image 1 in
+// direction 0 and image 2 in direction 1, so one side is a per-thread constant and the other is staged per column
+// (one float4 per column, computed once per tile by one thread instead of once per element by 128):
+//   mode 0 (F, dir 0): row (Fx0, Fx1, Fx2, Fx0^2 + Fx1^2)      column (x2, y2, Ft0^2, Ft1^2)
+//   mode 1 (F, dir 1): row (x2, y2, Ft0^2, Ft1^2)              column (Fx0, Fx1, Fx2, Fx0^2 + Fx1^2)
+//   mode 2 (H): u = (H x1)_x / w, v = (H x1)_y / w belong to image 1, (x2, y2) to image 2; r = (u - x2)^2 + (v - y2)^2
+//               (the sign of a correctly rounded difference does not change its square)
+__device__ __forceinline__ float4 side_image1(int kind, const float* M, float x1, float y1) {
   if (kind == 0) {
     const float Fx0 = __fadd_rn(__fadd_rn(__fmul_rn(M[0], x1), __fmul_rn(M[1], y1)), M[2]);
     const float Fx1 = __fadd_rn(__fadd_rn(__fmul_rn(M[3], x1), __fmul_rn(M[4], y1)), M[5]);
     const float Fx2 = __fadd_rn(__fadd_rn(__fmul_rn(M[6], x1), __fmul_rn(M[7], y1)), M[8]);
+    return make_float4(Fx0, Fx1, Fx2, __fadd_rn(__fmul_rn(Fx0, Fx0), __fmul_rn(Fx1, Fx1)));
+  }
+  const float w = __fadd_rn(__fadd_rn(__fmul_rn(M[6], x1), __fmul_rn(M[7], y1)), M[8]);
+  const float u = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x1), __fmul_rn(M[1], y1)), M[2]), w);
+  const float v = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[3], x1), __fmul_rn(M[4], y1)), M[5]), w);
+  return make_float4(u, v, 0.f, 0.f);
+}
+__device__ __forceinline__ float4 side_image2(int kind, const float* M, float x2, float y2) {
+  if (kind == 0) {
     const float Ft0 = __fadd_rn(__fadd_rn(__fmul_rn(M[0], x2), __fmul_rn(M[3], y2)), M[6]);
     const float Ft1 = __fadd_rn(__fadd_rn(__fmul_rn(M[1], x2), __fmul_rn(M[4], y2)), M[7]);
-    const float num = __fadd_rn(__fadd_rn(__fmul_rn(x2, Fx0), __fmul_rn(y2, Fx1)), Fx2);
-    const float den = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Fx0, Fx0), __fmul_rn(Fx1, Fx1)), __fmul_rn(Ft0, Ft0)),
-                                __fmul_rn(Ft1, Ft1));
-    const float a = __fmul_rn(num, num);
-    if (!(den > 0.0f) || !(a < __int_as_float(0x7f800000)) || !(den < __int_as_float(0x7f800000)))
-      return __fdiv_rn(a, den) <= thr;   // zero / infinite / NaN operands: the literal expression (never on real data)
-    const double lhs = static_cast<double>(a), rhs = static_cast<double>(den) * thr_mid;
-    return lhs < rhs || (lhs == rhs && thr_even);
-  } else {
-    const float w = __fadd_rn(__fadd_rn(__fmul_rn(M[6], x1), __fmul_rn(M[7], y1)), M[8]);
-    const float u = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x1), __fmul_rn(M[1], y1)), M[2]), w);
-    const float v = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[3], x1), __fmul_rn(M[4], y1)), M[5]), w);
-    const float du = __fsub_rn(u, x2), dv = __fsub_rn(v, y2);
-    r = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
+    return make_float4(x2, y2, __fmul_rn(Ft0, Ft0), __fmul_rn(Ft1, Ft1));
   }
-  return r <= thr;
+  return make_float4(x2, y2, 0.f, 0.f);
+}
+
+// `fl(a / den) <= thr` without the division.  thr_next = the next float above thr (thr > 0).
+//   a > RU(den * thr_next) >= den * thr_next > den * thr_mid  =>  the quotient rounds above thr          (reject)
+//   a < RD(den * thr)      <= den * thr                       =>  the quotient is below thr, rounds <= thr (accept)
+// and only in the sliver between the two (relative width 2^-23), or with zero / infinite / NaN operands, the exact
+// decision: the quotient rounds to a float <= thr iff a / den < thr_mid (the midpoint of thr and thr_next), or
+// == thr_mid and the tie goes to thr (even mantissa); (double) den * thr_mid is exact (24 x 25 significand bits).
+__device__ __noinline__ bool sampson_sliver(float a, float den, float thr, double thr_mid, bool thr_even) {
+  if (!(den > 0.0f) || !(a < __int_as_float(0x7f800000)) || !(den < __int_as_float(0x7f800000)))
+    return __fdiv_rn(a, den) <= thr;   // the literal expression (never on real data)
+  const double lhs = static_cast<double>(a), rhs = static_cast<double>(den) * thr_mid;
+  return lhs < rhs || (lhs == rhs && thr_even);
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {   // shared-window load (the staging pointer is generic)
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+
+// One 32-column chunk of a row: mask the dot products by the geometric test, update the four running top-2 key pairs.
+template <int MODE>
+__device__ __forceinline__ void scan_chunk(const uint32_t* v, uint32_t cols, int col_base, const float4 r, float thr,
+                                           float thr_next, double thr_mid, bool thr_even, uint32_t* k1, uint32_t* k2) {
+  uint32_t sliver = 0;   // elements whose decision needs the exact comparison: revisited after the sweep (rare)
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float4 c = lds_f4(cols + 16u * j);   // the same address for the whole warp: a broadcast
+    bool ok;
+    if (MODE == 2) {
+      const float du = __fsub_rn(r.x, c.x), dv = __fsub_rn(r.y, c.y);
+      ok = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)) <= thr;
+    } else {
+      float num, den;
+      if (MODE == 0) {
+        num = __fadd_rn(__fadd_rn(__fmul_rn(c.x, r.x), __fmul_rn(c.y, r.y)), r.z);
+        den = __fadd_rn(__fadd_rn(r.w, c.z), c.w);
+      } else {
+        num = __fadd_rn(__fadd_rn(__fmul_rn(r.x, c.x), __fmul_rn(r.y, c.y)), c.z);
+        den = __fadd_rn(__fadd_rn(c.w, r.z), r.w);
+      }
+      const float a = __fmul_rn(num, num);
+      ok = a < __fmul_rd(den, thr);
+      if (!ok && !(a > __fmul_ru(den, thr_next))) sliver |= 1u << j;
+    }
+    const uint32_t d = ok ? v[j] : 0u;
+    const uint32_t key = (d << 8) | static_cast<uint32_t>(255 - (col_base + j));
+    const uint32_t lo = min(k1[j & 3], key);
+    k1[j & 3] = max(k1[j & 3], key);
+    k2[j & 3] = max(k2[j & 3], lo);
+  }
+  if (MODE != 2 && sliver != 0) {
+    // the masked key of such an element is already in (harmless: dot product 0); add the real one where the exact
+    // decision accepts.  The running top-2 is a multiset maximum: insertion order does not matter.
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (!((sliver >> j) & 1u)) continue;
+      const float4 c = lds_f4(cols + 16u * j);
+      float num, den;
+      if (MODE == 0) {
+        num = __fadd_rn(__fadd_rn(__fmul_rn(c.x, r.x), __fmul_rn(c.y, r.y)), r.z);
+        den = __fadd_rn(__fadd_rn(r.w, c.z), c.w);
+      } else {
+        num = __fadd_rn(__fadd_rn(__fmul_rn(r.x, c.x), __fmul_rn(r.y, c.y)), c.z);
+        den = __fadd_rn(__fadd_rn(c.w, r.z), r.w);
+      }
+      if (!sampson_sliver(__fmul_rn(num, num), den, thr, thr_mid, thr_even)) continue;
+      const uint32_t key = (v[j] << 8) | static_cast<uint32_t>(255 - (col_base + j));
+      const uint32_t lo = min(k1[j & 3], key);
+      k1[j & 3] = max(k1[j & 3], key);
+      k2[j & 3] = max(k2[j & 3], lo);
+    }
+  }
 }
 
 }  // namespace
@@ -105,7 +178,7 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + kBytesA;
-  float2* kp_s = reinterpret_cast<float2*>(smem + kBytesA + kStages * kBytesB);
+  float4* kp_s = reinterpret_cast<float4*>(smem + kBytesA + kStages * kBytesB);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kBytesA + kStages * kBytesB + kKpBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -190,47 +263,35 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
     const bool thr_even = (__float_as_int(thr) & 1) == 0;
     const float2 kr = (row < nA) ? g.kpts[p.img_row0[ia] + row] : make_float2(0.f, 0.f);
     const float2* kcol = g.kpts + p.img_row0[ib];
+    // image 1 is pairs[2 * pair], image 2 is pairs[2 * pair + 1]: in direction 1 the rows are image 2
+    const int mode = gkind == 0 ? dir : 2;
+    const float4 rc = (dir == 0) ? side_image1(gkind, M, kr.x, kr.y) : side_image2(gkind, M, kr.x, kr.y);
     int32_t best_d = 0, best_c = -1, second_d = 0;
     uint32_t as = 0, aphase = 0;
     const uint32_t lane_base = (static_cast<uint32_t>(quarter * 32) << 16) + group * (kTileN / kColGroups);
     for (int t = 0; t < n_tiles; ++t) {
-      // stage the 256 column keypoints of this tile (two per thread), double-buffered by tile parity
-      float2* kb = kp_s + (t & 1) * kTileN;
+      // stage the column side of this tile's 256 columns (one per thread), double-buffered by tile parity
+      float4* kb = kp_s + (t & 1) * kTileN;
       for (int c = threadIdx.x; c < kTileN; c += kEpiWarps * 32) {
         const int j = t * kTileN + c;
-        kb[c] = (j < nB) ? kcol[j] : make_float2(0.f, 0.f);
+        const float2 kc = (j < nB) ? kcol[j] : make_float2(0.f, 0.f);
+        kb[c] = (dir == 0) ? side_image2(gkind, M, kc.x, kc.y) : side_image1(gkind, M, kc.x, kc.y);
       }
       asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + as * kTileN;
       uint32_t k1[4] = {0, 0, 0, 0}, k2[4] = {0, 0, 0, 0};
-      // LAZY geometric test: a dot product that does not exceed this row's running second best (over the CONSISTENT
-      // columns seen so far) cannot change (best, second) whether it is consistent or not -- the scan updates on
-      // strict `>` only -- so the float32 residual (25 separately rounded operations and a division) is evaluated
-      // only for the few columns that could still matter: after the first tile ~1 % of them.  Same result, bit for bit.
-      const uint32_t floor_d = static_cast<uint32_t>(second_d);
       const int col0 = group * (kTileN / kColGroups);   // this warp's columns of the tile
 #pragma unroll 1
       for (int c = 0; c < kTileN / kColGroups / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          uint32_t d = 0u;
-          if (v[j] > floor_d) {
-            const float2 kc = kb[col0 + c * 32 + j];
-            // image 1 is pairs[2*pair], image 2 is pairs[2*pair+1]: in direction 1 rows are image 2
-            const bool ok = (dir == 0) ? consistent(gkind, M, kr.x, kr.y, kc.x, kc.y, thr, thr_mid, thr_even)
-                                       : consistent(gkind, M, kc.x, kc.y, kr.x, kr.y, thr, thr_mid, thr_even);
-            d = ok ? v[j] : 0u;
-          }
-          const uint32_t key = (d << 8) | static_cast<uint32_t>(255 - (col0 + c * 32 + j));
-          const uint32_t lo = min(k1[j & 3], key);
-          k1[j & 3] = max(k1[j & 3], key);
-          k2[j & 3] = max(k2[j & 3], lo);
-        }
+        const uint32_t cols = smem_u32(kb + col0 + c * 32);
+        if (mode == 0) scan_chunk<0>(v, cols, col0 + c * 32, rc, thr, thr_next, thr_mid, thr_even, k1, k2);
+        else if (mode == 1) scan_chunk<1>(v, cols, col0 + c * 32, rc, thr, thr_next, thr_mid, thr_even, k1, k2);
+        else scan_chunk<2>(v, cols, col0 + c * 32, rc, thr, thr_next, thr_mid, thr_even, k1, k2);
       }
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[as]);

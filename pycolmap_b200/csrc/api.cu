@@ -448,7 +448,16 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       gp.kpts = S.d_kpts;
       const float me = static_cast<float>(tvg->ransac.max_error);
       gp.max_residual = me * me;
-      CU_TRY_R(launch_k1_guided(S.tmap, bp.mp, gp, nb, max_strips, n_dirs, st));
+      // cross-check: the column direction only for the matched columns (B2M_GUIDED_DIR1=full: both directions in full)
+      static const bool guided_full = [] {
+        const char* e = getenv("B2M_GUIDED_DIR1");
+        return e && !strcmp(e, "full");
+      }();
+      const bool guided_gather = n_dirs == 2 && !guided_full && ensure_gather(ctx) == B2M_OK;
+      if (guided_gather)
+        CU_TRY_R(launch_k1_guided_gather(S.tmap, W.tmap_gath, bp.mp, gp, S.d_desc, nb, max_strips, gather_scratch(), st));
+      else
+        CU_TRY_R(launch_k1_guided(S.tmap, bp.mp, gp, nb, max_strips, n_dirs, st));
       CU_TRY_R(cudaMemsetAsync(gs.cursor, 0, sizeof(unsigned long long), st));
       CompactParams gc = bp.cp;
       gc.arena = gs.arena;
@@ -458,10 +467,10 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       gc.kpts = nullptr;
       gc.pts = nullptr;
       gc.enable = gs.kind;
-      gc.colrank = nullptr;  // the guided kernel computes both directions in full
+      gc.colrank = guided_gather ? W.d_colrank : nullptr;
       CU_TRY_R(launch_crosscheck_compact(gc, nb, st));
       CU_TRY_R(cudaMemcpyAsync(gs.h_cursor, gs.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-      ctx->stats.kernel_launches += 2;
+      ctx->stats.kernel_launches += guided_gather ? 4 : 2;
     }
     CU_TRY_R(cudaMemcpyAsync(W.h_cursor[s], W.d_cursor[s], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU_TRY_R(cudaEventRecord(ctx->ev_k[s], st));

@@ -788,13 +788,15 @@ constexpr int kGatherMaxWords = 1024;  // columns / 32: images up to 32768 featu
 __global__ void __launch_bounds__(256) b2m_k1_gather_kernel(const MatchParams p, const uint8_t* __restrict__ desc,
                                                             uint8_t* __restrict__ gdesc, int32_t* __restrict__ colrank,
                                                             int32_t* __restrict__ cols, int32_t* __restrict__ gcnt,
-                                                            int32_t* __restrict__ items, int32_t* __restrict__ n_items) {
+                                                            int32_t* __restrict__ items, int32_t* __restrict__ n_items,
+                                                            const int32_t* __restrict__ enable) {
   const int pair = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ uint32_t s_bits[kGatherMaxWords];
   __shared__ int s_pref[kGatherMaxWords];
   __shared__ int s_warp[8], s_total, s_item0;
-  if (p.cand_cnt[2 * pair] == 0) {  // no candidate, hence no match: the column direction is never consulted
+  // no candidate, hence no match: the column direction is never consulted (K1); guided matching: pair not eligible
+  if (enable ? enable[pair] < 0 : p.cand_cnt[2 * pair] == 0) {
     if (tid == 0) gcnt[pair] = 0;
     return;
   }
@@ -911,7 +913,7 @@ cudaError_t launch_k1_gather_phase(int phase, const CUtensorMap& tmap, const CUt
       break;
     case 1:
       b2m_k1_resolve_kernel<<<n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, 0);
-      b2m_k1_gather_kernel<<<n_pairs, 256, 0, stream>>>(p, desc, g.desc, g.colrank, g.cols, g.cnt, g.items, g.n_items);
+      b2m_k1_gather_kernel<<<n_pairs, 256, 0, stream>>>(p, desc, g.desc, g.colrank, g.cols, g.cnt, g.items, g.n_items, nullptr);
       break;
     case 2: {
       // rows = gathered descriptors, columns = image a; outputs go to the direction-1 halves (every index in the
@@ -933,6 +935,15 @@ cudaError_t launch_k1_gather_phase(int phase, const CUtensorMap& tmap, const CUt
       b2m_k1_resolve_kernel<<<n_pairs * kResolveParts, 256, 0, stream>>>(p, desc, 1);
       break;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_matched_columns(const MatchParams& p, const uint8_t* desc, int n_pairs, const GatherScratch& g,
+                                          const int32_t* enable, cudaStream_t stream) {
+  if (n_pairs <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(g.n_items, 0, sizeof(int32_t), stream);
+  if (e != cudaSuccess) return e;
+  b2m_k1_gather_kernel<<<n_pairs, 256, 0, stream>>>(p, desc, g.desc, g.colrank, g.cols, g.cnt, g.items, g.n_items, enable);
   return cudaGetLastError();
 }
 

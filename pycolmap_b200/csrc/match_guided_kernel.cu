@@ -101,6 +101,23 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {   // shared-window loa
   return r;
 }
 
+// comparison -> 0xffffffff / 0 (ordered comparisons: false on NaN)
+__device__ __forceinline__ uint32_t set_lt(float a, float b) {
+  uint32_t m;
+  asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
+  return m;
+}
+__device__ __forceinline__ uint32_t set_le(float a, float b) {
+  uint32_t m;
+  asm("set.le.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
+  return m;
+}
+__device__ __forceinline__ uint32_t set_gt(float a, float b) {
+  uint32_t m;
+  asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
+  return m;
+}
+
 // One 32-column chunk of a row: mask the dot products by the geometric test, update the four running top-2 key pairs.
 template <int MODE>
 __device__ __forceinline__ void scan_chunk(const uint32_t* v, uint32_t cols, int col_base, const float4 r, float thr,
@@ -109,10 +126,10 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* v, uint32_t cols, int
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const float4 c = lds_f4(cols + 16u * j);   // the same address for the whole warp: a broadcast
-    bool ok;
+    uint32_t okm;   // all ones when the element is consistent (set.* masks keep the sweep free of branches)
     if (MODE == 2) {
       const float du = __fsub_rn(r.x, c.x), dv = __fsub_rn(r.y, c.y);
-      ok = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)) <= thr;
+      okm = set_le(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)), thr);
     } else {
       float num, den;
       if (MODE == 0) {
@@ -123,10 +140,11 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* v, uint32_t cols, int
         den = __fadd_rn(__fadd_rn(c.w, r.z), r.w);
       }
       const float a = __fmul_rn(num, num);
-      ok = a < __fmul_rd(den, thr);
-      if (!ok && !(a > __fmul_ru(den, thr_next))) sliver |= 1u << j;
+      okm = set_lt(a, __fmul_rd(den, thr));
+      const uint32_t rej = set_gt(a, __fmul_ru(den, thr_next));   // ordered: a NaN is neither accepted nor rejected here
+      sliver |= ~(okm | rej) & (1u << j);
     }
-    const uint32_t d = ok ? v[j] : 0u;
+    const uint32_t d = v[j] & okm;
     const uint32_t key = (d << 8) | static_cast<uint32_t>(255 - (col_base + j));
     const uint32_t lo = min(k1[j & 3], key);
     k1[j & 3] = max(k1[j & 3], key);
@@ -159,18 +177,22 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* v, uint32_t cols, int
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 2)  // 2 x 8 epilogue warps per SM
-b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams p, const GuidedParams g) {
+b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_a, const MatchParams p,
+                     const GuidedParams g) {
   const int pair = blockIdx.z;
   const int gkind = g.kind[pair];
   if (gkind < 0) return;  // pair not eligible for guided matching (uniform exit)
-  const int dir = blockIdx.y;
+  const int dir = g.only_dir >= 0 ? g.only_dir : blockIdx.y;
   const int strip = blockIdx.x;
   const int ia = p.pairs[2 * pair + dir];
   const int ib = p.pairs[2 * pair + (dir ^ 1)];
-  const int nA = p.img_nfeat[ia];
+  // gathered launch: the rows are the matched columns of the row direction, ranked ascending, their descriptors in the
+  // pair's slice of the scratch (tmap_a); row r is feature gath_cols[r] of image `ia`
+  const bool gathered = g.gath_cnt != nullptr;
+  const int nA = gathered ? g.gath_cnt[pair] : p.img_nfeat[ia];
   const int nB = p.img_nfeat[ib];
   if (strip * kTileM >= nA) return;
-  const int rowA = p.img_row0[ia] + strip * kTileM;
+  const int rowA = (gathered ? pair * p.mstride : p.img_row0[ia]) + strip * kTileM;
   const int rowB = p.img_row0[ib];
   const int n_tiles = (nB + kTileN - 1) / kTileN;
 
@@ -186,6 +208,7 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
 
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tmap);
+    tma_prefetch_desc(&tmap_a);
     mbar_init(&bars->full_a, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars->full_b[s], 1);
@@ -209,7 +232,7 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
   if (warp == kEpiWarps) {
     if (lane == 0 && n_tiles > 0) {
       mbar_arrive_expect_tx(&bars->full_a, kBytesA);
-      tma_load_2d(smA, &tmap, &bars->full_a, 0, rowA);
+      tma_load_2d(smA, &tmap_a, &bars->full_a, 0, rowA);
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&bars->empty_b[stage], phase ^ 1);
@@ -261,7 +284,8 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const MatchParams
     const float thr_next = __int_as_float(__float_as_int(thr) + 1);   // thr > 0: the next float above
     const double thr_mid = 0.5 * (static_cast<double>(thr) + static_cast<double>(thr_next));
     const bool thr_even = (__float_as_int(thr) & 1) == 0;
-    const float2 kr = (row < nA) ? g.kpts[p.img_row0[ia] + row] : make_float2(0.f, 0.f);
+    const float2 kr = (row < nA) ? g.kpts[p.img_row0[ia] + (gathered ? g.gath_cols[static_cast<int64_t>(pair) * p.mstride + row] : row)]
+                                 : make_float2(0.f, 0.f);
     const float2* kcol = g.kpts + p.img_row0[ib];
     // image 1 is pairs[2 * pair], image 2 is pairs[2 * pair + 1]: in direction 1 the rows are image 2
     const int mode = gkind == 0 ? dir : 2;
@@ -365,7 +389,46 @@ cudaError_t launch_k1_guided(const CUtensorMap& tmap, const MatchParams& p, cons
     attr_set[dev] = true;
   }
   dim3 grid(max_strips, n_dirs, n_pairs);
-  b2m_k1_guided_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, p, g);
+  GuidedParams gq = g;
+  gq.gath_cnt = nullptr;
+  gq.gath_cols = nullptr;
+  gq.only_dir = -1;
+  b2m_k1_guided_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, tmap, p, gq);
+  return cudaGetLastError();
+}
+
+// FindBestMatchesBruteForce keeps (i, m12[i]) iff m21[m12[i]] == i: the column direction is consulted at the matched
+// columns only (the argument of launch_k1_filter_gather; here the masked matrix is the same for both directions, so it
+// carries over unchanged).  Three launches: rows of image 1 against all of image 2; gather; the gathered rows of image
+// 2 against all of image 1.  CTAs of the last launch beyond a pair's gathered rows exit at once.
+cudaError_t launch_k1_guided_gather(const CUtensorMap& tmap, const CUtensorMap& tmap_gath, const MatchParams& p,
+                                    const GuidedParams& g, const uint8_t* desc, int n_pairs, int max_strips,
+                                    const GatherScratch& gs, cudaStream_t stream) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(b2m_k1_guided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSmemBytes));
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  if (n_pairs <= 0) return cudaSuccess;
+  dim3 grid(max_strips, 1, n_pairs);
+  GuidedParams g0 = g;
+  g0.gath_cnt = nullptr;
+  g0.gath_cols = nullptr;
+  g0.only_dir = 0;
+  b2m_k1_guided_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, tmap, p, g0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = launch_gather_matched_columns(p, desc, n_pairs, gs, g.kind, stream);
+  if (e != cudaSuccess) return e;
+  GuidedParams g1 = g;
+  g1.gath_cnt = gs.cnt;
+  g1.gath_cols = gs.cols;
+  g1.only_dir = 1;
+  b2m_k1_guided_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap, tmap_gath, p, g1);
   return cudaGetLastError();
 }
 

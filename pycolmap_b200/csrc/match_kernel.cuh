@@ -55,6 +55,12 @@ struct GuidedParams {
   const float* model;           // device [n_pairs][9] float32 row-major (as upstream: Eigen::Matrix3f)
   const float2* kpts;           // device keypoints indexed by padded row
   float max_residual;           // max_error^2 in float32
+  // gathered column direction (launch_k1_guided_gather), else nullptr: the rows of the launch are the features of
+  // image 2 some row of the first launch matched, ranked ascending -- gath_cnt [n_pairs] = rows per pair,
+  // gath_cols [n_pairs][mstride] = gathered row -> feature index in image 2
+  const int32_t* gath_cnt;
+  const int32_t* gath_cols;
+  int32_t only_dir;             // -1: blockIdx.y is the direction; 0 / 1: the launch computes this direction only
 };
 
 // Rows per A strip / columns per B tile: images are padded (with zero descriptors, which can
@@ -107,6 +113,14 @@ cudaError_t launch_k1_gather_phase(int phase, const CUtensorMap& tmap, const CUt
                                    cudaStream_t stream);
 cudaError_t launch_k1_guided(const CUtensorMap& tmap, const MatchParams& p, const GuidedParams& g, int n_pairs,
                              int max_strips, int n_dirs, cudaStream_t stream);
+// Cross-check variant: the row direction in full, then the column direction for the matched columns only (the
+// gather kernel and scratch of launch_k1_filter_gather); the compaction must look m21 up through g.colrank.
+cudaError_t launch_k1_guided_gather(const CUtensorMap& tmap, const CUtensorMap& tmap_gath, const MatchParams& p,
+                                    const GuidedParams& g, const uint8_t* desc, int n_pairs, int max_strips,
+                                    const GatherScratch& gs, cudaStream_t stream);
+// the gather step alone (match_filter_kernel.cu); enable: optional device [n_pairs], pairs with enable < 0 are skipped
+cudaError_t launch_gather_matched_columns(const MatchParams& p, const uint8_t* desc, int n_pairs, const GatherScratch& g,
+                                          const int32_t* enable, cudaStream_t stream);
 cudaError_t launch_crosscheck_compact(const CompactParams& p, int n_pairs, cudaStream_t stream);
 // Self-test helper: sets *mismatch != 0 when the match lists of two compaction runs over the same batch
 // differ (per pair: count, then every (idx1, idx2) entry; arena offsets may differ between runs).

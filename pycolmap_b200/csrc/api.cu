@@ -449,10 +449,8 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       const float me = static_cast<float>(tvg->ransac.max_error);
       gp.max_residual = me * me;
       // cross-check: the column direction only for the matched columns (B2M_GUIDED_DIR1=full: both directions in full)
-      static const bool guided_full = [] {
-        const char* e = getenv("B2M_GUIDED_DIR1");
-        return e && !strcmp(e, "full");
-      }();
+      const char* guided_env = getenv("B2M_GUIDED_DIR1");
+      const bool guided_full = guided_env && !strcmp(guided_env, "full");
       const bool guided_gather = n_dirs == 2 && !guided_full && ensure_gather(ctx) == B2M_OK;
       if (guided_gather)
         CU_TRY_R(launch_k1_guided_gather(S.tmap, W.tmap_gath, bp.mp, gp, S.d_desc, nb, max_strips, gather_scratch(), st));

@@ -187,3 +187,55 @@ def test_guided_matching_replaces_inliers(ctx):
         else:
             assert len(vg.inlier_matches) == len(vp.inlier_matches)
     assert n_guided >= 5
+
+
+def test_guided_matching_h_kind_and_gathered_direction():
+    """K1g on planar / panoramic / general two-view scenes with planted correspondences (descriptor k of image 2 is a
+    noisy copy of descriptor k of image 1, keypoints from the scene) + unmatched clutter: the H kind (forward transfer
+    error) and the F kind both bit-exact vs the oracle under the GPU's own model, and the gathered column direction of
+    the cross-check (default) equal to the two-direction launch (B2M_GUIDED_DIR1=full) and to cross_check=False + a
+    host-side cross-check."""
+    import os
+    rng = np.random.default_rng(77)
+    descs, kpts = [], []
+    kinds = ("planar", "general", "rotation", "planar")
+    for kind in kinds:
+        n, extra = 700, 324
+        p1, p2, _ = scenes.two_view_scene(rng, n, 0.25, kind)
+        d1 = syn.sift_like(rng, n + extra)
+        d2 = syn.sift_like(rng, n + extra)
+        d2[:n] = syn.perturb(rng, d1[:n])
+        clutter = lambda: np.c_[rng.uniform(0, 1600, extra), rng.uniform(0, 1200, extra)]
+        k1 = np.r_[p1, clutter()].astype(np.float32)
+        k2 = np.r_[p2, clutter()].astype(np.float32)
+        perm = rng.permutation(n + extra)       # matched features are not at equal indices
+        descs += [d1, d2[perm]]
+        kpts += [k1, k2[perm]]
+    cams = [scenes.CAM] * len(descs)
+    pairs = np.array([(2 * k, 2 * k + 1) for k in range(len(kinds))] + [(1, 0)], np.int32)
+    out = {}
+    for mode in ("gather", "full"):
+        if mode == "full":
+            os.environ["B2M_GUIDED_DIR1"] = "full"
+        try:
+            c = pb.Context(device=0, seed=0)
+            c.set_images(descs, kpts, cams)
+            res = c.match_pairs(pairs, {"guided_matching": True}, pb.TwoViewGeometryOptions())
+            out[mode] = [(int(res.two_view_geometry(k).config), res.inlier_matches(k).copy(),
+                          np.array(res.two_view_geometry(k).H), np.array(res.two_view_geometry(k).F)) for k in range(len(pairs))]
+            res.free()
+            c.close()
+        finally:
+            os.environ.pop("B2M_GUIDED_DIR1", None)
+    n_h = n_f = 0
+    for k, (i, j) in enumerate(pairs):
+        cfg, got, H, F = out["gather"][k]
+        assert cfg == out["full"][k][0] and np.array_equal(got, out["full"][k][1]), k
+        assert cfg != 0
+        kind = 1 if cfg in (R.PLANAR, R.PANORAMIC, R.PLANAR_OR_PANORAMIC) else 0
+        want = oracle.match_guided(descs[i], kpts[i], descs[j], kpts[j], kind, (H if kind else F).reshape(3, 3), 4.0)
+        assert np.array_equal(got, want), (k, kind, len(got), len(want))
+        assert len(got) >= 300
+        n_h += kind
+        n_f += 1 - kind
+    assert n_h >= 2 and n_f >= 1

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -120,17 +121,32 @@ struct b2m_ctx {
   unsigned long long* d_verify_counters = nullptr;  // [6]: models scored / residual evaluations per kind (verify.cu)
 };
 
+namespace b2m {
+// Allocator of the two big result arrays (hundreds of MB per exhaustive call): resize() leaves new elements
+// uninitialised -- every element is overwritten by the memcpy that follows -- instead of zero-filling them first.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInitAlloc<U>; };
+  NoInitAlloc() = default;
+  template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+  template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using BigU32 = std::vector<uint32_t, NoInitAlloc<uint32_t>>;
+}  // namespace b2m
+
 struct b2m_results {
+  ~b2m_results();                // parks the two big arrays in a one-deep process-wide cache (api.cu)
   std::vector<int32_t> pairs;    // [n x 2]
   std::vector<int64_t> off;      // per pair offset (in matches) into `matches`
   std::vector<int32_t> cnt;      // per pair match count
-  std::vector<uint32_t> matches; // [total x 2]
+  b2m::BigU32 matches;           // [total x 2]
   // verification outputs (filled when tvg options were given)
   bool verified = false;
   std::vector<int32_t> config;
   std::vector<int64_t> in_off;
   std::vector<int32_t> in_cnt;
-  std::vector<uint32_t> inliers;
+  b2m::BigU32 inliers;
   std::vector<int32_t> model_idx; // per pair: index into `models` (x 27), or -1 (no geometry: E = F = H = 0)
   std::vector<double> models;    // 27 doubles (E, F, H) per pair that has a geometry -- ~10 % of an exhaustive run
   std::vector<double> poses;     // per pair 8 doubles: qvec (w, x, y, z), tvec, tri_angle (compute_relative_pose)

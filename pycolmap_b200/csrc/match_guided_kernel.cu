@@ -119,19 +119,24 @@ __device__ __forceinline__ uint32_t set_gt(float a, float b) {
 }
 
 // One 32-column chunk of a row: mask the dot products by the geometric test, update the four running top-2 key pairs.
-template <int MODE>
-__device__ __forceinline__ void scan_chunk(const uint32_t* v, uint32_t cols, int col_base, const float4 r, float thr,
+// CB: first column of the chunk inside the warp's 128-column half of the tile -- a compile-time constant, so the
+// column byte of the key is an immediate.  Pipe balance (ncu r02: ALU pipe 70 % busy, FMA pipe 30 %): per element
+// 2 FSETP + SEL + PLOP3 + 3 VIMNMX on the ALU pipe, 5 FMUL + 4 FADD + 1 IMAD (key) on the FMA pipe.
+template <int MODE, int CB>
+__device__ __forceinline__ void scan_chunk(const uint32_t* v, uint32_t cols, const float4 r, float thr,
                                            float thr_next, double thr_mid, bool thr_even, uint32_t* k1, uint32_t* k2) {
-  uint32_t sliver = 0;   // elements whose decision needs the exact comparison: revisited after the sweep (rare)
+  uint32_t undecided = 0;   // some element of the chunk needs the exact comparison: the chunk is revisited (rare)
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const float4 c = lds_f4(cols + 16u * j);   // the same address for the whole warp: a broadcast
-    uint32_t okm;   // all ones when the element is consistent (set.* masks keep the sweep free of branches)
+    bool ok = false;
+    uint32_t d = 0;
+    float a = 0.f, den = 0.f;
     if (MODE == 2) {
       const float du = __fsub_rn(r.x, c.x), dv = __fsub_rn(r.y, c.y);
-      okm = set_le(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)), thr);
+      ok = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)) <= thr;
     } else {
-      float num, den;
+      float num;
       if (MODE == 0) {
         num = __fadd_rn(__fadd_rn(__fmul_rn(c.x, r.x), __fmul_rn(c.y, r.y)), r.z);
         den = __fadd_rn(__fadd_rn(r.w, c.z), c.w);
@@ -139,23 +144,29 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* v, uint32_t cols, int
         num = __fadd_rn(__fadd_rn(__fmul_rn(r.x, c.x), __fmul_rn(r.y, c.y)), c.z);
         den = __fadd_rn(__fadd_rn(c.w, r.z), r.w);
       }
-      const float a = __fmul_rn(num, num);
-      okm = set_lt(a, __fmul_rd(den, thr));
-      const uint32_t rej = set_gt(a, __fmul_ru(den, thr_next));   // ordered: a NaN is neither accepted nor rejected here
-      sliver |= ~(okm | rej) & (1u << j);
+      a = __fmul_rn(num, num);
+      // ok = a < RD(den * thr); decided = ok | a > RU(den * thr_next) (ordered compares: a NaN stays undecided).
+      // One asm block so that each predicate is consumed where it is produced (left to itself the compiler parks the
+      // 32 `ok` flags of a chunk in a bit mask: two more ALU-pipe instructions per element).
+      asm("{\n\t.reg .pred p, q;\n\t"
+          "setp.lt.f32 p, %2, %3;\n\t"
+          "setp.gt.or.f32 q, %2, %4, p;\n\t"
+          "selp.u32 %0, %5, 0, p;\n\t"
+          "@!q or.b32 %1, %1, 1;\n\t}"
+          : "=r"(d), "+r"(undecided)
+          : "f"(a), "f"(__fmul_rd(den, thr)), "f"(__fmul_ru(den, thr_next)), "r"(v[j]));
     }
-    const uint32_t d = v[j] & okm;
-    const uint32_t key = (d << 8) | static_cast<uint32_t>(255 - (col_base + j));
+    if (MODE == 2) d = ok ? v[j] : 0u;
+    const uint32_t key = d * 256u + static_cast<uint32_t>(255 - (CB + j));
     const uint32_t lo = min(k1[j & 3], key);
     k1[j & 3] = max(k1[j & 3], key);
     k2[j & 3] = max(k2[j & 3], lo);
   }
-  if (MODE != 2 && sliver != 0) {
-    // the masked key of such an element is already in (harmless: dot product 0); add the real one where the exact
+  if (MODE != 2 && undecided) {
+    // the masked key of an undecided element is already in (harmless: dot product 0); add the real one where the exact
     // decision accepts.  The running top-2 is a multiset maximum: insertion order does not matter.
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 32; ++j) {
-      if (!((sliver >> j) & 1u)) continue;
       const float4 c = lds_f4(cols + 16u * j);
       float num, den;
       if (MODE == 0) {
@@ -165,13 +176,42 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* v, uint32_t cols, int
         num = __fadd_rn(__fadd_rn(__fmul_rn(r.x, c.x), __fmul_rn(r.y, c.y)), c.z);
         den = __fadd_rn(__fadd_rn(c.w, r.z), r.w);
       }
-      if (!sampson_sliver(__fmul_rn(num, num), den, thr, thr_mid, thr_even)) continue;
-      const uint32_t key = (v[j] << 8) | static_cast<uint32_t>(255 - (col_base + j));
-      const uint32_t lo = min(k1[j & 3], key);
-      k1[j & 3] = max(k1[j & 3], key);
-      k2[j & 3] = max(k2[j & 3], lo);
+      const float a = __fmul_rn(num, num);
+      if (a < __fmul_rd(den, thr) || a > __fmul_ru(den, thr_next)) continue;   // decided in the sweep
+      if (!sampson_sliver(a, den, thr, thr_mid, thr_even)) continue;
+      uint32_t vj = 0;   // v[j] with a run-time j: a select chain instead of a local-memory array
+#pragma unroll
+      for (int q = 0; q < 32; ++q) vj = (q == j) ? v[q] : vj;
+      const uint32_t key = vj * 256u + static_cast<uint32_t>(255 - (CB + j));
+      const int a4 = j & 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q == a4) {
+          const uint32_t lo = min(k1[q], key);
+          k1[q] = max(k1[q], key);
+          k2[q] = max(k2[q], lo);
+        }
     }
   }
+}
+
+// The warp's 128 columns of a tile: four 32-column TMEM loads, each swept against the staged column sides.
+template <int MODE>
+__device__ __forceinline__ void scan_half(uint32_t taddr, uint32_t cols, const float4 r, float thr, float thr_next,
+                                          double thr_mid, bool thr_even, uint32_t* k1, uint32_t* k2) {
+  uint32_t v[32];
+  tmem_ld_32x32(taddr, v);
+  tmem_wait_ld();
+  scan_chunk<MODE, 0>(v, cols, r, thr, thr_next, thr_mid, thr_even, k1, k2);
+  tmem_ld_32x32(taddr + 32, v);
+  tmem_wait_ld();
+  scan_chunk<MODE, 32>(v, cols + 32 * 16, r, thr, thr_next, thr_mid, thr_even, k1, k2);
+  tmem_ld_32x32(taddr + 64, v);
+  tmem_wait_ld();
+  scan_chunk<MODE, 64>(v, cols + 64 * 16, r, thr, thr_next, thr_mid, thr_even, k1, k2);
+  tmem_ld_32x32(taddr + 96, v);
+  tmem_wait_ld();
+  scan_chunk<MODE, 96>(v, cols + 96 * 16, r, thr, thr_next, thr_mid, thr_even, k1, k2);
 }
 
 }  // namespace
@@ -307,15 +347,12 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       const uint32_t taddr = tmem_base + lane_base + as * kTileN;
       uint32_t k1[4] = {0, 0, 0, 0}, k2[4] = {0, 0, 0, 0};
       const int col0 = group * (kTileN / kColGroups);   // this warp's columns of the tile
-#pragma unroll 1
-      for (int c = 0; c < kTileN / kColGroups / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_wait_ld();
-        const uint32_t cols = smem_u32(kb + col0 + c * 32);
-        if (mode == 0) scan_chunk<0>(v, cols, col0 + c * 32, rc, thr, thr_next, thr_mid, thr_even, k1, k2);
-        else if (mode == 1) scan_chunk<1>(v, cols, col0 + c * 32, rc, thr, thr_next, thr_mid, thr_even, k1, k2);
-        else scan_chunk<2>(v, cols, col0 + c * 32, rc, thr, thr_next, thr_mid, thr_even, k1, k2);
+      static_assert(kTileN / kColGroups == 128, "scan_half sweeps four chunks of 32 columns");
+      {
+        const uint32_t cols = smem_u32(kb + col0);
+        if (mode == 0) scan_half<0>(taddr, cols, rc, thr, thr_next, thr_mid, thr_even, k1, k2);
+        else if (mode == 1) scan_half<1>(taddr, cols, rc, thr, thr_next, thr_mid, thr_even, k1, k2);
+        else scan_half<2>(taddr, cols, rc, thr, thr_next, thr_mid, thr_even, k1, k2);
       }
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[as]);
@@ -327,7 +364,7 @@ b2m_k1_guided_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       if (d1 > best_d) {
         second_d = max(best_d, d2);
         best_d = d1;
-        best_c = t * kTileN + (255 - static_cast<int32_t>(k1[0] & 255u));
+        best_c = t * kTileN + col0 + (255 - static_cast<int32_t>(k1[0] & 255u));
       } else {
         second_d = max(second_d, d1);
       }

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "geom.h"
+#include "eig_warp.cuh"
 #include "five_point_warp.cuh"
 #include "pose.h"
 #include "verify.cuh"
@@ -72,6 +73,7 @@ struct VerifyParams {
   int32_t force_calibrated;   // stand-alone: -1 use camera flags
   unsigned long long* prof;   // optional [3][8] cycle counters (B2M_PROF=1), else nullptr
   unsigned long long* counters;  // [6] models scored / residual evaluations per kind (b2m_stats), or nullptr
+  int32_t lo_eig_thread;      // A/B switch B2M_LO_EIG=thread: serial eigen-solve of the LO refits (default: one warp)
   double* e_scratch;          // E kernel, warp / hybrid minimal solves: [nb][kRansacThreads][kEStride] (models, N, polynomial, Mr)
   // guided matching hand-over (written by the decision kernel when guided_min_inliers >= 0)
   int32_t* guided_kind;       // [nb] -1 / 0 (F) / 1 (H)
@@ -547,27 +549,65 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
           }
           __syncthreads();
           B2M_TICK(3);
-          if (tid == 0) {
-            double St[45];
-            for (int k = 0; k < 45; ++k) St[k] = sh.red[0][k] + sh.red[1][k] + sh.red[2][k] + sh.red[3][k];
-            int nc = 0;
-            if (KIND == 0) {
-              // least-squares 4-D null space of the N x 9 system.  The 5-point solver fixes the coefficient of its
-              // LAST basis vector to 1, so that one must be the smallest singular vector (for noise-free inliers it
-              // IS the essential matrix).  The solver itself runs on warp 0 below.
-              double Nr[36];
-              smallest_eigvecs_invit<4>(St, Nr);
-              fpw::Scratch& WS = reinterpret_cast<fpw::Scratch*>(sh.chunk_d)[0];
-              for (int k = 0; k < 4; ++k)
-                for (int e = 0; e < 9; ++e) WS.N[k * 9 + e] = Nr[(3 - k) * 9 + e];
-            } else if (KIND == 1) {
-              nc = finish_F8(St, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
-            } else {
-              nc = finish_H(St, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
+          if (P.lo_eig_thread) {   // A/B switch B2M_LO_EIG=thread: the serial eigen-solve on thread 0
+            if (tid == 0) {
+              double St[45];
+              for (int k = 0; k < 45; ++k) St[k] = sh.red[0][k] + sh.red[1][k] + sh.red[2][k] + sh.red[3][k];
+              int nc = 0;
+              if (KIND == 0) {
+                // least-squares 4-D null space of the N x 9 system.  The 5-point solver fixes the coefficient of its
+                // LAST basis vector to 1, so that one must be the smallest singular vector (for noise-free inliers it
+                // IS the essential matrix).  The solver itself runs on warp 0 below.
+                double Nr[36];
+                smallest_eigvecs_invit<4>(St, Nr);
+                fpw::Scratch& WS = reinterpret_cast<fpw::Scratch*>(sh.chunk_d)[0];
+                for (int k = 0; k < 4; ++k)
+                  for (int e = 0; e < 9; ++e) WS.N[k * 9 + e] = Nr[(3 - k) * 9 + e];
+              } else if (KIND == 1) {
+                nc = finish_F8(St, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
+              } else {
+                nc = finish_H(St, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
+              }
+              sh.n_cand = nc;
             }
-            sh.n_cand = nc;
+            __syncthreads();
+          } else {
+            // the smallest eigenvector(s) of the normal matrix on warp 0 (eig_warp.cuh: bit-identical to the serial
+            // solver, a fraction of its latency -- the other three warps wait at the barrier either way)
+            if (warp == 0) {
+              double* St = sh.red[0];   // summed in place: red[0][k] += red[1..3][k]
+              for (int k = lane; k < 45; k += 32) St[k] = sh.red[0][k] + sh.red[1][k] + sh.red[2][k] + sh.red[3][k];
+              __syncwarp();
+              // scratch: the second warp slot of the 5-point scratch area (chunk_d is idle outside the scoring loop)
+              eigw::Scratch& ES = *reinterpret_cast<eigw::Scratch*>(reinterpret_cast<fpw::Scratch*>(sh.chunk_d) + 1);
+              double* vec = sh.sum_arr;   // [K][9], free between rounds
+              eigw::smallest_eigvecs_warp<KIND == 0 ? 4 : 1>(St, vec, ES, lane);
+              if (lane == 0) {
+                int nc = 0;
+                if (KIND == 0) {
+                  // least-squares 4-D null space of the N x 9 system.  The 5-point solver fixes the coefficient of
+                  // its LAST basis vector to 1, so that one must be the smallest singular vector (for noise-free
+                  // inliers it IS the essential matrix).
+                  fpw::Scratch& WS = reinterpret_cast<fpw::Scratch*>(sh.chunk_d)[0];
+                  for (int k = 0; k < 4; ++k)
+                    for (int e = 0; e < 9; ++e) WS.N[k * 9 + e] = vec[(3 - k) * 9 + e];
+                } else if (KIND == 1) {
+                  double Fn[9];
+                  for (int e = 0; e < 9; ++e) Fn[e] = vec[e];
+                  enforce_rank2(Fn);
+                  denormalize_F(Fn, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
+                  nc = 1;
+                } else {
+                  double Hn[9];
+                  for (int e = 0; e < 9; ++e) Hn[e] = vec[e];
+                  denormalize_H(Hn, s1, cx1, cy1, s2, cx2, cy2, sh.cand_models);
+                  nc = 1;
+                }
+                sh.n_cand = nc;
+              }
+            }
+            __syncthreads();
           }
-          __syncthreads();
           if (KIND == 0) {
             if (warp == 0) {
               const int nc = fpw::five_point_warp(reinterpret_cast<fpw::Scratch*>(sh.chunk_d)[0], sh.cand_models, lane);
@@ -913,6 +953,10 @@ int e5_minimal_mode() {
     return 2;   // measured on B200 (1000 x 8192, B2M_PROF `solve` per two steps): thread 206-348 k, warp 651 k, hybrid 175 k Mcycles
   }();
   return v;
+}
+int lo_eig_thread_mode() {
+  const char* e = getenv("B2M_LO_EIG");
+  return e && !strcmp(e, "thread") ? 1 : 0;
 }
 void launch_e_kernel(const VerifyParams& PE, int nb, cudaStream_t st) {
   switch (e5_minimal_mode()) {
@@ -1430,6 +1474,7 @@ int verify_batch_launch(b2m_ctx* ctx, ImageSet& S, const b2m_tvg_opts* tvg, cons
   P.prof = V->d_prof;
   P.counters = verify_counters(ctx);
   P.e_scratch = V->d_e_scratch;
+  P.lo_eig_thread = lo_eig_thread_mode();
   if (!V->rs.side[0]) {
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[0], cudaStreamNonBlocking));
     V_TRY(ctx, cudaStreamCreateWithFlags(&V->rs.side[1], cudaStreamNonBlocking));
@@ -1741,6 +1786,7 @@ int run_single(b2m_ctx* ctx, const std::vector<double4>& pts, const std::vector<
   P.single_kind = single_kind;
   P.counters = verify_counters(ctx);
   P.e_scratch = G.d_e_scratch;
+  P.lo_eig_thread = lo_eig_thread_mode();
   if (single_kind >= 0) {
     V_TRY(ctx, launch_ransac(P, 1, st));
   } else {
@@ -2047,6 +2093,7 @@ int b2m_estimate_two_view_geometry_batch(b2m_ctx* ctx, const b2m_tvg_problem* pr
     P.single_kind = -1;
     P.counters = verify_counters(ctx);
       P.e_scratch = G.d_e_scratch;
+    P.lo_eig_thread = lo_eig_thread_mode();
     const double4* pts_E = nullptr;
     if (int rc = undistort_for_E(ctx, G, P, full_cams.data(), 2 * nb, nb, cap, st, &pts_E)) return rc;
     V_TRY(ctx, launch_ransac(P, nb, st, nullptr, pts_E));

@@ -239,3 +239,28 @@ def test_guided_matching_h_kind_and_gathered_direction():
         n_h += kind
         n_f += 1 - kind
     assert n_h >= 2 and n_f >= 1
+
+
+def test_warp_eigen_solver_equals_serial_solver():
+    """eig_warp.cuh: the LO refits take the smallest eigenvector(s) of the 9 x 9 normal matrix on one warp; same
+    operations in the same order per matrix element as geom.h smallest_eigvecs_invit, so every output of the verifier
+    -- configuration, inlier lists, E / F / H to the last bit -- equals the serial solver's (B2M_LO_EIG=thread)."""
+    import os
+    rng = np.random.default_rng(123)
+    problems = []
+    for kind, cam in (("general", scenes.CAM), ("planar", scenes.CAM), ("rotation", scenes.CAM), ("general", scenes.CAM_NOPRIOR),
+                      ("general", scenes.CAM), ("planar", scenes.CAM_NOPRIOR)):
+        p1, p2, _ = scenes.two_view_scene(rng, 500, 0.3, kind, noise=0.4)
+        problems.append((cam, p1, cam, p2))
+    out = {}
+    for mode in ("warp", "thread"):
+        if mode == "thread":
+            os.environ["B2M_LO_EIG"] = "thread"
+        try:
+            gs = pb.estimate_two_view_geometries(problems, pb.TwoViewGeometryOptions())
+            out[mode] = [(int(g.config), g.inlier_matches.tobytes(), np.asarray(g.E).tobytes(), np.asarray(g.F).tobytes(),
+                          np.asarray(g.H).tobytes()) for g in gs]
+        finally:
+            os.environ.pop("B2M_LO_EIG", None)
+    assert all(o[0] != 0 for o in out["warp"])
+    assert out["warp"] == out["thread"]

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate(int iters, int n_tile, long l
     tmem_alloc(&tbase, 512);
     tmem_relinquish();
   }
-  fence_proxy_async();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the operands -> async proxy (UMMA)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -147,6 +147,23 @@ int main() {
     cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
     printf(", \"i8_mma_n%d_chip_TOPS\": %.1f", n_tile, 2.0 * 40000.0 * 128 * n_tile * 128 * 148 / (ms * 1e-3) / 1e12);
+  }
+  {
+    // SUSTAINED rate: the same MMA loop back to back for ~4 s (the board settles at its power-capped clock), the last
+    // second timed.  This is the denominator for a kernel timed inside a long step (B200_PROFILING.md); the burst
+    // figures above are for a kernel timed alone.
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    const int n_tile = 256;
+    const double ops_per_launch = 2.0 * 40000.0 * 128 * n_tile * 128 * 148;
+    for (int i = 0; i < 280; ++i) mma_rate<<<148, 128, 60000>>>(40000, n_tile, d_cycles);   // ~3 s of warm-up
+    cudaEventRecord(a);
+    const int timed = 92;                                                                    // ~1 s
+    for (int i = 0; i < timed; ++i) mma_rate<<<148, 128, 60000>>>(40000, n_tile, d_cycles);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    printf(", \"i8_mma_n256_chip_TOPS_sustained\": %.1f, \"sustained_window_ms\": %.0f", ops_per_launch * timed / (ms * 1e-3) / 1e12, ms);
   }
   printf("}\n");
   return 0;

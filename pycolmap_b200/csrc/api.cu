@@ -387,6 +387,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
     cp.kpts = tvg ? S.d_kpts : nullptr;
     cp.pts = tvg ? static_cast<double4*>(verify_points_arena(ctx, bp.s)) : nullptr;
     cp.enable = nullptr;
+    cp.cand_cnt = ctx->exact_k1 ? nullptr : W.d_cand_cnt;   // the filter epilogue's candidate counts (not produced by K1-exact)
     return bp;
   };
   // Column direction of the cross-check: computed for the matched columns only (launch_k1_filter_gather).  The
@@ -494,6 +495,7 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
       gc.kpts = nullptr;
       gc.pts = nullptr;
       gc.enable = gs.kind;
+      gc.cand_cnt = nullptr;   // the guided kernel writes final matches, no candidate lists
       gc.colrank = guided_gather ? W.d_colrank : nullptr;
       CU_TRY_R(launch_crosscheck_compact(gc, nb, st));
       CU_TRY_R(cudaMemcpyAsync(gs.h_cursor, gs.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

@@ -228,6 +228,14 @@ __global__ void __launch_bounds__(256) b2m_crosscheck_compact_kernel(const Compa
     return;
   }
 
+  if (p.cand_cnt && p.cand_cnt[2 * pair] == 0) {  // most pairs of an exhaustive batch: nothing matched
+    if (threadIdx.x == 0) {
+      p.pair_off[pair] = static_cast<int64_t>(atomicAdd(p.cursor, 0ull));
+      p.pair_cnt[pair] = 0;
+    }
+    return;
+  }
+
   // pass 1: count
   int cnt = 0;
   for (int i = threadIdx.x; i < n1; i += 256) {
@@ -244,8 +252,11 @@ __global__ void __launch_bounds__(256) b2m_crosscheck_compact_kernel(const Compa
     p.pair_off[pair] = static_cast<int64_t>(s_off);
     p.pair_cnt[pair] = total;
     s_base = 0;
+    s_warp[0] = total;
   }
   __syncthreads();
+  if (s_warp[0] == 0) return;   // uniform: nothing to write
+  __syncthreads();              // s_warp is reused by the ordered write
   uint2* out = p.arena + s_off;
 
   // pass 2: ordered write

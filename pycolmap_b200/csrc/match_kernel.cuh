@@ -47,6 +47,8 @@ struct CompactParams {
   const int32_t* enable;        // optional [n_pairs]: pairs with enable[pair] < 0 produce no output (guided pass)
   const int32_t* colrank;       // optional [n_pairs][mstride]: m21 is indexed by the RANK of a column among the pair's
                                 // matched columns (gathered column direction), not by the column itself
+  const int32_t* cand_cnt;      // optional [n_pairs][2] candidate counts of the filter epilogue (K1 v2): a pair without a
+                                // row-direction candidate has no match, its m12 rows need not be read
 };
 
 // Guided matching (K1g): per pair of the batch the geometry chosen by the verifier.

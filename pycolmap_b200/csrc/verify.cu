@@ -135,8 +135,10 @@ __device__ __forceinline__ int inlier_f32(const float* M, float x1, float y1, fl
     lhs = num * num;
     rhs = thr * fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, b1 * b1)));
   }
-  const int in = lhs <= 0.99f * rhs ? 1 : 0;
-  const int out = lhs >= 1.01f * rhs ? 1 : 0;
+  // STRICT comparisons: lhs == rhs == 0 (both underflowed) or == inf (both overflowed) is neither clearly in nor
+  // clearly out, like any NaN -> borderline -> decided in fp64
+  const int in = lhs < 0.99f * rhs ? 1 : 0;
+  const int out = lhs > 1.01f * rhs ? 1 : 0;
   return in | ((in | out) ^ 1) << 1;  // bit 0: inlier, bit 1: borderline (neither clearly in nor out)
 }
 
@@ -207,11 +209,13 @@ template <int KIND, int PPT>
 __device__ __forceinline__ void score_block(Shared& sh, const double4* pts, int64_t off, const PointXform& X, int n, int pb,
                                             int n_chunk, double thr, float thr_f, int tid, int need) {
   float px1[PPT], py1[PPT], px2[PPT], py2[PPT];
+  int live[PPT];   // 1 for a real match, 0 for a slot past the end: such a slot never counts, whatever the model
+                   // (its far-away point is an outlier for every sane model, but lhs and rhs can both overflow)
 #pragma unroll
   for (int q = 0; q < PPT; ++q) {
     const int i = pb + q * kRansacThreads + tid;
-    // slots past the end get a far-away point: a clear outlier for every finite model
     double x1 = 0, y1 = 0, x2 = 1e15, y2 = 1e15;
+    live[q] = i < n ? 1 : 0;
     if (i < n) load_pt(pts, off + i, X, x1, y1, x2, y2);
     px1[q] = static_cast<float>(x1); py1[q] = static_cast<float>(y1);
     px2[q] = static_cast<float>(x2); py2[q] = static_cast<float>(y2);
@@ -229,7 +233,7 @@ __device__ __forceinline__ void score_block(Shared& sh, const double4* pts, int6
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
       const int f = inlier_f32<KIND>(Mf, px1[q], py1[q], px2[q], py2[q], thr_f);
-      c += f & 1;
+      c += f & live[q];
       flags |= f;
     }
     if (flags & 2) {  // rare: a borderline point -> redo this thread's points of this model in fp64
@@ -415,7 +419,8 @@ __device__ void ransac_problem(const VerifyParams& P, Shared& sh, int pair, int6
           need = max(sh.best_cnt + 1, sh.round_max) - rem;
         }
         // the last block takes as few point slots per thread as cover it (a slot past the end costs a full test)
-        if (rem > 2 * kRansacThreads) score_block<KIND, 4>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid, need);
+        if (rem > 3 * kRansacThreads) score_block<KIND, 4>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid, need);
+        else if (rem > 2 * kRansacThreads) score_block<KIND, 3>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid, need);
         else if (rem > kRansacThreads) score_block<KIND, 2>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid, need);
         else score_block<KIND, 1>(sh, pts, off, X, n, pb, n_chunk, thr, thr_f, tid, need);
       }

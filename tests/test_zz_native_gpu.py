@@ -260,9 +260,19 @@ def test_native_batched_two_view_geometry():
         single = nat.estimate_two_view_geometry(*prob)
         assert g.config == single.config == want_cfg.get(k, single.config), (k, g.config, single.config)
         n1, n2 = len(g.inlier_matches), len(single.inlier_matches)
-        assert abs(n1 - n2) <= max(2, int(0.01 * n2)), (k, n1, n2)
+        # a problem's RANSAC stream is keyed by its position in the batch: batch and single call draw different samples.
+        # On planar / rotating scenes each run admits its own handful of the uniform outliers (tests/test_verify_gpu.py):
+        # the two results may differ by those
+        admitted = 0
+        if k < 6 and n1 and n2:
+            admitted = max(int((~planted[k][g.inlier_matches[:, 0]]).sum()), int((~planted[k][single.inlier_matches[:, 0]]).sum()))
+        assert abs(n1 - n2) <= max(2, int(0.01 * n2), admitted), (k, n1, n2, admitted)
         if k < 6 and n2:
-            assert abs(n1 - planted[k].sum()) <= max(4, int(0.02 * planted[k].sum()))
+            # general scenes: the planted inliers and nothing else; planar / rotating scenes: the winning mask may be
+            # E's or F's, under-constrained there, plus its handful of admitted outliers (bounded like nF in
+            # tests/test_verify_gpu.py: 5 % of n)
+            general = k in (0, 2, 4, 5)
+            assert abs(n1 - planted[k].sum()) <= (max(4, int(0.02 * planted[k].sum())) if general else max(6, int(0.05 * len(planted[k]))))
             assert np.all(np.diff(g.inlier_matches[:, 0].astype(np.int64)) > 0)      # identity matches stay ordered
     assert set(map(tuple, gs[6].inlier_matches)) <= set(map(tuple, m))
     assert len(gs[6].inlier_matches) >= 0.95 * pl[perm].sum()

@@ -262,8 +262,13 @@ int match_pairs_impl(b2m_ctx* ctx, ImageSet& S, const int32_t* pairs, int64_t n_
 
   // pairs per kernel batch; bounded so that the worst-case scratch of the gathered column direction
   // (batch x mstride descriptors) stays below 6 GB even for 32768-feature images
-  const int B = static_cast<int>(std::min<int64_t>(
-      ctx->pair_batch, std::max<int64_t>(64, (int64_t{6} << 30) / (static_cast<int64_t>(round_up(S.max_feat_pad, 512)) * 128))));
+  // Default: as many pairs as keep batch x (padded rows per image) at what 4096 pairs of 8192-feature images are -- the
+  // per-batch chain of small kernels and the RANSAC launch tails are a fixed cost per batch, so smaller images take
+  // proportionally more pairs per batch (5000 x 4096: 8192).
+  const int64_t rows_pad = round_up(S.max_feat_pad, 512);
+  const int64_t want = ctx->pair_batch_auto ? std::min<int64_t>(16384, std::max<int64_t>(1024, (int64_t{4096} * 8192) / rows_pad))
+                                            : ctx->pair_batch;
+  const int B = static_cast<int>(std::min<int64_t>(want, std::max<int64_t>(64, (int64_t{6} << 30) / (rows_pad * 128))));
   // rows are handed out in 512-row cluster blocks: keep the per-pair stride a multiple of that
   // sized for the pairs of this call, not for a full batch: a context that only ever sees small jobs stays small
   if (int rc = ensure_workspace(ctx, static_cast<int>(std::min<int64_t>(B, std::max<int64_t>(n_pairs, 1))),
@@ -785,7 +790,10 @@ int b2m_create(const b2m_device_cfg* cfg, b2m_ctx** out) {
   ctx->device = dev;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->seed = cfg ? cfg->seed : 0;
-  if (cfg && cfg->pair_batch > 0) ctx->pair_batch = std::min(cfg->pair_batch, 65535);
+  if (cfg && cfg->pair_batch > 0) {
+    ctx->pair_batch = std::min(cfg->pair_batch, 65535);
+    ctx->pair_batch_auto = false;
+  }
   ctx->stats.struct_size = sizeof(b2m_stats);
 #define CU_TRY_C(expr)                                                            \
   do {                                                                            \

@@ -46,7 +46,8 @@ typedef struct b2m_device_cfg {
   uint32_t struct_size;
   int32_t device;        /* CUDA ordinal; replaces SiftMatchingOptions.gpu_index (R:pipeline/match_features.h:76-81) */
   uint64_t seed;         /* RANSAC seed; replaces SetPRNGSeed(0) (R:estimators/essential_matrix.h:25) */
-  int32_t pair_batch;    /* image pairs per kernel batch, 0 = default */
+  int32_t pair_batch;    /* image pairs per kernel batch; 0 = default: 4096 for 8192-feature images, proportionally more for
+                          * smaller ones (1024 .. 16384).  Results do not depend on it (RANSAC is keyed by image ids). */
   int32_t reserved;
 } b2m_device_cfg;
 

@@ -86,13 +86,31 @@ Mat3 Transposed(const Mat3& m) { return Mat3{m[0], m[3], m[6], m[1], m[4], m[7],
 
 // ---- RAII prepared statement ---------------------------------------------------------------------
 struct Database::Stmt {
-  Stmt(Database* d, const char* sql) : db(d) {
+  // cached: `sql` is a string literal (its address is the key); the statement is reset, not finalized, when this
+  // handle goes out of scope, and lives until Close().  One handle per SQL text at a time (leaf functions only).
+  Stmt(Database* d, const char* sql, bool cached = false) : db(d), cached_(cached) {
     if (!d->db_) throw std::runtime_error("[database.cc] Check Failed: database is open");
+    if (cached) {
+      auto it = d->stmt_cache_.find(sql);
+      if (it != d->stmt_cache_.end()) {
+        st = it->second;
+        return;
+      }
+    }
     if (sq::api().prepare_v2(d->db_, sql, -1, &st, nullptr) != sq::kOk) d->Fail(sql);
+    if (cached) d->stmt_cache_[sql] = st;
   }
   ~Stmt() {
-    if (st) sq::api().finalize(st);
+    if (!st) return;
+    if (cached_) {
+      sq::api().reset(st);
+      sq::api().clear_bindings(st);
+    } else {
+      sq::api().finalize(st);
+    }
   }
+  Stmt(const Stmt&) = delete;
+  Stmt& operator=(const Stmt&) = delete;
   void I64(int i, int64_t v) { Check(sq::api().bind_int64(st, i, v)); }
   void F64(int i, double v) { Check(sq::api().bind_double(st, i, v)); }
   void Null(int i) { Check(sq::api().bind_null(st, i)); }
@@ -130,6 +148,7 @@ struct Database::Stmt {
   }
   Database* db;
   sq::sqlite3_stmt* st = nullptr;
+  bool cached_ = false;
 };
 
 void Database::Fail(const char* what) {
@@ -156,6 +175,8 @@ void Database::Open(const std::string& path) {
 }
 
 void Database::Close() {
+  for (auto& kv : stmt_cache_) sq::api().finalize(kv.second);
+  stmt_cache_.clear();
   if (db_) sq::api().close(db_);
   db_ = nullptr;
 }
@@ -323,13 +344,13 @@ DescriptorsBlob Database::ReadDescriptors(int64_t image_id) {
 }
 
 bool Database::ExistsMatches(int64_t id1, int64_t id2) {
-  Stmt s(this, "SELECT 1 FROM matches WHERE pair_id = ?");
+  Stmt s(this, "SELECT 1 FROM matches WHERE pair_id = ?", /*cached=*/true);
   s.I64(1, ImagePairToPairId(id1, id2));
   return s.Step();
 }
 
 bool Database::ExistsInlierMatches(int64_t id1, int64_t id2) {
-  Stmt s(this, "SELECT 1 FROM two_view_geometries WHERE pair_id = ?");
+  Stmt s(this, "SELECT 1 FROM two_view_geometries WHERE pair_id = ?", /*cached=*/true);
   s.I64(1, ImagePairToPairId(id1, id2));
   return s.Step();
 }
@@ -350,7 +371,7 @@ void SwapColumns(std::vector<uint32_t>* m) {
 }  // namespace
 
 std::vector<uint32_t> Database::ReadMatches(int64_t id1, int64_t id2) {
-  Stmt s(this, "SELECT rows, cols, data FROM matches WHERE pair_id = ?");
+  Stmt s(this, "SELECT rows, cols, data FROM matches WHERE pair_id = ?", /*cached=*/true);
   s.I64(1, ImagePairToPairId(id1, id2));
   if (!s.Step() || s.ColI64(0) == 0) return {};
   std::vector<uint32_t> m = s.ColBlob<uint32_t>(2);
@@ -360,7 +381,7 @@ std::vector<uint32_t> Database::ReadMatches(int64_t id1, int64_t id2) {
 }
 
 bool Database::ReadTwoViewGeometry(int64_t id1, int64_t id2, TwoViewGeometryRow* out) {
-  Stmt s(this, "SELECT rows, cols, data, config, F, E, H, qvec, tvec FROM two_view_geometries WHERE pair_id = ?");
+  Stmt s(this, "SELECT rows, cols, data, config, F, E, H, qvec, tvec FROM two_view_geometries WHERE pair_id = ?", /*cached=*/true);
   s.I64(1, ImagePairToPairId(id1, id2));
   if (!s.Step()) return false;
   TwoViewGeometryRow g;
@@ -399,7 +420,7 @@ void Database::WriteMatches(int64_t id1, int64_t id2, const uint32_t* matches, i
     SwapColumns(&swapped);
     matches = swapped.data();
   }
-  Stmt s(this, "INSERT OR REPLACE INTO matches VALUES (?, ?, 2, ?)");
+  Stmt s(this, "INSERT OR REPLACE INTO matches VALUES (?, ?, 2, ?)", /*cached=*/true);
   s.I64(1, ImagePairToPairId(id1, id2)); s.I64(2, n);
   s.Blob(3, matches, static_cast<size_t>(n) * 8);
   s.Step();
@@ -426,7 +447,7 @@ void Database::WriteTwoViewGeometry(int64_t id1, int64_t id2, int config, const 
   }
   const double* qvec = q.data();
   const double* tvec = t.data();
-  Stmt s(this, "INSERT OR REPLACE INTO two_view_geometries VALUES (?, ?, 2, ?, ?, ?, ?, ?, ?, ?)");
+  Stmt s(this, "INSERT OR REPLACE INTO two_view_geometries VALUES (?, ?, 2, ?, ?, ?, ?, ?, ?, ?)", /*cached=*/true);
   s.I64(1, ImagePairToPairId(id1, id2)); s.I64(2, n);
   s.Blob(3, inlier_matches, static_cast<size_t>(n) * 8);
   s.I64(4, config);

@@ -9,6 +9,7 @@
 #include <array>
 #include <cstdint>
 #include <string>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -130,6 +131,9 @@ class Database {
   int64_t Scalar(const char* sql);
   [[noreturn]] void Fail(const char* what);
   sq::sqlite3* db_ = nullptr;
+  // prepared statements of the per-pair calls (exists / read / write of matches and two-view geometries), keyed by the
+  // address of their SQL literal and reused across calls: an exhaustive run issues hundreds of thousands of them
+  std::unordered_map<const void*, sq::sqlite3_stmt*> stmt_cache_;
 };
 
 // DatabaseTransaction: BEGIN in the constructor, COMMIT in the destructor (ROLLBACK when unwinding).
